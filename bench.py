@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""Headline benchmark: point-vs-center feature evaluations per second (BASELINE.json metric) on the
+C2 workload (100 k synthetic 1.5 kb 16S-like sequences, --id 0.97 --kmer 4), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one Trainer::get_close-shaped pass (1 center x all n points: every live feature + the
+GLM decision + argmax/mark reduction) for each of S centers, i.e. S launches of the scan kernel.
+  value  : evals/s with the histograms resident in HBM.  The batch is stored R times (R*29 MB >
+           2x the 126 MB L2) and consecutive launches rotate through the replicas, so every launch
+           streams its rows from HBM ("inputs larger than L2").
+  e2e    : the same S-center pass through the host-buffer C-ABI call mc_scan_host(): pinned host
+           histograms -> HBM, S scans, marks + summaries back to the host, all inside the timed
+           region.
+  roofline: the scan kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json);
+           algorithmic bytes per eval = 4^k + 33.
+  cpu_baseline: the compiled unmodified reference (oracle/_ref/libmcref.so, Feature::compute +
+           GLM exactly as Trainer::get_close runs them, OpenMP over points like the reference) on a
+           bounded sample of the same workload, all host threads.
+--impl reference prints the reference CPU arm alone in the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "feature_evals_per_sec"
+UNIT = "evals/s"
+WORKLOAD = "c2"
+K = 4
+S_CENTERS = 10            # scans per step
+FALLBACK_HBM_GBS = 6650.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_workload(seed_shift: int = 0):
+    from meshclust_b200 import synth
+    c = synth.CONFIGS[WORKLOAD]
+    t0 = time.time()
+    letters, offs, tmpl = synth.generate(c.n, c.templates, c.length, c.mu, c.seed + 1000 * seed_shift, c.related)
+    log(f"[bench] generated {WORKLOAD}: n={c.n} bases={offs[-1]} in {time.time() - t0:.1f}s")
+    return c, letters, offs, tmpl
+
+
+def fit_model(ctx, n, tmpl, rng):
+    """Bounds from sampled pairs + least-squares GLM on template labels (a stand-in for
+    Trainer::train, whose alignment-labelled sampling is host control, not the measured path)."""
+    m = 3000
+    a = rng.integers(0, n, m).astype(np.int32)
+    ntem = int(tmpl.max()) + 1
+    b = np.where(rng.random(m) < 0.5, (a + ntem * rng.integers(1, 50, m)) % n, rng.integers(0, n, m)).astype(np.int32)
+    raw, _ = ctx.pair_features(a, b)
+    mins, maxs = raw.min(0), np.maximum(raw.max(0), np.finfo(float).tiny)
+    ctx.set_model(mins, maxs, np.array([0.0, 1.0, 1.0, 1.0, 1.0]), 4)
+    _, _, _, feats = ctx.pair_classify(a, b)
+    X = np.concatenate([np.ones((m, 1)), feats], 1)
+    y = np.where(tmpl[a] == tmpl[b], 1.0, -1.0)
+    w = np.linalg.lstsq(X, y, rcond=None)[0]
+    acc = float((np.sign(X @ w) == y).mean())
+    return mins, maxs, w, acc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU arm (also the cpu_baseline of our arm)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(hist, lens, mins, maxs, w, centers, target_s: float, steps: int | None = None, warmup: int = 0):
+    """evals/s of the compiled reference's get_close (Feature::compute + GLM + argmax/mark reduction,
+    OpenMP over points) on a bounded sample; the points exist as DivergencePoint objects beforehand,
+    like in the reference.  Returns (value, cores, kind, sample description, ms_per_step)."""
+    import _oracle
+    n = hist.shape[0]
+    ns = min(n, 20000)
+    sub, sublen = np.ascontiguousarray(hist[:ns]), np.ascontiguousarray(lens[:ns])
+    centers = [int(c) % ns for c in centers]
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)   # the reference prints "Adding combo ..." on every Feature set-up
+    try:
+        if _oracle.have_ref():
+            lib, kind = _oracle.ref(), "reference"
+            cores = int(lib.lib.ref_max_threads())
+            ps = lib.pointset(sub, sublen)
+            lib.pointset_set_model(ps, mins, maxs, 4)
+            flags = np.zeros(ns, np.uint8)
+            one_pass = lambda c: lib.pointset_scan(ps, c, w, flags)
+        else:   # the reference could not be compiled where this snapshot was built: oracle port
+            lib, kind = _oracle.oracle(), "port"
+            cores = os.cpu_count() or 1
+            ps = None
+            one_pass = lambda c: lib.scan(sub, sublen, sub[c], int(sublen[c]), mins, maxs, w, 4)
+        one_pass(centers[0])
+        t0 = time.perf_counter()
+        one_pass(centers[0])
+        one = time.perf_counter() - t0
+        if steps is None:
+            calls = max(2, int(target_s / max(one, 1e-4)))
+            t0 = time.perf_counter()
+            for i in range(calls):
+                one_pass(centers[i % len(centers)])
+            el = time.perf_counter() - t0
+            value = calls * ns / el
+            ms_step = el / calls * 1e3
+            sample = f"{calls} get_close passes over the first {ns} points of {WORKLOAD} ({el:.1f} s)"
+        else:
+            per_step = max(1, min(S_CENTERS, int(target_s / max(one, 1e-4) / max(steps, 1))))
+            for i in range(warmup):
+                one_pass(centers[0])
+            t0 = time.perf_counter()
+            for s in range(steps):
+                for j in range(per_step):
+                    one_pass(centers[(s * per_step + j) % len(centers)])
+            el = time.perf_counter() - t0
+            value = steps * per_step * ns / el
+            ms_step = el / steps * 1e3
+            sample = f"each step = {per_step} get_close passes over the first {ns} points of {WORKLOAD}"
+        if ps is not None:
+            lib.pointset_destroy(ps)
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+    return value, cores, kind, sample, ms_step
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4-shape roofline probe")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from meshclust_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: meshclust_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg, letters, offs, tmpl = make_workload(seed_shift=rank)
+    n = cfg.n
+    nbins = 4 ** K
+    rng = np.random.default_rng(7 + rank)
+    ctx = api.Context(local_rank)
+
+    # ---- stage 1 once (also reported): letters -> histograms on the GPU
+    t0 = time.perf_counter()
+    hist, mx = ctx.kmer_histograms_host(letters, offs, K, 1)
+    t_hist = time.perf_counter() - t0
+    lens = np.diff(offs).astype(np.uint64)
+    assert mx <= 255
+    mins, maxs, w, acc = fit_model(ctx, n, tmpl, rng)
+    log(f"[bench] rank {rank}: histograms {t_hist * 1e3:.0f} ms (host->host), model acc {acc:.3f}")
+
+    # ---- resident data: R replicas so that consecutive launches never re-read L2-resident rows
+    row_bytes = nbins + 24
+    R = int(np.ceil(2.2 * 126e6 / (n * row_bytes)))
+    big = np.ascontiguousarray(np.tile(hist, (R, 1)))
+    biglens = np.tile(lens, R)
+    ctx.load_histograms(big, biglens, K)
+    ctx.set_model(mins, maxs, w, 4)
+    del big
+    S = S_CENTERS
+    centers_local = rng.integers(0, n, 64)
+
+    def step_args(step):
+        reps = [(step * S + s) % R for s in range(S)]
+        cr = np.array([r * n + centers_local[(step * S + s) % 64] for s, r in enumerate(reps)], np.int64)
+        lo = np.array([r * n for r in reps], np.int64)
+        hi = lo + n - 1
+        return cr, lo, hi
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    def exchange(results):
+        """the real exchange of a sharded get_close: positives summed, (f0, row) arg-maxed"""
+        if world == 1:
+            return
+        t = torch.tensor([[r[1], r[0]] for r in results], dtype=torch.int64, device="cuda")
+        f0 = torch.tensor([r[3] for r in results], dtype=torch.float64, device="cuda")
+        rows = torch.tensor([r[2] + rank * n if r[2] >= 0 else 2 ** 62 for r in results], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        fmax = f0.clone()
+        dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+        rows = torch.where(f0 == fmax, rows, torch.full_like(rows, 2 ** 62))
+        dist.all_reduce(rows, op=dist.ReduceOp.MIN)
+        torch.cuda.current_stream().synchronize()
+
+    def run_step(step):
+        cr, lo, hi = step_args(step)
+        ctx.scan_enqueue_many(cr, lo, hi, False, 0)
+        if world > 1:
+            exchange(ctx.scan_collect(0, S))
+
+    for i in range(args.warmup):
+        run_step(i)
+    ctx.sync()
+    launches0 = ctx.launches
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    for i in range(args.steps):
+        run_step(args.warmup + i)
+    ev1.record(stream)
+    ctx.sync()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    gpu_launches = ctx.launches - launches0
+    results = ctx.scan_collect(0, S)
+    assert all(r[0] == n for r in results), "scan did not evaluate every point"
+
+    # device time when there is no exchange; wall (barrier+sync bracketed) when there is one
+    total_ms = dev_ms if world == 1 else t_wall * 1e3
+    if world > 1:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    evals_per_step = S * n * world
+    value = evals_per_step / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (scan): per-launch time from the CUDA events
+    peak, peak_src = measured_peak()
+    bytes_per_launch = n * (nbins + 33)
+    launch_us = dev_ms * 1e3 / (args.steps * S)
+    achieved = bytes_per_launch / (launch_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "kernel": f"scan_kernel<1,{nbins}>", "launch_us": round(launch_us, 3),
+                "algorithmic_bytes_per_launch": bytes_per_launch}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8", "data": "synthetic",
+           "config": {"workload": f"{WORKLOAD}: 100k synthetic 1.5 kb 16S-like sequences, --id 0.97 --kmer 4",
+                      "points_per_gpu": n, "bins": nbins, "centers_per_step": S, "evals_per_step": evals_per_step,
+                      "l2": f"inputs larger than L2: {R} replicas of the batch ({R * n * row_bytes / 1e6:.0f} MB), launches rotate through them",
+                      "model": "4 features, bounds from 3000 sampled pairs, least-squares GLM", "parallelism": f"points sharded x{world}"},
+           "clocks": clocks, "gpu_launches": int(gpu_launches), "roofline": roofline}
+
+    if rank == 0:
+        # ---- e2e through the host-buffer C-ABI call: pinned host histograms in, marks + summaries out
+        hp = torch.empty((n, nbins), dtype=torch.uint8, pin_memory=True)
+        hp.numpy()[:] = hist
+        lp = torch.empty(n, dtype=torch.int64, pin_memory=True)
+        lp.numpy()[:] = lens.astype(np.int64)
+        marks = torch.empty((S, n), dtype=torch.uint8, pin_memory=True)
+        ctx2 = api.Context(local_rank)
+        ctx2.set_model(mins, maxs, w, 4)
+        cr = centers_local[:S].astype(np.int64)
+        hnp, lnp, mnp = hp.numpy(), lp.numpy().view(np.uint64), marks.numpy()
+        for _ in range(3):
+            ctx2.scan_host(hnp, lnp, K, cr, mnp)
+        reps = max(5, min(args.steps, 30))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res = ctx2.scan_host(hnp, lnp, K, cr, mnp)
+        e2e_s = (time.perf_counter() - t0) / reps
+        out["e2e"] = {"value": S * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * nbins + n * 8 + S * 8),
+                      "d2h_bytes_per_step": int(S * n + S * 32), "ms_per_step": e2e_s * 1e3,
+                      "call": "mc_scan_host (pinned host histograms -> S scans -> marks + summaries on the host)"}
+        # parity spot-check of what was just timed (oracle as the checker only)
+        import _oracle
+        s_o, f0_o, fl_o = _oracle.oracle().scan(hist[:4000], lens[:4000], hist[cr[0]], int(lens[cr[0]]), mins, maxs, w, 4)
+        near = np.abs(s_o) < 1e-9
+        assert np.array_equal(mnp[0, :4000][~near], fl_o[~near]), "bench: scan marks differ from the oracle"
+        ctx2.close()
+
+        # ---- CPU baseline beside it: compiled reference on a bounded sample, all host threads
+        v, cores, kind, sample, _ = cpu_reference_rate(hist, lens, mins, maxs, w, centers_local[:8], target_s=12.0)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+
+        # ---- extra: the same kernel on the C4 shape (1 M points x 1024 bins, 1 GB > L2), HBM-bound regime
+        if not args.no_extra and world == 1:
+            try:
+                out["extra"] = {"c4_shape_scan": c4_shape_probe(api, local_rank, torch, peak)}
+            except Exception as e:   # never lose the headline line to the probe
+                out["extra"] = {"c4_shape_scan_error": str(e)[:200]}
+        out["stage1_histograms_ms_host_to_host"] = t_hist * 1e3
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def c4_shape_probe(api, device, torch, peak):
+    n, k = 1_000_000, 5
+    nb = 4 ** k
+    rng = np.random.default_rng(1)
+    base = rng.integers(1, 6, (1000, nb), dtype=np.uint8)
+    hist = base[rng.integers(0, 1000, n)]
+    lens = np.full(n, 1000, np.uint64)
+    ctx = api.Context(device)
+    ctx.load_histograms(hist, lens, k)
+    ctx.set_model(np.array([0, 0.5, 0, -1, 100.0]), np.array([100, 1, 4000, 1, 4000.0]), np.array([-1.0, 2, 1, 0.5, 0.5]), 4)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", device))
+    cr = np.array([11, 500_000, 999_999, 123_456, 654_321, 42, 777_777, 31_337], np.int64)
+    lo = np.zeros(8, np.int64)
+    hi = np.full(8, n - 1, np.int64)
+    ctx.scan_enqueue_many(cr, lo, hi, False, 0)
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ctx.scan_enqueue_many(cr, lo, hi, False, 0)
+    e1.record(stream)
+    ctx.sync()
+    us = e0.elapsed_time(e1) * 1e3 / 8
+    by = n * (nb + 33)
+    ach = by / (us * 1e-6) / 1e9
+    ctx.close()
+    return {"points": n, "bins": nb, "launch_us": round(us, 2), "evals_per_s": n / (us * 1e-6), "achieved_GBs": round(ach, 1),
+            "frac_of_peak": round(ach / peak, 4), "note": "1.06 GB of rows per launch (> L2): every launch streams from HBM"}
+
+
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (compiled, unmodified; OpenMP over points)
+    on a bounded sample of the same workload."""
+    import _oracle
+    cfg, letters, offs, tmpl = make_workload()
+    n = cfg.n
+    ns = 20000
+    sub_offs = offs[: ns + 1]
+    sub_letters = letters[: sub_offs[-1]]
+    o = _oracle.oracle()   # histograms + model for the sample come from the CPU oracle: no GPU on this arm
+    rc, hist, mx = o.hist_batch(sub_letters, sub_offs, K, 1)
+    lens = np.diff(sub_offs).astype(np.uint64)
+    rng = np.random.default_rng(7)
+    m = 3000
+    a = rng.integers(0, ns, m)
+    ntem = int(tmpl.max()) + 1
+    b = np.where(rng.random(m) < 0.5, (a + ntem * rng.integers(1, 10, m)) % ns, rng.integers(0, ns, m))
+    raw = np.array([o.features(hist[i], hist[j], int(lens[i]), int(lens[j]))[0] for i, j in zip(a, b)])
+    mins, maxs = raw.min(0), np.maximum(raw.max(0), np.finfo(float).tiny)
+    c = (raw - mins) / (maxs - mins)
+    c[:, [0, 2, 3]] = 1 - c[:, [0, 2, 3]]
+    feats = np.stack([c[:, 0] * c[:, 1], (c[:, 0] * c[:, 2]) ** 2, c[:, 3], (c[:, 0] * c[:, 4]) ** 2], 1)
+    X = np.concatenate([np.ones((m, 1)), feats], 1)
+    y = np.where(tmpl[a] == tmpl[b], 1.0, -1.0)
+    w = np.linalg.lstsq(X, y, rcond=None)[0]
+    centers = rng.integers(0, ns, 64)
+    v, cores, kind, sample, ms_step = cpu_reference_rate(hist, lens, mins, maxs, w, centers, target_s=60.0,
+                                                        steps=args.steps, warmup=args.warmup)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8", "data": "synthetic",
+           "config": {"workload": f"{WORKLOAD}: 100k synthetic 1.5 kb 16S-like sequences, --id 0.97 --kmer 4 (bounded sample)",
+                      "bins": 4 ** K, "parallelism": f"OpenMP x{cores} host threads"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

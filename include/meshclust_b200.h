@@ -1,0 +1,190 @@
+/* meshclust_b200 -- C-ABI of the B200-native MeShClust hot path.
+ *
+ * The reference (BioinformaticsToolsmith/MeShClust, C++11 + OpenMP) has no plugin / FFI interface:
+ * its hot path is a set of C++ methods called from Runner / Trainer / ClusterFactory.  Each entry
+ * point below replaces one of those call seams (cited as reference file:line); INTEGRATION.md
+ * shows the binding a maintainer of the reference would add at each seam.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative MC_ERR_* code; mc_last_error() gives the text
+ *     (thread-local).  No exception ever crosses this boundary.
+ *   - all pointer arguments are HOST pointers unless the name ends in _dev.
+ *   - a "row" is a point (one sequence) in the order the caller loaded it; the caller owns the
+ *     mapping between rows and its own ids / headers.
+ *   - histograms, sequences, alive flags, marks and the model stay resident in HBM between calls.
+ *   - there is no CPU fallback: without a CUDA device every call except mc_last_error(),
+ *     mc_version() and mc_host_segments() fails with MC_ERR_CUDA.
+ */
+#ifndef MESHCLUST_B200_H
+#define MESHCLUST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_OK 0
+#define MC_ERR_CUDA (-1)        /* CUDA runtime error / no device */
+#define MC_ERR_ARG (-2)         /* bad argument */
+#define MC_ERR_STATE (-3)       /* call order (e.g. scan before histograms are built) */
+#define MC_ERR_INPUT (-4)       /* invalid nucleotide / sequence with no usable segment:
+                                   the reference throws InvalidInputException (ChromosomeOneDigit.cpp:102-106)
+                                   or std::out_of_range (Chromosome.cpp:193) */
+#define MC_ERR_UNSUPPORTED (-5) /* k-mer count needs more than 16 bits, k too large, ... */
+
+typedef struct mc_ctx mc_ctx;
+
+const char *mc_version(void);
+const char *mc_last_error(void);
+int mc_device_count(void);
+
+/* Replaces the OpenMP runtime set-up (Runner.cpp:201-214).  One context drives one GPU. */
+int mc_ctx_create(mc_ctx **out, int device);
+void mc_ctx_destroy(mc_ctx *ctx);
+/* the cudaStream_t every kernel of this context is launched on (for external event timing) */
+void *mc_stream(mc_ctx *ctx);
+int mc_sync(mc_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py "gpu_launches") */
+int64_t mc_launch_count(mc_ctx *ctx);
+
+/* ---- stage 0: sequences ------------------------------------------------------------------ */
+
+/* Host helper (pure C, no GPU): the non-N segment list of one raw sequence, exactly as
+ * Chromosome::removeN / mergeSegments / makeSegmentList produce it (Chromosome.cpp:162-258).
+ * Writes up to max_segs [start,end] pairs; returns the segment count, or -1 when the reference
+ * would throw (no non-N run at all). */
+int mc_host_segments(const uint8_t *letters, int64_t len, int32_t *segs, int max_segs);
+
+/* Upload n raw sequences (letters as read from FASTA, any case, IUPAC allowed; concatenated,
+ * offsets[n+1]) with their segment lists (seg_offsets[n+1] into segs[2*nseg]), and encode them
+ * on the GPU into the reference's digit strings (ChromosomeOneDigit.cpp:95-144).
+ * Replaces ChromosomeOneDigit::encodeNucleotides for every record of ChromListMaker's list. */
+int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int64_t *offsets, int64_t n,
+                      const int32_t *segs, const int64_t *seg_offsets);
+/* D2H copy of the encoded digit strings (same layout as the letters) -- tests / debugging */
+int mc_copy_digits(mc_ctx *ctx, uint8_t *out);
+
+/* ---- stage 1: k-mer histograms ----------------------------------------------------------- */
+
+/* Build the dense 4^k count vector (pseudo-count 1) of every loaded sequence.
+ * Replaces fill_table (ClusterFactory.h:40-55) -> KmerHashTable::wholesaleIncrement
+ * (KmerHashTable.cpp:133-223) as called from Runner::run's pre-scan (Runner.cpp:57-67) and
+ * ClusterFactory::get_divergence_point (ClusterFactory.cpp:989-1010).
+ * tbytes = 1 or 2 selects uint8 / uint16 bins; 0 = choose like Runner.cpp:75-89 (smallest width
+ * that holds the largest bin).  *tbytes_out / *max_count_out report what was used / found. */
+int mc_build_histograms(mc_ctx *ctx, int k, int tbytes, int *tbytes_out, uint64_t *max_count_out);
+
+/* Alternative to the two calls above: upload ready-made histograms (n x 4^k bins of tbytes) and
+ * sequence lengths.  Point constants (mag, sum p^2) are computed on the GPU. */
+int mc_load_histograms(mc_ctx *ctx, const void *hists, int tbytes, int k, const uint64_t *lens,
+                       int64_t n);
+
+int mc_copy_histograms(mc_ctx *ctx, void *out);
+/* any of the three may be NULL */
+int mc_copy_point_stats(mc_ctx *ctx, uint64_t *len, uint64_t *mag, uint64_t *sumsq);
+
+/* ---- stage 2: pair features + GLM -------------------------------------------------------- */
+
+/* Install the trained classifier: normalisation bounds in lookup order
+ * [LD, INTERSECTION, MANHATTAN, PEARSON, KULCZYNSKI2] (Feature.cpp:15-28,87-114), GLM weights
+ * w[0..nfeat] (Trainer.cpp:611-612), nfeat in {3,4} (Trainer.cpp:584-587,603-646).
+ * Replaces the Feature<T> bounds + Trainer::weights that get_close/filter/merge read. */
+int mc_set_model(mc_ctx *ctx, const double *mins, const double *maxs, const double *weights,
+                 int nfeat);
+
+/* DivergencePoint::distance (DivergencePoint.cpp:68-81) of every row against C center rows,
+ * as used by the sort comparators of Trainer::split (Trainer.cpp:681-684,698-701).
+ * keys_out[c*n + row], values in [0,10000]. */
+int mc_distance_keys(mc_ctx *ctx, const int32_t *center_rows, int C, uint16_t *keys_out);
+
+/* Raw features of m (a,b) row pairs: out5[m][5] = LD, INTERSECTION, MANHATTAN, PEARSON,
+ * KULCZYNSKI2 (Feature.cpp:207-340), dist_out[m] = distance().  Either output may be NULL.
+ * Replaces Feature::raw as driven by Feature::normalize (Feature.cpp:87-114). */
+int mc_pair_features(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m, double *out5,
+                     uint64_t *dist_out);
+
+/* Classify m (a,b) row pairs with the installed model: GLM sum, f0 (first combo = "dist") and
+ * flag = (round(1/(1+exp(-sum))) == 1).  Any output may be NULL.
+ * Replaces Trainer::filter / Trainer::merge / generate_feat_mat loop bodies
+ * (Trainer.cpp:334-349,129-157,367-414).  feats_out[m][4] (optional) gets the combo features. */
+int mc_pair_classify(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m, double *sum_out,
+                     double *f0_out, uint8_t *flag_out, double *feats_out);
+
+typedef struct mc_scan_result {
+	int64_t n_eval;   /* alive rows evaluated in [lo,hi] */
+	int64_t n_pos;    /* rows classified similar (marked and removed from the alive set) */
+	int64_t best_row; /* argmax of f0 over the evaluated rows, first maximum wins; -1 when no
+	                     row has f0 > -1 (Trainer.cpp:42-48,99) */
+	double best_f0;
+} mc_scan_result;
+
+/* Reset alive flags (all rows alive) and clear marks: a fresh bvec (Runner.cpp:342-350). */
+int mc_alive_reset(mc_ctx *ctx);
+/* Remove single rows from the alive set: bvec::pop / bvec::erase (bvec.cpp:27-38,281-285). */
+int mc_alive_kill(mc_ctx *ctx, const int64_t *rows, int64_t m);
+
+/* Trainer::get_close (Trainer.cpp:34-114) over the alive rows of the inclusive row range
+ * [lo,hi], followed by bvec::remove_available (bvec.cpp:290-317): every row classified similar
+ * to center_row is marked in marks_out[row-lo] (1 byte each, optional) and leaves the alive set. */
+int mc_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, mc_scan_result *res,
+            uint8_t *marks_out);
+
+/* Pipelined form of mc_scan for callers that keep several scans in flight (speculative seeds,
+ * multi-center sweeps): mc_scan_enqueue launches the scan on the context's stream without waiting
+ * and parks its summary in result slot `slot` (0 <= slot < MC_SCAN_SLOTS); remove_marked = 0
+ * leaves the alive set untouched (get_close without the following remove_available).
+ * mc_scan_collect waits for the stream and copies nslots summaries starting at slot0. */
+#define MC_SCAN_SLOTS 1024
+int mc_scan_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                    int slot);
+int mc_scan_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *res);
+/* count scans enqueued back to back: scan i uses center_rows[i], [lo[i],hi[i]] and slot slot0+i */
+int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo,
+                         const int64_t *hi, int count, int remove_marked, int slot0);
+
+/* ---- stage 3: mean-shift centers --------------------------------------------------------- */
+
+/* get_mean (ClusterFactory.cpp:382-425): the member whose histogram is nearest
+ * (DivergencePoint::distance_d, first minimum wins) to the mean of all members.
+ * append != 0 extends the member list given by the previous call(s) instead of replacing it
+ * (accumulate() grows `current`, ClusterFactory.cpp:689-692). */
+int mc_mean_nearest(mc_ctx *ctx, const int64_t *rows, int64_t m, int append, int64_t *nearest_row,
+                    double *nearest_dist);
+
+/* One Jacobi sweep of mean_shift_update (ClusterFactory.cpp:289-380) for ncenters centers:
+ * center c sees the candidate rows cand_rows[cand_begin[c] .. cand_end[c]) (members of clusters
+ * c-delta..c+delta in order), keeps those Trainer::filter (Trainer.cpp:334-349) classifies
+ * similar to center_rows[c], averages them and returns in next_rows[c] the survivor nearest to
+ * that mean (Trainer::closest, Trainer.cpp:351-365), or -1 when none survives. */
+int mc_update_centers(mc_ctx *ctx, const int64_t *center_rows, int64_t ncenters,
+                      const int64_t *cand_rows, int64_t ncand, const int64_t *cand_begin,
+                      const int64_t *cand_end, int64_t *next_rows);
+
+/* ---- stage 4: global alignment identity -------------------------------------------------- */
+
+/* GlobAlignE(seq_a, seq_b, match 1, mismatch -1, open 2, continue 1) for m row pairs
+ * (GlobAlignE.cpp:123-305 via Trainer::align, Trainer.cpp:15-31, and Feature::align,
+ * Feature.cpp:222-243).  a is the reference's seq1, b its seq2 (results depend on the order in
+ * corner cases).  identity = matches / alen is left to the caller (0/0 = NaN as in the reference). */
+int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m, int32_t *score,
+                   int32_t *alen, int32_t *matches);
+
+/* ---- host-buffer one-shot entry points (end-to-end measurement, simple embedding) -------- */
+
+/* letters -> histograms in one call: upload, encode, count, download.  hists_out: n x 4^k bins. */
+int mc_kmer_histograms_host(mc_ctx *ctx, const uint8_t *letters, const int64_t *offsets, int64_t n,
+                            int k, int tbytes, void *hists_out, uint64_t *max_count_out);
+
+/* get_close for ncenters centers over host histograms: uploads the n x 4^k histograms + lengths,
+ * evaluates every (center, row) pair with the installed model and returns, per center, the mark
+ * bytes (marks_out[c*n + row], optional) and the scan summary.  Rows are not removed between
+ * centers (each center sees all n rows). */
+int mc_scan_host(mc_ctx *ctx, const void *hists, int tbytes, int k, const uint64_t *lens, int64_t n,
+                 const int64_t *center_rows, int ncenters, mc_scan_result *res, uint8_t *marks_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESHCLUST_B200_H */

@@ -1,0 +1,286 @@
+"""ctypes mirror of include/meshclust_b200.h (same names, same argument meaning, same errors).
+
+Nothing here computes: every method forwards host numpy buffers to the C-ABI.  The library must
+have been built in-tree (``python -m meshclust_b200.build``); a missing library is an ImportError,
+never a silent fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmeshclust_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m meshclust_b200.build` "
+        "(meshclust_b200 has no CPU fallback)")
+
+_lib = C.CDLL(LIB_PATH)
+
+MC_OK = 0
+MC_ERR_CUDA, MC_ERR_ARG, MC_ERR_STATE, MC_ERR_INPUT, MC_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+
+# every symbol include/meshclust_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "mc_version", "mc_last_error", "mc_device_count", "mc_ctx_create", "mc_ctx_destroy", "mc_stream",
+    "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_copy_digits",
+    "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
+    "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
+    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_mean_nearest", "mc_update_centers", "mc_align_pairs",
+    "mc_kmer_histograms_host", "mc_scan_host",
+]
+
+
+class ScanResult(C.Structure):
+    _fields_ = [("n_eval", C.c_int64), ("n_pos", C.c_int64), ("best_row", C.c_int64), ("best_f0", C.c_double)]
+
+    def as_tuple(self):
+        return (self.n_eval, self.n_pos, self.best_row, self.best_f0)
+
+
+_lib.mc_version.restype = C.c_char_p
+_lib.mc_last_error.restype = C.c_char_p
+_lib.mc_stream.restype = C.c_void_p
+_lib.mc_stream.argtypes = [C.c_void_p]
+_lib.mc_launch_count.restype = C.c_int64
+_lib.mc_launch_count.argtypes = [C.c_void_p]
+_lib.mc_ctx_destroy.restype = None
+_lib.mc_ctx_destroy.argtypes = [C.c_void_p]
+
+
+class McError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"meshclust_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _check(rc: int):
+    if rc != MC_OK:
+        raise McError(rc, _lib.mc_last_error().decode(errors="replace"))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def version() -> str:
+    return _lib.mc_version().decode()
+
+
+def device_count() -> int:
+    return int(_lib.mc_device_count())
+
+
+def host_segments(letters: np.ndarray | bytes, max_segs: int = 1 << 16):
+    """Chromosome::removeN/mergeSegments/makeSegmentList on the host; None when the reference throws."""
+    a = np.frombuffer(letters, dtype=np.uint8) if isinstance(letters, (bytes, bytearray)) else np.ascontiguousarray(letters, np.uint8)
+    segs = np.zeros(2 * max_segs, np.int32)
+    ns = _lib.mc_host_segments(_p(a), C.c_int64(a.size), _p(segs), C.c_int(max_segs))
+    if ns < 0:
+        return None
+    return segs[: 2 * ns].reshape(-1, 2).copy()
+
+
+def segments_for_batch(letters: np.ndarray, offsets: np.ndarray):
+    segs, seg_off = [], np.zeros(offsets.size, np.int64)
+    for i in range(offsets.size - 1):
+        s = host_segments(letters[offsets[i]:offsets[i + 1]])
+        if s is None:
+            raise McError(MC_ERR_INPUT, f"sequence {i} has no non-N run")
+        segs.append(s)
+        seg_off[i + 1] = seg_off[i] + len(s)
+    segs = np.concatenate(segs).astype(np.int32) if segs else np.zeros((0, 2), np.int32)
+    return np.ascontiguousarray(segs.reshape(-1)), seg_off
+
+
+class Context:
+    """One GPU.  Mirrors ``mc_ctx`` (replaces the reference's OpenMP runtime set-up, Runner.cpp:201-214)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(_lib.mc_ctx_create(C.byref(self._h), C.c_int(device)))
+        self.n = 0
+        self.k = 0
+        self.tbytes = 0
+        self.total_bases = 0
+
+    def close(self):
+        if self._h:
+            _lib.mc_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- plumbing -------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return int(_lib.mc_stream(self._h) or 0)
+
+    def sync(self):
+        _check(_lib.mc_sync(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(_lib.mc_launch_count(self._h))
+
+    # -- stage 0/1 ------------------------------------------------------------------------
+    def load_sequences(self, letters: np.ndarray, offsets: np.ndarray, segs=None, seg_offsets=None):
+        letters = np.ascontiguousarray(letters, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        if segs is None:
+            segs, seg_offsets = segments_for_batch(letters, offsets)
+        segs = np.ascontiguousarray(segs, np.int32)
+        seg_offsets = np.ascontiguousarray(seg_offsets, np.int64)
+        self.n = offsets.size - 1
+        self.total_bases = int(offsets[-1])
+        _check(_lib.mc_load_sequences(self._h, _p(letters), _p(offsets), C.c_int64(self.n), _p(segs), _p(seg_offsets)))
+
+    def copy_digits(self) -> np.ndarray:
+        out = np.zeros(self.total_bases, np.uint8)
+        _check(_lib.mc_copy_digits(self._h, _p(out)))
+        return out
+
+    def build_histograms(self, k: int, tbytes: int = 0):
+        used, mx = C.c_int(0), C.c_uint64(0)
+        _check(_lib.mc_build_histograms(self._h, C.c_int(k), C.c_int(tbytes), C.byref(used), C.byref(mx)))
+        self.k, self.tbytes = k, used.value
+        return used.value, int(mx.value)
+
+    def load_histograms(self, hists: np.ndarray, lens: np.ndarray, k: int):
+        hists = np.ascontiguousarray(hists)
+        assert hists.dtype in (np.uint8, np.uint16) and hists.shape[1] == 4 ** k
+        lens = np.ascontiguousarray(lens, np.uint64)
+        self.n, self.k, self.tbytes = hists.shape[0], k, hists.dtype.itemsize
+        _check(_lib.mc_load_histograms(self._h, _p(hists), C.c_int(self.tbytes), C.c_int(k), _p(lens), C.c_int64(self.n)))
+
+    def copy_histograms(self) -> np.ndarray:
+        out = np.zeros((self.n, 4 ** self.k), np.uint8 if self.tbytes == 1 else np.uint16)
+        _check(_lib.mc_copy_histograms(self._h, _p(out)))
+        return out
+
+    def copy_point_stats(self):
+        ln, mg, sq = (np.zeros(self.n, np.uint64) for _ in range(3))
+        _check(_lib.mc_copy_point_stats(self._h, _p(ln), _p(mg), _p(sq)))
+        return ln, mg, sq
+
+    # -- stage 2 --------------------------------------------------------------------------
+    def set_model(self, mins, maxs, weights, nfeat: int):
+        mins = np.ascontiguousarray(mins, np.float64)
+        maxs = np.ascontiguousarray(maxs, np.float64)
+        weights = np.ascontiguousarray(weights, np.float64)
+        _check(_lib.mc_set_model(self._h, _p(mins), _p(maxs), _p(weights), C.c_int(nfeat)))
+
+    def distance_keys(self, center_rows) -> np.ndarray:
+        cr = np.ascontiguousarray(center_rows, np.int32)
+        out = np.zeros((cr.size, self.n), np.uint16)
+        _check(_lib.mc_distance_keys(self._h, _p(cr), C.c_int(cr.size), _p(out)))
+        return out
+
+    def pair_features(self, a, b):
+        a = np.ascontiguousarray(a, np.int32)
+        b = np.ascontiguousarray(b, np.int32)
+        raw = np.zeros((a.size, 5), np.float64)
+        dist = np.zeros(a.size, np.uint64)
+        _check(_lib.mc_pair_features(self._h, _p(a), _p(b), C.c_int64(a.size), _p(raw), _p(dist)))
+        return raw, dist
+
+    def pair_classify(self, a, b):
+        a = np.ascontiguousarray(a, np.int32)
+        b = np.ascontiguousarray(b, np.int32)
+        s = np.zeros(a.size, np.float64)
+        f0 = np.zeros(a.size, np.float64)
+        fl = np.zeros(a.size, np.uint8)
+        feats = np.zeros((a.size, 4), np.float64)
+        _check(_lib.mc_pair_classify(self._h, _p(a), _p(b), C.c_int64(a.size), _p(s), _p(f0), _p(fl), _p(feats)))
+        return s, f0, fl, feats
+
+    def alive_reset(self):
+        _check(_lib.mc_alive_reset(self._h))
+
+    def alive_kill(self, rows):
+        r = np.ascontiguousarray(rows, np.int64)
+        _check(_lib.mc_alive_kill(self._h, _p(r), C.c_int64(r.size)))
+
+    def scan(self, center_row: int, lo: int, hi: int, want_marks: bool = True):
+        res = ScanResult()
+        marks = np.zeros(max(hi - lo + 1, 0), np.uint8) if want_marks else None
+        _check(_lib.mc_scan(self._h, C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi), C.byref(res), _p(marks)))
+        return res, marks
+
+    def scan_enqueue(self, center_row: int, lo: int, hi: int, remove_marked: bool, slot: int):
+        _check(_lib.mc_scan_enqueue(self._h, C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi),
+                                    C.c_int(1 if remove_marked else 0), C.c_int(slot)))
+
+    def scan_enqueue_many(self, center_rows, lo, hi, remove_marked: bool, slot0: int = 0):
+        cr = np.ascontiguousarray(center_rows, np.int64)
+        lo = np.ascontiguousarray(lo, np.int64)
+        hi = np.ascontiguousarray(hi, np.int64)
+        _check(_lib.mc_scan_enqueue_many(self._h, _p(cr), _p(lo), _p(hi), C.c_int(cr.size),
+                                         C.c_int(1 if remove_marked else 0), C.c_int(slot0)))
+
+    def scan_collect(self, slot0: int, nslots: int):
+        res = (ScanResult * nslots)()
+        _check(_lib.mc_scan_collect(self._h, C.c_int(slot0), C.c_int(nslots), C.byref(res)))
+        return [r.as_tuple() for r in res]
+
+    # -- stage 3 --------------------------------------------------------------------------
+    def mean_nearest(self, rows, append: bool = False):
+        r = np.ascontiguousarray(rows, np.int64)
+        row, dist = C.c_int64(-1), C.c_double(0)
+        _check(_lib.mc_mean_nearest(self._h, _p(r), C.c_int64(r.size), C.c_int(1 if append else 0), C.byref(row), C.byref(dist)))
+        return int(row.value), float(dist.value)
+
+    def update_centers(self, center_rows, cand_rows, cand_begin, cand_end) -> np.ndarray:
+        cr = np.ascontiguousarray(center_rows, np.int64)
+        cand = np.ascontiguousarray(cand_rows, np.int64)
+        cb = np.ascontiguousarray(cand_begin, np.int64)
+        ce = np.ascontiguousarray(cand_end, np.int64)
+        out = np.zeros(cr.size, np.int64)
+        _check(_lib.mc_update_centers(self._h, _p(cr), C.c_int64(cr.size), _p(cand), C.c_int64(cand.size), _p(cb), _p(ce), _p(out)))
+        return out
+
+    # -- stage 4 --------------------------------------------------------------------------
+    def align_pairs(self, a, b):
+        a = np.ascontiguousarray(a, np.int32)
+        b = np.ascontiguousarray(b, np.int32)
+        sc = np.zeros(a.size, np.int32)
+        ln = np.zeros(a.size, np.int32)
+        mt = np.zeros(a.size, np.int32)
+        _check(_lib.mc_align_pairs(self._h, _p(a), _p(b), C.c_int64(a.size), _p(sc), _p(ln), _p(mt)))
+        return sc, ln, mt
+
+    # -- one-shot host-buffer calls -------------------------------------------------------
+    def kmer_histograms_host(self, letters: np.ndarray, offsets: np.ndarray, k: int, tbytes: int = 1, out: np.ndarray | None = None):
+        letters = np.ascontiguousarray(letters, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        n = offsets.size - 1
+        if out is None:
+            out = np.zeros((n, 4 ** k), np.uint8 if tbytes == 1 else np.uint16)
+        mx = C.c_uint64(0)
+        _check(_lib.mc_kmer_histograms_host(self._h, _p(letters), _p(offsets), C.c_int64(n), C.c_int(k), C.c_int(tbytes), _p(out), C.byref(mx)))
+        self.n, self.k, self.tbytes, self.total_bases = n, k, tbytes, int(offsets[-1])
+        return out, int(mx.value)
+
+    def scan_host(self, hists: np.ndarray, lens: np.ndarray, k: int, center_rows, marks_out: np.ndarray | None = None):
+        hists = np.ascontiguousarray(hists)
+        lens = np.ascontiguousarray(lens, np.uint64)
+        cr = np.ascontiguousarray(center_rows, np.int64)
+        res = (ScanResult * cr.size)()
+        self.n, self.k, self.tbytes = hists.shape[0], k, hists.dtype.itemsize
+        _check(_lib.mc_scan_host(self._h, _p(hists), C.c_int(self.tbytes), C.c_int(k), _p(lens), C.c_int64(self.n),
+                                 _p(cr), C.c_int(cr.size), C.byref(res), _p(marks_out)))
+        return [r.as_tuple() for r in res]

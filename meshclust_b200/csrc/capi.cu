@@ -1,0 +1,689 @@
+// The C-ABI of include/meshclust_b200.h: context, HBM residency, host<->device staging.
+// Kernels live in kmer_hist.cu / pair_kernels.cu / center_mean.cu / nw_identity.cu.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "mc_common.cuh"
+
+// kernel launchers (defined in the other translation units)
+int mc_upload_lut();
+int mc_launch_encode(mc_ctx *ctx);
+int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes);
+int mc_launch_point_stats(mc_ctx *ctx);
+int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, void *partials_dev, void *result_dev);
+int64_t mc_scan_max_blocks(mc_ctx *ctx);
+int mc_launch_dist_keys(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint16_t *keys_dev);
+int mc_launch_pair_list(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, double *raw5_dev, uint64_t *dist_dev, double *sum_dev, double *f0_dev, uint8_t *flag_dev, double *feats_dev);
+int mc_launch_mean_nearest(mc_ctx *ctx, const int64_t *new_rows_dev, int64_t m_new, unsigned long long *sum_dev, const int64_t *members_dev, int64_t m_all, uint8_t *tq_dev, unsigned long long *magc_dev, void *partials_dev, long long *out_row_dev, double *out_dist_dev);
+int mc_launch_update_centers(mc_ctx *ctx, const int64_t *center_rows_dev, int64_t ncenters, const int64_t *cand_rows_dev, const int64_t *cand_begin_dev, const int64_t *cand_end_dev, const int64_t *flag_off_dev, uint8_t *flags_dev, long long *next_rows_dev);
+int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len, int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b, int64_t scratch_stride, int64_t nwarps);
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void mc_set_error(const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char *mc_last_error(void) { return g_err; }
+extern "C" const char *mc_version(void) { return "meshclust_b200 0.1 (sm_100a)"; }
+
+extern "C" int mc_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int mc_ensure_scratch(mc_ctx *ctx, size_t bytes) {
+	if (bytes <= ctx->scratch_bytes) return MC_OK;
+	if (ctx->d_scratch) { MC_CUDA(cudaStreamSynchronize(ctx->stream)); MC_CUDA(cudaFree(ctx->d_scratch)); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0; }
+	bytes = align_up(bytes + bytes / 4, 1 << 20);
+	MC_CUDA(cudaMalloc(&ctx->d_scratch, bytes));
+	ctx->scratch_bytes = bytes;
+	return MC_OK;
+}
+
+int mc_ensure_pinned(mc_ctx *ctx, size_t bytes) {
+	if (bytes <= ctx->pinned_bytes) return MC_OK;
+	if (ctx->h_pinned) { MC_CUDA(cudaStreamSynchronize(ctx->stream)); MC_CUDA(cudaFreeHost(ctx->h_pinned)); ctx->h_pinned = nullptr; ctx->pinned_bytes = 0; }
+	bytes = align_up(bytes + bytes / 4, 1 << 16);
+	MC_CUDA(cudaMallocHost(&ctx->h_pinned, bytes));
+	ctx->pinned_bytes = bytes;
+	return MC_OK;
+}
+
+// bump allocator over the scratch buffer
+struct Carve {
+	uint8_t *base;
+	size_t off = 0;
+	explicit Carve(void *b) : base((uint8_t *)b) {}
+	template <class T>
+	T *take(size_t count) {
+		off = align_up(off, 256);
+		T *p = reinterpret_cast<T *>(base + off);
+		off += count * sizeof(T);
+		return p;
+	}
+	static size_t need(std::initializer_list<size_t> sizes) {
+		size_t t = 0;
+		for (size_t s : sizes) t = align_up(t, 256) + s;
+		return t + 256;
+	}
+};
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int mc_ctx_create(mc_ctx **out, int device) {
+	MC_REQUIRE(out != nullptr, MC_ERR_ARG, "mc_ctx_create: out is NULL");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		mc_set_error("no CUDA device available (%s); meshclust_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+		return MC_ERR_CUDA;
+	}
+	MC_REQUIRE(device >= 0 && device < ndev, MC_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+	MC_CUDA(cudaSetDevice(device));
+	mc_ctx *ctx = new mc_ctx();
+	ctx->device = device;
+	cudaDeviceProp prop;
+	MC_CUDA(cudaGetDeviceProperties(&prop, device));
+	ctx->num_sms = prop.multiProcessorCount;
+	MC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	MC_CUDA(cudaMalloc(&ctx->d_ticket, 16 * sizeof(unsigned int)));
+	MC_CUDA(cudaMemsetAsync(ctx->d_ticket, 0, 16 * sizeof(unsigned int), ctx->stream));
+	MC_CUDA(cudaMalloc(&ctx->d_flags, 16 * sizeof(unsigned int)));
+	MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 16 * sizeof(unsigned int), ctx->stream));
+	int rc = mc_upload_lut();
+	if (rc) { delete ctx; return rc; }
+	rc = mc_ensure_pinned(ctx, 1 << 20);
+	if (rc) { delete ctx; return rc; }
+	ctx->model.valid = 0;
+	*out = ctx;
+	return MC_OK;
+}
+
+static void free_seq(mc_ctx *ctx) {
+	cudaFree(ctx->d_seq); cudaFree(ctx->d_seq_off); cudaFree(ctx->d_segs); cudaFree(ctx->d_seg_off);
+	ctx->d_seq = nullptr; ctx->d_seq_off = nullptr; ctx->d_segs = nullptr; ctx->d_seg_off = nullptr;
+	ctx->have_seq = false;
+}
+
+static void free_hist(mc_ctx *ctx) {
+	cudaFree(ctx->d_hist); cudaFree(ctx->d_len); cudaFree(ctx->d_mag); cudaFree(ctx->d_sq);
+	cudaFree(ctx->d_alive); cudaFree(ctx->d_marks); cudaFree(ctx->d_members); cudaFree(ctx->d_sum);
+	ctx->d_hist = nullptr; ctx->d_len = ctx->d_mag = ctx->d_sq = nullptr;
+	ctx->d_alive = ctx->d_marks = nullptr; ctx->d_members = nullptr; ctx->d_sum = nullptr;
+	ctx->hist_capacity = 0; ctx->aux_capacity = 0; ctx->members_cap = 0; ctx->members_n = 0; ctx->sum_bins = 0;
+	ctx->have_hist = false;
+}
+
+extern "C" void mc_ctx_destroy(mc_ctx *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	free_seq(ctx);
+	free_hist(ctx);
+	cudaFree(ctx->d_scratch);
+	cudaFree(ctx->d_scan_slots);
+	cudaFree(ctx->d_scan_partials);
+	cudaFreeHost(ctx->h_pinned);
+	cudaFree(ctx->d_ticket);
+	cudaFree(ctx->d_flags);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" void *mc_stream(mc_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int64_t mc_launch_count(mc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int mc_sync(mc_ctx *ctx) {
+	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helper: segments (Chromosome.cpp:162-258)
+// ---------------------------------------------------------------------------------------------
+extern "C" int mc_host_segments(const uint8_t *s, int64_t len, int32_t *segs, int max_segs) {
+	// pass 1+2 fused: maximal non-N runs, merged when the gap start2 - end1 < 10, kept when >= 20 bp,
+	// then cut at 1 Mbp.  A run that starts on the very last character is never closed by the
+	// reference (removeN's else-if chain), so it is ignored here too.
+	int nseg = 0;
+	bool any_raw = false, have_cur = false;
+	int64_t cs = 0, ce = 0;
+	auto emit = [&](int64_t a, int64_t b) {
+		const int64_t l = b - a + 1;
+		if (l < 20) return;
+		if (l > 1000000) {
+			const int64_t frag = l / 1000000;
+			for (int64_t h = 0; h < frag; h++) {
+				const int64_t fs = a + h * 1000000, fe = (h == frag - 1) ? b : fs + 1000000 - 1;
+				if (nseg < max_segs) { segs[2 * nseg] = (int32_t)fs; segs[2 * nseg + 1] = (int32_t)fe; }
+				nseg++;
+			}
+		} else {
+			if (nseg < max_segs) { segs[2 * nseg] = (int32_t)a; segs[2 * nseg + 1] = (int32_t)b; }
+			nseg++;
+		}
+	};
+	auto raw = [&](int64_t a, int64_t b) {
+		any_raw = true;
+		if (!have_cur) { cs = a; ce = b; have_cur = true; }
+		else if (a - ce < 10) { ce = b; }
+		else { emit(cs, ce); cs = a; ce = b; }
+	};
+	int64_t start = -1;
+	for (int64_t i = 0; i < len; i++) {
+		const bool isn = (s[i] | 0x20) == 'n';
+		if (!isn && start == -1) start = i;
+		else if (isn && start != -1) { raw(start, i - 1); start = -1; }
+		else if (i == len - 1 && !isn && start != -1) { raw(start, i); start = -1; }
+	}
+	if (!any_raw) return -1;
+	emit(cs, ce);
+	return nseg;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 0: sequences
+// ---------------------------------------------------------------------------------------------
+extern "C" int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int64_t *offsets, int64_t n,
+                                 const int32_t *segs, const int64_t *seg_offsets) {
+	MC_REQUIRE(ctx && letters && offsets && seg_offsets && n > 0, MC_ERR_ARG, "mc_load_sequences: bad arguments");
+	MC_REQUIRE(n < (1LL << 31), MC_ERR_UNSUPPORTED, "more than 2^31 sequences");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	free_seq(ctx);
+	const int64_t total = offsets[n];
+	const int64_t nseg = seg_offsets[n];
+	MC_REQUIRE(total >= 0 && nseg >= 0 && (nseg == 0 || segs), MC_ERR_ARG, "mc_load_sequences: bad offsets");
+	ctx->n = n; ctx->total_bases = total; ctx->nseg = nseg;
+	MC_CUDA(cudaMalloc(&ctx->d_seq, (size_t)total + 64));
+	MC_CUDA(cudaMalloc(&ctx->d_seq_off, (size_t)(n + 1) * sizeof(int64_t)));
+	MC_CUDA(cudaMalloc(&ctx->d_seg_off, (size_t)(n + 1) * sizeof(int64_t)));
+	MC_CUDA(cudaMalloc(&ctx->d_segs, (size_t)std::max<int64_t>(nseg, 1) * 2 * sizeof(int32_t)));
+	MC_CUDA(cudaMemsetAsync(ctx->d_seq + total, 0, 64, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(ctx->d_seq, letters, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(ctx->d_seq_off, offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(ctx->d_seg_off, seg_offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+	if (nseg) MC_CUDA(cudaMemcpyAsync(ctx->d_segs, segs, (size_t)nseg * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(unsigned int), ctx->stream));
+	int rc = mc_launch_encode(ctx);
+	if (rc) return rc;
+	unsigned int flags[4];
+	MC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->have_seq = true;
+	MC_REQUIRE(flags[0] == 0, MC_ERR_INPUT, "Invalid nucleotide in input (the reference throws InvalidInputException)");
+	return MC_OK;
+}
+
+extern "C" int mc_copy_digits(mc_ctx *ctx, uint8_t *out) {
+	MC_REQUIRE(ctx && out, MC_ERR_ARG, "bad arguments");
+	MC_REQUIRE(ctx->have_seq, MC_ERR_STATE, "no sequences loaded");
+	MC_CUDA(cudaMemcpyAsync(out, ctx->d_seq, (size_t)ctx->total_bases, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 1: histograms
+// ---------------------------------------------------------------------------------------------
+static int alloc_hist(mc_ctx *ctx, int64_t n, int k, int tbytes) {
+	const int nbins = 1 << (2 * k);
+	const size_t bytes = (size_t)n * nbins * tbytes + 256;   // +tail: 16-byte loads never leave the buffer
+	if (bytes > ctx->hist_capacity) {
+		if (ctx->d_hist) MC_CUDA(cudaFree(ctx->d_hist));
+		ctx->d_hist = nullptr;
+		MC_CUDA(cudaMalloc(&ctx->d_hist, bytes));
+		ctx->hist_capacity = bytes;
+	}
+	if (n > ctx->aux_capacity) {
+		cudaFree(ctx->d_len); cudaFree(ctx->d_mag); cudaFree(ctx->d_sq); cudaFree(ctx->d_alive); cudaFree(ctx->d_marks);
+		MC_CUDA(cudaMalloc(&ctx->d_len, (size_t)n * 8));
+		MC_CUDA(cudaMalloc(&ctx->d_mag, (size_t)n * 8));
+		MC_CUDA(cudaMalloc(&ctx->d_sq, (size_t)n * 8));
+		MC_CUDA(cudaMalloc(&ctx->d_alive, (size_t)n + 64));
+		MC_CUDA(cudaMalloc(&ctx->d_marks, (size_t)n + 64));
+		ctx->aux_capacity = n;
+	}
+	if (nbins > ctx->sum_bins) {
+		cudaFree(ctx->d_sum);
+		// running sum (uint64 per bin) + truncated-mean row + its magnitude
+		MC_CUDA(cudaMalloc(&ctx->d_sum, (size_t)nbins * 8 + (size_t)nbins * 2 + 64));
+		ctx->sum_bins = nbins;
+	}
+	ctx->n = n; ctx->k = k; ctx->nbins = nbins; ctx->tbytes = tbytes;
+	MC_CUDA(cudaMemsetAsync(ctx->d_alive, 1, (size_t)n, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(ctx->d_marks, 0, (size_t)n, ctx->stream));
+	ctx->members_n = 0;
+	return MC_OK;
+}
+
+extern "C" int mc_build_histograms(mc_ctx *ctx, int k, int tbytes, int *tbytes_out, uint64_t *max_count_out) {
+	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
+	MC_REQUIRE(ctx->have_seq, MC_ERR_STATE, "mc_build_histograms: load sequences first");
+	MC_REQUIRE(k >= 1 && k <= 7, MC_ERR_UNSUPPORTED, "k=%d unsupported (1..7)", k);
+	MC_REQUIRE(tbytes == 0 || tbytes == 1 || tbytes == 2, MC_ERR_ARG, "tbytes must be 0, 1 or 2");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int use = tbytes ? tbytes : 1;
+	unsigned int flags[4] = {0, 0, 0, 0};
+	for (;;) {
+		int rc = alloc_hist(ctx, ctx->n, k, use);
+		if (rc) return rc;
+		MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(unsigned int), ctx->stream));
+		rc = mc_launch_kmer_hist(ctx, k, use);
+		if (rc) return rc;
+		MC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+		// Runner.cpp:75-89: the width is the smallest that holds the largest bin
+		const int needed = flags[1] <= 0xffu ? 1 : (flags[1] <= 0xffffu ? 2 : 4);
+		if (needed > 2) {
+			mc_set_error("largest k-mer count %u needs 32-bit histograms; only 8/16-bit are on the GPU path", flags[1]);
+			return MC_ERR_UNSUPPORTED;
+		}
+		if (tbytes == 0 && needed > use) { use = needed; continue; }
+		MC_REQUIRE(needed <= use, MC_ERR_UNSUPPORTED, "largest k-mer count %u does not fit %d-byte bins", flags[1], use);
+		break;
+	}
+	if (tbytes_out) *tbytes_out = use;
+	if (max_count_out) *max_count_out = flags[1];
+	ctx->have_hist = true;
+	return MC_OK;
+}
+
+extern "C" int mc_load_histograms(mc_ctx *ctx, const void *hists, int tbytes, int k, const uint64_t *lens, int64_t n) {
+	MC_REQUIRE(ctx && hists && lens && n > 0, MC_ERR_ARG, "mc_load_histograms: bad arguments");
+	MC_REQUIRE(k >= 1 && k <= 8, MC_ERR_UNSUPPORTED, "k=%d unsupported (1..8)", k);
+	MC_REQUIRE(tbytes == 1 || tbytes == 2, MC_ERR_ARG, "tbytes must be 1 or 2");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int rc = alloc_hist(ctx, n, k, tbytes);
+	if (rc) return rc;
+	const size_t bytes = (size_t)n * ctx->nbins * tbytes;
+	MC_CUDA(cudaMemcpyAsync(ctx->d_hist, hists, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(ctx->d_len, lens, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+	rc = mc_launch_point_stats(ctx);
+	if (rc) return rc;
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->have_hist = true;
+	return MC_OK;
+}
+
+extern "C" int mc_copy_histograms(mc_ctx *ctx, void *out) {
+	MC_REQUIRE(ctx && out, MC_ERR_ARG, "bad arguments");
+	MC_REQUIRE(ctx->have_hist, MC_ERR_STATE, "no histograms");
+	MC_CUDA(cudaMemcpyAsync(out, ctx->d_hist, (size_t)ctx->n * ctx->nbins * ctx->tbytes, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_copy_point_stats(mc_ctx *ctx, uint64_t *len, uint64_t *mag, uint64_t *sumsq) {
+	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
+	MC_REQUIRE(ctx->have_hist, MC_ERR_STATE, "no histograms");
+	const size_t b = (size_t)ctx->n * 8;
+	if (len) MC_CUDA(cudaMemcpyAsync(len, ctx->d_len, b, cudaMemcpyDeviceToHost, ctx->stream));
+	if (mag) MC_CUDA(cudaMemcpyAsync(mag, ctx->d_mag, b, cudaMemcpyDeviceToHost, ctx->stream));
+	if (sumsq) MC_CUDA(cudaMemcpyAsync(sumsq, ctx->d_sq, b, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 2
+// ---------------------------------------------------------------------------------------------
+extern "C" int mc_set_model(mc_ctx *ctx, const double *mins, const double *maxs, const double *weights, int nfeat) {
+	MC_REQUIRE(ctx && mins && maxs && weights, MC_ERR_ARG, "mc_set_model: bad arguments");
+	MC_REQUIRE(nfeat == 3 || nfeat == 4, MC_ERR_ARG, "nfeat must be 3 or 4 (Trainer.cpp:603-646)");
+	const int nlookup = nfeat >= 4 ? 5 : 4;
+	for (int i = 0; i < 5; i++) {
+		ctx->model.mins[i] = i < nlookup ? mins[i] : 0.0;
+		ctx->model.maxs[i] = i < nlookup ? maxs[i] : 1.0;
+	}
+	for (int i = 0; i < 5; i++) ctx->model.w[i] = i <= nfeat ? weights[i] : 0.0;
+	ctx->model.nfeat = nfeat;
+	ctx->model.valid = 1;
+	return MC_OK;
+}
+
+#define MC_NEED_HIST(ctx) MC_REQUIRE((ctx) && (ctx)->have_hist, MC_ERR_STATE, "%s: histograms are not built", __func__)
+#define MC_NEED_MODEL(ctx) MC_REQUIRE((ctx)->model.valid, MC_ERR_STATE, "%s: mc_set_model has not been called", __func__)
+
+static int check_rows32(mc_ctx *ctx, const int32_t *r, int64_t m) {
+	for (int64_t i = 0; i < m; i++) MC_REQUIRE(r[i] >= 0 && r[i] < ctx->n, MC_ERR_ARG, "row %d out of range", (int)r[i]);
+	return MC_OK;
+}
+static int check_rows64(mc_ctx *ctx, const int64_t *r, int64_t m) {
+	for (int64_t i = 0; i < m; i++) MC_REQUIRE(r[i] >= 0 && r[i] < ctx->n, MC_ERR_ARG, "row %lld out of range", (long long)r[i]);
+	return MC_OK;
+}
+
+extern "C" int mc_distance_keys(mc_ctx *ctx, const int32_t *center_rows, int C, uint16_t *keys_out) {
+	MC_NEED_HIST(ctx);
+	MC_REQUIRE(center_rows && keys_out && C > 0, MC_ERR_ARG, "mc_distance_keys: bad arguments");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int rc = check_rows32(ctx, center_rows, C);
+	if (rc) return rc;
+	// chunks of centers so the key buffer stays modest
+	const int64_t n = ctx->n;
+	int cchunk = (int)std::max<int64_t>(1, std::min<int64_t>(C, (512LL << 20) / (n * 2)));
+	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)C * 4, (size_t)cchunk * n * 2}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	int32_t *d_c = cv.take<int32_t>(C);
+	uint16_t *d_k = cv.take<uint16_t>((size_t)cchunk * n);
+	MC_CUDA(cudaMemcpyAsync(d_c, center_rows, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->stream));
+	for (int c0 = 0; c0 < C; c0 += cchunk) {
+		const int cc = std::min(cchunk, C - c0);
+		rc = mc_launch_dist_keys(ctx, d_c + c0, cc, d_k);
+		if (rc) return rc;
+		MC_CUDA(cudaMemcpyAsync(keys_out + (size_t)c0 * n, d_k, (size_t)cc * n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	return MC_OK;
+}
+
+static int pair_list_common(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m, double *raw5, uint64_t *dist,
+                            double *sum, double *f0, uint8_t *flag, double *feats) {
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int rc = check_rows32(ctx, a, m);
+	if (rc) return rc;
+	rc = check_rows32(ctx, b, m);
+	if (rc) return rc;
+	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)m * 4, (size_t)m * 4, (size_t)m * 40, (size_t)m * 8, (size_t)m * 8, (size_t)m * 8, (size_t)m, (size_t)m * 32}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	int32_t *d_a = cv.take<int32_t>(m), *d_b = cv.take<int32_t>(m);
+	double *d_raw = raw5 ? cv.take<double>(m * 5) : nullptr;
+	uint64_t *d_dist = dist ? cv.take<uint64_t>(m) : nullptr;
+	double *d_sum = sum ? cv.take<double>(m) : nullptr;
+	double *d_f0 = f0 ? cv.take<double>(m) : nullptr;
+	uint8_t *d_flag = flag ? cv.take<uint8_t>(m) : nullptr;
+	double *d_feats = feats ? cv.take<double>(m * 4) : nullptr;
+	MC_CUDA(cudaMemcpyAsync(d_a, a, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(d_b, b, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+	rc = mc_launch_pair_list(ctx, d_a, d_b, m, d_raw, d_dist, d_sum, d_f0, d_flag, d_feats);
+	if (rc) return rc;
+	if (raw5) MC_CUDA(cudaMemcpyAsync(raw5, d_raw, (size_t)m * 40, cudaMemcpyDeviceToHost, ctx->stream));
+	if (dist) MC_CUDA(cudaMemcpyAsync(dist, d_dist, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if (sum) MC_CUDA(cudaMemcpyAsync(sum, d_sum, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if (f0) MC_CUDA(cudaMemcpyAsync(f0, d_f0, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	if (flag) MC_CUDA(cudaMemcpyAsync(flag, d_flag, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+	if (feats) MC_CUDA(cudaMemcpyAsync(feats, d_feats, (size_t)m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_pair_features(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m, double *out5, uint64_t *dist_out) {
+	MC_NEED_HIST(ctx);
+	MC_REQUIRE(a && b && m >= 0, MC_ERR_ARG, "mc_pair_features: bad arguments");
+	if (m == 0) return MC_OK;
+	return pair_list_common(ctx, a, b, m, out5, dist_out, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mc_pair_classify(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m, double *sum_out,
+                                double *f0_out, uint8_t *flag_out, double *feats_out) {
+	MC_NEED_HIST(ctx);
+	MC_NEED_MODEL(ctx);
+	MC_REQUIRE(a && b && m >= 0, MC_ERR_ARG, "mc_pair_classify: bad arguments");
+	if (m == 0) return MC_OK;
+	return pair_list_common(ctx, a, b, m, nullptr, nullptr, sum_out, f0_out, flag_out, feats_out);
+}
+
+extern "C" int mc_alive_reset(mc_ctx *ctx) {
+	MC_NEED_HIST(ctx);
+	MC_CUDA(cudaMemsetAsync(ctx->d_alive, 1, (size_t)ctx->n, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(ctx->d_marks, 0, (size_t)ctx->n, ctx->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_alive_kill(mc_ctx *ctx, const int64_t *rows, int64_t m) {
+	MC_NEED_HIST(ctx);
+	MC_REQUIRE(rows || m == 0, MC_ERR_ARG, "bad arguments");
+	int rc = check_rows64(ctx, rows, m);
+	if (rc) return rc;
+	for (int64_t i = 0; i < m; i++) MC_CUDA(cudaMemsetAsync(ctx->d_alive + rows[i], 0, 1, ctx->stream));
+	return MC_OK;
+}
+
+extern "C" int mc_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, mc_scan_result *res, uint8_t *marks_out) {
+	MC_NEED_HIST(ctx);
+	MC_NEED_MODEL(ctx);
+	MC_REQUIRE(res, MC_ERR_ARG, "mc_scan: res is NULL");
+	MC_REQUIRE(center_row >= 0 && center_row < ctx->n, MC_ERR_ARG, "center row out of range");
+	MC_REQUIRE(lo >= 0 && hi < ctx->n, MC_ERR_ARG, "scan range [%lld,%lld] out of range", (long long)lo, (long long)hi);
+	MC_CUDA(cudaSetDevice(ctx->device));
+	if (hi < lo) {   // empty bvec range (bvec_iterator.h:61-76 yields zero iterations)
+		res->n_eval = 0; res->n_pos = 0; res->best_row = -1; res->best_f0 = -1.0;
+		return MC_OK;
+	}
+	const size_t nblk = (size_t)mc_scan_max_blocks(ctx);
+	int rc = mc_ensure_scratch(ctx, Carve::need({nblk * 32, 64}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	void *d_part = cv.take<uint8_t>(nblk * 32);
+	void *d_res = cv.take<uint8_t>(64);
+	rc = mc_launch_scan(ctx, center_row, lo, hi, 1, d_part, d_res);
+	if (rc) return rc;
+	MC_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_res, sizeof(mc_scan_result), cudaMemcpyDeviceToHost, ctx->stream));
+	if (marks_out) MC_CUDA(cudaMemcpyAsync(marks_out, ctx->d_marks + lo, (size_t)(hi - lo + 1), cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	memcpy(res, ctx->h_pinned, sizeof(mc_scan_result));
+	return MC_OK;
+}
+
+extern "C" int mc_scan_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot) {
+	MC_NEED_HIST(ctx);
+	MC_NEED_MODEL(ctx);
+	MC_REQUIRE(slot >= 0 && slot < MC_SCAN_SLOTS, MC_ERR_ARG, "slot %d out of range", slot);
+	MC_REQUIRE(center_row >= 0 && center_row < ctx->n, MC_ERR_ARG, "center row out of range");
+	MC_REQUIRE(lo >= 0 && hi < ctx->n && lo <= hi, MC_ERR_ARG, "scan range [%lld,%lld] invalid", (long long)lo, (long long)hi);
+	if (!ctx->d_scan_slots) {
+		MC_CUDA(cudaSetDevice(ctx->device));
+		MC_CUDA(cudaMalloc(&ctx->d_scan_slots, (size_t)MC_SCAN_SLOTS * sizeof(mc_scan_result)));
+		MC_CUDA(cudaMalloc(&ctx->d_scan_partials, (size_t)mc_scan_max_blocks(ctx) * 32));
+	}
+	return mc_launch_scan(ctx, center_row, lo, hi, remove_marked, ctx->d_scan_partials,
+	                      (uint8_t *)ctx->d_scan_slots + (size_t)slot * sizeof(mc_scan_result));
+}
+
+extern "C" int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo, const int64_t *hi,
+                                    int count, int remove_marked, int slot0) {
+	MC_REQUIRE(center_rows && lo && hi && count > 0, MC_ERR_ARG, "mc_scan_enqueue_many: bad arguments");
+	for (int i = 0; i < count; i++) {
+		const int rc = mc_scan_enqueue(ctx, center_rows[i], lo[i], hi[i], remove_marked, slot0 + i);
+		if (rc) return rc;
+	}
+	return MC_OK;
+}
+
+extern "C" int mc_scan_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *res) {
+	MC_REQUIRE(ctx && res, MC_ERR_ARG, "bad arguments");
+	MC_REQUIRE(slot0 >= 0 && nslots > 0 && slot0 + nslots <= MC_SCAN_SLOTS, MC_ERR_ARG, "slot range invalid");
+	MC_REQUIRE(ctx->d_scan_slots, MC_ERR_STATE, "nothing was enqueued");
+	MC_CUDA(cudaMemcpyAsync(res, (uint8_t *)ctx->d_scan_slots + (size_t)slot0 * sizeof(mc_scan_result),
+	                        (size_t)nslots * sizeof(mc_scan_result), cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 3
+// ---------------------------------------------------------------------------------------------
+extern "C" int mc_mean_nearest(mc_ctx *ctx, const int64_t *rows, int64_t m, int append, int64_t *nearest_row, double *nearest_dist) {
+	MC_NEED_HIST(ctx);
+	MC_REQUIRE(rows && m > 0 && nearest_row, MC_ERR_ARG, "mc_mean_nearest: bad arguments");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int rc = check_rows64(ctx, rows, m);
+	if (rc) return rc;
+	if (!append) ctx->members_n = 0;
+	const int64_t total = ctx->members_n + m;
+	if (total > ctx->members_cap) {
+		const int64_t cap = std::max<int64_t>(total * 2, 1024);
+		int64_t *nm = nullptr;
+		MC_CUDA(cudaMalloc(&nm, (size_t)cap * 8));
+		if (ctx->members_n) MC_CUDA(cudaMemcpyAsync(nm, ctx->d_members, (size_t)ctx->members_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_members);
+		ctx->d_members = nm;
+		ctx->members_cap = cap;
+	}
+	unsigned long long *d_sum = reinterpret_cast<unsigned long long *>(ctx->d_sum);
+	uint8_t *d_tq = reinterpret_cast<uint8_t *>(ctx->d_sum) + (size_t)ctx->sum_bins * 8;
+	if (!append) MC_CUDA(cudaMemsetAsync(d_sum, 0, (size_t)ctx->nbins * 8, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(ctx->d_members + ctx->members_n, rows, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+	const size_t nblk = (size_t)ctx->num_sms * 4;
+	rc = mc_ensure_scratch(ctx, Carve::need({nblk * 16, 64}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	void *d_part = cv.take<uint8_t>(nblk * 16);
+	uint8_t *d_out = cv.take<uint8_t>(64);   // [0] magc, [8] row, [16] dist
+	rc = mc_launch_mean_nearest(ctx, ctx->d_members + ctx->members_n, m, d_sum, ctx->d_members, total, d_tq,
+	                            (unsigned long long *)d_out, d_part, (long long *)(d_out + 8), (double *)(d_out + 16));
+	if (rc) return rc;
+	ctx->members_n = total;
+	MC_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_out, 24, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	*nearest_row = *reinterpret_cast<int64_t *>((uint8_t *)ctx->h_pinned + 8);
+	if (nearest_dist) *nearest_dist = *reinterpret_cast<double *>((uint8_t *)ctx->h_pinned + 16);
+	return MC_OK;
+}
+
+extern "C" int mc_update_centers(mc_ctx *ctx, const int64_t *center_rows, int64_t ncenters, const int64_t *cand_rows,
+                                 int64_t ncand, const int64_t *cand_begin, const int64_t *cand_end, int64_t *next_rows) {
+	MC_NEED_HIST(ctx);
+	MC_NEED_MODEL(ctx);
+	MC_REQUIRE(center_rows && cand_rows && cand_begin && cand_end && next_rows && ncenters > 0, MC_ERR_ARG, "mc_update_centers: bad arguments");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int rc = check_rows64(ctx, center_rows, ncenters);
+	if (rc) return rc;
+	rc = check_rows64(ctx, cand_rows, ncand);
+	if (rc) return rc;
+	std::vector<int64_t> flag_off((size_t)ncenters + 1, 0);
+	for (int64_t c = 0; c < ncenters; c++) {
+		MC_REQUIRE(cand_begin[c] >= 0 && cand_end[c] >= cand_begin[c] && cand_end[c] <= ncand, MC_ERR_ARG, "candidate range of center %lld is invalid", (long long)c);
+		flag_off[c + 1] = flag_off[c] + (cand_end[c] - cand_begin[c]);
+	}
+	const size_t nflags = (size_t)flag_off[ncenters];
+	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)ncenters * 8, (size_t)ncand * 8, (size_t)ncenters * 8, (size_t)ncenters * 8, (size_t)(ncenters + 1) * 8, nflags + 16, (size_t)ncenters * 8}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	int64_t *d_cr = cv.take<int64_t>(ncenters), *d_cand = cv.take<int64_t>(std::max<int64_t>(ncand, 1));
+	int64_t *d_cb = cv.take<int64_t>(ncenters), *d_ce = cv.take<int64_t>(ncenters), *d_fo = cv.take<int64_t>(ncenters + 1);
+	uint8_t *d_fl = cv.take<uint8_t>(nflags + 16);
+	long long *d_next = cv.take<long long>(ncenters);
+	MC_CUDA(cudaMemcpyAsync(d_cr, center_rows, (size_t)ncenters * 8, cudaMemcpyHostToDevice, ctx->stream));
+	if (ncand) MC_CUDA(cudaMemcpyAsync(d_cand, cand_rows, (size_t)ncand * 8, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(d_cb, cand_begin, (size_t)ncenters * 8, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(d_ce, cand_end, (size_t)ncenters * 8, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(d_fo, flag_off.data(), (size_t)(ncenters + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	rc = mc_launch_update_centers(ctx, d_cr, ncenters, d_cand, d_cb, d_ce, d_fo, d_fl, d_next);
+	if (rc) return rc;
+	MC_CUDA(cudaMemcpyAsync(next_rows, d_next, (size_t)ncenters * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 4
+// ---------------------------------------------------------------------------------------------
+extern "C" int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m, int32_t *score, int32_t *alen, int32_t *matches) {
+	MC_REQUIRE(ctx && ctx->have_seq, MC_ERR_STATE, "mc_align_pairs: load sequences first");
+	MC_REQUIRE(a && b && score && alen && matches && m >= 0, MC_ERR_ARG, "mc_align_pairs: bad arguments");
+	if (m == 0) return MC_OK;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int rc = check_rows32(ctx, a, m);
+	if (rc) return rc;
+	rc = check_rows32(ctx, b, m);
+	if (rc) return rc;
+	// longest seq1 among the pairs decides the scratch line
+	std::vector<int64_t> off((size_t)ctx->n + 1);
+	MC_CUDA(cudaMemcpyAsync(off.data(), ctx->d_seq_off, (size_t)(ctx->n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	int64_t max_la = 0;
+	for (int64_t i = 0; i < m; i++) max_la = std::max(max_la, off[a[i] + 1] - off[a[i]]);
+	const int64_t stride = align_up((size_t)max_la + 2, 32);
+	int64_t nwarps = std::min<int64_t>(m, (int64_t)ctx->num_sms * 32);
+	// keep the scratch under ~4 GB
+	while (nwarps > ctx->num_sms && nwarps * 2 * stride * 24 > (4LL << 30)) nwarps /= 2;
+	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)nwarps * 2 * stride * 16, (size_t)nwarps * 2 * stride * 8}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	int32_t *d_a = cv.take<int32_t>(m), *d_b = cv.take<int32_t>(m), *d_s = cv.take<int32_t>(m), *d_l = cv.take<int32_t>(m), *d_i = cv.take<int32_t>(m);
+	void *d_sa = cv.take<uint8_t>((size_t)nwarps * 2 * stride * 16);
+	void *d_sb = cv.take<uint8_t>((size_t)nwarps * 2 * stride * 8);
+	MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(unsigned int), ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(d_a, a, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(d_b, b, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+	rc = mc_launch_nw(ctx, d_a, d_b, m, max_la, d_s, d_l, d_i, d_sa, d_sb, stride, nwarps);
+	if (rc) return rc;
+	unsigned int flags[4];
+	MC_CUDA(cudaMemcpyAsync(score, d_s, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(alen, d_l, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(matches, d_i, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	MC_REQUIRE(flags[2] == 0, MC_ERR_UNSUPPORTED, "a pair is longer than 65535 bases in total; not supported on the GPU path");
+	return MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one-shot host-buffer entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int mc_kmer_histograms_host(mc_ctx *ctx, const uint8_t *letters, const int64_t *offsets, int64_t n, int k,
+                                       int tbytes, void *hists_out, uint64_t *max_count_out) {
+	MC_REQUIRE(ctx && letters && offsets && hists_out && n > 0, MC_ERR_ARG, "mc_kmer_histograms_host: bad arguments");
+	std::vector<int32_t> segs;
+	std::vector<int64_t> seg_off((size_t)n + 1, 0);
+	int32_t buf[2 * 64];
+	for (int64_t i = 0; i < n; i++) {
+		const int64_t len = offsets[i + 1] - offsets[i];
+		int ns = mc_host_segments(letters + offsets[i], len, buf, 64);
+		MC_REQUIRE(ns >= 0, MC_ERR_INPUT, "sequence %lld has no non-N run (the reference throws at Chromosome.cpp:193)", (long long)i);
+		if (ns > 64) {
+			std::vector<int32_t> big((size_t)ns * 2);
+			mc_host_segments(letters + offsets[i], len, big.data(), ns);
+			segs.insert(segs.end(), big.begin(), big.end());
+		} else {
+			segs.insert(segs.end(), buf, buf + 2 * ns);
+		}
+		seg_off[i + 1] = seg_off[i] + ns;
+	}
+	int rc = mc_load_sequences(ctx, letters, offsets, n, segs.data(), seg_off.data());
+	if (rc) return rc;
+	int used = 0;
+	rc = mc_build_histograms(ctx, k, tbytes, &used, max_count_out);
+	if (rc) return rc;
+	MC_REQUIRE(tbytes == 0 || used == tbytes, MC_ERR_STATE, "unexpected histogram width");
+	return mc_copy_histograms(ctx, hists_out);
+}
+
+extern "C" int mc_scan_host(mc_ctx *ctx, const void *hists, int tbytes, int k, const uint64_t *lens, int64_t n,
+                            const int64_t *center_rows, int ncenters, mc_scan_result *res, uint8_t *marks_out) {
+	MC_REQUIRE(ctx && hists && lens && center_rows && res && n > 0 && ncenters > 0, MC_ERR_ARG, "mc_scan_host: bad arguments");
+	MC_NEED_MODEL(ctx);
+	int rc = mc_load_histograms(ctx, hists, tbytes, k, lens, n);
+	if (rc) return rc;
+	rc = check_rows64(ctx, center_rows, ncenters);
+	if (rc) return rc;
+	const size_t nblk = (size_t)mc_scan_max_blocks(ctx);
+	rc = mc_ensure_scratch(ctx, Carve::need({nblk * 32, (size_t)ncenters * 32}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	void *d_part = cv.take<uint8_t>(nblk * 32);
+	uint8_t *d_res = cv.take<uint8_t>((size_t)ncenters * 32);
+	for (int c = 0; c < ncenters; c++) {
+		rc = mc_launch_scan(ctx, center_rows[c], 0, n - 1, 0, d_part, d_res + (size_t)c * 32);
+		if (rc) return rc;
+		if (marks_out) MC_CUDA(cudaMemcpyAsync(marks_out + (size_t)c * n, ctx->d_marks, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	MC_CUDA(cudaMemcpyAsync(res, d_res, (size_t)ncenters * 32, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}

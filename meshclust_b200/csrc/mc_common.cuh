@@ -1,0 +1,181 @@
+// Shared definitions of the meshclust_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/meshclust_b200.h"
+
+#define MC_NUM_SMS_FALLBACK 148
+#define MC_FULL_MASK 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (no exceptions across the C-ABI)
+// ---------------------------------------------------------------------------------------------
+void mc_set_error(const char *fmt, ...);
+
+#define MC_CUDA(call)                                                                          \
+	do {                                                                                       \
+		cudaError_t _e = (call);                                                               \
+		if (_e != cudaSuccess) {                                                               \
+			mc_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+			return MC_ERR_CUDA;                                                                \
+		}                                                                                      \
+	} while (0)
+
+#define MC_REQUIRE(cond, code, ...)   \
+	do {                              \
+		if (!(cond)) {                \
+			mc_set_error(__VA_ARGS__); \
+			return (code);            \
+		}                             \
+	} while (0)
+
+// ---------------------------------------------------------------------------------------------
+// the trained classifier as the kernels see it (passed by value as a kernel argument)
+// lookup order [LD, INTERSECTION, MANHATTAN, PEARSON, KULCZYNSKI2]  (Feature.cpp:15-28)
+// ---------------------------------------------------------------------------------------------
+struct McModel {
+	double mins[5];
+	double maxs[5];
+	double w[5];   // w[0] bias, w[1..nfeat]
+	int nfeat;     // 3 or 4
+	int valid;
+};
+
+// round(1/(1+exp(-sum))) == 1.0 (Trainer.cpp:95,102) holds exactly when fl(1+exp(-sum)) <= 2,
+// i.e. exp(-sum) <= 1 + 2^-52 (ties-to-even), i.e. -sum < 1.5 * 2^-52.  NaN is never similar.
+#define MC_SIGMOID_SUM_THRESHOLD (-0x1.8p-52)
+
+// per-point constants next to the histogram
+struct McPointAux {
+	const uint64_t *len;   // sequence length in bases (all characters, Ns included)
+	const uint64_t *mag;   // sum of bins (pseudo-counts included)  DivergencePoint.cpp:97-109
+	const uint64_t *sq;    // sum of squared bins
+};
+
+// ---------------------------------------------------------------------------------------------
+// the context
+// ---------------------------------------------------------------------------------------------
+struct mc_ctx {
+	int device = 0;
+	int num_sms = MC_NUM_SMS_FALLBACK;
+	cudaStream_t stream = nullptr;
+	int64_t launches = 0;
+
+	// sequences
+	int64_t n = 0;            // rows
+	int64_t total_bases = 0;
+	uint8_t *d_seq = nullptr;      // letters, then digits in place
+	int64_t *d_seq_off = nullptr;  // n+1
+	int32_t *d_segs = nullptr;     // 2*nseg
+	int64_t *d_seg_off = nullptr;  // n+1
+	int64_t nseg = 0;
+	bool have_seq = false;
+
+	// histograms
+	int k = 0;
+	int nbins = 0;
+	int tbytes = 0;
+	void *d_hist = nullptr;
+	size_t hist_capacity = 0;
+	uint64_t *d_len = nullptr, *d_mag = nullptr, *d_sq = nullptr;
+	int64_t aux_capacity = 0;
+	bool have_hist = false;
+
+	// alive set / marks (bvec on the device)
+	uint8_t *d_alive = nullptr, *d_marks = nullptr;
+
+	// model
+	McModel model{};
+
+	// scratch
+	void *d_scratch = nullptr;
+	size_t scratch_bytes = 0;
+	void *h_pinned = nullptr;
+	size_t pinned_bytes = 0;
+	unsigned int *d_ticket = nullptr;   // last-block-done counter + flags
+	unsigned int *d_flags = nullptr;    // [0] invalid-input flag, [1] max count, ...
+
+	// result slots of mc_scan_enqueue + per-launch block partials
+	void *d_scan_slots = nullptr;
+	void *d_scan_partials = nullptr;
+
+	// mean-shift member list (Phase A)
+	int64_t *d_members = nullptr;
+	int64_t members_cap = 0, members_n = 0;
+	uint32_t *d_sum = nullptr;   // running per-bin sum of member histograms
+	int64_t sum_bins = 0;
+};
+
+int mc_ensure_scratch(mc_ctx *ctx, size_t bytes);
+int mc_ensure_pinned(mc_ctx *ctx, size_t bytes);
+
+// ---------------------------------------------------------------------------------------------
+// the shared FP64 epilogue: raw features -> normalised -> combos -> GLM sum.
+// Bit-faithful to Feature.cpp:207-340 + Feature.h:64-88 + Trainer.cpp:84-95 as compiled by the
+// reference's flags: the file is built with -fmad=false and the one fused multiply-add the
+// reference binary performs in the GLM sum is written as fma().
+// S = sum min(p,q), D = sum p*q; (lp,mp,sp) = (length, mag, sum p^2) of the point, (lq,mq,sq) of
+// the center; N = number of bins.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mc_raw_features(uint64_t S, uint64_t D, uint64_t lp, uint64_t mp,
+                                                 uint64_t sp, uint64_t lq, uint64_t mq, uint64_t sq,
+                                                 int N, bool need_kul, double c[5]) {
+	c[0] = (double)(lp > lq ? lp - lq : lq - lp);
+	c[1] = (double)(2 * S) / (double)(mp + mq);
+	c[2] = (double)(int)(mp + mq - 2 * S);
+	{
+		const double dap = (double)mp / N, daq = (double)mq / N;
+		const long long ap = (int)round(dap), aq = (int)round(daq);
+		const long long np = (long long)sp - 2 * ap * (long long)mp + (long long)N * ap * ap;
+		const long long nq = (long long)sq - 2 * aq * (long long)mq + (long long)N * aq * aq;
+		const long long dot =
+			(long long)D - aq * (long long)mp - ap * (long long)mq + (long long)N * ap * aq;
+		const double prod = (double)(np * nq);
+		c[3] = (double)dot / sqrt(prod > 0.5 ? prod : 0.5);
+		if (need_kul) {
+			const double coeff = N * (dap + daq) / (2 * dap * daq);
+			c[4] = coeff * (double)S;
+		} else {
+			c[4] = 0.0;
+		}
+	}
+}
+
+__device__ __forceinline__ void mc_eval_model(const McModel &m, const double c_raw[5], double f[4],
+                                               double &sum) {
+	double c[5];
+	// LD, MANHATTAN, PEARSON are distances (1 - v'), INTERSECTION and KULCZYNSKI2 similarities
+	// (Feature.cpp:162-204); no clamping (Feature.cpp:42-51)
+#pragma unroll
+	for (int j = 0; j < 5; j++) {
+		const double v = (c_raw[j] - m.mins[j]) / (m.maxs[j] - m.mins[j]);
+		c[j] = (j == 1 || j == 4) ? v : 1 - v;
+	}
+	f[0] = (1.0 * c[0]) * c[1];
+	f[1] = (1.0 * (c[0] * c[0])) * (c[2] * c[2]);
+	f[2] = 1.0 * c[3];
+	f[3] = (1.0 * (c[0] * c[0])) * (c[4] * c[4]);
+	sum = m.w[0];
+	sum = fma(m.w[1], f[0], sum);
+	sum = fma(m.w[2], f[1], sum);
+	sum = fma(m.w[3], f[2], sum);
+	if (m.nfeat >= 4) sum = fma(m.w[4], f[3], sum);
+}
+
+// DivergencePoint::distance (DivergencePoint.cpp:68-81), with the fused 1 - f*f of the compiled
+// reference
+__device__ __forceinline__ uint64_t mc_distance_key(uint64_t S, uint64_t magsum) {
+	const double frac = (double)(2 * S) / (double)magsum;
+	return (uint64_t)(10000.0 * fma(-frac, frac, 1.0));
+}
+
+// DivergencePoint::distance_d (DivergencePoint.cpp:53-65) against a truncated mean whose bins sum
+// to magc
+__device__ __forceinline__ double mc_distance_d(uint64_t S, uint64_t magp, uint64_t magc) {
+	const double frac = (double)(2 * S) / (double)(magp + magc);
+	return 10000.0 * fma(-frac, frac, 1.0);
+}

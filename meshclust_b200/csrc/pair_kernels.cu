@@ -1,0 +1,354 @@
+// Stage 2: point-vs-center feature evaluation + GLM decision (K2a scan, K2b keys / pair lists).
+// Replaces Trainer::get_close / filter / merge loop bodies and the DivergencePoint::distance
+// calls of Trainer::split's sort comparators.  HBM-bound byte work: one pass over the histogram
+// rows with 16-byte streaming loads, SIMD-in-word integer reductions, FP64 epilogue on all lanes.
+#include "pair_core.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// per-point constants
+// ---------------------------------------------------------------------------------------------
+template <int TB>
+__global__ void point_stats_kernel(const uint8_t *__restrict__ hist, int nbins, int64_t n,
+                                   uint64_t *__restrict__ mag, uint64_t *__restrict__ sq) {
+	const int lane = threadIdx.x & 31;
+	const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	for (int64_t row = warp; row < n; row += nwarps) {
+		unsigned long long m = 0, s = 0;
+		if (TB == 1) {
+			const uint8_t *p = hist + (size_t)row * nbins;
+			for (int i = lane; i < nbins; i += 32) { unsigned v = p[i]; m += v; s += v * v; }
+		} else {
+			const uint16_t *p = reinterpret_cast<const uint16_t *>(hist) + (size_t)row * nbins;
+			for (int i = lane; i < nbins; i += 32) { unsigned long long v = p[i]; m += v; s += v * v; }
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) {
+			m += __shfl_xor_sync(MC_FULL_MASK, m, o);
+			s += __shfl_xor_sync(MC_FULL_MASK, s, o);
+		}
+		if (lane == 0) { mag[row] = m; sq[row] = s; }
+	}
+}
+
+int mc_launch_point_stats(mc_ctx *ctx) {
+	const int threads = 256;
+	int64_t blocks = (ctx->n * 32 + threads - 1) / threads;
+	if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
+	if (blocks < 1) blocks = 1;
+	if (ctx->tbytes == 1)
+		point_stats_kernel<1><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, ctx->d_mag, ctx->d_sq);
+	else
+		point_stats_kernel<2><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, ctx->d_mag, ctx->d_sq);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2a: scan = Trainer::get_close + bvec::remove_available
+// ---------------------------------------------------------------------------------------------
+struct ScanPartial {
+	long long n_eval;
+	long long n_pos;
+	long long best_row;
+	double best_f0;
+};
+
+__device__ __forceinline__ void scan_merge(ScanPartial &a, const ScanPartial &b) {
+	a.n_eval += b.n_eval;
+	a.n_pos += b.n_pos;
+	// first maximum in row order wins (Trainer.cpp:99 strict >, serial iteration order)
+	if (b.best_row >= 0 && (b.best_f0 > a.best_f0 || (b.best_f0 == a.best_f0 && (a.best_row < 0 || b.best_row < a.best_row)))) {
+		a.best_f0 = b.best_f0;
+		a.best_row = b.best_row;
+	}
+}
+
+constexpr int SCAN_THREADS = 256;
+
+template <int TB, int RB>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(const uint8_t *__restrict__ hist, McPointAux aux, uint8_t *__restrict__ alive,
+            uint8_t *__restrict__ marks, long long lo, long long hi, long long center_row,
+            McModel model, int remove_marked, ScanPartial *__restrict__ partials,
+            unsigned int *__restrict__ ticket, ScanPartial *__restrict__ result) {
+	using C = RowCfg<RB>;
+	constexpr int NB = RB / TB;
+	extern __shared__ __align__(16) uint32_t cen_smem[];
+	__shared__ ScanPartial warp_part[SCAN_THREADS / 32];
+	__shared__ bool is_last;
+
+	const int lane = threadIdx.x & 31;
+	const int wib = threadIdx.x >> 5;
+	const int g = lane / C::LPP, r = lane % C::LPP;
+
+	const uint8_t *crow = hist + (size_t)center_row * RB;
+	CenterRegs<RB> cen;
+	cen.load(crow, r);
+	if constexpr (!C::CENTER_IN_REGS) {
+		for (int i = threadIdx.x; i < RB / 16; i += blockDim.x)
+			reinterpret_cast<uint4 *>(cen_smem)[i] = __ldg(reinterpret_cast<const uint4 *>(crow) + i);
+		__syncthreads();
+	}
+	const uint64_t lq = aux.len[center_row], mq = aux.mag[center_row], sq = aux.sq[center_row];
+
+	ScanPartial mine;
+	mine.n_eval = 0; mine.n_pos = 0; mine.best_row = -1; mine.best_f0 = -1.0;
+
+	const long long warps_total = (long long)gridDim.x * (SCAN_THREADS / 32);
+	const long long warp_id = (long long)blockIdx.x * (SCAN_THREADS / 32) + wib;
+	for (long long batch = lo + warp_id * 32; batch <= hi; batch += warps_total * 32) {
+		const long long row_mine = batch + lane;
+		const unsigned alive_mine = (row_mine <= hi) ? alive[row_mine] : 0u;
+		const unsigned alive_bits = __ballot_sync(MC_FULL_MASK, alive_mine != 0);
+		if (alive_bits == 0) {
+			if (row_mine <= hi) marks[row_mine] = 0;
+			continue;
+		}
+		PairAcc<TB> part[C::LPP];
+#pragma unroll
+		for (int it = 0; it < C::LPP; it++) {
+			const int pidx = g * C::LPP + it;
+			// dead / out-of-range rows read the (cache-hot) center row instead: loads stay
+			// unconditional so they can all be issued up front
+			const bool a = (alive_bits >> pidx) & 1u;
+			const uint8_t *row = a ? hist + (size_t)(batch + pidx) * RB : crow;
+			part[it] = mc_row_partial<TB, RB>(row, r, cen, cen_smem);
+		}
+		const PairAcc<TB> tot = mc_transpose_reduce<C::LPP>(part, r);
+		if (row_mine <= hi) {
+			unsigned flag = 0;
+			if (alive_mine) {
+				const uint64_t lp = aux.len[row_mine], mp = aux.mag[row_mine], sp = aux.sq[row_mine];
+				const uint64_t S = tot.summin(mp, mq);
+				double c[5], f[4], sum;
+				mc_raw_features(S, tot.dot(), lp, mp, sp, lq, mq, sq, NB, model.nfeat >= 4, c);
+				mc_eval_model(model, c, f, sum);
+				flag = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1u : 0u;
+				mine.n_eval++;
+				mine.n_pos += flag;
+				if (f[0] > mine.best_f0) { mine.best_f0 = f[0]; mine.best_row = row_mine; }
+				if (flag && remove_marked) alive[row_mine] = 0;
+			}
+			marks[row_mine] = (uint8_t)flag;
+		}
+	}
+
+	// warp -> block -> grid reduction, deterministic (merge rule is order independent)
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		ScanPartial other;
+		other.n_eval = __shfl_xor_sync(MC_FULL_MASK, mine.n_eval, o);
+		other.n_pos = __shfl_xor_sync(MC_FULL_MASK, mine.n_pos, o);
+		other.best_row = __shfl_xor_sync(MC_FULL_MASK, mine.best_row, o);
+		other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, mine.best_f0, o);
+		scan_merge(mine, other);
+	}
+	if (lane == 0) warp_part[wib] = mine;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		ScanPartial b = warp_part[0];
+		for (int w = 1; w < SCAN_THREADS / 32; w++) scan_merge(b, warp_part[w]);
+		partials[blockIdx.x] = b;
+		__threadfence();
+		const unsigned t = atomicAdd(ticket, 1u);
+		is_last = (t == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (is_last) {
+		// the last block folds every block's partial (tiny: <= a few thousand entries)
+		__threadfence();
+		ScanPartial b;
+		b.n_eval = 0; b.n_pos = 0; b.best_row = -1; b.best_f0 = -1.0;
+		for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+			ScanPartial p;   // L2 loads: the partials were written by other SMs
+			p.n_eval = __ldcg(&partials[i].n_eval);
+			p.n_pos = __ldcg(&partials[i].n_pos);
+			p.best_row = __ldcg(&partials[i].best_row);
+			p.best_f0 = __ldcg(&partials[i].best_f0);
+			scan_merge(b, p);
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) {
+			ScanPartial other;
+			other.n_eval = __shfl_xor_sync(MC_FULL_MASK, b.n_eval, o);
+			other.n_pos = __shfl_xor_sync(MC_FULL_MASK, b.n_pos, o);
+			other.best_row = __shfl_xor_sync(MC_FULL_MASK, b.best_row, o);
+			other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, b.best_f0, o);
+			scan_merge(b, other);
+		}
+		if (lane == 0) warp_part[wib] = b;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			ScanPartial t = warp_part[0];
+			for (int w = 1; w < SCAN_THREADS / 32; w++) scan_merge(t, warp_part[w]);
+			*result = t;
+			*ticket = 0;   // re-arm for the next launch on this stream
+		}
+	}
+}
+
+// result_dev: device pointer receiving the ScanPartial (same layout as mc_scan_result)
+int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                   void *partials_dev, void *result_dev) {
+	const int64_t rows = hi - lo + 1;
+	int64_t blocks = (rows + SCAN_THREADS - 1) / SCAN_THREADS;
+	const int64_t cap = (int64_t)ctx->num_sms * 8;
+	if (blocks > cap) blocks = cap;
+	if (blocks < 1) blocks = 1;
+	McPointAux aux{ctx->d_len, ctx->d_mag, ctx->d_sq};
+#define SCAN_CASE(TBv, RBv)                                                                            \
+	{                                                                                                  \
+		const size_t smem = RowCfg<RBv>::CENTER_IN_REGS ? 0 : (size_t)RBv;                             \
+		if (smem > 48 * 1024)                                                                          \
+			MC_CUDA(cudaFuncSetAttribute(scan_kernel<TBv, RBv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		scan_kernel<TBv, RBv><<<(int)blocks, SCAN_THREADS, smem, ctx->stream>>>(                       \
+			(const uint8_t *)ctx->d_hist, aux, ctx->d_alive, ctx->d_marks, lo, hi, center_row,         \
+			ctx->model, remove_marked, (ScanPartial *)partials_dev, ctx->d_ticket, (ScanPartial *)result_dev); \
+	}
+	MC_DISPATCH_ROW(ctx->tbytes, ctx->nbins, SCAN_CASE);
+#undef SCAN_CASE
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
+int64_t mc_scan_max_blocks(mc_ctx *ctx) { return (int64_t)ctx->num_sms * 8; }
+
+// ---------------------------------------------------------------------------------------------
+// K2b: distance keys of every row against C centers (Trainer::split sort keys)
+// grid.y = center index; same 32-rows-per-warp tile as the scan, integer epilogue only.
+// ---------------------------------------------------------------------------------------------
+template <int TB, int RB>
+__global__ void __launch_bounds__(SCAN_THREADS)
+dist_keys_kernel(const uint8_t *__restrict__ hist, const uint64_t *__restrict__ mag, long long n,
+                 const int32_t *__restrict__ center_rows, uint16_t *__restrict__ keys) {
+	using C = RowCfg<RB>;
+	extern __shared__ __align__(16) uint32_t cen_smem[];
+	const int lane = threadIdx.x & 31;
+	const int wib = threadIdx.x >> 5;
+	const int g = lane / C::LPP, r = lane % C::LPP;
+	const long long center_row = center_rows[blockIdx.y];
+	const uint8_t *crow = hist + (size_t)center_row * RB;
+	CenterRegs<RB> cen;
+	cen.load(crow, r);
+	if constexpr (!C::CENTER_IN_REGS) {
+		for (int i = threadIdx.x; i < RB / 16; i += blockDim.x)
+			reinterpret_cast<uint4 *>(cen_smem)[i] = __ldg(reinterpret_cast<const uint4 *>(crow) + i);
+		__syncthreads();
+	}
+	const uint64_t mq = mag[center_row];
+	uint16_t *out = keys + (size_t)blockIdx.y * n;
+	const long long warps_total = (long long)gridDim.x * (SCAN_THREADS / 32);
+	const long long warp_id = (long long)blockIdx.x * (SCAN_THREADS / 32) + wib;
+	for (long long batch = warp_id * 32; batch < n; batch += warps_total * 32) {
+		PairAcc<TB> part[C::LPP];
+#pragma unroll
+		for (int it = 0; it < C::LPP; it++) {
+			const long long row = batch + g * C::LPP + it;
+			const uint8_t *p = row < n ? hist + (size_t)row * RB : crow;
+			part[it] = mc_row_partial<TB, RB>(p, r, cen, cen_smem);
+		}
+		const PairAcc<TB> tot = mc_transpose_reduce<C::LPP>(part, r);
+		const long long row_mine = batch + lane;
+		if (row_mine < n) {
+			const uint64_t mp = mag[row_mine];
+			out[row_mine] = (uint16_t)mc_distance_key(tot.summin(mp, mq), mp + mq);
+		}
+	}
+}
+
+int mc_launch_dist_keys(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint16_t *keys_dev) {
+	int64_t blocks = (ctx->n + SCAN_THREADS - 1) / SCAN_THREADS;
+	const int64_t cap = (int64_t)ctx->num_sms * 4;
+	if (blocks > cap) blocks = cap;
+	if (blocks < 1) blocks = 1;
+	dim3 grid((unsigned)blocks, (unsigned)C);
+#define KEYS_CASE(TBv, RBv)                                                                            \
+	{                                                                                                  \
+		const size_t smem = RowCfg<RBv>::CENTER_IN_REGS ? 0 : (size_t)RBv;                             \
+		if (smem > 48 * 1024)                                                                          \
+			MC_CUDA(cudaFuncSetAttribute(dist_keys_kernel<TBv, RBv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		dist_keys_kernel<TBv, RBv><<<grid, SCAN_THREADS, smem, ctx->stream>>>(                          \
+			(const uint8_t *)ctx->d_hist, ctx->d_mag, ctx->n, center_rows_dev, keys_dev);              \
+	}
+	MC_DISPATCH_ROW(ctx->tbytes, ctx->nbins, KEYS_CASE);
+#undef KEYS_CASE
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair lists (training feature matrix, normalisation bounds, merge candidates): one warp per pair
+// ---------------------------------------------------------------------------------------------
+template <int TB>
+__global__ void pair_list_kernel(const uint8_t *__restrict__ hist, McPointAux aux, int nbins,
+                                 const int32_t *__restrict__ pa, const int32_t *__restrict__ pb,
+                                 long long m, McModel model, double *__restrict__ raw5,
+                                 unsigned long long *__restrict__ dist, double *__restrict__ sum_out,
+                                 double *__restrict__ f0_out, uint8_t *__restrict__ flag_out,
+                                 double *__restrict__ feats_out) {
+	const int lane = threadIdx.x & 31;
+	const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+	const int rb = nbins * TB;
+	for (long long i = warp; i < m; i += nwarps) {
+		const long long a = pa[i], b = pb[i];
+		const uint8_t *p = hist + (size_t)a * rb, *q = hist + (size_t)b * rb;
+		PairAcc<TB> acc;
+		if (rb >= 16) {
+			for (int c = lane; c < rb / 16; c += 32) {
+				const uint4 x = __ldg(reinterpret_cast<const uint4 *>(p) + c);
+				const uint4 y = __ldg(reinterpret_cast<const uint4 *>(q) + c);
+				acc.add(x.x, y.x); acc.add(x.y, y.y); acc.add(x.z, y.z); acc.add(x.w, y.w);
+			}
+		} else {
+			for (int c = lane; c < rb / 4; c += 32)
+				acc.add(__ldg(reinterpret_cast<const uint32_t *>(p) + c), __ldg(reinterpret_cast<const uint32_t *>(q) + c));
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) acc.shfl_add_from(acc, o);
+		if (lane == 0) {
+			const uint64_t lp = aux.len[a], mp = aux.mag[a], sp = aux.sq[a];
+			const uint64_t lq = aux.len[b], mq = aux.mag[b], sq = aux.sq[b];
+			const uint64_t S = acc.summin(mp, mq);
+			double c[5];
+			mc_raw_features(S, acc.dot(), lp, mp, sp, lq, mq, sq, nbins, true, c);
+			if (raw5) {
+#pragma unroll
+				for (int j = 0; j < 5; j++) raw5[i * 5 + j] = c[j];
+			}
+			if (dist) dist[i] = mc_distance_key(S, mp + mq);
+			if (sum_out || f0_out || flag_out || feats_out) {
+				double f[4], sum;
+				mc_eval_model(model, c, f, sum);
+				if (sum_out) sum_out[i] = sum;
+				if (f0_out) f0_out[i] = f[0];
+				if (flag_out) flag_out[i] = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1 : 0;
+				if (feats_out) {
+#pragma unroll
+					for (int j = 0; j < 4; j++) feats_out[i * 4 + j] = f[j];
+				}
+			}
+		}
+	}
+}
+
+int mc_launch_pair_list(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m,
+                        double *raw5_dev, uint64_t *dist_dev, double *sum_dev, double *f0_dev,
+                        uint8_t *flag_dev, double *feats_dev) {
+	const int threads = 256;
+	int64_t blocks = (m * 32 + threads - 1) / threads;
+	if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
+	if (blocks < 1) blocks = 1;
+	McPointAux aux{ctx->d_len, ctx->d_mag, ctx->d_sq};
+	if (ctx->tbytes == 1)
+		pair_list_kernel<1><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, aux, ctx->nbins, pa_dev, pb_dev, m, ctx->model, raw5_dev, (unsigned long long *)dist_dev, sum_dev, f0_dev, flag_dev, feats_dev);
+	else
+		pair_list_kernel<2><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, aux, ctx->nbins, pa_dev, pb_dev, m, ctx->model, raw5_dev, (unsigned long long *)dist_dev, sum_dev, f0_dev, flag_dev, feats_dev);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}

@@ -269,6 +269,94 @@ void ref_scan_u8(const uint8_t *hists, const uint64_t *lens, int n, int nbins,
 	delete c;
 }
 
+// The same evaluation over points that already exist as DivergencePoint<uint8_t> objects, the way
+// the reference holds them (built once by ClusterFactory::build_points): this is the timed CPU
+// baseline, so object construction stays outside it.
+struct RefPointSet {
+	std::vector<DivergencePoint<uint8_t> *> pts;
+	Feature<uint8_t> *feat = nullptr;
+	int nfeat = 0;
+};
+
+void *ref_pointset_create(const uint8_t *hists, const uint64_t *lens, int n, int nbins) {
+	RefPointSet *ps = new RefPointSet();
+	ps->pts.resize(n);
+	for (int i = 0; i < n; i++) {
+		ps->pts[i] = mk_point<uint8_t>(hists + (size_t)i * nbins, nbins, lens[i]);
+		ps->pts[i]->set_id(i);
+	}
+	return ps;
+}
+
+void ref_pointset_destroy(void *h) {
+	RefPointSet *ps = (RefPointSet *)h;
+	for (auto *p : ps->pts) delete p;
+	delete ps->feat;
+	delete ps;
+}
+
+void ref_pointset_set_model(void *h, const double *mins, const double *maxs, int nfeat) {
+	RefPointSet *ps = (RefPointSet *)h;
+	delete ps->feat;
+	ps->feat = new Feature<uint8_t>(0, NULL, 0);
+	ps->feat->add_feature(FEAT_INTERSECTION | FEAT_LD, COMBO_SELF);
+	ps->feat->add_feature(FEAT_MANHATTAN | FEAT_LD, COMBO_SQUARED);
+	ps->feat->add_feature(FEAT_PEARSON, COMBO_SELF);
+	if (nfeat >= 4) ps->feat->add_feature(FEAT_KULCZYNSKI2 | FEAT_LD, COMBO_SQUARED);
+	for (size_t i = 0; i < ps->feat->lookup.size(); i++) {
+		ps->feat->mins[i] = mins[i];
+		ps->feat->maxs[i] = maxs[i];
+	}
+	ps->feat->finalize();
+	ps->nfeat = nfeat;
+}
+
+// Trainer::get_close loop body + reductions (Trainer.cpp:81-106): returns the number of positives,
+// *best_idx / *best_f0 the argmax of f0 (first max wins), flag_out optional.
+long ref_pointset_scan(void *h, int center, const double *weights, uint8_t *flag_out, long *best_idx,
+		       double *best_f0) {
+	RefPointSet *ps = (RefPointSet *)h;
+	Feature<uint8_t> &feat = *ps->feat;
+	const int ncols = ps->nfeat + 1;
+	const int n = (int)ps->pts.size();
+	DivergencePoint<uint8_t> *c = ps->pts[center];
+	long npos = 0;
+	long bi = -1;
+	double bf = -1;
+#pragma omp parallel
+	{
+		long lpos = 0, lbi = -1;
+		double lbf = -1;
+#pragma omp for schedule(static) nowait
+		for (int i = 0; i < n; i++) {
+			DivergencePoint<uint8_t> *pt = ps->pts[i];
+			double sum = weights[0];
+			double dist = 0;
+			auto cache = feat.compute(*pt, *c);
+			for (int col = 1; col < ncols; col++) {
+				if (col == 1) {
+					dist = feat(col - 1, cache);
+					sum += weights[col] * dist;
+				} else {
+					sum += weights[col] * feat(col - 1, cache);
+				}
+			}
+			double res = round(1.0 / (1 + exp(-sum)));
+			if (dist > lbf) { lbf = dist; lbi = i; }
+			if (res == 1.0) lpos++;
+			if (flag_out) flag_out[i] = (res == 1.0);
+		}
+#pragma omp critical
+		{
+			npos += lpos;
+			if (lbi >= 0 && (lbf > bf || (lbf == bf && lbi < bi))) { bf = lbf; bi = lbi; }
+		}
+	}
+	*best_idx = bi;
+	*best_f0 = bf;
+	return npos;
+}
+
 // GlobAlignE(seq1, 0, la-1, seq2, 0, lb-1, match, mismatch, open, cont): GlobAlignE.cpp:22-57,123-305
 void ref_globalign(const char *s1, int la, const char *s2, int lb,
 		   int match, int mismatch, int gopen, int gcont,

@@ -119,6 +119,30 @@ class Oracle:
                                  C.c_int(nfeat), _ptr(s), _ptr(f0), _ptr(fl))
         return s, f0, fl
 
+    # -- reference-only: points held as objects, the way the reference holds them ---------
+    def pointset(self, hists: np.ndarray, lens: np.ndarray):
+        assert self.prefix == "ref_" and hists.dtype == np.uint8
+        hists = np.ascontiguousarray(hists)
+        lens = np.ascontiguousarray(lens, np.uint64)
+        self.lib.ref_pointset_create.restype = c_p
+        h = self.lib.ref_pointset_create(_ptr(hists), _ptr(lens), C.c_int(hists.shape[0]), C.c_int(hists.shape[1]))
+        return c_p(h)
+
+    def pointset_set_model(self, ps, mins, maxs, nfeat):
+        mins = np.ascontiguousarray(mins, np.float64)
+        maxs = np.ascontiguousarray(maxs, np.float64)
+        self.lib.ref_pointset_set_model(ps, _ptr(mins), _ptr(maxs), C.c_int(nfeat))
+
+    def pointset_scan(self, ps, center: int, weights, flags: np.ndarray | None = None):
+        weights = np.ascontiguousarray(weights, np.float64)
+        bi, bf = C.c_long(-1), C.c_double(-1)
+        self.lib.ref_pointset_scan.restype = C.c_long
+        npos = self.lib.ref_pointset_scan(ps, C.c_int(center), _ptr(weights), None if flags is None else _ptr(flags), C.byref(bi), C.byref(bf))
+        return int(npos), int(bi.value), float(bf.value)
+
+    def pointset_destroy(self, ps):
+        self.lib.ref_pointset_destroy(ps)
+
     # -- alignment ------------------------------------------------------------------------
     def globalign(self, s1: bytes, s2: bytes, params=(1, -1, 2, 1)):
         sc, ln, mt = C.c_int(0), C.c_int(0), C.c_int(0)

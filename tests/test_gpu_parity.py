@@ -1,0 +1,387 @@
+"""GPU: every stage of the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded inputs and against the committed golden vectors (outputs of the reference itself).
+
+Bars: histograms, digit strings, distance keys, alignment (score, len, matches), scan counts and
+argmax rows -- bit-exact.  Raw features -- bit-exact (they derive from exact integer reductions
+through the same FP64 formulas).  GLM sum / f0 -- stated tolerance 1e-12 relative; decisions must
+agree except for pairs with |sum| < 1e-9, which are counted.
+"""
+import numpy as np
+import pytest
+
+from meshclust_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+NEAR = 1e-9
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def _model(nfeat):
+    mins = np.array([0.0, 0.55, 12.0, -0.15, 180.0])
+    maxs = np.array([55.0, 0.995, 800.0, 0.9, 420.0])
+    w = np.array([-2.2, 2.4, 1.3, 0.6] if nfeat == 3 else [-3.1, 2.4, 1.3, 0.6, 0.9])
+    return mins, maxs, w
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 0/1
+# ----------------------------------------------------------------------------------------------
+def test_encode_and_hist_golden(ctx, golden):
+    letters, offs = golden["enc_letters"], golden["enc_offs"]
+    ctx.load_sequences(letters, offs)
+    assert np.array_equal(ctx.copy_digits(), golden["enc_digits"])
+    for k in (1, 2, 3, 4, 5, 6):
+        want = golden[f"hist_k{k}"]
+        used, mx = ctx.build_histograms(k, 0)
+        assert mx == int(want.max())
+        assert used == (1 if mx <= 255 else 2)
+        got = ctx.copy_histograms()
+        assert np.array_equal(got.astype(np.uint16), want)
+        ln, mg, sq = ctx.copy_point_stats()
+        assert np.array_equal(ln, np.diff(offs).astype(np.uint64))
+        assert np.array_equal(mg, want.astype(np.uint64).sum(1))
+        assert np.array_equal(sq, (want.astype(np.uint64) ** 2).sum(1))
+        # forced 16-bit bins give the same counts
+        ctx.build_histograms(k, 2)
+        assert np.array_equal(ctx.copy_histograms(), want)
+
+
+@pytest.mark.parametrize("cfg,n,k", [("c1", 3000, 3), ("c2", 2000, 4), ("c4", 2000, 5), ("c5", 300, 6), ("c3", 1500, 4)])
+def test_hist_vs_oracle_configs(ctx, oracle, cfg, n, k):
+    letters, offs, _ = synth.generate_config(cfg, n)
+    rc, want, mx = oracle.hist_batch(letters, offs, k, 1)
+    assert rc == 0 and mx <= 255
+    got, gmx = ctx.kmer_histograms_host(letters, offs, k, 1)
+    assert gmx == mx
+    assert np.array_equal(got, want)
+
+
+def test_hist_u16_homopolymer(ctx, oracle):
+    # long homopolymer runs push one bin past 255 -> 16-bit histograms (Runner.cpp:75-89)
+    rng = np.random.default_rng(0)
+    seqs = [b"A" * 700 + bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 300)), b"ACGT" * 200 + b"T" * 400,
+            bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 900))]
+    offs = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([len(s) for s in seqs], out=offs[1:])
+    letters = np.frombuffer(b"".join(seqs), np.uint8)
+    rc, want, mx = oracle.hist_batch(letters, offs, 3, 2)
+    assert mx > 255
+    ctx.load_sequences(letters, offs)
+    used, gmx = ctx.build_histograms(3, 0)
+    assert (used, gmx) == (2, mx)
+    assert np.array_equal(ctx.copy_histograms(), want)
+    with pytest.raises(Exception):
+        ctx.build_histograms(3, 1)       # forcing 8-bit bins must fail loudly, not wrap
+
+
+def test_invalid_input_is_rejected(ctx, built_lib):
+    s = np.frombuffer(b"ACGTACGTACGTACGTACGTAC-GTACGT", np.uint8)
+    with pytest.raises(built_lib.McError) as e:
+        ctx.load_sequences(s, np.array([0, s.size], np.int64))
+    assert e.value.code == built_lib.MC_ERR_INPUT
+    with pytest.raises(built_lib.McError):
+        ctx.load_sequences(np.frombuffer(b"NNNNNNNN", np.uint8), np.array([0, 8], np.int64))
+
+
+def test_ragged_and_tiny_sequences(ctx, oracle):
+    # 1-base, < 20 bp, exactly 20 bp, unaligned neighbours, N runs at both ends
+    seqs = [b"A", b"ACGTACGTAC", b"ACGTACGTACGTACGTACGT", b"C" * 33, b"NNNACGTACGTACGTACGTACGTACGTNN", b"G" * 17,
+            b"ACGTTGCAAC" * 13 + b"G", b"T" * 16, b"ACGGTCA" * 50]
+    offs = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([len(s) for s in seqs], out=offs[1:])
+    letters = np.frombuffer(b"".join(seqs), np.uint8)
+    for k in (1, 2, 4, 6):
+        rc, want, _ = oracle.hist_batch(letters, offs, k, 1)
+        got, _ = ctx.kmer_histograms_host(letters, offs, k, 1)
+        assert np.array_equal(got, want)
+    import _oracle
+    assert np.array_equal(ctx.copy_digits(), _oracle.encode_digits(letters, offs))
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 2
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["u8", "u16"])
+@pytest.mark.parametrize("nb", [16, 64, 256, 1024])
+def test_pair_features_golden(ctx, golden, name, nb):
+    H, lens = golden[f"pf_{name}_{nb}_H"], golden[f"pf_{name}_{nb}_lens"]
+    n = H.shape[0]
+    k = {16: 2, 64: 3, 256: 4, 1024: 5}[nb]
+    ctx.load_histograms(H, lens, k)
+    a, b = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    raw, dist = ctx.pair_features(a.reshape(-1), b.reshape(-1))
+    assert np.array_equal(_bits(raw), _bits(golden[f"pf_{name}_{nb}_raw"].reshape(-1, 5)))
+    assert np.array_equal(dist, golden[f"pf_{name}_{nb}_dist"].reshape(-1))
+    keys = ctx.distance_keys(np.arange(n))
+    assert np.array_equal(keys.astype(np.uint64), golden[f"pf_{name}_{nb}_dist"])
+    # mean of the first half + nearest member (get_mean) against the golden distance_d values
+    row, d = ctx.mean_nearest(np.arange(n // 2))
+    dd = golden[f"pf_{name}_{nb}_dd"][: n // 2]
+    assert row == int(np.argmin(dd)) and _bits(d) == _bits(dd.min())
+
+
+@pytest.mark.parametrize("nfeat", [3, 4])
+def test_scan_golden(ctx, golden, nfeat):
+    H, lens = golden["sc_H"], golden["sc_lens"]
+    n = H.shape[0]
+    ctx.load_histograms(H, lens, 4)
+    ctx.set_model(golden["sc_mins"], golden["sc_maxs"], golden[f"sc_w{nfeat}"], nfeat)
+    want_sum, want_f0, want_flag = golden[f"sc_sum{nfeat}"], golden[f"sc_f0{nfeat}"], golden[f"sc_flag{nfeat}"]
+    s, f0, fl, _ = ctx.pair_classify(np.arange(n), np.full(n, 7))
+    assert np.allclose(s, want_sum, rtol=RTOL, atol=0)
+    assert np.allclose(f0, want_f0, rtol=RTOL, atol=0)
+    near = np.abs(want_sum) < NEAR
+    assert np.array_equal(fl[~near], want_flag[~near])
+    res, marks = ctx.scan(7, 0, n - 1)
+    assert res.n_eval == n
+    assert np.array_equal(marks[~near], want_flag[~near])
+    assert res.n_pos == int(marks.sum())
+    assert res.best_row == int(np.argmax(want_f0)) and res.best_f0 == want_f0.max()
+
+
+def _rand_hists(rng, n, nb, dtype=np.uint8, hi=255, clusters=8):
+    bases = np.minimum(rng.poisson(max(1, 1000 // nb) + 1, (clusters, nb)) + 1, hi)
+    H = bases[rng.integers(0, clusters, n)] + rng.integers(-2, 3, (n, nb))
+    return np.minimum(np.maximum(H, 1), hi).astype(dtype)
+
+
+@pytest.mark.parametrize("k,n", [(1, 700), (2, 1000), (3, 5000), (4, 4000), (5, 3000), (6, 700), (7, 300)])
+@pytest.mark.parametrize("nfeat", [3, 4])
+def test_scan_vs_oracle(ctx, oracle, k, n, nfeat):
+    rng = np.random.default_rng(100 + k)
+    nb = 4 ** k
+    H = _rand_hists(rng, n, nb)
+    lens = (H.astype(np.int64).sum(1) - nb + k - 1 + rng.integers(0, 3, n)).astype(np.uint64)
+    mins, maxs, w = _model(nfeat)
+    maxs[2] = 4.0 * nb
+    maxs[4] = 2.0 * nb
+    mins[4] = 0.5 * nb
+    ctx.load_histograms(H, lens, k)
+    ctx.set_model(mins, maxs, w, nfeat)
+    total_near = 0
+    for center in (0, n // 3, n - 1):
+        ctx.alive_reset()
+        ws, wf0, wfl = oracle.scan(H, lens, H[center], int(lens[center]), mins, maxs, w, nfeat)
+        near = np.abs(ws) < NEAR
+        total_near += int(near.sum())
+        # ragged sub-range + a few dead rows
+        lo, hi = 5, n - 7
+        dead = np.array([lo, lo + 17, hi, (lo + hi) // 2])
+        ctx.alive_kill(dead)
+        live = np.ones(n, bool)
+        live[dead] = False
+        live[:lo] = False
+        live[hi + 1:] = False
+        res, marks = ctx.scan(center, lo, hi)
+        idx = np.nonzero(live)[0]
+        assert res.n_eval == idx.size
+        full = np.zeros(n, np.uint8)
+        full[lo:hi + 1] = marks
+        ok = live & ~near
+        assert np.array_equal(full[ok], wfl[ok])
+        assert not full[~live].any()
+        cand = wf0[idx]
+        best = idx[int(np.argmax(cand))] if cand.max() > -1 else -1
+        assert res.best_row == best
+        if best >= 0:
+            assert np.isclose(res.best_f0, wf0[best], rtol=RTOL, atol=0)
+        # marked rows left the alive set: a second scan sees only the survivors
+        res2, marks2 = ctx.scan(center, lo, hi)
+        assert res2.n_eval == idx.size - int(marks.sum())
+        assert res2.n_pos == 0 or near.any()
+    print(f"near-threshold pairs (|sum| < {NEAR}): {total_near}")
+
+
+def test_scan_first_max_wins_and_null(ctx, oracle):
+    # identical rows tie on f0: the first one in row order must win; f0 <= -1 everywhere -> no seed
+    rng = np.random.default_rng(9)
+    nb, n = 256, 2000
+    H = _rand_hists(rng, n, nb, clusters=2)
+    H[100] = H[900]
+    H[1500] = H[900]
+    lens = np.full(n, 300, np.uint64)
+    mins, maxs, w = _model(3)
+    ctx.load_histograms(H, lens, 4)
+    ctx.set_model(mins, maxs, w, 3)
+    _, wf0, _ = oracle.scan(H, lens, H[900], 300, mins, maxs, w, 3)
+    res, _ = ctx.scan(900, 0, n - 1)
+    assert res.best_row == int(np.argmax(wf0)) == 100
+    # length difference far beyond the training max drives LD' (and f0) below -1
+    lens2 = np.full(n, 300, np.uint64)
+    lens2[5] = 100000
+    ctx.load_histograms(H, lens2, 4)
+    ctx.set_model(mins, maxs, w, 3)
+    ctx.alive_kill(np.array([5]))
+    res, _ = ctx.scan(5, 0, n - 1)
+    assert res.best_row == -1 and res.best_f0 == -1.0 and res.n_pos == 0
+    # empty range
+    res, _ = ctx.scan(5, 10, 9)
+    assert res.as_tuple() == (0, 0, -1, -1.0)
+
+
+@pytest.mark.parametrize("k", [3, 4, 5])
+def test_distance_keys_vs_oracle(ctx, oracle, k):
+    rng = np.random.default_rng(40 + k)
+    nb, n = 4 ** k, 3000
+    H = _rand_hists(rng, n, nb)
+    lens = np.full(n, 1000, np.uint64)
+    ctx.load_histograms(H, lens, k)
+    centers = rng.integers(0, n, 9)
+    keys = ctx.distance_keys(centers)
+    for ci, c in enumerate(centers):
+        rows = rng.integers(0, n, 200)
+        want = [oracle.features(H[r], H[c], 1000, 1000)[1] for r in rows]
+        assert keys[ci, rows].tolist() == want
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 3
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,hi", [(np.uint8, 255), (np.uint16, 3000)])
+@pytest.mark.parametrize("k", [2, 4, 6])
+def test_mean_nearest_vs_oracle(ctx, oracle, dtype, hi, k):
+    rng = np.random.default_rng(60 + k)
+    nb, n = 4 ** k, 500
+    H = _rand_hists(rng, n, nb, dtype, hi, clusters=3)
+    ctx.load_histograms(H, np.full(n, 999, np.uint64), k)
+    members = rng.permutation(n)[:120]
+    members[7] = members[3]          # a duplicate row ties with itself: first position wins
+    pieces = [members[:1], members[1:40], members[40:41], members[41:]]
+    got = None
+    for i, p in enumerate(pieces):   # accumulate() grows `current` and re-runs get_mean
+        got = ctx.mean_nearest(p, append=i > 0)
+        cur = members[: sum(len(q) for q in pieces[: i + 1])]
+        mean = oracle.mean(H[cur])
+        dd = np.array([oracle.distance_d(H[r], mean) for r in cur])
+        assert got[0] == int(cur[int(np.argmin(dd))])
+        assert _bits(got[1]) == _bits(dd.min())
+
+
+@pytest.mark.parametrize("k", [3, 4, 5])
+def test_update_centers_vs_oracle(ctx, oracle, k):
+    rng = np.random.default_rng(80 + k)
+    nb, n = 4 ** k, 1500
+    H = _rand_hists(rng, n, nb, clusters=12)
+    lens = (H.astype(np.int64).sum(1) - nb + k - 1).astype(np.uint64)
+    mins, maxs, w = _model(4)
+    maxs[2], maxs[4], mins[4] = 4.0 * nb, 2.0 * nb, 0.5 * nb
+    ctx.load_histograms(H, lens, k)
+    ctx.set_model(mins, maxs, w, 4)
+    # 30 clusters of random members; center c sees clusters c-2..c+2 (delta = 2)
+    perm = rng.permutation(n)
+    cuts = np.sort(rng.choice(np.arange(1, n), 29, replace=False))
+    bounds = np.concatenate([[0], cuts, [n]])
+    centers = np.array([perm[bounds[c]] for c in range(30)])
+    delta = 2
+    cb = np.array([bounds[max(0, c - delta)] for c in range(30)])
+    ce = np.array([bounds[min(29, c + delta) + 1] for c in range(30)])
+    got = ctx.update_centers(centers, perm, cb, ce)
+    nsurv = 0
+    for c in range(30):
+        cand = perm[cb[c]:ce[c]]
+        s, f0, fl = oracle.scan(H[cand], lens[cand], H[centers[c]], int(lens[centers[c]]), mins, maxs, w, 4)
+        assert not (np.abs(s) < NEAR).any()
+        good = cand[fl == 1]
+        nsurv += good.size
+        if good.size == 0:
+            assert got[c] == -1
+            continue
+        mean = oracle.mean(H[good])
+        dd = np.array([oracle.distance_d(H[r], mean) for r in good])
+        assert got[c] == int(good[int(np.argmin(dd))])
+    assert nsurv > 0
+
+
+# ----------------------------------------------------------------------------------------------
+# stage 4
+# ----------------------------------------------------------------------------------------------
+def test_alignment_golden(ctx, golden):
+    digits, offs = golden["al_digits"], golden["al_offs"]
+    n = offs.size - 1
+    # digits are already encoded: load as sequences without segments (left untouched, upper-cased
+    # letters stay letters; bytes 0..3 and 'N' pass through)
+    ctx.load_sequences(digits, offs, np.zeros(0, np.int32), np.zeros(n + 1, np.int64))
+    assert np.array_equal(ctx.copy_digits(), digits)
+    sc, ln, mt = ctx.align_pairs(golden["al_pa"], golden["al_pb"])
+    assert np.array_equal(sc, golden["al_score"])
+    assert np.array_equal(ln, golden["al_len"])
+    assert np.array_equal(mt, golden["al_matches"])
+
+
+@pytest.mark.parametrize("cfg,n,npairs", [("c3", 400, 3000), ("c1", 300, 1200), ("c2", 120, 300)])
+def test_alignment_vs_oracle_configs(ctx, oracle, cfg, n, npairs):
+    import _oracle
+    letters, offs, tmpl = synth.generate_config(cfg, n)
+    ctx.load_sequences(letters, offs)
+    digits = _oracle.encode_digits(letters, offs)
+    assert np.array_equal(ctx.copy_digits(), digits)
+    rng = np.random.default_rng(12)
+    pa = rng.integers(0, n, npairs).astype(np.int32)
+    pb = rng.integers(0, n, npairs).astype(np.int32)
+    same = rng.random(npairs) < 0.5        # half the pairs from the same template (high identity)
+    pb[same] = (pa[same] + len(set(tmpl.tolist())) * rng.integers(0, 3, int(same.sum()))) % n
+    want = oracle.globalign_batch(digits, offs, pa, pb)
+    got = ctx.align_pairs(pa, pb)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+def test_alignment_lengths_sweep(ctx, oracle):
+    # lengths around the 32-row strip boundaries, empty strings, N bytes
+    rng = np.random.default_rng(13)
+    lens = [0, 1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 130, 257]
+    seqs = []
+    for L in lens:
+        s = rng.integers(0, 4, L, dtype=np.uint8)
+        if L > 40:
+            s[L // 2] = ord("N")
+        seqs.append(s)
+    offs = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([s.size for s in seqs], out=offs[1:])
+    digits = np.concatenate(seqs)
+    n = len(seqs)
+    ctx.load_sequences(digits, offs, np.zeros(0, np.int32), np.zeros(n + 1, np.int64))
+    pa, pb = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    pa, pb = pa.reshape(-1).astype(np.int32), pb.reshape(-1).astype(np.int32)
+    want = oracle.globalign_batch(digits, offs, pa, pb)
+    got = ctx.align_pairs(pa, pb)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+# ----------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE sizes (the oracle would take too long there)
+# ----------------------------------------------------------------------------------------------
+def test_full_size_properties_c2(ctx, oracle):
+    letters, offs, _ = synth.generate_config("c2")
+    n = offs.size - 1
+    hist, mx = ctx.kmer_histograms_host(letters, offs, 4, 1)
+    assert mx <= 255
+    ln, mg, sq = ctx.copy_point_stats()
+    # every k-mer start is counted exactly once: mag = 4^k + (L - k + 1)
+    assert np.array_equal(mg, (256 + np.diff(offs) - 3).astype(np.uint64))
+    assert np.array_equal(hist.astype(np.uint64).sum(1), mg)
+    # spot-check 300 rows bit-exactly against the oracle
+    rows = np.random.default_rng(0).integers(0, n, 300)
+    sub_offs = np.zeros(rows.size + 1, np.int64)
+    np.cumsum(np.diff(offs)[rows], out=sub_offs[1:])
+    sub = np.concatenate([letters[offs[r]:offs[r + 1]] for r in rows])
+    rc, want, _ = oracle.hist_batch(sub, sub_offs, 4, 1)
+    assert np.array_equal(hist[rows], want)
+    # scan: a row is always similar to itself with f0 = its maximum possible value; symmetric keys
+    mins = np.array([0.0, 0.5, 0.0, 0.0, 100.0])
+    maxs = np.array([80.0, 1.0, 1200.0, 1.0, 600.0])
+    ctx.set_model(mins, maxs, np.array([-1.0, 2.0, 1.0, 0.5]), 3)
+    for c in (0, n // 2, n - 1):
+        ctx.alive_reset()
+        res, marks = ctx.scan(c, 0, n - 1)
+        assert res.n_eval == n and marks[c] == 1 and res.n_pos == int(marks.sum())
+        s, f0, fl = oracle.scan(hist[c:c + 1], ln[c:c + 1], hist[c], int(ln[c]), mins, maxs, np.array([-1.0, 2.0, 1.0, 0.5]), 3)
+        assert res.best_f0 >= f0[0]
+    keys = ctx.distance_keys(np.array([3, 77]))
+    assert keys[0, 3] == 0 and keys[1, 77] == 0 and keys[0, 77] == keys[1, 3]
