@@ -12,6 +12,7 @@ int mc_upload_lut();
 int mc_launch_encode(mc_ctx *ctx);
 int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes);
 int mc_launch_point_stats(mc_ctx *ctx);
+int mc_launch_alive_reset(mc_ctx *ctx);
 int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, void *partials_dev, void *result_dev);
 int64_t mc_scan_max_blocks(mc_ctx *ctx);
 int mc_launch_dist_keys(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint16_t *keys_dev);
@@ -116,10 +117,10 @@ static void free_seq(mc_ctx *ctx) {
 }
 
 static void free_hist(mc_ctx *ctx) {
-	cudaFree(ctx->d_hist); cudaFree(ctx->d_len); cudaFree(ctx->d_mag); cudaFree(ctx->d_sq);
-	cudaFree(ctx->d_alive); cudaFree(ctx->d_marks); cudaFree(ctx->d_members); cudaFree(ctx->d_sum);
-	ctx->d_hist = nullptr; ctx->d_len = ctx->d_mag = ctx->d_sq = nullptr;
-	ctx->d_alive = ctx->d_marks = nullptr; ctx->d_members = nullptr; ctx->d_sum = nullptr;
+	cudaFree(ctx->d_hist); cudaFree(ctx->d_aux);
+	cudaFree(ctx->d_marks); cudaFree(ctx->d_members); cudaFree(ctx->d_sum);
+	ctx->d_hist = nullptr; ctx->d_aux = nullptr;
+	ctx->d_marks = nullptr; ctx->d_members = nullptr; ctx->d_sum = nullptr;
 	ctx->hist_capacity = 0; ctx->aux_capacity = 0; ctx->members_cap = 0; ctx->members_n = 0; ctx->sum_bins = 0;
 	ctx->have_hist = false;
 }
@@ -246,11 +247,8 @@ static int alloc_hist(mc_ctx *ctx, int64_t n, int k, int tbytes) {
 		ctx->hist_capacity = bytes;
 	}
 	if (n > ctx->aux_capacity) {
-		cudaFree(ctx->d_len); cudaFree(ctx->d_mag); cudaFree(ctx->d_sq); cudaFree(ctx->d_alive); cudaFree(ctx->d_marks);
-		MC_CUDA(cudaMalloc(&ctx->d_len, (size_t)n * 8));
-		MC_CUDA(cudaMalloc(&ctx->d_mag, (size_t)n * 8));
-		MC_CUDA(cudaMalloc(&ctx->d_sq, (size_t)n * 8));
-		MC_CUDA(cudaMalloc(&ctx->d_alive, (size_t)n + 64));
+		cudaFree(ctx->d_aux); cudaFree(ctx->d_marks);
+		MC_CUDA(cudaMalloc(&ctx->d_aux, ((size_t)n + 64) * sizeof(McRowAux)));   // +tail for tile-granular bulk copies
 		MC_CUDA(cudaMalloc(&ctx->d_marks, (size_t)n + 64));
 		ctx->aux_capacity = n;
 	}
@@ -261,7 +259,7 @@ static int alloc_hist(mc_ctx *ctx, int64_t n, int k, int tbytes) {
 		ctx->sum_bins = nbins;
 	}
 	ctx->n = n; ctx->k = k; ctx->nbins = nbins; ctx->tbytes = tbytes;
-	MC_CUDA(cudaMemsetAsync(ctx->d_alive, 1, (size_t)n, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(ctx->d_aux, 0, ((size_t)n + 64) * sizeof(McRowAux), ctx->stream));
 	MC_CUDA(cudaMemsetAsync(ctx->d_marks, 0, (size_t)n, ctx->stream));
 	ctx->members_n = 0;
 	return MC_OK;
@@ -308,7 +306,7 @@ extern "C" int mc_load_histograms(mc_ctx *ctx, const void *hists, int tbytes, in
 	if (rc) return rc;
 	const size_t bytes = (size_t)n * ctx->nbins * tbytes;
 	MC_CUDA(cudaMemcpyAsync(ctx->d_hist, hists, bytes, cudaMemcpyHostToDevice, ctx->stream));
-	MC_CUDA(cudaMemcpyAsync(ctx->d_len, lens, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpy2DAsync(&ctx->d_aux[0].len, sizeof(McRowAux), lens, 8, 8, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
 	rc = mc_launch_point_stats(ctx);
 	if (rc) return rc;
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -328,9 +326,10 @@ extern "C" int mc_copy_point_stats(mc_ctx *ctx, uint64_t *len, uint64_t *mag, ui
 	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
 	MC_REQUIRE(ctx->have_hist, MC_ERR_STATE, "no histograms");
 	const size_t b = (size_t)ctx->n * 8;
-	if (len) MC_CUDA(cudaMemcpyAsync(len, ctx->d_len, b, cudaMemcpyDeviceToHost, ctx->stream));
-	if (mag) MC_CUDA(cudaMemcpyAsync(mag, ctx->d_mag, b, cudaMemcpyDeviceToHost, ctx->stream));
-	if (sumsq) MC_CUDA(cudaMemcpyAsync(sumsq, ctx->d_sq, b, cudaMemcpyDeviceToHost, ctx->stream));
+	(void)b;
+	if (len) MC_CUDA(cudaMemcpy2DAsync(len, 8, &ctx->d_aux[0].len, sizeof(McRowAux), 8, (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+	if (mag) MC_CUDA(cudaMemcpy2DAsync(mag, 8, &ctx->d_aux[0].mag, sizeof(McRowAux), 8, (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+	if (sumsq) MC_CUDA(cudaMemcpy2DAsync(sumsq, 8, &ctx->d_aux[0].sq, sizeof(McRowAux), 8, (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	return MC_OK;
 }
@@ -438,7 +437,8 @@ extern "C" int mc_pair_classify(mc_ctx *ctx, const int32_t *a, const int32_t *b,
 
 extern "C" int mc_alive_reset(mc_ctx *ctx) {
 	MC_NEED_HIST(ctx);
-	MC_CUDA(cudaMemsetAsync(ctx->d_alive, 1, (size_t)ctx->n, ctx->stream));
+	int rc = mc_launch_alive_reset(ctx);
+	if (rc) return rc;
 	MC_CUDA(cudaMemsetAsync(ctx->d_marks, 0, (size_t)ctx->n, ctx->stream));
 	return MC_OK;
 }
@@ -448,7 +448,7 @@ extern "C" int mc_alive_kill(mc_ctx *ctx, const int64_t *rows, int64_t m) {
 	MC_REQUIRE(rows || m == 0, MC_ERR_ARG, "bad arguments");
 	int rc = check_rows64(ctx, rows, m);
 	if (rc) return rc;
-	for (int64_t i = 0; i < m; i++) MC_CUDA(cudaMemsetAsync(ctx->d_alive + rows[i], 0, 1, ctx->stream));
+	for (int64_t i = 0; i < m; i++) MC_CUDA(cudaMemsetAsync(&ctx->d_aux[rows[i]].alive, 0, 4, ctx->stream));
 	return MC_OK;
 }
 

@@ -76,7 +76,7 @@ __device__ __forceinline__ void near_merge(NearPartial &a, const NearPartial &b)
 }
 
 template <int TB>
-__global__ void nearest_kernel(const uint8_t *__restrict__ hist, const uint64_t *__restrict__ mag, int nbins,
+__global__ void nearest_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ aux, int nbins,
                                const int64_t *__restrict__ rows, long long m, const uint8_t *__restrict__ tq,
                                const unsigned long long *__restrict__ magc_p, NearPartial *__restrict__ partials,
                                unsigned int *__restrict__ ticket, long long *__restrict__ out_row,
@@ -91,7 +91,7 @@ __global__ void nearest_kernel(const uint8_t *__restrict__ hist, const uint64_t 
 	for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + wib; i < m; i += nwarps) {
 		const long long row = rows[i];
 		const PairAcc<TB> acc = warp_pair_reduce<TB>(hist + (size_t)row * rb, tq, rb, lane);
-		const uint64_t mp = mag[row];
+		const uint64_t mp = aux[row].mag;
 		const double d = mc_distance_d(acc.summin(mp, magc), mp, magc);
 		NearPartial c; c.pos = i; c.dist = d;
 		near_merge(best, c);   // NaN never replaces (comparisons false), like the reference's `<`
@@ -141,9 +141,9 @@ int mc_launch_mean_nearest(mc_ctx *ctx, const int64_t *new_rows_dev, int64_t m_n
 	if (blocks > (int64_t)ctx->num_sms * 4) blocks = (int64_t)ctx->num_sms * 4;
 	if (blocks < 1) blocks = 1;
 	if (ctx->tbytes == 1)
-		nearest_kernel<1><<<(int)blocks, 256, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->d_mag, nbins, members_dev, m_all, tq_dev, magc_dev, (NearPartial *)partials_dev, ctx->d_ticket + 1, out_row_dev, out_dist_dev);
+		nearest_kernel<1><<<(int)blocks, 256, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->d_aux, nbins, members_dev, m_all, tq_dev, magc_dev, (NearPartial *)partials_dev, ctx->d_ticket + 1, out_row_dev, out_dist_dev);
 	else
-		nearest_kernel<2><<<(int)blocks, 256, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->d_mag, nbins, members_dev, m_all, tq_dev, magc_dev, (NearPartial *)partials_dev, ctx->d_ticket + 1, out_row_dev, out_dist_dev);
+		nearest_kernel<2><<<(int)blocks, 256, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->d_aux, nbins, members_dev, m_all, tq_dev, magc_dev, (NearPartial *)partials_dev, ctx->d_ticket + 1, out_row_dev, out_dist_dev);
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
@@ -156,7 +156,7 @@ constexpr int UPD_THREADS = 256;
 
 template <int TB>
 __global__ void __launch_bounds__(UPD_THREADS)
-update_centers_kernel(const uint8_t *__restrict__ hist, McPointAux aux, int nbins,
+update_centers_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ aux, int nbins,
                       const int64_t *__restrict__ center_rows, const int64_t *__restrict__ cand_rows,
                       const int64_t *__restrict__ cand_begin, const int64_t *__restrict__ cand_end,
                       const int64_t *__restrict__ flag_off, uint8_t *__restrict__ flags, McModel model,
@@ -179,13 +179,13 @@ update_centers_kernel(const uint8_t *__restrict__ hist, McPointAux aux, int nbin
 	__syncthreads();
 
 	// pass 1: Trainer::filter -- keep candidates classified similar to the center
-	const uint64_t lq = aux.len[crow], mq = aux.mag[crow], sq = aux.sq[crow];
+	const uint64_t lq = aux[crow].len, mq = aux[crow].mag, sq = aux[crow].sq;
 	unsigned int kept = 0;
 	for (long long i = wib; i < ncand; i += UPD_THREADS / 32) {
 		const long long row = cand_rows[cb + i];
 		const PairAcc<TB> acc = warp_pair_reduce<TB>(hist + (size_t)row * rb, hist + (size_t)crow * rb, rb, lane);
 		if (lane == 0) {
-			const uint64_t lp = aux.len[row], mp = aux.mag[row], sp = aux.sq[row];
+			const uint64_t lp = aux[row].len, mp = aux[row].mag, sp = aux[row].sq;
 			double cc[5], f[4], sum;
 			mc_raw_features(acc.summin(mp, mq), acc.dot(), lp, mp, sp, lq, mq, sq, nbins, model.nfeat >= 4, cc);
 			mc_eval_model(model, cc, f, sum);
@@ -247,7 +247,7 @@ update_centers_kernel(const uint8_t *__restrict__ hist, McPointAux aux, int nbin
 		if (!fl[i]) continue;
 		const long long row = cand_rows[cb + i];
 		const PairAcc<TB> acc = warp_pair_reduce<TB>(hist + (size_t)row * rb, tq, rb, lane);
-		const uint64_t mp = aux.mag[row];
+		const uint64_t mp = aux[row].mag;
 		NearPartial cnd; cnd.pos = i; cnd.dist = mc_distance_d(acc.summin(mp, magc), mp, magc);
 		near_merge(best, cnd);
 	}
@@ -266,7 +266,7 @@ int mc_launch_update_centers(mc_ctx *ctx, const int64_t *center_rows_dev, int64_
                              long long *next_rows_dev) {
 	const size_t smem = (size_t)ctx->nbins * 4 + (size_t)ctx->nbins * ctx->tbytes + 16;
 	MC_REQUIRE(smem <= 200 * 1024, MC_ERR_UNSUPPORTED, "k too large for the update kernel");
-	McPointAux aux{ctx->d_len, ctx->d_mag, ctx->d_sq};
+	const McRowAux *aux = ctx->d_aux;
 	if (ctx->tbytes == 1) {
 		if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(update_centers_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		update_centers_kernel<1><<<(unsigned)ncenters, UPD_THREADS, smem, ctx->stream>>>((const uint8_t *)ctx->d_hist, aux, ctx->nbins, center_rows_dev, cand_rows_dev, cand_begin_dev, cand_end_dev, flag_off_dev, flags_dev, ctx->model, next_rows_dev);

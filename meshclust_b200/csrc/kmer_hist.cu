@@ -125,8 +125,7 @@ template <int TB>
 __global__ void kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
                                  const int32_t *__restrict__ segs, const int64_t *__restrict__ seg_off,
                                  long long n, int k, uint8_t *__restrict__ hist,
-                                 uint64_t *__restrict__ len_out, uint64_t *__restrict__ mag_out,
-                                 uint64_t *__restrict__ sq_out, unsigned int *__restrict__ flags) {
+                                 McRowAux *__restrict__ aux_out, unsigned int *__restrict__ flags) {
 	extern __shared__ uint32_t tables[];
 	const int nbins = 1 << (2 * k);
 	const uint32_t mask = (uint32_t)nbins - 1u;
@@ -202,9 +201,13 @@ __global__ void kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t 
 			q += __shfl_xor_sync(MC_FULL_MASK, q, o);
 		}
 		if (lane == 0) {
-			len_out[s] = (uint64_t)(b1 - b0);   // ClusterFactory.cpp:1007 set_length(base.length())
-			mag_out[s] = m;
-			sq_out[s] = q;
+			McRowAux a;
+			a.len = (uint64_t)(b1 - b0);   // ClusterFactory.cpp:1007 set_length(base.length())
+			a.mag = m;
+			a.sq = q;
+			a.alive = 1;
+			a.pad = 0;
+			aux_out[s] = a;
 		}
 		__syncwarp();
 	}
@@ -227,10 +230,10 @@ int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes) {
 	if (blocks < 1) blocks = 1;
 	if (tbytes == 1) {
 		if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kmer_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kmer_hist_kernel<1><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_len, ctx->d_mag, ctx->d_sq, ctx->d_flags);
+		kmer_hist_kernel<1><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_flags);
 	} else {
 		if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kmer_hist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kmer_hist_kernel<2><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_len, ctx->d_mag, ctx->d_sq, ctx->d_flags);
+		kmer_hist_kernel<2><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_flags);
 	}
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());

@@ -49,11 +49,14 @@ struct McModel {
 // i.e. exp(-sum) <= 1 + 2^-52 (ties-to-even), i.e. -sum < 1.5 * 2^-52.  NaN is never similar.
 #define MC_SIGMOID_SUM_THRESHOLD (-0x1.8p-52)
 
-// per-point constants next to the histogram
-struct McPointAux {
-	const uint64_t *len;   // sequence length in bases (all characters, Ns included)
-	const uint64_t *mag;   // sum of bins (pseudo-counts included)  DivergencePoint.cpp:97-109
-	const uint64_t *sq;    // sum of squared bins
+// per-point constants next to the histogram: one 32-byte record per row, so a tile of rows needs
+// one bulk copy for the histograms and one for these
+struct __align__(32) McRowAux {
+	uint64_t len;     // sequence length in bases (all characters, Ns included)
+	uint64_t mag;     // sum of bins (pseudo-counts included)  DivergencePoint.cpp:97-109
+	uint64_t sq;      // sum of squared bins
+	uint32_t alive;   // 1 while the row is still in the bvec (not yet assigned to a cluster)
+	uint32_t pad;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -81,12 +84,12 @@ struct mc_ctx {
 	int tbytes = 0;
 	void *d_hist = nullptr;
 	size_t hist_capacity = 0;
-	uint64_t *d_len = nullptr, *d_mag = nullptr, *d_sq = nullptr;
+	McRowAux *d_aux = nullptr;
 	int64_t aux_capacity = 0;
 	bool have_hist = false;
 
-	// alive set / marks (bvec on the device)
-	uint8_t *d_alive = nullptr, *d_marks = nullptr;
+	// marks of the last scan (the alive set lives in McRowAux::alive)
+	uint8_t *d_marks = nullptr;
 
 	// model
 	McModel model{};

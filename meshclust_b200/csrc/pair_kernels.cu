@@ -9,7 +9,7 @@
 // ---------------------------------------------------------------------------------------------
 template <int TB>
 __global__ void point_stats_kernel(const uint8_t *__restrict__ hist, int nbins, int64_t n,
-                                   uint64_t *__restrict__ mag, uint64_t *__restrict__ sq) {
+                                   McRowAux *__restrict__ aux) {
 	const int lane = threadIdx.x & 31;
 	const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -27,7 +27,7 @@ __global__ void point_stats_kernel(const uint8_t *__restrict__ hist, int nbins, 
 			m += __shfl_xor_sync(MC_FULL_MASK, m, o);
 			s += __shfl_xor_sync(MC_FULL_MASK, s, o);
 		}
-		if (lane == 0) { mag[row] = m; sq[row] = s; }
+		if (lane == 0) { aux[row].mag = m; aux[row].sq = s; aux[row].alive = 1; aux[row].pad = 0; }
 	}
 }
 
@@ -37,9 +37,22 @@ int mc_launch_point_stats(mc_ctx *ctx) {
 	if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
 	if (blocks < 1) blocks = 1;
 	if (ctx->tbytes == 1)
-		point_stats_kernel<1><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, ctx->d_mag, ctx->d_sq);
+		point_stats_kernel<1><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, ctx->d_aux);
 	else
-		point_stats_kernel<2><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, ctx->d_mag, ctx->d_sq);
+		point_stats_kernel<2><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, ctx->d_aux);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
+__global__ void alive_reset_kernel(McRowAux *__restrict__ aux, long long n) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) aux[i].alive = 1;
+}
+
+int mc_launch_alive_reset(mc_ctx *ctx) {
+	int64_t blocks = (ctx->n + 255) / 256;
+	if (blocks > (int64_t)ctx->num_sms * 8) blocks = (int64_t)ctx->num_sms * 8;
+	alive_reset_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(ctx->d_aux, ctx->n);
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
@@ -69,7 +82,7 @@ constexpr int SCAN_THREADS = 256;
 
 template <int TB, int RB>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(const uint8_t *__restrict__ hist, McPointAux aux, uint8_t *__restrict__ alive,
+scan_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux,
             uint8_t *__restrict__ marks, long long lo, long long hi, long long center_row,
             McModel model, int remove_marked, ScanPartial *__restrict__ partials,
             unsigned int *__restrict__ ticket, ScanPartial *__restrict__ result) {
@@ -91,7 +104,7 @@ scan_kernel(const uint8_t *__restrict__ hist, McPointAux aux, uint8_t *__restric
 			reinterpret_cast<uint4 *>(cen_smem)[i] = __ldg(reinterpret_cast<const uint4 *>(crow) + i);
 		__syncthreads();
 	}
-	const uint64_t lq = aux.len[center_row], mq = aux.mag[center_row], sq = aux.sq[center_row];
+	const uint64_t lq = aux[center_row].len, mq = aux[center_row].mag, sq = aux[center_row].sq;
 
 	ScanPartial mine;
 	mine.n_eval = 0; mine.n_pos = 0; mine.best_row = -1; mine.best_f0 = -1.0;
@@ -100,7 +113,7 @@ scan_kernel(const uint8_t *__restrict__ hist, McPointAux aux, uint8_t *__restric
 	const long long warp_id = (long long)blockIdx.x * (SCAN_THREADS / 32) + wib;
 	for (long long batch = lo + warp_id * 32; batch <= hi; batch += warps_total * 32) {
 		const long long row_mine = batch + lane;
-		const unsigned alive_mine = (row_mine <= hi) ? alive[row_mine] : 0u;
+		const unsigned alive_mine = (row_mine <= hi) ? aux[row_mine].alive : 0u;
 		const unsigned alive_bits = __ballot_sync(MC_FULL_MASK, alive_mine != 0);
 		if (alive_bits == 0) {
 			if (row_mine <= hi) marks[row_mine] = 0;
@@ -120,7 +133,7 @@ scan_kernel(const uint8_t *__restrict__ hist, McPointAux aux, uint8_t *__restric
 		if (row_mine <= hi) {
 			unsigned flag = 0;
 			if (alive_mine) {
-				const uint64_t lp = aux.len[row_mine], mp = aux.mag[row_mine], sp = aux.sq[row_mine];
+				const uint64_t lp = aux[row_mine].len, mp = aux[row_mine].mag, sp = aux[row_mine].sq;
 				const uint64_t S = tot.summin(mp, mq);
 				double c[5], f[4], sum;
 				mc_raw_features(S, tot.dot(), lp, mp, sp, lq, mq, sq, NB, model.nfeat >= 4, c);
@@ -129,7 +142,7 @@ scan_kernel(const uint8_t *__restrict__ hist, McPointAux aux, uint8_t *__restric
 				mine.n_eval++;
 				mine.n_pos += flag;
 				if (f[0] > mine.best_f0) { mine.best_f0 = f[0]; mine.best_row = row_mine; }
-				if (flag && remove_marked) alive[row_mine] = 0;
+				if (flag && remove_marked) aux[row_mine].alive = 0;
 			}
 			marks[row_mine] = (uint8_t)flag;
 		}
@@ -190,21 +203,20 @@ scan_kernel(const uint8_t *__restrict__ hist, McPointAux aux, uint8_t *__restric
 }
 
 // result_dev: device pointer receiving the ScanPartial (same layout as mc_scan_result)
-int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                   void *partials_dev, void *result_dev) {
+int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                          void *partials_dev, void *result_dev) {
 	const int64_t rows = hi - lo + 1;
 	int64_t blocks = (rows + SCAN_THREADS - 1) / SCAN_THREADS;
 	const int64_t cap = (int64_t)ctx->num_sms * 8;
 	if (blocks > cap) blocks = cap;
 	if (blocks < 1) blocks = 1;
-	McPointAux aux{ctx->d_len, ctx->d_mag, ctx->d_sq};
 #define SCAN_CASE(TBv, RBv)                                                                            \
 	{                                                                                                  \
 		const size_t smem = RowCfg<RBv>::CENTER_IN_REGS ? 0 : (size_t)RBv;                             \
 		if (smem > 48 * 1024)                                                                          \
 			MC_CUDA(cudaFuncSetAttribute(scan_kernel<TBv, RBv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 		scan_kernel<TBv, RBv><<<(int)blocks, SCAN_THREADS, smem, ctx->stream>>>(                       \
-			(const uint8_t *)ctx->d_hist, aux, ctx->d_alive, ctx->d_marks, lo, hi, center_row,         \
+			(const uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_marks, lo, hi, center_row,         \
 			ctx->model, remove_marked, (ScanPartial *)partials_dev, ctx->d_ticket, (ScanPartial *)result_dev); \
 	}
 	MC_DISPATCH_ROW(ctx->tbytes, ctx->nbins, SCAN_CASE);
@@ -222,7 +234,7 @@ int64_t mc_scan_max_blocks(mc_ctx *ctx) { return (int64_t)ctx->num_sms * 8; }
 // ---------------------------------------------------------------------------------------------
 template <int TB, int RB>
 __global__ void __launch_bounds__(SCAN_THREADS)
-dist_keys_kernel(const uint8_t *__restrict__ hist, const uint64_t *__restrict__ mag, long long n,
+dist_keys_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ aux, long long n,
                  const int32_t *__restrict__ center_rows, uint16_t *__restrict__ keys) {
 	using C = RowCfg<RB>;
 	extern __shared__ __align__(16) uint32_t cen_smem[];
@@ -238,7 +250,7 @@ dist_keys_kernel(const uint8_t *__restrict__ hist, const uint64_t *__restrict__ 
 			reinterpret_cast<uint4 *>(cen_smem)[i] = __ldg(reinterpret_cast<const uint4 *>(crow) + i);
 		__syncthreads();
 	}
-	const uint64_t mq = mag[center_row];
+	const uint64_t mq = aux[center_row].mag;
 	uint16_t *out = keys + (size_t)blockIdx.y * n;
 	const long long warps_total = (long long)gridDim.x * (SCAN_THREADS / 32);
 	const long long warp_id = (long long)blockIdx.x * (SCAN_THREADS / 32) + wib;
@@ -253,7 +265,7 @@ dist_keys_kernel(const uint8_t *__restrict__ hist, const uint64_t *__restrict__ 
 		const PairAcc<TB> tot = mc_transpose_reduce<C::LPP>(part, r);
 		const long long row_mine = batch + lane;
 		if (row_mine < n) {
-			const uint64_t mp = mag[row_mine];
+			const uint64_t mp = aux[row_mine].mag;
 			out[row_mine] = (uint16_t)mc_distance_key(tot.summin(mp, mq), mp + mq);
 		}
 	}
@@ -271,7 +283,7 @@ int mc_launch_dist_keys(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint
 		if (smem > 48 * 1024)                                                                          \
 			MC_CUDA(cudaFuncSetAttribute(dist_keys_kernel<TBv, RBv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 		dist_keys_kernel<TBv, RBv><<<grid, SCAN_THREADS, smem, ctx->stream>>>(                          \
-			(const uint8_t *)ctx->d_hist, ctx->d_mag, ctx->n, center_rows_dev, keys_dev);              \
+			(const uint8_t *)ctx->d_hist, ctx->d_aux, ctx->n, center_rows_dev, keys_dev);              \
 	}
 	MC_DISPATCH_ROW(ctx->tbytes, ctx->nbins, KEYS_CASE);
 #undef KEYS_CASE
@@ -284,7 +296,7 @@ int mc_launch_dist_keys(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint
 // pair lists (training feature matrix, normalisation bounds, merge candidates): one warp per pair
 // ---------------------------------------------------------------------------------------------
 template <int TB>
-__global__ void pair_list_kernel(const uint8_t *__restrict__ hist, McPointAux aux, int nbins,
+__global__ void pair_list_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ aux, int nbins,
                                  const int32_t *__restrict__ pa, const int32_t *__restrict__ pb,
                                  long long m, McModel model, double *__restrict__ raw5,
                                  unsigned long long *__restrict__ dist, double *__restrict__ sum_out,
@@ -311,8 +323,8 @@ __global__ void pair_list_kernel(const uint8_t *__restrict__ hist, McPointAux au
 #pragma unroll
 		for (int o = 16; o; o >>= 1) acc.shfl_add_from(acc, o);
 		if (lane == 0) {
-			const uint64_t lp = aux.len[a], mp = aux.mag[a], sp = aux.sq[a];
-			const uint64_t lq = aux.len[b], mq = aux.mag[b], sq = aux.sq[b];
+			const uint64_t lp = aux[a].len, mp = aux[a].mag, sp = aux[a].sq;
+			const uint64_t lq = aux[b].len, mq = aux[b].mag, sq = aux[b].sq;
 			const uint64_t S = acc.summin(mp, mq);
 			double c[5];
 			mc_raw_features(S, acc.dot(), lp, mp, sp, lq, mq, sq, nbins, true, c);
@@ -343,7 +355,7 @@ int mc_launch_pair_list(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_de
 	int64_t blocks = (m * 32 + threads - 1) / threads;
 	if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
 	if (blocks < 1) blocks = 1;
-	McPointAux aux{ctx->d_len, ctx->d_mag, ctx->d_sq};
+	const McRowAux *aux = ctx->d_aux;
 	if (ctx->tbytes == 1)
 		pair_list_kernel<1><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, aux, ctx->nbins, pa_dev, pb_dev, m, ctx->model, raw5_dev, (unsigned long long *)dist_dev, sum_dev, f0_dev, flag_dev, feats_dev);
 	else

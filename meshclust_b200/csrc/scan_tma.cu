@@ -1,0 +1,297 @@
+// K2a, the headline kernel: Trainer::get_close (Trainer.cpp:34-114) + bvec::remove_available
+// (bvec.cpp:290-317) for ONE center against every row of an inclusive row range.
+//
+// HBM-bound streaming kernel, warp-specialised and persistent (one CTA per SM):
+//   * warp 0 = producer: one elected lane feeds a ring of shared-memory stages with 1-D TMA bulk
+//     copies (cp.async.bulk ... mbarrier::complete_tx): per stage one copy of TR contiguous
+//     histogram rows and one of their 32-byte McRowAux records.  The ring is as deep as shared
+//     memory allows (up to ~220 KB in flight per SM), so HBM latency never reaches the math.
+//   * warps 1..NCW = consumers: a warp owns 32 consecutive rows ("super-tile" = 32/TR stages),
+//     reduces them against the center held in registers (VABSDIFF4 / IDP.4A on 16-byte LDS),
+//     transposes the partials so lane l owns row l, and runs the FP64 feature + GLM epilogue on
+//     all 32 lanes; marks, alive flags, count and arg-max follow.
+//   * grid-wide result by per-CTA partials + a last-CTA fold (ticket), re-armed for the next launch.
+// Dead rows are copied too ("dense" mode): the alive flag travels inside McRowAux, so there is no
+// dependent flag load before the row traffic starts.
+#include "pair_core.cuh"
+
+struct ScanPartial {
+	long long n_eval;
+	long long n_pos;
+	long long best_row;
+	double best_f0;
+};
+
+__device__ __forceinline__ void tscan_merge(ScanPartial &a, const ScanPartial &b) {
+	a.n_eval += b.n_eval;
+	a.n_pos += b.n_pos;
+	// first maximum in row order wins (Trainer.cpp:99 strict >, serial iteration order)
+	if (b.best_row >= 0 && (b.best_f0 > a.best_f0 || (b.best_f0 == a.best_f0 && (a.best_row < 0 || b.best_row < a.best_row)))) {
+		a.best_f0 = b.best_f0;
+		a.best_row = b.best_row;
+	}
+}
+
+// ---- mbarrier / TMA bulk-copy PTX --------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- geometry ----------------------------------------------------------------------------------
+constexpr int TSCAN_MAX_CONSUMERS = 16;
+constexpr int TSCAN_THREADS = 32 * (1 + TSCAN_MAX_CONSUMERS);
+constexpr int TSCAN_MAX_STAGES = 32;
+constexpr int TSCAN_SMEM_BUDGET = 216 * 1024;
+
+// A stage holds one consumer tile: RT consecutive rows + their McRowAux records.  RT = 32 (one row
+// per lane in the epilogue) while that fits 32 KB, fewer for very wide rows (lanes >= RT idle in
+// the epilogue, which is cheap next to a multi-KB row).  Every consumer warp owns a private ring
+// of D stages, so a warp never waits on a barrier more than one phase ahead of it.
+template <int RB>
+struct TileCfg {
+	static constexpr int RT = (RB * 32 <= 32 * 1024) ? 32 : ((32 * 1024) / RB > 0 ? (32 * 1024) / RB : 1);
+	static constexpr int ROW_BYTES = RT * RB;
+	static constexpr int AUX_BYTES = RT * 32;
+	static constexpr int STAGE_BYTES = ((ROW_BYTES + AUX_BYTES + 127) / 128) * 128;
+	static constexpr int NS_RAW = TSCAN_SMEM_BUDGET / STAGE_BYTES;
+	static constexpr int NS_CAP = NS_RAW > TSCAN_MAX_STAGES ? TSCAN_MAX_STAGES : NS_RAW;
+	static constexpr int NCW = NS_CAP > TSCAN_MAX_CONSUMERS ? TSCAN_MAX_CONSUMERS : NS_CAP;   // active consumer warps
+	static constexpr int D = NS_CAP / NCW;                                                   // ring depth per consumer
+	static constexpr int NS = NCW * D;
+	static_assert(NS_CAP >= 2, "row too wide for the staged scan");
+};
+
+template <int TB, int RB>
+__global__ void __launch_bounds__(32 * (1 + TileCfg<RB>::NCW), 1)
+scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, uint8_t *__restrict__ marks,
+                long long lo, long long hi, long long center_row, McModel model, int remove_marked,
+                ScanPartial *__restrict__ partials, unsigned int *__restrict__ ticket,
+                ScanPartial *__restrict__ result) {
+	using C = RowCfg<RB>;
+	using T = TileCfg<RB>;
+	constexpr int NB = RB / TB;
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ __align__(8) uint64_t full_bar[TSCAN_MAX_STAGES];
+	__shared__ __align__(8) uint64_t empty_bar[TSCAN_MAX_STAGES];
+	__shared__ ScanPartial warp_part[TSCAN_MAX_CONSUMERS];
+	__shared__ bool is_last;
+
+	const int lane = threadIdx.x & 31;
+	const int wib = threadIdx.x >> 5;
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < T::NS; s++) {
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncthreads();
+
+	// tiles of RT rows, dealt round-robin to CTAs, then round-robin to the CTA's consumer warps
+	const long long nrows = hi - lo + 1;
+	const long long ntiles = (nrows + T::RT - 1) / T::RT;
+	const long long my_first = blockIdx.x;
+	const long long nmine = my_first < ntiles ? (ntiles - my_first + gridDim.x - 1) / gridDim.x : 0;
+
+	ScanPartial mine;
+	mine.n_eval = 0; mine.n_pos = 0; mine.best_row = -1; mine.best_f0 = -1.0;
+
+	if (wib == 0) {
+		// ===================== producer =====================
+		if (lane == 0) {
+			for (long long jj = 0; jj < nmine; jj++) {
+				const int w = (int)(jj % T::NCW);
+				const long long u = jj / T::NCW;              // u-th tile of consumer w
+				const int slot = w * T::D + (int)(u % T::D);
+				const long long round = u / T::D;
+				if (round > 0) mbar_wait(&empty_bar[slot], (uint32_t)(round - 1) & 1);
+				const long long r0 = lo + (my_first + jj * gridDim.x) * T::RT;
+				long long nr = hi - r0 + 1;
+				if (nr > T::RT) nr = T::RT;
+				uint8_t *dst = smem + (size_t)slot * T::STAGE_BYTES;
+				mbar_expect_tx(&full_bar[slot], (uint32_t)(nr * RB + nr * 32));
+				tma_bulk_g2s(dst, hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[slot]);
+				tma_bulk_g2s(dst + T::ROW_BYTES, aux + r0, (uint32_t)(nr * 32), &full_bar[slot]);
+			}
+		}
+	} else if (wib - 1 < T::NCW) {
+		// ===================== consumers =====================
+		const int cw = wib - 1;
+		const int g = lane / C::LPP, r = lane % C::LPP;
+		const uint8_t *crow = hist + (size_t)center_row * RB;
+		CenterRegs<RB> cen;
+		cen.load(crow, r);
+		const uint64_t lq = aux[center_row].len, mq = aux[center_row].mag, sq = aux[center_row].sq;
+
+		long long u = 0;
+		for (long long jj = cw; jj < nmine; jj += T::NCW, u++) {
+			const long long row0 = lo + (my_first + jj * gridDim.x) * T::RT;
+			const long long row_mine = row0 + lane;
+			const bool have_row = lane < T::RT && row_mine <= hi;
+			const int slot = cw * T::D + (int)(u % T::D);
+			mbar_wait(&full_bar[slot], (uint32_t)(u / T::D) & 1);
+			const uint8_t *st = smem + (size_t)slot * T::STAGE_BYTES;
+			McRowAux my_aux;
+			my_aux.len = 0; my_aux.mag = 0; my_aux.sq = 0; my_aux.alive = 0; my_aux.pad = 0;
+			if (have_row) my_aux = *reinterpret_cast<const McRowAux *>(st + T::ROW_BYTES + (size_t)lane * 32);
+			// row p of the tile is reduced by lane group p / LPP in iteration p % LPP
+			PairAcc<TB> part[C::LPP];
+#pragma unroll
+			for (int it = 0; it < C::LPP; it++) {
+				const int p = g * C::LPP + it;
+				PairAcc<TB> acc;
+				if (p < T::RT && row0 + p <= hi) {
+					const uint8_t *row = st + (size_t)p * RB;
+#pragma unroll
+					for (int c = 0; c < C::CH; c++) {
+						const uint4 v = *reinterpret_cast<const uint4 *>(row + (size_t)(c * C::LPP + r) * 16);
+						acc.add(v.x, cen.w[c][0]); acc.add(v.y, cen.w[c][1]);
+						acc.add(v.z, cen.w[c][2]); acc.add(v.w, cen.w[c][3]);
+					}
+				}
+				part[it] = acc;
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty_bar[slot]);   // the stage can be refilled during the epilogue
+			const PairAcc<TB> tot = mc_transpose_reduce<C::LPP>(part, r);
+			if (have_row) {
+				unsigned flag = 0;
+				if (my_aux.alive) {
+					const uint64_t S = tot.summin(my_aux.mag, mq);
+					double c[5], f[4], sum;
+					mc_raw_features(S, tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, model.nfeat >= 4, c);
+					mc_eval_model(model, c, f, sum);
+					flag = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1u : 0u;
+					mine.n_eval++;
+					mine.n_pos += flag;
+					if (f[0] > mine.best_f0) { mine.best_f0 = f[0]; mine.best_row = row_mine; }
+					if (flag && remove_marked) aux[row_mine].alive = 0;
+				}
+				marks[row_mine] = (uint8_t)flag;
+			}
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) {
+			ScanPartial other;
+			other.n_eval = __shfl_xor_sync(MC_FULL_MASK, mine.n_eval, o);
+			other.n_pos = __shfl_xor_sync(MC_FULL_MASK, mine.n_pos, o);
+			other.best_row = __shfl_xor_sync(MC_FULL_MASK, mine.best_row, o);
+			other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, mine.best_f0, o);
+			tscan_merge(mine, other);
+		}
+		if (lane == 0) warp_part[cw] = mine;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		ScanPartial b = warp_part[0];
+		for (int w = 1; w < T::NCW; w++) tscan_merge(b, warp_part[w]);
+		partials[blockIdx.x] = b;
+		__threadfence();
+		is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (is_last && wib == 0) {
+		__threadfence();
+		ScanPartial b;
+		b.n_eval = 0; b.n_pos = 0; b.best_row = -1; b.best_f0 = -1.0;
+		for (int i = lane; i < (int)gridDim.x; i += 32) {
+			ScanPartial p;   // L2 loads: written by other SMs
+			p.n_eval = __ldcg(&partials[i].n_eval);
+			p.n_pos = __ldcg(&partials[i].n_pos);
+			p.best_row = __ldcg(&partials[i].best_row);
+			p.best_f0 = __ldcg(&partials[i].best_f0);
+			tscan_merge(b, p);
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) {
+			ScanPartial other;
+			other.n_eval = __shfl_xor_sync(MC_FULL_MASK, b.n_eval, o);
+			other.n_pos = __shfl_xor_sync(MC_FULL_MASK, b.n_pos, o);
+			other.best_row = __shfl_xor_sync(MC_FULL_MASK, b.best_row, o);
+			other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, b.best_f0, o);
+			tscan_merge(b, other);
+		}
+		if (lane == 0) {
+			*result = b;
+			*ticket = 0;   // re-arm for the next launch on this stream
+		}
+	}
+}
+
+// rows narrower than 16 bytes (k = 1) and rows too wide for two stages keep the direct-load kernel
+int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                          void *partials_dev, void *result_dev);
+
+template <int TB, int RB>
+static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                      void *partials_dev, void *result_dev) {
+	using T = TileCfg<RB>;
+	const size_t smem = (size_t)T::NS * T::STAGE_BYTES;
+	static bool attr_set = false;
+	if (!attr_set) {
+		MC_CUDA(cudaFuncSetAttribute(scan_tma_kernel<TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
+	const int64_t ntiles = (hi - lo + 1 + T::RT - 1) / T::RT;
+	int64_t blocks = ctx->num_sms;
+	if (blocks > ntiles) blocks = ntiles;
+	if (blocks < 1) blocks = 1;
+	scan_tma_kernel<TB, RB><<<(int)blocks, 32 * (1 + T::NCW), smem, ctx->stream>>>(
+		(const uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_marks, lo, hi, center_row, ctx->model, remove_marked,
+		(ScanPartial *)partials_dev, ctx->d_ticket, (ScanPartial *)result_dev);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
+int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                   void *partials_dev, void *result_dev) {
+	static const bool legacy = getenv("MC_SCAN_DIRECT") != nullptr;
+	const int rb = ctx->tbytes * ctx->nbins;
+	if (!legacy) {
+		if (ctx->tbytes == 1) {
+			switch (rb) {
+			case 16: return launch_tma<1, 16>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			case 64: return launch_tma<1, 64>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			case 256: return launch_tma<1, 256>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			case 1024: return launch_tma<1, 1024>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			case 4096: return launch_tma<1, 4096>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			default: break;
+			}
+		} else {
+			switch (rb) {
+			case 32: return launch_tma<2, 32>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			case 128: return launch_tma<2, 128>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			case 512: return launch_tma<2, 512>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			case 2048: return launch_tma<2, 2048>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			default: break;
+			}
+		}
+	}
+	return mc_launch_scan_direct(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+}

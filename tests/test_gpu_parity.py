@@ -221,8 +221,11 @@ def test_scan_first_max_wins_and_null(ctx, oracle):
     ctx.load_histograms(H, lens2, 4)
     ctx.set_model(mins, maxs, w, 3)
     ctx.alive_kill(np.array([5]))
+    ws, wf0, wfl = oracle.scan(H, lens2, H[5], 100000, mins, maxs, w, 3)
+    assert wf0[np.arange(n) != 5].max() <= -1
     res, _ = ctx.scan(5, 0, n - 1)
-    assert res.best_row == -1 and res.best_f0 == -1.0 and res.n_pos == 0
+    assert res.best_row == -1 and res.best_f0 == -1.0
+    assert res.n_pos == int(wfl.sum()) - int(wfl[5])
     # empty range
     res, _ = ctx.scan(5, 10, 9)
     assert res.as_tuple() == (0, 0, -1, -1.0)
