@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmeshclust_b200.so")
+# MESHCLUST_B200_LIB selects another BUILD of the same CUDA library (e.g. an instrumented one)
+LIB_PATH = os.environ.get("MESHCLUST_B200_LIB") or os.path.join(_PKG, "libmeshclust_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

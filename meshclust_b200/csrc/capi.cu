@@ -13,7 +13,7 @@ int mc_launch_encode(mc_ctx *ctx);
 int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes);
 int mc_launch_point_stats(mc_ctx *ctx);
 int mc_launch_alive_reset(mc_ctx *ctx);
-int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, void *partials_dev, void *result_dev);
+int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, void *partials_dev, int *nparts_out);
 int64_t mc_scan_max_blocks(mc_ctx *ctx);
 int mc_launch_dist_keys(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint16_t *keys_dev);
 int mc_launch_pair_list(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, double *raw5_dev, uint64_t *dist_dev, double *sum_dev, double *f0_dev, uint8_t *flag_dev, double *feats_dev);
@@ -435,6 +435,30 @@ extern "C" int mc_pair_classify(mc_ctx *ctx, const int32_t *a, const int32_t *b,
 	return pair_list_common(ctx, a, b, m, nullptr, nullptr, sum_out, f0_out, flag_out, feats_out);
 }
 
+// the fold the scan kernels leave to the reader: same rule as in the kernels (first maximum in
+// row order wins, Trainer.cpp:99)
+static void fold_partials(const mc_scan_result *p, int np, mc_scan_result *out) {
+	mc_scan_result r;
+	r.n_eval = 0; r.n_pos = 0; r.best_row = -1; r.best_f0 = -1.0;
+	for (int i = 0; i < np; i++) {
+		r.n_eval += p[i].n_eval;
+		r.n_pos += p[i].n_pos;
+		if (p[i].best_row >= 0 && (p[i].best_f0 > r.best_f0 || (p[i].best_f0 == r.best_f0 && (r.best_row < 0 || p[i].best_row < r.best_row)))) {
+			r.best_f0 = p[i].best_f0;
+			r.best_row = p[i].best_row;
+		}
+	}
+	*out = r;
+}
+
+static int ensure_scan_slots(mc_ctx *ctx) {
+	if (ctx->d_scan_slots) return MC_OK;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	MC_CUDA(cudaMalloc(&ctx->d_scan_slots, (size_t)MC_SCAN_SLOTS * MC_SCAN_PARTS * sizeof(mc_scan_result)));
+	for (int i = 0; i < MC_SCAN_SLOTS; i++) ctx->slot_nparts[i] = 0;
+	return MC_OK;
+}
+
 extern "C" int mc_alive_reset(mc_ctx *ctx) {
 	MC_NEED_HIST(ctx);
 	int rc = mc_launch_alive_reset(ctx);
@@ -463,18 +487,19 @@ extern "C" int mc_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, 
 		res->n_eval = 0; res->n_pos = 0; res->best_row = -1; res->best_f0 = -1.0;
 		return MC_OK;
 	}
-	const size_t nblk = (size_t)mc_scan_max_blocks(ctx);
-	int rc = mc_ensure_scratch(ctx, Carve::need({nblk * 32, 64}));
+	int rc = mc_ensure_scratch(ctx, Carve::need({(size_t)MC_SCAN_PARTS * 32}));
+	if (rc) return rc;
+	rc = mc_ensure_pinned(ctx, (size_t)MC_SCAN_PARTS * 32);
 	if (rc) return rc;
 	Carve cv(ctx->d_scratch);
-	void *d_part = cv.take<uint8_t>(nblk * 32);
-	void *d_res = cv.take<uint8_t>(64);
-	rc = mc_launch_scan(ctx, center_row, lo, hi, 1, d_part, d_res);
+	void *d_part = cv.take<uint8_t>((size_t)MC_SCAN_PARTS * 32);
+	int nparts = 0;
+	rc = mc_launch_scan(ctx, center_row, lo, hi, 1, d_part, &nparts);
 	if (rc) return rc;
-	MC_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_res, sizeof(mc_scan_result), cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_part, (size_t)nparts * sizeof(mc_scan_result), cudaMemcpyDeviceToHost, ctx->stream));
 	if (marks_out) MC_CUDA(cudaMemcpyAsync(marks_out, ctx->d_marks + lo, (size_t)(hi - lo + 1), cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
-	memcpy(res, ctx->h_pinned, sizeof(mc_scan_result));
+	fold_partials((const mc_scan_result *)ctx->h_pinned, nparts, res);
 	return MC_OK;
 }
 
@@ -484,13 +509,10 @@ extern "C" int mc_scan_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int6
 	MC_REQUIRE(slot >= 0 && slot < MC_SCAN_SLOTS, MC_ERR_ARG, "slot %d out of range", slot);
 	MC_REQUIRE(center_row >= 0 && center_row < ctx->n, MC_ERR_ARG, "center row out of range");
 	MC_REQUIRE(lo >= 0 && hi < ctx->n && lo <= hi, MC_ERR_ARG, "scan range [%lld,%lld] invalid", (long long)lo, (long long)hi);
-	if (!ctx->d_scan_slots) {
-		MC_CUDA(cudaSetDevice(ctx->device));
-		MC_CUDA(cudaMalloc(&ctx->d_scan_slots, (size_t)MC_SCAN_SLOTS * sizeof(mc_scan_result)));
-		MC_CUDA(cudaMalloc(&ctx->d_scan_partials, (size_t)mc_scan_max_blocks(ctx) * 32));
-	}
-	return mc_launch_scan(ctx, center_row, lo, hi, remove_marked, ctx->d_scan_partials,
-	                      (uint8_t *)ctx->d_scan_slots + (size_t)slot * sizeof(mc_scan_result));
+	int rc = ensure_scan_slots(ctx);
+	if (rc) return rc;
+	return mc_launch_scan(ctx, center_row, lo, hi, remove_marked,
+	                      (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result), &ctx->slot_nparts[slot]);
 }
 
 extern "C" int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo, const int64_t *hi,
@@ -507,9 +529,14 @@ extern "C" int mc_scan_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_resul
 	MC_REQUIRE(ctx && res, MC_ERR_ARG, "bad arguments");
 	MC_REQUIRE(slot0 >= 0 && nslots > 0 && slot0 + nslots <= MC_SCAN_SLOTS, MC_ERR_ARG, "slot range invalid");
 	MC_REQUIRE(ctx->d_scan_slots, MC_ERR_STATE, "nothing was enqueued");
-	MC_CUDA(cudaMemcpyAsync(res, (uint8_t *)ctx->d_scan_slots + (size_t)slot0 * sizeof(mc_scan_result),
-	                        (size_t)nslots * sizeof(mc_scan_result), cudaMemcpyDeviceToHost, ctx->stream));
+	const size_t slot_bytes = (size_t)MC_SCAN_PARTS * sizeof(mc_scan_result);
+	int rc = mc_ensure_pinned(ctx, (size_t)nslots * slot_bytes);
+	if (rc) return rc;
+	MC_CUDA(cudaMemcpyAsync(ctx->h_pinned, (uint8_t *)ctx->d_scan_slots + (size_t)slot0 * slot_bytes, (size_t)nslots * slot_bytes,
+	                        cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	for (int i = 0; i < nslots; i++)
+		fold_partials((const mc_scan_result *)((uint8_t *)ctx->h_pinned + (size_t)i * slot_bytes), ctx->slot_nparts[slot0 + i], &res[i]);
 	return MC_OK;
 }
 
@@ -672,18 +699,14 @@ extern "C" int mc_scan_host(mc_ctx *ctx, const void *hists, int tbytes, int k, c
 	if (rc) return rc;
 	rc = check_rows64(ctx, center_rows, ncenters);
 	if (rc) return rc;
-	const size_t nblk = (size_t)mc_scan_max_blocks(ctx);
-	rc = mc_ensure_scratch(ctx, Carve::need({nblk * 32, (size_t)ncenters * 32}));
+	MC_REQUIRE(ncenters <= MC_SCAN_SLOTS, MC_ERR_ARG, "at most %d centers per call", MC_SCAN_SLOTS);
+	rc = ensure_scan_slots(ctx);
 	if (rc) return rc;
-	Carve cv(ctx->d_scratch);
-	void *d_part = cv.take<uint8_t>(nblk * 32);
-	uint8_t *d_res = cv.take<uint8_t>((size_t)ncenters * 32);
+	const size_t slot_bytes = (size_t)MC_SCAN_PARTS * sizeof(mc_scan_result);
 	for (int c = 0; c < ncenters; c++) {
-		rc = mc_launch_scan(ctx, center_rows[c], 0, n - 1, 0, d_part, d_res + (size_t)c * 32);
+		rc = mc_launch_scan(ctx, center_rows[c], 0, n - 1, 0, (uint8_t *)ctx->d_scan_slots + (size_t)c * slot_bytes, &ctx->slot_nparts[c]);
 		if (rc) return rc;
 		if (marks_out) MC_CUDA(cudaMemcpyAsync(marks_out + (size_t)c * n, ctx->d_marks, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
 	}
-	MC_CUDA(cudaMemcpyAsync(res, d_res, (size_t)ncenters * 32, cudaMemcpyDeviceToHost, ctx->stream));
-	MC_CUDA(cudaStreamSynchronize(ctx->stream));
-	return MC_OK;
+	return mc_scan_collect(ctx, 0, ncenters, res);
 }

@@ -10,6 +10,7 @@
 
 #define MC_NUM_SMS_FALLBACK 148
 #define MC_FULL_MASK 0xffffffffu
+#define MC_SCAN_PARTS 160   // per-scan partial records (>= SM count)
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing (no exceptions across the C-ABI)
@@ -103,8 +104,9 @@ struct mc_ctx {
 	unsigned int *d_flags = nullptr;    // [0] invalid-input flag, [1] max count, ...
 
 	// result slots of mc_scan_enqueue + per-launch block partials
-	void *d_scan_slots = nullptr;
-	void *d_scan_partials = nullptr;
+	void *d_scan_slots = nullptr;      // MC_SCAN_SLOTS x MC_SCAN_PARTS partial records
+	void *d_scan_partials = nullptr;   // block partials of the direct-load kernel
+	int slot_nparts[MC_SCAN_SLOTS];
 
 	// mean-shift member list (Phase A)
 	int64_t *d_members = nullptr;

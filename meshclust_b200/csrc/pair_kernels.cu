@@ -202,9 +202,16 @@ scan_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux,
 	}
 }
 
-// result_dev: device pointer receiving the ScanPartial (same layout as mc_scan_result)
+int64_t mc_scan_max_blocks(mc_ctx *ctx);
+
+// direct-load variant (rows narrower than 16 bytes, very wide rows, MC_SCAN_DIRECT=1): folds on the
+// device, so it reports a single partial in partials_dev[0]; block partials go to a context buffer
 int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                          void *partials_dev, void *result_dev) {
+                          void *partials_dev, int *nparts_out) {
+	if (!ctx->d_scan_partials) MC_CUDA(cudaMalloc(&ctx->d_scan_partials, (size_t)mc_scan_max_blocks(ctx) * 32));
+	void *result_dev = partials_dev;
+	partials_dev = ctx->d_scan_partials;
+	*nparts_out = 1;
 	const int64_t rows = hi - lo + 1;
 	int64_t blocks = (rows + SCAN_THREADS - 1) / SCAN_THREADS;
 	const int64_t cap = (int64_t)ctx->num_sms * 8;

@@ -10,7 +10,9 @@
 //     reduces them against the center held in registers (VABSDIFF4 / IDP.4A on 16-byte LDS),
 //     transposes the partials so lane l owns row l, and runs the FP64 feature + GLM epilogue on
 //     all 32 lanes; marks, alive flags, count and arg-max follow.
-//   * grid-wide result by per-CTA partials + a last-CTA fold (ticket), re-armed for the next launch.
+//   * every CTA leaves one partial (count, positives, arg-max); the <= 148-entry fold is done by the
+//     reader of the result (host), which keeps a threadfence + atomic ticket + last-CTA pass out
+//     of a kernel whose whole body is a few microseconds.
 // Dead rows are copied too ("dense" mode): the alive flag travels inside McRowAux, so there is no
 // dependent flag load before the row traffic starts.
 #include "pair_core.cuh"
@@ -62,7 +64,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 
 // ---- geometry ----------------------------------------------------------------------------------
 constexpr int TSCAN_MAX_CONSUMERS = 16;
-constexpr int TSCAN_THREADS = 32 * (1 + TSCAN_MAX_CONSUMERS);
 constexpr int TSCAN_MAX_STAGES = 32;
 constexpr int TSCAN_SMEM_BUDGET = 216 * 1024;
 
@@ -84,12 +85,18 @@ struct TileCfg {
 	static_assert(NS_CAP >= 2, "row too wide for the staged scan");
 };
 
+#ifdef MC_SCAN_TRACE
+__device__ unsigned long long g_scan_trace[148 * 32 * 8];
+#define TRACE(slot) do { if (lane == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_scan_trace[(blockIdx.x * 32 + wib) * 8 + (slot)] = _t; } } while (0)
+#else
+#define TRACE(slot) do {} while (0)
+#endif
+
 template <int TB, int RB>
 __global__ void __launch_bounds__(32 * (1 + TileCfg<RB>::NCW), 1)
 scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, uint8_t *__restrict__ marks,
                 long long lo, long long hi, long long center_row, McModel model, int remove_marked,
-                ScanPartial *__restrict__ partials, unsigned int *__restrict__ ticket,
-                ScanPartial *__restrict__ result) {
+                ScanPartial *__restrict__ partials) {
 	using C = RowCfg<RB>;
 	using T = TileCfg<RB>;
 	constexpr int NB = RB / TB;
@@ -97,10 +104,10 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 	__shared__ __align__(8) uint64_t full_bar[TSCAN_MAX_STAGES];
 	__shared__ __align__(8) uint64_t empty_bar[TSCAN_MAX_STAGES];
 	__shared__ ScanPartial warp_part[TSCAN_MAX_CONSUMERS];
-	__shared__ bool is_last;
 
 	const int lane = threadIdx.x & 31;
 	const int wib = threadIdx.x >> 5;
+	TRACE(0);
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < T::NS; s++) {
@@ -111,6 +118,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();
+	TRACE(1);
 
 	// tiles of RT rows, dealt round-robin to CTAs, then round-robin to the CTA's consumer warps
 	const long long nrows = hi - lo + 1;
@@ -123,21 +131,21 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 
 	if (wib == 0) {
 		// ===================== producer =====================
-		if (lane == 0) {
-			for (long long jj = 0; jj < nmine; jj++) {
-				const int w = (int)(jj % T::NCW);
-				const long long u = jj / T::NCW;              // u-th tile of consumer w
-				const int slot = w * T::D + (int)(u % T::D);
-				const long long round = u / T::D;
-				if (round > 0) mbar_wait(&empty_bar[slot], (uint32_t)(round - 1) & 1);
-				const long long r0 = lo + (my_first + jj * gridDim.x) * T::RT;
-				long long nr = hi - r0 + 1;
-				if (nr > T::RT) nr = T::RT;
-				uint8_t *dst = smem + (size_t)slot * T::STAGE_BYTES;
-				mbar_expect_tx(&full_bar[slot], (uint32_t)(nr * RB + nr * 32));
-				tma_bulk_g2s(dst, hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[slot]);
-				tma_bulk_g2s(dst + T::ROW_BYTES, aux + r0, (uint32_t)(nr * 32), &full_bar[slot]);
-			}
+		// lane l issues the bulk copies of tiles jj = l, l+32, ...: a slot is only ever touched by
+		// the one lane whose jj maps to it in a given round, and issue cost is spread over the warp
+		for (long long jj = lane; jj < nmine; jj += 32) {
+			const int w = (int)(jj % T::NCW);
+			const long long u = jj / T::NCW;              // u-th tile of consumer w
+			const int slot = w * T::D + (int)(u % T::D);
+			const long long round = u / T::D;
+			if (round > 0) mbar_wait(&empty_bar[slot], (uint32_t)(round - 1) & 1);
+			const long long r0 = lo + (my_first + jj * gridDim.x) * T::RT;
+			long long nr = hi - r0 + 1;
+			if (nr > T::RT) nr = T::RT;
+			uint8_t *dst = smem + (size_t)slot * T::STAGE_BYTES;
+			mbar_expect_tx(&full_bar[slot], (uint32_t)(nr * RB + nr * 32));
+			tma_bulk_g2s(dst, hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[slot]);
+			tma_bulk_g2s(dst + T::ROW_BYTES, aux + r0, (uint32_t)(nr * 32), &full_bar[slot]);
 		}
 	} else if (wib - 1 < T::NCW) {
 		// ===================== consumers =====================
@@ -154,7 +162,9 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			const long long row_mine = row0 + lane;
 			const bool have_row = lane < T::RT && row_mine <= hi;
 			const int slot = cw * T::D + (int)(u % T::D);
+			if (u == 0) TRACE(2);
 			mbar_wait(&full_bar[slot], (uint32_t)(u / T::D) & 1);
+			if (u == 0) TRACE(3);
 			const uint8_t *st = smem + (size_t)slot * T::STAGE_BYTES;
 			McRowAux my_aux;
 			my_aux.len = 0; my_aux.mag = 0; my_aux.sq = 0; my_aux.alive = 0; my_aux.pad = 0;
@@ -179,6 +189,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&empty_bar[slot]);   // the stage can be refilled during the epilogue
 			const PairAcc<TB> tot = mc_transpose_reduce<C::LPP>(part, r);
+			if (u == 0) TRACE(4);
 			if (have_row) {
 				unsigned flag = 0;
 				if (my_aux.alive) {
@@ -205,28 +216,15 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			tscan_merge(mine, other);
 		}
 		if (lane == 0) warp_part[cw] = mine;
+		TRACE(5);
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		ScanPartial b = warp_part[0];
-		for (int w = 1; w < T::NCW; w++) tscan_merge(b, warp_part[w]);
-		partials[blockIdx.x] = b;
-		__threadfence();
-		is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-	}
-	__syncthreads();
-	if (is_last && wib == 0) {
-		__threadfence();
+	TRACE(6);
+	// per-CTA partial; the (tiny) fold over <= 148 partials is left to whoever reads the result
+	if (wib == 0) {
 		ScanPartial b;
 		b.n_eval = 0; b.n_pos = 0; b.best_row = -1; b.best_f0 = -1.0;
-		for (int i = lane; i < (int)gridDim.x; i += 32) {
-			ScanPartial p;   // L2 loads: written by other SMs
-			p.n_eval = __ldcg(&partials[i].n_eval);
-			p.n_pos = __ldcg(&partials[i].n_pos);
-			p.best_row = __ldcg(&partials[i].best_row);
-			p.best_f0 = __ldcg(&partials[i].best_f0);
-			tscan_merge(b, p);
-		}
+		if (lane < T::NCW) b = warp_part[lane];
 #pragma unroll
 		for (int o = 16; o; o >>= 1) {
 			ScanPartial other;
@@ -236,20 +234,24 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, b.best_f0, o);
 			tscan_merge(b, other);
 		}
-		if (lane == 0) {
-			*result = b;
-			*ticket = 0;   // re-arm for the next launch on this stream
-		}
+		if (lane == 0) partials[blockIdx.x] = b;
+		TRACE(7);
 	}
 }
 
+#ifdef MC_SCAN_TRACE
+extern "C" int mc_debug_scan_trace(unsigned long long *out) {
+	return cudaMemcpyFromSymbol(out, g_scan_trace, sizeof(g_scan_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 // rows narrower than 16 bytes (k = 1) and rows too wide for two stages keep the direct-load kernel
 int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                          void *partials_dev, void *result_dev);
+                          void *partials_dev, int *nparts_out);
 
 template <int TB, int RB>
 static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                      void *partials_dev, void *result_dev) {
+                      void *partials_dev, int *nparts_out) {
 	using T = TileCfg<RB>;
 	const size_t smem = (size_t)T::NS * T::STAGE_BYTES;
 	static bool attr_set = false;
@@ -263,35 +265,37 @@ static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, i
 	if (blocks < 1) blocks = 1;
 	scan_tma_kernel<TB, RB><<<(int)blocks, 32 * (1 + T::NCW), smem, ctx->stream>>>(
 		(const uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_marks, lo, hi, center_row, ctx->model, remove_marked,
-		(ScanPartial *)partials_dev, ctx->d_ticket, (ScanPartial *)result_dev);
+		(ScanPartial *)partials_dev);
+	*nparts_out = (int)blocks;
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
 }
 
+// partials_dev must hold MC_SCAN_PARTS entries of 32 bytes; *nparts_out says how many were written
 int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                   void *partials_dev, void *result_dev) {
+                   void *partials_dev, int *nparts_out) {
 	static const bool legacy = getenv("MC_SCAN_DIRECT") != nullptr;
 	const int rb = ctx->tbytes * ctx->nbins;
 	if (!legacy) {
 		if (ctx->tbytes == 1) {
 			switch (rb) {
-			case 16: return launch_tma<1, 16>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
-			case 64: return launch_tma<1, 64>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
-			case 256: return launch_tma<1, 256>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
-			case 1024: return launch_tma<1, 1024>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
-			case 4096: return launch_tma<1, 4096>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			case 16: return launch_tma<1, 16>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+			case 64: return launch_tma<1, 64>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+			case 256: return launch_tma<1, 256>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+			case 1024: return launch_tma<1, 1024>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+			case 4096: return launch_tma<1, 4096>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
 			default: break;
 			}
 		} else {
 			switch (rb) {
-			case 32: return launch_tma<2, 32>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
-			case 128: return launch_tma<2, 128>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
-			case 512: return launch_tma<2, 512>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
-			case 2048: return launch_tma<2, 2048>(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+			case 32: return launch_tma<2, 32>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+			case 128: return launch_tma<2, 128>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+			case 512: return launch_tma<2, 512>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+			case 2048: return launch_tma<2, 2048>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
 			default: break;
 			}
 		}
 	}
-	return mc_launch_scan_direct(ctx, center_row, lo, hi, remove_marked, partials_dev, result_dev);
+	return mc_launch_scan_direct(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
 }

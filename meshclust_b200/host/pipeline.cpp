@@ -1,0 +1,783 @@
+// Host control flow of bin/meshclust.  Mirrors, step by step, what the reference does between its
+// hot loops (citations inline); every hot loop is a call into the C-ABI of include/meshclust_b200.h.
+// Compiled with -ffp-contract=off; see matrix.hpp for the two places the reference binary fuses.
+#include "pipeline.hpp"
+
+#include <libgen.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <stdexcept>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "bvec.hpp"
+#include "fasta.hpp"
+#include "matrix.hpp"
+#include "meshclust_b200.h"
+
+namespace mch {
+
+namespace {
+
+struct Timer {
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	double lap() {
+		auto t1 = std::chrono::steady_clock::now();
+		double s = std::chrono::duration<double>(t1 - t0).count();
+		t0 = t1;
+		return s;
+	}
+};
+
+[[noreturn]] void die_gpu(const char *what) {
+	fprintf(stderr, "meshclust: %s failed: %s\n", what, mc_last_error());
+	exit(2);
+}
+#define GPU(call)                          \
+	do {                                   \
+		if ((call) != MC_OK) die_gpu(#call); \
+	} while (0)
+
+// ----------------------------------------------------------------------------------------------
+struct Dataset {
+	FastaBatch fa;                    // file order = point id order (Runner.cpp:345-349)
+	int64_t n = 0;
+	std::vector<uint64_t> len;        // by id
+	std::vector<int64_t> row_of_id;   // GPU row (= initial bvec iteration order) of each id
+	std::vector<int64_t> id_of_row;
+};
+
+struct Model {
+	int nfeat = 0;                    // 3 or 4 combos
+	double mins[5] = {0, 0, 0, 0, 0}, maxs[5] = {1, 1, 1, 1, 1};
+	double w[5] = {0, 0, 0, 0, 0};
+	bool align = false;               // --align: single FEAT_ALIGN feature, weights [-id, 1]
+	double cutoff = 0;
+};
+
+struct Ctx {
+	mc_ctx *gpu = nullptr;
+	Options opt;
+	Dataset ds;
+	Model model;
+	int k = 0;
+	int tbytes = 1;
+};
+
+// ----------------------------------------------------------------------------------------------
+// Trainer (Trainer.cpp)
+// ----------------------------------------------------------------------------------------------
+using Pair = std::pair<int, int>;   // point ids (first has the smaller header, Trainer.cpp:746,755)
+
+struct HeaderPairLess {
+	const std::vector<std::string> *h;
+	bool operator()(const Pair &a, const Pair &b) const {
+		const int c = (*h)[a.first].compare((*h)[b.first]);
+		if (c < 0) return true;
+		return (*h)[a.first] == (*h)[b.first] && (*h)[a.second].compare((*h)[b.second]) < 0;
+	}
+};
+struct ScoredLess {
+	HeaderPairLess base;
+	bool operator()(const std::pair<Pair, double> &a, const std::pair<Pair, double> &b) const { return base(a.first, b.first); }
+};
+
+// GlobAlignE identity of (a, b) id pairs: matches / length as double (GlobAlignE.cpp:301-305)
+std::vector<double> align_ids(Ctx &c, const std::vector<Pair> &pairs) {
+	const size_t m = pairs.size();
+	std::vector<int32_t> a(m), b(m), sc(m), ln(m), mt(m);
+	for (size_t i = 0; i < m; i++) {
+		a[i] = (int32_t)c.ds.row_of_id[pairs[i].first];
+		b[i] = (int32_t)c.ds.row_of_id[pairs[i].second];
+	}
+	if (m) GPU(mc_align_pairs(c.gpu, a.data(), b.data(), (int64_t)m, sc.data(), ln.data(), mt.data()));
+	std::vector<double> id(m);
+	for (size_t i = 0; i < m; i++) id[i] = (double)mt[i] / ln[i];
+	return id;
+}
+
+// Trainer::split (Trainer.cpp:653-783)
+std::vector<Pair> trainer_split(Ctx &c) {
+	const Dataset &ds = c.ds;
+	const int64_t n = ds.n;
+	const double cutoff = c.opt.similarity;
+	const size_t n_points = (size_t)c.opt.sample_size, max_pts_from_one = (size_t)c.opt.pivots;
+	std::vector<int> points((size_t)n);
+	for (int64_t i = 0; i < n; i++) points[i] = (int)i;
+	// :672-675 unstable sort by length, then the median-length point
+	std::sort(points.begin(), points.end(), [&](int a, int b) { return ds.len[a] < ds.len[b]; });
+	const int begin_pt = points[points.size() / 2];
+	// :681-684 sort by distance to it
+	std::vector<uint16_t> key1((size_t)n);
+	{
+		int32_t r = (int32_t)ds.row_of_id[begin_pt];
+		GPU(mc_distance_keys(c.gpu, &r, 1, key1.data()));
+	}
+	std::sort(points.begin(), points.end(), [&](int a, int b) { return key1[ds.row_of_id[a]] < key1[ds.row_of_id[b]]; });
+	// :685-690 pivots at even ranks
+	const int num_iterations = (int)std::ceil(((double)n_points) / max_pts_from_one) - 1;
+	std::vector<int> pivots;
+	for (int i = 0; i <= num_iterations; i++) {
+		const int idx = (int)((size_t)i * (points.size() - 1) / (size_t)num_iterations);
+		pivots.push_back(points[idx]);
+	}
+	printf("Point pairs: %zu\n", pivots.size());
+	const size_t np = pivots.size();
+	const size_t to_add_each = max_pts_from_one / 2;
+
+	// distance keys of every point against every pivot (the reference evaluates them inside the
+	// sort comparators, 2 per comparison)
+	std::vector<int32_t> prow(np);
+	for (size_t i = 0; i < np; i++) prow[i] = (int32_t)ds.row_of_id[pivots[i]];
+	std::vector<uint16_t> keys(np * (size_t)n);
+	GPU(mc_distance_keys(c.gpu, prow.data(), (int)np, keys.data()));
+
+	// :694-701 per pivot: copy + unstable sort by distance to the pivot.  Independent per pivot, so
+	// the host threads can share them without changing any permutation.
+	std::vector<std::vector<int>> sorted(np);
+#pragma omp parallel for schedule(dynamic)
+	for (long i = 0; i < (long)np; i++) {
+		std::vector<int> pts = points;
+		const uint16_t *kk = keys.data() + (size_t)i * n;
+		std::sort(pts.begin(), pts.end(), [&](int a, int b) { return kk[ds.row_of_id[a]] < kk[ds.row_of_id[b]]; });
+		sorted[i].swap(pts);
+	}
+	keys.clear();
+	keys.shrink_to_fit();
+
+	// :703-721 binary search with alignment, all pivots in lock step (each search is independent)
+	std::vector<size_t> offset(np, (size_t)n / 4), pos(np, 2 * ((size_t)n / 4));
+	std::vector<char> active(np, 1);
+	for (size_t i = 0; i < np; i++) active[i] = offset[i] > 0;
+	for (;;) {
+		std::vector<Pair> q;
+		std::vector<size_t> who;
+		for (size_t i = 0; i < np; i++)
+			if (active[i]) { q.push_back({pivots[i], sorted[i][pos[i]]}); who.push_back(i); }
+		if (q.empty()) break;
+		const std::vector<double> algn = align_ids(c, q);
+		for (size_t t = 0; t < who.size(); t++) {
+			const size_t i = who[t];
+			if (algn[t] < cutoff) pos[i] -= offset[i];
+			else if (algn[t] > cutoff) pos[i] += offset[i];
+			else { active[i] = 0; continue; }   // break: offset is not halved, pos stays
+			offset[i] /= 2;
+			if (offset[i] == 0) active[i] = 0;
+		}
+	}
+
+	// :723-765 ten picks below and ten above the boundary at evenly strided ranks
+	int aerr = 0;
+	HeaderPairLess less{&ds.fa.headers};
+	std::set<Pair, HeaderPairLess> pairs(less);
+	for (size_t i = 0; i < np; i++) {
+		const std::vector<int> &pts = sorted[i];
+		const int p = pivots[i];
+		const size_t pivot = pos[i];
+		const double before_inc = (double)pivot / to_add_each;
+		const double after_inc = ((double)(pts.size() - pivot)) / to_add_each;
+		if (before_inc < 1) aerr = 1;
+		else if (after_inc < 1) aerr = -1;
+		double before_start = 0, after_start = (double)pivot;
+		std::vector<Pair> buf;
+		auto ordered = [&](int other) {
+			return ds.fa.headers[p].compare(ds.fa.headers[other]) < 0 ? Pair{p, other} : Pair{other, p};
+		};
+		for (size_t t = 0; t < to_add_each; t++) {
+			const int idx = (int)std::round(before_start);
+			buf.push_back(ordered(pts[idx]));
+			before_start += before_inc;
+		}
+		for (size_t t = 0; t < to_add_each && std::round(after_start) < pts.size(); t++) {
+			const int idx = (int)std::round(after_start);
+			buf.push_back(ordered(pts[idx]));
+			after_start += after_inc;
+		}
+		pairs.insert(buf.begin(), buf.end());
+	}
+	if (aerr < 0) fprintf(stderr, "Warning: Alignment may be too small for sampling\n");
+	else if (aerr > 0) fprintf(stderr, "Warning: Alignment may be too large for sampling\n");
+	return std::vector<Pair>(pairs.begin(), pairs.end());
+}
+
+using Scored = std::pair<Pair, double>;
+
+// resize_vec (Trainer.cpp:201-243): note that it can return MORE than new_size items and repeats
+// items when a bin runs dry -- kept as is
+std::vector<Scored> resize_vec(const std::vector<Scored> &vec, size_t new_size, double min_align, double max_align, int num_bins) {
+	if (new_size == vec.size()) return vec;
+	std::vector<std::vector<Scored>> bins((size_t)num_bins);
+	auto get_bin = [&](double x) {
+		if (x >= max_align) return num_bins - 1;
+		if (x <= min_align) return 0;
+		return (int)(num_bins * (x - min_align) / (max_align - min_align));
+	};
+	for (const auto &p : vec) bins.at((size_t)get_bin(p.second)).push_back(p);
+	std::vector<Scored> data;
+	while (data.size() < new_size) {
+		const int items_left = (int)(new_size - data.size());
+		const int take = (int)std::ceil((double)items_left / num_bins);
+		for (int i = (int)bins.size() - 1; i >= 0; i--)
+			for (int j = 0; j < (int)std::min((size_t)take, bins[i].size()); j++) data.push_back(bins[i][j]);
+	}
+	return data;
+}
+
+// bin_data (Trainer.cpp:490-526): ten identity bins, alternate train/test, parity flips per bin
+void bin_data(const std::vector<Scored> &vec, double min_align, double max_align, std::vector<Pair> &train, std::vector<Pair> &test) {
+	const int n_bins = 10;
+	auto get_bin = [&](double x) {
+		if (x >= max_align) return n_bins - 1;
+		if (x <= min_align) return 0;
+		return (int)(n_bins * (x - min_align) / (max_align - min_align));
+	};
+	std::vector<std::vector<Scored>> bins((size_t)n_bins);
+	for (const auto &d : vec) bins.at((size_t)get_bin(d.second)).push_back(d);
+	int last = 0;
+	for (const auto &bin : bins) {
+		for (int i = 0; i < (int)bin.size(); i++) {
+			if (i % 2 == last) train.push_back(bin[i].first);
+			else test.push_back(bin[i].first);
+		}
+		last = !last;
+	}
+}
+
+// Trainer::get_labels (Trainer.cpp:253-333)
+void trainer_get_labels(Ctx &c, std::vector<Pair> vec, std::vector<Scored> &pos_out, std::vector<Scored> &neg_out) {
+	const double cutoff = c.opt.similarity;
+	// struct rng: srand(0), rand() % n; libstdc++ random_shuffle(first, last, rng)
+	srand(0);
+	for (size_t i = 1; i < vec.size(); i++) {
+		const size_t j = (size_t)(rand() % (int)(i + 1));
+		if (i != j) std::swap(vec[i], vec[j]);
+	}
+	const std::vector<double> algn = align_ids(c, vec);
+	ScoredLess sless{HeaderPairLess{&c.ds.fa.headers}};
+	std::set<Scored, ScoredLess> buf_pos(sless), buf_neg(sless);
+	for (size_t i = 0; i < vec.size(); i++) {
+		if (algn[i] >= cutoff) buf_pos.insert({vec[i], algn[i]});
+		else buf_neg.insert({vec[i], algn[i]});
+	}
+	printf("positive=%zu negative=%zu\n", buf_pos.size(), buf_neg.size());
+	if (buf_pos.empty() || buf_neg.empty()) {
+		printf("Identity value does not match sampled data: %s\n",
+		       buf_pos.empty() ? "Too many sequences below identity" : "Too many sequences above identity");
+		exit(0);   // Trainer.cpp:306-315
+	}
+	const size_t m_size = std::min(buf_pos.size(), buf_neg.size());
+	const std::vector<Scored> vpos(buf_pos.begin(), buf_pos.end()), vneg(buf_neg.begin(), buf_neg.end());
+	pos_out = resize_vec(vpos, m_size, cutoff, 1, 5);
+	neg_out = resize_vec(vneg, m_size, 0.4, cutoff, 5);
+	printf("positive=%zu negative=%zu\n", pos_out.size(), neg_out.size());
+}
+
+// raw features of id pairs in lookup order [LD, INTERSECTION, MANHATTAN, PEARSON, KULCZYNSKI2]
+std::vector<double> raw_features(Ctx &c, const std::vector<Pair> &pairs) {
+	const size_t m = pairs.size();
+	std::vector<int32_t> a(m), b(m);
+	for (size_t i = 0; i < m; i++) {
+		a[i] = (int32_t)c.ds.row_of_id[pairs[i].first];
+		b[i] = (int32_t)c.ds.row_of_id[pairs[i].second];
+	}
+	std::vector<double> raw(m * 5);
+	if (m) GPU(mc_pair_features(c.gpu, a.data(), b.data(), (int64_t)m, raw.data(), nullptr));
+	return raw;
+}
+
+// generate_feat_mat (Trainer.cpp:367-414): rows = positives then negatives, leading 1 column
+void feature_matrix(Ctx &c, const std::vector<Pair> &pos, const std::vector<Pair> &neg, int ncols, Mat &X, Mat &y) {
+	std::vector<Pair> all(pos);
+	all.insert(all.end(), neg.begin(), neg.end());
+	const size_t m = all.size();
+	std::vector<int32_t> a(m), b(m);
+	for (size_t i = 0; i < m; i++) {
+		a[i] = (int32_t)c.ds.row_of_id[all[i].first];
+		b[i] = (int32_t)c.ds.row_of_id[all[i].second];
+	}
+	std::vector<double> feats(m * 4);
+	GPU(mc_pair_classify(c.gpu, a.data(), b.data(), (int64_t)m, nullptr, nullptr, nullptr, feats.data()));
+	X = Mat((int)m, ncols);
+	y = Mat((int)m, 1);
+	for (size_t i = 0; i < m; i++) {
+		X.at((int)i, 0) = 1;
+		for (int col = 1; col < ncols; col++) X.at((int)i, col) = feats[i * 4 + (col - 1)];
+		y.at((int)i, 0) = i < pos.size() ? 1 : -1;
+	}
+}
+
+// Trainer::train (Trainer.cpp:527-651)
+void trainer_train(Ctx &c) {
+	Model &M = c.model;
+	M.cutoff = c.opt.similarity;
+	if (c.opt.align) {
+		// :570-577 single FEAT_ALIGN feature with bounds [0,1]; res == 1  <=>  identity >= id
+		M.align = true;
+		M.nfeat = 1;
+		M.w[0] = -1 * M.cutoff;
+		M.w[1] = 1;
+		return;
+	}
+	printf("Splitting data\n");
+	Timer tm;
+	std::vector<Pair> sample = trainer_split(c);
+	printf("  [split %.2fs, %zu pairs]\n", tm.lap(), sample.size());
+	std::vector<Scored> pos, neg;
+	trainer_get_labels(c, sample, pos, neg);
+	printf("  [labels %.2fs]\n", tm.lap());
+	std::vector<Pair> train_pos, test_pos, train_neg, test_neg;
+	bin_data(pos, M.cutoff, 1, train_pos, test_pos);
+	bin_data(neg, 0, M.cutoff, train_neg, test_neg);
+	printf("training positive: %zu\ntraining negative: %zu\ntesting positive: %zu\ntesting negative: %zu\n",
+	       train_pos.size(), train_neg.size(), test_pos.size(), test_neg.size());
+	if (test_pos.empty() || test_neg.empty()) {
+		fprintf(stderr, "terminate called after throwing an instance of 'char const*' (not enough points to sample)\n");
+		abort();
+	}
+
+	// :584-587 feature combos in order; lookups appear in the order add_feature() meets them:
+	// LD, INTERSECTION | MANHATTAN | PEARSON | KULCZYNSKI2  ->  bounds for lookups 0..3 are fixed by
+	// the 3-feature round, lookup 4 by the 4-feature round (Feature::normalize skips finalized ones)
+	const double raw_init_min = DBL_MAX, raw_init_max = DBL_MIN;   // Feature.cpp:21-22 (DBL_MIN > 0!)
+	double mins[5], maxs[5];
+	for (int i = 0; i < 5; i++) { mins[i] = raw_init_min; maxs[i] = raw_init_max; }
+	const std::vector<double> raw_pos = raw_features(c, train_pos), raw_neg = raw_features(c, train_neg);
+	auto fold = [&](int lo, int hi) {
+		for (int i = lo; i < hi; i++) {
+			double small = mins[i], big = maxs[i];
+			for (const std::vector<double> *raw : {&raw_pos, &raw_neg})
+				for (size_t j = 0; j < raw->size() / 5; j++) {
+					const double v = (*raw)[j * 5 + i];
+					if (v < small) small = v;
+					if (v > big) big = v;
+				}
+			mins[i] = small;
+			maxs[i] = big;
+		}
+	};
+	double prev_acc = -10000;
+	struct Snap { int nfeat; double mins[5], maxs[5], w[5]; };
+	std::vector<Snap> snaps;
+	for (int nf = 3; nf <= 4; nf++) {
+		if (nf == 3) fold(0, 4); else fold(4, 5);
+		for (int i = 0; i < (nf == 3 ? 4 : 5); i++) printf("bounds[%d]: %g to %g\n", i, mins[i], maxs[i]);
+		const double w0[5] = {0, 0, 0, 0, 0};
+		GPU(mc_set_model(c.gpu, mins, maxs, w0, nf));
+		Mat Xtr, ytr, Xte, yte;
+		feature_matrix(c, train_pos, train_neg, nf + 1, Xtr, ytr);
+		feature_matrix(c, test_pos, test_neg, nf + 1, Xte, yte);
+		const Mat w = glm_train(Xtr, ytr);
+		const double acc = glm_accuracy(Xte, w, yte);
+		glm_accuracy(Xtr, w, ytr);
+		if (acc - prev_acc <= 1 && acc >= 90.0) {   // :633-638 keep the previous, smaller model
+			printf("feat size is %d\n", snaps.back().nfeat);
+			break;
+		}
+		Snap s;
+		s.nfeat = nf;
+		for (int i = 0; i < 5; i++) { s.mins[i] = mins[i]; s.maxs[i] = maxs[i]; s.w[i] = i <= nf ? w.at(i, 0) : 0.0; }
+		snaps.push_back(s);
+		prev_acc = acc;
+		if (acc >= 97.5) { printf("breaking from acc cutoff\n"); break; }
+	}
+	const Snap &s = snaps.back();
+	M.nfeat = s.nfeat;
+	for (int i = 0; i < 5; i++) { M.mins[i] = s.mins[i]; M.maxs[i] = s.maxs[i]; M.w[i] = s.w[i]; }
+	printf("Using %d features\n", M.nfeat);
+	GPU(mc_set_model(c.gpu, M.mins, M.maxs, M.w, M.nfeat));
+	printf("  [glm %.2fs]\n", tm.lap());
+}
+
+// ----------------------------------------------------------------------------------------------
+// ClusterFactory::MS (ClusterFactory.cpp:717-761)
+// ----------------------------------------------------------------------------------------------
+struct Cluster {
+	int64_t center_row;              // the row the center was cloned from (Center.h:14)
+	std::vector<int64_t> rows;       // members in the reference's order
+	bool removed = false;
+};
+
+// --align: identity cache of Feature::align (Feature.cpp:222-243), keyed by the id pair
+struct AlignCache {
+	std::map<std::pair<int64_t, int64_t>, double> tab;
+};
+
+// one get_close over [lo,hi] in --align mode: every alive row of the range is aligned against the
+// center (point = seq1, center = seq2, Feature.cpp:231-235), res == 1 <=> identity >= id
+void align_scan(Ctx &c, BVec &bv, AlignCache &cache, int64_t center_row, int64_t lo, int64_t hi,
+                std::vector<uint8_t> &alive, mc_scan_result &res, std::vector<uint8_t> &marks) {
+	const Dataset &ds = c.ds;
+	std::vector<int64_t> rows;
+	for (int64_t r = lo; r <= hi; r++) if (alive[r]) rows.push_back(r);
+	std::vector<int32_t> a, b;
+	std::vector<size_t> need;
+	std::vector<double> ident(rows.size());
+	const int64_t cid = ds.id_of_row[center_row];
+	for (size_t i = 0; i < rows.size(); i++) {
+		const int64_t pid = ds.id_of_row[rows[i]];
+		const auto key = pid < cid ? std::make_pair(pid, cid) : std::make_pair(cid, pid);
+		auto it = cache.tab.find(key);
+		if (it != cache.tab.end()) ident[i] = it->second;
+		else { need.push_back(i); a.push_back((int32_t)rows[i]); b.push_back((int32_t)center_row); }
+	}
+	if (!need.empty()) {
+		std::vector<int32_t> sc(need.size()), ln(need.size()), mt(need.size());
+		GPU(mc_align_pairs(c.gpu, a.data(), b.data(), (int64_t)need.size(), sc.data(), ln.data(), mt.data()));
+		for (size_t t = 0; t < need.size(); t++) {
+			const double v = (double)mt[t] / ln[t];
+			ident[need[t]] = v;
+			const int64_t pid = ds.id_of_row[rows[need[t]]];
+			cache.tab[pid < cid ? std::make_pair(pid, cid) : std::make_pair(cid, pid)] = v;
+		}
+	}
+	res.n_eval = (int64_t)rows.size();
+	res.n_pos = 0;
+	res.best_row = -1;
+	res.best_f0 = -1;
+	marks.assign((size_t)(hi - lo + 1), 0);
+	for (size_t i = 0; i < rows.size(); i++) {
+		// normalised FEAT_ALIGN = (v - 0) / (1 - 0); sum = -id + 1 * v
+		const double v = (ident[i] - 0.0) / (1.0 - 0.0);
+		const double sum = std::fma(c.model.w[1], v, c.model.w[0]);
+		const double r = std::round(1.0 / (1 + std::exp(-sum)));
+		if (v > res.best_f0) { res.best_f0 = v; res.best_row = rows[i]; }
+		if (r == 1.0) { marks[(size_t)(rows[i] - lo)] = 1; res.n_pos++; alive[rows[i]] = 0; }
+	}
+	(void)bv;
+}
+
+void write_clstr(const Ctx &c, const std::vector<Cluster> &part) {
+	// print_output (ClusterFactory.cpp:495-520)
+	printf("Printing output\n");
+	FILE *f = fopen(c.opt.output.c_str(), "w");
+	if (!f) { fprintf(stderr, "cannot open %s\n", c.opt.output.c_str()); exit(1); }
+	int counter = 0;
+	for (const Cluster &cl : part) {
+		if (cl.rows.empty()) continue;
+		fprintf(f, ">Cluster %d\n", counter);
+		int pt = 0;
+		for (int64_t r : cl.rows) {
+			const int64_t id = c.ds.id_of_row[r];
+			fprintf(f, "%d\t%llunt, %s... ", pt, (unsigned long long)c.ds.len[id], c.ds.fa.headers[id].c_str());
+			if (r == cl.center_row) fputc('*', f);
+			fputc('\n', f);
+			pt++;
+		}
+		counter++;
+	}
+	fclose(f);
+}
+
+void mean_shift(Ctx &c, BVec &bv) {
+	const Dataset &ds = c.ds;
+	const double sim = c.opt.similarity;
+	const int delta = c.opt.delta;
+	std::vector<Cluster> part;
+	Timer tm;
+	AlignCache cache;
+	std::vector<uint8_t> alive;   // host mirror, only needed by the --align scans
+	if (c.model.align) alive.assign((size_t)ds.n, 1);
+	GPU(mc_alive_reset(c.gpu));
+
+	auto kill_row = [&](int64_t row) {
+		GPU(mc_alive_kill(c.gpu, &row, 1));
+		if (c.model.align) alive[row] = 0;
+	};
+
+	// ---------------- Phase A: accumulate (ClusterFactory.cpp:637-714, :722-729) -----------------
+	int64_t last = bv.pop();
+	if (last >= 0) kill_row(last);
+	std::vector<uint8_t> marks;
+	int64_t scans = 0, evals = 0;
+	while (last >= 0) {
+		std::vector<int64_t> current{last};
+		bool is_min = false, first_mean = true;
+		int64_t next_seed = -1;
+		while (!is_min) {
+			const uint64_t len = ds.len[ds.id_of_row[last]];
+			const auto bounds = bv.get_range((uint64_t)(len * sim), (uint64_t)(len / sim));
+			mc_scan_result res;
+			res.n_eval = 0; res.n_pos = 0; res.best_row = -1; res.best_f0 = -1;
+			int64_t lo = 0, hi = -1;
+			if (bv.trip_count(bounds.first, bounds.second) > 0) {
+				lo = bv.row_at(bounds.first);
+				hi = bv.row_at(bounds.second);
+			}
+			if (hi >= lo) {
+				marks.resize((size_t)(hi - lo + 1));
+				if (c.model.align) align_scan(c, bv, cache, last, lo, hi, alive, res, marks);
+				else GPU(mc_scan(c.gpu, last, lo, hi, &res, marks.data()));
+				scans++;
+				evals += res.n_eval;
+			}
+			is_min = res.n_pos == 0;
+			if (is_min) {
+				// no close point left: the arg-max of f0 becomes the next seed (or the first point)
+				if (res.best_row < 0) next_seed = bv.pop();
+				else { next_seed = res.best_row; bv.erase_row(res.best_row); }
+				if (next_seed >= 0) kill_row(next_seed);
+			} else {
+				const size_t prev = current.size();
+				bv.remove_marked(bounds.first.bin, bounds.second.bin,
+				                 [&](int64_t r) { return r >= lo && r <= hi && marks[(size_t)(r - lo)] != 0; }, current);
+				// get_mean over all of `current` (ClusterFactory.cpp:382-425)
+				int64_t nearest = -1;
+				if (first_mean) GPU(mc_mean_nearest(c.gpu, current.data(), (int64_t)current.size(), 0, &nearest, nullptr));
+				else GPU(mc_mean_nearest(c.gpu, current.data() + prev, (int64_t)(current.size() - prev), 1, &nearest, nullptr));
+				first_mean = false;
+				last = nearest;
+			}
+		}
+		Cluster cl;
+		cl.center_row = last;
+		cl.rows.swap(current);
+		part.push_back(std::move(cl));
+		last = next_seed;
+	}
+	printf("Accumulation: %zu clusters, %lld scans, %lld evals  [%.2fs]\n", part.size(), (long long)scans, (long long)evals, tm.lap());
+
+	// ---------------- Phase B: update + merge (ClusterFactory.cpp:733-753) -----------------------
+	for (int iter = 0; iter < c.opt.iterations; iter++) {
+		const int64_t nc = (int64_t)part.size();
+		if (nc == 0) break;
+		// mean_shift_update for every center (Jacobi sweep: each j only rewrites its own center)
+		std::vector<int64_t> cand, off((size_t)nc + 1, 0), centers((size_t)nc), cb((size_t)nc), ce((size_t)nc), next((size_t)nc, -1);
+		for (int64_t j = 0; j < nc; j++) {
+			off[j + 1] = off[j] + (int64_t)part[j].rows.size();
+			cand.insert(cand.end(), part[j].rows.begin(), part[j].rows.end());
+			centers[j] = part[j].center_row;
+		}
+		for (int64_t j = 0; j < nc; j++) {
+			cb[j] = off[std::max<int64_t>(0, j - delta)];
+			ce[j] = off[std::min<int64_t>(j + delta, nc - 1) + 1];
+		}
+		if (!c.model.align) {
+			GPU(mc_update_centers(c.gpu, centers.data(), nc, cand.data(), (int64_t)cand.size(), cb.data(), ce.data(), next.data()));
+			for (int64_t j = 0; j < nc; j++)
+				if (next[j] >= 0 && next[j] != part[j].center_row) part[j].center_row = next[j];
+		}
+		// merge (ClusterFactory.cpp:427-493 with Trainer::merge, Trainer.cpp:129-157): the pair
+		// evaluations of a pass do not depend on the merges of that pass, so they go in one batch
+		std::vector<int32_t> pa, pb;
+		std::vector<int64_t> first_pair((size_t)nc + 1, 0);
+		for (int64_t i = 0; i < nc; i++) {
+			const int64_t lastj = std::min<int64_t>(nc - 1, i + delta);
+			for (int64_t t = i + 1; t <= lastj; t++) { pa.push_back((int32_t)part[t].center_row); pb.push_back((int32_t)part[i].center_row); }
+			first_pair[i + 1] = (int64_t)pa.size();
+		}
+		std::vector<double> f0(pa.size());
+		std::vector<uint8_t> fl(pa.size());
+		if (!pa.empty() && !c.model.align) GPU(mc_pair_classify(c.gpu, pa.data(), pb.data(), (int64_t)pa.size(), nullptr, f0.data(), fl.data(), nullptr));
+		for (int64_t i = 0; i < nc; i++) {
+			std::pair<long, double> best(0, DBL_MIN);   // Trainer.cpp:135 initial value: DBL_MIN is positive
+			for (int64_t q = first_pair[i]; q < first_pair[i + 1]; q++) {
+				const long t = (long)(i + 1 + (q - first_pair[i]));
+				if (fl[q]) best = best.second > f0[q] ? best : std::make_pair(t, f0[q]);
+			}
+			if (best.first > i) {
+				auto &to_add = part[best.first].rows;
+				to_add.insert(to_add.end(), part[i].rows.begin(), part[i].rows.end());
+				part[i].removed = true;
+			}
+		}
+		part.erase(std::remove_if(part.begin(), part.end(), [](const Cluster &p) { return p.removed; }), part.end());
+	}
+	printf("Update: %zu clusters  [%.2fs]\n", part.size(), tm.lap());
+	write_clstr(c, part);
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+int run_pipeline(Options opt) {
+	Ctx c;
+	c.opt = opt;
+	Timer total, tm;
+#ifdef _OPENMP
+	if (opt.threads > 0) omp_set_num_threads(opt.threads);
+#endif
+	// ---- read (Runner.cpp:43-52, ChromListMaker) ------------------------------------------------
+	std::vector<size_t> file_first;
+	for (const std::string &f : opt.files) {
+		if (access(f.c_str(), F_OK) == -1) {
+			fprintf(stderr, "File \"%s\" does not exist\n", f.c_str());
+			exit(1);
+		}
+		std::string msg;
+		file_first.push_back(c.ds.fa.size());
+		if (!read_fasta(f, c.ds.fa, msg)) {
+			fprintf(stderr, "meshclust: %s\n", msg.c_str());
+			abort();   // the reference dies with an uncaught exception on malformed input
+		}
+	}
+	file_first.push_back(c.ds.fa.size());
+	Dataset &ds = c.ds;
+	ds.n = (int64_t)ds.fa.size();
+	ds.len.resize((size_t)ds.n);
+	for (int64_t i = 0; i < ds.n; i++) ds.len[i] = (uint64_t)(ds.fa.offsets[i + 1] - ds.fa.offsets[i]);
+	printf("Read %lld sequences  [%.2fs]\n", (long long)ds.n, tm.lap());
+
+	// ---- k (Runner.cpp:265-292 find_k) ----------------------------------------------------------
+	c.k = opt.k;
+	if (c.k == -1) {
+		unsigned long long length = 0;
+		for (size_t fi = 0; fi + 1 < file_first.size(); fi++) {
+			unsigned long long l = 0;
+			for (size_t i = file_first[fi]; i < file_first[fi + 1]; i++) l += ds.len[i];
+			l /= (file_first[fi + 1] - file_first[fi]);
+			length += l;
+		}
+		length /= opt.files.size();
+		c.k = (int)std::ceil(std::log((double)length) / std::log(4)) - 1;
+		printf("avg length: %llu\nRecommended K: %d\n", length, c.k);
+	}
+	if (opt.similarity < 0.6) c.opt.align = true;   // Runner.cpp:32-34
+	if (c.opt.sample_size == 0) c.opt.sample_size = 3000;
+	srand(10);
+
+	// ---- bvec layout from the lengths alone (Runner.cpp:342-350; bvec.cpp) ----------------------
+	BVec bv(ds.len, 1000);
+	for (int64_t i = 0; i < ds.n; i++) bv.insert(i, ds.len[i]);
+	bv.finalize();
+	ds.id_of_row = bv.assign_rows();
+	ds.row_of_id.assign((size_t)ds.n, -1);
+	for (int64_t r = 0; r < ds.n; r++) ds.row_of_id[ds.id_of_row[r]] = r;
+
+	// ---- upload in row order, encode, histograms (K1) -------------------------------------------
+	GPU(mc_ctx_create(&c.gpu, opt.device));
+	{
+		std::vector<uint8_t> letters(ds.fa.letters.size());
+		std::vector<int64_t> offs((size_t)ds.n + 1, 0), seg_off((size_t)ds.n + 1, 0);
+		std::vector<int32_t> segs;
+		int32_t buf[2 * 256];
+		for (int64_t r = 0; r < ds.n; r++) {
+			const int64_t id = ds.id_of_row[r];
+			const uint8_t *src = ds.fa.letters.data() + ds.fa.offsets[id];
+			const int64_t len = (int64_t)ds.len[id];
+			memcpy(letters.data() + offs[r], src, (size_t)len);
+			offs[r + 1] = offs[r] + len;
+			int ns = mc_host_segments(src, len, buf, 256);
+			if (ns < 0) {
+				fprintf(stderr, "meshclust: record \"%s\" has no usable sequence (the reference throws std::out_of_range)\n", ds.fa.headers[id].c_str());
+				abort();
+			}
+			if (ns > 256) {
+				std::vector<int32_t> big((size_t)ns * 2);
+				mc_host_segments(src, len, big.data(), ns);
+				segs.insert(segs.end(), big.begin(), big.end());
+			} else segs.insert(segs.end(), buf, buf + 2 * ns);
+			seg_off[r + 1] = seg_off[r] + ns;
+		}
+		if (mc_load_sequences(c.gpu, letters.data(), offs.data(), ds.n, segs.data(), seg_off.data()) != MC_OK) {
+			fprintf(stderr, "meshclust: %s\n", mc_last_error());
+			abort();   // InvalidInputException in the reference
+		}
+	}
+	uint64_t largest = 0;
+	GPU(mc_build_histograms(c.gpu, c.k, 0, &c.tbytes, &largest));
+	printf("Using %d bit histograms\n", c.tbytes * 8);   // Runner.cpp:75-89
+	printf("Counted %d-mers, largest count %llu  [%.2fs]\n", c.k, (unsigned long long)largest, tm.lap());
+
+	// ---- train, cluster, write ------------------------------------------------------------------
+	trainer_train(c);
+	if (!opt.dump_model.empty()) {
+		FILE *f = fopen(opt.dump_model.c_str(), "w");
+		if (f) {
+			fprintf(f, "nfeat %d\n", c.model.nfeat);
+			for (int i = 0; i < 5; i++) fprintf(f, "bounds %d %.17g %.17g\n", i, c.model.mins[i], c.model.maxs[i]);
+			for (int i = 0; i < 5; i++) fprintf(f, "weight %d %.17g\n", i, c.model.w[i]);
+			fclose(f);
+		}
+	}
+	mean_shift(c, bv);
+	printf("Total %.2fs\n", total.lap());
+	mc_ctx_destroy(c.gpu);
+	return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+void usage(const std::string &prog) {
+	printf("Usage: %s *.fasta [--id 0.90] [--kmer 3] [--delta 5] [--output output.clstr] [--iterations 20] [--align] [--sample 3000] [--pivot 40] [--threads TMAX]\n\n", prog.c_str());
+	printf("meshclust_b200: B200-native hot path behind the MeShClust 1.2.0 command line.\n\n"
+	       "--id          identity threshold (below 0.6 alignment is used automatically)\n"
+	       "--kmer        k-mer size (default: from the average sequence length)\n"
+	       "--delta       clusters looked at on each side in the final stage (default 5)\n"
+	       "--output      output file, CD-HIT CLSTR format (default output.clstr)\n"
+	       "--iterations  update/merge iterations (default 15)\n"
+	       "--align       force alignment instead of k-mer features\n"
+	       "--sample      number of sampled training pairs (default 3000)\n"
+	       "--pivot       pairs per pivot sequence (default 20)\n"
+	       "--threads     host threads\n"
+	       "Any other argument is an input file.\n\n");
+}
+
+Options parse_options(int argc, char **argv) {
+	Options o;
+	auto need_long = [&](int &i, const char *what, bool allow_zero) -> long {
+		errno = 0;
+		const long v = strtol(argv[i + 1], NULL, 10);
+		if (errno) { perror(argv[i + 1]); exit(EXIT_FAILURE); }
+		if (allow_zero ? v < 0 : v <= 0) { fprintf(stderr, "%s must be greater than 0.\n", what); exit(EXIT_FAILURE); }
+		i++;
+		return v;
+	};
+	for (int i = 1; i < argc; i++) {
+		const std::string arg = argv[i];
+		const bool more = i + 1 < argc;
+		if (arg == "--id" && more) {
+			try {
+				o.similarity = std::stod(argv[i + 1]);
+				if (o.similarity <= 0 || o.similarity >= 1) throw std::invalid_argument("");
+			} catch (const std::exception &) {
+				fprintf(stderr, "Similarity must be between 0 and 1\n");
+				exit(EXIT_FAILURE);
+			}
+			i++;
+		} else if ((arg == "-k" || arg == "--kmer") && more) o.k = (int)need_long(i, "K", false);
+		else if ((arg == "-o" || arg == "--output") && more) o.output = argv[++i];
+		else if (arg == "-a" || arg == "--align") o.align = true;
+		else if ((arg == "-s" || arg == "--sample") && more) o.sample_size = (int)need_long(i, "Sample size", false);
+		else if ((arg == "-p" || arg == "--pivot") && more) o.pivots = (int)need_long(i, "Points per pivot", false);
+		else if ((arg == "-t" || arg == "--threads") && more) {
+			try {
+				o.threads = std::stoi(argv[i + 1]);
+				if (o.threads <= 0) throw std::invalid_argument("");
+			} catch (const std::exception &) {
+				fprintf(stderr, "Number of threads must be greater than 0.\n");
+				exit(1);
+			}
+			i++;
+		} else if ((arg == "-d" || arg == "--delta") && more) o.delta = (int)need_long(i, "Delta", true);
+		else if ((arg == "-i" || arg == "--iter" || arg == "--iterations") && more) o.iterations = (int)need_long(i, "Iterations", false);
+		else if (arg == "--device" && more) o.device = atoi(argv[++i]);          // extension: GPU ordinal
+		else if (arg == "--dump-model" && more) o.dump_model = argv[++i];        // extension: test hook
+		else {
+			struct stat st;
+			if (stat(argv[i], &st) == 0 && S_ISREG(st.st_mode)) o.files.push_back(argv[i]);
+			else { usage(argv[0]); exit(EXIT_FAILURE); }
+		}
+	}
+	if (o.files.empty()) { usage(argv[0]); exit(EXIT_FAILURE); }
+	// Runner.cpp:253-262: files ordered by basename
+	std::sort(o.files.begin(), o.files.end(), [](const std::string &a, const std::string &b) {
+		std::string as = a, bs = b;
+		const std::string ab = basename(&as[0]), bb = basename(&bs[0]);
+		return ab < bb;
+	});
+	return o;
+}
+
+}  // namespace mch
