@@ -131,21 +131,24 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 
 	if (wib == 0) {
 		// ===================== producer =====================
-		// lane l issues the bulk copies of tiles jj = l, l+32, ...: a slot is only ever touched by
-		// the one lane whose jj maps to it in a given round, and issue cost is spread over the warp
-		for (long long jj = lane; jj < nmine; jj += 32) {
-			const int w = (int)(jj % T::NCW);
-			const long long u = jj / T::NCW;              // u-th tile of consumer w
-			const int slot = w * T::D + (int)(u % T::D);
-			const long long round = u / T::D;
-			if (round > 0) mbar_wait(&empty_bar[slot], (uint32_t)(round - 1) & 1);
-			const long long r0 = lo + (my_first + jj * gridDim.x) * T::RT;
-			long long nr = hi - r0 + 1;
-			if (nr > T::RT) nr = T::RT;
-			uint8_t *dst = smem + (size_t)slot * T::STAGE_BYTES;
-			mbar_expect_tx(&full_bar[slot], (uint32_t)(nr * RB + nr * 32));
-			tma_bulk_g2s(dst, hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[slot]);
-			tma_bulk_g2s(dst + T::ROW_BYTES, aux + r0, (uint32_t)(nr * 32), &full_bar[slot]);
+		// lane l owns ring slot l (consumer l / D, ring position l % D) and issues every bulk copy
+		// that lands there, in order.  Slots fill in parallel (issue cost spread over the warp) while
+		// one lane never runs more than one phase ahead of its slot's barriers.
+		if (lane < T::NS) {
+			const int w = lane / T::D;
+			for (long long u = lane % T::D; ; u += T::D) {
+				const long long jj = u * T::NCW + w;          // u-th tile of consumer w
+				if (jj >= nmine) break;
+				const long long round = u / T::D;
+				if (round > 0) mbar_wait(&empty_bar[lane], (uint32_t)(round - 1) & 1);
+				const long long r0 = lo + (my_first + jj * gridDim.x) * T::RT;
+				long long nr = hi - r0 + 1;
+				if (nr > T::RT) nr = T::RT;
+				uint8_t *dst = smem + (size_t)lane * T::STAGE_BYTES;
+				mbar_expect_tx(&full_bar[lane], (uint32_t)(nr * RB + nr * 32));
+				tma_bulk_g2s(dst, hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[lane]);
+				tma_bulk_g2s(dst + T::ROW_BYTES, aux + r0, (uint32_t)(nr * 32), &full_bar[lane]);
+			}
 		}
 	} else if (wib - 1 < T::NCW) {
 		// ===================== consumers =====================
