@@ -100,7 +100,7 @@ def build_cli(force: bool = False) -> str | None:
         return BIN
     os.makedirs(os.path.dirname(BIN), exist_ok=True)
     os.makedirs(OBJ, exist_ok=True)
-    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-Wall", "-Wno-sign-compare",
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-Wall", "-Wno-sign-compare",
            "-I", os.path.join(ROOT, "include"), *srcs, "-o", BIN,
            "-L", PKG, "-lmeshclust_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../meshclust_b200"]
     subprocess.check_call(cmd)

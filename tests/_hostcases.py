@@ -1,0 +1,68 @@
+"""Small end-to-end cases for the host control flow (bin/meshclust vs the reference binary at
+--threads 1).  The FASTA inputs are regenerated from seeds; the expected CLSTR files are committed
+under tests/golden/clstr/ (made by tests/golden/make_host_golden.py with the compiled reference)."""
+from __future__ import annotations
+
+import gzip
+import os
+
+import numpy as np
+
+from meshclust_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden", "clstr")
+
+
+def var_len_fasta(path, n, ntemp, lmin, lmax, mu, seed, related=0.0, iupac=False):
+    rng = np.random.default_rng(seed)
+    temps = [rng.integers(0, 4, int(rng.integers(lmin, lmax)), dtype=np.uint8) for _ in range(ntemp)]
+    if related > 0:
+        anc = temps[0]
+        temps = [synth._mutate(rng, anc.copy(), np.array([0, anc.size]), related)[0] for _ in range(ntemp)]
+    pieces, offs, tm = [], [0], []
+    for i in range(n):
+        t = i % ntemp
+        c, _ = synth._mutate(rng, temps[t].copy(), np.array([0, temps[t].size]), mu)
+        pieces.append(c)
+        offs.append(offs[-1] + c.size)
+        tm.append(t)
+    letters = synth._ACGT[np.concatenate(pieces)].copy()
+    if iupac:   # lower case, N runs (short and long) and IUPAC codes sprinkled in
+        letters[::3] |= 0x20
+        for s in rng.integers(0, letters.size - 40, n // 4):
+            letters[s:s + int(rng.choice([1, 3, 12, 30]))] = ord("N")
+        letters[rng.integers(0, letters.size, n)] = rng.choice(np.frombuffer(b"RYMKSWHBVD", np.uint8), n)
+    synth.write_fasta(path, letters, np.array(offs, np.int64), [f">seq{i} template{tm[i]}" for i in range(n)])
+
+
+# name -> (list of (file name, generator kwargs), CLI arguments)
+CASES = {
+    "A": ([("A.fa", dict(n=1500, ntemp=15, lmin=300, lmax=301, mu=0.03, seed=11))], ["--id", "0.90", "--kmer", "3"]),
+    "B": ([("B.fa", dict(n=2500, ntemp=25, lmin=200, lmax=700, mu=0.03, seed=12))], ["--id", "0.90", "--kmer", "3"]),
+    "D": ([("D2.fa", dict(n=800, ntemp=12, lmin=280, lmax=340, mu=0.04, seed=15)),
+           ("D1.fa", dict(n=700, ntemp=10, lmin=300, lmax=330, mu=0.04, seed=14))],
+          ["--id", "0.88", "--kmer", "3", "--delta", "2", "--iterations", "5"]),
+    "E": ([("E.fa", dict(n=1200, ntemp=40, lmin=250, lmax=400, mu=0.02, seed=16, related=0.08))], ["--id", "0.93"]),
+    "F": ([("F.fa", dict(n=1300, ntemp=20, lmin=260, lmax=420, mu=0.03, seed=17, iupac=True))],
+          ["--id", "0.90", "--kmer", "4", "--sample", "2000", "--pivot", "10"]),
+}
+
+
+def make_inputs(name: str, workdir: str):
+    files, args = CASES[name]
+    paths = []
+    for fname, kw in files:
+        p = os.path.join(workdir, fname)
+        var_len_fasta(p, **kw)
+        paths.append(p)
+    return paths, list(args)
+
+
+def golden_path(name: str) -> str:
+    return os.path.join(GOLDEN_DIR, f"{name}.clstr.gz")
+
+
+def read_golden(name: str) -> bytes:
+    with gzip.open(golden_path(name), "rb") as f:
+        return f.read()

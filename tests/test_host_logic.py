@@ -1,0 +1,67 @@
+"""The host control flow of bin/meshclust (sampling, GLM, bvec, accumulate / update / merge
+bookkeeping, CLSTR writer) against CLSTR files produced by the reference binary at --threads 1.
+
+CPU (not gpu): the host sources are linked against tests/mock/mock_capi.cpp, a CPU stand-in for
+the C-ABI built on the oracle -- test infrastructure only, the product binary never links it.
+GPU: the real bin/meshclust (linked against libmeshclust_b200.so) on the same inputs."""
+import os
+import subprocess
+
+import pytest
+
+import _hostcases as H
+
+ROOT = H.ROOT
+HOST = os.path.join(ROOT, "meshclust_b200", "host")
+MOCK_BIN = os.path.join(ROOT, "tests", "_build", "meshclust_hostlogic")
+
+
+@pytest.fixture(scope="session")
+def mock_cli():
+    srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")]
+    srcs += [os.path.join(ROOT, "tests", "mock", "mock_capi.cpp")]
+    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + [os.path.join(ROOT, "oracle", "mc_oracle.c")]
+    if (not os.path.exists(MOCK_BIN)) or any(os.path.getmtime(d) > os.path.getmtime(MOCK_BIN) for d in deps):
+        os.makedirs(os.path.dirname(MOCK_BIN), exist_ok=True)
+        obj = os.path.join(os.path.dirname(MOCK_BIN), "mc_oracle.o")
+        subprocess.check_call(["/usr/bin/gcc", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-std=c11", "-fopenmp", "-c",
+                               os.path.join(ROOT, "oracle", "mc_oracle.c"), "-o", obj])
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-Wno-sign-compare",
+                               "-I", os.path.join(ROOT, "include"), *srcs, obj, "-o", MOCK_BIN, "-lm"])
+    return MOCK_BIN
+
+
+def _run(binary, name, tmp_path, extra=()):
+    paths, args = H.make_inputs(name, str(tmp_path))
+    out = os.path.join(str(tmp_path), "out.clstr")
+    r = subprocess.run([binary, *paths, *args, *extra, "--output", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return open(out, "rb").read(), r.stdout
+
+
+@pytest.mark.parametrize("name", list(H.CASES))
+def test_clstr_identical_to_reference_cpu(mock_cli, tmp_path, name):
+    got, _ = _run(mock_cli, name, tmp_path)
+    assert got == H.read_golden(name)
+
+
+def test_cli_errors(mock_cli, tmp_path):
+    # Runner.cpp:150-263: bad values and missing files exit non-zero with the reference's messages
+    r = subprocess.run([mock_cli], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stdout
+    r = subprocess.run([mock_cli, "--id", "1.5", __file__], capture_output=True, text=True)
+    assert r.returncode == 1 and "Similarity must be between 0 and 1" in r.stderr
+    r = subprocess.run([mock_cli, "/nonexistent.fa"], capture_output=True, text=True)
+    assert r.returncode == 1
+    r = subprocess.run([mock_cli, "--kmer", "0", __file__], capture_output=True, text=True)
+    assert r.returncode == 1 and "K must be greater than 0" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(H.CASES))
+def test_clstr_identical_to_reference_gpu(built_lib, tmp_path, name):
+    from meshclust_b200 import build
+    cli = build.build_cli()
+    assert cli and os.path.exists(cli)
+    got, log = _run(cli, name, tmp_path)
+    assert got == H.read_golden(name), log[-1500:]
