@@ -44,6 +44,8 @@ CASES = {
            ("D1.fa", dict(n=700, ntemp=10, lmin=300, lmax=330, mu=0.04, seed=14))],
           ["--id", "0.88", "--kmer", "3", "--delta", "2", "--iterations", "5"]),
     "E": ([("E.fa", dict(n=1200, ntemp=40, lmin=250, lmax=400, mu=0.02, seed=16, related=0.08))], ["--id", "0.93"]),
+    # BASELINE.json configs[0] in full: 10k synthetic 1 kb sequences from 100 mutated templates
+    "c1_full": ([("c1.fa", dict(config="c1"))], ["--id", "0.90", "--kmer", "3"]),
     "F": ([("F.fa", dict(n=1300, ntemp=20, lmin=260, lmax=420, mu=0.03, seed=17, iupac=True))],
           ["--id", "0.90", "--kmer", "4", "--sample", "2000", "--pivot", "10"]),
 }
@@ -54,7 +56,11 @@ def make_inputs(name: str, workdir: str):
     paths = []
     for fname, kw in files:
         p = os.path.join(workdir, fname)
-        var_len_fasta(p, **kw)
+        if "config" in kw:
+            letters, offs, tmpl = synth.generate_config(kw["config"], kw.get("n"))
+            synth.write_fasta(p, letters, offs, synth.headers_for(offs.size - 1, tmpl))
+        else:
+            var_len_fasta(p, **kw)
         paths.append(p)
     return paths, list(args)
 
