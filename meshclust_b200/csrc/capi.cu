@@ -2,6 +2,7 @@
 // Kernels live in kmer_hist.cu / pair_kernels.cu / center_mean.cu / nw_identity.cu.
 #include <stdarg.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 
@@ -82,6 +83,10 @@ struct Carve {
 // ---------------------------------------------------------------------------------------------
 extern "C" int mc_ctx_create(mc_ctx **out, int device) {
 	MC_REQUIRE(out != nullptr, MC_ERR_ARG, "mc_ctx_create: out is NULL");
+	const bool dbg = getenv("MC_DEBUG_TIMING") != nullptr;
+	auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+	double t_prev = now();
+	auto lap = [&](const char *what) { if (dbg) { const double t = now(); fprintf(stderr, "[mc_ctx_create] %-28s %.3f s\n", what, t - t_prev); t_prev = t; } };
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
 	if (e != cudaSuccess || ndev == 0) {
@@ -90,21 +95,28 @@ extern "C" int mc_ctx_create(mc_ctx **out, int device) {
 		return MC_ERR_CUDA;
 	}
 	MC_REQUIRE(device >= 0 && device < ndev, MC_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+	lap("cudaGetDeviceCount");
 	MC_CUDA(cudaSetDevice(device));
+	MC_CUDA(cudaFree(0));
+	lap("cudaSetDevice + context");
 	mc_ctx *ctx = new mc_ctx();
 	ctx->device = device;
 	cudaDeviceProp prop;
 	MC_CUDA(cudaGetDeviceProperties(&prop, device));
 	ctx->num_sms = prop.multiProcessorCount;
+	lap("cudaGetDeviceProperties");
 	MC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	MC_CUDA(cudaMalloc(&ctx->d_ticket, 16 * sizeof(unsigned int)));
 	MC_CUDA(cudaMemsetAsync(ctx->d_ticket, 0, 16 * sizeof(unsigned int), ctx->stream));
 	MC_CUDA(cudaMalloc(&ctx->d_flags, 16 * sizeof(unsigned int)));
 	MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 16 * sizeof(unsigned int), ctx->stream));
+	lap("stream + small allocations");
 	int rc = mc_upload_lut();
 	if (rc) { delete ctx; return rc; }
+	lap("constant LUT (module load)");
 	rc = mc_ensure_pinned(ctx, 1 << 20);
 	if (rc) { delete ctx; return rc; }
+	lap("pinned staging buffer");
 	ctx->model.valid = 0;
 	*out = ctx;
 	return MC_OK;

@@ -2,10 +2,12 @@
 // Replaces utility/GlobAlignE.cpp:123-305 as called by Trainer::align (Trainer.cpp:15-31) and
 // Feature::align (Feature.cpp:222-243), parameters (match 1, mismatch -1, open 2, continue 1).
 //
-// Integer, compute-bound.  One warp per pair, anti-diagonal wavefront: the rows j of seq2 are cut
-// into strips of 32, lane l owns row j0+1+l and at step t fills column i = t-l+1 of seq1.  The
-// row above arrives by __shfl_up from lane l-1 (which filled the same column one step earlier);
-// lane 31's row is parked in a global scratch line for lane 0 of the next strip.
+// Integer, compute-bound.  One warp per pair, anti-diagonal wavefront with register blocking:
+// the rows j of seq2 are cut into strips of 32*R rows, lane l owns R consecutive rows and at step t
+// fills column i = t-l+1 of seq1 for all of them (top row first: the vertical dependency stays
+// inside the lane).  Only the lane's LAST row travels to the lane below (__shfl_up, 6 words per
+// step for 32*R cells); lane 31's last row is parked in a global scratch line for lane 0 of the
+// next strip, which reads it back in coalesced 32-column chunks fetched one chunk ahead.
 // Each DP state carries (score, len, id); len and id travel packed as (len << 16) | id so a path
 // copy is one move and "+1 column [+1 match]" one add.  Requires la + lb <= 65535.
 //
@@ -23,6 +25,29 @@ constexpr int NW_OPEN_EXT = 3;   // gapOpen + gapContinue
 constexpr int NW_EXT = 1;        // gapContinue
 constexpr int NW_OPEN = 2;
 constexpr uint32_t NW_LEN1 = 0x10000u;
+constexpr int NW_R = 4;          // rows per lane
+
+__device__ __forceinline__ NwCell nw_shfl_up(const NwCell &c) {
+	NwCell r;
+	r.m = __shfl_up_sync(MC_FULL_MASK, c.m, 1);
+	r.u = __shfl_up_sync(MC_FULL_MASK, c.u, 1);
+	r.l = __shfl_up_sync(MC_FULL_MASK, c.l, 1);
+	r.pm = __shfl_up_sync(MC_FULL_MASK, c.pm, 1);
+	r.pu = __shfl_up_sync(MC_FULL_MASK, c.pu, 1);
+	r.pl = __shfl_up_sync(MC_FULL_MASK, c.pl, 1);
+	return r;
+}
+
+__device__ __forceinline__ NwCell nw_shfl_from(const NwCell &c, int src) {
+	NwCell r;
+	r.m = __shfl_sync(MC_FULL_MASK, c.m, src);
+	r.u = __shfl_sync(MC_FULL_MASK, c.u, src);
+	r.l = __shfl_sync(MC_FULL_MASK, c.l, src);
+	r.pm = __shfl_sync(MC_FULL_MASK, c.pm, src);
+	r.pu = __shfl_sync(MC_FULL_MASK, c.pu, src);
+	r.pl = __shfl_sync(MC_FULL_MASK, c.pl, src);
+	return r;
+}
 
 __global__ void __launch_bounds__(128)
 nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
@@ -30,6 +55,7 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
           int4 *__restrict__ scratch_a, int2 *__restrict__ scratch_b, long long scratch_stride,
           int32_t *__restrict__ score_out, int32_t *__restrict__ len_out, int32_t *__restrict__ id_out,
           unsigned int *__restrict__ flags) {
+	constexpr int R = NW_R;
 	const int lane = threadIdx.x & 31;
 	const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -63,92 +89,125 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 		}
 
 		int res_sc = 0; uint32_t res_p = 0;
-		const int nstrips = (lb + 31) / 32;
+		const int rows_per_strip = 32 * R;
+		const int nstrips = (lb + rows_per_strip - 1) / rows_per_strip;
 		for (int strip = 0; strip < nstrips; strip++) {
-			const int j = strip * 32 + 1 + lane;          // this lane's row (1-based)
+			const int j0 = strip * rows_per_strip + lane * R + 1;   // first row of this lane (1-based)
 			const int4 *sa_in = sa0 + (strip & 1) * scratch_stride;
 			const int2 *sb_in = sb0 + (strip & 1) * scratch_stride;
 			int4 *sa_out = sa0 + ((strip + 1) & 1) * scratch_stride;
 			int2 *sb_out = sb0 + ((strip + 1) & 1) * scratch_stride;
-			const int bj = (j <= lb) ? B[j - 1] : 0xfe;   // 0xfe never equals a base
-			// state of (row j, column i-1): starts at column 0 = {M,L} = ninf with len j
-			int m_left = ninf, l_left = ninf;
-			uint32_t pm_left = (uint32_t)j << 16, pl_left = (uint32_t)j << 16;
-			// diagonal (row j-1, column i-1): starts at column 0 of the row above
-			int m_d = (j == 1) ? 0 : ninf, l_d = ninf, u_d = -NW_OPEN - (j - 1) * NW_EXT;
-			uint32_t pm_d = (uint32_t)(j - 1) << 16, pl_d = pm_d, pu_d = pm_d;
-			// what this lane publishes to the lane below: its last cell
-			NwCell mine; mine.m = 0; mine.u = 0; mine.l = 0; mine.pm = 0; mine.pu = 0; mine.pl = 0;
+
+			int bj[R];
+			// per row: the cell just to the left (row j, column i-1) and, for the row BELOW it, the
+			// same cell one step older (the diagonal)
+			NwCell left[R];    // (row r, column i-1)
+			NwCell diag[R];    // (row r-1, column i-1): what row r adds its match score to
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const int j = j0 + r;
+				bj[r] = (j <= lb) ? B[j - 1] : 0xfe;   // 0xfe never equals a base
+				// column 0 of row j: M = L = ninf with len j (U[0] is never read through `left`)
+				left[r].m = ninf; left[r].l = ninf; left[r].u = 0;
+				left[r].pm = (uint32_t)j << 16; left[r].pl = (uint32_t)j << 16; left[r].pu = 0;
+				// column 0 of row j-1 as the first diagonal (GlobAlignE.cpp:164-170,250-256)
+				diag[r].m = (j == 1) ? 0 : ninf;
+				diag[r].l = ninf;
+				diag[r].u = -NW_OPEN - (j - 1) * NW_EXT;
+				diag[r].pm = diag[r].pl = diag[r].pu = (uint32_t)(j - 1) << 16;
+			}
+			NwCell mine;   // last row's newest cell, published to the lane below
+			mine.m = 0; mine.u = 0; mine.l = 0; mine.pm = 0; mine.pu = 0; mine.pl = 0;
 			uint32_t achunk = 0, achar = 0;
+			NwCell bchunk, bnext;   // boundary row of the previous strip, 32 columns per lane-chunk
+			bchunk.m = bchunk.u = bchunk.l = 0; bchunk.pm = bchunk.pu = bchunk.pl = 0;
+			bnext = bchunk;
+			if (strip > 0) {
+				// prefetch columns 1..32 (chunk 0); chunk c holds columns 32c+1 .. 32c+32
+				const int col = 1 + lane;
+				if (col <= la) {
+					const int4 x = __ldcg(&sa_in[col]);
+					const int2 y = __ldcg(&sb_in[col]);
+					bnext.m = x.x; bnext.u = x.y; bnext.l = x.z; bnext.pm = (uint32_t)x.w;
+					bnext.pu = (uint32_t)y.x; bnext.pl = (uint32_t)y.y;
+				}
+			}
 
 			const int nsteps = la + 31;
 			for (int t = 0; t < nsteps; t++) {
-				if ((t & 31) == 0) achunk = (t + lane < la) ? A[t + lane] : 0xff;
+				if ((t & 31) == 0) {
+					achunk = (t + lane < la) ? A[t + lane] : 0xff;
+					if (strip > 0) {
+						bchunk = bnext;
+						const int col = t + 32 + 1 + lane;   // next chunk, one chunk ahead
+						if (col <= la) {
+							const int4 x = __ldcg(&sa_in[col]);
+							const int2 y = __ldcg(&sb_in[col]);
+							bnext.m = x.x; bnext.u = x.y; bnext.l = x.z; bnext.pm = (uint32_t)x.w;
+							bnext.pu = (uint32_t)y.x; bnext.pl = (uint32_t)y.y;
+						}
+					}
+				}
 				// base of column t+1 enters at lane 0 and moves one lane down per step
 				const uint32_t a_in = __shfl_sync(MC_FULL_MASK, achunk, t & 31);
 				const uint32_t a_dn = __shfl_up_sync(MC_FULL_MASK, achar, 1);
 				achar = lane == 0 ? a_in : a_dn;
 
-				NwCell up;
-				up.m = __shfl_up_sync(MC_FULL_MASK, mine.m, 1);
-				up.u = __shfl_up_sync(MC_FULL_MASK, mine.u, 1);
-				up.l = __shfl_up_sync(MC_FULL_MASK, mine.l, 1);
-				up.pm = __shfl_up_sync(MC_FULL_MASK, mine.pm, 1);
-				up.pu = __shfl_up_sync(MC_FULL_MASK, mine.pu, 1);
-				up.pl = __shfl_up_sync(MC_FULL_MASK, mine.pl, 1);
+				// the row above this lane's first row, same column
+				NwCell up = nw_shfl_up(mine);
 				const int i = t - lane + 1;               // column (1-based)
-				if (lane == 0 && i <= la) {
-					if (strip == 0) {
-						// init row (GlobAlignE.cpp:137-160)
-						up.m = ninf; up.u = ninf; up.l = -NW_OPEN - i * NW_EXT;
-						up.pm = up.pu = up.pl = (uint32_t)i << 16;
-					} else {
-						const int4 x = __ldcg(&sa_in[i]);
-						const int2 y = __ldcg(&sb_in[i]);
-						up.m = x.x; up.u = x.y; up.l = x.z; up.pm = (uint32_t)x.w;
-						up.pu = (uint32_t)y.x; up.pl = (uint32_t)y.y;
-					}
+				if (strip > 0) {
+					const NwCell b = nw_shfl_from(bchunk, t & 31);   // lane 0's column is t+1
+					if (lane == 0) up = b;
+				} else if (lane == 0) {
+					// init row (GlobAlignE.cpp:137-160)
+					up.m = ninf; up.u = ninf; up.l = -NW_OPEN - i * NW_EXT;
+					up.pm = up.pu = up.pl = (uint32_t)i << 16;
 				}
 				if (i >= 1 && i <= la) {
-					// vertical gap
-					const int ub = up.m - NW_OPEN_EXT, uc = up.u - NW_EXT;
-					const bool ubeg = ub >= uc;
-					const int u = ubeg ? ub : uc;
-					const uint32_t pu = (ubeg ? up.pm : up.pu) + NW_LEN1;
-					// diagonal
-					const bool eq = achar == (uint32_t)bj;
-					const int s = eq ? 1 : -1;
-					int best = m_d; uint32_t pb_ = pm_d;
-					if (l_d > best) { best = l_d; pb_ = pl_d; }
-					if (u_d > best) { best = u_d; pb_ = pu_d; }
-					const int m = best + s;
-					const uint32_t pm = pb_ + NW_LEN1 + (eq ? 1u : 0u);
-					// horizontal gap on the current row
-					const int lb_ = m_left - NW_OPEN_EXT, lc = l_left - NW_EXT;
-					const bool lbeg = lb_ >= lc;
-					const int l = lbeg ? lb_ : lc;
-					const uint32_t pl = (lbeg ? pm_left : pl_left) + NW_LEN1;
-					// roll
-					m_d = up.m; l_d = up.l; u_d = up.u; pm_d = up.pm; pl_d = up.pl; pu_d = up.pu;
-					m_left = m; l_left = l; pm_left = pm; pl_left = pl;
-					mine.m = m; mine.u = u; mine.l = l; mine.pm = pm; mine.pu = pu; mine.pl = pl;
-					if (lane == 31 && strip + 1 < nstrips) {
-						__stcg(&sa_out[i], make_int4(m, u, l, (int)pm));
-						__stcg(&sb_out[i], make_int2((int)pu, (int)pl));
+#pragma unroll
+					for (int r = 0; r < R; r++) {
+						// vertical gap: from (row-1, i)
+						const int ub = up.m - NW_OPEN_EXT, uc = up.u - NW_EXT;
+						const bool ubeg = ub >= uc;
+						NwCell cur;
+						cur.u = ubeg ? ub : uc;
+						cur.pu = (ubeg ? up.pm : up.pu) + NW_LEN1;
+						// diagonal: from (row-1, i-1), tie order M, L, U
+						const bool eq = achar == (uint32_t)bj[r];
+						int best = diag[r].m; uint32_t pbst = diag[r].pm;
+						if (diag[r].l > best) { best = diag[r].l; pbst = diag[r].pl; }
+						if (diag[r].u > best) { best = diag[r].u; pbst = diag[r].pu; }
+						cur.m = best + (eq ? 1 : -1);
+						cur.pm = pbst + NW_LEN1 + (eq ? 1u : 0u);
+						// horizontal gap on the current row: from (row, i-1)
+						const int hb = left[r].m - NW_OPEN_EXT, hc = left[r].l - NW_EXT;
+						const bool hbeg = hb >= hc;
+						cur.l = hbeg ? hb : hc;
+						cur.pl = (hbeg ? left[r].pm : left[r].pl) + NW_LEN1;
+						// roll: (row-1, i) becomes the diagonal of (row, i+1); this cell the left of (row, i+1)
+						diag[r] = up;
+						left[r] = cur;
+						if (j0 + r == lb && i == la) {
+							// GlobAlignE.cpp:278-291: tie order M, L, U
+							int bs = cur.m; uint32_t bp = cur.pm;
+							if (cur.l > bs) { bs = cur.l; bp = cur.pl; }
+							if (cur.u > bs) { bs = cur.u; bp = cur.pu; }
+							res_sc = bs; res_p = bp;
+						}
+						up = cur;   // the next row of this lane sits right below
 					}
-					if (j == lb && i == la) {
-						// GlobAlignE.cpp:278-291: tie order M, L, U
-						int bs = m; uint32_t bp = pm;
-						if (l > bs) { bs = l; bp = pl; }
-						if (u > bs) { bs = u; bp = pu; }
-						res_sc = bs; res_p = bp;
+					mine = up;      // == last row's cell
+					if (lane == 31 && strip + 1 < nstrips) {
+						__stcg(&sa_out[i], make_int4(mine.m, mine.u, mine.l, (int)mine.pm));
+						__stcg(&sb_out[i], make_int2((int)mine.pu, (int)mine.pl));
 					}
 				}
 			}
 			__syncwarp();
 		}
 		// the lane that owned row lb holds the result
-		const int owner = (lb - 1) & 31;
+		const int owner = ((lb - 1) % (32 * R)) / R;
 		res_sc = __shfl_sync(MC_FULL_MASK, res_sc, owner);
 		res_p = __shfl_sync(MC_FULL_MASK, res_p, owner);
 		if (lane == 0) {

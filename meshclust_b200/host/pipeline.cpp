@@ -117,6 +117,7 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	const size_t n_points = (size_t)c.opt.sample_size, max_pts_from_one = (size_t)c.opt.pivots;
 	std::vector<int> points((size_t)n);
 	for (int64_t i = 0; i < n; i++) points[i] = (int)i;
+	Timer st;
 	// :672-675 unstable sort by length, then the median-length point
 	std::sort(points.begin(), points.end(), [&](int a, int b) { return ds.len[a] < ds.len[b]; });
 	const int begin_pt = points[points.size() / 2];
@@ -143,7 +144,9 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	std::vector<int32_t> prow(np);
 	for (size_t i = 0; i < np; i++) prow[i] = (int32_t)ds.row_of_id[pivots[i]];
 	std::vector<uint16_t> keys(np * (size_t)n);
+	const double t_first = st.lap();
 	GPU(mc_distance_keys(c.gpu, prow.data(), (int)np, keys.data()));
+	const double t_keys = st.lap();
 
 	// :694-701 per pivot: copy + unstable sort by distance to the pivot.  Independent per pivot, so
 	// the host threads can share them without changing any permutation.
@@ -157,6 +160,8 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	}
 	keys.clear();
 	keys.shrink_to_fit();
+	const double t_sorts = st.lap();
+	int rounds = 0;
 
 	// :703-721 binary search with alignment, all pivots in lock step (each search is independent)
 	std::vector<size_t> offset(np, (size_t)n / 4), pos(np, 2 * ((size_t)n / 4));
@@ -169,6 +174,7 @@ std::vector<Pair> trainer_split(Ctx &c) {
 			if (active[i]) { q.push_back({pivots[i], sorted[i][pos[i]]}); who.push_back(i); }
 		if (q.empty()) break;
 		const std::vector<double> algn = align_ids(c, q);
+		rounds++;
 		for (size_t t = 0; t < who.size(); t++) {
 			const size_t i = who[t];
 			if (algn[t] < cutoff) pos[i] -= offset[i];
@@ -179,6 +185,7 @@ std::vector<Pair> trainer_split(Ctx &c) {
 		}
 	}
 
+	printf("  [split: first sorts %.3fs, %zu x n distance keys %.3fs, pivot sorts %.3fs, %d alignment rounds %.3fs]\n", t_first, np, t_keys, t_sorts, rounds, st.lap());
 	// :723-765 ten picks below and ten above the boundary at evenly strided ranks
 	int aerr = 0;
 	HeaderPairLess less{&ds.fa.headers};
@@ -658,6 +665,7 @@ int run_pipeline(Options opt) {
 
 	// ---- upload in row order, encode, histograms (K1) -------------------------------------------
 	GPU(mc_ctx_create(&c.gpu, opt.device));
+	printf("  [gpu context %.2fs]\n", tm.lap());
 	{
 		std::vector<uint8_t> letters(ds.fa.letters.size());
 		std::vector<int64_t> offs((size_t)ds.n + 1, 0), seg_off((size_t)ds.n + 1, 0);
@@ -681,11 +689,13 @@ int run_pipeline(Options opt) {
 			} else segs.insert(segs.end(), buf, buf + 2 * ns);
 			seg_off[r + 1] = seg_off[r] + ns;
 		}
+		printf("  [row order + segments %.2fs]\n", tm.lap());
 		if (mc_load_sequences(c.gpu, letters.data(), offs.data(), ds.n, segs.data(), seg_off.data()) != MC_OK) {
 			fprintf(stderr, "meshclust: %s\n", mc_last_error());
 			abort();   // InvalidInputException in the reference
 		}
 	}
+	printf("  [upload + encode %.2fs]\n", tm.lap());
 	uint64_t largest = 0;
 	GPU(mc_build_histograms(c.gpu, c.k, 0, &c.tbytes, &largest));
 	printf("Using %d bit histograms\n", c.tbytes * 8);   // Runner.cpp:75-89
