@@ -636,6 +636,10 @@ extern "C" int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, i
 	MC_REQUIRE(ctx && ctx->have_seq, MC_ERR_STATE, "mc_align_pairs: load sequences first");
 	MC_REQUIRE(a && b && score && alen && matches && m >= 0, MC_ERR_ARG, "mc_align_pairs: bad arguments");
 	if (m == 0) return MC_OK;
+	const bool dbg = getenv("MC_DEBUG_TIMING") != nullptr;
+	auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+	double t_prev = now();
+	auto lap = [&](const char *what) { if (dbg) { const double t = now(); fprintf(stderr, "[mc_align_pairs m=%lld] %-22s %.4f s\n", (long long)m, what, t - t_prev); t_prev = t; } };
 	MC_CUDA(cudaSetDevice(ctx->device));
 	int rc = check_rows32(ctx, a, m);
 	if (rc) return rc;
@@ -651,8 +655,10 @@ extern "C" int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, i
 	int64_t nwarps = std::min<int64_t>(m, (int64_t)ctx->num_sms * 32);
 	// keep the scratch under ~4 GB
 	while (nwarps > ctx->num_sms && nwarps * 2 * stride * 24 > (4LL << 30)) nwarps /= 2;
+	lap("offsets D2H");
 	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)nwarps * 2 * stride * 16, (size_t)nwarps * 2 * stride * 8}));
 	if (rc) return rc;
+	lap("scratch");
 	Carve cv(ctx->d_scratch);
 	int32_t *d_a = cv.take<int32_t>(m), *d_b = cv.take<int32_t>(m), *d_s = cv.take<int32_t>(m), *d_l = cv.take<int32_t>(m), *d_i = cv.take<int32_t>(m);
 	void *d_sa = cv.take<uint8_t>((size_t)nwarps * 2 * stride * 16);
@@ -668,6 +674,7 @@ extern "C" int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, i
 	MC_CUDA(cudaMemcpyAsync(matches, d_i, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	lap("kernel + copies");
 	MC_REQUIRE(flags[2] == 0, MC_ERR_UNSUPPORTED, "a pair is longer than 65535 bases in total; not supported on the GPU path");
 	return MC_OK;
 }
