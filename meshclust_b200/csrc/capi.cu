@@ -5,6 +5,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "mc_common.cuh"
 
@@ -358,6 +359,34 @@ extern "C" int mc_set_model(mc_ctx *ctx, const double *mins, const double *maxs,
 		ctx->model.maxs[i] = i < nlookup ? maxs[i] : 1.0;
 	}
 	for (int i = 0; i < 5; i++) ctx->model.w[i] = i <= nfeat ? weights[i] : 0.0;
+	// division-free normalisation: allowed per feature only when q + (a - b*q)*RN(1/b) reproduces
+	// a / b bit for bit on a dense probe of the feature's value range (and on every special value)
+	ctx->model.fast_div = 0;
+	for (int j = 0; j < 5; j++) {
+		const double lo = ctx->model.mins[j], b = ctx->model.maxs[j] - lo, y = 1.0 / b;
+		ctx->model.rcp[j] = y;
+		if (!(std::isfinite(b) && std::isfinite(y) && b != 0.0 && std::isfinite(lo)) || std::fabs(b) < 1e-290 || std::fabs(b) > 1e290) continue;
+		bool ok = true;
+		uint64_t rng = 0x9E3779B97F4A7C15ull + (uint64_t)j;
+		for (int t = 0; t < 200000 && ok; t++) {
+			rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+			const double u = (double)(rng >> 11) * (1.0 / 9007199254740992.0);   // [0,1)
+			double a;
+			switch (t & 3) {
+			case 0: a = (u * 1.2 - 0.1) * b; break;                // inside the trained range
+			case 1: a = (u * 40.0 - 20.0) * b; break;               // far outside it
+			case 2: a = std::ldexp(u - 0.5, (int)(rng & 63) - 40) * b; break;   // many magnitudes
+			default: a = std::floor(u * 65536.0) - lo; break;      // integer-valued raw features
+			}
+			const double q = a * y, r = std::fma(-b, q, a), fast = std::fma(r, y, q), ref = a / b;
+			if (!(fast == ref) && !(fast != fast && ref != ref)) ok = false;
+		}
+		for (double a : {0.0, -0.0, b, -b, 1.0, -1.0, lo, -lo}) {
+			const double q = a * y, r = std::fma(-b, q, a), fast = std::fma(r, y, q), ref = a / b;
+			if (memcmp(&fast, &ref, 8) != 0) ok = false;
+		}
+		if (ok) ctx->model.fast_div |= 1 << j;
+	}
 	ctx->model.nfeat = nfeat;
 	ctx->model.valid = 1;
 	return MC_OK;

@@ -42,6 +42,8 @@ struct McModel {
 	double mins[5];
 	double maxs[5];
 	double w[5];   // w[0] bias, w[1..nfeat]
+	double rcp[5]; // correctly rounded 1 / (maxs - mins), for the division-free normalisation
+	int fast_div;  // bit j set: (x - mins[j]) / (maxs[j] - mins[j]) may use rcp[j] (validated on the host)
 	int nfeat;     // 3 or 4
 	int valid;
 };
@@ -169,6 +171,65 @@ __device__ __forceinline__ void mc_eval_model(const McModel &m, const double c_r
 	sum = fma(m.w[2], f[1], sum);
 	sum = fma(m.w[3], f[2], sum);
 	if (m.nfeat >= 4) sum = fma(m.w[4], f[3], sum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same epilogue, trimmed for the streaming scan kernel (bit-identical results):
+//  * uint8 histograms with k <= 6 keep every integer quantity below 2^31, so the moments are
+//    32-bit IMADs and the conversions single I2F instructions instead of 64-bit emulation;
+//  * mag / N is a multiplication by the exact power of two 1/N;
+//  * a quotient by a per-model constant b (the normalisation ranges) is q = a*y, r = a - b*q,
+//    q' = q + r*y with y = RN(1/b): the correctly rounded a/b (Markstein), which mc_set_model
+//    additionally verifies on the host against true division before setting the fast_div bit;
+//  * KULCZYNSKI2 is skipped entirely for 3-feature models.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mc_div_const(double a, double b, double y) {
+	const double q = a * y;
+	const double r = fma(-b, q, a);
+	return fma(r, y, q);
+}
+
+template <int TB>
+__device__ __forceinline__ void mc_scan_epilogue(const McModel &m, uint64_t S64, uint64_t D64, uint64_t lp,
+                                                  uint64_t mp64, uint64_t sp64, uint64_t lq, uint64_t mq64,
+                                                  uint64_t sq64, int N, double invN, double &f0, double &sum) {
+	double c[5];
+	if constexpr (TB == 1) {
+		const uint32_t S = (uint32_t)S64, mp = (uint32_t)mp64, mq = (uint32_t)mq64;
+		c[0] = (double)(lp > lq ? lp - lq : lq - lp);
+		c[1] = (double)(2u * S) / (double)(mp + mq);
+		c[2] = (double)(int)(mp + mq - 2u * S);
+		const double dap = (double)mp * invN, daq = (double)mq * invN;
+		const int ap = (int)round(dap), aq = (int)round(daq);
+		const int np = (int)(uint32_t)sp64 - 2 * ap * (int)mp + N * ap * ap;
+		const int nq = (int)(uint32_t)sq64 - 2 * aq * (int)mq + N * aq * aq;
+		const int dot = (int)(uint32_t)D64 - aq * (int)mp - ap * (int)mq + N * ap * aq;
+		const double prod = (double)((long long)np * (long long)nq);
+		c[3] = (double)dot / sqrt(prod > 0.5 ? prod : 0.5);
+		if (m.nfeat >= 4) {
+			const double coeff = N * (dap + daq) / (2 * dap * daq);
+			c[4] = coeff * (double)S;
+		} else {
+			c[4] = 0.0;
+		}
+	} else {
+		mc_raw_features(S64, D64, lp, mp64, sp64, lq, mq64, sq64, N, m.nfeat >= 4, c);
+	}
+	double v[5];
+#pragma unroll
+	for (int j = 0; j < 5; j++) {
+		if (j == 4 && m.nfeat < 4) { v[j] = 0.0; continue; }
+		const double num = c[j] - m.mins[j], den = m.maxs[j] - m.mins[j];
+		const double q = ((m.fast_div >> j) & 1) ? mc_div_const(num, den, m.rcp[j]) : num / den;
+		v[j] = (j == 1 || j == 4) ? q : 1 - q;
+	}
+	const double f1 = (1.0 * (v[0] * v[0])) * (v[2] * v[2]);
+	f0 = (1.0 * v[0]) * v[1];
+	sum = m.w[0];
+	sum = fma(m.w[1], f0, sum);
+	sum = fma(m.w[2], f1, sum);
+	sum = fma(m.w[3], 1.0 * v[3], sum);
+	if (m.nfeat >= 4) sum = fma(m.w[4], (1.0 * (v[0] * v[0])) * (v[4] * v[4]), sum);
 }
 
 // DivergencePoint::distance (DivergencePoint.cpp:68-81), with the fused 1 - f*f of the compiled

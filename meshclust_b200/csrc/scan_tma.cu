@@ -108,6 +108,10 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 	const int lane = threadIdx.x & 31;
 	const int wib = threadIdx.x >> 5;
 	TRACE(0);
+	// programmatic dependent launch: let the next scan of the stream start its launch + prologue
+	// while this one still runs; it blocks at griddepcontrol.wait below until this grid has
+	// completed and flushed (alive flags / marks written here are read there)
+	asm volatile("griddepcontrol.launch_dependents;");
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < T::NS; s++) {
@@ -118,6 +122,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 	TRACE(1);
 
 	// tiles of RT rows, dealt round-robin to CTAs, then round-robin to the CTA's consumer warps
@@ -174,11 +179,13 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			if (have_row) my_aux = *reinterpret_cast<const McRowAux *>(st + T::ROW_BYTES + (size_t)lane * 32);
 			// row p of the tile is reduced by lane group p / LPP in iteration p % LPP
 			PairAcc<TB> part[C::LPP];
+			// rows past the end of a partial tile hold stale bytes of an older tile: harmless, their
+			// lanes never reach the epilogue (have_row), so the reduction itself is branch-free
 #pragma unroll
 			for (int it = 0; it < C::LPP; it++) {
 				const int p = g * C::LPP + it;
 				PairAcc<TB> acc;
-				if (p < T::RT && row0 + p <= hi) {
+				if (T::RT == 32 || p < T::RT) {
 					const uint8_t *row = st + (size_t)p * RB;
 #pragma unroll
 					for (int c = 0; c < C::CH; c++) {
@@ -197,13 +204,12 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 				unsigned flag = 0;
 				if (my_aux.alive) {
 					const uint64_t S = tot.summin(my_aux.mag, mq);
-					double c[5], f[4], sum;
-					mc_raw_features(S, tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, model.nfeat >= 4, c);
-					mc_eval_model(model, c, f, sum);
+					double f0, sum;
+					mc_scan_epilogue<TB>(model, S, tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
 					flag = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1u : 0u;
 					mine.n_eval++;
 					mine.n_pos += flag;
-					if (f[0] > mine.best_f0) { mine.best_f0 = f[0]; mine.best_row = row_mine; }
+					if (f0 > mine.best_f0) { mine.best_f0 = f0; mine.best_row = row_mine; }
 					if (flag && remove_marked) aux[row_mine].alive = 0;
 				}
 				marks[row_mine] = (uint8_t)flag;
@@ -266,9 +272,20 @@ static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, i
 	int64_t blocks = ctx->num_sms;
 	if (blocks > ntiles) blocks = ntiles;
 	if (blocks < 1) blocks = 1;
-	scan_tma_kernel<TB, RB><<<(int)blocks, 32 * (1 + T::NCW), smem, ctx->stream>>>(
-		(const uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_marks, lo, hi, center_row, ctx->model, remove_marked,
-		(ScanPartial *)partials_dev);
+	static const bool no_pdl = getenv("MC_NO_PDL") != nullptr;
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3((unsigned)blocks);
+	cfg.blockDim = dim3(32 * (1 + T::NCW));
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = ctx->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = no_pdl ? 0 : 1;
+	MC_CUDA(cudaLaunchKernelEx(&cfg, scan_tma_kernel<TB, RB>, (const uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_marks,
+	                           (long long)lo, (long long)hi, (long long)center_row, ctx->model, remove_marked,
+	                           (ScanPartial *)partials_dev));
 	*nparts_out = (int)blocks;
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
