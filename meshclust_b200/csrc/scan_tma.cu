@@ -122,7 +122,6 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();
-	asm volatile("griddepcontrol.wait;" ::: "memory");
 	TRACE(1);
 
 	// tiles of RT rows, dealt round-robin to CTAs, then round-robin to the CTA's consumer warps
@@ -141,6 +140,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		// one lane never runs more than one phase ahead of its slot's barriers.
 		if (lane < T::NS) {
 			const int w = lane / T::D;
+			bool first = true;
 			for (long long u = lane % T::D; ; u += T::D) {
 				const long long jj = u * T::NCW + w;          // u-th tile of consumer w
 				if (jj >= nmine) break;
@@ -151,9 +151,15 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 				if (nr > T::RT) nr = T::RT;
 				uint8_t *dst = smem + (size_t)lane * T::STAGE_BYTES;
 				mbar_expect_tx(&full_bar[lane], (uint32_t)(nr * RB + nr * 32));
+				// histogram rows are immutable: their copy may start while the previous scan of the
+				// stream is still finishing; the constants carry its alive flags, so they wait for it
 				tma_bulk_g2s(dst, hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[lane]);
+				if (first) { asm volatile("griddepcontrol.wait;" ::: "memory"); first = false; }
 				tma_bulk_g2s(dst + T::ROW_BYTES, aux + r0, (uint32_t)(nr * 32), &full_bar[lane]);
 			}
+			if (first) asm volatile("griddepcontrol.wait;" ::: "memory");
+		} else {
+			asm volatile("griddepcontrol.wait;" ::: "memory");
 		}
 	} else if (wib - 1 < T::NCW) {
 		// ===================== consumers =====================
@@ -163,6 +169,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		CenterRegs<RB> cen;
 		cen.load(crow, r);
 		const uint64_t lq = aux[center_row].len, mq = aux[center_row].mag, sq = aux[center_row].sq;
+		asm volatile("griddepcontrol.wait;" ::: "memory");   // before the first global write of this warp
 
 		long long u = 0;
 		for (long long jj = cw; jj < nmine; jj += T::NCW, u++) {
