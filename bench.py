@@ -327,10 +327,18 @@ def main():
     bytes_per_launch = n * (nbins + 33)
     launch_us = dev_ms * 1e3 / (args.steps * S)
     achieved = bytes_per_launch / (launch_us * 1e-6) / 1e9
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel and shape from the
+    # committed `ncu --set full` capture (profiles/scan_traffic.json), not measured in this run
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))[f"c2_{nbins}"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                "kernel": f"scan_kernel<1,{nbins}>", "launch_us": round(launch_us, 3),
-                "algorithmic_bytes_per_launch": bytes_per_launch}
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "kernel": f"scan_tma_kernel<1,{nbins}>", "launch_us": round(launch_us, 3),
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "note": "back-to-back launches on one stream (programmatic dependent launch); launch_us = CUDA-event time / launches"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

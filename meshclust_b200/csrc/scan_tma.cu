@@ -63,7 +63,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 }
 
 // ---- geometry ----------------------------------------------------------------------------------
-constexpr int TSCAN_MAX_CONSUMERS = 16;
+constexpr int TSCAN_MAX_CONSUMERS = 24;   // small rows: one tile per warp hides the FP64 epilogue latency of short scans
 constexpr int TSCAN_MAX_STAGES = 32;
 constexpr int TSCAN_SMEM_BUDGET = 216 * 1024;
 
@@ -79,7 +79,8 @@ struct TileCfg {
 	static constexpr int STAGE_BYTES = ((ROW_BYTES + AUX_BYTES + 127) / 128) * 128;
 	static constexpr int NS_RAW = TSCAN_SMEM_BUDGET / STAGE_BYTES;
 	static constexpr int NS_CAP = NS_RAW > TSCAN_MAX_STAGES ? TSCAN_MAX_STAGES : NS_RAW;
-	static constexpr int NCW = NS_CAP > TSCAN_MAX_CONSUMERS ? TSCAN_MAX_CONSUMERS : NS_CAP;   // active consumer warps
+	static constexpr int MAXC = RB <= 256 ? TSCAN_MAX_CONSUMERS : 16;
+	static constexpr int NCW = NS_CAP > MAXC ? MAXC : NS_CAP;   // active consumer warps
 	static constexpr int D = NS_CAP / NCW;                                                   // ring depth per consumer
 	static constexpr int NS = NCW * D;
 	static_assert(NS_CAP >= 2, "row too wide for the staged scan");
