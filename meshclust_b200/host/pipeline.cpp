@@ -575,6 +575,29 @@ void mean_shift(Ctx &c, BVec &bv) {
 			GPU(mc_update_centers(c.gpu, centers.data(), nc, cand.data(), (int64_t)cand.size(), cb.data(), ce.data(), next.data()));
 			for (int64_t j = 0; j < nc; j++)
 				if (next[j] >= 0 && next[j] != part[j].center_row) part[j].center_row = next[j];
+		} else {
+			// --align: a Center holds a CLONE, and DivergencePoint::clone() does not
+			// copy the sequence (DivergencePoint.h:37-43, Center.h:14).  Feature::align therefore aligns
+			// a member against an EMPTY string (identity 0/len = 0) unless that id pair was cached in
+			// Phase A, and caches whatever it computed.  No alignment is needed here, only the cache.
+			for (int64_t j = 0; j < nc; j++) {
+				const int64_t cid = ds.id_of_row[part[j].center_row];
+				std::vector<int64_t> good;
+				for (int64_t q = cb[j]; q < ce[j]; q++) {
+					const int64_t pid = ds.id_of_row[cand[q]];
+					const auto key = pid < cid ? std::make_pair(pid, cid) : std::make_pair(cid, pid);
+					auto it = cache.tab.find(key);
+					double v;
+					if (it != cache.tab.end()) v = it->second;
+					else { v = ds.len[pid] > 0 ? 0.0 : std::nan(""); cache.tab[key] = v; }
+					const double sum = std::fma(c.model.w[1], (v - 0.0) / (1.0 - 0.0), c.model.w[0]);
+					if (std::round(1.0 / (1 + std::exp(-sum))) == 1.0) good.push_back(cand[q]);
+				}
+				if (good.empty()) continue;
+				int64_t nearest = -1;
+				GPU(mc_mean_nearest(c.gpu, good.data(), (int64_t)good.size(), 0, &nearest, nullptr));
+				if (nearest >= 0 && nearest != part[j].center_row) part[j].center_row = nearest;
+			}
 		}
 		// merge (ClusterFactory.cpp:427-493 with Trainer::merge, Trainer.cpp:129-157): the pair
 		// evaluations of a pass do not depend on the merges of that pass, so they go in one batch
@@ -588,6 +611,20 @@ void mean_shift(Ctx &c, BVec &bv) {
 		std::vector<double> f0(pa.size());
 		std::vector<uint8_t> fl(pa.size());
 		if (!pa.empty() && !c.model.align) GPU(mc_pair_classify(c.gpu, pa.data(), pb.data(), (int64_t)pa.size(), nullptr, f0.data(), fl.data(), nullptr));
+		if (c.model.align) {
+			// Trainer::merge on two clones: both strings are empty -> 0/0 = NaN unless the pair is cached
+			for (size_t q = 0; q < pa.size(); q++) {
+				const int64_t ia = ds.id_of_row[pa[q]], ib = ds.id_of_row[pb[q]];
+				const auto key = ia < ib ? std::make_pair(ia, ib) : std::make_pair(ib, ia);
+				auto it = cache.tab.find(key);
+				double v;
+				if (it != cache.tab.end()) v = it->second;
+				else { v = std::nan(""); cache.tab[key] = v; }
+				const double sum = std::fma(c.model.w[1], (v - 0.0) / (1.0 - 0.0), c.model.w[0]);
+				f0[q] = v;
+				fl[q] = std::round(1.0 / (1 + std::exp(-sum))) == 1.0;
+			}
+		}
 		for (int64_t i = 0; i < nc; i++) {
 			std::pair<long, double> best(0, DBL_MIN);   // Trainer.cpp:135 initial value: DBL_MIN is positive
 			for (int64_t q = first_pair[i]; q < first_pair[i + 1]; q++) {

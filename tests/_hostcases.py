@@ -46,6 +46,9 @@ CASES = {
     "E": ([("E.fa", dict(n=1200, ntemp=40, lmin=250, lmax=400, mu=0.02, seed=16, related=0.08))], ["--id", "0.93"]),
     # BASELINE.json configs[0] in full: 10k synthetic 1 kb sequences from 100 mutated templates
     "c1_full": ([("c1.fa", dict(config="c1"))], ["--id", "0.90", "--kmer", "3"]),
+    # --align (forced) and automatic alignment below 60 % identity (Runner.cpp:32-34)
+    "G": ([("G.fa", dict(n=500, ntemp=10, lmin=180, lmax=240, mu=0.08, seed=18))], ["--id", "0.75", "--align"]),
+    "H": ([("H.fa", dict(n=400, ntemp=8, lmin=150, lmax=260, mu=0.15, seed=19))], ["--id", "0.55", "--delta", "3"]),
     "F": ([("F.fa", dict(n=1300, ntemp=20, lmin=260, lmax=420, mu=0.03, seed=17, iupac=True))],
           ["--id", "0.90", "--kmer", "4", "--sample", "2000", "--pivot", "10"]),
 }
