@@ -13,7 +13,7 @@
 int mc_upload_lut();
 int mc_launch_encode(mc_ctx *ctx);
 int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes);
-int mc_launch_point_stats(mc_ctx *ctx);
+int mc_launch_point_stats(mc_ctx *ctx, const uint64_t *lens_dev);
 int mc_launch_alive_reset(mc_ctx *ctx);
 int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, void *partials_dev, int *nparts_out);
 int64_t mc_scan_max_blocks(mc_ctx *ctx);
@@ -319,9 +319,13 @@ extern "C" int mc_load_histograms(mc_ctx *ctx, const void *hists, int tbytes, in
 	if (rc) return rc;
 	const size_t bytes = (size_t)n * ctx->nbins * tbytes;
 	MC_CUDA(cudaMemcpyAsync(ctx->d_hist, hists, bytes, cudaMemcpyHostToDevice, ctx->stream));
-	MC_CUDA(cudaMemcpy2DAsync(&ctx->d_aux[0].len, sizeof(McRowAux), lens, 8, 8, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-	rc = mc_launch_point_stats(ctx);
+	rc = mc_ensure_scratch(ctx, (size_t)n * 8 + 256);
 	if (rc) return rc;
+	MC_CUDA(cudaMemcpyAsync(ctx->d_scratch, lens, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+	rc = mc_launch_point_stats(ctx, (const uint64_t *)ctx->d_scratch);
+	if (rc) return rc;
+	// stream-ordered: later calls on this context queue behind the copy; the host buffers may be
+	// reused once the copies have been consumed
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->have_hist = true;
 	return MC_OK;

@@ -9,7 +9,7 @@
 // ---------------------------------------------------------------------------------------------
 template <int TB>
 __global__ void point_stats_kernel(const uint8_t *__restrict__ hist, int nbins, int64_t n,
-                                   McRowAux *__restrict__ aux) {
+                                   const uint64_t *__restrict__ lens, McRowAux *__restrict__ aux) {
 	const int lane = threadIdx.x & 31;
 	const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -27,19 +27,23 @@ __global__ void point_stats_kernel(const uint8_t *__restrict__ hist, int nbins, 
 			m += __shfl_xor_sync(MC_FULL_MASK, m, o);
 			s += __shfl_xor_sync(MC_FULL_MASK, s, o);
 		}
-		if (lane == 0) { aux[row].mag = m; aux[row].sq = s; aux[row].alive = 1; aux[row].pad = 0; }
+		if (lane == 0) {
+			McRowAux a;
+			a.len = lens[row]; a.mag = m; a.sq = s; a.alive = 1; a.pad = 0;
+			aux[row] = a;
+		}
 	}
 }
 
-int mc_launch_point_stats(mc_ctx *ctx) {
+int mc_launch_point_stats(mc_ctx *ctx, const uint64_t *lens_dev) {
 	const int threads = 256;
 	int64_t blocks = (ctx->n * 32 + threads - 1) / threads;
 	if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
 	if (blocks < 1) blocks = 1;
 	if (ctx->tbytes == 1)
-		point_stats_kernel<1><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, ctx->d_aux);
+		point_stats_kernel<1><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, lens_dev, ctx->d_aux);
 	else
-		point_stats_kernel<2><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, ctx->d_aux);
+		point_stats_kernel<2><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, lens_dev, ctx->d_aux);
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
