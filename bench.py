@@ -156,6 +156,7 @@ def cpu_reference_rate(hist, lens, mins, maxs, w, centers, target_s: float, step
     try:
         if _oracle.have_ref():
             lib, kind = _oracle.ref(), "reference"
+            lib.lib.ref_set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1
             cores = int(lib.lib.ref_max_threads())
             ps = lib.pointset(sub, sublen)
             lib.pointset_set_model(ps, mins, maxs, 4)
@@ -263,21 +264,20 @@ def main():
         hi = lo + n - 1
         return cr, lo, hi
 
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
-    def exchange(results):
-        """the real exchange of a sharded get_close: positives summed, (f0, row) arg-maxed"""
-        if world == 1:
-            return results
-        out = sharding.combine_scan_results(results, rank * n, torch.device("cuda", local_rank))
-        torch.cuda.current_stream().synchronize()
-        return out
+    # N > 1: the context launches on torch's current stream, the per-scan summaries are folded on the
+    # device and all-gathered over NCCL (one collective per step, 32 bytes per scan and rank)
+    if world > 1:
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        records = torch.zeros((S, 4), dtype=torch.int64, device="cuda")
 
     def run_step(step):
         cr, lo, hi = step_args(step)
         ctx.scan_enqueue_many(cr, lo, hi, False, 0)
         if world > 1:
-            exchange(ctx.scan_collect(0, S))
+            ctx.scan_fold_dev(0, S, records.data_ptr())
+            return sharding.combine_scan_records(records, n)
+        return None
 
     for i in range(args.warmup):
         run_step(i)
@@ -289,6 +289,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record(stream)

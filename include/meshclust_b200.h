@@ -144,6 +144,14 @@ int mc_scan_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *res);
 int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo,
                          const int64_t *hi, int count, int remove_marked, int slot0);
 
+/* Device-side fold for sharded scans: reduces the partial records of nslots enqueued scans to one
+ * mc_scan_result each, written to out_dev (DEVICE memory, nslots records) on the context's stream,
+ * so a multi-GPU caller can hand them to a collective without a host round trip. */
+int mc_scan_fold_dev(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *out_dev);
+/* Adopt an externally owned cudaStream_t (e.g. the stream a communication library orders against)
+ * for every later launch of this context; NULL restores the context's own stream. */
+int mc_set_stream(mc_ctx *ctx, void *stream);
+
 /* ---- stage 3: mean-shift centers --------------------------------------------------------- */
 
 /* get_mean (ClusterFactory.cpp:382-425): the member whose histogram is nearest

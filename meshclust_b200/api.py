@@ -31,7 +31,7 @@ EXPORTS = [
     "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_copy_digits",
     "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
     "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
-    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_mean_nearest", "mc_update_centers", "mc_align_pairs",
+    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_update_centers", "mc_align_pairs",
     "mc_kmer_histograms_host", "mc_scan_host",
 ]
 
@@ -232,6 +232,13 @@ class Context:
         hi = np.ascontiguousarray(hi, np.int64)
         _check(_lib.mc_scan_enqueue_many(self._h, _p(cr), _p(lo), _p(hi), C.c_int(cr.size),
                                          C.c_int(1 if remove_marked else 0), C.c_int(slot0)))
+
+    def scan_fold_dev(self, slot0: int, nslots: int, out_dev_ptr: int):
+        """fold nslots scans into mc_scan_result records at a DEVICE address (e.g. tensor.data_ptr())"""
+        _check(_lib.mc_scan_fold_dev(self._h, C.c_int(slot0), C.c_int(nslots), C.c_void_p(out_dev_ptr)))
+
+    def set_stream(self, stream_ptr: int):
+        _check(_lib.mc_set_stream(self._h, C.c_void_p(stream_ptr)))
 
     def scan_collect(self, slot0: int, nslots: int):
         res = (ScanResult * nslots)()

@@ -107,6 +107,7 @@ extern "C" int mc_ctx_create(mc_ctx **out, int device) {
 	ctx->num_sms = prop.multiProcessorCount;
 	lap("cudaGetDeviceProperties");
 	MC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	ctx->own_stream = ctx->stream;
 	MC_CUDA(cudaMalloc(&ctx->d_ticket, 16 * sizeof(unsigned int)));
 	MC_CUDA(cudaMemsetAsync(ctx->d_ticket, 0, 16 * sizeof(unsigned int), ctx->stream));
 	MC_CUDA(cudaMalloc(&ctx->d_flags, 16 * sizeof(unsigned int)));
@@ -150,12 +151,19 @@ extern "C" void mc_ctx_destroy(mc_ctx *ctx) {
 	cudaFreeHost(ctx->h_pinned);
 	cudaFree(ctx->d_ticket);
 	cudaFree(ctx->d_flags);
-	cudaStreamDestroy(ctx->stream);
+	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
 
 extern "C" void *mc_stream(mc_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" int64_t mc_launch_count(mc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int mc_set_stream(mc_ctx *ctx, void *stream) {
+	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+	return MC_OK;
+}
 
 extern "C" int mc_sync(mc_ctx *ctx) {
 	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
@@ -558,6 +566,19 @@ extern "C" int mc_scan_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int6
 	if (rc) return rc;
 	return mc_launch_scan(ctx, center_row, lo, hi, remove_marked,
 	                      (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result), &ctx->slot_nparts[slot]);
+}
+
+int mc_launch_scan_fold(mc_ctx *ctx, const void *slots_dev, const int *nparts_dev, int nslots, void *out_dev);
+
+extern "C" int mc_scan_fold_dev(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *out_dev) {
+	MC_REQUIRE(ctx && out_dev, MC_ERR_ARG, "bad arguments");
+	MC_REQUIRE(slot0 >= 0 && nslots > 0 && slot0 + nslots <= MC_SCAN_SLOTS, MC_ERR_ARG, "slot range invalid");
+	MC_REQUIRE(ctx->d_scan_slots, MC_ERR_STATE, "nothing was enqueued");
+	int rc = mc_ensure_scratch(ctx, (size_t)MC_SCAN_SLOTS * sizeof(int) + 256);
+	if (rc) return rc;
+	int *d_np = (int *)ctx->d_scratch;
+	MC_CUDA(cudaMemcpyAsync(d_np, ctx->slot_nparts + slot0, (size_t)nslots * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+	return mc_launch_scan_fold(ctx, (uint8_t *)ctx->d_scan_slots + (size_t)slot0 * MC_SCAN_PARTS * sizeof(mc_scan_result), d_np, nslots, out_dev);
 }
 
 extern "C" int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo, const int64_t *hi,

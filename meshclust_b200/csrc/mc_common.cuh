@@ -69,6 +69,7 @@ struct mc_ctx {
 	int device = 0;
 	int num_sms = MC_NUM_SMS_FALLBACK;
 	cudaStream_t stream = nullptr;
+	cudaStream_t own_stream = nullptr;
 	int64_t launches = 0;
 
 	// sequences

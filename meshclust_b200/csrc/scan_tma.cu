@@ -262,6 +262,36 @@ extern "C" int mc_debug_scan_trace(unsigned long long *out) {
 }
 #endif
 
+// one warp per slot: fold its partial records (same rule as the host fold)
+__global__ void scan_fold_kernel(const ScanPartial *__restrict__ slots, const int *__restrict__ nparts, int nslots,
+                                 ScanPartial *__restrict__ out) {
+	const int lane = threadIdx.x & 31;
+	const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (s >= nslots) return;
+	const ScanPartial *p = slots + (size_t)s * MC_SCAN_PARTS;
+	ScanPartial b;
+	b.n_eval = 0; b.n_pos = 0; b.best_row = -1; b.best_f0 = -1.0;
+	for (int i = lane; i < nparts[s]; i += 32) tscan_merge(b, p[i]);
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		ScanPartial other;
+		other.n_eval = __shfl_xor_sync(MC_FULL_MASK, b.n_eval, o);
+		other.n_pos = __shfl_xor_sync(MC_FULL_MASK, b.n_pos, o);
+		other.best_row = __shfl_xor_sync(MC_FULL_MASK, b.best_row, o);
+		other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, b.best_f0, o);
+		tscan_merge(b, other);
+	}
+	if (lane == 0) out[s] = b;
+}
+
+int mc_launch_scan_fold(mc_ctx *ctx, const void *slots_dev, const int *nparts_dev, int nslots, void *out_dev) {
+	const int threads = 128;
+	scan_fold_kernel<<<(nslots * 32 + threads - 1) / threads, threads, 0, ctx->stream>>>((const ScanPartial *)slots_dev, nparts_dev, nslots, (ScanPartial *)out_dev);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
 // rows narrower than 16 bytes (k = 1) and rows too wide for two stages keep the direct-load kernel
 int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                           void *partials_dev, int *nparts_out);

@@ -41,3 +41,34 @@ def shard_bounds(n: int, world: int, rank: int):
     base, extra = divmod(n, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def combine_scan_records(records: torch.Tensor, rows_per_rank: int):
+    """Device path: `records` is an int64 tensor [S, 4] holding S mc_scan_result records
+    (n_eval, n_pos, best_row, bits of best_f0) of this rank.  One all-gather, then the fold on the
+    host.  Returns global tuples like combine_scan_results."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world > 1:
+        if dist.get_backend() == "nccl":
+            gathered = torch.empty((world,) + tuple(records.shape), dtype=records.dtype, device=records.device)
+            dist.all_gather_into_tensor(gathered, records)
+        else:   # gloo (CPU tests)
+            parts = [torch.empty_like(records) for _ in range(world)]
+            dist.all_gather(parts, records)
+            gathered = torch.stack(parts)
+    else:
+        gathered = records.unsqueeze(0)
+    g = gathered.cpu()
+    f0 = g[:, :, 3].contiguous().view(torch.float64)
+    out = []
+    for s in range(g.shape[1]):
+        n_eval = int(g[:, s, 0].sum())
+        n_pos = int(g[:, s, 1].sum())
+        best_row, best_f0 = -1, -1.0
+        for w in range(world):                      # ranks hold ascending row blocks: first max wins
+            r = int(g[w, s, 2])
+            v = float(f0[w, s])
+            if r >= 0 and v > best_f0:
+                best_f0, best_row = v, r + w * rows_per_rank
+        out.append((n_eval, n_pos, best_row, best_f0))
+    return out

@@ -37,8 +37,17 @@ def _worker(rank, world, port, f0_all, flags_all, q):
     lo, hi = sharding.shard_bounds(n, world, rank)
     local = [_single_rank_scan(f0_all[s, lo:hi], flags_all[s, lo:hi]) for s in range(f0_all.shape[0])]
     got = sharding.combine_scan_results(local, lo, torch.device("cpu"))
+    # device-record path (one all-gather): same answer.  It assumes equal blocks per rank, so it is
+    # fed blocks of the first `world * (n // world)` rows only.
+    per = n // world
+    rec = torch.zeros((f0_all.shape[0], 4), dtype=torch.int64)
+    for s in range(f0_all.shape[0]):
+        t = _single_rank_scan(f0_all[s, rank * per:(rank + 1) * per], flags_all[s, rank * per:(rank + 1) * per])
+        rec[s, 0], rec[s, 1], rec[s, 2] = t[0], t[1], t[2]
+        rec[s, 3] = int(np.float64(t[3]).view(np.int64))
+    got2 = sharding.combine_scan_records(rec, per)
     if rank == 0:
-        q.put(got)
+        q.put((got, got2))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -60,11 +69,14 @@ def test_sharded_scan_exchange(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, f0, flags, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = q.get(timeout=120)
+    got, got2 = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert got == want
+    per = n // world
+    want2 = [_single_rank_scan(f0[s, :per * world], flags[s, :per * world]) for s in range(scans)]
+    assert got2 == want2
     assert want[1][2] == 10 and want[2][2] == -1 and want[3][2] == 900
 
 
