@@ -414,11 +414,14 @@ def cli_leg(letters, offs, tmpl, cfg):
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             raise RuntimeError(r.stderr[-200:])
-        m = re.search(r"gpu context ([0-9.]+)s", r.stdout)
-        ctx_s = float(m.group(1)) if m else 0.0
+        # the CUDA context is created on a helper thread while the FASTA is read; only the part the
+        # main thread had to wait for is start-up cost on the critical path
+        m = re.search(r"gpu context ([0-9.]+)s on a helper thread, waited ([0-9.]+)s", r.stdout)
+        ctx_s = float(m.group(2)) if m else 0.0
         ncl = open(os.path.join(d, "o.clstr")).read().count(">Cluster")
         res = {"workload": "c2 full (100k x 1.5 kb), bin/meshclust --id 0.97 --kmer 4", "wall_s": round(wall, 3),
-               "cuda_context_s": round(ctx_s, 3), "value": cfg.n / wall, "value_excluding_cuda_context": cfg.n / max(wall - ctx_s, 1e-9),
+               "cuda_context_wait_s": round(ctx_s, 3), "value": cfg.n / wall, "value_excluding_cuda_context_wait": cfg.n / max(wall - ctx_s, 1e-9),
+               "stages": [ln.strip() for ln in r.stdout.splitlines() if "[" in ln and "s]" in ln][:16],
                "unit": "seqs/s", "clusters": ncl}
         if os.path.exists(_oracle.REF_BIN):
             ns = 4000

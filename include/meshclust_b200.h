@@ -161,6 +161,24 @@ int mc_set_stream(mc_ctx *ctx, void *stream);
 int mc_mean_nearest(mc_ctx *ctx, const int64_t *rows, int64_t m, int append, int64_t *nearest_row,
                     double *nearest_dist);
 
+typedef struct mc_step_result {
+	mc_scan_result scan;  /* what mc_scan would have returned */
+	int64_t nearest_row;  /* get_mean's pick after the marked rows joined `current`; -1 when scan.n_pos == 0 */
+	int64_t n_members;    /* size of `current` after this step */
+} mc_step_result;
+
+/* One iteration of accumulate()'s inner loop (ClusterFactory.cpp:649-692) as a single submission
+ * with a single host synchronisation: Trainer::get_close over the alive rows of [lo,hi]
+ * (Trainer.cpp:34-114), bvec::remove_available (bvec.cpp:290-317) and -- when any row was marked --
+ * get_mean (ClusterFactory.cpp:382-425) over `current` extended by the marked rows in iteration
+ * order (ascending row).  restart != 0 begins a new cluster: `current` = {center_row}
+ * (ClusterFactory.cpp:641).  The member list, its running bin sums and the marks never leave HBM;
+ * marked_rows_out (optional, capacity cap >= number of marked rows, else MC_ERR_ARG) receives the
+ * marked rows in ascending order so that the caller can drop them from its own bvec.
+ * hi < lo is an empty range (no evaluation; nearest_row = -1). */
+int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart,
+                       mc_step_result *res, int64_t *marked_rows_out, int64_t cap);
+
 /* One Jacobi sweep of mean_shift_update (ClusterFactory.cpp:289-380) for ncenters centers:
  * center c sees the candidate rows cand_rows[cand_begin[c] .. cand_end[c]) (members of clusters
  * c-delta..c+delta in order), keeps those Trainer::filter (Trainer.cpp:334-349) classifies

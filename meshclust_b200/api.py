@@ -31,7 +31,7 @@ EXPORTS = [
     "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_copy_digits",
     "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
     "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
-    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_update_centers", "mc_align_pairs",
+    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_update_centers", "mc_align_pairs",
     "mc_kmer_histograms_host", "mc_scan_host",
 ]
 
@@ -41,6 +41,10 @@ class ScanResult(C.Structure):
 
     def as_tuple(self):
         return (self.n_eval, self.n_pos, self.best_row, self.best_f0)
+
+
+class StepResult(C.Structure):
+    _fields_ = [("scan", ScanResult), ("nearest_row", C.c_int64), ("n_members", C.c_int64)]
 
 
 _lib.mc_version.restype = C.c_char_p
@@ -251,6 +255,14 @@ class Context:
         row, dist = C.c_int64(-1), C.c_double(0)
         _check(_lib.mc_mean_nearest(self._h, _p(r), C.c_int64(r.size), C.c_int(1 if append else 0), C.byref(row), C.byref(dist)))
         return int(row.value), float(dist.value)
+
+    def accumulate_step(self, center_row: int, lo: int, hi: int, restart: bool):
+        """one accumulate() iteration: scan + remove + get_mean; returns (StepResult, marked rows ascending)"""
+        res = StepResult()
+        rows = np.zeros(max(self.n, 1), np.int64)
+        _check(_lib.mc_accumulate_step(self._h, C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi), C.c_int(1 if restart else 0),
+                                       C.byref(res), _p(rows), C.c_int64(rows.size)))
+        return res, rows[: res.scan.n_pos].copy()
 
     def update_centers(self, center_rows, cand_rows, cand_begin, cand_end) -> np.ndarray:
         cr = np.ascontiguousarray(center_rows, np.int64)

@@ -20,6 +20,8 @@ int64_t mc_scan_max_blocks(mc_ctx *ctx);
 int mc_launch_dist_keys(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint16_t *keys_dev);
 int mc_launch_pair_list(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, double *raw5_dev, uint64_t *dist_dev, double *sum_dev, double *f0_dev, uint8_t *flag_dev, double *feats_dev);
 int mc_launch_mean_nearest(mc_ctx *ctx, const int64_t *new_rows_dev, int64_t m_new, unsigned long long *sum_dev, const int64_t *members_dev, int64_t m_all, uint8_t *tq_dev, unsigned long long *magc_dev, void *partials_dev, long long *out_row_dev, double *out_dist_dev);
+size_t mc_acc_dev_bytes();
+int mc_launch_accumulate_tail(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart, const void *partials_dev, int nparts, void *acc_dev, void *out_host_dev, int32_t *list_host_dev);
 int mc_launch_update_centers(mc_ctx *ctx, const int64_t *center_rows_dev, int64_t ncenters, const int64_t *cand_rows_dev, const int64_t *cand_begin_dev, const int64_t *cand_end_dev, const int64_t *flag_off_dev, uint8_t *flags_dev, long long *next_rows_dev);
 int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len, int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b, int64_t scratch_stride, int64_t nwarps);
 
@@ -149,6 +151,8 @@ extern "C" void mc_ctx_destroy(mc_ctx *ctx) {
 	cudaFree(ctx->d_scan_slots);
 	cudaFree(ctx->d_scan_partials);
 	cudaFreeHost(ctx->h_pinned);
+	cudaFree(ctx->d_acc);
+	if (ctx->h_step) cudaFreeHost(ctx->h_step);
 	cudaFree(ctx->d_ticket);
 	cudaFree(ctx->d_flags);
 	cudaStreamDestroy(ctx->own_stream);
@@ -609,6 +613,18 @@ extern "C" int mc_scan_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_resul
 // ---------------------------------------------------------------------------------------------
 // stage 3
 // ---------------------------------------------------------------------------------------------
+static int ensure_members(mc_ctx *ctx, int64_t cap) {
+	if (cap <= ctx->members_cap) return MC_OK;
+	int64_t *nm = nullptr;
+	MC_CUDA(cudaMalloc(&nm, (size_t)cap * 8));
+	if (ctx->members_n) MC_CUDA(cudaMemcpyAsync(nm, ctx->d_members, (size_t)ctx->members_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	cudaFree(ctx->d_members);
+	ctx->d_members = nm;
+	ctx->members_cap = cap;
+	return MC_OK;
+}
+
 extern "C" int mc_mean_nearest(mc_ctx *ctx, const int64_t *rows, int64_t m, int append, int64_t *nearest_row, double *nearest_dist) {
 	MC_NEED_HIST(ctx);
 	MC_REQUIRE(rows && m > 0 && nearest_row, MC_ERR_ARG, "mc_mean_nearest: bad arguments");
@@ -618,14 +634,8 @@ extern "C" int mc_mean_nearest(mc_ctx *ctx, const int64_t *rows, int64_t m, int 
 	if (!append) ctx->members_n = 0;
 	const int64_t total = ctx->members_n + m;
 	if (total > ctx->members_cap) {
-		const int64_t cap = std::max<int64_t>(total * 2, 1024);
-		int64_t *nm = nullptr;
-		MC_CUDA(cudaMalloc(&nm, (size_t)cap * 8));
-		if (ctx->members_n) MC_CUDA(cudaMemcpyAsync(nm, ctx->d_members, (size_t)ctx->members_n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-		MC_CUDA(cudaStreamSynchronize(ctx->stream));
-		cudaFree(ctx->d_members);
-		ctx->d_members = nm;
-		ctx->members_cap = cap;
+		rc = ensure_members(ctx, std::max<int64_t>(total * 2, 1024));
+		if (rc) return rc;
 	}
 	unsigned long long *d_sum = reinterpret_cast<unsigned long long *>(ctx->d_sum);
 	uint8_t *d_tq = reinterpret_cast<uint8_t *>(ctx->d_sum) + (size_t)ctx->sum_bins * 8;
@@ -645,6 +655,51 @@ extern "C" int mc_mean_nearest(mc_ctx *ctx, const int64_t *rows, int64_t m, int 
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	*nearest_row = *reinterpret_cast<int64_t *>((uint8_t *)ctx->h_pinned + 8);
 	if (nearest_dist) *nearest_dist = *reinterpret_cast<double *>((uint8_t *)ctx->h_pinned + 16);
+	return MC_OK;
+}
+
+extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart,
+                                  mc_step_result *res, int64_t *marked_rows_out, int64_t cap) {
+	MC_NEED_HIST(ctx);
+	MC_NEED_MODEL(ctx);
+	MC_REQUIRE(res, MC_ERR_ARG, "mc_accumulate_step: res is NULL");
+	MC_REQUIRE(center_row >= 0 && center_row < ctx->n, MC_ERR_ARG, "center row out of range");
+	MC_REQUIRE(hi < lo || (lo >= 0 && hi < ctx->n), MC_ERR_ARG, "scan range [%lld,%lld] out of range", (long long)lo, (long long)hi);
+	MC_REQUIRE(restart || ctx->members_n > 0, MC_ERR_STATE, "mc_accumulate_step: no cluster has been started (restart = 0)");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int rc = ensure_members(ctx, ctx->n + 1);   // a cluster holds every row at most once
+	if (rc) return rc;
+	if (!ctx->d_acc) {
+		MC_CUDA(cudaMalloc(&ctx->d_acc, mc_acc_dev_bytes()));
+		MC_CUDA(cudaMemsetAsync(ctx->d_acc, 0, mc_acc_dev_bytes(), ctx->stream));
+	}
+	const size_t need = 64 + ((size_t)ctx->n + 16) * sizeof(int32_t);
+	if (need > ctx->h_step_bytes) {
+		if (ctx->h_step) { MC_CUDA(cudaStreamSynchronize(ctx->stream)); MC_CUDA(cudaFreeHost(ctx->h_step)); ctx->h_step = nullptr; ctx->h_step_bytes = 0; }
+		MC_CUDA(cudaHostAlloc(&ctx->h_step, need, cudaHostAllocMapped));
+		MC_CUDA(cudaHostGetDevicePointer(&ctx->h_step_dev, ctx->h_step, 0));
+		ctx->h_step_bytes = need;
+	}
+	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)MC_SCAN_PARTS * 32}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	void *d_part = cv.take<uint8_t>((size_t)MC_SCAN_PARTS * 32);
+	int nparts = 0;
+	if (hi >= lo) {
+		rc = mc_launch_scan(ctx, center_row, lo, hi, 1, d_part, &nparts);
+		if (rc) return rc;
+	}
+	rc = mc_launch_accumulate_tail(ctx, center_row, lo, hi, restart, d_part, nparts, ctx->d_acc, ctx->h_step_dev,
+	                               reinterpret_cast<int32_t *>((uint8_t *)ctx->h_step_dev + 64));
+	if (rc) return rc;
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	*res = *reinterpret_cast<const mc_step_result *>(ctx->h_step);
+	ctx->members_n = res->n_members;
+	if (marked_rows_out) {
+		MC_REQUIRE(cap >= res->scan.n_pos, MC_ERR_ARG, "marked_rows_out holds %lld rows, %lld were marked", (long long)cap, (long long)res->scan.n_pos);
+		const int32_t *src = reinterpret_cast<const int32_t *>((const uint8_t *)ctx->h_step + 64);
+		for (int64_t i = 0; i < res->scan.n_pos; i++) marked_rows_out[i] = src[i];
+	}
 	return MC_OK;
 }
 

@@ -6,6 +6,8 @@
 // type inside the min and accumulates its magnitude through a uint64 (DivergencePoint.cpp:53-65),
 // so only tq_i = floor(sum_i / count) (integer division; exact) and
 // magc = sum_i tq_i are needed.
+#include <cooperative_groups.h>
+
 #include "pair_core.cuh"
 
 // generic-address pair reduction of one row against a "center" row (global or shared memory)
@@ -146,6 +148,255 @@ int mc_launch_mean_nearest(mc_ctx *ctx, const int64_t *new_rows_dev, int64_t m_n
 		nearest_kernel<2><<<(int)blocks, 256, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->d_aux, nbins, members_dev, m_all, tq_dev, magc_dev, (NearPartial *)partials_dev, ctx->d_ticket + 1, out_row_dev, out_dist_dev);
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase A, fused: everything accumulate() does between two get_close calls, in ONE cooperative
+// launch behind the scan kernel (ClusterFactory.cpp:676-692):
+//   fold the scan's per-CTA partials -> ordered compaction of the marked rows (what
+//   bvec::remove_available appends to `current`, bvec.cpp:302-316) into the device-resident member
+//   list and into a host-mapped list -> running bin sums += their histograms -> truncated mean ->
+//   nearest member (get_mean's argmin, first minimum in `current` order).
+// The grid is one CTA per SM; phases are separated by grid-wide barriers.  When nothing was marked
+// (is_min: once per cluster) every CTA leaves right after the fold.
+// ---------------------------------------------------------------------------------------------
+struct AccDev {
+	long long members_n;                     // |current|
+	unsigned int counts[MC_SCAN_PARTS];      // marked rows per CTA chunk
+	NearPartial near[MC_SCAN_PARTS];
+};
+
+constexpr int ACC_THREADS = 256;
+
+__device__ __forceinline__ void step_merge(mc_scan_result &a, const mc_scan_result &b) {
+	a.n_eval += b.n_eval;
+	a.n_pos += b.n_pos;
+	if (b.best_row >= 0 && (b.best_f0 > a.best_f0 || (b.best_f0 == a.best_f0 && (a.best_row < 0 || b.best_row < a.best_row)))) {
+		a.best_f0 = b.best_f0;
+		a.best_row = b.best_row;
+	}
+}
+
+template <int TB>
+__global__ void __launch_bounds__(ACC_THREADS)
+accumulate_tail_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ aux,
+                       const uint8_t *__restrict__ marks, int nbins, long long lo, long long hi,
+                       long long center_row, int restart, const mc_scan_result *__restrict__ partials,
+                       int nparts, long long *__restrict__ members, unsigned long long *__restrict__ sum,
+                       AccDev *__restrict__ acc, mc_step_result *__restrict__ out_host,
+                       int32_t *__restrict__ list_host) {
+	namespace cg = cooperative_groups;
+	cg::grid_group grid = cg::this_grid();
+	extern __shared__ __align__(16) uint8_t tq[];   // truncated mean, nbins * TB bytes
+	__shared__ mc_scan_result s_scan;
+	__shared__ unsigned int s_warp[ACC_THREADS / 32];
+	__shared__ unsigned long long s_red[ACC_THREADS / 32];
+	__shared__ unsigned int s_base;
+	__shared__ unsigned long long s_magc;
+	__shared__ NearPartial s_near[ACC_THREADS / 32];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int rb = nbins * TB;
+	const int G = gridDim.x, b = blockIdx.x;
+
+	// ---- fold (every CTA, redundantly: <= 160 records out of L2)
+	if (wib == 0) {
+		mc_scan_result r;
+		r.n_eval = 0; r.n_pos = 0; r.best_row = -1; r.best_f0 = -1.0;
+		for (int i = lane; i < nparts; i += 32) {
+			mc_scan_result p;
+			p.n_eval = __ldcg(&partials[i].n_eval); p.n_pos = __ldcg(&partials[i].n_pos);
+			p.best_row = __ldcg(&partials[i].best_row); p.best_f0 = __ldcg(&partials[i].best_f0);
+			step_merge(r, p);
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) {
+			mc_scan_result other;
+			other.n_eval = __shfl_xor_sync(MC_FULL_MASK, r.n_eval, o);
+			other.n_pos = __shfl_xor_sync(MC_FULL_MASK, r.n_pos, o);
+			other.best_row = __shfl_xor_sync(MC_FULL_MASK, r.best_row, o);
+			other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, r.best_f0, o);
+			step_merge(r, other);
+		}
+		if (lane == 0) s_scan = r;
+	}
+	const long long m0 = restart ? 1 : acc->members_n;   // read before anyone may rewrite it (end of the kernel)
+	__syncthreads();
+	const mc_scan_result scan = s_scan;
+	const long long n_new = scan.n_pos;
+	if (b == 0 && restart) {
+		// `current` = {center}: member 0 and the running sums start from its histogram
+		if (threadIdx.x == 0) members[0] = center_row;
+		for (int i = threadIdx.x; i < nbins; i += ACC_THREADS)
+			sum[i] = TB == 1 ? (unsigned long long)hist[(size_t)center_row * rb + i]
+			                 : (unsigned long long)reinterpret_cast<const uint16_t *>(hist + (size_t)center_row * rb)[i];
+	}
+	if (n_new == 0) {
+		if (b == 0 && threadIdx.x == 0) {
+			out_host->scan = scan;
+			out_host->nearest_row = -1;
+			out_host->n_members = m0;
+			acc->members_n = m0;
+		}
+		return;   // uniform across the grid: nobody reaches a barrier
+	}
+
+	// ---- ordered compaction of the marks of [lo, hi]: count, barrier, scatter
+	const long long nrows = hi - lo + 1;
+	long long chunk = (nrows + G - 1) / G;
+	const long long per = (chunk + ACC_THREADS - 1) / ACC_THREADS;
+	chunk = per * ACC_THREADS;
+	const long long t0 = lo + (long long)b * chunk + (long long)threadIdx.x * per;
+	long long t1 = t0 + per;
+	if (t1 > hi + 1) t1 = hi + 1;
+	unsigned int mine = 0;
+	for (long long r = t0; r < t1; r++) mine += marks[r];
+	unsigned int incl = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const unsigned int v = __shfl_up_sync(MC_FULL_MASK, incl, o);
+		if (lane >= o) incl += v;
+	}
+	if (lane == 31) s_warp[wib] = incl;
+	__syncthreads();
+	unsigned int warp_base = 0, block_total = 0;
+	for (int w = 0; w < ACC_THREADS / 32; w++) {
+		if (w < wib) warp_base += s_warp[w];
+		block_total += s_warp[w];
+	}
+	const unsigned int excl = warp_base + incl - mine;
+	if (threadIdx.x == 0) acc->counts[b] = block_total;
+	grid.sync();
+	if (wib == 0) {
+		unsigned int v = 0;
+		for (int i = lane; i < b; i += 32) v += __ldcg(&acc->counts[i]);
+#pragma unroll
+		for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(MC_FULL_MASK, v, o);
+		if (lane == 0) s_base = v;
+	}
+	__syncthreads();
+	if (mine) {
+		long long at = (long long)s_base + excl;
+		for (long long r = t0; r < t1; r++)
+			if (marks[r]) {
+				members[m0 + at] = r;
+				list_host[at] = (int32_t)r;
+				at++;
+			}
+	}
+	grid.sync();
+
+	// ---- running sums += the new members' histograms (exact integers)
+	{
+		const int words = rb / 4;
+		for (int w0 = 0; w0 < words; w0 += ACC_THREADS) {
+			const int w = w0 + threadIdx.x;
+			uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+			if (w < words) {
+				for (long long i = b; i < n_new; i += G) {
+					const long long row = __ldcg(&members[m0 + i]);
+					const uint32_t v = *(reinterpret_cast<const uint32_t *>(hist + (size_t)row * rb) + w);
+					if (TB == 1) { a0 += v & 0xff; a1 += (v >> 8) & 0xff; a2 += (v >> 16) & 0xff; a3 += v >> 24; }
+					else { a0 += v & 0xffff; a1 += v >> 16; }
+				}
+				if (TB == 1) {
+					if (a0) atomicAdd(&sum[w * 4 + 0], (unsigned long long)a0);
+					if (a1) atomicAdd(&sum[w * 4 + 1], (unsigned long long)a1);
+					if (a2) atomicAdd(&sum[w * 4 + 2], (unsigned long long)a2);
+					if (a3) atomicAdd(&sum[w * 4 + 3], (unsigned long long)a3);
+				} else {
+					if (a0) atomicAdd(&sum[w * 2 + 0], (unsigned long long)a0);
+					if (a1) atomicAdd(&sum[w * 2 + 1], (unsigned long long)a1);
+				}
+			}
+		}
+	}
+	grid.sync();
+
+	// ---- truncated mean (per CTA, in shared memory) and its magnitude
+	const long long m_all = m0 + n_new;
+	{
+		unsigned long long local = 0;
+		for (int i = threadIdx.x; i < nbins; i += ACC_THREADS) {
+			const unsigned long long v = __ldcg(&sum[i]) / (unsigned long long)m_all;
+			if (TB == 1) tq[i] = (uint8_t)v; else reinterpret_cast<uint16_t *>(tq)[i] = (uint16_t)v;
+			local += v;
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(MC_FULL_MASK, local, o);
+		if (lane == 0) s_red[wib] = local;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			unsigned long long t = 0;
+			for (int w = 0; w < ACC_THREADS / 32; w++) t += s_red[w];
+			s_magc = t;
+		}
+		__syncthreads();
+	}
+	const unsigned long long magc = s_magc;
+
+	// ---- nearest member: first minimum of distance_d in `current` order
+	NearPartial best; best.pos = -1; best.dist = 0;
+	for (long long i = (long long)b * (ACC_THREADS / 32) + wib; i < m_all; i += (long long)G * (ACC_THREADS / 32)) {
+		const long long row = __ldcg(&members[i]);
+		const PairAcc<TB> pa = warp_pair_reduce<TB>(hist + (size_t)row * rb, tq, rb, lane);
+		const uint64_t mp = aux[row].mag;
+		NearPartial cnd; cnd.pos = i; cnd.dist = mc_distance_d(pa.summin(mp, magc), mp, magc);
+		near_merge(best, cnd);
+	}
+	if (lane == 0) s_near[wib] = best;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		NearPartial r = s_near[0];
+		for (int w = 1; w < ACC_THREADS / 32; w++) near_merge(r, s_near[w]);
+		acc->near[b] = r;
+	}
+	grid.sync();
+	if (b == 0 && wib == 0) {
+		NearPartial r; r.pos = -1; r.dist = 0;
+		for (int i = lane; i < G; i += 32) {
+			NearPartial p;
+			p.pos = __ldcg(&acc->near[i].pos);
+			p.dist = __ldcg(&acc->near[i].dist);
+			near_merge(r, p);
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) {
+			NearPartial other;
+			other.pos = __shfl_xor_sync(MC_FULL_MASK, r.pos, o);
+			other.dist = __shfl_xor_sync(MC_FULL_MASK, r.dist, o);
+			near_merge(r, other);
+		}
+		if (lane == 0) {
+			out_host->scan = scan;
+			out_host->nearest_row = r.pos >= 0 ? __ldcg(&members[r.pos]) : -1;
+			out_host->n_members = m_all;
+			acc->members_n = m_all;
+		}
+	}
+}
+
+size_t mc_acc_dev_bytes() { return sizeof(AccDev); }
+
+int mc_launch_accumulate_tail(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart,
+                              const void *partials_dev, int nparts, void *acc_dev, void *out_host_dev,
+                              int32_t *list_host_dev) {
+	const int nbins = ctx->nbins;
+	const size_t smem = (size_t)nbins * ctx->tbytes;
+	MC_REQUIRE(smem <= 96 * 1024, MC_ERR_UNSUPPORTED, "k too large for the accumulate kernel");
+	const uint8_t *hist = (const uint8_t *)ctx->d_hist;
+	const McRowAux *aux = ctx->d_aux;
+	const uint8_t *marks = ctx->d_marks;
+	long long lo_ = lo, hi_ = hi, cr = center_row;
+	long long *members = (long long *)ctx->d_members;
+	unsigned long long *sum = (unsigned long long *)ctx->d_sum;
+	int nb = nbins, rs = restart, np = nparts;
+	void *args[] = {&hist, &aux, &marks, &nb, &lo_, &hi_, &cr, &rs, &partials_dev, &np, &members, &sum, &acc_dev, &out_host_dev, &list_host_dev};
+	int grid = ctx->num_sms < MC_SCAN_PARTS ? ctx->num_sms : MC_SCAN_PARTS;
+	const void *fn = ctx->tbytes == 1 ? (const void *)accumulate_tail_kernel<1> : (const void *)accumulate_tail_kernel<2>;
+	if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	MC_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(ACC_THREADS), args, smem, ctx->stream));
+	ctx->launches++;
 	return MC_OK;
 }
 

@@ -63,6 +63,41 @@ struct __align__(32) McRowAux {
 };
 
 // ---------------------------------------------------------------------------------------------
+// multi-GPU exchange of scan summaries over NVLink peer memory.
+// Every rank owns an "inbox" in its HBM; the scan kernel of rank r stores each CTA's 32-byte partial
+// straight into the inbox of every rank as 8 low-latency words {u32 data, u32 epoch}: an 8-byte
+// store is atomic, so a reader that sees the epoch in a word also sees its data and no fence or
+// remote atomic is needed (the scheme NCCL calls LL).  Inbox address of a record:
+//   ((parity * MC_XSLOTS + slot) * MC_MAX_PEERS + source rank) * MC_SCAN_PARTS + CTA) * 64
+// parity = epoch & 1 double-buffers a slot: a rank can be at most one exchange ahead of a peer.
+// ---------------------------------------------------------------------------------------------
+#define MC_MAX_PEERS 8
+#define MC_XSLOTS 64
+#define MC_LL_RECORD_BYTES 64
+#define MC_INBOX_BYTES ((size_t)2 * MC_XSLOTS * MC_MAX_PEERS * MC_SCAN_PARTS * MC_LL_RECORD_BYTES)
+
+struct McPeerPush {                            // by-value argument of the scan kernel
+	unsigned long long inbox[MC_MAX_PEERS];    // every rank's inbox as this GPU addresses it
+	int world;                                 // 0: single GPU, nothing is sent
+	int rank;
+	unsigned int epoch;                        // flag value of this exchange, never 0
+	unsigned int fence;                        // 1: make earlier peer stores (marks) visible before the record
+	unsigned long long slot_off;               // byte offset of (parity, slot) inside an inbox
+};
+
+struct McComm {
+	int world = 0, rank = 0;
+	int64_t shard_lo = 0, shard_hi = -1;       // rows this rank evaluates (inclusive)
+	uint8_t *inbox = nullptr;                  // this rank's inbox (cudaMalloc, IPC-exportable)
+	uint8_t *peer_inbox[MC_MAX_PEERS] = {};
+	bool ipc_opened[MC_MAX_PEERS] = {};
+	bool connected = false;
+	unsigned int slot_epoch[MC_XSLOTS] = {};
+	unsigned char slot_pending[MC_XSLOTS] = {};
+	void *d_out = nullptr;                     // MC_XSLOTS combined records + error word
+};
+
+// ---------------------------------------------------------------------------------------------
 // the context
 // ---------------------------------------------------------------------------------------------
 struct mc_ctx {
@@ -116,6 +151,14 @@ struct mc_ctx {
 	int64_t members_cap = 0, members_n = 0;
 	uint32_t *d_sum = nullptr;   // running per-bin sum of member histograms
 	int64_t sum_bins = 0;
+
+	McComm comm;
+
+	// fused Phase-A step (mc_accumulate_step): device state + host-mapped result / marked-row list
+	void *d_acc = nullptr;
+	void *h_step = nullptr;      // cudaHostAlloc(Mapped): mc_step_result, then int32 rows
+	void *h_step_dev = nullptr;  // device alias of h_step
+	size_t h_step_bytes = 0;
 };
 
 int mc_ensure_scratch(mc_ctx *ctx, size_t bytes);

@@ -97,7 +97,7 @@ template <int TB, int RB>
 __global__ void __launch_bounds__(32 * (1 + TileCfg<RB>::NCW), 1)
 scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, uint8_t *__restrict__ marks,
                 long long lo, long long hi, long long center_row, McModel model, int remove_marked,
-                ScanPartial *__restrict__ partials) {
+                ScanPartial *__restrict__ partials, McPeerPush push) {
 	using C = RowCfg<RB>;
 	using T = TileCfg<RB>;
 	constexpr int NB = RB / TB;
@@ -252,6 +252,24 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			tscan_merge(b, other);
 		}
 		if (lane == 0) partials[blockIdx.x] = b;
+		if (push.world > 0) {
+			// sharded scan: this CTA's partial goes straight into every rank's inbox over NVLink, one
+			// 8-byte {data, epoch} store per word; lane = 8 * (peer mod 4) + word
+			if (push.fence) __threadfence_system();
+			unsigned long long f[4];
+			f[0] = (unsigned long long)__shfl_sync(MC_FULL_MASK, b.n_eval, 0);
+			f[1] = (unsigned long long)__shfl_sync(MC_FULL_MASK, b.n_pos, 0);
+			f[2] = (unsigned long long)__shfl_sync(MC_FULL_MASK, b.best_row, 0);
+			f[3] = (unsigned long long)__double_as_longlong(__shfl_sync(MC_FULL_MASK, b.best_f0, 0));
+			const int w = lane & 7;
+			const unsigned long long fld = (w >> 1) == 0 ? f[0] : ((w >> 1) == 1 ? f[1] : ((w >> 1) == 2 ? f[2] : f[3]));
+			const unsigned int data = (w & 1) ? (unsigned int)(fld >> 32) : (unsigned int)fld;
+			for (int p = lane >> 3; p < push.world; p += 4) {
+				const unsigned long long dst = push.inbox[p] + push.slot_off +
+					((unsigned long long)push.rank * MC_SCAN_PARTS + blockIdx.x) * MC_LL_RECORD_BYTES + (unsigned long long)w * 8;
+				asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(data), "r"(push.epoch) : "memory");
+			}
+		}
 		TRACE(7);
 	}
 }
@@ -298,7 +316,7 @@ int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t h
 
 template <int TB, int RB>
 static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                      void *partials_dev, int *nparts_out) {
+                      void *partials_dev, int *nparts_out, const McPeerPush *push) {
 	using T = TileCfg<RB>;
 	const size_t smem = (size_t)T::NS * T::STAGE_BYTES;
 	static bool attr_set = false;
@@ -310,6 +328,11 @@ static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, i
 	int64_t blocks = ctx->num_sms;
 	if (blocks > ntiles) blocks = ntiles;
 	if (blocks < 1) blocks = 1;
+	McPeerPush pp{};
+	if (push) {   // sharded: every rank always sends num_sms records, so a reader knows how many to expect
+		pp = *push;
+		blocks = ctx->num_sms;
+	}
 	static const bool no_pdl = getenv("MC_NO_PDL") != nullptr;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3((unsigned)blocks);
@@ -323,7 +346,7 @@ static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, i
 	cfg.numAttrs = no_pdl ? 0 : 1;
 	MC_CUDA(cudaLaunchKernelEx(&cfg, scan_tma_kernel<TB, RB>, (const uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_marks,
 	                           (long long)lo, (long long)hi, (long long)center_row, ctx->model, remove_marked,
-	                           (ScanPartial *)partials_dev));
+	                           (ScanPartial *)partials_dev, pp));
 	*nparts_out = (int)blocks;
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
@@ -331,29 +354,39 @@ static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, i
 }
 
 // partials_dev must hold MC_SCAN_PARTS entries of 32 bytes; *nparts_out says how many were written
+int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                        void *partials_dev, int *nparts_out, const McPeerPush *push);
+
 int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                    void *partials_dev, int *nparts_out) {
+	return mc_launch_scan_push(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, nullptr);
+}
+
+// push != NULL: sharded scan, every CTA also stores its partial into the peers' inboxes
+int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                        void *partials_dev, int *nparts_out, const McPeerPush *push) {
 	static const bool legacy = getenv("MC_SCAN_DIRECT") != nullptr;
 	const int rb = ctx->tbytes * ctx->nbins;
 	if (!legacy) {
 		if (ctx->tbytes == 1) {
 			switch (rb) {
-			case 16: return launch_tma<1, 16>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
-			case 64: return launch_tma<1, 64>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
-			case 256: return launch_tma<1, 256>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
-			case 1024: return launch_tma<1, 1024>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
-			case 4096: return launch_tma<1, 4096>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+			case 16: return launch_tma<1, 16>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+			case 64: return launch_tma<1, 64>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+			case 256: return launch_tma<1, 256>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+			case 1024: return launch_tma<1, 1024>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+			case 4096: return launch_tma<1, 4096>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
 			default: break;
 			}
 		} else {
 			switch (rb) {
-			case 32: return launch_tma<2, 32>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
-			case 128: return launch_tma<2, 128>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
-			case 512: return launch_tma<2, 512>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
-			case 2048: return launch_tma<2, 2048>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+			case 32: return launch_tma<2, 32>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+			case 128: return launch_tma<2, 128>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+			case 512: return launch_tma<2, 512>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+			case 2048: return launch_tma<2, 2048>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
 			default: break;
 			}
 		}
 	}
+	MC_REQUIRE(!push, MC_ERR_UNSUPPORTED, "sharded scans need the staged scan kernel (16-byte rows and wider, no MC_SCAN_DIRECT)");
 	return mc_launch_scan_direct(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
 }

@@ -17,6 +17,10 @@ struct BvIdx {
 	size_t bin = 0, pos = 0;
 };
 
+// Layout: a bin keeps its entries where finalize() put them for good; removal clears a bit in the
+// bin's alive bitmap, and "element i of the bin" (what the reference indexes after its erases) is
+// the i-th set bit.  Removing the rows a scan marked therefore costs O(marked), not O(range), and
+// the GPU row of an entry (= its rank in the initial iteration order) never changes.
 class BVec {
 public:
 	// entries are point ids while the container is being filled, rows afterwards
@@ -32,8 +36,26 @@ public:
 		data_.resize(bounds_.size());
 	}
 
-	// bvec::index_of (bvec.cpp:123-149)
+	// bvec::index_of (bvec.cpp:123-149).  The reference walks every bound and keeps the smallest and
+	// largest i-1 (0 for i = 0) over all i with bounds[i-1] <= point <= bounds[i] (bounds[-1] = 0);
+	// the bounds are sorted, so those i form the interval [first bound >= point, #bounds <= point]
+	// and two binary searches give the same answer (index_of_linear is the literal loop, kept for
+	// the self-check in tests/test_host_units.py).
 	void index_of(uint64_t point, size_t *pfront, size_t *pback) const {
+		const size_t nb = bounds_.size();
+		size_t low = nb - 1, high = 0;
+		const size_t i1 = (size_t)(std::lower_bound(bounds_.begin(), bounds_.end(), point) - bounds_.begin());
+		if (i1 < nb) {
+			const size_t ub = (size_t)(std::upper_bound(bounds_.begin(), bounds_.end(), point) - bounds_.begin());
+			const size_t imax = std::min(ub, nb - 1);
+			low = std::min(low, i1 > 0 ? i1 - 1 : 0);
+			high = std::max(high, imax > 0 ? imax - 1 : 0);
+		}
+		if (point >= bounds_.back()) high = std::max(high, nb - 1);
+		if (pfront) *pfront = low;
+		if (pback) *pback = high;
+	}
+	void index_of_linear(uint64_t point, size_t *pfront, size_t *pback) const {
 		size_t low = bounds_.size() - 1, high = 0;
 		for (size_t i = 0; i < bounds_.size(); i++) {
 			const size_t prev = i > 0 ? bounds_[i - 1] : 0;
@@ -55,77 +77,85 @@ public:
 		std::vector<size_t> mins;
 		size_t minimum = std::numeric_limits<size_t>::max();
 		for (size_t i = front; i <= back; i++) {
-			const size_t sz = data_[i].size();
+			const size_t sz = data_[i].items.size();
 			if (sz < minimum) { minimum = sz; mins.clear(); mins.push_back(i); }
 			else if (sz == minimum) mins.push_back(i);
 		}
 		// front > back leaves no candidate: the reference prints an error and then indexes an empty
 		// vector (undefined); it cannot happen for bounds taken from the same lengths
-		data_.at(mins.at(mins.size() / 2)).push_back({id, len});
+		data_.at(mins.at(mins.size() / 2)).items.push_back({id, len});
 	}
 
 	// bvec::insert_finalize (bvec.cpp:209-218): per-bin std::sort by length (unstable: the same
 	// libstdc++ introsort on the same sequence and comparator gives the same permutation)
 	void finalize() {
 		for (auto &bin : data_)
-			std::sort(bin.begin(), bin.end(), [](const Entry &a, const Entry &b) { return a.len < b.len; });
+			std::sort(bin.items.begin(), bin.items.end(), [](const Entry &a, const Entry &b) { return a.len < b.len; });
 	}
 
 	// after finalize(): rename the entries to their position in iteration order; returns id per row
 	std::vector<int64_t> assign_rows() {
 		std::vector<int64_t> id_of_row;
-		for (auto &bin : data_)
-			for (auto &e : bin) {
+		row0_.clear();
+		for (auto &bin : data_) {
+			row0_.push_back((int64_t)id_of_row.size());
+			for (auto &e : bin.items) {
 				id_of_row.push_back(e.v);
 				e.v = (int64_t)id_of_row.size() - 1;
 			}
+			bin.alive = bin.items.size();
+			bin.bits.assign((bin.items.size() + 63) / 64, ~0ull);
+			if (bin.items.size() % 64) bin.bits.back() = (1ull << (bin.items.size() % 64)) - 1;
+		}
 		return id_of_row;
 	}
 
 	size_t size() const {
 		size_t t = 0;
-		for (auto &b : data_) t += b.size();
+		for (auto &b : data_) t += b.alive;
 		return t;
 	}
 
 	// bvec::pop (bvec.cpp:27-38): first element of the first non-empty bin, or -1
 	int64_t pop() {
-		for (auto &bin : data_)
-			if (!bin.empty()) {
-				const int64_t r = bin.front().v;
-				bin.erase(bin.begin());
-				return r;
+		for (; first_live_ < data_.size(); first_live_++) {
+			Bin &bin = data_[first_live_];
+			if (bin.alive) {
+				const size_t at = bin.select(0);
+				bin.clear(at);
+				return bin.items[at].v;
 			}
+		}
 		return -1;
 	}
 
 	// bvec::inner_index_of (bvec.cpp:52-120)
 	void inner_index_of(uint64_t length, size_t &idx, size_t *pfront, size_t *pback) const {
-		if (data_.at(idx).empty()) {
+		if (data_.at(idx).alive == 0) {
 			if (pfront)
 				for (size_t i = 0; i < data_.size(); i++)
-					if (!data_[i].empty()) { idx = i; *pfront = 0; break; }
+					if (data_[i].alive) { idx = i; *pfront = 0; break; }
 			if (pback)
 				for (long i = (long)data_.size() - 1; i >= 0; i--)
-					if (!data_[i].empty()) { idx = (size_t)i; *pback = 0; break; }
+					if (data_[i].alive) { idx = (size_t)i; *pback = 0; break; }
 			return;
 		}
-		const auto &bin = data_[idx];
-		size_t front = 0, back = 0, low = 0, high = bin.size() - 1;
+		const Bin &bin = data_[idx];
+		size_t front = 0, back = 0, low = 0, high = bin.alive - 1;
 		while (low <= high) {
 			const size_t mid = (low + high) / 2;
-			const uint64_t d = bin[mid].len;
+			const uint64_t d = bin.at(mid).len;
 			if (d == length) { front = back = mid; break; }
 			else if (length < d) high = mid;
 			else low = mid + 1;
 			if (low == high) { front = low; back = high; break; }
 		}
 		if (pfront) {
-			for (long i = (long)front; i >= 0 && bin[i].len == length; i--) front = (size_t)i;
+			for (long i = (long)front; i >= 0 && bin.at((size_t)i).len == length; i--) front = (size_t)i;
 			*pfront = front;
 		}
 		if (pback) {
-			for (size_t i = back; i < bin.size() && bin[i].len == length; i++) back = i;
+			for (size_t i = back; i < bin.alive && bin.at(i).len == length; i++) back = i;
 			*pback = back;
 		}
 	}
@@ -134,7 +164,7 @@ public:
 	std::pair<BvIdx, BvIdx> get_range(uint64_t begin_len, uint64_t end_len) const {
 		BvIdx front, back;
 		back.bin = data_.size() - 1;
-		back.pos = data_[back.bin].size() - 1;   // wraps to SIZE_MAX on an empty last bin, as in the reference
+		back.pos = data_[back.bin].alive - 1;   // wraps to SIZE_MAX on an empty last bin, as in the reference
 		index_of(begin_len, &front.bin, nullptr);
 		index_of(end_len, nullptr, &back.bin);
 		inner_index_of(begin_len, front.bin, &front.pos, nullptr);
@@ -149,28 +179,21 @@ public:
 	}
 
 	// row of an element; the caller guarantees it exists
-	int64_t row_at(const BvIdx &i) const { return data_[i.bin][i.pos].v; }
-
-	// the reference iterates `trip_count` steps from `front` with operator++ (which skips empty
-	// bins); this returns the row reached by the last step, i.e. the inclusive upper row bound
-	int64_t last_row_of_walk(BvIdx f, int64_t steps) const {
-		size_t r = f.bin, c = f.pos;
-		for (int64_t i = 1; i < steps; i++) {
-			if (c + 1 < data_[r].size()) c++;
-			else {
-				r++; c = 0;
-				while (r < data_.size() && data_[r].empty()) r++;
-			}
-		}
-		return data_[r][c].v;
-	}
+	int64_t row_at(const BvIdx &i) const { return data_[i.bin].at(i.pos).v; }
 
 	// bvec::erase (bvec.cpp:281-285) by row: the argmax element of the last scan
 	void erase_row(int64_t row) {
-		for (auto &bin : data_) {
-			if (bin.empty() || bin.front().v > row || bin.back().v < row) continue;
-			auto it = std::lower_bound(bin.begin(), bin.end(), row, [](const Entry &e, int64_t r) { return e.v < r; });
-			if (it != bin.end() && it->v == row) { bin.erase(it); return; }
+		const size_t b = bin_of_row(row);
+		data_[b].clear((size_t)(row - row0_[b]));
+	}
+
+	// bvec::remove_available (bvec.cpp:290-317) when the marked rows are already known as a list
+	// (ascending rows = bin order, position order: the serial order of the reference)
+	void remove_rows(const int64_t *rows, size_t m) {
+		size_t b = 0;
+		for (size_t i = 0; i < m; i++) {
+			if (!(b < data_.size() && rows[i] >= row0_[b] && rows[i] < row0_[b] + (int64_t)data_[b].items.size())) b = bin_of_row(rows[i]);
+			data_[b].clear((size_t)(rows[i] - row0_[b]));
 		}
 	}
 
@@ -179,30 +202,63 @@ public:
 	template <class IsMarked>
 	void remove_marked(size_t a, size_t b, IsMarked marked, std::vector<int64_t> &out) {
 		for (size_t i = a; i <= b && i < data_.size(); i++) {
-			auto &bin = data_[i];
-			size_t w = 0;
-			for (size_t j = 0; j < bin.size(); j++) {
-				if (marked(bin[j].v)) out.push_back(bin[j].v);
-				else bin[w++] = bin[j];
+			Bin &bin = data_[i];
+			for (size_t w = 0; w < bin.bits.size(); w++) {
+				uint64_t word = bin.bits[w];
+				while (word) {
+					const size_t at = w * 64 + (size_t)__builtin_ctzll(word);
+					word &= word - 1;
+					if (marked(bin.items[at].v)) { out.push_back(bin.items[at].v); bin.clear(at); }
+				}
 			}
-			bin.resize(w);
 		}
 	}
 
 	size_t nbins() const { return data_.size(); }
 
 private:
+	struct Bin {
+		std::vector<Entry> items;     // fixed after finalize(); items[j].v = row0 + j
+		std::vector<uint64_t> bits;   // alive bitmap over items
+		size_t alive = 0;
+		// index in items of the i-th alive entry
+		size_t select(size_t i) const {
+			for (size_t w = 0; w < bits.size(); w++) {
+				const size_t c = (size_t)__builtin_popcountll(bits[w]);
+				if (i < c) {
+					uint64_t word = bits[w];
+					for (; i; i--) word &= word - 1;
+					return w * 64 + (size_t)__builtin_ctzll(word);
+				}
+				i -= c;
+			}
+			return items.size();   // out of range: the caller asked for an element that is not there
+		}
+		const Entry &at(size_t i) const { return items.at(select(i)); }
+		void clear(size_t at) {
+			uint64_t &w = bits[at / 64];
+			const uint64_t m = 1ull << (at % 64);
+			if (w & m) { w &= ~m; alive--; }
+		}
+	};
+
+	size_t bin_of_row(int64_t row) const {
+		return (size_t)(std::upper_bound(row0_.begin(), row0_.end(), row) - row0_.begin()) - 1;
+	}
+
 	int64_t diff(const BvIdx &a, const BvIdx &rhs) const {   // a - rhs
 		if (a.bin < rhs.bin || (a.bin == rhs.bin && a.pos < rhs.pos)) return -diff(rhs, a);
 		if (a.bin == rhs.bin) return (int64_t)(a.pos - rhs.pos);
 		int64_t sum = (int64_t)a.pos;
-		sum += (int64_t)(data_.at(rhs.bin).size() - rhs.pos);
-		for (size_t i = rhs.bin + 1; i < a.bin; i++) sum += (int64_t)data_[i].size();
+		sum += (int64_t)(data_.at(rhs.bin).alive - rhs.pos);
+		for (size_t i = rhs.bin + 1; i < a.bin; i++) sum += (int64_t)data_[i].alive;
 		return sum;
 	}
 
-	std::vector<std::vector<Entry>> data_;
+	std::vector<Bin> data_;
 	std::vector<uint64_t> bounds_;
+	std::vector<int64_t> row0_;   // first row of each bin
+	size_t first_live_ = 0;       // bins before this one are empty (pop() only ever moves forward)
 };
 
 }  // namespace mch

@@ -5,14 +5,41 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
 namespace mch {
 
+// byte buffer that grows without value-initialising (a 1 GB std::vector::resize is a 1 GB memset)
+class RawBytes {
+public:
+	RawBytes() = default;
+	RawBytes(const RawBytes &) = delete;
+	RawBytes &operator=(const RawBytes &) = delete;
+	~RawBytes() { free(p_); }
+	uint8_t *data() { return p_; }
+	const uint8_t *data() const { return p_; }
+	size_t size() const { return n_; }
+	void resize(size_t n) {
+		if (n > cap_) {
+			void *q = realloc(p_, n);
+			if (!q) throw std::bad_alloc();
+			p_ = (uint8_t *)q;
+			cap_ = n;
+		}
+		n_ = n;
+	}
+private:
+	uint8_t *p_ = nullptr;
+	size_t n_ = 0, cap_ = 0;
+};
+
 struct FastaBatch {
 	std::vector<std::string> headers;
-	std::vector<uint8_t> letters;     // concatenated raw sequence bytes (no newlines)
+	RawBytes letters;                 // concatenated raw sequence bytes (no newlines)
 	std::vector<int64_t> offsets{0};  // n+1
 	size_t size() const { return headers.size(); }
 };
@@ -21,7 +48,7 @@ struct FastaBatch {
 inline bool read_fasta(const std::string &path, FastaBatch &out, std::string &msg) {
 	FILE *f = fopen(path.c_str(), "rb");
 	if (!f) { msg = "File \"" + path + "\" does not exist"; return false; }
-	std::vector<char> buf;
+	RawBytes buf;
 	{
 		fseek(f, 0, SEEK_END);
 		const long sz = ftell(f);
@@ -31,26 +58,41 @@ inline bool read_fasta(const std::string &path, FastaBatch &out, std::string &ms
 		fclose(f);
 	}
 	const size_t n = buf.size();
+	const char *bd = (const char *)buf.data();
 	size_t i = 0;
 	bool open = false, has_line = false;
+	const size_t base = out.letters.size();
+	size_t w = base;
 	auto close_record = [&]() -> bool {
 		if (!open) return true;
 		if (!has_line) {   // Chromosome::finalize: header and sequence must both have been set
 			msg = "record \"" + out.headers.back() + "\" has no sequence line";
 			return false;
 		}
-		out.offsets.push_back((int64_t)out.letters.size());
+		out.offsets.push_back((int64_t)w);
 		return true;
 	};
+	// sequence bytes are compacted into one buffer sized for the whole file up front (the letters
+	// of a file never outnumber its bytes); line ends are found with memchr
+	out.letters.resize(base + n);
+	uint8_t *dst = out.letters.data();
+	const bool any_cr = n > 0 && memchr(bd, '\r', n) != nullptr;
 	// the reference loops `while (in.good())`: after the last newline it reads one more, empty, line
 	bool more = true;
 	while (more) {
-		size_t j = i;
-		while (j < n && buf[j] != '\n' && buf[j] != '\r') j++;
-		const char *line = buf.data() + i;
+		size_t j;
+		{
+			const char *nl = i < n ? (const char *)memchr(bd + i, '\n', n - i) : nullptr;
+			j = nl ? (size_t)(nl - bd) : n;
+			if (any_cr && j > i) {
+				const char *cr = (const char *)memchr(bd + i, '\r', j - i);
+				if (cr) j = (size_t)(cr - bd);
+			}
+		}
+		const char *line = bd + i;
 		const size_t len = j - i;
 		if (j >= n) more = false;                       // EOF reached while reading this line
-		else if (buf[j] == '\r' && j + 1 < n && buf[j + 1] == '\n') i = j + 2;
+		else if (bd[j] == '\r' && j + 1 < n && bd[j + 1] == '\n') i = j + 2;
 		else i = j + 1;
 		if (len > 0 && line[0] == '>') {
 			if (!close_record()) return false;
@@ -60,13 +102,16 @@ inline bool read_fasta(const std::string &path, FastaBatch &out, std::string &ms
 		} else {
 			if (!open) {
 				if (len == 0 && !more) break;            // empty file
+				out.letters.resize(base);
 				msg = "sequence data before the first header in " + path;
 				return false;
 			}
-			out.letters.insert(out.letters.end(), line, line + len);
+			memcpy(dst + w, line, len);
+			w += len;
 			has_line = true;
 		}
 	}
+	out.letters.resize(w);
 	if (!open) { msg = "no FASTA record in " + path; return false; }
 	return close_record();
 }

@@ -18,6 +18,7 @@
 #include <map>
 #include <set>
 #include <stdexcept>
+#include <thread>
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -118,16 +119,29 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	std::vector<int> points((size_t)n);
 	for (int64_t i = 0; i < n; i++) points[i] = (int)i;
 	Timer st;
+	// The reference sorts Point* arrays with comparators that look the key up through the pointer.
+	// std::sort's permutation depends only on the comparison outcomes, so sorting (key, id) records
+	// with the same comparator on the key yields the identical order without the random accesses.
+	struct LenId { uint64_t key; int id; };
+	struct KeyId { uint16_t key; int id; };
 	// :672-675 unstable sort by length, then the median-length point
-	std::sort(points.begin(), points.end(), [&](int a, int b) { return ds.len[a] < ds.len[b]; });
+	{
+		std::vector<LenId> rec((size_t)n);
+		for (int64_t i = 0; i < n; i++) rec[i] = {ds.len[i], (int)i};
+		std::sort(rec.begin(), rec.end(), [](const LenId &a, const LenId &b) { return a.key < b.key; });
+		for (int64_t i = 0; i < n; i++) points[i] = rec[i].id;
+	}
 	const int begin_pt = points[points.size() / 2];
 	// :681-684 sort by distance to it
-	std::vector<uint16_t> key1((size_t)n);
 	{
+		std::vector<uint16_t> key1((size_t)n);
 		int32_t r = (int32_t)ds.row_of_id[begin_pt];
 		GPU(mc_distance_keys(c.gpu, &r, 1, key1.data()));
+		std::vector<KeyId> rec((size_t)n);
+		for (int64_t i = 0; i < n; i++) rec[i] = {key1[ds.row_of_id[points[i]]], points[i]};
+		std::sort(rec.begin(), rec.end(), [](const KeyId &a, const KeyId &b) { return a.key < b.key; });
+		for (int64_t i = 0; i < n; i++) points[i] = rec[i].id;
 	}
-	std::sort(points.begin(), points.end(), [&](int a, int b) { return key1[ds.row_of_id[a]] < key1[ds.row_of_id[b]]; });
 	// :685-690 pivots at even ranks
 	const int num_iterations = (int)std::ceil(((double)n_points) / max_pts_from_one) - 1;
 	std::vector<int> pivots;
@@ -151,11 +165,16 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	// :694-701 per pivot: copy + unstable sort by distance to the pivot.  Independent per pivot, so
 	// the host threads can share them without changing any permutation.
 	std::vector<std::vector<int>> sorted(np);
+	std::vector<int32_t> row_of_point((size_t)n);
+	for (int64_t i = 0; i < n; i++) row_of_point[i] = (int32_t)ds.row_of_id[points[i]];
 #pragma omp parallel for schedule(dynamic)
 	for (long i = 0; i < (long)np; i++) {
-		std::vector<int> pts = points;
 		const uint16_t *kk = keys.data() + (size_t)i * n;
-		std::sort(pts.begin(), pts.end(), [&](int a, int b) { return kk[ds.row_of_id[a]] < kk[ds.row_of_id[b]]; });
+		std::vector<KeyId> rec((size_t)n);
+		for (int64_t j = 0; j < n; j++) rec[j] = {kk[row_of_point[j]], points[j]};
+		std::sort(rec.begin(), rec.end(), [](const KeyId &a, const KeyId &b) { return a.key < b.key; });
+		std::vector<int> pts((size_t)n);
+		for (int64_t j = 0; j < n; j++) pts[j] = rec[j].id;
 		sorted[i].swap(pts);
 	}
 	keys.clear();
@@ -508,6 +527,7 @@ void mean_shift(Ctx &c, BVec &bv) {
 	int64_t last = bv.pop();
 	if (last >= 0) kill_row(last);
 	std::vector<uint8_t> marks;
+	std::vector<int64_t> marked_rows((size_t)ds.n);
 	int64_t scans = 0, evals = 0;
 	while (last >= 0) {
 		std::vector<int64_t> current{last};
@@ -518,32 +538,43 @@ void mean_shift(Ctx &c, BVec &bv) {
 			const auto bounds = bv.get_range((uint64_t)(len * sim), (uint64_t)(len / sim));
 			mc_scan_result res;
 			res.n_eval = 0; res.n_pos = 0; res.best_row = -1; res.best_f0 = -1;
-			int64_t lo = 0, hi = -1;
+			int64_t lo = 0, hi = -1, nearest = -1;
 			if (bv.trip_count(bounds.first, bounds.second) > 0) {
 				lo = bv.row_at(bounds.first);
 				hi = bv.row_at(bounds.second);
 			}
-			if (hi >= lo) {
-				marks.resize((size_t)(hi - lo + 1));
-				if (c.model.align) align_scan(c, bv, cache, last, lo, hi, alive, res, marks);
-				else GPU(mc_scan(c.gpu, last, lo, hi, &res, marks.data()));
-				scans++;
-				evals += res.n_eval;
+			if (c.model.align) {
+				if (hi >= lo) {
+					marks.resize((size_t)(hi - lo + 1));
+					align_scan(c, bv, cache, last, lo, hi, alive, res, marks);
+				}
+			} else {
+				// get_close + remove_available + get_mean in one submission: the marked rows come back as
+				// a list, `current` and its running bin sums stay in HBM
+				mc_step_result sr;
+				GPU(mc_accumulate_step(c.gpu, last, lo, hi, first_mean ? 1 : 0, &sr, marked_rows.data(), (int64_t)marked_rows.size()));
+				res = sr.scan;
+				nearest = sr.nearest_row;
 			}
+			if (hi >= lo) { scans++; evals += res.n_eval; }
 			is_min = res.n_pos == 0;
 			if (is_min) {
 				// no close point left: the arg-max of f0 becomes the next seed (or the first point)
 				if (res.best_row < 0) next_seed = bv.pop();
 				else { next_seed = res.best_row; bv.erase_row(res.best_row); }
 				if (next_seed >= 0) kill_row(next_seed);
-			} else {
+			} else if (c.model.align) {
 				const size_t prev = current.size();
 				bv.remove_marked(bounds.first.bin, bounds.second.bin,
 				                 [&](int64_t r) { return r >= lo && r <= hi && marks[(size_t)(r - lo)] != 0; }, current);
 				// get_mean over all of `current` (ClusterFactory.cpp:382-425)
-				int64_t nearest = -1;
 				if (first_mean) GPU(mc_mean_nearest(c.gpu, current.data(), (int64_t)current.size(), 0, &nearest, nullptr));
 				else GPU(mc_mean_nearest(c.gpu, current.data() + prev, (int64_t)(current.size() - prev), 1, &nearest, nullptr));
+				first_mean = false;
+				last = nearest;
+			} else {
+				bv.remove_rows(marked_rows.data(), (size_t)res.n_pos);
+				current.insert(current.end(), marked_rows.begin(), marked_rows.begin() + res.n_pos);
 				first_mean = false;
 				last = nearest;
 			}
@@ -653,17 +684,30 @@ int run_pipeline(Options opt) {
 #ifdef _OPENMP
 	if (opt.threads > 0) omp_set_num_threads(opt.threads);
 #endif
+	// the CUDA context (driver start-up, ~1 s) is created on a helper thread while the files are read
+	int ctx_rc = MC_OK;
+	std::string ctx_err;
+	double ctx_s = 0;
+	std::thread ctx_thread([&]() {
+		Timer t;
+		ctx_rc = mc_ctx_create(&c.gpu, opt.device);
+		if (ctx_rc != MC_OK) ctx_err = mc_last_error();
+		ctx_s = t.lap();
+	});
+	struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{ctx_thread};
 	// ---- read (Runner.cpp:43-52, ChromListMaker) ------------------------------------------------
 	std::vector<size_t> file_first;
 	for (const std::string &f : opt.files) {
 		if (access(f.c_str(), F_OK) == -1) {
 			fprintf(stderr, "File \"%s\" does not exist\n", f.c_str());
+			ctx_thread.join();
 			exit(1);
 		}
 		std::string msg;
 		file_first.push_back(c.ds.fa.size());
 		if (!read_fasta(f, c.ds.fa, msg)) {
 			fprintf(stderr, "meshclust: %s\n", msg.c_str());
+			ctx_thread.join();
 			abort();   // the reference dies with an uncaught exception on malformed input
 		}
 	}
@@ -701,32 +745,52 @@ int run_pipeline(Options opt) {
 	for (int64_t r = 0; r < ds.n; r++) ds.row_of_id[ds.id_of_row[r]] = r;
 
 	// ---- upload in row order, encode, histograms (K1) -------------------------------------------
-	GPU(mc_ctx_create(&c.gpu, opt.device));
-	printf("  [gpu context %.2fs]\n", tm.lap());
 	{
-		std::vector<uint8_t> letters(ds.fa.letters.size());
+		// letters in row order + the non-N segment list of every row; rows are independent, so the
+		// host threads share them (segments: first pass counts, second pass fills)
+		RawBytes letters;
+		letters.resize(ds.fa.letters.size());
 		std::vector<int64_t> offs((size_t)ds.n + 1, 0), seg_off((size_t)ds.n + 1, 0);
-		std::vector<int32_t> segs;
-		int32_t buf[2 * 256];
+		for (int64_t r = 0; r < ds.n; r++) offs[r + 1] = offs[r] + (int64_t)ds.len[ds.id_of_row[r]];
+		constexpr int INLINE_SEGS = 4;
+		std::vector<int32_t> seg_inline((size_t)ds.n * 2 * INLINE_SEGS);
+		std::vector<int32_t> nseg((size_t)ds.n);
+		int64_t bad_row = -1;
+#pragma omp parallel for schedule(static)
 		for (int64_t r = 0; r < ds.n; r++) {
 			const int64_t id = ds.id_of_row[r];
 			const uint8_t *src = ds.fa.letters.data() + ds.fa.offsets[id];
 			const int64_t len = (int64_t)ds.len[id];
 			memcpy(letters.data() + offs[r], src, (size_t)len);
-			offs[r + 1] = offs[r] + len;
-			int ns = mc_host_segments(src, len, buf, 256);
-			if (ns < 0) {
-				fprintf(stderr, "meshclust: record \"%s\" has no usable sequence (the reference throws std::out_of_range)\n", ds.fa.headers[id].c_str());
-				abort();
+			nseg[r] = mc_host_segments(src, len, seg_inline.data() + (size_t)r * 2 * INLINE_SEGS, INLINE_SEGS);
+			if (nseg[r] < 0) {
+#pragma omp critical
+				if (bad_row < 0 || r < bad_row) bad_row = r;
 			}
-			if (ns > 256) {
-				std::vector<int32_t> big((size_t)ns * 2);
-				mc_host_segments(src, len, big.data(), ns);
-				segs.insert(segs.end(), big.begin(), big.end());
-			} else segs.insert(segs.end(), buf, buf + 2 * ns);
-			seg_off[r + 1] = seg_off[r] + ns;
+		}
+		if (bad_row >= 0) {
+			fprintf(stderr, "meshclust: record \"%s\" has no usable sequence (the reference throws std::out_of_range)\n", ds.fa.headers[ds.id_of_row[bad_row]].c_str());
+			ctx_thread.join();
+			abort();
+		}
+		for (int64_t r = 0; r < ds.n; r++) seg_off[r + 1] = seg_off[r] + nseg[r];
+		std::vector<int32_t> segs((size_t)seg_off[ds.n] * 2);
+#pragma omp parallel for schedule(static)
+		for (int64_t r = 0; r < ds.n; r++) {
+			int32_t *dst = segs.data() + 2 * seg_off[r];
+			if (nseg[r] <= INLINE_SEGS) memcpy(dst, seg_inline.data() + (size_t)r * 2 * INLINE_SEGS, (size_t)nseg[r] * 2 * sizeof(int32_t));
+			else {
+				const int64_t id = ds.id_of_row[r];
+				mc_host_segments(ds.fa.letters.data() + ds.fa.offsets[id], (int64_t)ds.len[id], dst, nseg[r]);
+			}
 		}
 		printf("  [row order + segments %.2fs]\n", tm.lap());
+		ctx_thread.join();
+		if (ctx_rc != MC_OK) {
+			fprintf(stderr, "meshclust: mc_ctx_create failed: %s\n", ctx_err.c_str());
+			exit(2);
+		}
+		printf("  [gpu context %.2fs on a helper thread, waited %.2fs]\n", ctx_s, tm.lap());
 		if (mc_load_sequences(c.gpu, letters.data(), offs.data(), ds.n, segs.data(), seg_off.data()) != MC_OK) {
 			fprintf(stderr, "meshclust: %s\n", mc_last_error());
 			abort();   // InvalidInputException in the reference
@@ -751,8 +815,11 @@ int run_pipeline(Options opt) {
 	}
 	mean_shift(c, bv);
 	printf("Total %.2fs\n", total.lap());
-	mc_ctx_destroy(c.gpu);
-	return 0;
+	if (getenv("MC_CLEAN_EXIT")) { mc_ctx_destroy(c.gpu); return 0; }
+	// the output file is closed: skip the teardown of the CUDA context and of GBs of host vectors
+	fflush(stdout);
+	fflush(stderr);
+	_exit(0);
 }
 
 // ----------------------------------------------------------------------------------------------

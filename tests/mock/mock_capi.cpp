@@ -210,6 +210,21 @@ int mc_mean_nearest(mc_ctx *c, const int64_t *rows, int64_t m, int append, int64
 	*nearest = nearest_of(c, c->members, dist);
 	return MC_OK;
 }
+int mc_accumulate_step(mc_ctx *c, int64_t center, int64_t lo, int64_t hi, int restart, mc_step_result *res, int64_t *rows_out, int64_t cap) {
+	if (restart) { c->members.clear(); c->members.push_back(center); }
+	std::vector<uint8_t> marks((size_t)(hi >= lo ? hi - lo + 1 : 0));
+	mc_scan(c, center, lo, hi, &res->scan, marks.data());
+	res->nearest_row = -1;
+	if (res->scan.n_pos > 0) {
+		if (rows_out && cap < res->scan.n_pos) return fail(MC_ERR_ARG, "marked_rows_out too small");
+		int64_t w = 0;
+		for (int64_t r = lo; r <= hi; r++)
+			if (marks[(size_t)(r - lo)]) { c->members.push_back(r); if (rows_out) rows_out[w++] = r; }
+		res->nearest_row = nearest_of(c, c->members, nullptr);
+	}
+	res->n_members = (int64_t)c->members.size();
+	return MC_OK;
+}
 int mc_update_centers(mc_ctx *c, const int64_t *centers, int64_t nc, const int64_t *cand, int64_t, const int64_t *cb, const int64_t *ce, int64_t *next) {
 #pragma omp parallel for schedule(dynamic)
 	for (int64_t j = 0; j < nc; j++) {

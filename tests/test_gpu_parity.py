@@ -269,6 +269,110 @@ def test_mean_nearest_vs_oracle(ctx, oracle, dtype, hi, k):
         assert _bits(got[1]) == _bits(dd.min())
 
 
+@pytest.mark.parametrize("dtype,hi,k,n", [(np.uint8, 255, 3, 6000), (np.uint8, 255, 5, 3000), (np.uint16, 3000, 4, 2500), (np.uint8, 200, 6, 900)])
+def test_accumulate_step_vs_unfused_and_oracle(ctx, oracle, dtype, hi, k, n):
+    """mc_accumulate_step (scan + remove + get_mean in one submission) against the same greedy loop
+    driven through mc_scan + mc_mean_nearest, and against the oracle's scan / mean / distance_d."""
+    from meshclust_b200 import api
+    rng = np.random.default_rng(300 + k)
+    nb = 4 ** k
+    H = _rand_hists(rng, n, nb, dtype, hi, clusters=7)
+    lens = (1000 + rng.integers(0, 40, n)).astype(np.uint64)
+    mins, maxs, w = _model(3)
+    maxs[2] = 4.0 * nb * (hi / 255.0)
+    # pick the bias so that a scan marks a sizeable but partial set of rows
+    ctx.load_histograms(H, lens, k)
+    ctx.set_model(mins, maxs, w, 3)
+    s0, _, _ = oracle.scan(H, lens, H[0], int(lens[0]), mins, maxs, w, 3)
+    w = w.copy()
+    w[0] -= np.sort(s0)[int(0.9 * n)]
+    ctx.set_model(mins, maxs, w, 3)
+
+    def greedy(step_fn, reset_fn):
+        reset_fn()
+        alive = np.ones(n, bool)
+        trace = []
+        seed = 0
+        for _ in range(6):
+            alive[seed] = False
+            last, restart, is_min = seed, True, False
+            lo, hi_ = 3, n - 4
+            while not is_min:
+                scan, nearest, rows = step_fn(last, lo, hi_, restart)
+                restart = False
+                trace.append((last, scan[0], scan[1], scan[2], nearest, tuple(rows[:50]), len(rows)))
+                alive[rows] = False
+                is_min = scan[1] == 0
+                if not is_min:
+                    last = nearest
+                if len(trace) > 60:
+                    break
+            nxt = scan[2]
+            if nxt < 0:
+                break
+            seed = int(nxt)
+        return trace
+
+    # fused
+    c1 = ctx
+
+    def reset1():
+        c1.alive_reset()
+
+    def step1(last, lo, hi_, restart):
+        if restart:
+            c1.alive_kill(np.array([last]))
+        r, rows = c1.accumulate_step(last, lo, hi_, restart)
+        return r.scan.as_tuple(), r.nearest_row, rows
+
+    t1 = greedy(step1, reset1)
+
+    # unfused on a second context
+    with api.Context(0) as c2:
+        c2.load_histograms(H, lens, k)
+        c2.set_model(mins, maxs, w, 3)
+        state = {"cur": None}
+
+        def reset2():
+            c2.alive_reset()
+
+        def step2(last, lo, hi_, restart):
+            if restart:
+                c2.alive_kill(np.array([last]))
+                state["cur"] = [last]
+            res, marks = c2.scan(last, lo, hi_)
+            rows = np.nonzero(marks)[0] + lo
+            nearest = -1
+            if rows.size:
+                state["cur"].extend(rows.tolist())
+                nearest, _ = c2.mean_nearest(np.array(state["cur"], np.int64))
+            return res.as_tuple(), nearest, rows
+
+        t2 = greedy(step2, reset2)
+    assert len(t1) == len(t2) and len(t1) >= 6
+    for a, b in zip(t1, t2):
+        assert a[:5] == b[:5] and a[6] == b[6] and a[5] == b[5], (a, b)
+    assert sum(t[6] for t in t1) > 50, "the test model marks nothing: no mean was exercised"
+
+    # oracle check of the first productive step: marks and the nearest member
+    ctx.alive_reset()
+    ctx.alive_kill(np.array([0]))
+    r, rows = ctx.accumulate_step(0, 0, n - 1, True)
+    ws, wf0, wfl = oracle.scan(H, lens, H[0], int(lens[0]), mins, maxs, w, 3)
+    near = np.abs(ws) < NEAR
+    want = np.nonzero(wfl.astype(bool) & (np.arange(n) != 0))[0]
+    if not near.any():
+        assert np.array_equal(rows, want)
+    cur = np.concatenate([[0], rows])
+    mean = oracle.mean(H[cur])
+    dd = np.array([oracle.distance_d(H[x], mean) for x in cur])
+    assert r.nearest_row == int(cur[int(np.argmin(dd))])
+    assert r.n_members == cur.size
+    # empty range: nothing evaluated, nothing marked, the cluster is just its seed
+    r, rows = ctx.accumulate_step(5, 10, 9, True)
+    assert r.scan.as_tuple() == (0, 0, -1, -1.0) and r.nearest_row == -1 and r.n_members == 1 and rows.size == 0
+
+
 @pytest.mark.parametrize("k", [3, 4, 5])
 def test_update_centers_vs_oracle(ctx, oracle, k):
     rng = np.random.default_rng(80 + k)

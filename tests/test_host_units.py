@@ -1,0 +1,14 @@
+"""Unit self-checks of the host-side containers (CPU): compiled from tests/units/*.cpp."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bvec_selfcheck(tmp_path):
+    # binary-search index_of == the reference's literal loop (bvec.cpp:123-149); bitmap-backed bins ==
+    # an erase-based model: pop order, sizes, and "a bvec range is a contiguous alive row range"
+    exe = os.path.join(str(tmp_path), "bvec_selfcheck")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "units", "bvec_selfcheck.cpp"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
