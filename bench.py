@@ -43,6 +43,18 @@ S_CENTERS = 10            # scans per step
 FALLBACK_HBM_GBS = 6650.0
 
 
+_JSON_FD = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -212,6 +224,13 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
+    # the contract is ONE JSON line on stdout: libraries that print banners to fd 1 (NCCL's version line)
+    # are sent to stderr, the JSON line goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -246,41 +265,101 @@ def main():
     mins, maxs, w, acc = fit_model(ctx, n, tmpl, rng)
     log(f"[bench] rank {rank}: histograms {t_hist * 1e3:.0f} ms (host->host), model acc {acc:.3f}")
 
+    # ---- N > 1: every rank holds the whole histogram matrix (all-gathered once over NCCL, the
+    # "centers are broadcast" of SURVEY 8(e) paid once instead of per scan); scan work and alive
+    # flags are sharded: rank r evaluates rows [r*n, (r+1)*n) of the N = world*n points
+    exchange = "none"
+    N = n * world
+    if world > 1:
+        t_loc = torch.from_numpy(hist).cuda()
+        t_all = torch.empty((N, nbins), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(t_all, t_loc)
+        l_loc = torch.from_numpy(lens.astype(np.int64)).cuda()
+        l_all = torch.empty(N, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(l_all, l_loc)
+        hist_all = t_all.cpu().numpy()
+        lens_all = l_all.cpu().numpy().astype(np.uint64)
+        del t_loc, t_all, l_loc, l_all
+        model = [mins, maxs, w]
+        dist.broadcast_object_list(model, src=0)   # one classifier for the job
+        mins, maxs, w = model
+    else:
+        hist_all, lens_all = hist, lens
+
     # ---- resident data: R replicas so that consecutive launches never re-read L2-resident rows
     row_bytes = nbins + 24
     R = int(np.ceil(2.2 * 126e6 / (n * row_bytes)))
-    big = np.ascontiguousarray(np.tile(hist, (R, 1)))
-    biglens = np.tile(lens, R)
+    big = np.ascontiguousarray(np.tile(hist_all, (R, 1)))
+    biglens = np.tile(lens_all, R)
     ctx.load_histograms(big, biglens, K)
     ctx.set_model(mins, maxs, w, 4)
     del big
     S = S_CENTERS
-    centers_local = rng.integers(0, n, 64)
+    centers_global = np.random.default_rng(1234).integers(0, N, 64)   # the same centers on every rank
+    centers_local = centers_global if world == 1 else rng.integers(0, n, 64)
 
     def step_args(step):
         reps = [(step * S + s) % R for s in range(S)]
-        cr = np.array([r * n + centers_local[(step * S + s) % 64] for s, r in enumerate(reps)], np.int64)
-        lo = np.array([r * n for r in reps], np.int64)
-        hi = lo + n - 1
+        cr = np.array([r * N + centers_global[(step * S + s) % 64] for s, r in enumerate(reps)], np.int64)
+        lo = np.array([r * N for r in reps], np.int64)
+        hi = lo + N - 1
         return cr, lo, hi
 
-
-    # N > 1: the context launches on torch's current stream, the per-scan summaries are folded on the
-    # device and all-gathered over NCCL (one collective per step, 32 bytes per scan and rank)
+    # N > 1: the scan kernel stores every CTA's partial into all ranks' inboxes over NVLink peer memory
+    # (CUDA IPC between the processes); one tiny combine kernel per step folds world x SMs records per
+    # scan on the device.  Fallback when peer memory cannot be opened: device fold + NCCL all-gather.
     if world > 1:
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        records = torch.zeros((S, 4), dtype=torch.int64, device="cuda")
+        try:
+            handle = ctx.comm_init(rank, world, 0, -1)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            ctx.comm_connect(handles)
+            ok = torch.ones(1, device="cuda")
+        except Exception as e:   # noqa: BLE001
+            log(f"[bench] rank {rank}: peer inboxes unavailable ({e}); falling back to NCCL all-gather")
+            ok = torch.zeros(1, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        exchange = "peer_inbox" if float(ok.item()) > 0 else "nccl_allgather"
+        if exchange == "nccl_allgather":
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            records = torch.zeros((S, 4), dtype=torch.int64, device="cuda")
+    last_results = [None]
+
+    def enqueue_sharded(step):
+        cr, lo, hi = step_args(step)
+        ctx.scan_sharded_enqueue_many(cr, lo, hi, lo + rank * n, lo + (rank + 1) * n - 1, False, (step & 1) * S)
+
+    pending = [None]   # step whose exchange has been sent but not folded yet
 
     def run_step(step):
-        cr, lo, hi = step_args(step)
-        ctx.scan_enqueue_many(cr, lo, hi, False, 0)
-        if world > 1:
+        if world == 1:
+            cr, lo, hi = step_args(step)
+            ctx.scan_enqueue_many(cr, lo, hi, False, 0)
+            return
+        if exchange == "nccl_allgather":
+            cr, lo, hi = step_args(step)
+            ctx.scan_enqueue_many(cr, lo + rank * n, lo + (rank + 1) * n - 1, False, 0)
             ctx.scan_fold_dev(0, S, records.data_ptr())
-            return sharding.combine_scan_records(records, n)
-        return None
+            last_results[0] = sharding.combine_scan_records(records, 0)
+            return
+        # software pipeline: fold the previous step's exchange on the device, enqueue this step's scans
+        # behind it, and only then let the host wait for the previous summaries
+        prev = pending[0]
+        if prev is not None:
+            ctx.scan_sharded_combine((prev & 1) * S, S)
+        enqueue_sharded(step)
+        if prev is not None:
+            last_results[0] = ctx.scan_sharded_wait((prev & 1) * S, S)
+        pending[0] = step
+
+    def drain():
+        if world > 1 and exchange == "peer_inbox" and pending[0] is not None:
+            last_results[0] = ctx.scan_sharded_collect((pending[0] & 1) * S, S)
+            pending[0] = None
 
     for i in range(args.warmup):
         run_step(i)
+    drain()
     ctx.sync()
     launches0 = ctx.launches
 
@@ -295,6 +374,7 @@ def main():
     ev0.record(stream)
     for i in range(args.steps):
         run_step(args.warmup + i)
+    drain()
     ev1.record(stream)
     ctx.sync()
     torch.cuda.synchronize()
@@ -304,8 +384,19 @@ def main():
     clocks = sampler.stop()
     dev_ms = ev0.elapsed_time(ev1)
     gpu_launches = ctx.launches - launches0
-    results = ctx.scan_collect(0, S)
-    assert all(r[0] == n for r in results), "scan did not evaluate every point"
+    if world == 1:
+        results = ctx.scan_collect(0, S)
+        assert all(r[0] == n for r in results), "scan did not evaluate every point"
+    else:
+        results = last_results[0]
+        assert all(r[0] == N for r in results), f"sharded scan did not evaluate every point: {results[:2]}"
+        if exchange == "peer_inbox":
+            # self-check of the exchange: this rank also holds all rows, so one un-sharded scan over the
+            # whole replica must give exactly the exchanged summary
+            cr, lo, hi = step_args(args.warmup + args.steps - 1)
+            ctx.scan_enqueue(int(cr[0]), int(lo[0]), int(hi[0]), False, 100)
+            whole = ctx.scan_collect(100, 1)[0]
+            assert whole == results[0], f"sharded summary {results[0]} != single-GPU summary {whole}"
 
     # device time when there is no exchange; wall (barrier+sync bracketed) when there is one
     total_ms = dev_ms if world == 1 else t_wall * 1e3
@@ -341,7 +432,7 @@ def main():
            "config": {"workload": f"{WORKLOAD}: 100k synthetic 1.5 kb 16S-like sequences, --id 0.97 --kmer 4",
                       "points_per_gpu": n, "bins": nbins, "centers_per_step": S, "evals_per_step": evals_per_step,
                       "l2": f"inputs larger than L2: {R} replicas of the batch ({R * n * row_bytes / 1e6:.0f} MB), launches rotate through them",
-                      "model": "4 features, bounds from 3000 sampled pairs, least-squares GLM", "parallelism": f"points sharded x{world}"},
+                      "model": "4 features, bounds from 3000 sampled pairs, least-squares GLM", "parallelism": f"points sharded x{world}", "exchange": exchange},
            "clocks": clocks, "gpu_launches": int(gpu_launches), "roofline": roofline}
 
     if rank == 0:
@@ -391,7 +482,7 @@ def main():
                 out["seqs_clustered"] = cli_leg(letters, offs, tmpl, cfg)
             except Exception as e:
                 out["seqs_clustered"] = {"error": str(e)[:200]}
-        print(json.dumps(out), flush=True)
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -501,7 +592,7 @@ def reference_arm(args):
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 

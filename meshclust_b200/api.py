@@ -31,7 +31,8 @@ EXPORTS = [
     "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_copy_digits",
     "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
     "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
-    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_update_centers", "mc_align_pairs",
+    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_comm_init", "mc_comm_set_shard", "mc_comm_connect", "mc_comm_connect_local",
+    "mc_scan_sharded_enqueue", "mc_scan_sharded_enqueue_many", "mc_scan_sharded_collect", "mc_scan_sharded_combine", "mc_scan_sharded_wait", "mc_clone_points", "mc_accumulate_step_sharded", "mc_update_centers", "mc_align_pairs",
     "mc_kmer_histograms_host", "mc_scan_host",
 ]
 
@@ -248,6 +249,66 @@ class Context:
         res = (ScanResult * nslots)()
         _check(_lib.mc_scan_collect(self._h, C.c_int(slot0), C.c_int(nslots), C.byref(res)))
         return [r.as_tuple() for r in res]
+
+    # -- multi-GPU: sharded scans ---------------------------------------------------------
+    def comm_init(self, rank: int, world: int, shard_lo: int, shard_hi: int) -> bytes:
+        """allocate this rank's inbox; returns its CUDA IPC handle (64 bytes) for the other ranks"""
+        h = (C.c_uint8 * 64)()
+        _check(_lib.mc_comm_init(self._h, C.c_int(rank), C.c_int(world), C.c_int64(shard_lo), C.c_int64(shard_hi), h))
+        return bytes(h)
+
+    def comm_connect(self, handles):
+        """handles: the 64-byte IPC handles of all ranks in rank order (other processes)"""
+        buf = b"".join(handles)
+        arr = (C.c_uint8 * len(buf)).from_buffer_copy(buf)
+        _check(_lib.mc_comm_connect(self._h, arr))
+
+    @staticmethod
+    def comm_connect_local(contexts):
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        _check(_lib.mc_comm_connect_local(arr, C.c_int(len(contexts))))
+
+    def scan_sharded_enqueue(self, center_row: int, lo: int, hi: int, remove_marked: bool, slot: int):
+        _check(_lib.mc_scan_sharded_enqueue(self._h, C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi),
+                                            C.c_int(1 if remove_marked else 0), C.c_int(slot)))
+
+    def scan_sharded_enqueue_many(self, center_rows, lo, hi, shard_lo, shard_hi, remove_marked: bool, slot0: int = 0):
+        cr = np.ascontiguousarray(center_rows, np.int64)
+        lo = np.ascontiguousarray(lo, np.int64)
+        hi = np.ascontiguousarray(hi, np.int64)
+        sl = None if shard_lo is None else np.ascontiguousarray(shard_lo, np.int64)
+        sh = None if shard_hi is None else np.ascontiguousarray(shard_hi, np.int64)
+        _check(_lib.mc_scan_sharded_enqueue_many(self._h, _p(cr), _p(lo), _p(hi), _p(sl), _p(sh), C.c_int(cr.size),
+                                                 C.c_int(1 if remove_marked else 0), C.c_int(slot0)))
+
+    def scan_sharded_collect(self, slot0: int, nslots: int):
+        res = (ScanResult * nslots)()
+        _check(_lib.mc_scan_sharded_collect(self._h, C.c_int(slot0), C.c_int(nslots), C.byref(res)))
+        return [r.as_tuple() for r in res]
+
+    def scan_sharded_combine(self, slot0: int, nslots: int):
+        _check(_lib.mc_scan_sharded_combine(self._h, C.c_int(slot0), C.c_int(nslots)))
+
+    def scan_sharded_wait(self, slot0: int, nslots: int):
+        res = (ScanResult * nslots)()
+        _check(_lib.mc_scan_sharded_wait(self._h, C.c_int(slot0), C.c_int(nslots), C.byref(res)))
+        return [r.as_tuple() for r in res]
+
+    def clone_points_from(self, src: "Context"):
+        _check(_lib.mc_clone_points(self._h, src._h))
+        self.n, self.k, self.tbytes = src.n, src.k, src.tbytes
+
+    @staticmethod
+    def accumulate_step_sharded(contexts, center_row: int, lo: int, hi: int, restart: bool):
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        res = StepResult()
+        rows = np.zeros(max(contexts[0].n, 1), np.int64)
+        _check(_lib.mc_accumulate_step_sharded(arr, C.c_int(len(contexts)), C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi),
+                                               C.c_int(1 if restart else 0), C.byref(res), _p(rows), C.c_int64(rows.size)))
+        return res, rows[: res.scan.n_pos].copy()
+
+    def comm_set_shard(self, shard_lo: int, shard_hi: int):
+        _check(_lib.mc_comm_set_shard(self._h, C.c_int64(shard_lo), C.c_int64(shard_hi)))
 
     # -- stage 3 --------------------------------------------------------------------------
     def mean_nearest(self, rows, append: bool = False):

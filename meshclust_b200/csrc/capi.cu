@@ -145,6 +145,7 @@ extern "C" void mc_ctx_destroy(mc_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	mc_comm_destroy(ctx);
 	free_seq(ctx);
 	free_hist(ctx);
 	cudaFree(ctx->d_scratch);
@@ -658,17 +659,9 @@ extern "C" int mc_mean_nearest(mc_ctx *ctx, const int64_t *rows, int64_t m, int 
 	return MC_OK;
 }
 
-extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart,
-                                  mc_step_result *res, int64_t *marked_rows_out, int64_t cap) {
-	MC_NEED_HIST(ctx);
-	MC_NEED_MODEL(ctx);
-	MC_REQUIRE(res, MC_ERR_ARG, "mc_accumulate_step: res is NULL");
-	MC_REQUIRE(center_row >= 0 && center_row < ctx->n, MC_ERR_ARG, "center row out of range");
-	MC_REQUIRE(hi < lo || (lo >= 0 && hi < ctx->n), MC_ERR_ARG, "scan range [%lld,%lld] out of range", (long long)lo, (long long)hi);
-	MC_REQUIRE(restart || ctx->members_n > 0, MC_ERR_STATE, "mc_accumulate_step: no cluster has been started (restart = 0)");
-	MC_CUDA(cudaSetDevice(ctx->device));
-	int rc = ensure_members(ctx, ctx->n + 1);   // a cluster holds every row at most once
-	if (rc) return rc;
+// device state of the fused step + its host-mapped result block: [0,48) mc_step_result, [56,60) error
+// word of a sharded step, [64, ...) int32 marked rows
+static int ensure_step_buffers(mc_ctx *ctx) {
 	if (!ctx->d_acc) {
 		MC_CUDA(cudaMalloc(&ctx->d_acc, mc_acc_dev_bytes()));
 		MC_CUDA(cudaMemsetAsync(ctx->d_acc, 0, mc_acc_dev_bytes(), ctx->stream));
@@ -680,6 +673,22 @@ extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, i
 		MC_CUDA(cudaHostGetDevicePointer(&ctx->h_step_dev, ctx->h_step, 0));
 		ctx->h_step_bytes = need;
 	}
+	return MC_OK;
+}
+
+extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart,
+                                  mc_step_result *res, int64_t *marked_rows_out, int64_t cap) {
+	MC_NEED_HIST(ctx);
+	MC_NEED_MODEL(ctx);
+	MC_REQUIRE(res, MC_ERR_ARG, "mc_accumulate_step: res is NULL");
+	MC_REQUIRE(center_row >= 0 && center_row < ctx->n, MC_ERR_ARG, "center row out of range");
+	MC_REQUIRE(hi < lo || (lo >= 0 && hi < ctx->n), MC_ERR_ARG, "scan range [%lld,%lld] out of range", (long long)lo, (long long)hi);
+	MC_REQUIRE(restart || ctx->members_n > 0, MC_ERR_STATE, "mc_accumulate_step: no cluster has been started (restart = 0)");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int rc = ensure_members(ctx, ctx->n + 1);   // a cluster holds every row at most once
+	if (rc) return rc;
+	rc = ensure_step_buffers(ctx);
+	if (rc) return rc;
 	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)MC_SCAN_PARTS * 32}));
 	if (rc) return rc;
 	Carve cv(ctx->d_scratch);
@@ -698,6 +707,84 @@ extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, i
 	if (marked_rows_out) {
 		MC_REQUIRE(cap >= res->scan.n_pos, MC_ERR_ARG, "marked_rows_out holds %lld rows, %lld were marked", (long long)cap, (long long)res->scan.n_pos);
 		const int32_t *src = reinterpret_cast<const int32_t *>((const uint8_t *)ctx->h_step + 64);
+		for (int64_t i = 0; i < res->scan.n_pos; i++) marked_rows_out[i] = src[i];
+	}
+	return MC_OK;
+}
+
+int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence);
+int mc_comm_combine_dev(mc_ctx *ctx, int slot, const void **rec_dev_out, unsigned int **err_dev_out);
+
+extern "C" int mc_clone_points(mc_ctx *dst, mc_ctx *src) {
+	MC_REQUIRE(dst && src && dst != src, MC_ERR_ARG, "mc_clone_points: bad arguments");
+	MC_REQUIRE(src->have_hist, MC_ERR_STATE, "mc_clone_points: the source has no histograms");
+	MC_CUDA(cudaSetDevice(src->device));
+	MC_CUDA(cudaStreamSynchronize(src->stream));
+	MC_CUDA(cudaSetDevice(dst->device));
+	int rc = alloc_hist(dst, src->n, src->k, src->tbytes);
+	if (rc) return rc;
+	const size_t hb = (size_t)src->n * src->nbins * src->tbytes, ab = (size_t)src->n * sizeof(McRowAux);
+	if (dst->device == src->device) {
+		MC_CUDA(cudaMemcpyAsync(dst->d_hist, src->d_hist, hb, cudaMemcpyDeviceToDevice, dst->stream));
+		MC_CUDA(cudaMemcpyAsync(dst->d_aux, src->d_aux, ab, cudaMemcpyDeviceToDevice, dst->stream));
+	} else {
+		MC_CUDA(cudaMemcpyPeerAsync(dst->d_hist, dst->device, src->d_hist, src->device, hb, dst->stream));
+		MC_CUDA(cudaMemcpyPeerAsync(dst->d_aux, dst->device, src->d_aux, src->device, ab, dst->stream));
+	}
+	MC_CUDA(cudaStreamSynchronize(dst->stream));
+	dst->model = src->model;
+	dst->have_hist = true;
+	return MC_OK;
+}
+
+extern "C" int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_t center_row, int64_t lo, int64_t hi,
+                                          int restart, mc_step_result *res, int64_t *marked_rows_out, int64_t cap) {
+	MC_REQUIRE(ctxs && world >= 1 && world <= MC_MAX_PEERS && res, MC_ERR_ARG, "mc_accumulate_step_sharded: bad arguments");
+	mc_ctx *root = ctxs[0];
+	for (int r = 0; r < world; r++) {
+		mc_ctx *c = ctxs[r];
+		MC_REQUIRE(c && c->have_hist && c->model.valid, MC_ERR_STATE, "rank %d: histograms / model missing (mc_clone_points)", r);
+		MC_REQUIRE(c->comm.world == world && c->comm.rank == r && c->comm.connected, MC_ERR_STATE, "rank %d: mc_comm_init + mc_comm_connect_local first", r);
+		MC_REQUIRE(c->n == root->n && c->nbins == root->nbins && c->tbytes == root->tbytes, MC_ERR_STATE, "rank %d holds different points", r);
+		MC_REQUIRE(!c->comm.slot_pending[0], MC_ERR_STATE, "rank %d: exchange slot 0 is busy", r);
+	}
+	MC_REQUIRE(center_row >= 0 && center_row < root->n, MC_ERR_ARG, "center row out of range");
+	MC_REQUIRE(hi < lo || (lo >= 0 && hi < root->n), MC_ERR_ARG, "scan range [%lld,%lld] out of range", (long long)lo, (long long)hi);
+	MC_REQUIRE(restart || root->members_n > 0, MC_ERR_STATE, "mc_accumulate_step_sharded: no cluster has been started (restart = 0)");
+	MC_CUDA(cudaSetDevice(root->device));
+	int rc = ensure_members(root, root->n + 1);
+	if (rc) return rc;
+	rc = ensure_step_buffers(root);
+	if (rc) return rc;
+	// every rank scans its shard; marks land in rank 0's array, summaries in every inbox (the
+	// system-scope fence in the kernel orders a CTA's marks before its record)
+	for (int r = world - 1; r >= 0; r--) {
+		mc_ctx *c = ctxs[r];
+		c->comm.marks_target = r == 0 ? nullptr : root->d_marks;
+		rc = mc_comm_scan_push(c, center_row, lo, hi, 1, 0, 1);
+		c->comm.marks_target = nullptr;
+		if (rc) return rc;
+	}
+	const void *rec = nullptr;
+	unsigned int *d_err = nullptr;
+	rc = mc_comm_combine_dev(root, 0, &rec, &d_err);
+	if (rc) return rc;
+	rc = mc_launch_accumulate_tail(root, center_row, lo, hi, restart, rec, 1, root->d_acc, root->h_step_dev,
+	                               reinterpret_cast<int32_t *>((uint8_t *)root->h_step_dev + 64));
+	if (rc) return rc;
+	unsigned int *h_err = reinterpret_cast<unsigned int *>((uint8_t *)root->h_step + 56);
+	MC_CUDA(cudaMemcpyAsync(h_err, d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, root->stream));
+	MC_CUDA(cudaStreamSynchronize(root->stream));
+	if (*h_err) {
+		MC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), root->stream));
+		mc_set_error("sharded step: a rank's records did not arrive (world %d)", world);
+		return MC_ERR_CUDA;
+	}
+	*res = *reinterpret_cast<const mc_step_result *>(root->h_step);
+	root->members_n = res->n_members;
+	if (marked_rows_out) {
+		MC_REQUIRE(cap >= res->scan.n_pos, MC_ERR_ARG, "marked_rows_out holds %lld rows, %lld were marked", (long long)cap, (long long)res->scan.n_pos);
+		const int32_t *src = reinterpret_cast<const int32_t *>((const uint8_t *)root->h_step + 64);
 		for (int64_t i = 0; i < res->scan.n_pos; i++) marked_rows_out[i] = src[i];
 	}
 	return MC_OK;

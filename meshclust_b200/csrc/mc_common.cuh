@@ -72,7 +72,9 @@ struct __align__(32) McRowAux {
 // parity = epoch & 1 double-buffers a slot: a rank can be at most one exchange ahead of a peer.
 // ---------------------------------------------------------------------------------------------
 #define MC_MAX_PEERS 8
+#ifndef MC_XSLOTS
 #define MC_XSLOTS 64
+#endif
 #define MC_LL_RECORD_BYTES 64
 #define MC_INBOX_BYTES ((size_t)2 * MC_XSLOTS * MC_MAX_PEERS * MC_SCAN_PARTS * MC_LL_RECORD_BYTES)
 
@@ -93,8 +95,11 @@ struct McComm {
 	bool ipc_opened[MC_MAX_PEERS] = {};
 	bool connected = false;
 	unsigned int slot_epoch[MC_XSLOTS] = {};
-	unsigned char slot_pending[MC_XSLOTS] = {};
+	unsigned char slot_pending[MC_XSLOTS] = {};   // 0 free, 1 scan enqueued, 2 combine enqueued
 	void *d_out = nullptr;                     // MC_XSLOTS combined records + error word
+	void *h_out = nullptr;                     // pinned host copy of d_out
+	cudaEvent_t done = nullptr;                // recorded behind the last combine
+	uint8_t *marks_target = nullptr;           // sharded Phase A: the marks array of the rank that runs the tail
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -161,6 +166,7 @@ struct mc_ctx {
 	size_t h_step_bytes = 0;
 };
 
+void mc_comm_destroy(mc_ctx *ctx);
 int mc_ensure_scratch(mc_ctx *ctx, size_t bytes);
 int mc_ensure_pinned(mc_ctx *ctx, size_t bytes);
 

@@ -1,0 +1,324 @@
+// Multi-GPU exchange for sharded scans: every rank evaluates the rows of its
+// shard against the same center; what has to cross GPUs per scan is one 32-byte summary (count,
+// positives, first-max arg-max).  The reference's counterpart is the OpenMP reduction at the end of
+// Trainer::get_close (custom `pmax` arg-max + `&&`, Trainer.cpp:38-48,81).
+//
+// The scan kernel itself stores each CTA's partial into every rank's inbox over NVLink peer memory
+// (McPeerPush in mc_common.cuh, {data, epoch} words); scan_combine_kernel below waits for the
+// world x num_sms records of a slot and folds them with the reference's rule (largest f0, first
+// row among equals).  No host round trip, no collective library call, nothing but posted stores on
+// the critical path.  Rows are numbered globally on every rank (the histogram matrix is replicated
+// once after K1; only scan work and alive flags are sharded), so records compare directly.
+#include <string.h>
+
+#include "mc_common.cuh"
+
+int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                        void *partials_dev, int *nparts_out, const McPeerPush *push);
+
+int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence);
+
+struct CombineArgs {
+	unsigned long long slot_off[MC_XSLOTS];
+	unsigned int epoch[MC_XSLOTS];
+};
+
+constexpr int COMBINE_THREADS = 256;
+constexpr unsigned long long COMBINE_TIMEOUT_NS = 4000000000ull;   // a peer that never sends is an error, not a hang
+
+__device__ __forceinline__ void xmerge(mc_scan_result &a, const mc_scan_result &b) {
+	a.n_eval += b.n_eval;
+	a.n_pos += b.n_pos;
+	if (b.best_row >= 0 && (b.best_f0 > a.best_f0 || (b.best_f0 == a.best_f0 && (a.best_row < 0 || b.best_row < a.best_row)))) {
+		a.best_f0 = b.best_f0;
+		a.best_row = b.best_row;
+	}
+}
+
+__device__ __forceinline__ uint4 ld_volatile16(const void *p) {
+	uint4 r;
+	asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+	return r;
+}
+
+// one CTA per slot
+__global__ void __launch_bounds__(COMBINE_THREADS)
+scan_combine_kernel(const uint8_t *__restrict__ inbox, int world, int nparts, CombineArgs args, int slot0,
+                    mc_scan_result *__restrict__ out, unsigned int *__restrict__ err) {
+	__shared__ mc_scan_result s_part[COMBINE_THREADS / 32];
+	const int slot = slot0 + blockIdx.x;
+	const unsigned int epoch = args.epoch[slot];
+	const uint8_t *base = inbox + args.slot_off[slot];
+	mc_scan_result mine;
+	mine.n_eval = 0; mine.n_pos = 0; mine.best_row = -1; mine.best_f0 = -1.0;
+	unsigned long long t0;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	bool failed = false;
+	for (int i = threadIdx.x; i < world * nparts; i += COMBINE_THREADS) {
+		const int rank = i / nparts, cta = i % nparts;
+		const uint8_t *rec = base + ((size_t)rank * MC_SCAN_PARTS + cta) * MC_LL_RECORD_BYTES;
+		uint4 q[4];
+		for (;;) {
+#pragma unroll
+			for (int j = 0; j < 4; j++) q[j] = ld_volatile16(rec + j * 16);
+			bool ok = true;
+#pragma unroll
+			for (int j = 0; j < 4; j++) ok = ok && q[j].y == epoch && q[j].w == epoch;
+			if (ok) break;
+			unsigned long long t1;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if (t1 - t0 > COMBINE_TIMEOUT_NS) { failed = true; break; }
+		}
+		if (failed) break;
+		mc_scan_result r;
+		r.n_eval = (long long)((unsigned long long)q[0].x | ((unsigned long long)q[0].z << 32));
+		r.n_pos = (long long)((unsigned long long)q[1].x | ((unsigned long long)q[1].z << 32));
+		r.best_row = (long long)((unsigned long long)q[2].x | ((unsigned long long)q[2].z << 32));
+		r.best_f0 = __longlong_as_double((long long)((unsigned long long)q[3].x | ((unsigned long long)q[3].z << 32)));
+		xmerge(mine, r);
+	}
+	if (failed) atomicExch(err, 1u);
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		mc_scan_result other;
+		other.n_eval = __shfl_xor_sync(MC_FULL_MASK, mine.n_eval, o);
+		other.n_pos = __shfl_xor_sync(MC_FULL_MASK, mine.n_pos, o);
+		other.best_row = __shfl_xor_sync(MC_FULL_MASK, mine.best_row, o);
+		other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, mine.best_f0, o);
+		xmerge(mine, other);
+	}
+	if (lane == 0) s_part[wib] = mine;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		mc_scan_result r = s_part[0];
+		for (int w = 1; w < COMBINE_THREADS / 32; w++) xmerge(r, s_part[w]);
+		out[slot] = r;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+static void comm_release(mc_ctx *ctx) {
+	McComm &cm = ctx->comm;
+	for (int p = 0; p < MC_MAX_PEERS; p++) {
+		if (cm.ipc_opened[p] && cm.peer_inbox[p]) cudaIpcCloseMemHandle(cm.peer_inbox[p]);
+		cm.peer_inbox[p] = nullptr;
+		cm.ipc_opened[p] = false;
+	}
+	cudaFree(cm.inbox);
+	cudaFree(cm.d_out);
+	if (cm.h_out) { cudaFreeHost(cm.h_out); cudaEventDestroy(cm.done); }
+	cm = McComm();
+}
+
+void mc_comm_destroy(mc_ctx *ctx) {
+	if (ctx && ctx->comm.world) comm_release(ctx);
+}
+
+extern "C" int mc_comm_init(mc_ctx *ctx, int rank, int world, int64_t shard_lo, int64_t shard_hi, uint8_t *handle_out) {
+	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
+	MC_REQUIRE(world >= 1 && world <= MC_MAX_PEERS && rank >= 0 && rank < world, MC_ERR_ARG, "rank %d / world %d invalid (at most %d ranks)", rank, world, MC_MAX_PEERS);
+	MC_CUDA(cudaSetDevice(ctx->device));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (ctx->comm.world) comm_release(ctx);
+	McComm &cm = ctx->comm;
+	MC_CUDA(cudaMalloc(&cm.inbox, MC_INBOX_BYTES));
+	MC_CUDA(cudaMemset(cm.inbox, 0, MC_INBOX_BYTES));
+	MC_CUDA(cudaMalloc(&cm.d_out, (size_t)MC_XSLOTS * sizeof(mc_scan_result) + 64));
+	MC_CUDA(cudaMemset(cm.d_out, 0, (size_t)MC_XSLOTS * sizeof(mc_scan_result) + 64));
+	cm.world = world;
+	cm.rank = rank;
+	cm.shard_lo = shard_lo;
+	cm.shard_hi = shard_hi;
+	cm.peer_inbox[rank] = cm.inbox;
+	cm.connected = world == 1;
+	if (handle_out) {
+		static_assert(sizeof(cudaIpcMemHandle_t) <= MC_COMM_HANDLE_BYTES, "handle size");
+		cudaIpcMemHandle_t h;
+		memset(handle_out, 0, MC_COMM_HANDLE_BYTES);
+		MC_CUDA(cudaIpcGetMemHandle(&h, cm.inbox));
+		memcpy(handle_out, &h, sizeof(h));
+	}
+	return MC_OK;
+}
+
+extern "C" int mc_comm_set_shard(mc_ctx *ctx, int64_t shard_lo, int64_t shard_hi) {
+	MC_REQUIRE(ctx && ctx->comm.world, MC_ERR_STATE, "mc_comm_init has not been called");
+	ctx->comm.shard_lo = shard_lo;
+	ctx->comm.shard_hi = shard_hi;
+	return MC_OK;
+}
+
+extern "C" int mc_comm_connect(mc_ctx *ctx, const uint8_t *handles) {
+	MC_REQUIRE(ctx && handles, MC_ERR_ARG, "bad arguments");
+	McComm &cm = ctx->comm;
+	MC_REQUIRE(cm.world, MC_ERR_STATE, "mc_comm_init has not been called");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	for (int p = 0; p < cm.world; p++) {
+		if (p == cm.rank) continue;
+		cudaIpcMemHandle_t h;
+		memcpy(&h, handles + (size_t)p * MC_COMM_HANDLE_BYTES, sizeof(h));
+		void *ptr = nullptr;
+		MC_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+		cm.peer_inbox[p] = (uint8_t *)ptr;
+		cm.ipc_opened[p] = true;
+	}
+	cm.connected = true;
+	return MC_OK;
+}
+
+extern "C" int mc_comm_connect_local(mc_ctx *const *ctxs, int world) {
+	MC_REQUIRE(ctxs && world >= 1 && world <= MC_MAX_PEERS, MC_ERR_ARG, "bad arguments");
+	for (int r = 0; r < world; r++) {
+		MC_REQUIRE(ctxs[r] && ctxs[r]->comm.world == world && ctxs[r]->comm.rank == r, MC_ERR_STATE, "context %d: mc_comm_init(rank %d, world %d) first", r, r, world);
+	}
+	for (int r = 0; r < world; r++) {
+		MC_CUDA(cudaSetDevice(ctxs[r]->device));
+		for (int p = 0; p < world; p++) {
+			if (p == r) continue;
+			if (ctxs[p]->device != ctxs[r]->device) {
+				int can = 0;
+				MC_CUDA(cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[p]->device));
+				MC_REQUIRE(can, MC_ERR_UNSUPPORTED, "GPU %d cannot address GPU %d's memory (no NVLink / P2P)", ctxs[r]->device, ctxs[p]->device);
+				cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[p]->device, 0);
+				if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+				else MC_CUDA(e);
+			}
+			ctxs[r]->comm.peer_inbox[p] = ctxs[p]->comm.inbox;
+		}
+		ctxs[r]->comm.connected = true;
+	}
+	return MC_OK;
+}
+
+
+extern "C" int mc_scan_sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot) {
+	MC_REQUIRE(ctx && ctx->have_hist, MC_ERR_STATE, "mc_scan_sharded_enqueue: histograms are not built");
+	MC_REQUIRE(ctx->model.valid, MC_ERR_STATE, "mc_scan_sharded_enqueue: mc_set_model has not been called");
+	McComm &cm = ctx->comm;
+	MC_REQUIRE(cm.world && cm.connected, MC_ERR_STATE, "mc_scan_sharded_enqueue: mc_comm_init / mc_comm_connect first");
+	MC_REQUIRE(slot >= 0 && slot < MC_XSLOTS, MC_ERR_ARG, "slot %d out of range (0..%d)", slot, MC_XSLOTS - 1);
+	MC_REQUIRE(!cm.slot_pending[slot], MC_ERR_STATE, "slot %d still holds an exchange that was not collected", slot);
+	MC_REQUIRE(center_row >= 0 && center_row < ctx->n, MC_ERR_ARG, "center row out of range");
+	MC_REQUIRE(hi < lo || (lo >= 0 && hi < ctx->n), MC_ERR_ARG, "scan range [%lld,%lld] out of range", (long long)lo, (long long)hi);
+	int rc = mc_comm_scan_push(ctx, center_row, lo, hi, remove_marked, slot, 0);
+	if (rc) return rc;
+	cm.slot_pending[slot] = 1;
+	return MC_OK;
+}
+
+extern "C" int mc_scan_sharded_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo, const int64_t *hi,
+                                            const int64_t *shard_lo, const int64_t *shard_hi, int count, int remove_marked, int slot0) {
+	MC_REQUIRE(ctx && center_rows && lo && hi && count > 0, MC_ERR_ARG, "mc_scan_sharded_enqueue_many: bad arguments");
+	MC_REQUIRE((shard_lo == nullptr) == (shard_hi == nullptr), MC_ERR_ARG, "shard_lo and shard_hi go together");
+	for (int i = 0; i < count; i++) {
+		if (shard_lo) { ctx->comm.shard_lo = shard_lo[i]; ctx->comm.shard_hi = shard_hi[i]; }
+		const int rc = mc_scan_sharded_enqueue(ctx, center_rows[i], lo[i], hi[i], remove_marked, slot0 + i);
+		if (rc) return rc;
+	}
+	return MC_OK;
+}
+
+static unsigned long long slot_offset(unsigned int epoch, int slot) {
+	return ((unsigned long long)(epoch & 1u) * MC_XSLOTS + (unsigned long long)slot) * MC_MAX_PEERS * MC_SCAN_PARTS * MC_LL_RECORD_BYTES;
+}
+
+// internal: sharded scan of one slot on one rank (fence = 1 orders earlier peer stores, i.e. marks
+// written into another rank's array, before the record)
+int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence) {
+	McComm &cm = ctx->comm;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	if (!ctx->d_scan_slots) {
+		MC_CUDA(cudaMalloc(&ctx->d_scan_slots, (size_t)MC_SCAN_SLOTS * MC_SCAN_PARTS * sizeof(mc_scan_result)));
+		for (int i = 0; i < MC_SCAN_SLOTS; i++) ctx->slot_nparts[i] = 0;
+	}
+	int64_t l = lo > cm.shard_lo ? lo : cm.shard_lo, h = hi < cm.shard_hi ? hi : cm.shard_hi;
+	if (h < l) { l = 0; h = -1; }
+	unsigned int epoch = ++cm.slot_epoch[slot];
+	if (epoch == 0) epoch = cm.slot_epoch[slot] = 2;   // never 0 (the cleared inbox), parity kept
+	McPeerPush push{};
+	for (int p = 0; p < cm.world; p++) push.inbox[p] = (unsigned long long)cm.peer_inbox[p];
+	push.world = cm.world;
+	push.rank = cm.rank;
+	push.epoch = epoch;
+	push.fence = (unsigned int)fence;
+	push.slot_off = slot_offset(epoch, slot);
+	return mc_launch_scan_push(ctx, center_row, l, h, remove_marked,
+	                           (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result),
+	                           &ctx->slot_nparts[slot], &push);
+}
+
+// internal: fold one slot on the device; *rec_dev_out is the combined record, *err_dev_out the timeout flag
+int mc_comm_combine_dev(mc_ctx *ctx, int slot, const void **rec_dev_out, unsigned int **err_dev_out) {
+	McComm &cm = ctx->comm;
+	CombineArgs args;
+	memset(&args, 0, sizeof(args));
+	args.epoch[slot] = cm.slot_epoch[slot];
+	args.slot_off[slot] = slot_offset(cm.slot_epoch[slot], slot);
+	MC_CUDA(cudaSetDevice(ctx->device));
+	mc_scan_result *d_out = (mc_scan_result *)cm.d_out;
+	unsigned int *d_err = (unsigned int *)((uint8_t *)cm.d_out + (size_t)MC_XSLOTS * sizeof(mc_scan_result));
+	scan_combine_kernel<<<1, COMBINE_THREADS, 0, ctx->stream>>>(cm.inbox, cm.world, ctx->num_sms, args, slot, d_out, d_err);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	*rec_dev_out = d_out + slot;
+	*err_dev_out = d_err;
+	return MC_OK;
+}
+
+// the device half of a collect: fold on the device, results to pinned host memory, an event behind it
+extern "C" int mc_scan_sharded_combine(mc_ctx *ctx, int slot0, int nslots) {
+	MC_REQUIRE(ctx, MC_ERR_ARG, "bad arguments");
+	McComm &cm = ctx->comm;
+	MC_REQUIRE(cm.world && cm.connected, MC_ERR_STATE, "mc_scan_sharded_combine: mc_comm_init / mc_comm_connect first");
+	MC_REQUIRE(slot0 >= 0 && nslots > 0 && slot0 + nslots <= MC_XSLOTS, MC_ERR_ARG, "slot range invalid");
+	CombineArgs args;
+	memset(&args, 0, sizeof(args));
+	for (int s = slot0; s < slot0 + nslots; s++) {
+		MC_REQUIRE(cm.slot_pending[s] == 1, MC_ERR_STATE, "slot %d has no exchange in flight", s);
+		args.epoch[s] = cm.slot_epoch[s];
+		args.slot_off[s] = slot_offset(cm.slot_epoch[s], s);
+	}
+	MC_CUDA(cudaSetDevice(ctx->device));
+	if (!cm.h_out) {
+		MC_CUDA(cudaMallocHost(&cm.h_out, (size_t)MC_XSLOTS * sizeof(mc_scan_result) + 64));
+		MC_CUDA(cudaEventCreateWithFlags(&cm.done, cudaEventDisableTiming));
+	}
+	mc_scan_result *d_out = (mc_scan_result *)cm.d_out;
+	unsigned int *d_err = (unsigned int *)((uint8_t *)cm.d_out + (size_t)MC_XSLOTS * sizeof(mc_scan_result));
+	scan_combine_kernel<<<nslots, COMBINE_THREADS, 0, ctx->stream>>>(cm.inbox, cm.world, ctx->num_sms, args, slot0, d_out, d_err);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	mc_scan_result *h_out = (mc_scan_result *)cm.h_out;
+	MC_CUDA(cudaMemcpyAsync(h_out + slot0, d_out + slot0, (size_t)nslots * sizeof(mc_scan_result), cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(h_out + MC_XSLOTS, d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaEventRecord(cm.done, ctx->stream));
+	for (int s = slot0; s < slot0 + nslots; s++) cm.slot_pending[s] = 2;
+	return MC_OK;
+}
+
+// the host half: wait for the event of the last combine and hand the summaries out
+extern "C" int mc_scan_sharded_wait(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *res) {
+	MC_REQUIRE(ctx && res, MC_ERR_ARG, "bad arguments");
+	McComm &cm = ctx->comm;
+	MC_REQUIRE(slot0 >= 0 && nslots > 0 && slot0 + nslots <= MC_XSLOTS, MC_ERR_ARG, "slot range invalid");
+	for (int s = slot0; s < slot0 + nslots; s++) MC_REQUIRE(cm.slot_pending[s] == 2, MC_ERR_STATE, "slot %d was not combined", s);
+	MC_CUDA(cudaSetDevice(ctx->device));
+	MC_CUDA(cudaEventSynchronize(cm.done));
+	for (int s = slot0; s < slot0 + nslots; s++) cm.slot_pending[s] = 0;
+	const mc_scan_result *h_out = (const mc_scan_result *)cm.h_out;
+	if (*(const unsigned int *)(h_out + MC_XSLOTS)) {
+		unsigned int *d_err = (unsigned int *)((uint8_t *)cm.d_out + (size_t)MC_XSLOTS * sizeof(mc_scan_result));
+		MC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), ctx->stream));
+		mc_set_error("sharded scan: a peer's records did not arrive within %.0f s (rank %d of %d)", COMBINE_TIMEOUT_NS * 1e-9, cm.rank, cm.world);
+		return MC_ERR_CUDA;
+	}
+	memcpy(res, h_out + slot0, (size_t)nslots * sizeof(mc_scan_result));
+	return MC_OK;
+}
+
+extern "C" int mc_scan_sharded_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *res) {
+	const int rc = mc_scan_sharded_combine(ctx, slot0, nslots);
+	if (rc) return rc;
+	return mc_scan_sharded_wait(ctx, slot0, nslots, res);
+}

@@ -93,11 +93,18 @@ __device__ unsigned long long g_scan_trace[148 * 32 * 8];
 #define TRACE(slot) do {} while (0)
 #endif
 
-template <int TB, int RB>
+// PUSH = true is the sharded variant (multi-GPU): identical, plus the peer stores at the very end;
+// the single-GPU instantiation carries neither the extra arguments nor the branch
+template <bool PUSH>
+struct PushArg { McPeerPush v; };
+template <>
+struct PushArg<false> {};
+
+template <int TB, int RB, bool PUSH>
 __global__ void __launch_bounds__(32 * (1 + TileCfg<RB>::NCW), 1)
 scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, uint8_t *__restrict__ marks,
                 long long lo, long long hi, long long center_row, McModel model, int remove_marked,
-                ScanPartial *__restrict__ partials, McPeerPush push) {
+                ScanPartial *__restrict__ partials, PushArg<PUSH> push_arg) {
 	using C = RowCfg<RB>;
 	using T = TileCfg<RB>;
 	constexpr int NB = RB / TB;
@@ -252,7 +259,8 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			tscan_merge(b, other);
 		}
 		if (lane == 0) partials[blockIdx.x] = b;
-		if (push.world > 0) {
+		if constexpr (PUSH) {
+			const McPeerPush &push = push_arg.v;
 			// sharded scan: this CTA's partial goes straight into every rank's inbox over NVLink, one
 			// 8-byte {data, epoch} store per word; lane = 8 * (peer mod 4) + word
 			if (push.fence) __threadfence_system();
@@ -314,24 +322,26 @@ int mc_launch_scan_fold(mc_ctx *ctx, const void *slots_dev, const int *nparts_de
 int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                           void *partials_dev, int *nparts_out);
 
-template <int TB, int RB>
-static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                      void *partials_dev, int *nparts_out, const McPeerPush *push) {
+template <int TB, int RB, bool PUSH>
+static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                           void *partials_dev, int *nparts_out, const McPeerPush *push) {
 	using T = TileCfg<RB>;
 	const size_t smem = (size_t)T::NS * T::STAGE_BYTES;
 	static bool attr_set = false;
 	if (!attr_set) {
-		MC_CUDA(cudaFuncSetAttribute(scan_tma_kernel<TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		MC_CUDA(cudaFuncSetAttribute(scan_tma_kernel<TB, RB, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
 	const int64_t ntiles = (hi - lo + 1 + T::RT - 1) / T::RT;
 	int64_t blocks = ctx->num_sms;
 	if (blocks > ntiles) blocks = ntiles;
 	if (blocks < 1) blocks = 1;
-	McPeerPush pp{};
-	if (push) {   // sharded: every rank always sends num_sms records, so a reader knows how many to expect
-		pp = *push;
+	PushArg<PUSH> pa{};
+	uint8_t *marks = ctx->d_marks;
+	if constexpr (PUSH) {   // sharded: every rank always sends num_sms records, so a reader knows how many to expect
+		pa.v = *push;
 		blocks = ctx->num_sms;
+		if (ctx->comm.marks_target) marks = ctx->comm.marks_target;   // marks go to the rank that compacts them
 	}
 	static const bool no_pdl = getenv("MC_NO_PDL") != nullptr;
 	cudaLaunchConfig_t cfg{};
@@ -344,13 +354,20 @@ static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, i
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = no_pdl ? 0 : 1;
-	MC_CUDA(cudaLaunchKernelEx(&cfg, scan_tma_kernel<TB, RB>, (const uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_marks,
+	MC_CUDA(cudaLaunchKernelEx(&cfg, scan_tma_kernel<TB, RB, PUSH>, (const uint8_t *)ctx->d_hist, ctx->d_aux, marks,
 	                           (long long)lo, (long long)hi, (long long)center_row, ctx->model, remove_marked,
-	                           (ScanPartial *)partials_dev, pp));
+	                           (ScanPartial *)partials_dev, pa));
 	*nparts_out = (int)blocks;
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
+}
+
+template <int TB, int RB>
+static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                      void *partials_dev, int *nparts_out, const McPeerPush *push) {
+	if (push) return launch_tma_impl<TB, RB, true>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+	return launch_tma_impl<TB, RB, false>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, nullptr);
 }
 
 // partials_dev must hold MC_SCAN_PARTS entries of 32 bytes; *nparts_out says how many were written

@@ -70,7 +70,8 @@ struct Model {
 };
 
 struct Ctx {
-	mc_ctx *gpu = nullptr;
+	mc_ctx *gpu = nullptr;            // rank 0: holds the sequences, runs training, Phase B and the Phase-A tail
+	std::vector<mc_ctx *> ranks;      // all GPUs that share the Phase-A scans (ranks[0] == gpu)
 	Options opt;
 	Dataset ds;
 	Model model;
@@ -516,10 +517,24 @@ void mean_shift(Ctx &c, BVec &bv) {
 	AlignCache cache;
 	std::vector<uint8_t> alive;   // host mirror, only needed by the --align scans
 	if (c.model.align) alive.assign((size_t)ds.n, 1);
-	GPU(mc_alive_reset(c.gpu));
+	const int world = (int)c.ranks.size();
+	if (world > 1 && !c.model.align) {
+		// rows are replicated once (device-to-device), scan work and alive flags are sharded
+		// in contiguous row blocks; summaries and marks cross GPUs inside the scan kernel
+		Timer ts;
+		for (int r = 1; r < world; r++) GPU(mc_clone_points(c.ranks[r], c.gpu));
+		for (int r = 0; r < world; r++) {
+			const int64_t lo = ds.n * r / world, hi = ds.n * (r + 1) / world - 1;
+			GPU(mc_comm_init(c.ranks[r], r, world, lo, hi, nullptr));
+		}
+		GPU(mc_comm_connect_local(c.ranks.data(), world));
+		printf("  [points replicated to %d GPUs, peer inboxes connected %.2fs]\n", world, ts.lap());
+	}
+	const bool sharded = world > 1 && !c.model.align;
+	for (int r = 0; r < (sharded ? world : 1); r++) GPU(mc_alive_reset(c.ranks[r]));
 
 	auto kill_row = [&](int64_t row) {
-		GPU(mc_alive_kill(c.gpu, &row, 1));
+		for (int r = 0; r < (sharded ? world : 1); r++) GPU(mc_alive_kill(c.ranks[r], &row, 1));
 		if (c.model.align) alive[row] = 0;
 	};
 
@@ -552,7 +567,8 @@ void mean_shift(Ctx &c, BVec &bv) {
 				// get_close + remove_available + get_mean in one submission: the marked rows come back as
 				// a list, `current` and its running bin sums stay in HBM
 				mc_step_result sr;
-				GPU(mc_accumulate_step(c.gpu, last, lo, hi, first_mean ? 1 : 0, &sr, marked_rows.data(), (int64_t)marked_rows.size()));
+				if (sharded) GPU(mc_accumulate_step_sharded(c.ranks.data(), world, last, lo, hi, first_mean ? 1 : 0, &sr, marked_rows.data(), (int64_t)marked_rows.size()));
+				else GPU(mc_accumulate_step(c.gpu, last, lo, hi, first_mean ? 1 : 0, &sr, marked_rows.data(), (int64_t)marked_rows.size()));
 				res = sr.scan;
 				nearest = sr.nearest_row;
 			}
@@ -688,10 +704,16 @@ int run_pipeline(Options opt) {
 	int ctx_rc = MC_OK;
 	std::string ctx_err;
 	double ctx_s = 0;
+	c.ranks.assign((size_t)std::max(1, opt.gpus), nullptr);
 	std::thread ctx_thread([&]() {
 		Timer t;
-		ctx_rc = mc_ctx_create(&c.gpu, opt.device);
-		if (ctx_rc != MC_OK) ctx_err = mc_last_error();
+		const int ndev = std::max(1, mc_device_count());
+		for (size_t r = 0; r < c.ranks.size() && ctx_rc == MC_OK; r++) {
+			// rank r sits on the r-th GPU after --device; with fewer GPUs than ranks they share devices
+			ctx_rc = mc_ctx_create(&c.ranks[r], (opt.device + (int)r) % ndev);
+			if (ctx_rc != MC_OK) ctx_err = mc_last_error();
+		}
+		c.gpu = c.ranks[0];
 		ctx_s = t.lap();
 	});
 	struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{ctx_thread};
@@ -815,7 +837,7 @@ int run_pipeline(Options opt) {
 	}
 	mean_shift(c, bv);
 	printf("Total %.2fs\n", total.lap());
-	if (getenv("MC_CLEAN_EXIT")) { mc_ctx_destroy(c.gpu); return 0; }
+	if (getenv("MC_CLEAN_EXIT")) { for (mc_ctx *g : c.ranks) mc_ctx_destroy(g); return 0; }
 	// the output file is closed: skip the teardown of the CUDA context and of GBs of host vectors
 	fflush(stdout);
 	fflush(stderr);
@@ -877,6 +899,10 @@ Options parse_options(int argc, char **argv) {
 		} else if ((arg == "-d" || arg == "--delta") && more) o.delta = (int)need_long(i, "Delta", true);
 		else if ((arg == "-i" || arg == "--iter" || arg == "--iterations") && more) o.iterations = (int)need_long(i, "Iterations", false);
 		else if (arg == "--device" && more) o.device = atoi(argv[++i]);          // extension: GPU ordinal
+		else if (arg == "--gpus" && more) {                                      // extension: GPUs sharing the scans
+			o.gpus = atoi(argv[++i]);
+			if (o.gpus < 1 || o.gpus > 8) { fprintf(stderr, "--gpus must be between 1 and 8\n"); exit(EXIT_FAILURE); }
+		}
 		else if (arg == "--dump-model" && more) o.dump_model = argv[++i];        // extension: test hook
 		else {
 			struct stat st;

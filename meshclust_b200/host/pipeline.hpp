@@ -18,6 +18,7 @@ struct Options {
 	int pivots = 20;
 	int threads = 0;
 	int device = 0;
+	int gpus = 1;          // extension: GPUs that share the Phase-A scans
 	std::vector<std::string> files;
 	std::string output = "output.clstr";
 	std::string dump_model;   // test hook: write the trained bounds/weights/sample sizes as text

@@ -373,6 +373,135 @@ def test_accumulate_step_vs_unfused_and_oracle(ctx, oracle, dtype, hi, k, n):
     assert r.scan.as_tuple() == (0, 0, -1, -1.0) and r.nearest_row == -1 and r.n_members == 1 and rows.size == 0
 
 
+@pytest.mark.parametrize("world,k,n", [(2, 4, 5000), (3, 3, 4001), (4, 5, 3000)])
+def test_sharded_scan_equals_single(ctx, world, k, n):
+    """`world` ranks (here: contexts on one GPU, wired like ranks of one process) each scan
+    their shard and exchange CTA partials through peer inboxes; every rank must end up with exactly
+    the summary a single context computes over the whole range, scan after scan, with removal."""
+    from meshclust_b200 import api, sharding
+    rng = np.random.default_rng(500 + world)
+    nb = 4 ** k
+    H = _rand_hists(rng, n, nb, clusters=5)
+    H[n // 2 + 3] = H[7]            # an exact tie on f0 across two shards: the smaller row must win
+    lens = (1000 + rng.integers(0, 30, n)).astype(np.uint64)
+    lens[n // 2 + 3] = lens[7]
+    mins, maxs, w = _model(3)
+    maxs[2] = 4.0 * nb
+    ctx.load_histograms(H, lens, k)
+    ctx.set_model(mins, maxs, w, 3)
+    ranks = []
+    try:
+        for r in range(world):
+            c = api.Context(0)
+            c.load_histograms(H, lens, k)
+            c.set_model(mins, maxs, w, 3)
+            lo, hi = sharding.shard_bounds(n, world, r)
+            c.comm_init(r, world, lo, hi - 1)
+            ranks.append(c)
+        api.Context.comm_connect_local(ranks)
+        ctx.alive_reset()
+        for c in ranks:
+            c.alive_reset()
+        centers = [7, n // 2 + 3, n - 1, 0, n // 3]
+        for it, center in enumerate(centers):
+            lo, hi = (0, n - 1) if it % 2 == 0 else (11, n - 13)
+            want, _ = ctx.scan(center, lo, hi)
+            for slot_base in (0,):
+                for c in ranks:      # all ranks enqueue before anyone waits (one host thread drives them)
+                    c.scan_sharded_enqueue(center, lo, hi, True, slot_base + it % 5)
+                for c in ranks:
+                    got = c.scan_sharded_collect(slot_base + it % 5, 1)[0]
+                    assert got == want.as_tuple(), (it, got, want.as_tuple())
+        # several scans in flight, no removal, collected together
+        want = []
+        for i, center in enumerate(centers):
+            ctx.scan_enqueue(center, 0, n - 1, False, i)
+        want = ctx.scan_collect(0, len(centers))
+        for c in ranks:
+            for i, center in enumerate(centers):
+                c.scan_sharded_enqueue(center, 0, n - 1, False, 10 + i)
+        for c in ranks:
+            assert c.scan_sharded_collect(10, len(centers)) == want
+        # a range that misses some shards entirely
+        w1, _ = ctx.scan(3, 0, n // (2 * world))
+        for c in ranks:
+            c.scan_sharded_enqueue(3, 0, n // (2 * world), True, 63)
+        for c in ranks:
+            assert c.scan_sharded_collect(63, 1)[0] == w1.as_tuple()
+        # protocol errors are reported, not hung on
+        ranks[0].scan_sharded_enqueue(3, 0, 10, False, 5)
+        with pytest.raises(api.McError):
+            ranks[0].scan_sharded_enqueue(3, 0, 10, False, 5)
+        for c in ranks[1:]:
+            c.scan_sharded_enqueue(3, 0, 10, False, 5)
+        for c in ranks:
+            c.scan_sharded_collect(5, 1)
+    finally:
+        for c in ranks:
+            c.close()
+
+
+@pytest.mark.parametrize("world,k,n", [(2, 4, 4000), (3, 5, 2500)])
+def test_accumulate_step_sharded_equals_single(ctx, world, k, n):
+    """the sharded Phase-A step (ranks scan their shard, marks land in rank 0's array over peer
+    memory, rank 0 folds the inboxes and runs the tail) against mc_accumulate_step on one context"""
+    from meshclust_b200 import api
+    rng = np.random.default_rng(700 + world)
+    nb = 4 ** k
+    H = _rand_hists(rng, n, nb, clusters=6)
+    lens = (1000 + rng.integers(0, 40, n)).astype(np.uint64)
+    mins, maxs, w = _model(3)
+    maxs[2] = 4.0 * nb
+    ctx.load_histograms(H, lens, k)
+    ctx.set_model(mins, maxs, w, 3)
+    s0 = ctx.pair_classify(np.arange(n, dtype=np.int32), np.zeros(n, np.int32))[0]
+    w = w.copy()
+    w[0] -= np.sort(s0)[int(0.9 * n)]
+    ctx.set_model(mins, maxs, w, 3)
+    ranks = []
+    try:
+        for r in range(world):
+            c = api.Context(0)
+            if r == 0:
+                c.load_histograms(H, lens, k)
+                c.set_model(mins, maxs, w, 3)
+            else:
+                c.clone_points_from(ranks[0])
+            c.comm_init(r, world, n * r // world, n * (r + 1) // world - 1)
+            ranks.append(c)
+        api.Context.comm_connect_local(ranks)
+        ctx.alive_reset()
+        for c in ranks:
+            c.alive_reset()
+        seed, steps, marked_total = 1, 0, 0
+        for cluster in range(5):
+            kill = np.array([seed])
+            ctx.alive_kill(kill)
+            for c in ranks:
+                c.alive_kill(kill)
+            last, restart = seed, True
+            while True:
+                lo, hi = (0, n - 1) if steps % 2 == 0 else (9, n - 10)
+                want, wrows = ctx.accumulate_step(last, lo, hi, restart)
+                got, grows = api.Context.accumulate_step_sharded(ranks, last, lo, hi, restart)
+                assert got.scan.as_tuple() == want.scan.as_tuple(), (cluster, steps)
+                assert got.nearest_row == want.nearest_row and got.n_members == want.n_members
+                assert np.array_equal(grows, wrows)
+                restart = False
+                steps += 1
+                marked_total += wrows.size
+                if want.scan.n_pos == 0 or steps > 40:
+                    break
+                last = want.nearest_row
+            if want.scan.best_row < 0:
+                break
+            seed = int(want.scan.best_row)
+        assert steps >= 6 and marked_total > 50
+    finally:
+        for c in ranks:
+            c.close()
+
+
 @pytest.mark.parametrize("k", [3, 4, 5])
 def test_update_centers_vs_oracle(ctx, oracle, k):
     rng = np.random.default_rng(80 + k)

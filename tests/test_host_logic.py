@@ -65,3 +65,15 @@ def test_clstr_identical_to_reference_gpu(built_lib, tmp_path, name):
     assert cli and os.path.exists(cli)
     got, log = _run(cli, name, tmp_path)
     assert got == H.read_golden(name), log[-1500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,gpus", [("B", 2), ("c1_full", 3), ("F", 2)])
+def test_clstr_identical_with_sharded_phase_a(built_lib, tmp_path, name, gpus):
+    # --gpus N shares the Phase-A scans between N contexts (on a 1-GPU box they share the device):
+    # the CLSTR file must not change
+    from meshclust_b200 import build
+    cli = build.build_cli()
+    got, log = _run(cli, name, tmp_path, extra=("--gpus", str(gpus)))
+    assert "peer inboxes connected" in log
+    assert got == H.read_golden(name), log[-1500:]

@@ -12,3 +12,12 @@ def test_bvec_selfcheck(tmp_path):
     subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "units", "bvec_selfcheck.cpp"), "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def test_fasta_parallel_parser_selfcheck(tmp_path):
+    # the multi-threaded FASTA parser == the serial one (ChromListMaker.cpp:92-120 semantics) on regular
+    # files; CRLF files, headers without sequence and other irregular inputs fall back to the serial path
+    exe = os.path.join(str(tmp_path), "fasta_selfcheck")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", os.path.join(ROOT, "tests", "units", "fasta_selfcheck.cpp"), "-o", exe])
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env={**os.environ, "OMP_NUM_THREADS": "7"})
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
