@@ -154,24 +154,24 @@ int mc_set_stream(mc_ctx *ctx, void *stream);
 
 /* ---- multi-GPU: sharded scans ------------------------------------ */
 
-/* `world` contexts, one per GPU (in one process or one process each), hold the same rows; rank r
- * evaluates only the rows of its shard [shard_lo, shard_hi] and owns their alive flags.  What the
- * reference reduces with OpenMP at the end of Trainer::get_close (Trainer.cpp:38-48,81: arg-max,
- * positives) crosses GPUs inside the scan kernel: every CTA stores its partial into all ranks'
- * inboxes over NVLink peer memory, and the collect call folds world x SMs records on the device.
+/* `world` contexts, one per GPU (in one process or one process each), hold the same rows; the
+ * scan work and the alive flags are sharded in tiles: tile t (rows [t*T, (t+1)*T), T = 32 rows for
+ * rows up to 1 KB) belongs to rank t mod world, so any length window spreads over all GPUs and
+ * the owner of a row never changes.  What the reference reduces with OpenMP at the end of
+ * Trainer::get_close (Trainer.cpp:38-48,81: arg-max, positives) crosses GPUs inside the scan
+ * kernel: every CTA stores its partial into all ranks' inboxes over NVLink peer memory, and the
+ * collect call folds world x SMs records on the device.
  *
  * mc_comm_init allocates this rank's inbox and writes its CUDA IPC handle to handle_out
  * (MC_COMM_HANDLE_BYTES, may be NULL for same-process use); mc_comm_connect takes the handles of
  * all ranks in rank order (exchanged by the caller, e.g. torch.distributed.all_gather_object);
  * mc_comm_connect_local wires contexts that live in one process.  At most 8 ranks. */
 #define MC_COMM_HANDLE_BYTES 64
-int mc_comm_init(mc_ctx *ctx, int rank, int world, int64_t shard_lo, int64_t shard_hi,
-                 uint8_t *handle_out);
-int mc_comm_set_shard(mc_ctx *ctx, int64_t shard_lo, int64_t shard_hi);
+int mc_comm_init(mc_ctx *ctx, int rank, int world, uint8_t *handle_out);
 int mc_comm_connect(mc_ctx *ctx, const uint8_t *handles);
 int mc_comm_connect_local(mc_ctx *const *ctxs, int world);
 
-/* get_close over the part of [lo,hi] inside this rank's shard, summary exchanged with all ranks.
+/* get_close over this rank's tiles of [lo,hi], summary exchanged with all ranks.
  * Every rank must issue the same sequence of enqueue / collect calls (same center, range, slot);
  * a slot (0 <= slot < MC_XSLOTS) must be collected before it is enqueued again.  Collect returns
  * the same global summaries on every rank (rows are global row numbers); it fails with
@@ -179,16 +179,19 @@ int mc_comm_connect_local(mc_ctx *const *ctxs, int world);
 #define MC_XSLOTS 64
 int mc_scan_sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi,
                             int remove_marked, int slot);
-/* count scans back to back into slots slot0..; shard_lo/shard_hi (both or neither) give the rows
- * this rank evaluates per scan, e.g. when consecutive scans address different copies of the points */
+/* count scans back to back into slots slot0.. */
 int mc_scan_sharded_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo,
-                                 const int64_t *hi, const int64_t *shard_lo, const int64_t *shard_hi,
-                                 int count, int remove_marked, int slot0);
+                                 const int64_t *hi, int count, int remove_marked, int slot0);
 int mc_scan_sharded_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *res);
 /* collect = combine (device fold + copy to pinned host memory, asynchronous) + wait (host).  Callers
  * that keep the GPU busy enqueue the next scans between the two. */
 int mc_scan_sharded_combine(mc_ctx *ctx, int slot0, int nslots);
 int mc_scan_sharded_wait(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *res);
+/* combine(previous burst) + enqueue_many(this burst) + wait(previous burst) in one call; either
+ * count may be 0 */
+int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo,
+                          const int64_t *hi, int count, int remove_marked, int slot0, int prev_slot0,
+                          int prev_count, mc_scan_result *prev_res);
 
 /* ---- stage 3: mean-shift centers --------------------------------------------------------- */
 
@@ -223,7 +226,7 @@ int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, 
 int mc_clone_points(mc_ctx *dst, mc_ctx *src);
 
 /* mc_accumulate_step across `world` contexts of one process wired with mc_comm_connect_local:
- * rank r evaluates the rows of its shard (mc_comm_init) and owns their alive flags, the marks of
+ * rank r evaluates its tiles of the range and owns their alive flags, the marks of
  * all ranks land in rank 0's array over peer memory, rank 0 waits for every rank's summaries on the
  * device and runs the tail (compaction, running sums, get_mean).  Same results, same arguments. */
 int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_t center_row, int64_t lo,

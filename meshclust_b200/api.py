@@ -31,8 +31,8 @@ EXPORTS = [
     "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_copy_digits",
     "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
     "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
-    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_comm_init", "mc_comm_set_shard", "mc_comm_connect", "mc_comm_connect_local",
-    "mc_scan_sharded_enqueue", "mc_scan_sharded_enqueue_many", "mc_scan_sharded_collect", "mc_scan_sharded_combine", "mc_scan_sharded_wait", "mc_clone_points", "mc_accumulate_step_sharded", "mc_update_centers", "mc_align_pairs",
+    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_comm_init", "mc_comm_connect", "mc_comm_connect_local",
+    "mc_scan_sharded_enqueue", "mc_scan_sharded_enqueue_many", "mc_scan_sharded_collect", "mc_scan_sharded_combine", "mc_scan_sharded_wait", "mc_scan_sharded_burst", "mc_clone_points", "mc_accumulate_step_sharded", "mc_update_centers", "mc_align_pairs",
     "mc_kmer_histograms_host", "mc_scan_host",
 ]
 
@@ -251,10 +251,10 @@ class Context:
         return [r.as_tuple() for r in res]
 
     # -- multi-GPU: sharded scans ---------------------------------------------------------
-    def comm_init(self, rank: int, world: int, shard_lo: int, shard_hi: int) -> bytes:
+    def comm_init(self, rank: int, world: int) -> bytes:
         """allocate this rank's inbox; returns its CUDA IPC handle (64 bytes) for the other ranks"""
         h = (C.c_uint8 * 64)()
-        _check(_lib.mc_comm_init(self._h, C.c_int(rank), C.c_int(world), C.c_int64(shard_lo), C.c_int64(shard_hi), h))
+        _check(_lib.mc_comm_init(self._h, C.c_int(rank), C.c_int(world), h))
         return bytes(h)
 
     def comm_connect(self, handles):
@@ -272,19 +272,25 @@ class Context:
         _check(_lib.mc_scan_sharded_enqueue(self._h, C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi),
                                             C.c_int(1 if remove_marked else 0), C.c_int(slot)))
 
-    def scan_sharded_enqueue_many(self, center_rows, lo, hi, shard_lo, shard_hi, remove_marked: bool, slot0: int = 0):
+    def scan_sharded_enqueue_many(self, center_rows, lo, hi, remove_marked: bool, slot0: int = 0):
         cr = np.ascontiguousarray(center_rows, np.int64)
         lo = np.ascontiguousarray(lo, np.int64)
         hi = np.ascontiguousarray(hi, np.int64)
-        sl = None if shard_lo is None else np.ascontiguousarray(shard_lo, np.int64)
-        sh = None if shard_hi is None else np.ascontiguousarray(shard_hi, np.int64)
-        _check(_lib.mc_scan_sharded_enqueue_many(self._h, _p(cr), _p(lo), _p(hi), _p(sl), _p(sh), C.c_int(cr.size),
+        _check(_lib.mc_scan_sharded_enqueue_many(self._h, _p(cr), _p(lo), _p(hi), C.c_int(cr.size),
                                                  C.c_int(1 if remove_marked else 0), C.c_int(slot0)))
 
     def scan_sharded_collect(self, slot0: int, nslots: int):
         res = (ScanResult * nslots)()
         _check(_lib.mc_scan_sharded_collect(self._h, C.c_int(slot0), C.c_int(nslots), C.byref(res)))
         return [r.as_tuple() for r in res]
+
+    def scan_sharded_burst(self, cr, lo, hi, remove_marked: bool, slot0: int, prev_slot0: int, prev_count: int):
+        """arrays must already be contiguous int64 (this is the per-step call of a streaming caller)"""
+        res = (ScanResult * max(prev_count, 1))()
+        _check(_lib.mc_scan_sharded_burst(self._h, _p(cr), _p(lo), _p(hi), C.c_int(cr.size),
+                                          C.c_int(1 if remove_marked else 0), C.c_int(slot0), C.c_int(prev_slot0),
+                                          C.c_int(prev_count), C.byref(res)))
+        return [res[i].as_tuple() for i in range(prev_count)]
 
     def scan_sharded_combine(self, slot0: int, nslots: int):
         _check(_lib.mc_scan_sharded_combine(self._h, C.c_int(slot0), C.c_int(nslots)))
@@ -306,9 +312,6 @@ class Context:
         _check(_lib.mc_accumulate_step_sharded(arr, C.c_int(len(contexts)), C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi),
                                                C.c_int(1 if restart else 0), C.byref(res), _p(rows), C.c_int64(rows.size)))
         return res, rows[: res.scan.n_pos].copy()
-
-    def comm_set_shard(self, shard_lo: int, shard_hi: int):
-        _check(_lib.mc_comm_set_shard(self._h, C.c_int64(shard_lo), C.c_int64(shard_hi)))
 
     # -- stage 3 --------------------------------------------------------------------------
     def mean_nearest(self, rows, append: bool = False):

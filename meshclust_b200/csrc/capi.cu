@@ -165,6 +165,7 @@ extern "C" int64_t mc_launch_count(mc_ctx *ctx) { return ctx ? ctx->launches : 0
 
 extern "C" int mc_set_stream(mc_ctx *ctx, void *stream) {
 	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
+	MC_CUDA(cudaSetDevice(ctx->device));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
 	return MC_OK;
@@ -172,6 +173,7 @@ extern "C" int mc_set_stream(mc_ctx *ctx, void *stream) {
 
 extern "C" int mc_sync(mc_ctx *ctx) {
 	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
+	MC_CUDA(cudaSetDevice(ctx->device));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	return MC_OK;
 }
@@ -255,6 +257,7 @@ extern "C" int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int6
 extern "C" int mc_copy_digits(mc_ctx *ctx, uint8_t *out) {
 	MC_REQUIRE(ctx && out, MC_ERR_ARG, "bad arguments");
 	MC_REQUIRE(ctx->have_seq, MC_ERR_STATE, "no sequences loaded");
+	MC_CUDA(cudaSetDevice(ctx->device));
 	MC_CUDA(cudaMemcpyAsync(out, ctx->d_seq, (size_t)ctx->total_bases, cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	return MC_OK;
@@ -409,7 +412,13 @@ extern "C" int mc_set_model(mc_ctx *ctx, const double *mins, const double *maxs,
 	return MC_OK;
 }
 
-#define MC_NEED_HIST(ctx) MC_REQUIRE((ctx) && (ctx)->have_hist, MC_ERR_STATE, "%s: histograms are not built", __func__)
+// every entry point makes its context's GPU current first: contexts of several GPUs may be driven
+// from one host thread (cudaSetDevice is a no-op when the device is already current)
+#define MC_NEED_HIST(ctx)                                                                             \
+	do {                                                                                              \
+		MC_REQUIRE((ctx) && (ctx)->have_hist, MC_ERR_STATE, "%s: histograms are not built", __func__); \
+		MC_CUDA(cudaSetDevice((ctx)->device));                                                        \
+	} while (0)
 #define MC_NEED_MODEL(ctx) MC_REQUIRE((ctx)->model.valid, MC_ERR_STATE, "%s: mc_set_model has not been called", __func__)
 
 static int check_rows32(mc_ctx *ctx, const int32_t *r, int64_t m) {
@@ -579,6 +588,7 @@ extern "C" int mc_scan_fold_dev(mc_ctx *ctx, int slot0, int nslots, mc_scan_resu
 	MC_REQUIRE(ctx && out_dev, MC_ERR_ARG, "bad arguments");
 	MC_REQUIRE(slot0 >= 0 && nslots > 0 && slot0 + nslots <= MC_SCAN_SLOTS, MC_ERR_ARG, "slot range invalid");
 	MC_REQUIRE(ctx->d_scan_slots, MC_ERR_STATE, "nothing was enqueued");
+	MC_CUDA(cudaSetDevice(ctx->device));
 	int rc = mc_ensure_scratch(ctx, (size_t)MC_SCAN_SLOTS * sizeof(int) + 256);
 	if (rc) return rc;
 	int *d_np = (int *)ctx->d_scratch;
@@ -600,6 +610,7 @@ extern "C" int mc_scan_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_resul
 	MC_REQUIRE(ctx && res, MC_ERR_ARG, "bad arguments");
 	MC_REQUIRE(slot0 >= 0 && nslots > 0 && slot0 + nslots <= MC_SCAN_SLOTS, MC_ERR_ARG, "slot range invalid");
 	MC_REQUIRE(ctx->d_scan_slots, MC_ERR_STATE, "nothing was enqueued");
+	MC_CUDA(cudaSetDevice(ctx->device));
 	const size_t slot_bytes = (size_t)MC_SCAN_PARTS * sizeof(mc_scan_result);
 	int rc = mc_ensure_pinned(ctx, (size_t)nslots * slot_bytes);
 	if (rc) return rc;
@@ -712,7 +723,7 @@ extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, i
 	return MC_OK;
 }
 
-int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence);
+int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence, int mode);
 int mc_comm_combine_dev(mc_ctx *ctx, int slot, const void **rec_dev_out, unsigned int **err_dev_out);
 
 extern "C" int mc_clone_points(mc_ctx *dst, mc_ctx *src) {
@@ -756,14 +767,26 @@ extern "C" int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_
 	if (rc) return rc;
 	rc = ensure_step_buffers(root);
 	if (rc) return rc;
-	// every rank scans its shard; marks land in rank 0's array, summaries in every inbox (the
+	// every rank scans its tiles; marks land in rank 0's array, summaries in every inbox (the
 	// system-scope fence in the kernel orders a CTA's marks before its record)
+	static const bool dbg = getenv("MC_DEBUG_TIMING") != nullptr;
+	static double t_launch = 0, t_scans = 0, t_tail = 0;
+	static long n_steps = 0;
+	auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+	const double ta = dbg ? now() : 0;
 	for (int r = world - 1; r >= 0; r--) {
 		mc_ctx *c = ctxs[r];
 		c->comm.marks_target = r == 0 ? nullptr : root->d_marks;
-		rc = mc_comm_scan_push(c, center_row, lo, hi, 1, 0, 1);
+		rc = mc_comm_scan_push(c, center_row, lo, hi, 1, 0, 1, 1);
 		c->comm.marks_target = nullptr;
 		if (rc) return rc;
+	}
+	double tb = 0, tc = 0;
+	if (dbg) {   // phase times (serialising): launches, all scans finished, tail finished
+		tb = now();
+		for (int r = 0; r < world; r++) { cudaSetDevice(ctxs[r]->device); cudaStreamSynchronize(ctxs[r]->stream); }
+		tc = now();
+		cudaSetDevice(root->device);
 	}
 	const void *rec = nullptr;
 	unsigned int *d_err = nullptr;
@@ -775,6 +798,12 @@ extern "C" int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_
 	unsigned int *h_err = reinterpret_cast<unsigned int *>((uint8_t *)root->h_step + 56);
 	MC_CUDA(cudaMemcpyAsync(h_err, d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, root->stream));
 	MC_CUDA(cudaStreamSynchronize(root->stream));
+	if (dbg) {
+		t_launch += tb - ta; t_scans += tc - tb; t_tail += now() - tc;
+		if (++n_steps % 500 == 0)
+			fprintf(stderr, "[mc_accumulate_step_sharded x%d] %ld steps: launches %.1f us, scans done +%.1f us, combine+tail+sync +%.1f us (averages)\n",
+			        world, n_steps, t_launch / n_steps * 1e6, t_scans / n_steps * 1e6, t_tail / n_steps * 1e6);
+	}
 	if (*h_err) {
 		MC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), root->stream));
 		mc_set_error("sharded step: a rank's records did not arrive (world %d)", world);

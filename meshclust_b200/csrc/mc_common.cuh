@@ -85,21 +85,27 @@ struct McPeerPush {                            // by-value argument of the scan 
 	unsigned int epoch;                        // flag value of this exchange, never 0
 	unsigned int fence;                        // 1: make earlier peer stores (marks) visible before the record
 	unsigned long long slot_off;               // byte offset of (parity, slot) inside an inbox
+	// host-side only (launcher): deferred = 1 selects the variant that sends prev_partials (the CTA
+	// partials of the previous sharded scan, described by the fields above) at the start of the kernel
+	int deferred;
+	const void *prev_partials;
 };
 
 struct McComm {
 	int world = 0, rank = 0;
-	int64_t shard_lo = 0, shard_hi = -1;       // rows this rank evaluates (inclusive)
 	uint8_t *inbox = nullptr;                  // this rank's inbox (cudaMalloc, IPC-exportable)
 	uint8_t *peer_inbox[MC_MAX_PEERS] = {};
 	bool ipc_opened[MC_MAX_PEERS] = {};
 	bool connected = false;
 	unsigned int slot_epoch[MC_XSLOTS] = {};
-	unsigned char slot_pending[MC_XSLOTS] = {};   // 0 free, 1 scan enqueued, 2 combine enqueued
+	unsigned char slot_pending[MC_XSLOTS] = {};   // 0 free, 1 scan enqueued, 2 combine enqueued, 3 burst scan enqueued (one folded record per rank)
 	void *d_out = nullptr;                     // MC_XSLOTS combined records + error word
 	void *h_out = nullptr;                     // pinned host copy of d_out
 	cudaEvent_t done = nullptr;                // recorded behind the last combine
 	uint8_t *marks_target = nullptr;           // sharded Phase A: the marks array of the rank that runs the tail
+	cudaStream_t xstream = nullptr;            // exchange stream of the burst path (fold + send + combine)
+	cudaEvent_t scans_done = nullptr;          // recorded on the scan stream behind a burst
+	McPeerPush pending{};                      // deferred push: the last sharded scan whose partials have not left yet (epoch != 0)
 };
 
 // ---------------------------------------------------------------------------------------------

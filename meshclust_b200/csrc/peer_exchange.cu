@@ -8,7 +8,8 @@
 // world x num_sms records of a slot and folds them with the reference's rule (largest f0, first
 // row among equals).  No host round trip, no collective library call, nothing but posted stores on
 // the critical path.  Rows are numbered globally on every rank (the histogram matrix is replicated
-// once after K1; only scan work and alive flags are sharded), so records compare directly.
+// once after K1; only scan work and alive flags are sharded, tile t of 32 rows belonging to rank
+// t mod world), so records compare directly.
 #include <string.h>
 
 #include "mc_common.cuh"
@@ -16,7 +17,8 @@
 int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                         void *partials_dev, int *nparts_out, const McPeerPush *push);
 
-int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence);
+int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence, int mode);
+int mc_comm_flush(mc_ctx *ctx);
 
 struct CombineArgs {
 	unsigned long long slot_off[MC_XSLOTS];
@@ -65,6 +67,7 @@ scan_combine_kernel(const uint8_t *__restrict__ inbox, int world, int nparts, Co
 #pragma unroll
 			for (int j = 0; j < 4; j++) ok = ok && q[j].y == epoch && q[j].w == epoch;
 			if (ok) break;
+			__nanosleep(64);   // the scans of the next burst may share this SM
 			unsigned long long t1;
 			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
 			if (t1 - t0 > COMBINE_TIMEOUT_NS) { failed = true; break; }
@@ -108,6 +111,7 @@ static void comm_release(mc_ctx *ctx) {
 	cudaFree(cm.inbox);
 	cudaFree(cm.d_out);
 	if (cm.h_out) { cudaFreeHost(cm.h_out); cudaEventDestroy(cm.done); }
+	if (cm.xstream) { cudaStreamSynchronize(cm.xstream); cudaStreamDestroy(cm.xstream); cudaEventDestroy(cm.scans_done); }
 	cm = McComm();
 }
 
@@ -115,7 +119,7 @@ void mc_comm_destroy(mc_ctx *ctx) {
 	if (ctx && ctx->comm.world) comm_release(ctx);
 }
 
-extern "C" int mc_comm_init(mc_ctx *ctx, int rank, int world, int64_t shard_lo, int64_t shard_hi, uint8_t *handle_out) {
+extern "C" int mc_comm_init(mc_ctx *ctx, int rank, int world, uint8_t *handle_out) {
 	MC_REQUIRE(ctx, MC_ERR_ARG, "ctx is NULL");
 	MC_REQUIRE(world >= 1 && world <= MC_MAX_PEERS && rank >= 0 && rank < world, MC_ERR_ARG, "rank %d / world %d invalid (at most %d ranks)", rank, world, MC_MAX_PEERS);
 	MC_CUDA(cudaSetDevice(ctx->device));
@@ -128,8 +132,6 @@ extern "C" int mc_comm_init(mc_ctx *ctx, int rank, int world, int64_t shard_lo, 
 	MC_CUDA(cudaMemset(cm.d_out, 0, (size_t)MC_XSLOTS * sizeof(mc_scan_result) + 64));
 	cm.world = world;
 	cm.rank = rank;
-	cm.shard_lo = shard_lo;
-	cm.shard_hi = shard_hi;
 	cm.peer_inbox[rank] = cm.inbox;
 	cm.connected = world == 1;
 	if (handle_out) {
@@ -139,13 +141,6 @@ extern "C" int mc_comm_init(mc_ctx *ctx, int rank, int world, int64_t shard_lo, 
 		MC_CUDA(cudaIpcGetMemHandle(&h, cm.inbox));
 		memcpy(handle_out, &h, sizeof(h));
 	}
-	return MC_OK;
-}
-
-extern "C" int mc_comm_set_shard(mc_ctx *ctx, int64_t shard_lo, int64_t shard_hi) {
-	MC_REQUIRE(ctx && ctx->comm.world, MC_ERR_STATE, "mc_comm_init has not been called");
-	ctx->comm.shard_lo = shard_lo;
-	ctx->comm.shard_hi = shard_hi;
 	return MC_OK;
 }
 
@@ -192,7 +187,7 @@ extern "C" int mc_comm_connect_local(mc_ctx *const *ctxs, int world) {
 }
 
 
-extern "C" int mc_scan_sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot) {
+static int sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int mode) {
 	MC_REQUIRE(ctx && ctx->have_hist, MC_ERR_STATE, "mc_scan_sharded_enqueue: histograms are not built");
 	MC_REQUIRE(ctx->model.valid, MC_ERR_STATE, "mc_scan_sharded_enqueue: mc_set_model has not been called");
 	McComm &cm = ctx->comm;
@@ -201,51 +196,92 @@ extern "C" int mc_scan_sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t 
 	MC_REQUIRE(!cm.slot_pending[slot], MC_ERR_STATE, "slot %d still holds an exchange that was not collected", slot);
 	MC_REQUIRE(center_row >= 0 && center_row < ctx->n, MC_ERR_ARG, "center row out of range");
 	MC_REQUIRE(hi < lo || (lo >= 0 && hi < ctx->n), MC_ERR_ARG, "scan range [%lld,%lld] out of range", (long long)lo, (long long)hi);
-	int rc = mc_comm_scan_push(ctx, center_row, lo, hi, remove_marked, slot, 0);
+	int rc = mc_comm_scan_push(ctx, center_row, lo, hi, remove_marked, slot, 0, mode);
 	if (rc) return rc;
 	cm.slot_pending[slot] = 1;
 	return MC_OK;
 }
 
+extern "C" int mc_scan_sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot) {
+	return sharded_enqueue(ctx, center_row, lo, hi, remove_marked, slot, 1);
+}
+
+// a burst: scan i+1 sends scan i's partials while it runs (deferred variant), the last scan's leave
+// with a one-CTA flush kernel, so nothing is left unsent when the call returns
 extern "C" int mc_scan_sharded_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo, const int64_t *hi,
-                                            const int64_t *shard_lo, const int64_t *shard_hi, int count, int remove_marked, int slot0) {
+                                            int count, int remove_marked, int slot0) {
 	MC_REQUIRE(ctx && center_rows && lo && hi && count > 0, MC_ERR_ARG, "mc_scan_sharded_enqueue_many: bad arguments");
-	MC_REQUIRE((shard_lo == nullptr) == (shard_hi == nullptr), MC_ERR_ARG, "shard_lo and shard_hi go together");
 	for (int i = 0; i < count; i++) {
-		if (shard_lo) { ctx->comm.shard_lo = shard_lo[i]; ctx->comm.shard_hi = shard_hi[i]; }
-		const int rc = mc_scan_sharded_enqueue(ctx, center_rows[i], lo[i], hi[i], remove_marked, slot0 + i);
+		const int rc = sharded_enqueue(ctx, center_rows[i], lo[i], hi[i], remove_marked, slot0 + i, count > 1 ? 2 : 1);
 		if (rc) return rc;
 	}
-	return MC_OK;
+	return mc_comm_flush(ctx);
 }
 
 static unsigned long long slot_offset(unsigned int epoch, int slot) {
 	return ((unsigned long long)(epoch & 1u) * MC_XSLOTS + (unsigned long long)slot) * MC_MAX_PEERS * MC_SCAN_PARTS * MC_LL_RECORD_BYTES;
 }
 
-// internal: sharded scan of one slot on one rank (fence = 1 orders earlier peer stores, i.e. marks
-// written into another rank's array, before the record)
-int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence) {
+// sends the CTA partials of the last deferred scan (one CTA; record c, word w -> every peer)
+__global__ void __launch_bounds__(256) peer_flush_kernel(McPeerPush push, const unsigned int *__restrict__ partials, int nparts) {
+	for (int i = threadIdx.x; i < nparts * 8 * push.world; i += blockDim.x) {
+		const int p = i / (nparts * 8), rem = i % (nparts * 8), cta = rem >> 3, w = rem & 7;
+		const unsigned long long dst = push.inbox[p] + push.slot_off +
+			((unsigned long long)push.rank * MC_SCAN_PARTS + cta) * MC_LL_RECORD_BYTES + (unsigned long long)w * 8;
+		const unsigned int data = __ldcg(partials + cta * 8 + w);
+		asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(data), "r"(push.epoch) : "memory");
+	}
+}
+
+// internal: if a deferred scan's partials are still waiting, send them now
+int mc_comm_flush(mc_ctx *ctx) {
+	McComm &cm = ctx->comm;
+	if (cm.pending.epoch == 0) return MC_OK;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	peer_flush_kernel<<<1, 256, 0, ctx->stream>>>(cm.pending, (const unsigned int *)cm.pending.prev_partials, ctx->num_sms);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	cm.pending = McPeerPush{};
+	return MC_OK;
+}
+
+// internal: sharded scan of one slot on one rank.
+//   mode 1 (direct): the kernel sends its own partials when it ends; fence = 1 additionally orders
+//     earlier peer stores (marks written into another rank's array) before the record.
+//   mode 2 (deferred): the kernel sends the partials of the previous deferred scan at its start and
+//     leaves its own for the next one (or for mc_comm_flush).
+int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence, int mode) {
 	McComm &cm = ctx->comm;
 	MC_CUDA(cudaSetDevice(ctx->device));
 	if (!ctx->d_scan_slots) {
 		MC_CUDA(cudaMalloc(&ctx->d_scan_slots, (size_t)MC_SCAN_SLOTS * MC_SCAN_PARTS * sizeof(mc_scan_result)));
 		for (int i = 0; i < MC_SCAN_SLOTS; i++) ctx->slot_nparts[i] = 0;
 	}
-	int64_t l = lo > cm.shard_lo ? lo : cm.shard_lo, h = hi < cm.shard_hi ? hi : cm.shard_hi;
-	if (h < l) { l = 0; h = -1; }
+	const int64_t l = lo, h = hi;   // the kernel picks this rank's tiles (tile t belongs to rank t mod world)
 	unsigned int epoch = ++cm.slot_epoch[slot];
 	if (epoch == 0) epoch = cm.slot_epoch[slot] = 2;   // never 0 (the cleared inbox), parity kept
-	McPeerPush push{};
-	for (int p = 0; p < cm.world; p++) push.inbox[p] = (unsigned long long)cm.peer_inbox[p];
-	push.world = cm.world;
-	push.rank = cm.rank;
-	push.epoch = epoch;
-	push.fence = (unsigned int)fence;
-	push.slot_off = slot_offset(epoch, slot);
-	return mc_launch_scan_push(ctx, center_row, l, h, remove_marked,
-	                           (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result),
-	                           &ctx->slot_nparts[slot], &push);
+	void *partials = (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result);
+	McPeerPush mine{};
+	for (int p = 0; p < cm.world; p++) mine.inbox[p] = (unsigned long long)cm.peer_inbox[p];
+	mine.world = cm.world;
+	mine.rank = cm.rank;
+	mine.epoch = epoch;
+	mine.fence = (unsigned int)fence;
+	mine.slot_off = slot_offset(epoch, slot);
+	if (mode == 2) {
+		McPeerPush arg = cm.pending;     // what this kernel sends: the previous scan (epoch 0: nothing)
+		arg.deferred = 1;
+		if (arg.epoch == 0) { arg = mine; arg.epoch = 0; arg.deferred = 1; arg.prev_partials = partials; }
+		const int rc = mc_launch_scan_push(ctx, center_row, l, h, remove_marked, partials, &ctx->slot_nparts[slot], &arg);
+		if (rc) return rc;
+		cm.pending = mine;
+		cm.pending.prev_partials = partials;
+		return MC_OK;
+	}
+	int rc = mc_comm_flush(ctx);   // keep the order of arrival = the order of the scans
+	if (rc) return rc;
+	mine.deferred = 0;
+	return mc_launch_scan_push(ctx, center_row, l, h, remove_marked, partials, &ctx->slot_nparts[slot], &mine);
 }
 
 // internal: fold one slot on the device; *rec_dev_out is the combined record, *err_dev_out the timeout flag
@@ -256,6 +292,10 @@ int mc_comm_combine_dev(mc_ctx *ctx, int slot, const void **rec_dev_out, unsigne
 	args.epoch[slot] = cm.slot_epoch[slot];
 	args.slot_off[slot] = slot_offset(cm.slot_epoch[slot], slot);
 	MC_CUDA(cudaSetDevice(ctx->device));
+	{
+		const int frc = mc_comm_flush(ctx);
+		if (frc) return frc;
+	}
 	mc_scan_result *d_out = (mc_scan_result *)cm.d_out;
 	unsigned int *d_err = (unsigned int *)((uint8_t *)cm.d_out + (size_t)MC_XSLOTS * sizeof(mc_scan_result));
 	scan_combine_kernel<<<1, COMBINE_THREADS, 0, ctx->stream>>>(cm.inbox, cm.world, ctx->num_sms, args, slot, d_out, d_err);
@@ -280,6 +320,10 @@ extern "C" int mc_scan_sharded_combine(mc_ctx *ctx, int slot0, int nslots) {
 		args.slot_off[s] = slot_offset(cm.slot_epoch[s], s);
 	}
 	MC_CUDA(cudaSetDevice(ctx->device));
+	{
+		const int frc = mc_comm_flush(ctx);   // the last scan of the burst still holds its partials
+		if (frc) return frc;
+	}
 	if (!cm.h_out) {
 		MC_CUDA(cudaMallocHost(&cm.h_out, (size_t)MC_XSLOTS * sizeof(mc_scan_result) + 64));
 		MC_CUDA(cudaEventCreateWithFlags(&cm.done, cudaEventDisableTiming));
@@ -321,4 +365,141 @@ extern "C" int mc_scan_sharded_collect(mc_ctx *ctx, int slot0, int nslots, mc_sc
 	const int rc = mc_scan_sharded_combine(ctx, slot0, nslots);
 	if (rc) return rc;
 	return mc_scan_sharded_wait(ctx, slot0, nslots, res);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Burst path (streaming callers, bench.py): the scans run back to back on the context's stream
+// exactly like single-GPU scans (tiles-only variant, no peer store in the kernel); a second stream
+// folds each scan's CTA partials to ONE record per rank, stores it into every inbox and combines the
+// world records per scan.  The scan stream never waits for the exchange.
+// ---------------------------------------------------------------------------------------------
+struct BurstArgs {
+	unsigned long long slot_off[MC_XSLOTS];
+	unsigned int epoch[MC_XSLOTS];
+};
+
+// one warp per slot: fold the CTA partials of this rank's scan, then send the record (CTA index 0)
+__global__ void __launch_bounds__(32) fold_send_kernel(const mc_scan_result *__restrict__ slots, int nparts, BurstArgs args, int slot0,
+                                                       McPeerPush push) {
+	const int slot = slot0 + blockIdx.x, lane = threadIdx.x;
+	const mc_scan_result *p = slots + (size_t)slot * MC_SCAN_PARTS;
+	mc_scan_result b;
+	b.n_eval = 0; b.n_pos = 0; b.best_row = -1; b.best_f0 = -1.0;
+	for (int i = lane; i < nparts; i += 32) {
+		mc_scan_result q;
+		q.n_eval = __ldcg(&p[i].n_eval); q.n_pos = __ldcg(&p[i].n_pos);
+		q.best_row = __ldcg(&p[i].best_row); q.best_f0 = __ldcg(&p[i].best_f0);
+		xmerge(b, q);
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		mc_scan_result other;
+		other.n_eval = __shfl_xor_sync(MC_FULL_MASK, b.n_eval, o);
+		other.n_pos = __shfl_xor_sync(MC_FULL_MASK, b.n_pos, o);
+		other.best_row = __shfl_xor_sync(MC_FULL_MASK, b.best_row, o);
+		other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, b.best_f0, o);
+		xmerge(b, other);
+	}
+	unsigned long long f[4] = {(unsigned long long)b.n_eval, (unsigned long long)b.n_pos, (unsigned long long)b.best_row,
+	                           (unsigned long long)__double_as_longlong(b.best_f0)};
+	const int w = lane & 7;
+	const unsigned long long fld = (w >> 1) == 0 ? f[0] : ((w >> 1) == 1 ? f[1] : ((w >> 1) == 2 ? f[2] : f[3]));
+	const unsigned int data = (w & 1) ? (unsigned int)(fld >> 32) : (unsigned int)fld;
+	for (int q = lane >> 3; q < push.world; q += 4) {
+		const unsigned long long dst = push.inbox[q] + args.slot_off[slot] +
+			((unsigned long long)push.rank * MC_SCAN_PARTS + 0) * MC_LL_RECORD_BYTES + (unsigned long long)w * 8;
+		asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(data), "r"(args.epoch[slot]) : "memory");
+	}
+}
+
+static int burst_streams(mc_ctx *ctx) {
+	McComm &cm = ctx->comm;
+	if (cm.xstream) return MC_OK;
+	MC_CUDA(cudaStreamCreateWithFlags(&cm.xstream, cudaStreamNonBlocking));
+	MC_CUDA(cudaEventCreateWithFlags(&cm.scans_done, cudaEventDisableTiming));
+	if (!cm.h_out) {
+		MC_CUDA(cudaMallocHost(&cm.h_out, (size_t)MC_XSLOTS * sizeof(mc_scan_result) + 64));
+		MC_CUDA(cudaEventCreateWithFlags(&cm.done, cudaEventDisableTiming));
+	}
+	return MC_OK;
+}
+
+// One pipelined burst: fold the previous burst on the exchange stream (asynchronous), enqueue this
+// burst's scans on the scan stream and their fold + send on the exchange stream, and only then
+// wait for the previous summaries -- the GPU already runs this burst while the host waits.
+extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo, const int64_t *hi,
+                                     int count, int remove_marked, int slot0, int prev_slot0, int prev_count,
+                                     mc_scan_result *prev_res) {
+	MC_REQUIRE(ctx && ctx->have_hist && ctx->model.valid, MC_ERR_STATE, "mc_scan_sharded_burst: histograms / model missing");
+	McComm &cm = ctx->comm;
+	MC_REQUIRE(cm.world && cm.connected, MC_ERR_STATE, "mc_scan_sharded_burst: mc_comm_init / mc_comm_connect first");
+	MC_REQUIRE(count >= 0 && prev_count >= 0 && slot0 >= 0 && slot0 + count <= MC_XSLOTS && prev_slot0 >= 0 && prev_slot0 + prev_count <= MC_XSLOTS,
+	           MC_ERR_ARG, "slot ranges invalid");
+	MC_REQUIRE(count == 0 || (center_rows && lo && hi), MC_ERR_ARG, "mc_scan_sharded_burst: bad arguments");
+	MC_REQUIRE(prev_count == 0 || prev_res, MC_ERR_ARG, "mc_scan_sharded_burst: prev_res is NULL");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	int rc = burst_streams(ctx);
+	if (rc) return rc;
+	mc_scan_result *d_out = (mc_scan_result *)cm.d_out;
+	unsigned int *d_err = (unsigned int *)((uint8_t *)cm.d_out + (size_t)MC_XSLOTS * sizeof(mc_scan_result));
+	mc_scan_result *h_out = (mc_scan_result *)cm.h_out;
+	if (prev_count > 0) {
+		CombineArgs args;
+		memset(&args, 0, sizeof(args));
+		for (int s = prev_slot0; s < prev_slot0 + prev_count; s++) {
+			MC_REQUIRE(cm.slot_pending[s] == 3, MC_ERR_STATE, "slot %d holds no burst scan", s);
+			args.epoch[s] = cm.slot_epoch[s];
+			args.slot_off[s] = slot_offset(cm.slot_epoch[s], s);
+		}
+		scan_combine_kernel<<<prev_count, COMBINE_THREADS, 0, cm.xstream>>>(cm.inbox, cm.world, 1, args, prev_slot0, d_out, d_err);
+		ctx->launches++;
+		MC_CUDA(cudaGetLastError());
+		MC_CUDA(cudaMemcpyAsync(h_out + prev_slot0, d_out + prev_slot0, (size_t)prev_count * sizeof(mc_scan_result), cudaMemcpyDeviceToHost, cm.xstream));
+		MC_CUDA(cudaMemcpyAsync(h_out + MC_XSLOTS, d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, cm.xstream));
+		MC_CUDA(cudaEventRecord(cm.done, cm.xstream));
+	}
+	if (count > 0) {
+		if (!ctx->d_scan_slots) {
+			MC_CUDA(cudaMalloc(&ctx->d_scan_slots, (size_t)MC_SCAN_SLOTS * MC_SCAN_PARTS * sizeof(mc_scan_result)));
+			for (int i = 0; i < MC_SCAN_SLOTS; i++) ctx->slot_nparts[i] = 0;
+		}
+		McPeerPush push{};
+		for (int p = 0; p < cm.world; p++) push.inbox[p] = (unsigned long long)cm.peer_inbox[p];
+		push.world = cm.world;
+		push.rank = cm.rank;
+		push.deferred = 3;   // tiles only
+		BurstArgs bargs;
+		memset(&bargs, 0, sizeof(bargs));
+		for (int i = 0; i < count; i++) {
+			const int slot = slot0 + i;
+			MC_REQUIRE(!cm.slot_pending[slot], MC_ERR_STATE, "slot %d still holds an exchange that was not collected", slot);
+			MC_REQUIRE(center_rows[i] >= 0 && center_rows[i] < ctx->n, MC_ERR_ARG, "center row out of range");
+			MC_REQUIRE(hi[i] < lo[i] || (lo[i] >= 0 && hi[i] < ctx->n), MC_ERR_ARG, "scan range out of range");
+			unsigned int epoch = ++cm.slot_epoch[slot];
+			if (epoch == 0) epoch = cm.slot_epoch[slot] = 2;
+			bargs.epoch[slot] = epoch;
+			bargs.slot_off[slot] = slot_offset(epoch, slot);
+			rc = mc_launch_scan_push(ctx, center_rows[i], lo[i], hi[i], remove_marked,
+			                         (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result),
+			                         &ctx->slot_nparts[slot], &push);
+			if (rc) return rc;
+			cm.slot_pending[slot] = 3;
+		}
+		MC_CUDA(cudaEventRecord(cm.scans_done, ctx->stream));
+		MC_CUDA(cudaStreamWaitEvent(cm.xstream, cm.scans_done, 0));
+		fold_send_kernel<<<count, 32, 0, cm.xstream>>>((const mc_scan_result *)ctx->d_scan_slots, ctx->num_sms, bargs, slot0, push);
+		ctx->launches++;
+		MC_CUDA(cudaGetLastError());
+	}
+	if (prev_count > 0) {
+		MC_CUDA(cudaEventSynchronize(cm.done));
+		for (int s = prev_slot0; s < prev_slot0 + prev_count; s++) cm.slot_pending[s] = 0;
+		if (*(const unsigned int *)(h_out + MC_XSLOTS)) {
+			MC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), cm.xstream));
+			mc_set_error("sharded burst: a peer's records did not arrive within %.0f s (rank %d of %d)", COMBINE_TIMEOUT_NS * 1e-9, cm.rank, cm.world);
+			return MC_ERR_CUDA;
+		}
+		memcpy(prev_res, h_out + prev_slot0, (size_t)prev_count * sizeof(mc_scan_result));
+	}
+	return MC_OK;
 }

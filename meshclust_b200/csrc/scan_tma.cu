@@ -93,18 +93,35 @@ __device__ unsigned long long g_scan_trace[148 * 32 * 8];
 #define TRACE(slot) do {} while (0)
 #endif
 
-// PUSH = true is the sharded variant (multi-GPU): identical, plus the peer stores at the very end;
-// the single-GPU instantiation carries neither the extra arguments nor the branch
-template <bool PUSH>
-struct PushArg { McPeerPush v; };
+// PUSH selects the sharded (multi-GPU) variants; the single-GPU instantiation (0) carries neither the
+// extra arguments nor a branch.
+//   1  direct:   this scan's CTA partials go to the peers' inboxes at the very end of the kernel (the
+//                kernel then ends only when the remote stores are acknowledged: right when something
+//                waits for this very scan, e.g. the sharded Phase-A step)
+//   2  deferred: the kernel starts by sending the PREVIOUS sharded scan's partials (read back from
+//                global memory), so the NVLink round trip overlaps this scan instead of sitting
+//                between two dependent launches; the last scan of a burst is sent by
+//                peer_flush_kernel (peer_exchange.cu)
+template <int PUSH>
+struct PushArg { McPeerPush v; const unsigned int *prev_partials; };
 template <>
-struct PushArg<false> {};
+struct PushArg<0> {};
 
-template <int TB, int RB, bool PUSH>
+__device__ __forceinline__ void peer_store_words(const McPeerPush &push, int cta, int lane, unsigned int data) {
+	// lane = 8 * (peer mod 4) + word: one 8-byte {data, epoch} store per word and peer
+	const int w = lane & 7;
+	for (int p = lane >> 3; p < push.world; p += 4) {
+		const unsigned long long dst = push.inbox[p] + push.slot_off +
+			((unsigned long long)push.rank * MC_SCAN_PARTS + cta) * MC_LL_RECORD_BYTES + (unsigned long long)w * 8;
+		asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(data), "r"(push.epoch) : "memory");
+	}
+}
+
+template <int TB, int RB, int PUSH>
 __global__ void __launch_bounds__(32 * (1 + TileCfg<RB>::NCW), 1)
 scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, uint8_t *__restrict__ marks,
-                long long lo, long long hi, long long center_row, McModel model, int remove_marked,
-                ScanPartial *__restrict__ partials, PushArg<PUSH> push_arg) {
+                long long lo, long long hi, long long nrows_total, long long center_row, McModel model,
+                int remove_marked, ScanPartial *__restrict__ partials, PushArg<PUSH> push_arg) {
 	using C = RowCfg<RB>;
 	using T = TileCfg<RB>;
 	constexpr int NB = RB / TB;
@@ -132,9 +149,16 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 	__syncthreads();
 	TRACE(1);
 
-	// tiles of RT rows, dealt round-robin to CTAs, then round-robin to the CTA's consumer warps
-	const long long nrows = hi - lo + 1;
-	const long long ntiles = (nrows + T::RT - 1) / T::RT;
+	// Tiles are RT rows on an ABSOLUTE grid (tile t = rows [t*RT, (t+1)*RT)), so which GPU owns a row
+	// -- and with it the row's alive flag -- never depends on the range of a scan: tile t belongs to
+	// rank t mod world (tile-interleaved sharding: any length window spreads over all GPUs).  A
+	// rank's tiles are dealt round-robin to its CTAs, then round-robin to the CTA's consumer warps.
+	// Rows of the first / last tile outside [lo, hi] are copied but never evaluated.
+	int world = 1, rank = 0;
+	if constexpr (PUSH != 0) { world = push_arg.v.world; rank = push_arg.v.rank; }
+	const long long t0 = lo / T::RT, t1 = hi / T::RT;
+	const long long tf = t0 + (((long long)rank - t0 % world) + world) % world;   // first tile of this rank
+	const long long ntiles = (hi >= lo && tf <= t1) ? (t1 - tf) / world + 1 : 0;
 	const long long my_first = blockIdx.x;
 	const long long nmine = my_first < ntiles ? (ntiles - my_first + gridDim.x - 1) / gridDim.x : 0;
 
@@ -154,8 +178,8 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 				if (jj >= nmine) break;
 				const long long round = u / T::D;
 				if (round > 0) mbar_wait(&empty_bar[lane], (uint32_t)(round - 1) & 1);
-				const long long r0 = lo + (my_first + jj * gridDim.x) * T::RT;
-				long long nr = hi - r0 + 1;
+				const long long r0 = (tf + (my_first + jj * gridDim.x) * world) * T::RT;
+				long long nr = nrows_total - r0;
 				if (nr > T::RT) nr = T::RT;
 				uint8_t *dst = smem + (size_t)lane * T::STAGE_BYTES;
 				mbar_expect_tx(&full_bar[lane], (uint32_t)(nr * RB + nr * 32));
@@ -178,12 +202,18 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		cen.load(crow, r);
 		const uint64_t lq = aux[center_row].len, mq = aux[center_row].mag, sq = aux[center_row].sq;
 		asm volatile("griddepcontrol.wait;" ::: "memory");   // before the first global write of this warp
+		if constexpr (PUSH == 2) {
+			// the previous sharded scan of this stream left its CTA partials in global memory; they leave
+			// for the peers now, while this scan's tiles are in flight
+			if (cw == 0 && push_arg.v.epoch != 0)
+				peer_store_words(push_arg.v, blockIdx.x, lane, __ldcg(push_arg.prev_partials + blockIdx.x * 8 + (lane & 7)));
+		}
 
 		long long u = 0;
 		for (long long jj = cw; jj < nmine; jj += T::NCW, u++) {
-			const long long row0 = lo + (my_first + jj * gridDim.x) * T::RT;
+			const long long row0 = (tf + (my_first + jj * gridDim.x) * world) * T::RT;
 			const long long row_mine = row0 + lane;
-			const bool have_row = lane < T::RT && row_mine <= hi;
+			const bool have_row = lane < T::RT && row_mine >= lo && row_mine <= hi;
 			const int slot = cw * T::D + (int)(u % T::D);
 			if (u == 0) TRACE(2);
 			mbar_wait(&full_bar[slot], (uint32_t)(u / T::D) & 1);
@@ -194,8 +224,9 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			if (have_row) my_aux = *reinterpret_cast<const McRowAux *>(st + T::ROW_BYTES + (size_t)lane * 32);
 			// row p of the tile is reduced by lane group p / LPP in iteration p % LPP
 			PairAcc<TB> part[C::LPP];
-			// rows past the end of a partial tile hold stale bytes of an older tile: harmless, their
-			// lanes never reach the epilogue (have_row), so the reduction itself is branch-free
+			// rows outside [lo, hi] (or past the end of the array, where the stage keeps stale bytes of an
+			// older tile) are harmless: their lanes never reach the epilogue (have_row), so the
+			// reduction itself is branch-free
 #pragma unroll
 			for (int it = 0; it < C::LPP; it++) {
 				const int p = g * C::LPP + it;
@@ -259,10 +290,9 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			tscan_merge(b, other);
 		}
 		if (lane == 0) partials[blockIdx.x] = b;
-		if constexpr (PUSH) {
+		if constexpr (PUSH == 1) {
+			// sharded scan: this CTA's partial goes straight into every rank's inbox over NVLink
 			const McPeerPush &push = push_arg.v;
-			// sharded scan: this CTA's partial goes straight into every rank's inbox over NVLink, one
-			// 8-byte {data, epoch} store per word; lane = 8 * (peer mod 4) + word
 			if (push.fence) __threadfence_system();
 			unsigned long long f[4];
 			f[0] = (unsigned long long)__shfl_sync(MC_FULL_MASK, b.n_eval, 0);
@@ -271,12 +301,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			f[3] = (unsigned long long)__double_as_longlong(__shfl_sync(MC_FULL_MASK, b.best_f0, 0));
 			const int w = lane & 7;
 			const unsigned long long fld = (w >> 1) == 0 ? f[0] : ((w >> 1) == 1 ? f[1] : ((w >> 1) == 2 ? f[2] : f[3]));
-			const unsigned int data = (w & 1) ? (unsigned int)(fld >> 32) : (unsigned int)fld;
-			for (int p = lane >> 3; p < push.world; p += 4) {
-				const unsigned long long dst = push.inbox[p] + push.slot_off +
-					((unsigned long long)push.rank * MC_SCAN_PARTS + blockIdx.x) * MC_LL_RECORD_BYTES + (unsigned long long)w * 8;
-				asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(data), "r"(push.epoch) : "memory");
-			}
+			peer_store_words(push, blockIdx.x, lane, (w & 1) ? (unsigned int)(fld >> 32) : (unsigned int)fld);
 		}
 		TRACE(7);
 	}
@@ -322,24 +347,25 @@ int mc_launch_scan_fold(mc_ctx *ctx, const void *slots_dev, const int *nparts_de
 int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                           void *partials_dev, int *nparts_out);
 
-template <int TB, int RB, bool PUSH>
+template <int TB, int RB, int PUSH>
 static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                           void *partials_dev, int *nparts_out, const McPeerPush *push) {
+                           void *partials_dev, int *nparts_out, const McPeerPush *push, const void *prev_partials) {
 	using T = TileCfg<RB>;
 	const size_t smem = (size_t)T::NS * T::STAGE_BYTES;
-	static bool attr_set = false;
-	if (!attr_set) {
+	static bool attr_set[64] = {};   // function attributes are per device
+	if (!attr_set[ctx->device & 63]) {
 		MC_CUDA(cudaFuncSetAttribute(scan_tma_kernel<TB, RB, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set = true;
+		attr_set[ctx->device & 63] = true;
 	}
-	const int64_t ntiles = (hi - lo + 1 + T::RT - 1) / T::RT;
+	const int64_t ntiles = hi >= lo ? hi / T::RT - lo / T::RT + 1 : 0;   // absolute tiles touched by [lo, hi]
 	int64_t blocks = ctx->num_sms;
 	if (blocks > ntiles) blocks = ntiles;
 	if (blocks < 1) blocks = 1;
 	PushArg<PUSH> pa{};
 	uint8_t *marks = ctx->d_marks;
-	if constexpr (PUSH) {   // sharded: every rank always sends num_sms records, so a reader knows how many to expect
+	if constexpr (PUSH != 0) {   // sharded: every rank always sends num_sms records, so a reader knows how many to expect
 		pa.v = *push;
+		pa.prev_partials = (const unsigned int *)prev_partials;
 		blocks = ctx->num_sms;
 		if (ctx->comm.marks_target) marks = ctx->comm.marks_target;   // marks go to the rank that compacts them
 	}
@@ -355,7 +381,7 @@ static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t 
 	cfg.attrs = attr;
 	cfg.numAttrs = no_pdl ? 0 : 1;
 	MC_CUDA(cudaLaunchKernelEx(&cfg, scan_tma_kernel<TB, RB, PUSH>, (const uint8_t *)ctx->d_hist, ctx->d_aux, marks,
-	                           (long long)lo, (long long)hi, (long long)center_row, ctx->model, remove_marked,
+	                           (long long)lo, (long long)hi, (long long)ctx->n, (long long)center_row, ctx->model, remove_marked,
 	                           (ScanPartial *)partials_dev, pa));
 	*nparts_out = (int)blocks;
 	ctx->launches++;
@@ -366,8 +392,10 @@ static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t 
 template <int TB, int RB>
 static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                       void *partials_dev, int *nparts_out, const McPeerPush *push) {
-	if (push) return launch_tma_impl<TB, RB, true>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-	return launch_tma_impl<TB, RB, false>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, nullptr);
+	if (push && push->deferred == 3) return launch_tma_impl<TB, RB, 3>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push, nullptr);
+	if (push && push->deferred) return launch_tma_impl<TB, RB, 2>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push, push->prev_partials);
+	if (push) return launch_tma_impl<TB, RB, 1>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push, nullptr);
+	return launch_tma_impl<TB, RB, 0>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, nullptr, nullptr);
 }
 
 // partials_dev must hold MC_SCAN_PARTS entries of 32 bytes; *nparts_out says how many were written

@@ -491,20 +491,38 @@ void write_clstr(const Ctx &c, const std::vector<Cluster> &part) {
 	printf("Printing output\n");
 	FILE *f = fopen(c.opt.output.c_str(), "w");
 	if (!f) { fprintf(stderr, "cannot open %s\n", c.opt.output.c_str()); exit(1); }
+	// one big buffer, decimal conversion by hand: a million fprintf calls are a visible slice of a run
+	std::string buf;
+	buf.reserve(1 << 22);
+	char num[32];
+	auto put_u = [&](unsigned long long v) {
+		int k = 0;
+		do { num[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+		while (k) buf.push_back(num[--k]);
+	};
 	int counter = 0;
 	for (const Cluster &cl : part) {
 		if (cl.rows.empty()) continue;
-		fprintf(f, ">Cluster %d\n", counter);
-		int pt = 0;
+		buf += ">Cluster ";
+		put_u((unsigned long long)counter);
+		buf.push_back('\n');
+		unsigned long long pt = 0;
 		for (int64_t r : cl.rows) {
 			const int64_t id = c.ds.id_of_row[r];
-			fprintf(f, "%d\t%llunt, %s... ", pt, (unsigned long long)c.ds.len[id], c.ds.fa.headers[id].c_str());
-			if (r == cl.center_row) fputc('*', f);
-			fputc('\n', f);
+			put_u(pt);
+			buf.push_back('\t');
+			put_u((unsigned long long)c.ds.len[id]);
+			buf += "nt, ";
+			buf += c.ds.fa.headers[id];
+			buf += "... ";
+			if (r == cl.center_row) buf.push_back('*');
+			buf.push_back('\n');
 			pt++;
+			if (buf.size() > (1 << 22) - 4096) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
 		}
 		counter++;
 	}
+	fwrite(buf.data(), 1, buf.size(), f);
 	fclose(f);
 }
 
@@ -520,13 +538,11 @@ void mean_shift(Ctx &c, BVec &bv) {
 	const int world = (int)c.ranks.size();
 	if (world > 1 && !c.model.align) {
 		// rows are replicated once (device-to-device), scan work and alive flags are sharded
-		// in contiguous row blocks; summaries and marks cross GPUs inside the scan kernel
+		// tile-interleaved (tile t of 32 rows belongs to GPU t mod N); summaries and marks cross GPUs
+		// inside the scan kernel
 		Timer ts;
 		for (int r = 1; r < world; r++) GPU(mc_clone_points(c.ranks[r], c.gpu));
-		for (int r = 0; r < world; r++) {
-			const int64_t lo = ds.n * r / world, hi = ds.n * (r + 1) / world - 1;
-			GPU(mc_comm_init(c.ranks[r], r, world, lo, hi, nullptr));
-		}
+		for (int r = 0; r < world; r++) GPU(mc_comm_init(c.ranks[r], r, world, nullptr));
 		GPU(mc_comm_connect_local(c.ranks.data(), world));
 		printf("  [points replicated to %d GPUs, peer inboxes connected %.2fs]\n", world, ts.lap());
 	}
@@ -604,6 +620,7 @@ void mean_shift(Ctx &c, BVec &bv) {
 	printf("Accumulation: %zu clusters, %lld scans, %lld evals  [%.2fs]\n", part.size(), (long long)scans, (long long)evals, tm.lap());
 
 	// ---------------- Phase B: update + merge (ClusterFactory.cpp:733-753) -----------------------
+	int iters_run = 0;
 	for (int iter = 0; iter < c.opt.iterations; iter++) {
 		const int64_t nc = (int64_t)part.size();
 		if (nc == 0) break;
@@ -618,10 +635,11 @@ void mean_shift(Ctx &c, BVec &bv) {
 			cb[j] = off[std::max<int64_t>(0, j - delta)];
 			ce[j] = off[std::min<int64_t>(j + delta, nc - 1) + 1];
 		}
+		bool changed = false;
 		if (!c.model.align) {
 			GPU(mc_update_centers(c.gpu, centers.data(), nc, cand.data(), (int64_t)cand.size(), cb.data(), ce.data(), next.data()));
 			for (int64_t j = 0; j < nc; j++)
-				if (next[j] >= 0 && next[j] != part[j].center_row) part[j].center_row = next[j];
+				if (next[j] >= 0 && next[j] != part[j].center_row) { part[j].center_row = next[j]; changed = true; }
 		} else {
 			// --align: a Center holds a CLONE, and DivergencePoint::clone() does not
 			// copy the sequence (DivergencePoint.h:37-43, Center.h:14).  Feature::align therefore aligns
@@ -682,11 +700,17 @@ void mean_shift(Ctx &c, BVec &bv) {
 				auto &to_add = part[best.first].rows;
 				to_add.insert(to_add.end(), part[i].rows.begin(), part[i].rows.end());
 				part[i].removed = true;
+				changed = true;
 			}
 		}
 		part.erase(std::remove_if(part.begin(), part.end(), [](const Cluster &p) { return p.removed; }), part.end());
+		// An iteration is a pure function of (centers, member lists): once one changes nothing, the
+		// remaining ones cannot either, and the reference's fixed count of iterations (:733) is spent on
+		// identical no-ops.  (--align keeps going: its id-pair cache changes between iterations.)
+		if (!changed && !c.model.align) { iters_run = iter + 1; break; }
+		iters_run = iter + 1;
 	}
-	printf("Update: %zu clusters  [%.2fs]\n", part.size(), tm.lap());
+	printf("Update: %zu clusters after %d of %d iterations (fixed point)  [%.2fs]\n", part.size(), iters_run, c.opt.iterations, tm.lap());
 	write_clstr(c, part);
 }
 
@@ -704,6 +728,14 @@ int run_pipeline(Options opt) {
 	int ctx_rc = MC_OK;
 	std::string ctx_err;
 	double ctx_s = 0;
+	// CUDA start-up time grows with the number of GPUs the driver has to initialise: expose only the
+	// ones this run uses (unless the user has chosen a set already)
+	if (!getenv("CUDA_VISIBLE_DEVICES")) {
+		std::string vis;
+		for (int r = 0; r < std::max(1, opt.gpus); r++) vis += (r ? "," : "") + std::to_string(opt.device + r);
+		setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+		opt.device = 0;
+	}
 	c.ranks.assign((size_t)std::max(1, opt.gpus), nullptr);
 	std::thread ctx_thread([&]() {
 		Timer t;

@@ -226,7 +226,7 @@ int mc_accumulate_step(mc_ctx *c, int64_t center, int64_t lo, int64_t hi, int re
 	return MC_OK;
 }
 int mc_clone_points(mc_ctx *dst, mc_ctx *src) { *dst = *src; return MC_OK; }
-int mc_comm_init(mc_ctx *, int, int, int64_t, int64_t, uint8_t *) { return MC_OK; }
+int mc_comm_init(mc_ctx *, int, int, uint8_t *) { return MC_OK; }
 int mc_comm_connect_local(mc_ctx *const *, int) { return MC_OK; }
 int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_t center, int64_t lo, int64_t hi, int restart, mc_step_result *res, int64_t *rows_out, int64_t cap) {
 	const int rc = mc_accumulate_step(ctxs[0], center, lo, hi, restart, res, rows_out, cap);

@@ -395,8 +395,7 @@ def test_sharded_scan_equals_single(ctx, world, k, n):
             c = api.Context(0)
             c.load_histograms(H, lens, k)
             c.set_model(mins, maxs, w, 3)
-            lo, hi = sharding.shard_bounds(n, world, r)
-            c.comm_init(r, world, lo, hi - 1)
+            c.comm_init(r, world)
             ranks.append(c)
         api.Context.comm_connect_local(ranks)
         ctx.alive_reset()
@@ -422,6 +421,18 @@ def test_sharded_scan_equals_single(ctx, world, k, n):
                 c.scan_sharded_enqueue(center, 0, n - 1, False, 10 + i)
         for c in ranks:
             assert c.scan_sharded_collect(10, len(centers)) == want
+        # the streaming form: bursts of scans on the scan stream, fold + send + combine on a second stream,
+        # results one burst behind
+        cr = np.array(centers, np.int64)
+        lo_a = np.zeros(len(centers), np.int64)
+        hi_a = np.full(len(centers), n - 1, np.int64)
+        e = np.zeros(0, np.int64)
+        for c in ranks:
+            assert c.scan_sharded_burst(cr, lo_a, hi_a, False, 20, 0, 0) == []
+        for c in ranks:
+            assert c.scan_sharded_burst(cr[::-1].copy(), lo_a, hi_a, False, 30, 20, len(centers)) == want
+        for c in ranks:
+            assert c.scan_sharded_burst(e, e, e, False, 0, 30, len(centers)) == want[::-1]
         # a range that misses some shards entirely
         w1, _ = ctx.scan(3, 0, n // (2 * world))
         for c in ranks:
@@ -467,7 +478,7 @@ def test_accumulate_step_sharded_equals_single(ctx, world, k, n):
                 c.set_model(mins, maxs, w, 3)
             else:
                 c.clone_points_from(ranks[0])
-            c.comm_init(r, world, n * r // world, n * (r + 1) // world - 1)
+            c.comm_init(r, world)
             ranks.append(c)
         api.Context.comm_connect_local(ranks)
         ctx.alive_reset()
