@@ -323,7 +323,9 @@ class Context:
     def accumulate_step(self, center_row: int, lo: int, hi: int, restart: bool):
         """one accumulate() iteration: scan + remove + get_mean; returns (StepResult, marked rows ascending)"""
         res = StepResult()
-        rows = np.zeros(max(self.n, 1), np.int64)
+        rows = getattr(self, "_rows_buf", None)
+        if rows is None or rows.size < max(self.n, 1):
+            rows = self._rows_buf = np.empty(max(self.n, 1), np.int64)
         _check(_lib.mc_accumulate_step(self._h, C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi), C.c_int(1 if restart else 0),
                                        C.byref(res), _p(rows), C.c_int64(rows.size)))
         return res, rows[: res.scan.n_pos].copy()

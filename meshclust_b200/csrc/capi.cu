@@ -723,7 +723,7 @@ extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, i
 	return MC_OK;
 }
 
-int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence, int mode);
+int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence);
 int mc_comm_combine_dev(mc_ctx *ctx, int slot, const void **rec_dev_out, unsigned int **err_dev_out);
 
 extern "C" int mc_clone_points(mc_ctx *dst, mc_ctx *src) {
@@ -777,7 +777,7 @@ extern "C" int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_
 	for (int r = world - 1; r >= 0; r--) {
 		mc_ctx *c = ctxs[r];
 		c->comm.marks_target = r == 0 ? nullptr : root->d_marks;
-		rc = mc_comm_scan_push(c, center_row, lo, hi, 1, 0, 1, 1);
+		rc = mc_comm_scan_push(c, center_row, lo, hi, 1, 0, 1);
 		c->comm.marks_target = nullptr;
 		if (rc) return rc;
 	}

@@ -85,10 +85,7 @@ struct McPeerPush {                            // by-value argument of the scan 
 	unsigned int epoch;                        // flag value of this exchange, never 0
 	unsigned int fence;                        // 1: make earlier peer stores (marks) visible before the record
 	unsigned long long slot_off;               // byte offset of (parity, slot) inside an inbox
-	// host-side only (launcher): deferred = 1 selects the variant that sends prev_partials (the CTA
-	// partials of the previous sharded scan, described by the fields above) at the start of the kernel
-	int deferred;
-	const void *prev_partials;
+	int tiles_only;                            // host-side only (launcher): 1 selects the variant that sends nothing
 };
 
 struct McComm {
@@ -105,7 +102,6 @@ struct McComm {
 	uint8_t *marks_target = nullptr;           // sharded Phase A: the marks array of the rank that runs the tail
 	cudaStream_t xstream = nullptr;            // exchange stream of the burst path (fold + send + combine)
 	cudaEvent_t scans_done = nullptr;          // recorded on the scan stream behind a burst
-	McPeerPush pending{};                      // deferred push: the last sharded scan whose partials have not left yet (epoch != 0)
 };
 
 // ---------------------------------------------------------------------------------------------

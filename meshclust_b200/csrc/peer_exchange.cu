@@ -17,8 +17,7 @@
 int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                         void *partials_dev, int *nparts_out, const McPeerPush *push);
 
-int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence, int mode);
-int mc_comm_flush(mc_ctx *ctx);
+int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence);
 
 struct CombineArgs {
 	unsigned long long slot_off[MC_XSLOTS];
@@ -187,7 +186,7 @@ extern "C" int mc_comm_connect_local(mc_ctx *const *ctxs, int world) {
 }
 
 
-static int sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int mode) {
+static int sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot) {
 	MC_REQUIRE(ctx && ctx->have_hist, MC_ERR_STATE, "mc_scan_sharded_enqueue: histograms are not built");
 	MC_REQUIRE(ctx->model.valid, MC_ERR_STATE, "mc_scan_sharded_enqueue: mc_set_model has not been called");
 	McComm &cm = ctx->comm;
@@ -196,92 +195,53 @@ static int sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t 
 	MC_REQUIRE(!cm.slot_pending[slot], MC_ERR_STATE, "slot %d still holds an exchange that was not collected", slot);
 	MC_REQUIRE(center_row >= 0 && center_row < ctx->n, MC_ERR_ARG, "center row out of range");
 	MC_REQUIRE(hi < lo || (lo >= 0 && hi < ctx->n), MC_ERR_ARG, "scan range [%lld,%lld] out of range", (long long)lo, (long long)hi);
-	int rc = mc_comm_scan_push(ctx, center_row, lo, hi, remove_marked, slot, 0, mode);
+	int rc = mc_comm_scan_push(ctx, center_row, lo, hi, remove_marked, slot, 0);
 	if (rc) return rc;
 	cm.slot_pending[slot] = 1;
 	return MC_OK;
 }
 
 extern "C" int mc_scan_sharded_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot) {
-	return sharded_enqueue(ctx, center_row, lo, hi, remove_marked, slot, 1);
+	return sharded_enqueue(ctx, center_row, lo, hi, remove_marked, slot);
 }
 
-// a burst: scan i+1 sends scan i's partials while it runs (deferred variant), the last scan's leave
-// with a one-CTA flush kernel, so nothing is left unsent when the call returns
 extern "C" int mc_scan_sharded_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo, const int64_t *hi,
                                             int count, int remove_marked, int slot0) {
 	MC_REQUIRE(ctx && center_rows && lo && hi && count > 0, MC_ERR_ARG, "mc_scan_sharded_enqueue_many: bad arguments");
 	for (int i = 0; i < count; i++) {
-		const int rc = sharded_enqueue(ctx, center_rows[i], lo[i], hi[i], remove_marked, slot0 + i, count > 1 ? 2 : 1);
+		const int rc = sharded_enqueue(ctx, center_rows[i], lo[i], hi[i], remove_marked, slot0 + i);
 		if (rc) return rc;
 	}
-	return mc_comm_flush(ctx);
+	return MC_OK;
 }
 
 static unsigned long long slot_offset(unsigned int epoch, int slot) {
 	return ((unsigned long long)(epoch & 1u) * MC_XSLOTS + (unsigned long long)slot) * MC_MAX_PEERS * MC_SCAN_PARTS * MC_LL_RECORD_BYTES;
 }
 
-// sends the CTA partials of the last deferred scan (one CTA; record c, word w -> every peer)
-__global__ void __launch_bounds__(256) peer_flush_kernel(McPeerPush push, const unsigned int *__restrict__ partials, int nparts) {
-	for (int i = threadIdx.x; i < nparts * 8 * push.world; i += blockDim.x) {
-		const int p = i / (nparts * 8), rem = i % (nparts * 8), cta = rem >> 3, w = rem & 7;
-		const unsigned long long dst = push.inbox[p] + push.slot_off +
-			((unsigned long long)push.rank * MC_SCAN_PARTS + cta) * MC_LL_RECORD_BYTES + (unsigned long long)w * 8;
-		const unsigned int data = __ldcg(partials + cta * 8 + w);
-		asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(data), "r"(push.epoch) : "memory");
-	}
-}
-
-// internal: if a deferred scan's partials are still waiting, send them now
-int mc_comm_flush(mc_ctx *ctx) {
-	McComm &cm = ctx->comm;
-	if (cm.pending.epoch == 0) return MC_OK;
-	MC_CUDA(cudaSetDevice(ctx->device));
-	peer_flush_kernel<<<1, 256, 0, ctx->stream>>>(cm.pending, (const unsigned int *)cm.pending.prev_partials, ctx->num_sms);
-	ctx->launches++;
-	MC_CUDA(cudaGetLastError());
-	cm.pending = McPeerPush{};
-	return MC_OK;
-}
-
-// internal: sharded scan of one slot on one rank.
-//   mode 1 (direct): the kernel sends its own partials when it ends; fence = 1 additionally orders
-//     earlier peer stores (marks written into another rank's array) before the record.
-//   mode 2 (deferred): the kernel sends the partials of the previous deferred scan at its start and
-//     leaves its own for the next one (or for mc_comm_flush).
-int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence, int mode) {
+// internal: sharded scan of one slot on one rank; the kernel sends its own CTA partials when it ends.
+// fence = 1 additionally orders earlier peer stores (marks written into another rank's array) before
+// the record.
+int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence) {
 	McComm &cm = ctx->comm;
 	MC_CUDA(cudaSetDevice(ctx->device));
 	if (!ctx->d_scan_slots) {
 		MC_CUDA(cudaMalloc(&ctx->d_scan_slots, (size_t)MC_SCAN_SLOTS * MC_SCAN_PARTS * sizeof(mc_scan_result)));
 		for (int i = 0; i < MC_SCAN_SLOTS; i++) ctx->slot_nparts[i] = 0;
 	}
-	const int64_t l = lo, h = hi;   // the kernel picks this rank's tiles (tile t belongs to rank t mod world)
 	unsigned int epoch = ++cm.slot_epoch[slot];
 	if (epoch == 0) epoch = cm.slot_epoch[slot] = 2;   // never 0 (the cleared inbox), parity kept
-	void *partials = (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result);
-	McPeerPush mine{};
-	for (int p = 0; p < cm.world; p++) mine.inbox[p] = (unsigned long long)cm.peer_inbox[p];
-	mine.world = cm.world;
-	mine.rank = cm.rank;
-	mine.epoch = epoch;
-	mine.fence = (unsigned int)fence;
-	mine.slot_off = slot_offset(epoch, slot);
-	if (mode == 2) {
-		McPeerPush arg = cm.pending;     // what this kernel sends: the previous scan (epoch 0: nothing)
-		arg.deferred = 1;
-		if (arg.epoch == 0) { arg = mine; arg.epoch = 0; arg.deferred = 1; arg.prev_partials = partials; }
-		const int rc = mc_launch_scan_push(ctx, center_row, l, h, remove_marked, partials, &ctx->slot_nparts[slot], &arg);
-		if (rc) return rc;
-		cm.pending = mine;
-		cm.pending.prev_partials = partials;
-		return MC_OK;
-	}
-	int rc = mc_comm_flush(ctx);   // keep the order of arrival = the order of the scans
-	if (rc) return rc;
-	mine.deferred = 0;
-	return mc_launch_scan_push(ctx, center_row, l, h, remove_marked, partials, &ctx->slot_nparts[slot], &mine);
+	McPeerPush push{};
+	for (int p = 0; p < cm.world; p++) push.inbox[p] = (unsigned long long)cm.peer_inbox[p];
+	push.world = cm.world;
+	push.rank = cm.rank;
+	push.epoch = epoch;
+	push.fence = (unsigned int)fence;
+	push.slot_off = slot_offset(epoch, slot);
+	push.tiles_only = 0;
+	return mc_launch_scan_push(ctx, center_row, lo, hi, remove_marked,
+	                           (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result),
+	                           &ctx->slot_nparts[slot], &push);
 }
 
 // internal: fold one slot on the device; *rec_dev_out is the combined record, *err_dev_out the timeout flag
@@ -292,10 +252,6 @@ int mc_comm_combine_dev(mc_ctx *ctx, int slot, const void **rec_dev_out, unsigne
 	args.epoch[slot] = cm.slot_epoch[slot];
 	args.slot_off[slot] = slot_offset(cm.slot_epoch[slot], slot);
 	MC_CUDA(cudaSetDevice(ctx->device));
-	{
-		const int frc = mc_comm_flush(ctx);
-		if (frc) return frc;
-	}
 	mc_scan_result *d_out = (mc_scan_result *)cm.d_out;
 	unsigned int *d_err = (unsigned int *)((uint8_t *)cm.d_out + (size_t)MC_XSLOTS * sizeof(mc_scan_result));
 	scan_combine_kernel<<<1, COMBINE_THREADS, 0, ctx->stream>>>(cm.inbox, cm.world, ctx->num_sms, args, slot, d_out, d_err);
@@ -320,10 +276,6 @@ extern "C" int mc_scan_sharded_combine(mc_ctx *ctx, int slot0, int nslots) {
 		args.slot_off[s] = slot_offset(cm.slot_epoch[s], s);
 	}
 	MC_CUDA(cudaSetDevice(ctx->device));
-	{
-		const int frc = mc_comm_flush(ctx);   // the last scan of the burst still holds its partials
-		if (frc) return frc;
-	}
 	if (!cm.h_out) {
 		MC_CUDA(cudaMallocHost(&cm.h_out, (size_t)MC_XSLOTS * sizeof(mc_scan_result) + 64));
 		MC_CUDA(cudaEventCreateWithFlags(&cm.done, cudaEventDisableTiming));
@@ -467,7 +419,7 @@ extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, co
 		for (int p = 0; p < cm.world; p++) push.inbox[p] = (unsigned long long)cm.peer_inbox[p];
 		push.world = cm.world;
 		push.rank = cm.rank;
-		push.deferred = 3;   // tiles only
+		push.tiles_only = 1;
 		BurstArgs bargs;
 		memset(&bargs, 0, sizeof(bargs));
 		for (int i = 0; i < count; i++) {

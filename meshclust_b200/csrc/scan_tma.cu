@@ -94,16 +94,17 @@ __device__ unsigned long long g_scan_trace[148 * 32 * 8];
 #endif
 
 // PUSH selects the sharded (multi-GPU) variants; the single-GPU instantiation (0) carries neither the
-// extra arguments nor a branch.
-//   1  direct:   this scan's CTA partials go to the peers' inboxes at the very end of the kernel (the
-//                kernel then ends only when the remote stores are acknowledged: right when something
-//                waits for this very scan, e.g. the sharded Phase-A step)
-//   2  deferred: the kernel starts by sending the PREVIOUS sharded scan's partials (read back from
-//                global memory), so the NVLink round trip overlaps this scan instead of sitting
-//                between two dependent launches; the last scan of a burst is sent by
-//                peer_flush_kernel (peer_exchange.cu)
+// extra arguments nor a branch.  All sharded variants evaluate only this rank's tiles of the range.
+//   1  direct:     this scan's CTA partials go to the peers' inboxes at the very end of the kernel --
+//                  lowest latency for a single scan whose result is awaited right away (the sharded
+//                  Phase-A step).  A kernel that ends with remote stores completes only when NVLink
+//                  has acknowledged them, which costs a stream of back-to-back scans ~5 us per launch
+//                  (measured at 2 GPUs: 9.0 -> 13.8 us), hence:
+//   2  tiles only: nothing is sent from the kernel; a second stream folds the CTA partials of a
+//                  burst of scans and sends one record per scan and rank (peer_exchange.cu), so the
+//                  scan stream never waits for the exchange
 template <int PUSH>
-struct PushArg { McPeerPush v; const unsigned int *prev_partials; };
+struct PushArg { McPeerPush v; };
 template <>
 struct PushArg<0> {};
 
@@ -202,13 +203,6 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		cen.load(crow, r);
 		const uint64_t lq = aux[center_row].len, mq = aux[center_row].mag, sq = aux[center_row].sq;
 		asm volatile("griddepcontrol.wait;" ::: "memory");   // before the first global write of this warp
-		if constexpr (PUSH == 2) {
-			// the previous sharded scan of this stream left its CTA partials in global memory; they leave
-			// for the peers now, while this scan's tiles are in flight
-			if (cw == 0 && push_arg.v.epoch != 0)
-				peer_store_words(push_arg.v, blockIdx.x, lane, __ldcg(push_arg.prev_partials + blockIdx.x * 8 + (lane & 7)));
-		}
-
 		long long u = 0;
 		for (long long jj = cw; jj < nmine; jj += T::NCW, u++) {
 			const long long row0 = (tf + (my_first + jj * gridDim.x) * world) * T::RT;
@@ -349,7 +343,7 @@ int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t h
 
 template <int TB, int RB, int PUSH>
 static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                           void *partials_dev, int *nparts_out, const McPeerPush *push, const void *prev_partials) {
+                           void *partials_dev, int *nparts_out, const McPeerPush *push) {
 	using T = TileCfg<RB>;
 	const size_t smem = (size_t)T::NS * T::STAGE_BYTES;
 	static bool attr_set[64] = {};   // function attributes are per device
@@ -365,7 +359,6 @@ static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t 
 	uint8_t *marks = ctx->d_marks;
 	if constexpr (PUSH != 0) {   // sharded: every rank always sends num_sms records, so a reader knows how many to expect
 		pa.v = *push;
-		pa.prev_partials = (const unsigned int *)prev_partials;
 		blocks = ctx->num_sms;
 		if (ctx->comm.marks_target) marks = ctx->comm.marks_target;   // marks go to the rank that compacts them
 	}
@@ -392,10 +385,9 @@ static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t 
 template <int TB, int RB>
 static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                       void *partials_dev, int *nparts_out, const McPeerPush *push) {
-	if (push && push->deferred == 3) return launch_tma_impl<TB, RB, 3>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push, nullptr);
-	if (push && push->deferred) return launch_tma_impl<TB, RB, 2>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push, push->prev_partials);
-	if (push) return launch_tma_impl<TB, RB, 1>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push, nullptr);
-	return launch_tma_impl<TB, RB, 0>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, nullptr, nullptr);
+	if (push && push->tiles_only) return launch_tma_impl<TB, RB, 2>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+	if (push) return launch_tma_impl<TB, RB, 1>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+	return launch_tma_impl<TB, RB, 0>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, nullptr);
 }
 
 // partials_dev must hold MC_SCAN_PARTS entries of 32 bytes; *nparts_out says how many were written

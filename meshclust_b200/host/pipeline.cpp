@@ -19,6 +19,7 @@
 #include <set>
 #include <stdexcept>
 #include <thread>
+#include <unordered_map>
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -72,6 +73,9 @@ struct Model {
 struct Ctx {
 	mc_ctx *gpu = nullptr;            // rank 0: holds the sequences, runs training, Phase B and the Phase-A tail
 	std::vector<mc_ctx *> ranks;      // all GPUs that share the Phase-A scans (ranks[0] == gpu)
+	std::thread ranks_thread;         // creates the contexts of ranks 1.. in the background
+	int ranks_rc = MC_OK;
+	std::string ranks_err;
 	Options opt;
 	Dataset ds;
 	Model model;
@@ -438,8 +442,17 @@ struct Cluster {
 };
 
 // --align: identity cache of Feature::align (Feature.cpp:222-243), keyed by the id pair
+struct PairKeyHash {
+	size_t operator()(const std::pair<int64_t, int64_t> &k) const {
+		uint64_t x = ((uint64_t)k.first << 32) ^ (uint64_t)k.second;
+		x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33;
+		return (size_t)x;
+	}
+};
 struct AlignCache {
-	std::map<std::pair<int64_t, int64_t>, double> tab;
+	// only find / insert by key are used (never iteration), so a hash table stands in for the
+	// reference's std::map
+	std::unordered_map<std::pair<int64_t, int64_t>, double, PairKeyHash> tab;
 };
 
 // one get_close over [lo,hi] in --align mode: every alive row of the range is aligned against the
@@ -536,6 +549,11 @@ void mean_shift(Ctx &c, BVec &bv) {
 	std::vector<uint8_t> alive;   // host mirror, only needed by the --align scans
 	if (c.model.align) alive.assign((size_t)ds.n, 1);
 	const int world = (int)c.ranks.size();
+	if (c.ranks_thread.joinable()) c.ranks_thread.join();
+	if (c.ranks_rc != MC_OK) {
+		fprintf(stderr, "meshclust: mc_ctx_create failed on an additional GPU: %s\n", c.ranks_err.c_str());
+		exit(2);
+	}
 	if (world > 1 && !c.model.align) {
 		// rows are replicated once (device-to-device), scan work and alive flags are sharded
 		// tile-interleaved (tile t of 32 rows belongs to GPU t mod N); summaries and marks cross GPUs
@@ -740,14 +758,29 @@ int run_pipeline(Options opt) {
 	std::thread ctx_thread([&]() {
 		Timer t;
 		const int ndev = std::max(1, mc_device_count());
-		for (size_t r = 0; r < c.ranks.size() && ctx_rc == MC_OK; r++) {
-			// rank r sits on the r-th GPU after --device; with fewer GPUs than ranks they share devices
-			ctx_rc = mc_ctx_create(&c.ranks[r], (opt.device + (int)r) % ndev);
-			if (ctx_rc != MC_OK) ctx_err = mc_last_error();
-		}
+		// rank r sits on the r-th GPU after --device; with fewer GPUs than ranks they share devices
+		ctx_rc = mc_ctx_create(&c.ranks[0], opt.device % ndev);
+		if (ctx_rc != MC_OK) ctx_err = mc_last_error();
 		c.gpu = c.ranks[0];
 		ctx_s = t.lap();
 	});
+	// the other ranks are needed only when Phase A starts: their contexts come up in parallel, in the
+	// background, and are joined there
+	if (c.ranks.size() > 1)
+		c.ranks_thread = std::thread([&c, opt]() {
+			const int ndev = std::max(1, mc_device_count());
+			std::vector<std::thread> more;
+			std::vector<int> rcs(c.ranks.size(), MC_OK);
+			std::vector<std::string> errs(c.ranks.size());
+			for (size_t r = 1; r < c.ranks.size(); r++)
+				more.emplace_back([&, r]() {
+					rcs[r] = mc_ctx_create(&c.ranks[r], (opt.device + (int)r) % ndev);
+					if (rcs[r] != MC_OK) errs[r] = mc_last_error();
+				});
+			for (auto &th : more) th.join();
+			for (size_t r = 1; r < c.ranks.size(); r++)
+				if (rcs[r] != MC_OK && c.ranks_rc == MC_OK) { c.ranks_rc = rcs[r]; c.ranks_err = errs[r]; }
+		});
 	struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{ctx_thread};
 	// ---- read (Runner.cpp:43-52, ChromListMaker) ------------------------------------------------
 	std::vector<size_t> file_first;
