@@ -21,7 +21,7 @@ int mc_launch_dist_keys(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint
 int mc_launch_pair_list(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, double *raw5_dev, uint64_t *dist_dev, double *sum_dev, double *f0_dev, uint8_t *flag_dev, double *feats_dev);
 int mc_launch_mean_nearest(mc_ctx *ctx, const int64_t *new_rows_dev, int64_t m_new, unsigned long long *sum_dev, const int64_t *members_dev, int64_t m_all, uint8_t *tq_dev, unsigned long long *magc_dev, void *partials_dev, long long *out_row_dev, double *out_dist_dev);
 size_t mc_acc_dev_bytes();
-int mc_launch_accumulate_tail(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart, const void *partials_dev, int nparts, void *acc_dev, void *out_host_dev, int32_t *list_host_dev);
+int mc_launch_accumulate_tail(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart, const void *partials_dev, int nparts, void *acc_dev, void *out_host_dev, int32_t *list_host_dev, unsigned long long seq, const unsigned int *err_dev);
 int mc_launch_update_centers(mc_ctx *ctx, const int64_t *center_rows_dev, int64_t ncenters, const int64_t *cand_rows_dev, const int64_t *cand_begin_dev, const int64_t *cand_end_dev, const int64_t *flag_off_dev, uint8_t *flags_dev, long long *next_rows_dev);
 int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len, int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b, int64_t scratch_stride, int64_t nwarps);
 
@@ -670,6 +670,26 @@ extern "C" int mc_mean_nearest(mc_ctx *ctx, const int64_t *rows, int64_t m, int 
 	return MC_OK;
 }
 
+// The fused step publishes its result in host-mapped memory and writes a sequence word last; the
+// host polls that word instead of synchronising with the stream (saves the completion interrupt /
+// driver round trip of a few microseconds per step).  The stream is queried now and then so that a
+// failed launch or a dead kernel is still reported.
+static int wait_step(mc_ctx *ctx, unsigned long long seq) {
+	volatile unsigned long long *word = reinterpret_cast<volatile unsigned long long *>((uint8_t *)ctx->h_step + 48);
+	for (unsigned long spins = 0;; spins++) {
+		if (*word == seq) return MC_OK;
+		__builtin_ia32_pause();
+		if ((spins & 0xfff) == 0xfff) {
+			const cudaError_t q = cudaStreamQuery(ctx->stream);
+			if (q == cudaSuccess) {   // the stream is idle: the word must be there (or the kernel never ran)
+				if (*word == seq) return MC_OK;
+				MC_REQUIRE(false, MC_ERR_CUDA, "fused step finished without publishing its result");
+			}
+			if (q != cudaErrorNotReady) MC_CUDA(q);
+		}
+	}
+}
+
 // device state of the fused step + its host-mapped result block: [0,48) mc_step_result, [56,60) error
 // word of a sharded step, [64, ...) int32 marked rows
 static int ensure_step_buffers(mc_ctx *ctx) {
@@ -681,6 +701,7 @@ static int ensure_step_buffers(mc_ctx *ctx) {
 	if (need > ctx->h_step_bytes) {
 		if (ctx->h_step) { MC_CUDA(cudaStreamSynchronize(ctx->stream)); MC_CUDA(cudaFreeHost(ctx->h_step)); ctx->h_step = nullptr; ctx->h_step_bytes = 0; }
 		MC_CUDA(cudaHostAlloc(&ctx->h_step, need, cudaHostAllocMapped));
+		memset(ctx->h_step, 0, 64);   // sequence word starts at 0; step_seq counts from 1
 		MC_CUDA(cudaHostGetDevicePointer(&ctx->h_step_dev, ctx->h_step, 0));
 		ctx->h_step_bytes = need;
 	}
@@ -709,10 +730,12 @@ extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, i
 		rc = mc_launch_scan(ctx, center_row, lo, hi, 1, d_part, &nparts);
 		if (rc) return rc;
 	}
+	const unsigned long long seq = ++ctx->step_seq;
 	rc = mc_launch_accumulate_tail(ctx, center_row, lo, hi, restart, d_part, nparts, ctx->d_acc, ctx->h_step_dev,
-	                               reinterpret_cast<int32_t *>((uint8_t *)ctx->h_step_dev + 64));
+	                               reinterpret_cast<int32_t *>((uint8_t *)ctx->h_step_dev + 64), seq, nullptr);
 	if (rc) return rc;
-	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	rc = wait_step(ctx, seq);
+	if (rc) return rc;
 	*res = *reinterpret_cast<const mc_step_result *>(ctx->h_step);
 	ctx->members_n = res->n_members;
 	if (marked_rows_out) {
@@ -792,12 +815,13 @@ extern "C" int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_
 	unsigned int *d_err = nullptr;
 	rc = mc_comm_combine_dev(root, 0, &rec, &d_err);
 	if (rc) return rc;
+	const unsigned long long seq = ++root->step_seq;
 	rc = mc_launch_accumulate_tail(root, center_row, lo, hi, restart, rec, 1, root->d_acc, root->h_step_dev,
-	                               reinterpret_cast<int32_t *>((uint8_t *)root->h_step_dev + 64));
+	                               reinterpret_cast<int32_t *>((uint8_t *)root->h_step_dev + 64), seq, d_err);
+	if (rc) return rc;
+	rc = wait_step(root, seq);
 	if (rc) return rc;
 	unsigned int *h_err = reinterpret_cast<unsigned int *>((uint8_t *)root->h_step + 56);
-	MC_CUDA(cudaMemcpyAsync(h_err, d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, root->stream));
-	MC_CUDA(cudaStreamSynchronize(root->stream));
 	if (dbg) {
 		t_launch += tb - ta; t_scans += tc - tb; t_tail += now() - tc;
 		if (++n_steps % 500 == 0)

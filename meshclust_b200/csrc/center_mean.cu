@@ -178,6 +178,16 @@ __device__ __forceinline__ void step_merge(mc_scan_result &a, const mc_scan_resu
 	}
 }
 
+// The result block lives in host-mapped pinned memory: [0,48) mc_step_result, [48,56) sequence word,
+// [56,60) error word of a sharded step.  The host does not synchronise with the stream; it polls the
+// sequence word, which is written last, behind a system-scope fence.
+__device__ __forceinline__ void step_publish(mc_step_result *out_host, unsigned long long seq, const unsigned int *err_dev) {
+	volatile unsigned int *err = reinterpret_cast<volatile unsigned int *>(reinterpret_cast<uint8_t *>(out_host) + 56);
+	*err = err_dev ? __ldcg(err_dev) : 0u;
+	__threadfence_system();
+	*reinterpret_cast<volatile unsigned long long *>(reinterpret_cast<uint8_t *>(out_host) + 48) = seq;
+}
+
 template <int TB>
 __global__ void __launch_bounds__(ACC_THREADS)
 accumulate_tail_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ aux,
@@ -185,7 +195,8 @@ accumulate_tail_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restr
                        long long center_row, int restart, const mc_scan_result *__restrict__ partials,
                        int nparts, long long *__restrict__ members, unsigned long long *__restrict__ sum,
                        AccDev *__restrict__ acc, mc_step_result *__restrict__ out_host,
-                       int32_t *__restrict__ list_host) {
+                       int32_t *__restrict__ list_host, unsigned long long seq,
+                       const unsigned int *__restrict__ err_dev) {
 	namespace cg = cooperative_groups;
 	cg::grid_group grid = cg::this_grid();
 	extern __shared__ __align__(16) uint8_t tq[];   // truncated mean, nbins * TB bytes
@@ -237,6 +248,7 @@ accumulate_tail_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restr
 			out_host->nearest_row = -1;
 			out_host->n_members = m0;
 			acc->members_n = m0;
+			step_publish(out_host, seq, err_dev);
 		}
 		return;   // uniform across the grid: nobody reaches a barrier
 	}
@@ -283,6 +295,7 @@ accumulate_tail_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restr
 				list_host[at] = (int32_t)r;
 				at++;
 			}
+		__threadfence_system();   // the list is read by the host as soon as the sequence word appears
 	}
 	grid.sync();
 
@@ -372,6 +385,7 @@ accumulate_tail_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restr
 			out_host->nearest_row = r.pos >= 0 ? __ldcg(&members[r.pos]) : -1;
 			out_host->n_members = m_all;
 			acc->members_n = m_all;
+			step_publish(out_host, seq, err_dev);
 		}
 	}
 }
@@ -380,7 +394,7 @@ size_t mc_acc_dev_bytes() { return sizeof(AccDev); }
 
 int mc_launch_accumulate_tail(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart,
                               const void *partials_dev, int nparts, void *acc_dev, void *out_host_dev,
-                              int32_t *list_host_dev) {
+                              int32_t *list_host_dev, unsigned long long seq, const unsigned int *err_dev) {
 	const int nbins = ctx->nbins;
 	const size_t smem = (size_t)nbins * ctx->tbytes;
 	MC_REQUIRE(smem <= 96 * 1024, MC_ERR_UNSUPPORTED, "k too large for the accumulate kernel");
@@ -391,7 +405,7 @@ int mc_launch_accumulate_tail(mc_ctx *ctx, int64_t center_row, int64_t lo, int64
 	long long *members = (long long *)ctx->d_members;
 	unsigned long long *sum = (unsigned long long *)ctx->d_sum;
 	int nb = nbins, rs = restart, np = nparts;
-	void *args[] = {&hist, &aux, &marks, &nb, &lo_, &hi_, &cr, &rs, &partials_dev, &np, &members, &sum, &acc_dev, &out_host_dev, &list_host_dev};
+	void *args[] = {&hist, &aux, &marks, &nb, &lo_, &hi_, &cr, &rs, &partials_dev, &np, &members, &sum, &acc_dev, &out_host_dev, &list_host_dev, &seq, &err_dev};
 	int grid = ctx->num_sms < MC_SCAN_PARTS ? ctx->num_sms : MC_SCAN_PARTS;
 	const void *fn = ctx->tbytes == 1 ? (const void *)accumulate_tail_kernel<1> : (const void *)accumulate_tail_kernel<2>;
 	if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -166,6 +166,7 @@ struct mc_ctx {
 	void *h_step = nullptr;      // cudaHostAlloc(Mapped): mc_step_result, then int32 rows
 	void *h_step_dev = nullptr;  // device alias of h_step
 	size_t h_step_bytes = 0;
+	unsigned long long step_seq = 0;   // sequence number the fused step publishes behind its result
 };
 
 void mc_comm_destroy(mc_ctx *ctx);
