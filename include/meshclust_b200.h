@@ -233,6 +233,18 @@ int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_t center_ro
                                int64_t hi, int restart, mc_step_result *res,
                                int64_t *marked_rows_out, int64_t cap);
 
+/* Re-number the first `count` rows: new row i (i < count) takes the histogram and constants of old
+ * row old_of_new[i] (a permutation of 0..count-1); rows below n_alive are flagged alive, rows in
+ * [n_alive, count) dead; rows >= count are untouched.  The host uses it while accumulate()
+ * (ClusterFactory.cpp:637-714) consumes the points: rows that already belong to a cluster are moved
+ * behind the alive ones (keeping the iteration order of both groups), so the scans that follow
+ * stream alive rows only.  Nothing the reference computes depends on the numbering.  Sequences keep
+ * their original rows: mc_align_pairs returns MC_ERR_STATE after a permutation.  The member list of
+ * mc_accumulate_step / mc_mean_nearest must be empty or about to be restarted. */
+int mc_permute_rows(mc_ctx *ctx, const int64_t *old_of_new, int64_t count, int64_t n_alive);
+/* optional: allocate mc_permute_rows' staging buffers for all rows ahead of time */
+int mc_reserve_permute(mc_ctx *ctx);
+
 /* One Jacobi sweep of mean_shift_update (ClusterFactory.cpp:289-380) for ncenters centers:
  * center c sees the candidate rows cand_rows[cand_begin[c] .. cand_end[c]) (members of clusters
  * c-delta..c+delta in order), keeps those Trainer::filter (Trainer.cpp:334-349) classifies

@@ -31,7 +31,7 @@ EXPORTS = [
     "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_copy_digits",
     "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
     "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
-    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_comm_init", "mc_comm_connect", "mc_comm_connect_local",
+    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_permute_rows", "mc_reserve_permute", "mc_comm_init", "mc_comm_connect", "mc_comm_connect_local",
     "mc_scan_sharded_enqueue", "mc_scan_sharded_enqueue_many", "mc_scan_sharded_collect", "mc_scan_sharded_combine", "mc_scan_sharded_wait", "mc_scan_sharded_burst", "mc_clone_points", "mc_accumulate_step_sharded", "mc_update_centers", "mc_align_pairs",
     "mc_kmer_histograms_host", "mc_scan_host",
 ]
@@ -329,6 +329,10 @@ class Context:
         _check(_lib.mc_accumulate_step(self._h, C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi), C.c_int(1 if restart else 0),
                                        C.byref(res), _p(rows), C.c_int64(rows.size)))
         return res, rows[: res.scan.n_pos].copy()
+
+    def permute_rows(self, old_of_new, n_alive: int):
+        o = np.ascontiguousarray(old_of_new, np.int64)
+        _check(_lib.mc_permute_rows(self._h, _p(o), C.c_int64(o.size), C.c_int64(n_alive)))
 
     def update_centers(self, center_rows, cand_rows, cand_begin, cand_end) -> np.ndarray:
         cr = np.ascontiguousarray(center_rows, np.int64)

@@ -22,6 +22,7 @@ int mc_launch_pair_list(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_de
 int mc_launch_mean_nearest(mc_ctx *ctx, const int64_t *new_rows_dev, int64_t m_new, unsigned long long *sum_dev, const int64_t *members_dev, int64_t m_all, uint8_t *tq_dev, unsigned long long *magc_dev, void *partials_dev, long long *out_row_dev, double *out_dist_dev);
 size_t mc_acc_dev_bytes();
 int mc_launch_accumulate_tail(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart, const void *partials_dev, int nparts, void *acc_dev, void *out_host_dev, int32_t *list_host_dev, unsigned long long seq, const unsigned int *err_dev);
+int mc_launch_permute_rows(mc_ctx *ctx, const int32_t *old_of_new_dev, int64_t count, int64_t n_alive, void *hist_out, void *aux_out);
 int mc_launch_update_centers(mc_ctx *ctx, const int64_t *center_rows_dev, int64_t ncenters, const int64_t *cand_rows_dev, const int64_t *cand_begin_dev, const int64_t *cand_end_dev, const int64_t *flag_off_dev, uint8_t *flags_dev, long long *next_rows_dev);
 int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len, int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b, int64_t scratch_stride, int64_t nwarps);
 
@@ -133,6 +134,8 @@ static void free_seq(mc_ctx *ctx) {
 }
 
 static void free_hist(mc_ctx *ctx) {
+	cudaFree(ctx->d_hist_tmp); cudaFree(ctx->d_aux_tmp);
+	ctx->d_hist_tmp = nullptr; ctx->d_aux_tmp = nullptr; ctx->tmp_rows = 0;
 	cudaFree(ctx->d_hist); cudaFree(ctx->d_aux);
 	cudaFree(ctx->d_marks); cudaFree(ctx->d_members); cudaFree(ctx->d_sum);
 	ctx->d_hist = nullptr; ctx->d_aux = nullptr;
@@ -288,6 +291,7 @@ static int alloc_hist(mc_ctx *ctx, int64_t n, int k, int tbytes) {
 		ctx->sum_bins = nbins;
 	}
 	ctx->n = n; ctx->k = k; ctx->nbins = nbins; ctx->tbytes = tbytes;
+	ctx->rows_permuted = false;
 	MC_CUDA(cudaMemsetAsync(ctx->d_aux, 0, ((size_t)n + 64) * sizeof(McRowAux), ctx->stream));
 	MC_CUDA(cudaMemsetAsync(ctx->d_marks, 0, (size_t)n, ctx->stream));
 	ctx->members_n = 0;
@@ -843,6 +847,67 @@ extern "C" int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_
 	return MC_OK;
 }
 
+// staging buffers of mc_permute_rows for up to `count` rows (device copy of the rows, pinned + device
+// copy of the permutation)
+static int reserve_permute(mc_ctx *ctx, int64_t count) {
+	const size_t rb = (size_t)ctx->nbins * ctx->tbytes;
+	if ((size_t)count > ctx->tmp_rows) {
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_hist_tmp); cudaFree(ctx->d_aux_tmp);
+		ctx->d_hist_tmp = nullptr; ctx->d_aux_tmp = nullptr; ctx->tmp_rows = 0;
+		MC_CUDA(cudaMalloc(&ctx->d_hist_tmp, (size_t)count * rb + 256));
+		MC_CUDA(cudaMalloc(&ctx->d_aux_tmp, ((size_t)count + 64) * sizeof(McRowAux)));
+		ctx->tmp_rows = (size_t)count;
+	}
+	int rc = mc_ensure_scratch(ctx, (size_t)count * 4 + 256);
+	if (rc) return rc;
+	return mc_ensure_pinned(ctx, (size_t)count * 4);
+}
+
+// Allocate what mc_permute_rows will need for the whole point set now (e.g. while the host is busy
+// with something else), so that no allocation happens between two scans later.
+extern "C" int mc_reserve_permute(mc_ctx *ctx) {
+	MC_NEED_HIST(ctx);
+	return reserve_permute(ctx, ctx->n);
+}
+
+extern "C" int mc_permute_rows(mc_ctx *ctx, const int64_t *old_of_new, int64_t count, int64_t n_alive) {
+	MC_NEED_HIST(ctx);
+	MC_REQUIRE(old_of_new && count >= 0 && count <= ctx->n && n_alive >= 0 && n_alive <= count, MC_ERR_ARG, "mc_permute_rows: bad arguments");
+	if (count == 0) return MC_OK;
+	const bool dbg = getenv("MC_DEBUG_TIMING") != nullptr;
+	auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+	double t_prev = now();
+	auto lap = [&](const char *what) { if (dbg) { const double t = now(); fprintf(stderr, "[mc_permute_rows count=%lld] %-22s %.4f s\n", (long long)count, what, t - t_prev); t_prev = t; } };
+	const size_t rb = (size_t)ctx->nbins * ctx->tbytes;
+	int rc = reserve_permute(ctx, count);
+	if (rc) return rc;
+	// validate (a permutation of 0..count-1) while narrowing to 32 bits
+	int32_t *h = (int32_t *)ctx->h_pinned;
+	{
+		std::vector<uint8_t> seen((size_t)count, 0);
+		for (int64_t i = 0; i < count; i++) {
+			const int64_t o = old_of_new[i];
+			MC_REQUIRE(o >= 0 && o < count && !seen[(size_t)o], MC_ERR_ARG, "mc_permute_rows: old_of_new is not a permutation of 0..count-1 (entry %lld)", (long long)i);
+			seen[(size_t)o] = 1;
+			h[i] = (int32_t)o;
+		}
+	}
+	lap("buffers + validation");
+	int32_t *d_perm = (int32_t *)ctx->d_scratch;
+	MC_CUDA(cudaMemcpyAsync(d_perm, h, (size_t)count * 4, cudaMemcpyHostToDevice, ctx->stream));
+	rc = mc_launch_permute_rows(ctx, d_perm, count, n_alive, ctx->d_hist_tmp, ctx->d_aux_tmp);
+	if (rc) return rc;
+	MC_CUDA(cudaMemcpyAsync(ctx->d_hist, ctx->d_hist_tmp, (size_t)count * rb, cudaMemcpyDeviceToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(ctx->d_aux, ctx->d_aux_tmp, (size_t)count * sizeof(McRowAux), cudaMemcpyDeviceToDevice, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(ctx->d_marks, 0, (size_t)count, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));   // the pinned staging buffer is reused by later calls
+	lap("upload + gather + copy");
+	ctx->rows_permuted = true;
+	ctx->members_n = 0;
+	return MC_OK;
+}
+
 extern "C" int mc_update_centers(mc_ctx *ctx, const int64_t *center_rows, int64_t ncenters, const int64_t *cand_rows,
                                  int64_t ncand, const int64_t *cand_begin, const int64_t *cand_end, int64_t *next_rows) {
 	MC_NEED_HIST(ctx);
@@ -884,6 +949,7 @@ extern "C" int mc_update_centers(mc_ctx *ctx, const int64_t *center_rows, int64_
 extern "C" int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m, int32_t *score, int32_t *alen, int32_t *matches) {
 	MC_REQUIRE(ctx && ctx->have_seq, MC_ERR_STATE, "mc_align_pairs: load sequences first");
 	MC_REQUIRE(a && b && score && alen && matches && m >= 0, MC_ERR_ARG, "mc_align_pairs: bad arguments");
+	MC_REQUIRE(!ctx->rows_permuted, MC_ERR_STATE, "mc_align_pairs: rows were re-numbered by mc_permute_rows; the sequences still use the original rows");
 	if (m == 0) return MC_OK;
 	const bool dbg = getenv("MC_DEBUG_TIMING") != nullptr;
 	auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };

@@ -134,6 +134,12 @@ struct mc_ctx {
 	int64_t aux_capacity = 0;
 	bool have_hist = false;
 
+	// staging for mc_permute_rows (allocated on first use, sized like the histograms)
+	void *d_hist_tmp = nullptr;
+	McRowAux *d_aux_tmp = nullptr;
+	size_t tmp_rows = 0;
+	bool rows_permuted = false;   // sequences (d_seq_off) still use the original rows
+
 	// marks of the last scan (the alive set lives in McRowAux::alive)
 	uint8_t *d_marks = nullptr;
 

@@ -375,3 +375,41 @@ int mc_launch_pair_list(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_de
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// mc_permute_rows: gather rows (histogram + constants) into a staging buffer, one warp per row
+// ---------------------------------------------------------------------------------------------
+__global__ void permute_rows_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ aux,
+                                    const int32_t *__restrict__ old_of_new, long long count, long long n_alive, int rb,
+                                    uint8_t *__restrict__ hist_out, McRowAux *__restrict__ aux_out) {
+	const int lane = threadIdx.x & 31;
+	const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+	for (long long i = warp; i < count; i += nwarps) {
+		const long long o = old_of_new[i];
+		const uint8_t *src = hist + (size_t)o * rb;
+		uint8_t *dst = hist_out + (size_t)i * rb;
+		if (rb >= 16) {
+			for (int c = lane; c < rb / 16; c += 32) reinterpret_cast<uint4 *>(dst)[c] = reinterpret_cast<const uint4 *>(src)[c];
+		} else {
+			for (int c = lane; c < rb / 4; c += 32) reinterpret_cast<uint32_t *>(dst)[c] = reinterpret_cast<const uint32_t *>(src)[c];
+		}
+		if (lane == 0) {
+			McRowAux a = aux[o];
+			a.alive = i < n_alive ? 1u : 0u;
+			aux_out[i] = a;
+		}
+	}
+}
+
+int mc_launch_permute_rows(mc_ctx *ctx, const int32_t *old_of_new_dev, int64_t count, int64_t n_alive, void *hist_out, void *aux_out) {
+	const int threads = 256;
+	int64_t blocks = (count * 32 + threads - 1) / threads;
+	if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
+	if (blocks < 1) blocks = 1;
+	permute_rows_kernel<<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->d_aux, old_of_new_dev, count, n_alive,
+	                                                              ctx->nbins * ctx->tbytes, (uint8_t *)hist_out, (McRowAux *)aux_out);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}

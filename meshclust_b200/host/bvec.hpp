@@ -214,6 +214,31 @@ public:
 		}
 	}
 
+	// Drop the removed entries for good and number the survivors 0, 1, 2, ... in iteration order
+	// (what assign_rows did at the start).  Appends, for every survivor in order, its previous row to
+	// `old_rows`: old_rows[new row] = old row.  Nothing observable changes: element i of a bin is the
+	// same point as before, only its row number differs.
+	void compact(std::vector<int64_t> &old_rows) {
+		int64_t next = (int64_t)old_rows.size();
+		for (size_t b = 0; b < data_.size(); b++) {
+			Bin &bin = data_[b];
+			row0_[b] = next;
+			size_t w = 0;
+			for (size_t j = 0; j < bin.items.size(); j++) {
+				if (!((bin.bits[j / 64] >> (j % 64)) & 1)) continue;
+				old_rows.push_back(bin.items[j].v);
+				bin.items[w] = bin.items[j];
+				bin.items[w].v = next++;
+				w++;
+			}
+			bin.items.resize(w);
+			bin.alive = w;
+			bin.bits.assign((w + 63) / 64, ~0ull);
+			if (w % 64) bin.bits.back() = (1ull << (w % 64)) - 1;
+		}
+		first_live_ = 0;
+	}
+
 	size_t nbins() const { return data_.size(); }
 
 private:

@@ -187,25 +187,58 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	const double t_sorts = st.lap();
 	int rounds = 0;
 
-	// :703-721 binary search with alignment, all pivots in lock step (each search is independent)
+	// :703-721 binary search with alignment, all pivots in lock step (each search is independent).
+	// One round of the reference is one alignment per pivot: 150 pairs cannot fill a GPU, and a
+	// search is a chain of ~log2(n/4) dependent rounds.  So every batch aligns, per pivot, all the
+	// positions the next SPEC rounds can reach (2^SPEC - 1 of them), and the rounds are then replayed
+	// from the answers exactly as the reference takes them; the unused answers are discarded.
+	constexpr int SPEC = 4;
 	std::vector<size_t> offset(np, (size_t)n / 4), pos(np, 2 * ((size_t)n / 4));
 	std::vector<char> active(np, 1);
 	for (size_t i = 0; i < np; i++) active[i] = offset[i] > 0;
 	for (;;) {
 		std::vector<Pair> q;
-		std::vector<size_t> who;
-		for (size_t i = 0; i < np; i++)
-			if (active[i]) { q.push_back({pivots[i], sorted[i][pos[i]]}); who.push_back(i); }
+		std::vector<char> reach;             // per node: will the search ever align it?
+		std::vector<size_t> first(np + 1, 0);
+		for (size_t i = 0; i < np; i++) {
+			first[i] = q.size();
+			if (!active[i]) continue;
+			// breadth-first over the decision tree: node 0 = current position; children of node t are
+			// 2t+1 (answer below the cutoff: pos - off) and 2t+2 (above: pos + off), off halving per level
+			std::vector<size_t> npos((size_t)(1 << SPEC) - 1), noff((size_t)(1 << SPEC) - 1);
+			npos[0] = pos[i]; noff[0] = offset[i];
+			for (size_t t = 0; t < npos.size(); t++) {
+				const bool reachable = noff[t] > 0;   // offset 0 ends the search before this alignment
+				q.push_back({pivots[i], reachable ? sorted[i][npos[t]] : pivots[i]});
+				reach.push_back(reachable ? 1 : 0);
+				if (2 * t + 2 < npos.size()) {
+					npos[2 * t + 1] = reachable ? npos[t] - noff[t] : 0; noff[2 * t + 1] = reachable ? noff[t] / 2 : 0;
+					npos[2 * t + 2] = reachable ? npos[t] + noff[t] : 0; noff[2 * t + 2] = reachable ? noff[t] / 2 : 0;
+				}
+			}
+		}
+		first[np] = q.size();
 		if (q.empty()) break;
-		const std::vector<double> algn = align_ids(c, q);
+		// unreachable placeholders are not aligned
+		std::vector<Pair> real;
+		std::vector<size_t> where(q.size(), (size_t)-1);
+		for (size_t t = 0; t < q.size(); t++)
+			if (reach[t]) { where[t] = real.size(); real.push_back(q[t]); }
+		const std::vector<double> algn = align_ids(c, real);
 		rounds++;
-		for (size_t t = 0; t < who.size(); t++) {
-			const size_t i = who[t];
-			if (algn[t] < cutoff) pos[i] -= offset[i];
-			else if (algn[t] > cutoff) pos[i] += offset[i];
-			else { active[i] = 0; continue; }   // break: offset is not halved, pos stays
-			offset[i] /= 2;
-			if (offset[i] == 0) active[i] = 0;
+		for (size_t i = 0; i < np; i++) {
+			if (!active[i]) continue;
+			size_t t = 0;
+			for (int level = 0; level < SPEC && active[i]; level++) {
+				const size_t slot = first[i] + t;
+				// (an unreachable node is never visited: offset 0 deactivates the search one level above it)
+				const double a = algn[where[slot]];
+				if (a < cutoff) { pos[i] -= offset[i]; t = 2 * t + 1; }
+				else if (a > cutoff) { pos[i] += offset[i]; t = 2 * t + 2; }
+				else { active[i] = 0; break; }   // break: offset is not halved, pos stays
+				offset[i] /= 2;
+				if (offset[i] == 0) active[i] = 0;
+			}
 		}
 	}
 
@@ -566,6 +599,10 @@ void mean_shift(Ctx &c, BVec &bv) {
 	}
 	const bool sharded = world > 1 && !c.model.align;
 	for (int r = 0; r < (sharded ? world : 1); r++) GPU(mc_alive_reset(c.ranks[r]));
+	const int64_t compact_min = getenv("MC_COMPACT_MIN_ROWS") ? atoll(getenv("MC_COMPACT_MIN_ROWS")) : 32768;
+	if (!c.model.align && ds.n >= compact_min)   // staging for the row compactions: allocated before the clock of Phase A starts
+		for (int r = 0; r < (sharded ? world : 1); r++) GPU(mc_reserve_permute(c.ranks[r]));
+	tm.lap();
 
 	auto kill_row = [&](int64_t row) {
 		for (int r = 0; r < (sharded ? world : 1); r++) GPU(mc_alive_kill(c.ranks[r], &row, 1));
@@ -578,7 +615,41 @@ void mean_shift(Ctx &c, BVec &bv) {
 	std::vector<uint8_t> marks;
 	std::vector<int64_t> marked_rows((size_t)ds.n);
 	int64_t scans = 0, evals = 0;
+	// Row compaction: once at most 60 % of the rows the scans still stream are alive, the alive rows
+	// are moved to the front (same order) on the GPU(s) and every row number the host holds is
+	// translated.  Scans then read alive rows only; nothing observable depends on the numbering.
+	int64_t prefix = ds.n;                      // rows [0, prefix) may still be alive
+	int64_t n_alive = (int64_t)bv.size();
+	int compactions = 0;
+	double compact_host_s = 0, compact_gpu_s = 0;
+	auto compact_rows = [&](int64_t &seed) {
+		Timer tc;
+		std::vector<int64_t> old_of_new;
+		old_of_new.reserve((size_t)prefix);
+		bv.compact(old_of_new);                 // survivors, in iteration order
+		const int64_t alive_now = (int64_t)old_of_new.size();
+		std::vector<int64_t> new_of_old((size_t)prefix, -1);
+		for (int64_t i = 0; i < alive_now; i++) new_of_old[(size_t)old_of_new[(size_t)i]] = i;
+		for (int64_t o = 0; o < prefix; o++)    // then the rows that have left, in their old order
+			if (new_of_old[(size_t)o] < 0) { new_of_old[(size_t)o] = (int64_t)old_of_new.size(); old_of_new.push_back(o); }
+		compact_host_s += tc.lap();
+		for (int r = 0; r < (sharded ? world : 1); r++) GPU(mc_permute_rows(c.ranks[r], old_of_new.data(), prefix, alive_now));
+		compact_gpu_s += tc.lap();
+		auto tr = [&](int64_t &row) { if (row >= 0 && row < prefix) row = new_of_old[(size_t)row]; };
+#pragma omp parallel for schedule(dynamic, 16)
+		for (long ci = 0; ci < (long)part.size(); ci++) { Cluster &cl = part[(size_t)ci]; tr(cl.center_row); for (int64_t &r : cl.rows) tr(r); }
+		tr(seed);
+		std::vector<int64_t> ids((size_t)prefix);
+#pragma omp parallel for schedule(static)
+		for (int64_t i = 0; i < prefix; i++) ids[(size_t)i] = c.ds.id_of_row[(size_t)old_of_new[(size_t)i]];
+#pragma omp parallel for schedule(static)
+		for (int64_t i = 0; i < prefix; i++) { c.ds.id_of_row[(size_t)i] = ids[(size_t)i]; c.ds.row_of_id[(size_t)ids[(size_t)i]] = i; }
+		prefix = alive_now;
+		compactions++;
+		compact_host_s += tc.lap();
+	};
 	while (last >= 0) {
+		if (!c.model.align && prefix >= compact_min && n_alive * 5 <= prefix * 3) compact_rows(last);
 		std::vector<int64_t> current{last};
 		bool is_min = false, first_mean = true;
 		int64_t next_seed = -1;
@@ -612,7 +683,7 @@ void mean_shift(Ctx &c, BVec &bv) {
 				// no close point left: the arg-max of f0 becomes the next seed (or the first point)
 				if (res.best_row < 0) next_seed = bv.pop();
 				else { next_seed = res.best_row; bv.erase_row(res.best_row); }
-				if (next_seed >= 0) kill_row(next_seed);
+				if (next_seed >= 0) { kill_row(next_seed); n_alive--; }
 			} else if (c.model.align) {
 				const size_t prev = current.size();
 				bv.remove_marked(bounds.first.bin, bounds.second.bin,
@@ -624,6 +695,7 @@ void mean_shift(Ctx &c, BVec &bv) {
 				last = nearest;
 			} else {
 				bv.remove_rows(marked_rows.data(), (size_t)res.n_pos);
+				n_alive -= res.n_pos;
 				current.insert(current.end(), marked_rows.begin(), marked_rows.begin() + res.n_pos);
 				first_mean = false;
 				last = nearest;
@@ -635,7 +707,7 @@ void mean_shift(Ctx &c, BVec &bv) {
 		part.push_back(std::move(cl));
 		last = next_seed;
 	}
-	printf("Accumulation: %zu clusters, %lld scans, %lld evals  [%.2fs]\n", part.size(), (long long)scans, (long long)evals, tm.lap());
+	printf("Accumulation: %zu clusters, %lld scans, %lld evals, %d row compactions (host %.3fs, gpu calls %.3fs)  [%.2fs]\n", part.size(), (long long)scans, (long long)evals, compactions, compact_host_s, compact_gpu_s, tm.lap());
 
 	// ---------------- Phase B: update + merge (ClusterFactory.cpp:733-753) -----------------------
 	int iters_run = 0;

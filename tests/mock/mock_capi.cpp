@@ -233,6 +233,20 @@ int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_t center, i
 	for (int r = 1; r < world; r++) ctxs[r]->alive = ctxs[0]->alive;
 	return rc;
 }
+int mc_reserve_permute(mc_ctx *) { return MC_OK; }
+int mc_permute_rows(mc_ctx *c, const int64_t *old_of_new, int64_t count, int64_t n_alive) {
+	const size_t rb = (size_t)c->nbins * c->tbytes;
+	std::vector<uint8_t> h((size_t)count * rb);
+	std::vector<uint64_t> l((size_t)count);
+	for (int64_t i = 0; i < count; i++) {
+		memcpy(h.data() + (size_t)i * rb, c->hist.data() + (size_t)old_of_new[i] * rb, rb);
+		l[(size_t)i] = c->len[(size_t)old_of_new[i]];
+	}
+	memcpy(c->hist.data(), h.data(), h.size());
+	for (int64_t i = 0; i < count; i++) { c->len[(size_t)i] = l[(size_t)i]; c->alive[(size_t)i] = i < n_alive; }
+	c->members.clear();
+	return MC_OK;
+}
 int mc_update_centers(mc_ctx *c, const int64_t *centers, int64_t nc, const int64_t *cand, int64_t, const int64_t *cb, const int64_t *ce, int64_t *next) {
 #pragma omp parallel for schedule(dynamic)
 	for (int64_t j = 0; j < nc; j++) {

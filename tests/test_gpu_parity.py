@@ -513,6 +513,45 @@ def test_accumulate_step_sharded_equals_single(ctx, world, k, n):
             c.close()
 
 
+@pytest.mark.parametrize("dtype,k,n", [(np.uint8, 4, 3000), (np.uint16, 3, 1000), (np.uint8, 1, 500)])
+def test_permute_rows(ctx, dtype, k, n):
+    """mc_permute_rows re-numbers a prefix of the rows: histograms and constants follow, alive flags are
+    set from n_alive, rows beyond the prefix stay, scans give the same answers in the new numbering"""
+    from meshclust_b200 import api
+    rng = np.random.default_rng(900 + k)
+    nb = 4 ** k
+    H = _rand_hists(rng, n, nb, dtype, 255 if dtype == np.uint8 else 2000, clusters=4)
+    lens = (800 + rng.integers(0, 200, n)).astype(np.uint64)
+    mins, maxs, w = _model(3)
+    maxs[2] = 4.0 * nb
+    ctx.load_histograms(H, lens, k)
+    ctx.set_model(mins, maxs, w, 3)
+    count, n_alive = n - 37, n // 2
+    perm = rng.permutation(count)
+    ctx.permute_rows(perm, n_alive)
+    want = H.copy()
+    want[:count] = H[perm]
+    wl = lens.copy()
+    wl[:count] = lens[perm]
+    assert np.array_equal(ctx.copy_histograms(), want)
+    ln, mg, sq = ctx.copy_point_stats()
+    assert np.array_equal(ln, wl)
+    assert np.array_equal(mg, want.astype(np.uint64).sum(1))
+    assert np.array_equal(sq, (want.astype(np.uint64) ** 2).sum(1))
+    # alive: rows < n_alive and the untouched tail (still alive from the load)
+    res, marks = ctx.scan(0, 0, n - 1)
+    assert res.n_eval == n_alive + (n - count)
+    # same scan on a fresh context holding the permuted data, with the same rows alive
+    with api.Context(0) as c2:
+        c2.load_histograms(want, wl, k)
+        c2.set_model(mins, maxs, w, 3)
+        c2.alive_kill(np.arange(n_alive, count))
+        res2, marks2 = c2.scan(0, 0, n - 1)
+    assert res.as_tuple() == res2.as_tuple() and np.array_equal(marks, marks2)
+    with pytest.raises(api.McError):
+        ctx.permute_rows(np.zeros(5, np.int64), 2)      # not a permutation
+
+
 @pytest.mark.parametrize("k", [3, 4, 5])
 def test_update_centers_vs_oracle(ctx, oracle, k):
     rng = np.random.default_rng(80 + k)

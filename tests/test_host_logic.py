@@ -31,10 +31,11 @@ def mock_cli():
     return MOCK_BIN
 
 
-def _run(binary, name, tmp_path, extra=()):
+def _run(binary, name, tmp_path, extra=(), env=None):
     paths, args = H.make_inputs(name, str(tmp_path))
     out = os.path.join(str(tmp_path), "out.clstr")
-    r = subprocess.run([binary, *paths, *args, *extra, "--output", out], capture_output=True, text=True)
+    r = subprocess.run([binary, *paths, *args, *extra, "--output", out], capture_output=True, text=True,
+                       env=None if env is None else {**os.environ, **env})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return open(out, "rb").read(), r.stdout
 
@@ -42,6 +43,15 @@ def _run(binary, name, tmp_path, extra=()):
 @pytest.mark.parametrize("name", list(H.CASES))
 def test_clstr_identical_to_reference_cpu(mock_cli, tmp_path, name):
     got, _ = _run(mock_cli, name, tmp_path)
+    assert got == H.read_golden(name)
+
+
+@pytest.mark.parametrize("name", ["A", "B", "D", "E", "F"])
+def test_clstr_identical_with_row_compaction_cpu(mock_cli, tmp_path, name):
+    # rows that have joined a cluster are moved behind the alive ones as Phase A proceeds (here: from
+    # 16 rows on, i.e. many times per run); the CLSTR file must not change
+    got, log = _run(mock_cli, name, tmp_path, env={"MC_COMPACT_MIN_ROWS": "16"})
+    assert " 0 row compactions" not in log and "row compactions" in log
     assert got == H.read_golden(name)
 
 
@@ -76,4 +86,14 @@ def test_clstr_identical_with_sharded_phase_a(built_lib, tmp_path, name, gpus):
     cli = build.build_cli()
     got, log = _run(cli, name, tmp_path, extra=("--gpus", str(gpus)))
     assert "peer inboxes connected" in log
+    assert got == H.read_golden(name), log[-1500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,gpus", [("A", 1), ("B", 1), ("c1_full", 1), ("E", 2), ("F", 3)])
+def test_clstr_identical_with_row_compaction_gpu(built_lib, tmp_path, name, gpus):
+    from meshclust_b200 import build
+    cli = build.build_cli()
+    got, log = _run(cli, name, tmp_path, extra=("--gpus", str(gpus)), env={"MC_COMPACT_MIN_ROWS": "16"})
+    assert " 0 row compactions" not in log and "row compactions" in log
     assert got == H.read_golden(name), log[-1500:]
