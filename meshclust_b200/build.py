@@ -16,9 +16,12 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 HOST = os.path.join(PKG, "host")
-LIB = os.path.join(PKG, "libmeshclust_b200.so")
+# MC_LIB_VARIANT=name + MC_EXTRA_NVCC_FLAGS="-D..." build an experimental variant next to the product
+# library (libmeshclust_b200_<name>.so, selected at run time with MESHCLUST_B200_LIB)
+_VARIANT = os.environ.get("MC_LIB_VARIANT", "")
+LIB = os.path.join(PKG, f"libmeshclust_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 BIN = os.path.join(ROOT, "bin", "meshclust")
-OBJ = os.path.join(PKG, "_build")
+OBJ = os.path.join(PKG, "_build" + ("_" + _VARIANT if _VARIANT else ""))
 
 CU_SOURCES = ["capi.cu", "kmer_hist.cu", "pair_kernels.cu", "scan_tma.cu", "center_mean.cu", "nw_identity.cu", "peer_exchange.cu"]
 NVCC_FLAGS = [
@@ -27,7 +30,7 @@ NVCC_FLAGS = [
     "-fmad=false",                 # FP64 parity: the only fused ops are the explicit fma() calls
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("MC_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:
@@ -111,7 +114,7 @@ def build_cli(force: bool = False) -> str | None:
 
 def build_all(force: bool = False, verbose: bool = False):
     lib = build_lib(force, verbose)
-    cli = build_cli(force)
+    cli = None if _VARIANT else build_cli(force)
     return lib, cli
 
 

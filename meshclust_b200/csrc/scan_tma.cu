@@ -2,7 +2,7 @@
 // (bvec.cpp:290-317) for ONE center against every row of an inclusive row range.
 //
 // HBM-bound streaming kernel, warp-specialised and persistent (one CTA per SM):
-//   * warp 0 = producer: one elected lane feeds a ring of shared-memory stages with 1-D TMA bulk
+//   * warp 0 = producer: one lane per ring slot feeds the shared-memory stages with 1-D TMA bulk
 //     copies (cp.async.bulk ... mbarrier::complete_tx): per stage one copy of TR contiguous
 //     histogram rows and one of their 32-byte McRowAux records.  The ring is as deep as shared
 //     memory allows (up to ~220 KB in flight per SM), so HBM latency never reaches the math.
@@ -66,6 +66,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 constexpr int TSCAN_MAX_CONSUMERS = 24;   // small rows: one tile per warp hides the FP64 epilogue latency of short scans
 constexpr int TSCAN_MAX_STAGES = 32;
 constexpr int TSCAN_SMEM_BUDGET = 216 * 1024;
+// Narrow rows make short scans (C2 shape: 29 MB, ~4 us of HBM time per launch), where what matters is
+// how soon the NEXT scan of the stream has its tiles in flight.  With half the shared memory and half
+// the warps per CTA, two CTAs fit an SM: the next launch (programmatic dependent launch) becomes
+// resident and prefetches while this one still runs its epilogue.
+#ifndef MC_SCAN_SMALL_CTAS_PER_SM
+#define MC_SCAN_SMALL_CTAS_PER_SM 2
+#endif
+constexpr int TSCAN_SMALL_ROW = 256;
 
 // A stage holds one consumer tile: RT consecutive rows + their McRowAux records.  RT = 32 (one row
 // per lane in the epilogue) while that fits 32 KB, fewer for very wide rows (lanes >= RT idle in
@@ -77,9 +85,10 @@ struct TileCfg {
 	static constexpr int ROW_BYTES = RT * RB;
 	static constexpr int AUX_BYTES = RT * 32;
 	static constexpr int STAGE_BYTES = ((ROW_BYTES + AUX_BYTES + 127) / 128) * 128;
-	static constexpr int NS_RAW = TSCAN_SMEM_BUDGET / STAGE_BYTES;
+	static constexpr int CTAS_PER_SM = RB <= TSCAN_SMALL_ROW ? MC_SCAN_SMALL_CTAS_PER_SM : 1;
+	static constexpr int NS_RAW = (TSCAN_SMEM_BUDGET / CTAS_PER_SM) / STAGE_BYTES;
 	static constexpr int NS_CAP = NS_RAW > TSCAN_MAX_STAGES ? TSCAN_MAX_STAGES : NS_RAW;
-	static constexpr int MAXC = RB <= 256 ? TSCAN_MAX_CONSUMERS : 16;
+	static constexpr int MAXC = RB <= TSCAN_SMALL_ROW ? TSCAN_MAX_CONSUMERS / CTAS_PER_SM : 16;
 	static constexpr int NCW = NS_CAP > MAXC ? MAXC : NS_CAP;   // active consumer warps
 	static constexpr int D = NS_CAP / NCW;                                                   // ring depth per consumer
 	static constexpr int NS = NCW * D;
@@ -87,8 +96,9 @@ struct TileCfg {
 };
 
 #ifdef MC_SCAN_TRACE
-__device__ unsigned long long g_scan_trace[148 * 32 * 8];
-#define TRACE(slot) do { if (lane == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_scan_trace[(blockIdx.x * 32 + wib) * 8 + (slot)] = _t; } } while (0)
+// timelines of 8 consecutive launches (keyed by the result slot the launch writes to)
+__device__ unsigned long long g_scan_trace[8 * 148 * 32 * 8];
+#define TRACE(slot) do { if (lane == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); g_scan_trace[((((unsigned long long)partials / (MC_SCAN_PARTS * 32)) & 7) * 148 * 32 + blockIdx.x * 32 + wib) * 8 + (slot)] = _t; } } while (0)
 #else
 #define TRACE(slot) do {} while (0)
 #endif
@@ -119,7 +129,7 @@ __device__ __forceinline__ void peer_store_words(const McPeerPush &push, int cta
 }
 
 template <int TB, int RB, int PUSH>
-__global__ void __launch_bounds__(32 * (1 + TileCfg<RB>::NCW), 1)
+__global__ void __launch_bounds__(32 * (1 + TileCfg<RB>::NCW), TileCfg<RB>::CTAS_PER_SM)
 scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, uint8_t *__restrict__ marks,
                 long long lo, long long hi, long long nrows_total, long long center_row, McModel model,
                 int remove_marked, ScanPartial *__restrict__ partials, PushArg<PUSH> push_arg) {
@@ -171,9 +181,11 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		// lane l owns ring slot l (consumer l / D, ring position l % D) and issues every bulk copy
 		// that lands there, in order.  Slots fill in parallel (issue cost spread over the warp) while
 		// one lane never runs more than one phase ahead of its slot's barriers.
+		// Everything the producer copies is immutable while scans run (histograms, and the constants
+		// len / mag / sum p^2 of McRowAux; the alive word that travels along is ignored), so it never
+		// waits for the previous scan of the stream: its tiles are in flight while that scan finishes.
 		if (lane < T::NS) {
 			const int w = lane / T::D;
-			bool first = true;
 			for (long long u = lane % T::D; ; u += T::D) {
 				const long long jj = u * T::NCW + w;          // u-th tile of consumer w
 				if (jj >= nmine) break;
@@ -184,15 +196,9 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 				if (nr > T::RT) nr = T::RT;
 				uint8_t *dst = smem + (size_t)lane * T::STAGE_BYTES;
 				mbar_expect_tx(&full_bar[lane], (uint32_t)(nr * RB + nr * 32));
-				// histogram rows are immutable: their copy may start while the previous scan of the
-				// stream is still finishing; the constants carry its alive flags, so they wait for it
 				tma_bulk_g2s(dst, hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[lane]);
-				if (first) { asm volatile("griddepcontrol.wait;" ::: "memory"); first = false; }
 				tma_bulk_g2s(dst + T::ROW_BYTES, aux + r0, (uint32_t)(nr * 32), &full_bar[lane]);
 			}
-			if (first) asm volatile("griddepcontrol.wait;" ::: "memory");
-		} else {
-			asm volatile("griddepcontrol.wait;" ::: "memory");
 		}
 	} else if (wib - 1 < T::NCW) {
 		// ===================== consumers =====================
@@ -202,11 +208,40 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		CenterRegs<RB> cen;
 		cen.load(crow, r);
 		const uint64_t lq = aux[center_row].len, mq = aux[center_row].mag, sq = aux[center_row].sq;
-		asm volatile("griddepcontrol.wait;" ::: "memory");   // before the first global write of this warp
+
+		// What depends on the previous scan of the stream is only WHICH rows are still alive (and the
+		// right to write marks / alive flags).  The reductions and the FP64 feature + GLM epilogue of a
+		// warp's first PRE tiles therefore run before griddepcontrol.wait -- while the previous scan is
+		// still finishing -- and only their application (alive test, counts, arg-max, marks) waits.
+		constexpr int PRE = 2;
+		double pre_f0_0 = 0.0, pre_f0_1 = 0.0;
+		unsigned pre_flag_0 = 0, pre_flag_1 = 0;
+		int npre = 0;
+		bool waited = false;
+		auto row_of_tile = [&](long long uu) { return (tf + (my_first + ((long long)cw + uu * T::NCW) * gridDim.x) * world) * T::RT + lane; };
+		auto apply = [&](long long row, double f0, unsigned flag_in) {
+			if (lane < T::RT && row >= lo && row <= hi) {
+				unsigned flag = 0;
+				if (__ldcg(&aux[row].alive)) {
+					flag = flag_in;
+					mine.n_eval++;
+					mine.n_pos += flag;
+					if (f0 > mine.best_f0) { mine.best_f0 = f0; mine.best_row = row; }
+					if (flag && remove_marked) aux[row].alive = 0;
+				}
+				marks[row] = (uint8_t)flag;
+			}
+		};
+		auto dependency_wait = [&]() {
+			asm volatile("griddepcontrol.wait;" ::: "memory");
+			waited = true;
+			if (npre > 0) apply(row_of_tile(0), pre_f0_0, pre_flag_0);
+			if (npre > 1) apply(row_of_tile(1), pre_f0_1, pre_flag_1);
+		};
+
 		long long u = 0;
 		for (long long jj = cw; jj < nmine; jj += T::NCW, u++) {
-			const long long row0 = (tf + (my_first + jj * gridDim.x) * world) * T::RT;
-			const long long row_mine = row0 + lane;
+			const long long row_mine = row_of_tile(u);
 			const bool have_row = lane < T::RT && row_mine >= lo && row_mine <= hi;
 			const int slot = cw * T::D + (int)(u % T::D);
 			if (u == 0) TRACE(2);
@@ -240,12 +275,23 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			if (lane == 0) mbar_arrive(&empty_bar[slot]);   // the stage can be refilled during the epilogue
 			const PairAcc<TB> tot = mc_transpose_reduce<C::LPP>(part, r);
 			if (u == 0) TRACE(4);
-			if (have_row) {
+			if (!waited && u >= PRE) dependency_wait();
+			if (!waited) {
+				// alive is not known yet: evaluate the row regardless, apply after the wait
+				double f0 = 0.0;
 				unsigned flag = 0;
-				if (my_aux.alive) {
-					const uint64_t S = tot.summin(my_aux.mag, mq);
+				if (have_row) {
+					double sum;
+					mc_scan_epilogue<TB>(model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
+					flag = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1u : 0u;
+				}
+				if (u == 0) { pre_f0_0 = f0; pre_flag_0 = flag; } else { pre_f0_1 = f0; pre_flag_1 = flag; }
+				npre = (int)u + 1;
+			} else if (have_row) {
+				unsigned flag = 0;
+				if (__ldcg(&aux[row_mine].alive)) {   // dead rows skip the epilogue
 					double f0, sum;
-					mc_scan_epilogue<TB>(model, S, tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
+					mc_scan_epilogue<TB>(model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
 					flag = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1u : 0u;
 					mine.n_eval++;
 					mine.n_pos += flag;
@@ -255,6 +301,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 				marks[row_mine] = (uint8_t)flag;
 			}
 		}
+		if (!waited) dependency_wait();
 #pragma unroll
 		for (int o = 16; o; o >>= 1) {
 			ScanPartial other;
@@ -271,6 +318,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 	TRACE(6);
 	// per-CTA partial; the (tiny) fold over <= 148 partials is left to whoever reads the result
 	if (wib == 0) {
+		asm volatile("griddepcontrol.wait;" ::: "memory");   // returns at once: the consumers of this CTA have passed it
 		ScanPartial b;
 		b.n_eval = 0; b.n_pos = 0; b.best_row = -1; b.best_f0 = -1.0;
 		if (lane < T::NCW) b = warp_part[lane];

@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-python tools/gen_config.py c4 /tmp/c4.fa > gpurun_out/gen.log 2>&1
-( time MC_DEBUG_TIMING=1 bin/meshclust /tmp/c4.fa --id 0.90 --kmer 5 --output /tmp/c4_a.clstr ) 2>&1 | grep -v "mc_align\|mc_ctx_create" > gpurun_out/cli_c4_a.log
-( time bin/meshclust /tmp/c4.fa --id 0.90 --kmer 5 --output /tmp/c4_a.clstr ) > gpurun_out/cli_c4_a2.log 2>&1
-( time MC_COMPACT_MIN_ROWS=999999999 bin/meshclust /tmp/c4.fa --id 0.90 --kmer 5 --output /tmp/c4_b.clstr ) > gpurun_out/cli_c4_b.log 2>&1
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+python tools/time_scan.py > gpurun_out/time_scan_pre.log 2>&1
+python tools/trace_scan.py c2 > gpurun_out/trace_pre_c2.log 2>&1
+python bench.py --steps 50 --warmup 5 --no-extra > gpurun_out/bench_pre.json 2> gpurun_out/bench_pre.err
