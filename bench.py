@@ -5,7 +5,9 @@ C2 workload (100 k synthetic 1.5 kb 16S-like sequences, --id 0.97 --kmer 4), one
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A "step" is one Trainer::get_close-shaped pass (1 center x all n points: every live feature + the
-GLM decision + argmax/mark reduction) for each of S centers, i.e. S launches of the scan kernel.
+GLM decision + argmax/mark reduction) for each of S centers.  The S passes of a step remove nothing,
+so they are independent and mc_scan_enqueue_many sends them as one launch of the scan kernel
+(blockIdx.y = center); `dependent_chain` in the JSON line is the same work as S chained launches.
   value  : evals/s with the histograms resident in HBM.  The batch is stored R times (R*29 MB >
            2x the 126 MB L2) and consecutive launches rotate through the replicas, so every launch
            streams its rows from HBM ("inputs larger than L2").
@@ -415,23 +417,50 @@ def main():
     evals_per_step = S * n * world
     value = evals_per_step / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (scan): per-launch time from the CUDA events
+    # ---- roofline of the dominant kernel (scan): per-launch time from the CUDA events.  The S scans of a
+    # step are independent (nothing is removed), so one launch carries all of them (blockIdx.y = scan):
+    # bytes per launch = S x n x (4^k + 33)
     peak, peak_src = measured_peak()
-    bytes_per_launch = n * (nbins + 33)
-    launch_us = dev_ms * 1e3 / (args.steps * S)
+    scans_per_launch = S if exchange != "nccl_allgather" else 1
+    bytes_per_launch = scans_per_launch * n * (nbins + 33)
+    launch_us = dev_ms * 1e3 / (args.steps * S / scans_per_launch)
     achieved = bytes_per_launch / (launch_us * 1e-6) / 1e9
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel and shape from the
-    # committed `ncu --set full` capture (profiles/scan_traffic.json), not measured in this run
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel and shape from the committed
+    # `ncu --set full` capture (profiles/scan_traffic.json, per scan), not measured in this run
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))[f"c2_{nbins}"]["dram_bytes_per_launch"]
+        traffic = scans_per_launch * json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))[f"c2_{nbins}"]["dram_bytes_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "kernel": f"scan_tma_kernel<1,{nbins}>", "launch_us": round(launch_us, 3),
+                "scans_per_launch": scans_per_launch, "us_per_scan": round(launch_us / scans_per_launch, 3),
                 "algorithmic_bytes_per_launch": bytes_per_launch,
-                "note": "back-to-back launches on one stream (programmatic dependent launch); launch_us = CUDA-event time / launches"}
+                "note": "launch_us = CUDA-event time of the timed region / kernel launches in it; the scans of a step share a launch"}
+
+    # the same scans as a dependent chain (what accumulate() issues: each scan may remove rows the next
+    # one must not see): one launch per scan, chained by programmatic dependent launch
+    chain = None
+    if world == 1:
+        os.environ["MC_SCAN_NO_BATCH"] = "1"   # mc_scan_enqueue_many: one launch per scan (read by the library per call)
+        for rep in range(2):
+            cr, lo, hi, _, _ = step_args(rep)
+            ctx.scan_enqueue_many(cr, lo, hi, False, 200)
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        reps_chain = 30
+        for rep in range(reps_chain):
+            cr, lo, hi, _, _ = step_args(args.warmup + rep % max(args.steps, 1))
+            ctx.scan_enqueue_many(cr, lo, hi, False, 200)
+        e1.record(stream)
+        ctx.sync()
+        del os.environ["MC_SCAN_NO_BATCH"]
+        us = e0.elapsed_time(e1) * 1e3 / (reps_chain * S)
+        chain = {"us_per_scan": round(us, 3), "evals_per_s": n / (us * 1e-6), "achieved_GBs": round(n * (nbins + 33) / (us * 1e-6) / 1e9, 1),
+                 "frac_of_peak": round(n * (nbins + 33) / (us * 1e-6) / 1e9 / peak, 4),
+                 "note": "one launch per scan, programmatic dependent launch"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -441,6 +470,8 @@ def main():
                       "l2": f"inputs larger than L2: {R} replicas of the batch ({R * n * row_bytes / 1e6:.0f} MB), launches rotate through them",
                       "model": "4 features, bounds from 3000 sampled pairs, least-squares GLM", "parallelism": f"points sharded x{world}", "exchange": exchange},
            "clocks": clocks, "gpu_launches": int(gpu_launches), "roofline": roofline}
+    if chain is not None:
+        out["dependent_chain"] = chain
 
     if rank == 0:
         # ---- e2e through the host-buffer C-ABI call: pinned host histograms in, marks + summaries out

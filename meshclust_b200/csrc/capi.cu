@@ -603,6 +603,30 @@ extern "C" int mc_scan_fold_dev(mc_ctx *ctx, int slot0, int nslots, mc_scan_resu
 extern "C" int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo, const int64_t *hi,
                                     int count, int remove_marked, int slot0) {
 	MC_REQUIRE(center_rows && lo && hi && count > 0, MC_ERR_ARG, "mc_scan_enqueue_many: bad arguments");
+	if (remove_marked == 0 && count > 1 && ctx && ctx->have_hist && ctx->tbytes * ctx->nbins >= 16 && !getenv("MC_SCAN_DIRECT") && !getenv("MC_SCAN_NO_BATCH")) {
+		// scans that remove nothing are independent of each other: up to MC_SCAN_BATCH of them share one
+		// launch (blockIdx.y = scan), so no launch latency sits between them
+		MC_NEED_HIST(ctx);
+		MC_NEED_MODEL(ctx);
+		MC_REQUIRE(slot0 >= 0 && slot0 + count <= MC_SCAN_SLOTS, MC_ERR_ARG, "slot range invalid");
+		int rc = ensure_scan_slots(ctx);
+		if (rc) return rc;
+		for (int i0 = 0; i0 < count; i0 += MC_SCAN_BATCH) {
+			const int m = std::min(MC_SCAN_BATCH, count - i0);
+			McScanReq req[MC_SCAN_BATCH];
+			for (int i = 0; i < m; i++) {
+				const int64_t c = center_rows[i0 + i], l = lo[i0 + i], h = hi[i0 + i];
+				MC_REQUIRE(c >= 0 && c < ctx->n, MC_ERR_ARG, "center row out of range");
+				MC_REQUIRE(l >= 0 && h < ctx->n && l <= h, MC_ERR_ARG, "scan range [%lld,%lld] invalid", (long long)l, (long long)h);
+				req[i].lo = l; req[i].hi = h; req[i].center_row = c;
+				req[i].partials_dev = (uint8_t *)ctx->d_scan_slots + (size_t)(slot0 + i0 + i) * MC_SCAN_PARTS * sizeof(mc_scan_result);
+			}
+			rc = mc_launch_scan_batch(ctx, req, m, 0, &ctx->slot_nparts[slot0 + i0], nullptr);
+			if (rc == MC_ERR_UNSUPPORTED) break;   // shape only the direct-load kernel handles: one launch per scan below
+			if (rc) return rc;
+			if (i0 + m >= count) return MC_OK;
+		}
+	}
 	for (int i = 0; i < count; i++) {
 		const int rc = mc_scan_enqueue(ctx, center_rows[i], lo[i], hi[i], remove_marked, slot0 + i);
 		if (rc) return rc;

@@ -11,6 +11,12 @@
 #define MC_NUM_SMS_FALLBACK 148
 #define MC_FULL_MASK 0xffffffffu
 #define MC_SCAN_PARTS 160   // per-scan partial records (>= SM count)
+#define MC_SCAN_BATCH 16    // independent scans one launch can carry
+
+struct McScanReq {          // one scan of a batch launch (host side)
+	long long lo, hi, center_row;
+	void *partials_dev;
+};
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing (no exceptions across the C-ABI)
@@ -176,6 +182,7 @@ struct mc_ctx {
 };
 
 void mc_comm_destroy(mc_ctx *ctx);
+int mc_launch_scan_batch(mc_ctx *ctx, const McScanReq *req, int count, int remove_marked, int *nparts_out, const struct McPeerPush *push);
 int mc_ensure_scratch(mc_ctx *ctx, size_t bytes);
 int mc_ensure_pinned(mc_ctx *ctx, size_t bytes);
 

@@ -427,15 +427,25 @@ extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, co
 			MC_REQUIRE(!cm.slot_pending[slot], MC_ERR_STATE, "slot %d still holds an exchange that was not collected", slot);
 			MC_REQUIRE(center_rows[i] >= 0 && center_rows[i] < ctx->n, MC_ERR_ARG, "center row out of range");
 			MC_REQUIRE(hi[i] < lo[i] || (lo[i] >= 0 && hi[i] < ctx->n), MC_ERR_ARG, "scan range out of range");
-			unsigned int epoch = ++cm.slot_epoch[slot];
-			if (epoch == 0) epoch = cm.slot_epoch[slot] = 2;
-			bargs.epoch[slot] = epoch;
-			bargs.slot_off[slot] = slot_offset(epoch, slot);
-			rc = mc_launch_scan_push(ctx, center_rows[i], lo[i], hi[i], remove_marked,
-			                         (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result),
-			                         &ctx->slot_nparts[slot], &push);
+		}
+		// scans that remove nothing are independent: up to MC_SCAN_BATCH per launch; otherwise one
+		// launch per scan, chained by programmatic dependent launch
+		const int per_launch = remove_marked ? 1 : MC_SCAN_BATCH;
+		for (int i0 = 0; i0 < count; i0 += per_launch) {
+			const int m = count - i0 < per_launch ? count - i0 : per_launch;
+			McScanReq req[MC_SCAN_BATCH];
+			for (int i = 0; i < m; i++) {
+				const int slot = slot0 + i0 + i;
+				unsigned int epoch = ++cm.slot_epoch[slot];
+				if (epoch == 0) epoch = cm.slot_epoch[slot] = 2;
+				bargs.epoch[slot] = epoch;
+				bargs.slot_off[slot] = slot_offset(epoch, slot);
+				req[i].lo = lo[i0 + i]; req[i].hi = hi[i0 + i]; req[i].center_row = center_rows[i0 + i];
+				req[i].partials_dev = (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result);
+				cm.slot_pending[slot] = 3;
+			}
+			rc = mc_launch_scan_batch(ctx, req, m, remove_marked, &ctx->slot_nparts[slot0 + i0], &push);
 			if (rc) return rc;
-			cm.slot_pending[slot] = 3;
 		}
 		MC_CUDA(cudaEventRecord(cm.scans_done, ctx->stream));
 		MC_CUDA(cudaStreamWaitEvent(cm.xstream, cm.scans_done, 0));

@@ -128,11 +128,25 @@ __device__ __forceinline__ void peer_store_words(const McPeerPush &push, int cta
 	}
 }
 
+// One launch carries up to MC_SCAN_BATCH scans: blockIdx.y selects the scan.  Scans of one launch must be
+// independent of each other (no removal of marked rows): they are the "several centers against the
+// same generation of the alive set" form of mc_scan_enqueue_many / mc_scan_sharded_burst.  Their CTAs
+// queue behind each other on the SMs, so consecutive scans overlap without any launch in between.
+struct ScanDesc {
+	long long lo, hi, center_row;
+	ScanPartial *partials;
+};
+struct ScanBatch {
+	ScanDesc d[MC_SCAN_BATCH];
+};
+
 template <int TB, int RB, int PUSH>
 __global__ void __launch_bounds__(32 * (1 + TileCfg<RB>::NCW), TileCfg<RB>::CTAS_PER_SM)
 scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, uint8_t *__restrict__ marks,
-                long long lo, long long hi, long long nrows_total, long long center_row, McModel model,
-                int remove_marked, ScanPartial *__restrict__ partials, PushArg<PUSH> push_arg) {
+                const __grid_constant__ ScanBatch batch, long long nrows_total, McModel model,
+                int remove_marked, PushArg<PUSH> push_arg) {
+	const long long lo = batch.d[blockIdx.y].lo, hi = batch.d[blockIdx.y].hi, center_row = batch.d[blockIdx.y].center_row;
+	ScanPartial *__restrict__ partials = batch.d[blockIdx.y].partials;
 	using C = RowCfg<RB>;
 	using T = TileCfg<RB>;
 	constexpr int NB = RB / TB;
@@ -390,8 +404,7 @@ int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t h
                           void *partials_dev, int *nparts_out);
 
 template <int TB, int RB, int PUSH>
-static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                           void *partials_dev, int *nparts_out, const McPeerPush *push) {
+static int launch_tma_impl(mc_ctx *ctx, const McScanReq *req, int count, int remove_marked, int *nparts_out, const McPeerPush *push) {
 	using T = TileCfg<RB>;
 	const size_t smem = (size_t)T::NS * T::STAGE_BYTES;
 	static bool attr_set[64] = {};   // function attributes are per device
@@ -399,20 +412,28 @@ static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t 
 		MC_CUDA(cudaFuncSetAttribute(scan_tma_kernel<TB, RB, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set[ctx->device & 63] = true;
 	}
-	const int64_t ntiles = hi >= lo ? hi / T::RT - lo / T::RT + 1 : 0;   // absolute tiles touched by [lo, hi]
 	int64_t blocks = ctx->num_sms;
-	if (blocks > ntiles) blocks = ntiles;
-	if (blocks < 1) blocks = 1;
+	if (count == 1 && PUSH == 0) {   // a short single scan does not need every SM
+		const int64_t ntiles = req[0].hi >= req[0].lo ? req[0].hi / T::RT - req[0].lo / T::RT + 1 : 0;   // absolute tiles touched by [lo, hi]
+		if (blocks > ntiles) blocks = ntiles;
+		if (blocks < 1) blocks = 1;
+	}
+	// sharded variants: every rank always leaves num_sms records per scan, so a reader knows how many to expect
 	PushArg<PUSH> pa{};
 	uint8_t *marks = ctx->d_marks;
-	if constexpr (PUSH != 0) {   // sharded: every rank always sends num_sms records, so a reader knows how many to expect
+	if constexpr (PUSH != 0) {
 		pa.v = *push;
-		blocks = ctx->num_sms;
 		if (ctx->comm.marks_target) marks = ctx->comm.marks_target;   // marks go to the rank that compacts them
+	}
+	ScanBatch batch{};
+	for (int i = 0; i < count; i++) {
+		batch.d[i].lo = req[i].lo; batch.d[i].hi = req[i].hi; batch.d[i].center_row = req[i].center_row;
+		batch.d[i].partials = (ScanPartial *)req[i].partials_dev;
+		nparts_out[i] = (int)blocks;
 	}
 	static const bool no_pdl = getenv("MC_NO_PDL") != nullptr;
 	cudaLaunchConfig_t cfg{};
-	cfg.gridDim = dim3((unsigned)blocks);
+	cfg.gridDim = dim3((unsigned)blocks, (unsigned)count);
 	cfg.blockDim = dim3(32 * (1 + T::NCW));
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = ctx->stream;
@@ -422,56 +443,64 @@ static int launch_tma_impl(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t 
 	cfg.attrs = attr;
 	cfg.numAttrs = no_pdl ? 0 : 1;
 	MC_CUDA(cudaLaunchKernelEx(&cfg, scan_tma_kernel<TB, RB, PUSH>, (const uint8_t *)ctx->d_hist, ctx->d_aux, marks,
-	                           (long long)lo, (long long)hi, (long long)ctx->n, (long long)center_row, ctx->model, remove_marked,
-	                           (ScanPartial *)partials_dev, pa));
-	*nparts_out = (int)blocks;
+	                           batch, (long long)ctx->n, ctx->model, remove_marked, pa));
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
 }
 
 template <int TB, int RB>
-static int launch_tma(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                      void *partials_dev, int *nparts_out, const McPeerPush *push) {
-	if (push && push->tiles_only) return launch_tma_impl<TB, RB, 2>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-	if (push) return launch_tma_impl<TB, RB, 1>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-	return launch_tma_impl<TB, RB, 0>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, nullptr);
+static int launch_tma(mc_ctx *ctx, const McScanReq *req, int count, int remove_marked, int *nparts_out, const McPeerPush *push) {
+	if (push && push->tiles_only) return launch_tma_impl<TB, RB, 2>(ctx, req, count, remove_marked, nparts_out, push);
+	if (push) return launch_tma_impl<TB, RB, 1>(ctx, req, count, remove_marked, nparts_out, push);
+	return launch_tma_impl<TB, RB, 0>(ctx, req, count, remove_marked, nparts_out, nullptr);
 }
 
-// partials_dev must hold MC_SCAN_PARTS entries of 32 bytes; *nparts_out says how many were written
-int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                        void *partials_dev, int *nparts_out, const McPeerPush *push);
+// rows narrower than 16 bytes (k = 1) and rows too wide for two stages keep the direct-load kernel
+int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                          void *partials_dev, int *nparts_out);
 
-int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                   void *partials_dev, int *nparts_out) {
-	return mc_launch_scan_push(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, nullptr);
-}
-
-// push != NULL: sharded scan, every CTA also stores its partial into the peers' inboxes
-int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
-                        void *partials_dev, int *nparts_out, const McPeerPush *push) {
+// `count` scans (1 <= count <= MC_SCAN_BATCH) in ONE launch; count > 1 requires scans that are
+// independent of each other.  Every req[i].partials_dev must hold MC_SCAN_PARTS entries of 32 bytes;
+// nparts_out[i] says how many were written.  push != NULL: sharded variants (this rank's tiles only).
+// Returns MC_ERR_UNSUPPORTED for shapes only the direct-load kernel handles when count > 1 or push.
+int mc_launch_scan_batch(mc_ctx *ctx, const McScanReq *req, int count, int remove_marked, int *nparts_out, const McPeerPush *push) {
 	static const bool legacy = getenv("MC_SCAN_DIRECT") != nullptr;
+	MC_REQUIRE(count >= 1 && count <= MC_SCAN_BATCH, MC_ERR_ARG, "scan batch of %d", count);
 	const int rb = ctx->tbytes * ctx->nbins;
 	if (!legacy) {
 		if (ctx->tbytes == 1) {
 			switch (rb) {
-			case 16: return launch_tma<1, 16>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-			case 64: return launch_tma<1, 64>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-			case 256: return launch_tma<1, 256>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-			case 1024: return launch_tma<1, 1024>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-			case 4096: return launch_tma<1, 4096>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+			case 16: return launch_tma<1, 16>(ctx, req, count, remove_marked, nparts_out, push);
+			case 64: return launch_tma<1, 64>(ctx, req, count, remove_marked, nparts_out, push);
+			case 256: return launch_tma<1, 256>(ctx, req, count, remove_marked, nparts_out, push);
+			case 1024: return launch_tma<1, 1024>(ctx, req, count, remove_marked, nparts_out, push);
+			case 4096: return launch_tma<1, 4096>(ctx, req, count, remove_marked, nparts_out, push);
 			default: break;
 			}
 		} else {
 			switch (rb) {
-			case 32: return launch_tma<2, 32>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-			case 128: return launch_tma<2, 128>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-			case 512: return launch_tma<2, 512>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
-			case 2048: return launch_tma<2, 2048>(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, push);
+			case 32: return launch_tma<2, 32>(ctx, req, count, remove_marked, nparts_out, push);
+			case 128: return launch_tma<2, 128>(ctx, req, count, remove_marked, nparts_out, push);
+			case 512: return launch_tma<2, 512>(ctx, req, count, remove_marked, nparts_out, push);
+			case 2048: return launch_tma<2, 2048>(ctx, req, count, remove_marked, nparts_out, push);
 			default: break;
 			}
 		}
 	}
 	MC_REQUIRE(!push, MC_ERR_UNSUPPORTED, "sharded scans need the staged scan kernel (16-byte rows and wider, no MC_SCAN_DIRECT)");
-	return mc_launch_scan_direct(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out);
+	MC_REQUIRE(count == 1, MC_ERR_UNSUPPORTED, "scan batches need the staged scan kernel");
+	return mc_launch_scan_direct(ctx, req[0].center_row, req[0].lo, req[0].hi, remove_marked, req[0].partials_dev, nparts_out);
+}
+
+int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                        void *partials_dev, int *nparts_out, const McPeerPush *push) {
+	McScanReq r;
+	r.lo = lo; r.hi = hi; r.center_row = center_row; r.partials_dev = partials_dev;
+	return mc_launch_scan_batch(ctx, &r, 1, remove_marked, nparts_out, push);
+}
+
+int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
+                   void *partials_dev, int *nparts_out) {
+	return mc_launch_scan_push(ctx, center_row, lo, hi, remove_marked, partials_dev, nparts_out, nullptr);
 }

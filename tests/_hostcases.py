@@ -14,9 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden", "clstr")
 
 
-def var_len_fasta(path, n, ntemp, lmin, lmax, mu, seed, related=0.0, iupac=False):
+def var_len_fasta(path, n, ntemp, lmin, lmax, mu, seed, related=0.0, iupac=False, homopolymer=0):
     rng = np.random.default_rng(seed)
     temps = [rng.integers(0, 4, int(rng.integers(lmin, lmax)), dtype=np.uint8) for _ in range(ntemp)]
+    if homopolymer:   # a long single-letter run in every template: some k-mer count exceeds 255 -> 16-bit histograms
+        for t_i, t in enumerate(temps):
+            s0 = int(rng.integers(0, max(1, t.size - homopolymer)))
+            t[s0:s0 + homopolymer] = t_i % 4
     if related > 0:
         anc = temps[0]
         temps = [synth._mutate(rng, anc.copy(), np.array([0, anc.size]), related)[0] for _ in range(ntemp)]
@@ -49,6 +53,8 @@ CASES = {
     # --align (forced) and automatic alignment below 60 % identity (Runner.cpp:32-34)
     "G": ([("G.fa", dict(n=500, ntemp=10, lmin=180, lmax=240, mu=0.08, seed=18))], ["--id", "0.75", "--align"]),
     "H": ([("H.fa", dict(n=400, ntemp=8, lmin=150, lmax=260, mu=0.15, seed=19))], ["--id", "0.55", "--delta", "3"]),
+    # low-complexity runs: the largest k-mer count exceeds 255, so the run uses 16-bit histograms (Runner.cpp:75-89)
+    "I": ([("I.fa", dict(n=900, ntemp=12, lmin=900, lmax=1100, mu=0.03, seed=21, homopolymer=330))], ["--id", "0.90", "--kmer", "3"]),
     "F": ([("F.fa", dict(n=1300, ntemp=20, lmin=260, lmax=420, mu=0.03, seed=17, iupac=True))],
           ["--id", "0.90", "--kmer", "4", "--sample", "2000", "--pivot", "10"]),
 }

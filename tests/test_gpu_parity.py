@@ -201,6 +201,36 @@ def test_scan_vs_oracle(ctx, oracle, k, n, nfeat):
     print(f"near-threshold pairs (|sum| < {NEAR}): {total_near}")
 
 
+@pytest.mark.parametrize("k,n", [(2, 3000), (4, 5000), (5, 2100), (6, 600)])
+def test_scan_batch_launch_equals_single_scans(ctx, k, n, monkeypatch):
+    """independent scans (nothing removed) share one launch (blockIdx.y = scan): same summaries as one
+    launch per scan, for more scans than one launch carries, ragged ranges and an empty alive set"""
+    rng = np.random.default_rng(1200 + k)
+    nb = 4 ** k
+    H = _rand_hists(rng, n, nb, clusters=6)
+    lens = (900 + rng.integers(0, 60, n)).astype(np.uint64)
+    mins, maxs, w = _model(4)
+    maxs[2] = 4.0 * nb
+    maxs[4] = 2.0 * nb
+    mins[4] = 0.5 * nb
+    ctx.load_histograms(H, lens, k)
+    ctx.set_model(mins, maxs, w, 4)
+    ctx.alive_kill(rng.integers(0, n, n // 5))
+    m = 37
+    cr = rng.integers(0, n, m)
+    lo = rng.integers(0, n // 3, m)
+    hi = n - 1 - rng.integers(0, n // 3, m)
+    lo[3], hi[3] = 17, 17
+    ctx.scan_enqueue_many(cr, lo, hi, False, 0)            # batched launches
+    got = ctx.scan_collect(0, m)
+    monkeypatch.setenv("MC_SCAN_NO_BATCH", "1")
+    ctx.scan_enqueue_many(cr, lo, hi, False, 100)          # one launch per scan
+    want = ctx.scan_collect(100, m)
+    assert got == want
+    one = [ctx.scan_enqueue(int(cr[i]), int(lo[i]), int(hi[i]), False, 300 + i) for i in range(5)]
+    assert ctx.scan_collect(300, 5) == want[:5]
+
+
 def test_scan_first_max_wins_and_null(ctx, oracle):
     # identical rows tie on f0: the first one in row order must win; f0 <= -1 everywhere -> no seed
     rng = np.random.default_rng(9)
