@@ -155,9 +155,9 @@ int mc_set_stream(mc_ctx *ctx, void *stream);
 /* ---- multi-GPU: sharded scans ------------------------------------ */
 
 /* `world` contexts, one per GPU (in one process or one process each), hold the same rows; the
- * scan work and the alive flags are sharded in tiles: tile t (rows [t*T, (t+1)*T), T = 32 rows for
- * rows up to 1 KB) belongs to rank t mod world, so any length window spreads over all GPUs and
- * the owner of a row never changes.  What the reference reduces with OpenMP at the end of
+ * scan work and the alive flags are sharded in blocks of consecutive rows (~256 KB of histograms:
+ * 1024 rows at k = 4, 256 rows at k = 5): block b belongs to rank b mod world, so any length
+ * window wider than a few blocks spreads over all GPUs and the owner of a row never changes.  What the reference reduces with OpenMP at the end of
  * Trainer::get_close (Trainer.cpp:38-48,81: arg-max, positives) crosses GPUs inside the scan
  * kernel: every CTA stores its partial into all ranks' inboxes over NVLink peer memory, and the
  * collect call folds world x SMs records on the device.
@@ -187,8 +187,10 @@ int mc_scan_sharded_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *
  * that keep the GPU busy enqueue the next scans between the two. */
 int mc_scan_sharded_combine(mc_ctx *ctx, int slot0, int nslots);
 int mc_scan_sharded_wait(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *res);
-/* combine(previous burst) + enqueue_many(this burst) + wait(previous burst) in one call; either
- * count may be 0 */
+/* Streaming form for independent bursts of scans: enqueue this burst (scans on the context's
+ * stream; fold + send + combine on a second, high-priority stream) and then wait for the summaries
+ * of an earlier burst (slots prev_slot0.., e.g. the previous one); either count may be 0.  Bursts
+ * should start at slots that are multiples of 16 (one completion event per bank). */
 int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo,
                           const int64_t *hi, int count, int remove_marked, int slot0, int prev_slot0,
                           int prev_count, mc_scan_result *prev_res);

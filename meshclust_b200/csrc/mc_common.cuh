@@ -108,6 +108,7 @@ struct McComm {
 	uint8_t *marks_target = nullptr;           // sharded Phase A: the marks array of the rank that runs the tail
 	cudaStream_t xstream = nullptr;            // exchange stream of the burst path (fold + send + combine)
 	cudaEvent_t scans_done = nullptr;          // recorded on the scan stream behind a burst
+	cudaEvent_t burst_done[4] = {};            // per bank of MC_SCAN_BATCH slots: the burst's summaries are on the host
 };
 
 // ---------------------------------------------------------------------------------------------

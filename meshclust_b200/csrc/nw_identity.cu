@@ -99,23 +99,26 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 			int2 *sb_out = sb0 + ((strip + 1) & 1) * scratch_stride;
 
 			int bj[R];
-			// per row: the cell just to the left (row j, column i-1) and, for the row BELOW it, the
-			// same cell one step older (the diagonal)
+			// per row: the cell just to the left (row j, column i-1).  The diagonal of row r+1 is that
+			// same cell before this step overwrites it, so only the top row of the lane needs a separate
+			// diagonal (row j0-1, column i-1); the U fields of `left`, which the horizontal recurrence
+			// never reads, carry the synthesised U of column 0 for that purpose.
 			NwCell left[R];    // (row r, column i-1)
-			NwCell diag[R];    // (row r-1, column i-1): what row r adds its match score to
+			NwCell diag0;      // (row j0-1, column i-1): what the lane's first row adds its match score to
 #pragma unroll
 			for (int r = 0; r < R; r++) {
 				const int j = j0 + r;
 				bj[r] = (j <= lb) ? B[j - 1] : 0xfe;   // 0xfe never equals a base
-				// column 0 of row j: M = L = ninf with len j (U[0] is never read through `left`)
-				left[r].m = ninf; left[r].l = ninf; left[r].u = 0;
-				left[r].pm = (uint32_t)j << 16; left[r].pl = (uint32_t)j << 16; left[r].pu = 0;
-				// column 0 of row j-1 as the first diagonal (GlobAlignE.cpp:164-170,250-256)
-				diag[r].m = (j == 1) ? 0 : ninf;
-				diag[r].l = ninf;
-				diag[r].u = -NW_OPEN - (j - 1) * NW_EXT;
-				diag[r].pm = diag[r].pl = diag[r].pu = (uint32_t)(j - 1) << 16;
+				// column 0 of row j: M = L = ninf with len j; U[0] as the row below synthesises it
+				// (GlobAlignE.cpp:164-170,250-256)
+				left[r].m = ninf; left[r].l = ninf; left[r].u = -NW_OPEN - j * NW_EXT;
+				left[r].pm = left[r].pl = left[r].pu = (uint32_t)j << 16;
 			}
+			// column 0 of row j0-1
+			diag0.m = (j0 == 1) ? 0 : ninf;
+			diag0.l = ninf;
+			diag0.u = -NW_OPEN - (j0 - 1) * NW_EXT;
+			diag0.pm = diag0.pl = diag0.pu = (uint32_t)(j0 - 1) << 16;
 			NwCell mine;   // last row's newest cell, published to the lane below
 			mine.m = 0; mine.u = 0; mine.l = 0; mine.pm = 0; mine.pu = 0; mine.pl = 0;
 			uint32_t achunk = 0, achar = 0;
@@ -165,6 +168,8 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 					up.pm = up.pu = up.pl = (uint32_t)i << 16;
 				}
 				if (i >= 1 && i <= la) {
+					NwCell dg = diag0;   // diagonal of the row being filled
+					diag0 = up;          // (row j0-1, column i) is the top row's diagonal at the next column
 #pragma unroll
 					for (int r = 0; r < R; r++) {
 						// vertical gap: from (row-1, i)
@@ -175,9 +180,9 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 						cur.pu = (ubeg ? up.pm : up.pu) + NW_LEN1;
 						// diagonal: from (row-1, i-1), tie order M, L, U
 						const bool eq = achar == (uint32_t)bj[r];
-						int best = diag[r].m; uint32_t pbst = diag[r].pm;
-						if (diag[r].l > best) { best = diag[r].l; pbst = diag[r].pl; }
-						if (diag[r].u > best) { best = diag[r].u; pbst = diag[r].pu; }
+						int best = dg.m; uint32_t pbst = dg.pm;
+						if (dg.l > best) { best = dg.l; pbst = dg.pl; }
+						if (dg.u > best) { best = dg.u; pbst = dg.pu; }
 						cur.m = best + (eq ? 1 : -1);
 						cur.pm = pbst + NW_LEN1 + (eq ? 1u : 0u);
 						// horizontal gap on the current row: from (row, i-1)
@@ -185,17 +190,21 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 						const bool hbeg = hb >= hc;
 						cur.l = hbeg ? hb : hc;
 						cur.pl = (hbeg ? left[r].pm : left[r].pl) + NW_LEN1;
-						// roll: (row-1, i) becomes the diagonal of (row, i+1); this cell the left of (row, i+1)
-						diag[r] = up;
+						// roll: (row, i-1) is the diagonal of the row below; this cell the left of (row, i+1)
+						dg = left[r];
 						left[r] = cur;
-						if (j0 + r == lb && i == la) {
-							// GlobAlignE.cpp:278-291: tie order M, L, U
-							int bs = cur.m; uint32_t bp = cur.pm;
-							if (cur.l > bs) { bs = cur.l; bp = cur.pl; }
-							if (cur.u > bs) { bs = cur.u; bp = cur.pu; }
-							res_sc = bs; res_p = bp;
-						}
 						up = cur;   // the next row of this lane sits right below
+					}
+					if (i == la) {
+#pragma unroll
+						for (int r = 0; r < R; r++)
+							if (j0 + r == lb) {
+								// GlobAlignE.cpp:278-291: tie order M, L, U
+								int bs = left[r].m; uint32_t bp = left[r].pm;
+								if (left[r].l > bs) { bs = left[r].l; bp = left[r].pl; }
+								if (left[r].u > bs) { bs = left[r].u; bp = left[r].pu; }
+								res_sc = bs; res_p = bp;
+							}
 					}
 					mine = up;      // == last row's cell
 					if (lane == 31 && strip + 1 < nstrips) {

@@ -8,8 +8,8 @@
 // world x num_sms records of a slot and folds them with the reference's rule (largest f0, first
 // row among equals).  No host round trip, no collective library call, nothing but posted stores on
 // the critical path.  Rows are numbered globally on every rank (the histogram matrix is replicated
-// once after K1; only scan work and alive flags are sharded, tile t of 32 rows belonging to rank
-// t mod world), so records compare directly.
+// once after K1; only scan work and alive flags are sharded, in blocks of ~256 KB of consecutive rows
+// dealt round-robin to the ranks), so records compare directly.
 #include <string.h>
 
 #include "mc_common.cuh"
@@ -55,7 +55,7 @@ scan_combine_kernel(const uint8_t *__restrict__ inbox, int world, int nparts, Co
 	unsigned long long t0;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 	bool failed = false;
-	for (int i = threadIdx.x; i < world * nparts; i += COMBINE_THREADS) {
+	for (int i = threadIdx.x; i < world * nparts; i += blockDim.x) {
 		const int rank = i / nparts, cta = i % nparts;
 		const uint8_t *rec = base + ((size_t)rank * MC_SCAN_PARTS + cta) * MC_LL_RECORD_BYTES;
 		uint4 q[4];
@@ -94,7 +94,7 @@ scan_combine_kernel(const uint8_t *__restrict__ inbox, int world, int nparts, Co
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		mc_scan_result r = s_part[0];
-		for (int w = 1; w < COMBINE_THREADS / 32; w++) xmerge(r, s_part[w]);
+		for (int w = 1; w < (int)(blockDim.x >> 5); w++) xmerge(r, s_part[w]);
 		out[slot] = r;
 	}
 }
@@ -111,6 +111,7 @@ static void comm_release(mc_ctx *ctx) {
 	cudaFree(cm.d_out);
 	if (cm.h_out) { cudaFreeHost(cm.h_out); cudaEventDestroy(cm.done); }
 	if (cm.xstream) { cudaStreamSynchronize(cm.xstream); cudaStreamDestroy(cm.xstream); cudaEventDestroy(cm.scans_done); }
+	for (int b = 0; b < 4; b++) if (cm.burst_done[b]) cudaEventDestroy(cm.burst_done[b]);
 	cm = McComm();
 }
 
@@ -367,7 +368,12 @@ __global__ void __launch_bounds__(32) fold_send_kernel(const mc_scan_result *__r
 static int burst_streams(mc_ctx *ctx) {
 	McComm &cm = ctx->comm;
 	if (cm.xstream) return MC_OK;
-	MC_CUDA(cudaStreamCreateWithFlags(&cm.xstream, cudaStreamNonBlocking));
+	// highest priority: when an SM has room, the (tiny) exchange kernels go before the queued CTAs of
+	// the next scans -- otherwise the summaries of a burst would only leave once the NEXT burst has
+	// drained (measured: 70 us from the end of a burst to its summaries on the host)
+	int prio_lo = 0, prio_hi = 0;
+	MC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	MC_CUDA(cudaStreamCreateWithPriority(&cm.xstream, cudaStreamNonBlocking, prio_hi));
 	MC_CUDA(cudaEventCreateWithFlags(&cm.scans_done, cudaEventDisableTiming));
 	if (!cm.h_out) {
 		MC_CUDA(cudaMallocHost(&cm.h_out, (size_t)MC_XSLOTS * sizeof(mc_scan_result) + 64));
@@ -376,9 +382,10 @@ static int burst_streams(mc_ctx *ctx) {
 	return MC_OK;
 }
 
-// One pipelined burst: fold the previous burst on the exchange stream (asynchronous), enqueue this
-// burst's scans on the scan stream and their fold + send on the exchange stream, and only then
-// wait for the previous summaries -- the GPU already runs this burst while the host waits.
+// One pipelined burst: enqueue this burst's scans on the scan stream and their fold + send + combine
+// on the exchange stream, then wait for the summaries of an EARLIER burst (slots prev_slot0..) -- the
+// GPU already runs this burst while the host waits.  A burst's slots should start at a multiple of
+// MC_SCAN_BATCH (one completion event per such bank, four banks).
 extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo, const int64_t *hi,
                                      int count, int remove_marked, int slot0, int prev_slot0, int prev_count,
                                      mc_scan_result *prev_res) {
@@ -392,24 +399,18 @@ extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, co
 	MC_CUDA(cudaSetDevice(ctx->device));
 	int rc = burst_streams(ctx);
 	if (rc) return rc;
+	static const bool dbg = getenv("MC_DEBUG_TIMING") != nullptr;
+	static const bool no_exchange = getenv("MC_BURST_NO_EXCHANGE") != nullptr;   // diagnosis only: scans without fold / send / combine
+	static double t_comb = 0, t_scan = 0, t_fold = 0, t_wait = 0;
+	static long n_calls = 0;
+	auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+	double tq0 = dbg ? now() : 0, tq1 = 0, tq2 = 0, tq3 = 0;
 	mc_scan_result *d_out = (mc_scan_result *)cm.d_out;
 	unsigned int *d_err = (unsigned int *)((uint8_t *)cm.d_out + (size_t)MC_XSLOTS * sizeof(mc_scan_result));
 	mc_scan_result *h_out = (mc_scan_result *)cm.h_out;
-	if (prev_count > 0) {
-		CombineArgs args;
-		memset(&args, 0, sizeof(args));
-		for (int s = prev_slot0; s < prev_slot0 + prev_count; s++) {
-			MC_REQUIRE(cm.slot_pending[s] == 3, MC_ERR_STATE, "slot %d holds no burst scan", s);
-			args.epoch[s] = cm.slot_epoch[s];
-			args.slot_off[s] = slot_offset(cm.slot_epoch[s], s);
-		}
-		scan_combine_kernel<<<prev_count, COMBINE_THREADS, 0, cm.xstream>>>(cm.inbox, cm.world, 1, args, prev_slot0, d_out, d_err);
-		ctx->launches++;
-		MC_CUDA(cudaGetLastError());
-		MC_CUDA(cudaMemcpyAsync(h_out + prev_slot0, d_out + prev_slot0, (size_t)prev_count * sizeof(mc_scan_result), cudaMemcpyDeviceToHost, cm.xstream));
-		MC_CUDA(cudaMemcpyAsync(h_out + MC_XSLOTS, d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, cm.xstream));
-		MC_CUDA(cudaEventRecord(cm.done, cm.xstream));
-	}
+	for (int sl = prev_slot0; sl < prev_slot0 + prev_count; sl++)
+		MC_REQUIRE(cm.slot_pending[sl] == 4 || (no_exchange && cm.slot_pending[sl] == 3), MC_ERR_STATE, "slot %d holds no burst scan", sl);
+	if (dbg) tq1 = now();
 	if (count > 0) {
 		if (!ctx->d_scan_slots) {
 			MC_CUDA(cudaMalloc(&ctx->d_scan_slots, (size_t)MC_SCAN_SLOTS * MC_SCAN_PARTS * sizeof(mc_scan_result)));
@@ -447,14 +448,49 @@ extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, co
 			rc = mc_launch_scan_batch(ctx, req, m, remove_marked, &ctx->slot_nparts[slot0 + i0], &push);
 			if (rc) return rc;
 		}
-		MC_CUDA(cudaEventRecord(cm.scans_done, ctx->stream));
-		MC_CUDA(cudaStreamWaitEvent(cm.xstream, cm.scans_done, 0));
-		fold_send_kernel<<<count, 32, 0, cm.xstream>>>((const mc_scan_result *)ctx->d_scan_slots, ctx->num_sms, bargs, slot0, push);
-		ctx->launches++;
-		MC_CUDA(cudaGetLastError());
+		if (dbg) tq2 = now();
+		if (!no_exchange) {
+			MC_CUDA(cudaEventRecord(cm.scans_done, ctx->stream));
+			MC_CUDA(cudaStreamWaitEvent(cm.xstream, cm.scans_done, 0));
+			fold_send_kernel<<<count, 32, 0, cm.xstream>>>((const mc_scan_result *)ctx->d_scan_slots, ctx->num_sms, bargs, slot0, push);
+			ctx->launches++;
+			MC_CUDA(cudaGetLastError());
+			// the combine of THIS burst goes out right behind its send (one warp per scan: world records
+			// to fold, and a CTA this small fits next to the resident scan CTAs); its summaries are on the
+			// host a few microseconds after the burst's last scan, whenever the caller asks for them
+			CombineArgs args;
+			memset(&args, 0, sizeof(args));
+			for (int sl = slot0; sl < slot0 + count; sl++) {
+				args.epoch[sl] = cm.slot_epoch[sl];
+				args.slot_off[sl] = slot_offset(cm.slot_epoch[sl], sl);
+				cm.slot_pending[sl] = 4;
+			}
+			scan_combine_kernel<<<count, 32, 0, cm.xstream>>>(cm.inbox, cm.world, 1, args, slot0, d_out, d_err);
+			ctx->launches++;
+			MC_CUDA(cudaGetLastError());
+			MC_CUDA(cudaMemcpyAsync(h_out + slot0, d_out + slot0, (size_t)count * sizeof(mc_scan_result), cudaMemcpyDeviceToHost, cm.xstream));
+			MC_CUDA(cudaMemcpyAsync(h_out + MC_XSLOTS, d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, cm.xstream));
+			cudaEvent_t &ev = cm.burst_done[(slot0 / MC_SCAN_BATCH) & 3];
+			if (!ev) MC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+			MC_CUDA(cudaEventRecord(ev, cm.xstream));
+		}
+	}
+	if (dbg) { if (tq2 == 0) tq2 = now(); tq3 = now(); }
+	if (prev_count > 0 && no_exchange) {
+		for (int s = prev_slot0; s < prev_slot0 + prev_count; s++) cm.slot_pending[s] = 0;
+		memset(prev_res, 0, (size_t)prev_count * sizeof(mc_scan_result));
+		return MC_OK;
 	}
 	if (prev_count > 0) {
-		MC_CUDA(cudaEventSynchronize(cm.done));
+		cudaEvent_t ev = cm.burst_done[(prev_slot0 / MC_SCAN_BATCH) & 3];
+		MC_REQUIRE(ev, MC_ERR_STATE, "no burst was enqueued on slots %d..", prev_slot0);
+		MC_CUDA(cudaEventSynchronize(ev));
+		if (dbg) {
+			t_comb += tq1 - tq0; t_scan += tq2 - tq1; t_fold += tq3 - tq2; t_wait += now() - tq3;
+			if (++n_calls % 25 == 0)
+				fprintf(stderr, "[mc_scan_sharded_burst rank %d] %ld calls: combine enqueue %.1f us, scans enqueue %.1f us, fold enqueue %.1f us, wait for the previous burst %.1f us (averages)\n",
+				        cm.rank, n_calls, t_comb / n_calls * 1e6, t_scan / n_calls * 1e6, t_fold / n_calls * 1e6, t_wait / n_calls * 1e6);
+		}
 		for (int s = prev_slot0; s < prev_slot0 + prev_count; s++) cm.slot_pending[s] = 0;
 		if (*(const unsigned int *)(h_out + MC_XSLOTS)) {
 			MC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned int), cm.xstream));

@@ -88,10 +88,14 @@ struct TileCfg {
 	static constexpr int CTAS_PER_SM = RB <= TSCAN_SMALL_ROW ? MC_SCAN_SMALL_CTAS_PER_SM : 1;
 	static constexpr int NS_RAW = (TSCAN_SMEM_BUDGET / CTAS_PER_SM) / STAGE_BYTES;
 	static constexpr int NS_CAP = NS_RAW > TSCAN_MAX_STAGES ? TSCAN_MAX_STAGES : NS_RAW;
-	static constexpr int MAXC = RB <= TSCAN_SMALL_ROW ? TSCAN_MAX_CONSUMERS / CTAS_PER_SM : 16;
+	// two CTAs per SM: 11 consumers + the producer = 384 threads, i.e. 80 registers per thread (12 consumers
+	// would cap them at 72 and spill inside the tile loop)
+	static constexpr int MAXC = RB <= TSCAN_SMALL_ROW ? (CTAS_PER_SM == 2 ? 11 : TSCAN_MAX_CONSUMERS / CTAS_PER_SM) : 16;
 	static constexpr int NCW = NS_CAP > MAXC ? MAXC : NS_CAP;   // active consumer warps
 	static constexpr int D = NS_CAP / NCW;                                                   // ring depth per consumer
 	static constexpr int NS = NCW * D;
+	// sharded scans: consecutive tiles one rank owns (a power of two, ~256 KB of rows)
+	static constexpr int GROUP_TILES = (262144 / ROW_BYTES) >= 1 ? (262144 / ROW_BYTES) : 1;
 	static_assert(NS_CAP >= 2, "row too wide for the staged scan");
 };
 
@@ -175,15 +179,28 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 	TRACE(1);
 
 	// Tiles are RT rows on an ABSOLUTE grid (tile t = rows [t*RT, (t+1)*RT)), so which GPU owns a row
-	// -- and with it the row's alive flag -- never depends on the range of a scan: tile t belongs to
-	// rank t mod world (tile-interleaved sharding: any length window spreads over all GPUs).  A
-	// rank's tiles are dealt round-robin to its CTAs, then round-robin to the CTA's consumer warps.
-	// Rows of the first / last tile outside [lo, hi] are copied but never evaluated.
+	// -- and with it the row's alive flag -- never depends on the range of a scan.  Ownership goes by
+	// blocks of GT consecutive tiles (~256 KB of histogram rows): block b belongs to rank b mod world.
+	// Any length window wider than a few blocks spreads over all GPUs, and every rank still streams
+	// long contiguous runs (interleaving single 8 KB tiles cost 40 % of the bandwidth: 5.8 -> 10 us per
+	// C2-shape scan).  A rank's tiles are dealt round-robin to its CTAs, then round-robin to the CTA's
+	// consumer warps.  Rows of the first / last tile outside [lo, hi] are copied but never evaluated.
 	int world = 1, rank = 0;
 	if constexpr (PUSH != 0) { world = push_arg.v.world; rank = push_arg.v.rank; }
+	constexpr long long GT = T::GROUP_TILES;
+	// tiles of this rank below tile t
+	auto owned_below = [&](long long t) {
+		const long long period = GT * world, rem = t % period - (long long)rank * GT;
+		return (t / period) * GT + (rem < 0 ? 0 : (rem > GT ? GT : rem));
+	};
 	const long long t0 = lo / T::RT, t1 = hi / T::RT;
-	const long long tf = t0 + (((long long)rank - t0 % world) + world) % world;   // first tile of this rank
-	const long long ntiles = (hi >= lo && tf <= t1) ? (t1 - tf) / world + 1 : 0;
+	const long long base = owned_below(t0);
+	const long long ntiles = hi >= lo ? owned_below(t1 + 1) - base : 0;
+	// j-th tile of this rank inside the range -> absolute tile
+	auto tile_of = [&](long long j) {
+		const long long J = base + j;
+		return (J / GT) * (GT * world) + (long long)rank * GT + J % GT;
+	};
 	const long long my_first = blockIdx.x;
 	const long long nmine = my_first < ntiles ? (ntiles - my_first + gridDim.x - 1) / gridDim.x : 0;
 
@@ -205,7 +222,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 				if (jj >= nmine) break;
 				const long long round = u / T::D;
 				if (round > 0) mbar_wait(&empty_bar[lane], (uint32_t)(round - 1) & 1);
-				const long long r0 = (tf + (my_first + jj * gridDim.x) * world) * T::RT;
+				const long long r0 = tile_of(my_first + jj * gridDim.x) * T::RT;
 				long long nr = nrows_total - r0;
 				if (nr > T::RT) nr = T::RT;
 				uint8_t *dst = smem + (size_t)lane * T::STAGE_BYTES;
@@ -232,7 +249,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		unsigned pre_flag_0 = 0, pre_flag_1 = 0;
 		int npre = 0;
 		bool waited = false;
-		auto row_of_tile = [&](long long uu) { return (tf + (my_first + ((long long)cw + uu * T::NCW) * gridDim.x) * world) * T::RT + lane; };
+		auto row_of_tile = [&](long long uu) { return tile_of(my_first + ((long long)cw + uu * T::NCW) * gridDim.x) * T::RT + lane; };
 		auto apply = [&](long long row, double f0, unsigned flag_in) {
 			if (lane < T::RT && row >= lo && row <= hi) {
 				unsigned flag = 0;

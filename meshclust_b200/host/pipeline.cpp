@@ -589,8 +589,8 @@ void mean_shift(Ctx &c, BVec &bv) {
 	}
 	if (world > 1 && !c.model.align) {
 		// rows are replicated once (device-to-device), scan work and alive flags are sharded
-		// tile-interleaved (tile t of 32 rows belongs to GPU t mod N); summaries and marks cross GPUs
-		// inside the scan kernel
+		// block-interleaved (~256 KB of consecutive rows per block, blocks round-robin over the GPUs);
+		// summaries and marks cross GPUs inside the scan kernel
 		Timer ts;
 		for (int r = 1; r < world; r++) GPU(mc_clone_points(c.ranks[r], c.gpu));
 		for (int r = 0; r < world; r++) GPU(mc_comm_init(c.ranks[r], r, world, nullptr));

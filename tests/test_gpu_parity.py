@@ -458,11 +458,11 @@ def test_sharded_scan_equals_single(ctx, world, k, n):
         hi_a = np.full(len(centers), n - 1, np.int64)
         e = np.zeros(0, np.int64)
         for c in ranks:
-            assert c.scan_sharded_burst(cr, lo_a, hi_a, False, 20, 0, 0) == []
+            assert c.scan_sharded_burst(cr, lo_a, hi_a, False, 16, 0, 0) == []
         for c in ranks:
-            assert c.scan_sharded_burst(cr[::-1].copy(), lo_a, hi_a, False, 30, 20, len(centers)) == want
+            assert c.scan_sharded_burst(cr[::-1].copy(), lo_a, hi_a, False, 32, 16, len(centers)) == want
         for c in ranks:
-            assert c.scan_sharded_burst(e, e, e, False, 0, 30, len(centers)) == want[::-1]
+            assert c.scan_sharded_burst(e, e, e, False, 0, 32, len(centers)) == want[::-1]
         # a range that misses some shards entirely
         w1, _ = ctx.scan(3, 0, n // (2 * world))
         for c in ranks:

@@ -2,6 +2,7 @@
 # multi-GPU session: weak scaling of bench.py at N = 1, 2, 4 (and 8 when the box has them)
 set -u
 mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q -k "scan or sharded or accumulate" > gpurun_out/pytest4.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest4.log
 NG=$(nvidia-smi -L | wc -l)
 for N in 1 2 4 8; do
   if [ "$N" -gt "$NG" ]; then continue; fi
