@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the C4-shape roofline probe")
+    ap.add_argument("--scaling-only", action="store_true", help="development: skip the e2e and CPU-baseline legs too")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -338,7 +339,7 @@ def main():
             records = torch.zeros((S, 4), dtype=torch.int64, device="cuda")
     last_results = [None]
 
-    pending = [None]   # step whose exchange has been sent but not folded yet
+    inflight = []   # steps whose summaries have not been collected yet (at most 2 + the one being enqueued)
 
     def run_step(step):
         if world == 1:
@@ -351,20 +352,23 @@ def main():
             ctx.scan_fold_dev(0, S, records.data_ptr())
             last_results[0] = sharding.combine_scan_records(records, 0)
             return
-        # software pipeline, one C-ABI call per step: fold the previous step's exchange on the device,
-        # enqueue this step's scans behind it, and only then let the host wait for the previous summaries
+        # software pipeline, one C-ABI call per step: enqueue this step's scans (+ fold / send / combine on
+        # the exchange stream) and collect the summaries of the step before the previous one, so the ~50 us
+        # from the end of a burst to its summaries on the host never stall the next enqueue
         cr, lo, hi, sl, sh = step_args(step)
-        prev = pending[0]
-        res = ctx.scan_sharded_burst(cr, lo, hi, False, (step & 1) * 16, 0 if prev is None else (prev & 1) * 16, 0 if prev is None else S)
-        if prev is not None:
-            last_results[0] = res
-        pending[0] = step
+        inflight.append(step)
+        if len(inflight) > 2:
+            old = inflight.pop(0)
+            last_results[0] = ctx.scan_sharded_burst(cr, lo, hi, False, (step % 3) * 16, (old % 3) * 16, S)
+        else:
+            ctx.scan_sharded_burst(cr, lo, hi, False, (step % 3) * 16, 0, 0)
 
     def drain():
-        if world > 1 and exchange == "peer_inbox" and pending[0] is not None:
+        if world > 1 and exchange == "peer_inbox":
             e = np.zeros(0, np.int64)
-            last_results[0] = ctx.scan_sharded_burst(e, e, e, False, 0, (pending[0] & 1) * 16, S)
-            pending[0] = None
+            while inflight:
+                old = inflight.pop(0)
+                last_results[0] = ctx.scan_sharded_burst(e, e, e, False, 0, (old % 3) * 16, S)
 
     for i in range(args.warmup):
         run_step(i)
@@ -476,7 +480,9 @@ def main():
     if chain is not None:
         out["dependent_chain"] = chain
 
-    if rank == 0:
+    if rank == 0 and args.scaling_only:
+        emit(out)
+    elif rank == 0:
         # ---- e2e through the host-buffer C-ABI call: pinned host histograms in, marks + summaries out
         hp = torch.empty((n, nbins), dtype=torch.uint8, pin_memory=True)
         hp.numpy()[:] = hist

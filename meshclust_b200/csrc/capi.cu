@@ -620,6 +620,8 @@ extern "C" int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, con
 				MC_REQUIRE(l >= 0 && h < ctx->n && l <= h, MC_ERR_ARG, "scan range [%lld,%lld] invalid", (long long)l, (long long)h);
 				req[i].lo = l; req[i].hi = h; req[i].center_row = c;
 				req[i].partials_dev = (uint8_t *)ctx->d_scan_slots + (size_t)(slot0 + i0 + i) * MC_SCAN_PARTS * sizeof(mc_scan_result);
+				req[i].ll_partials_dev = nullptr;
+				req[i].ll_tag = 0;
 			}
 			rc = mc_launch_scan_batch(ctx, req, m, 0, &ctx->slot_nparts[slot0 + i0], nullptr);
 			if (rc == MC_ERR_UNSUPPORTED) break;   // shape only the direct-load kernel handles: one launch per scan below

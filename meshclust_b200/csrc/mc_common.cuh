@@ -16,6 +16,8 @@
 struct McScanReq {          // one scan of a batch launch (host side)
 	long long lo, hi, center_row;
 	void *partials_dev;
+	void *ll_partials_dev;    // optional (burst path): MC_SCAN_PARTS x 8 {data, tag} words for this scan's CTA partials
+	unsigned int ll_tag;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -108,6 +110,8 @@ struct McComm {
 	uint8_t *marks_target = nullptr;           // sharded Phase A: the marks array of the rank that runs the tail
 	cudaStream_t xstream = nullptr;            // exchange stream of the burst path (fold + send + combine)
 	cudaEvent_t scans_done = nullptr;          // recorded on the scan stream behind a burst
+	unsigned int *d_ll_partials = nullptr;     // per exchange slot: MC_SCAN_PARTS CTA partials as {data, tag} words (burst path)
+	unsigned int slot_uses[MC_XSLOTS] = {};
 	cudaEvent_t burst_done[4] = {};            // per bank of MC_SCAN_BATCH slots: the burst's summaries are on the host
 };
 

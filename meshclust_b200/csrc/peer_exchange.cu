@@ -112,6 +112,7 @@ static void comm_release(mc_ctx *ctx) {
 	if (cm.h_out) { cudaFreeHost(cm.h_out); cudaEventDestroy(cm.done); }
 	if (cm.xstream) { cudaStreamSynchronize(cm.xstream); cudaStreamDestroy(cm.xstream); cudaEventDestroy(cm.scans_done); }
 	for (int b = 0; b < 4; b++) if (cm.burst_done[b]) cudaEventDestroy(cm.burst_done[b]);
+	cudaFree(cm.d_ll_partials);
 	cm = McComm();
 }
 
@@ -329,21 +330,46 @@ extern "C" int mc_scan_sharded_collect(mc_ctx *ctx, int slot0, int nslots, mc_sc
 struct BurstArgs {
 	unsigned long long slot_off[MC_XSLOTS];
 	unsigned int epoch[MC_XSLOTS];
+	unsigned int tag[MC_XSLOTS];      // tag the CTA partials of this use of the slot carry
 };
 
 // one warp per slot: fold the CTA partials of this rank's scan, then send the record (CTA index 0)
-__global__ void __launch_bounds__(32) fold_send_kernel(const mc_scan_result *__restrict__ slots, int nparts, BurstArgs args, int slot0,
-                                                       McPeerPush push) {
+__global__ void __launch_bounds__(32) fold_send_kernel(const unsigned int *__restrict__ ll_partials, int nparts, BurstArgs args, int slot0,
+                                                       McPeerPush push, unsigned int *__restrict__ err) {
 	const int slot = slot0 + blockIdx.x, lane = threadIdx.x;
-	const mc_scan_result *p = slots + (size_t)slot * MC_SCAN_PARTS;
+	// this kernel is not ordered behind the scans by the stream: it polls the {data, tag} copies of the
+	// CTA partials until every word carries this use's tag
+	const unsigned int tag = args.tag[slot];
+	const unsigned int *base = ll_partials + (size_t)slot * MC_SCAN_PARTS * 16;
 	mc_scan_result b;
 	b.n_eval = 0; b.n_pos = 0; b.best_row = -1; b.best_f0 = -1.0;
-	for (int i = lane; i < nparts; i += 32) {
-		mc_scan_result q;
-		q.n_eval = __ldcg(&p[i].n_eval); q.n_pos = __ldcg(&p[i].n_pos);
-		q.best_row = __ldcg(&p[i].best_row); q.best_f0 = __ldcg(&p[i].best_f0);
-		xmerge(b, q);
+	unsigned long long t0;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+	bool failed = false;
+	for (int i = lane; i < nparts && !failed; i += 32) {
+		const unsigned int *rec = base + (size_t)i * 16;
+		uint4 q[4];
+		for (;;) {
+#pragma unroll
+			for (int j = 0; j < 4; j++) q[j] = ld_volatile16(rec + j * 4);
+			bool ok = true;
+#pragma unroll
+			for (int j = 0; j < 4; j++) ok = ok && q[j].y == tag && q[j].w == tag;
+			if (ok) break;
+			__nanosleep(100);
+			unsigned long long t1;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if (t1 - t0 > COMBINE_TIMEOUT_NS) { failed = true; break; }
+		}
+		if (failed) break;
+		mc_scan_result r;
+		r.n_eval = (long long)((unsigned long long)q[0].x | ((unsigned long long)q[0].z << 32));
+		r.n_pos = (long long)((unsigned long long)q[1].x | ((unsigned long long)q[1].z << 32));
+		r.best_row = (long long)((unsigned long long)q[2].x | ((unsigned long long)q[2].z << 32));
+		r.best_f0 = __longlong_as_double((long long)((unsigned long long)q[3].x | ((unsigned long long)q[3].z << 32)));
+		xmerge(b, r);
 	}
+	if (__any_sync(MC_FULL_MASK, failed)) { if (lane == 0) atomicExch(err, 1u); return; }
 #pragma unroll
 	for (int o = 16; o; o >>= 1) {
 		mc_scan_result other;
@@ -368,6 +394,8 @@ __global__ void __launch_bounds__(32) fold_send_kernel(const mc_scan_result *__r
 static int burst_streams(mc_ctx *ctx) {
 	McComm &cm = ctx->comm;
 	if (cm.xstream) return MC_OK;
+	MC_CUDA(cudaMalloc(&cm.d_ll_partials, (size_t)MC_XSLOTS * MC_SCAN_PARTS * 16 * sizeof(unsigned int)));
+	MC_CUDA(cudaMemset(cm.d_ll_partials, 0, (size_t)MC_XSLOTS * MC_SCAN_PARTS * 16 * sizeof(unsigned int)));
 	// highest priority: when an SM has room, the (tiny) exchange kernels go before the queued CTAs of
 	// the next scans -- otherwise the summaries of a burst would only leave once the NEXT burst has
 	// drained (measured: 70 us from the end of a burst to its summaries on the host)
@@ -443,6 +471,11 @@ extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, co
 				bargs.slot_off[slot] = slot_offset(epoch, slot);
 				req[i].lo = lo[i0 + i]; req[i].hi = hi[i0 + i]; req[i].center_row = center_rows[i0 + i];
 				req[i].partials_dev = (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result);
+				cm.slot_uses[slot]++;
+				if (cm.slot_uses[slot] == 0) cm.slot_uses[slot] = 1;   // never the tag of the cleared buffer
+				req[i].ll_partials_dev = cm.d_ll_partials + (size_t)slot * MC_SCAN_PARTS * 16;
+				req[i].ll_tag = cm.slot_uses[slot];
+				bargs.tag[slot] = cm.slot_uses[slot];
 				cm.slot_pending[slot] = 3;
 			}
 			rc = mc_launch_scan_batch(ctx, req, m, remove_marked, &ctx->slot_nparts[slot0 + i0], &push);
@@ -450,9 +483,7 @@ extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, co
 		}
 		if (dbg) tq2 = now();
 		if (!no_exchange) {
-			MC_CUDA(cudaEventRecord(cm.scans_done, ctx->stream));
-			MC_CUDA(cudaStreamWaitEvent(cm.xstream, cm.scans_done, 0));
-			fold_send_kernel<<<count, 32, 0, cm.xstream>>>((const mc_scan_result *)ctx->d_scan_slots, ctx->num_sms, bargs, slot0, push);
+			fold_send_kernel<<<count, 32, 0, cm.xstream>>>(cm.d_ll_partials, ctx->num_sms, bargs, slot0, push, d_err);
 			ctx->launches++;
 			MC_CUDA(cudaGetLastError());
 			// the combine of THIS burst goes out right behind its send (one warp per scan: world records

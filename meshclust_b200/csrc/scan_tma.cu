@@ -139,6 +139,8 @@ __device__ __forceinline__ void peer_store_words(const McPeerPush &push, int cta
 struct ScanDesc {
 	long long lo, hi, center_row;
 	ScanPartial *partials;
+	unsigned int *ll_partials;    // optional (burst path): this scan's CTA partials as {data, tag} words
+	unsigned int ll_tag;
 };
 struct ScanBatch {
 	ScanDesc d[MC_SCAN_BATCH];
@@ -363,6 +365,26 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			tscan_merge(b, other);
 		}
 		if (lane == 0) partials[blockIdx.x] = b;
+		if constexpr (PUSH == 2) {
+			// burst path: the exchange stream is not ordered behind this launch by an event (which would sit
+			// between two scan launches and undo their overlap) nor by a fence + counter (a microsecond at
+			// the end of every CTA): the partial is written a second time as eight {data, tag} words, each
+			// an atomic 8-byte store, and fold_send_kernel polls the tags
+			unsigned int *ll = batch.d[blockIdx.y].ll_partials;
+			if (ll) {
+				unsigned long long f[4];
+				f[0] = (unsigned long long)__shfl_sync(MC_FULL_MASK, b.n_eval, 0);
+				f[1] = (unsigned long long)__shfl_sync(MC_FULL_MASK, b.n_pos, 0);
+				f[2] = (unsigned long long)__shfl_sync(MC_FULL_MASK, b.best_row, 0);
+				f[3] = (unsigned long long)__double_as_longlong(__shfl_sync(MC_FULL_MASK, b.best_f0, 0));
+				if (lane < 8) {
+					const unsigned long long fld = (lane >> 1) == 0 ? f[0] : ((lane >> 1) == 1 ? f[1] : ((lane >> 1) == 2 ? f[2] : f[3]));
+					const unsigned int data = (lane & 1) ? (unsigned int)(fld >> 32) : (unsigned int)fld;
+					unsigned int *dst = ll + ((size_t)blockIdx.x * 8 + lane) * 2;
+					asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(data), "r"(batch.d[blockIdx.y].ll_tag) : "memory");
+				}
+			}
+		}
 		if constexpr (PUSH == 1) {
 			// sharded scan: this CTA's partial goes straight into every rank's inbox over NVLink
 			const McPeerPush &push = push_arg.v;
@@ -446,6 +468,8 @@ static int launch_tma_impl(mc_ctx *ctx, const McScanReq *req, int count, int rem
 	for (int i = 0; i < count; i++) {
 		batch.d[i].lo = req[i].lo; batch.d[i].hi = req[i].hi; batch.d[i].center_row = req[i].center_row;
 		batch.d[i].partials = (ScanPartial *)req[i].partials_dev;
+		batch.d[i].ll_partials = (unsigned int *)req[i].ll_partials_dev;
+		batch.d[i].ll_tag = req[i].ll_tag;
 		nparts_out[i] = (int)blocks;
 	}
 	static const bool no_pdl = getenv("MC_NO_PDL") != nullptr;
@@ -513,7 +537,7 @@ int mc_launch_scan_batch(mc_ctx *ctx, const McScanReq *req, int count, int remov
 int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                         void *partials_dev, int *nparts_out, const McPeerPush *push) {
 	McScanReq r;
-	r.lo = lo; r.hi = hi; r.center_row = center_row; r.partials_dev = partials_dev;
+	r.lo = lo; r.hi = hi; r.center_row = center_row; r.partials_dev = partials_dev; r.ll_partials_dev = nullptr; r.ll_tag = 0;
 	return mc_launch_scan_batch(ctx, &r, 1, remove_marked, nparts_out, push);
 }
 
