@@ -212,6 +212,13 @@ extern "C" int mc_host_segments(const uint8_t *s, int64_t len, int32_t *segs, in
 		else if (a - ce < 10) { ce = b; }
 		else { emit(cs, ce); cs = a; ce = b; }
 	};
+	// fast path: no N at all (the usual case) -> the whole record is one run
+	if (len > 0 && !memchr(s, 'N', (size_t)len) && !memchr(s, 'n', (size_t)len)) {
+		// a one-character record never closes its run in the reference (see above)
+		if (len == 1) return -1;
+		emit(0, len - 1);
+		return nseg;
+	}
 	int64_t start = -1;
 	for (int64_t i = 0; i < len; i++) {
 		const bool isn = (s[i] | 0x20) == 'n';

@@ -74,16 +74,20 @@ public:
 	void insert(int64_t id, uint64_t len) {
 		size_t front = 0, back = 0;
 		index_of(len, &front, &back);
-		std::vector<size_t> mins;
-		size_t minimum = std::numeric_limits<size_t>::max();
+		// least-filled candidate bin, the middle one among equals (the reference collects the minima in
+		// a vector and takes mins[mins.size() / 2]); two passes instead of a vector per insert
+		size_t minimum = std::numeric_limits<size_t>::max(), nmin = 0;
 		for (size_t i = front; i <= back; i++) {
 			const size_t sz = data_[i].items.size();
-			if (sz < minimum) { minimum = sz; mins.clear(); mins.push_back(i); }
-			else if (sz == minimum) mins.push_back(i);
+			if (sz < minimum) { minimum = sz; nmin = 1; }
+			else if (sz == minimum) nmin++;
 		}
 		// front > back leaves no candidate: the reference prints an error and then indexes an empty
 		// vector (undefined); it cannot happen for bounds taken from the same lengths
-		data_.at(mins.at(mins.size() / 2)).items.push_back({id, len});
+		size_t pick = data_.size(), seen = 0;
+		for (size_t i = front; i <= back; i++)
+			if (data_[i].items.size() == minimum && seen++ == nmin / 2) { pick = i; break; }
+		data_.at(pick).items.push_back({id, len});
 	}
 
 	// bvec::insert_finalize (bvec.cpp:209-218): per-bin std::sort by length (unstable: the same

@@ -896,12 +896,19 @@ int run_pipeline(Options opt) {
 	srand(10);
 
 	// ---- bvec layout from the lengths alone (Runner.cpp:342-350; bvec.cpp) ----------------------
+	const bool dbg_t = getenv("MC_DEBUG_TIMING") != nullptr;
+	Timer tsub;
+	auto sub = [&](const char *what) { if (dbg_t) fprintf(stderr, "  [rows: %-28s %.3f s]\n", what, tsub.lap()); };
 	BVec bv(ds.len, 1000);
+	sub("bvec bounds (sort lengths)");
 	for (int64_t i = 0; i < ds.n; i++) bv.insert(i, ds.len[i]);
+	sub("bvec insert");
 	bv.finalize();
+	sub("bvec per-bin sorts");
 	ds.id_of_row = bv.assign_rows();
 	ds.row_of_id.assign((size_t)ds.n, -1);
 	for (int64_t r = 0; r < ds.n; r++) ds.row_of_id[ds.id_of_row[r]] = r;
+	sub("row numbering");
 
 	// ---- upload in row order, encode, histograms (K1) -------------------------------------------
 	{
@@ -932,6 +939,7 @@ int run_pipeline(Options opt) {
 			ctx_thread.join();
 			abort();
 		}
+		sub("letters to row order + segments");
 		for (int64_t r = 0; r < ds.n; r++) seg_off[r + 1] = seg_off[r] + nseg[r];
 		std::vector<int32_t> segs((size_t)seg_off[ds.n] * 2);
 #pragma omp parallel for schedule(static)
