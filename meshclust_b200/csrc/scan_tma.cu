@@ -73,24 +73,32 @@ constexpr int TSCAN_SMEM_BUDGET = 216 * 1024;
 #ifndef MC_SCAN_SMALL_CTAS_PER_SM
 #define MC_SCAN_SMALL_CTAS_PER_SM 2
 #endif
+// A launch that carries several independent scans never needs room for a NEXT launch: its own scans
+// follow each other on the SMs, and what costs is the start and the end of every CTA.  Three smaller
+// CTAs per SM leave two streaming while one starts or ends (measured on the C2 shape: 5.34 -> 4.95 us
+// per scan; a single scan per launch is better off with two larger CTAs: 5.4 vs 7.0 us).
+#ifndef MC_SCAN_BATCH_CTAS_PER_SM
+#define MC_SCAN_BATCH_CTAS_PER_SM 3
+#endif
 constexpr int TSCAN_SMALL_ROW = 256;
 
 // A stage holds one consumer tile: RT consecutive rows + their McRowAux records.  RT = 32 (one row
 // per lane in the epilogue) while that fits 32 KB, fewer for very wide rows (lanes >= RT idle in
 // the epilogue, which is cheap next to a multi-KB row).  Every consumer warp owns a private ring
 // of D stages, so a warp never waits on a barrier more than one phase ahead of it.
-template <int RB>
+template <int RB, int CPS>
 struct TileCfg {
 	static constexpr int RT = (RB * 32 <= 32 * 1024) ? 32 : ((32 * 1024) / RB > 0 ? (32 * 1024) / RB : 1);
 	static constexpr int ROW_BYTES = RT * RB;
 	static constexpr int AUX_BYTES = RT * 32;
 	static constexpr int STAGE_BYTES = ((ROW_BYTES + AUX_BYTES + 127) / 128) * 128;
-	static constexpr int CTAS_PER_SM = RB <= TSCAN_SMALL_ROW ? MC_SCAN_SMALL_CTAS_PER_SM : 1;
+	static constexpr int CTAS_PER_SM = CPS;
 	static constexpr int NS_RAW = (TSCAN_SMEM_BUDGET / CTAS_PER_SM) / STAGE_BYTES;
 	static constexpr int NS_CAP = NS_RAW > TSCAN_MAX_STAGES ? TSCAN_MAX_STAGES : NS_RAW;
 	// two CTAs per SM: 11 consumers + the producer = 384 threads, i.e. 80 registers per thread (12 consumers
 	// would cap them at 72 and spill inside the tile loop)
-	static constexpr int MAXC = RB <= TSCAN_SMALL_ROW ? (CTAS_PER_SM == 2 ? 11 : TSCAN_MAX_CONSUMERS / CTAS_PER_SM) : 16;
+	// three CTAs: 7 consumers (256 threads); four: 5 consumers (192 threads)
+	static constexpr int MAXC = RB <= TSCAN_SMALL_ROW ? (CTAS_PER_SM == 2 ? 11 : (CTAS_PER_SM == 3 ? 7 : (CTAS_PER_SM == 4 ? 5 : TSCAN_MAX_CONSUMERS / CTAS_PER_SM))) : 16;
 	static constexpr int NCW = NS_CAP > MAXC ? MAXC : NS_CAP;   // active consumer warps
 	static constexpr int D = NS_CAP / NCW;                                                   // ring depth per consumer
 	static constexpr int NS = NCW * D;
@@ -146,15 +154,15 @@ struct ScanBatch {
 	ScanDesc d[MC_SCAN_BATCH];
 };
 
-template <int TB, int RB, int PUSH>
-__global__ void __launch_bounds__(32 * (1 + TileCfg<RB>::NCW), TileCfg<RB>::CTAS_PER_SM)
+template <int TB, int RB, int PUSH, int CPS>
+__global__ void __launch_bounds__(32 * (1 + TileCfg<RB, CPS>::NCW), CPS)
 scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, uint8_t *__restrict__ marks,
                 const __grid_constant__ ScanBatch batch, long long nrows_total, McModel model,
                 int remove_marked, PushArg<PUSH> push_arg) {
 	const long long lo = batch.d[blockIdx.y].lo, hi = batch.d[blockIdx.y].hi, center_row = batch.d[blockIdx.y].center_row;
 	ScanPartial *__restrict__ partials = batch.d[blockIdx.y].partials;
 	using C = RowCfg<RB>;
-	using T = TileCfg<RB>;
+	using T = TileCfg<RB, CPS>;
 	constexpr int NB = RB / TB;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t full_bar[TSCAN_MAX_STAGES];
@@ -442,13 +450,13 @@ int mc_launch_scan_fold(mc_ctx *ctx, const void *slots_dev, const int *nparts_de
 int mc_launch_scan_direct(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                           void *partials_dev, int *nparts_out);
 
-template <int TB, int RB, int PUSH>
-static int launch_tma_impl(mc_ctx *ctx, const McScanReq *req, int count, int remove_marked, int *nparts_out, const McPeerPush *push) {
-	using T = TileCfg<RB>;
+template <int TB, int RB, int PUSH, int CPS>
+static int launch_tma_cps(mc_ctx *ctx, const McScanReq *req, int count, int remove_marked, int *nparts_out, const McPeerPush *push) {
+	using T = TileCfg<RB, CPS>;
 	const size_t smem = (size_t)T::NS * T::STAGE_BYTES;
 	static bool attr_set[64] = {};   // function attributes are per device
 	if (!attr_set[ctx->device & 63]) {
-		MC_CUDA(cudaFuncSetAttribute(scan_tma_kernel<TB, RB, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		MC_CUDA(cudaFuncSetAttribute(scan_tma_kernel<TB, RB, PUSH, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set[ctx->device & 63] = true;
 	}
 	int64_t blocks = ctx->num_sms;
@@ -483,11 +491,23 @@ static int launch_tma_impl(mc_ctx *ctx, const McScanReq *req, int count, int rem
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = no_pdl ? 0 : 1;
-	MC_CUDA(cudaLaunchKernelEx(&cfg, scan_tma_kernel<TB, RB, PUSH>, (const uint8_t *)ctx->d_hist, ctx->d_aux, marks,
+	MC_CUDA(cudaLaunchKernelEx(&cfg, scan_tma_kernel<TB, RB, PUSH, CPS>, (const uint8_t *)ctx->d_hist, ctx->d_aux, marks,
 	                           batch, (long long)ctx->n, ctx->model, remove_marked, pa));
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
+}
+
+// rows up to 256 bytes: two CTAs per SM for a single scan per launch (room for the next launch of the
+// stream), three for a launch that carries several scans; wider rows: one
+template <int TB, int RB, int PUSH>
+static int launch_tma_impl(mc_ctx *ctx, const McScanReq *req, int count, int remove_marked, int *nparts_out, const McPeerPush *push) {
+	if constexpr (RB <= TSCAN_SMALL_ROW) {
+		if (count > 1 && PUSH != 1) return launch_tma_cps<TB, RB, PUSH, MC_SCAN_BATCH_CTAS_PER_SM>(ctx, req, count, remove_marked, nparts_out, push);
+		return launch_tma_cps<TB, RB, PUSH, MC_SCAN_SMALL_CTAS_PER_SM>(ctx, req, count, remove_marked, nparts_out, push);
+	} else {
+		return launch_tma_cps<TB, RB, PUSH, 1>(ctx, req, count, remove_marked, nparts_out, push);
+	}
 }
 
 template <int TB, int RB>
