@@ -14,6 +14,7 @@ int mc_upload_lut();
 int mc_launch_encode(mc_ctx *ctx);
 int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes);
 int mc_launch_point_stats(mc_ctx *ctx, const uint64_t *lens_dev);
+int mc_launch_point_stats_range(mc_ctx *ctx, int64_t row0, int64_t n, const uint64_t *lens_dev, cudaStream_t stream);
 int mc_launch_alive_reset(mc_ctx *ctx);
 int mc_launch_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, void *partials_dev, int *nparts_out);
 int64_t mc_scan_max_blocks(mc_ctx *ctx);
@@ -157,6 +158,8 @@ extern "C" void mc_ctx_destroy(mc_ctx *ctx) {
 	cudaFreeHost(ctx->h_pinned);
 	cudaFree(ctx->d_acc);
 	if (ctx->h_step) cudaFreeHost(ctx->h_step);
+	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+	for (int i = 0; i < 8; i++) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
 	cudaFree(ctx->d_ticket);
 	cudaFree(ctx->d_flags);
 	cudaStreamDestroy(ctx->own_stream);
@@ -627,6 +630,7 @@ extern "C" int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, con
 				MC_REQUIRE(l >= 0 && h < ctx->n && l <= h, MC_ERR_ARG, "scan range [%lld,%lld] invalid", (long long)l, (long long)h);
 				req[i].lo = l; req[i].hi = h; req[i].center_row = c;
 				req[i].partials_dev = (uint8_t *)ctx->d_scan_slots + (size_t)(slot0 + i0 + i) * MC_SCAN_PARTS * sizeof(mc_scan_result);
+				req[i].marks_dev = nullptr;
 				req[i].ll_partials_dev = nullptr;
 				req[i].ll_tag = 0;
 			}
@@ -1058,22 +1062,119 @@ extern "C" int mc_kmer_histograms_host(mc_ctx *ctx, const uint8_t *letters, cons
 	return mc_copy_histograms(ctx, hists_out);
 }
 
+// get_close for several centers over HOST histograms, as a pipeline: the rows are uploaded in chunks
+// on a copy stream while the compute stream derives the constants of the previous chunk and runs all
+// centers against it in one launch (every center keeps its own mark array); marks return chunk by
+// chunk.  What the call costs is the upload of the histograms over PCIe, not upload + compute.
 extern "C" int mc_scan_host(mc_ctx *ctx, const void *hists, int tbytes, int k, const uint64_t *lens, int64_t n,
                             const int64_t *center_rows, int ncenters, mc_scan_result *res, uint8_t *marks_out) {
 	MC_REQUIRE(ctx && hists && lens && center_rows && res && n > 0 && ncenters > 0, MC_ERR_ARG, "mc_scan_host: bad arguments");
 	MC_NEED_MODEL(ctx);
-	int rc = mc_load_histograms(ctx, hists, tbytes, k, lens, n);
-	if (rc) return rc;
-	rc = check_rows64(ctx, center_rows, ncenters);
-	if (rc) return rc;
+	MC_REQUIRE(k >= 1 && k <= 8, MC_ERR_UNSUPPORTED, "k=%d unsupported (1..8)", k);
+	MC_REQUIRE(tbytes == 1 || tbytes == 2, MC_ERR_ARG, "tbytes must be 1 or 2");
 	MC_REQUIRE(ncenters <= MC_SCAN_SLOTS, MC_ERR_ARG, "at most %d centers per call", MC_SCAN_SLOTS);
+	for (int c = 0; c < ncenters; c++) MC_REQUIRE(center_rows[c] >= 0 && center_rows[c] < n, MC_ERR_ARG, "row %lld out of range", (long long)center_rows[c]);
+	MC_CUDA(cudaSetDevice(ctx->device));
+	const int nbins = 1 << (2 * k);
+	const size_t rb = (size_t)nbins * tbytes;
+	constexpr int NCHUNK = 4;
+	const bool staged_shape = rb >= 16 && (tbytes == 1 ? rb <= 4096 : rb <= 2048);   // shapes of the TMA-staged scan kernel
+	const bool pipelined = staged_shape && ncenters <= MC_SCAN_BATCH && (int64_t)ncenters * NCHUNK <= MC_SCAN_SLOTS && n >= 4096 && !getenv("MC_SCAN_DIRECT");
+	if (!pipelined) {
+		// small inputs, many centers, or shapes only the direct-load kernel handles: upload, then scan by scan
+		int rc = mc_load_histograms(ctx, hists, tbytes, k, lens, n);
+		if (rc) return rc;
+		rc = ensure_scan_slots(ctx);
+		if (rc) return rc;
+		const size_t slot_bytes = (size_t)MC_SCAN_PARTS * sizeof(mc_scan_result);
+		for (int c = 0; c < ncenters; c++) {
+			rc = mc_launch_scan(ctx, center_rows[c], 0, n - 1, 0, (uint8_t *)ctx->d_scan_slots + (size_t)c * slot_bytes, &ctx->slot_nparts[c]);
+			if (rc) return rc;
+			if (marks_out) MC_CUDA(cudaMemcpyAsync(marks_out + (size_t)c * n, ctx->d_marks, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+		return mc_scan_collect(ctx, 0, ncenters, res);
+	}
+	// rows n .. n+ncenters-1 hold copies of the center rows, so that every chunk can be scanned as soon
+	// as it has landed, wherever its centers live
+	int rc = alloc_hist(ctx, n + ncenters, k, tbytes);
+	if (rc) return rc;
+	ctx->n = n;
 	rc = ensure_scan_slots(ctx);
 	if (rc) return rc;
-	const size_t slot_bytes = (size_t)MC_SCAN_PARTS * sizeof(mc_scan_result);
-	for (int c = 0; c < ncenters; c++) {
-		rc = mc_launch_scan(ctx, center_rows[c], 0, n - 1, 0, (uint8_t *)ctx->d_scan_slots + (size_t)c * slot_bytes, &ctx->slot_nparts[c]);
-		if (rc) return rc;
-		if (marks_out) MC_CUDA(cudaMemcpyAsync(marks_out + (size_t)c * n, ctx->d_marks, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+	if (!ctx->copy_stream) {
+		MC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+		for (int i = 0; i < 8; i++) MC_CUDA(cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming));
 	}
-	return mc_scan_collect(ctx, 0, ncenters, res);
+	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)(n + ncenters) * 8, (size_t)ncenters * (size_t)n + 64}));
+	if (rc) return rc;
+	rc = mc_ensure_pinned(ctx, (size_t)ncenters * rb + (size_t)ncenters * 8 + (size_t)NCHUNK * ncenters * MC_SCAN_PARTS * sizeof(mc_scan_result));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	uint64_t *d_lens = cv.take<uint64_t>((size_t)(n + ncenters));
+	uint8_t *d_marks_multi = cv.take<uint8_t>((size_t)ncenters * (size_t)n + 64);
+	uint8_t *d_hist = (uint8_t *)ctx->d_hist;
+	// the stream of the context may still be busy with earlier work on these buffers
+	MC_CUDA(cudaEventRecord(ctx->chunk_ev[NCHUNK], ctx->stream));
+	MC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[NCHUNK], 0));
+	// centers first (tiny): gathered on the host into pinned memory
+	uint8_t *h_cent = (uint8_t *)ctx->h_pinned;
+	uint64_t *h_clen = (uint64_t *)(h_cent + (size_t)ncenters * rb);
+	mc_scan_result *h_part = (mc_scan_result *)(h_clen + ncenters);
+	for (int c = 0; c < ncenters; c++) {
+		memcpy(h_cent + (size_t)c * rb, (const uint8_t *)hists + (size_t)center_rows[c] * rb, rb);
+		h_clen[c] = lens[center_rows[c]];
+	}
+	MC_CUDA(cudaMemcpyAsync(d_hist + (size_t)n * rb, h_cent, (size_t)ncenters * rb, cudaMemcpyHostToDevice, ctx->copy_stream));
+	MC_CUDA(cudaMemcpyAsync(d_lens + n, h_clen, (size_t)ncenters * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+	const int64_t per = ((n + NCHUNK - 1) / NCHUNK + 1023) / 1024 * 1024;   // chunk boundaries on 1024 rows
+	int nchunks = 0;
+	for (int64_t r0 = 0; r0 < n; r0 += per, nchunks++) {
+		const int64_t r1 = std::min(n, r0 + per);
+		MC_CUDA(cudaMemcpyAsync(d_hist + (size_t)r0 * rb, (const uint8_t *)hists + (size_t)r0 * rb, (size_t)(r1 - r0) * rb, cudaMemcpyHostToDevice, ctx->copy_stream));
+		MC_CUDA(cudaMemcpyAsync(d_lens + r0, lens + r0, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+		MC_CUDA(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->copy_stream));
+	}
+	const size_t slot_bytes = (size_t)MC_SCAN_PARTS * sizeof(mc_scan_result);
+	int chunk = 0;
+	for (int64_t r0 = 0; r0 < n; r0 += per, chunk++) {
+		const int64_t r1 = std::min(n, r0 + per);
+		MC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[chunk], 0));
+		if (chunk == 0) {
+			rc = mc_launch_point_stats_range(ctx, n, ncenters, d_lens + n, ctx->stream);
+			if (rc) return rc;
+		}
+		rc = mc_launch_point_stats_range(ctx, r0, r1 - r0, d_lens + r0, ctx->stream);
+		if (rc) return rc;
+		McScanReq req[MC_SCAN_BATCH];
+		for (int c = 0; c < ncenters; c++) {
+			req[c].lo = r0; req[c].hi = r1 - 1; req[c].center_row = n + c;
+			req[c].partials_dev = (uint8_t *)ctx->d_scan_slots + (size_t)(chunk * ncenters + c) * slot_bytes;
+			req[c].marks_dev = d_marks_multi + (size_t)c * (size_t)n;
+			req[c].ll_partials_dev = nullptr;
+			req[c].ll_tag = 0;
+		}
+		// no programmatic overlap with the kernel in front: it has just written the constants these scans
+		// read before their dependency wait
+		ctx->pdl_enabled = false;
+		rc = mc_launch_scan_batch(ctx, req, ncenters, 0, &ctx->slot_nparts[chunk * ncenters], nullptr);
+		ctx->pdl_enabled = true;
+		if (rc) return rc;
+		if (marks_out)
+			MC_CUDA(cudaMemcpy2DAsync(marks_out + r0, (size_t)n, d_marks_multi + r0, (size_t)n, (size_t)(r1 - r0), (size_t)ncenters, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	MC_CUDA(cudaMemcpyAsync(h_part, ctx->d_scan_slots, (size_t)nchunks * ncenters * slot_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->have_hist = true;
+	// fold: per center, the CTA partials of all its chunks
+	std::vector<mc_scan_result> tmp((size_t)nchunks * MC_SCAN_PARTS);
+	for (int c = 0; c < ncenters; c++) {
+		int np = 0;
+		for (int ch = 0; ch < nchunks; ch++) {
+			const int cnt = ctx->slot_nparts[ch * ncenters + c];
+			memcpy(tmp.data() + np, (const uint8_t *)h_part + (size_t)(ch * ncenters + c) * slot_bytes, (size_t)cnt * sizeof(mc_scan_result));
+			np += cnt;
+		}
+		fold_partials(tmp.data(), np, &res[c]);
+	}
+	return MC_OK;
 }

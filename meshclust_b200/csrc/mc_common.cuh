@@ -16,6 +16,7 @@
 struct McScanReq {          // one scan of a batch launch (host side)
 	long long lo, hi, center_row;
 	void *partials_dev;
+	void *marks_dev;          // optional: a mark array of its own for this scan (scans of one launch that all keep their marks)
 	void *ll_partials_dev;    // optional (burst path): MC_SCAN_PARTS x 8 {data, tag} words for this scan's CTA partials
 	unsigned int ll_tag;
 };
@@ -124,6 +125,7 @@ struct mc_ctx {
 	cudaStream_t stream = nullptr;
 	cudaStream_t own_stream = nullptr;
 	int64_t launches = 0;
+	bool pdl_enabled = true;   // scans are launched with programmatic stream serialization unless a caller switches it off
 
 	// sequences
 	int64_t n = 0;            // rows
@@ -144,6 +146,10 @@ struct mc_ctx {
 	McRowAux *d_aux = nullptr;
 	int64_t aux_capacity = 0;
 	bool have_hist = false;
+
+	// mc_scan_host: upload stream + one event per chunk of rows (created on first use)
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t chunk_ev[8] = {};
 
 	// staging for mc_permute_rows (allocated on first use, sized like the histograms)
 	void *d_hist_tmp = nullptr;

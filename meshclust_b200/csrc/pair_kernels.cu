@@ -8,19 +8,39 @@
 // per-point constants
 // ---------------------------------------------------------------------------------------------
 template <int TB>
-__global__ void point_stats_kernel(const uint8_t *__restrict__ hist, int nbins, int64_t n,
+__global__ void point_stats_kernel(const uint8_t *__restrict__ hist, int nbins, int64_t row0, int64_t n,
                                    const uint64_t *__restrict__ lens, McRowAux *__restrict__ aux) {
+	// rows [row0, row0 + n); lens[i] belongs to row row0 + i
 	const int lane = threadIdx.x & 31;
 	const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-	for (int64_t row = warp; row < n; row += nwarps) {
+	const int rb = nbins * TB;
+	for (int64_t i = warp; i < n; i += nwarps) {
+		const int64_t row = row0 + i;
 		unsigned long long m = 0, s = 0;
-		if (TB == 1) {
-			const uint8_t *p = hist + (size_t)row * nbins;
-			for (int i = lane; i < nbins; i += 32) { unsigned v = p[i]; m += v; s += v * v; }
+		const uint8_t *p = hist + (size_t)row * rb;
+		if (rb >= 16) {
+			// 16-byte loads; uint8: sum and sum of squares with two dot products per word
+			for (int c = lane; c < rb / 16; c += 32) {
+				const uint4 v = *reinterpret_cast<const uint4 *>(p + (size_t)c * 16);
+				const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					if (TB == 1) {
+						m += __dp4a(w[j], 0x01010101u, 0u);
+						s += __dp4a(w[j], w[j], 0u);
+					} else {
+						const unsigned long long a = w[j] & 0xffffu, b = w[j] >> 16;
+						m += a + b;
+						s += a * a + b * b;
+					}
+				}
+			}
+		} else if (TB == 1) {
+			for (int b = lane; b < nbins; b += 32) { unsigned v = p[b]; m += v; s += v * v; }
 		} else {
-			const uint16_t *p = reinterpret_cast<const uint16_t *>(hist) + (size_t)row * nbins;
-			for (int i = lane; i < nbins; i += 32) { unsigned long long v = p[i]; m += v; s += v * v; }
+			const uint16_t *q = reinterpret_cast<const uint16_t *>(p);
+			for (int b = lane; b < nbins; b += 32) { unsigned long long v = q[b]; m += v; s += v * v; }
 		}
 #pragma unroll
 		for (int o = 16; o; o >>= 1) {
@@ -29,24 +49,29 @@ __global__ void point_stats_kernel(const uint8_t *__restrict__ hist, int nbins, 
 		}
 		if (lane == 0) {
 			McRowAux a;
-			a.len = lens[row]; a.mag = m; a.sq = s; a.alive = 1; a.pad = 0;
+			a.len = lens[i]; a.mag = m; a.sq = s; a.alive = 1; a.pad = 0;
 			aux[row] = a;
 		}
 	}
 }
 
-int mc_launch_point_stats(mc_ctx *ctx, const uint64_t *lens_dev) {
+// constants of rows [row0, row0 + n) from their histograms and lens_dev[0 .. n)
+int mc_launch_point_stats_range(mc_ctx *ctx, int64_t row0, int64_t n, const uint64_t *lens_dev, cudaStream_t stream) {
 	const int threads = 256;
-	int64_t blocks = (ctx->n * 32 + threads - 1) / threads;
+	int64_t blocks = (n * 32 + threads - 1) / threads;
 	if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
 	if (blocks < 1) blocks = 1;
 	if (ctx->tbytes == 1)
-		point_stats_kernel<1><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, lens_dev, ctx->d_aux);
+		point_stats_kernel<1><<<(int)blocks, threads, 0, stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, row0, n, lens_dev, ctx->d_aux);
 	else
-		point_stats_kernel<2><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, ctx->n, lens_dev, ctx->d_aux);
+		point_stats_kernel<2><<<(int)blocks, threads, 0, stream>>>((const uint8_t *)ctx->d_hist, ctx->nbins, row0, n, lens_dev, ctx->d_aux);
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
+}
+
+int mc_launch_point_stats(mc_ctx *ctx, const uint64_t *lens_dev) {
+	return mc_launch_point_stats_range(ctx, 0, ctx->n, lens_dev, ctx->stream);
 }
 
 __global__ void alive_reset_kernel(McRowAux *__restrict__ aux, long long n) {

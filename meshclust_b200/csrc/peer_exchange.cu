@@ -471,6 +471,7 @@ extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, co
 				bargs.slot_off[slot] = slot_offset(epoch, slot);
 				req[i].lo = lo[i0 + i]; req[i].hi = hi[i0 + i]; req[i].center_row = center_rows[i0 + i];
 				req[i].partials_dev = (uint8_t *)ctx->d_scan_slots + (size_t)slot * MC_SCAN_PARTS * sizeof(mc_scan_result);
+				req[i].marks_dev = nullptr;
 				cm.slot_uses[slot]++;
 				if (cm.slot_uses[slot] == 0) cm.slot_uses[slot] = 1;   // never the tag of the cleared buffer
 				req[i].ll_partials_dev = cm.d_ll_partials + (size_t)slot * MC_SCAN_PARTS * 16;

@@ -147,6 +147,7 @@ __device__ __forceinline__ void peer_store_words(const McPeerPush &push, int cta
 struct ScanDesc {
 	long long lo, hi, center_row;
 	ScanPartial *partials;
+	uint8_t *marks;               // optional: this scan's own mark array (indexed by row) instead of the shared one
 	unsigned int *ll_partials;    // optional (burst path): this scan's CTA partials as {data, tag} words
 	unsigned int ll_tag;
 };
@@ -161,6 +162,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
                 int remove_marked, PushArg<PUSH> push_arg) {
 	const long long lo = batch.d[blockIdx.y].lo, hi = batch.d[blockIdx.y].hi, center_row = batch.d[blockIdx.y].center_row;
 	ScanPartial *__restrict__ partials = batch.d[blockIdx.y].partials;
+	if (batch.d[blockIdx.y].marks) marks = batch.d[blockIdx.y].marks;
 	using C = RowCfg<RB>;
 	using T = TileCfg<RB, CPS>;
 	constexpr int NB = RB / TB;
@@ -476,6 +478,7 @@ static int launch_tma_cps(mc_ctx *ctx, const McScanReq *req, int count, int remo
 	for (int i = 0; i < count; i++) {
 		batch.d[i].lo = req[i].lo; batch.d[i].hi = req[i].hi; batch.d[i].center_row = req[i].center_row;
 		batch.d[i].partials = (ScanPartial *)req[i].partials_dev;
+		batch.d[i].marks = (uint8_t *)req[i].marks_dev;
 		batch.d[i].ll_partials = (unsigned int *)req[i].ll_partials_dev;
 		batch.d[i].ll_tag = req[i].ll_tag;
 		nparts_out[i] = (int)blocks;
@@ -490,7 +493,7 @@ static int launch_tma_cps(mc_ctx *ctx, const McScanReq *req, int count, int remo
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
-	cfg.numAttrs = no_pdl ? 0 : 1;
+	cfg.numAttrs = (no_pdl || !ctx->pdl_enabled) ? 0 : 1;
 	MC_CUDA(cudaLaunchKernelEx(&cfg, scan_tma_kernel<TB, RB, PUSH, CPS>, (const uint8_t *)ctx->d_hist, ctx->d_aux, marks,
 	                           batch, (long long)ctx->n, ctx->model, remove_marked, pa));
 	ctx->launches++;
@@ -557,7 +560,7 @@ int mc_launch_scan_batch(mc_ctx *ctx, const McScanReq *req, int count, int remov
 int mc_launch_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                         void *partials_dev, int *nparts_out, const McPeerPush *push) {
 	McScanReq r;
-	r.lo = lo; r.hi = hi; r.center_row = center_row; r.partials_dev = partials_dev; r.ll_partials_dev = nullptr; r.ll_tag = 0;
+	r.lo = lo; r.hi = hi; r.center_row = center_row; r.partials_dev = partials_dev; r.marks_dev = nullptr; r.ll_partials_dev = nullptr; r.ll_tag = 0;
 	return mc_launch_scan_batch(ctx, &r, 1, remove_marked, nparts_out, push);
 }
 

@@ -231,6 +231,37 @@ def test_scan_batch_launch_equals_single_scans(ctx, k, n, monkeypatch):
     assert ctx.scan_collect(300, 5) == want[:5]
 
 
+@pytest.mark.parametrize("dtype,k,n,nc", [(np.uint8, 4, 20000, 10), (np.uint8, 5, 9000, 3), (np.uint16, 3, 6000, 16), (np.uint8, 4, 3000, 4), (np.uint8, 2, 5000, 20)])
+def test_scan_host_pipeline_equals_resident_scans(ctx, dtype, k, n, nc):
+    """mc_scan_host (chunked upload overlapped with the scans, every center with its own mark array)
+    against mc_load_histograms + one mc_scan per center on the resident rows"""
+    from meshclust_b200 import api
+    rng = np.random.default_rng(1500 + k)
+    nb = 4 ** k
+    H = _rand_hists(rng, n, nb, dtype, 255 if dtype == np.uint8 else 1500, clusters=6)
+    lens = (900 + rng.integers(0, 120, n)).astype(np.uint64)
+    mins, maxs, w = _model(4)
+    maxs[2] = 4.0 * nb
+    maxs[4] = 2.0 * nb
+    mins[4] = 0.5 * nb
+    centers = rng.integers(0, n, nc)
+    centers[0], centers[-1] = n - 1, 0
+    ctx.set_model(mins, maxs, w, 4)
+    marks = np.full((nc, n), 7, np.uint8)
+    got = ctx.scan_host(H, lens, k, centers, marks)
+    with api.Context(0) as c2:
+        c2.load_histograms(H, lens, k)
+        c2.set_model(mins, maxs, w, 4)
+        for i, c in enumerate(centers):
+            c2.alive_reset()
+            want, wm = c2.scan(int(c), 0, n - 1)
+            assert got[i] == want.as_tuple(), (i, got[i], want.as_tuple())
+            assert np.array_equal(marks[i], wm)
+    # the rows stay resident for later calls
+    res, _ = ctx.scan(int(centers[1]), 0, n - 1)
+    assert res.n_eval == n
+
+
 def test_scan_first_max_wins_and_null(ctx, oracle):
     # identical rows tie on f0: the first one in row order must win; f0 <= -1 everywhere -> no seed
     rng = np.random.default_rng(9)
