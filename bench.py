@@ -524,9 +524,11 @@ def main():
         # ---- second half of the metric: sequences clustered per second, FASTA in -> CLSTR out, through
         # the drop-in CLI (bin/meshclust) on the full C2 input; the reference CLI beside it on a bounded
         # sample (its training sorts are O(150 n log n 4^k) on the CPU)
-        if not args.no_extra and world == 1:
+        if not args.no_extra:
+            # at N > 1 the same input goes through `bin/meshclust --gpus N` (one process driving N GPUs: Phase A
+            # sharded, the rest on GPU 0); this rank's own CUDA context stays alive next to it
             try:
-                out["seqs_clustered"] = cli_leg(letters, offs, tmpl, cfg)
+                out["seqs_clustered"] = cli_leg(letters, offs, tmpl, cfg, world)
             except Exception as e:
                 out["seqs_clustered"] = {"error": str(e)[:200]}
         emit(out)
@@ -536,7 +538,7 @@ def main():
     return 0
 
 
-def cli_leg(letters, offs, tmpl, cfg):
+def cli_leg(letters, offs, tmpl, cfg, gpus=1):
     import re
     import tempfile
     from meshclust_b200 import build, synth
@@ -547,7 +549,7 @@ def cli_leg(letters, offs, tmpl, cfg):
         fa = os.path.join(d, "c2.fa")
         synth.write_fasta(fa, letters, offs, synth.headers_for(cfg.n, tmpl))
         t0 = time.perf_counter()
-        r = subprocess.run([cli, fa, "--id", str(cfg.identity), "--kmer", str(cfg.kmer), "--output", os.path.join(d, "o.clstr")],
+        r = subprocess.run([cli, fa, "--id", str(cfg.identity), "--kmer", str(cfg.kmer), "--gpus", str(gpus), "--output", os.path.join(d, "o.clstr")],
                            capture_output=True, text=True, timeout=600)
         wall = time.perf_counter() - t0
         if r.returncode != 0:
@@ -557,11 +559,11 @@ def cli_leg(letters, offs, tmpl, cfg):
         m = re.search(r"gpu context ([0-9.]+)s on a helper thread, waited ([0-9.]+)s", r.stdout)
         ctx_s = float(m.group(2)) if m else 0.0
         ncl = open(os.path.join(d, "o.clstr")).read().count(">Cluster")
-        res = {"workload": "c2 full (100k x 1.5 kb), bin/meshclust --id 0.97 --kmer 4", "wall_s": round(wall, 3),
+        res = {"workload": f"c2 full (100k x 1.5 kb), bin/meshclust --id 0.97 --kmer 4 --gpus {gpus}", "wall_s": round(wall, 3),
                "cuda_context_wait_s": round(ctx_s, 3), "value": cfg.n / wall, "value_excluding_cuda_context_wait": cfg.n / max(wall - ctx_s, 1e-9),
                "stages": [ln.strip() for ln in r.stdout.splitlines() if "[" in ln and "s]" in ln][:16],
                "unit": "seqs/s", "clusters": ncl}
-        if os.path.exists(_oracle.REF_BIN):
+        if os.path.exists(_oracle.REF_BIN) and gpus == 1:
             ns = 4000
             fs = os.path.join(d, "c2_sample.fa")
             synth.write_fasta(fs, letters[: offs[ns]], offs[: ns + 1], synth.headers_for(ns, tmpl))
