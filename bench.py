@@ -549,8 +549,11 @@ def cli_leg(letters, offs, tmpl, cfg, gpus=1):
         fa = os.path.join(d, "c2.fa")
         synth.write_fasta(fa, letters, offs, synth.headers_for(cfg.n, tmpl))
         t0 = time.perf_counter()
+        env = dict(os.environ)
+        if gpus > 1:
+            env.pop("OMP_NUM_THREADS", None)   # torchrun exports OMP_NUM_THREADS=1 for its ranks; the CLI is its own program
         r = subprocess.run([cli, fa, "--id", str(cfg.identity), "--kmer", str(cfg.kmer), "--gpus", str(gpus), "--output", os.path.join(d, "o.clstr")],
-                           capture_output=True, text=True, timeout=600)
+                           capture_output=True, text=True, timeout=600, env=env)
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             raise RuntimeError(r.stderr[-200:])
