@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden", "clstr")
 
 
-def var_len_fasta(path, n, ntemp, lmin, lmax, mu, seed, related=0.0, iupac=False, homopolymer=0):
+def var_len_fasta(path, n, ntemp, lmin, lmax, mu, seed, related=0.0, iupac=False, homopolymer=0, crlf=False):
     rng = np.random.default_rng(seed)
     temps = [rng.integers(0, 4, int(rng.integers(lmin, lmax)), dtype=np.uint8) for _ in range(ntemp)]
     if homopolymer:   # a long single-letter run in every template: some k-mer count exceeds 255 -> 16-bit histograms
@@ -38,6 +38,11 @@ def var_len_fasta(path, n, ntemp, lmin, lmax, mu, seed, related=0.0, iupac=False
             letters[s:s + int(rng.choice([1, 3, 12, 30]))] = ord("N")
         letters[rng.integers(0, letters.size, n)] = rng.choice(np.frombuffer(b"RYMKSWHBVD", np.uint8), n)
     synth.write_fasta(path, letters, np.array(offs, np.int64), [f">seq{i} template{tm[i]}" for i in range(n)])
+    if crlf:   # DOS line ends, a blank line inside a record and no newline at the very end (safe_getline, ChromListMaker.cpp:23-47)
+        data = open(path, "rb").read().replace(b"\n", b"\r\n")
+        first = data.index(b"\r\n", data.index(b"\r\n") + 2)
+        data = data[:first] + b"\r\n" + data[first:]
+        open(path, "wb").write(data.rstrip(b"\r\n"))
 
 
 # name -> (list of (file name, generator kwargs), CLI arguments)
@@ -55,6 +60,8 @@ CASES = {
     "H": ([("H.fa", dict(n=400, ntemp=8, lmin=150, lmax=260, mu=0.15, seed=19))], ["--id", "0.55", "--delta", "3"]),
     # low-complexity runs: the largest k-mer count exceeds 255, so the run uses 16-bit histograms (Runner.cpp:75-89)
     "I": ([("I.fa", dict(n=900, ntemp=12, lmin=900, lmax=1100, mu=0.03, seed=21, homopolymer=330))], ["--id", "0.90", "--kmer", "3"]),
+    # CRLF line ends, an empty line, no final newline: the serial FASTA parser (the parallel one hands such files over)
+    "J": ([("J.fa", dict(n=900, ntemp=9, lmin=300, lmax=360, mu=0.03, seed=23, crlf=True))], ["--id", "0.90", "--kmer", "3"]),
     "F": ([("F.fa", dict(n=1300, ntemp=20, lmin=260, lmax=420, mu=0.03, seed=17, iupac=True))],
           ["--id", "0.90", "--kmer", "4", "--sample", "2000", "--pivot", "10"]),
 }
