@@ -500,9 +500,11 @@ def main():
         for _ in range(reps):
             res = ctx2.scan_host(hnp, lnp, K, cr, mnp)
         e2e_s = (time.perf_counter() - t0) / reps
-        out["e2e"] = {"value": S * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * nbins + n * 8 + S * 8),
-                      "d2h_bytes_per_step": int(S * n + S * 32), "ms_per_step": e2e_s * 1e3,
-                      "call": "mc_scan_host (pinned host histograms -> S scans -> marks + summaries on the host)"}
+        # bytes mc_scan_host moves per call: histograms + lengths + copies of the S center rows up; S mark
+        # arrays + the CTA partial records of S scans x 4 chunks (160 x 32 B each) down
+        out["e2e"] = {"value": S * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * nbins + n * 8 + S * (nbins + 8)),
+                      "d2h_bytes_per_step": int(S * n + 4 * S * 160 * 32), "ms_per_step": e2e_s * 1e3,
+                      "call": "mc_scan_host (pinned host histograms -> chunked upload overlapped with S scans per chunk -> marks + summaries on the host)"}
         # parity spot-check of what was just timed (oracle as the checker only)
         import _oracle
         s_o, f0_o, fl_o = _oracle.oracle().scan(hist[:4000], lens[:4000], hist[cr[0]], int(lens[cr[0]]), mins, maxs, w, 4)
