@@ -60,6 +60,10 @@ CASES = {
     "H": ([("H.fa", dict(n=400, ntemp=8, lmin=150, lmax=260, mu=0.15, seed=19))], ["--id", "0.55", "--delta", "3"]),
     # low-complexity runs: the largest k-mer count exceeds 255, so the run uses 16-bit histograms (Runner.cpp:75-89)
     "I": ([("I.fa", dict(n=900, ntemp=12, lmin=900, lmax=1100, mu=0.03, seed=21, homopolymer=330))], ["--id", "0.90", "--kmer", "3"]),
+    # harder data (10-12 % mutation): the 3-feature model stays below 97.5 % accuracy, so the greedy selection
+    # (Trainer.cpp:603-646) goes on to 4 features (KULCZYNSKI2 joins) and Phase B runs all its iterations
+    "K": ([("K.fa", dict(n=2000, ntemp=40, lmin=300, lmax=500, mu=0.10, seed=31))], ["--id", "0.80", "--kmer", "3"]),
+    "L": ([("L.fa", dict(n=2500, ntemp=60, lmin=200, lmax=900, mu=0.12, seed=33, related=0.2))], ["--id", "0.80", "--kmer", "4"]),
     # CRLF line ends, an empty line, no final newline: the serial FASTA parser (the parallel one hands such files over)
     "J": ([("J.fa", dict(n=900, ntemp=9, lmin=300, lmax=360, mu=0.03, seed=23, crlf=True))], ["--id", "0.90", "--kmer", "3"]),
     "F": ([("F.fa", dict(n=1300, ntemp=20, lmin=260, lmax=420, mu=0.03, seed=17, iupac=True))],
