@@ -64,6 +64,12 @@ CASES = {
     # (Trainer.cpp:603-646) goes on to 4 features (KULCZYNSKI2 joins) and Phase B runs all its iterations
     "K": ([("K.fa", dict(n=2000, ntemp=40, lmin=300, lmax=500, mu=0.10, seed=31))], ["--id", "0.80", "--kmer", "3"]),
     "L": ([("L.fa", dict(n=2500, ntemp=60, lmin=200, lmax=900, mu=0.12, seed=33, related=0.2))], ["--id", "0.80", "--kmer", "4"]),
+    # --delta 0 (every center only sees its own members, nothing merges), few iterations
+    "M": ([("M.fa", dict(n=1500, ntemp=15, lmin=300, lmax=301, mu=0.03, seed=11))], ["--id", "0.90", "--kmer", "3", "--delta", "0", "--iterations", "3"]),
+    # small inputs: fewer points than pivots x picks (duplicated pivots, one bvec bin); 90 sequences with automatic k
+    # make the reference warn "Alignment may be too large for sampling" and end with a 4-feature model
+    "N": ([("N.fa", dict(n=200, ntemp=5, lmin=250, lmax=320, mu=0.03, seed=41))], ["--id", "0.90", "--kmer", "3"]),
+    "O": ([("O.fa", dict(n=90, ntemp=3, lmin=400, lmax=420, mu=0.02, seed=42))], ["--id", "0.95"]),
     # CRLF line ends, an empty line, no final newline: the serial FASTA parser (the parallel one hands such files over)
     "J": ([("J.fa", dict(n=900, ntemp=9, lmin=300, lmax=360, mu=0.03, seed=23, crlf=True))], ["--id", "0.90", "--kmer", "3"]),
     "F": ([("F.fa", dict(n=1300, ntemp=20, lmin=260, lmax=420, mu=0.03, seed=17, iupac=True))],
