@@ -475,17 +475,48 @@ struct Cluster {
 };
 
 // --align: identity cache of Feature::align (Feature.cpp:222-243), keyed by the id pair
-struct PairKeyHash {
-	size_t operator()(const std::pair<int64_t, int64_t> &k) const {
-		uint64_t x = ((uint64_t)k.first << 32) ^ (uint64_t)k.second;
-		x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33;
-		return (size_t)x;
+// Open-addressing table keyed by the unordered id pair: only find / insert are ever used (never
+// iteration), so it stands in for the reference's std::map<pair<id,id>,double> at a fraction of
+// the cost (a --align run makes millions of look-ups and inserts).
+class AlignCache {
+public:
+	AlignCache() { keys_.assign(1 << 16, EMPTY); vals_.resize(1 << 16); }
+	static uint64_t key_of(int64_t a, int64_t b) { return a < b ? ((uint64_t)a << 32) | (uint64_t)b : ((uint64_t)b << 32) | (uint64_t)a; }
+	const double *find(uint64_t key) const {
+		for (size_t i = slot(key);; i = (i + 1) & (keys_.size() - 1)) {
+			if (keys_[i] == key) return &vals_[i];
+			if (keys_[i] == EMPTY) return nullptr;
+		}
 	}
-};
-struct AlignCache {
-	// only find / insert by key are used (never iteration), so a hash table stands in for the
-	// reference's std::map
-	std::unordered_map<std::pair<int64_t, int64_t>, double, PairKeyHash> tab;
+	void set(uint64_t key, double v) {
+		if ((used_ + 1) * 5 > keys_.size() * 3) grow();
+		for (size_t i = slot(key);; i = (i + 1) & (keys_.size() - 1)) {
+			if (keys_[i] == key) { vals_[i] = v; return; }
+			if (keys_[i] == EMPTY) { keys_[i] = key; vals_[i] = v; used_++; return; }
+		}
+	}
+	// ids that have been the center of a scan: a pair (point, center) can only be in the table when the
+	// center has been one before -- a point that is still alive has never been a center itself
+	std::vector<char> was_center;
+
+private:
+	static constexpr uint64_t EMPTY = ~0ull;
+	size_t slot(uint64_t k) const {
+		k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+		return (size_t)k & (keys_.size() - 1);
+	}
+	void grow() {
+		std::vector<uint64_t> ok;
+		std::vector<double> ov;
+		ok.swap(keys_); ov.swap(vals_);
+		keys_.assign(ok.size() * 2, EMPTY);
+		vals_.resize(ok.size() * 2);
+		used_ = 0;
+		for (size_t i = 0; i < ok.size(); i++) if (ok[i] != EMPTY) set(ok[i], ov[i]);
+	}
+	std::vector<uint64_t> keys_;
+	std::vector<double> vals_;
+	size_t used_ = 0;
 };
 
 // one get_close over [lo,hi] in --align mode: every alive row of the range is aligned against the
@@ -499,11 +530,13 @@ void align_scan(Ctx &c, BVec &bv, AlignCache &cache, int64_t center_row, int64_t
 	std::vector<size_t> need;
 	std::vector<double> ident(rows.size());
 	const int64_t cid = ds.id_of_row[center_row];
+	if (cache.was_center.empty()) cache.was_center.assign((size_t)ds.n, 0);
+	const bool seen_before = cache.was_center[(size_t)cid] != 0;
+	cache.was_center[(size_t)cid] = 1;
 	for (size_t i = 0; i < rows.size(); i++) {
 		const int64_t pid = ds.id_of_row[rows[i]];
-		const auto key = pid < cid ? std::make_pair(pid, cid) : std::make_pair(cid, pid);
-		auto it = cache.tab.find(key);
-		if (it != cache.tab.end()) ident[i] = it->second;
+		const double *hit = seen_before ? cache.find(AlignCache::key_of(pid, cid)) : nullptr;
+		if (hit) ident[i] = *hit;
 		else { need.push_back(i); a.push_back((int32_t)rows[i]); b.push_back((int32_t)center_row); }
 	}
 	if (!need.empty()) {
@@ -512,8 +545,7 @@ void align_scan(Ctx &c, BVec &bv, AlignCache &cache, int64_t center_row, int64_t
 		for (size_t t = 0; t < need.size(); t++) {
 			const double v = (double)mt[t] / ln[t];
 			ident[need[t]] = v;
-			const int64_t pid = ds.id_of_row[rows[need[t]]];
-			cache.tab[pid < cid ? std::make_pair(pid, cid) : std::make_pair(cid, pid)] = v;
+			cache.set(AlignCache::key_of(ds.id_of_row[rows[need[t]]], cid), v);
 		}
 	}
 	res.n_eval = (int64_t)rows.size();
@@ -740,11 +772,11 @@ void mean_shift(Ctx &c, BVec &bv) {
 				std::vector<int64_t> good;
 				for (int64_t q = cb[j]; q < ce[j]; q++) {
 					const int64_t pid = ds.id_of_row[cand[q]];
-					const auto key = pid < cid ? std::make_pair(pid, cid) : std::make_pair(cid, pid);
-					auto it = cache.tab.find(key);
+					const uint64_t key = AlignCache::key_of(pid, cid);
+					const double *hit = cache.find(key);
 					double v;
-					if (it != cache.tab.end()) v = it->second;
-					else { v = ds.len[pid] > 0 ? 0.0 : std::nan(""); cache.tab[key] = v; }
+					if (hit) v = *hit;
+					else { v = ds.len[pid] > 0 ? 0.0 : std::nan(""); cache.set(key, v); }
 					const double sum = std::fma(c.model.w[1], (v - 0.0) / (1.0 - 0.0), c.model.w[0]);
 					if (std::round(1.0 / (1 + std::exp(-sum))) == 1.0) good.push_back(cand[q]);
 				}
@@ -770,11 +802,11 @@ void mean_shift(Ctx &c, BVec &bv) {
 			// Trainer::merge on two clones: both strings are empty -> 0/0 = NaN unless the pair is cached
 			for (size_t q = 0; q < pa.size(); q++) {
 				const int64_t ia = ds.id_of_row[pa[q]], ib = ds.id_of_row[pb[q]];
-				const auto key = ia < ib ? std::make_pair(ia, ib) : std::make_pair(ib, ia);
-				auto it = cache.tab.find(key);
+				const uint64_t key = AlignCache::key_of(ia, ib);
+				const double *hit = cache.find(key);
 				double v;
-				if (it != cache.tab.end()) v = it->second;
-				else { v = std::nan(""); cache.tab[key] = v; }
+				if (hit) v = *hit;
+				else { v = std::nan(""); cache.set(key, v); }
 				const double sum = std::fma(c.model.w[1], (v - 0.0) / (1.0 - 0.0), c.model.w[0]);
 				f0[q] = v;
 				fl[q] = std::round(1.0 / (1 + std::exp(-sum))) == 1.0;
