@@ -12,8 +12,11 @@ so they are independent and mc_scan_enqueue_many sends them as one launch of the
            2x the 126 MB L2) and consecutive launches rotate through the replicas, so every launch
            streams its rows from HBM ("inputs larger than L2").
   e2e    : the same S-center pass through the host-buffer C-ABI call mc_scan_host(): pinned host
-           histograms -> HBM, S scans, marks + summaries back to the host, all inside the timed
-           region.
+           histograms -> HBM (in chunks, overlapped with the scans of the previous chunk), S scans,
+           marks + summaries back to the host, all inside the timed region.
+  --gpus N (torchrun, one process per GPU): every rank holds all N*n points and evaluates its n of
+           every scan; the summaries cross GPUs through NVLink peer inboxes (CUDA IPC) on a second
+           stream; value = evals of all ranks / max-over-ranks time.  DESIGN.md section 5.
   roofline: the scan kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json);
            algorithmic bytes per eval = 4^k + 33.
   cpu_baseline: the compiled unmodified reference (oracle/_ref/libmcref.so, Feature::compute +
