@@ -18,6 +18,7 @@
 #include <map>
 #include <set>
 #include <stdexcept>
+#include <future>
 #include <thread>
 #include <unordered_map>
 
@@ -73,6 +74,7 @@ struct Model {
 struct Ctx {
 	mc_ctx *gpu = nullptr;            // rank 0: holds the sequences, runs training, Phase B and the Phase-A tail
 	std::vector<mc_ctx *> ranks;      // all GPUs that share the Phase-A scans (ranks[0] == gpu)
+	std::future<std::vector<int>> by_length;   // Trainer::split's first sort, started as soon as the lengths are known
 	std::thread ranks_thread;         // creates the contexts of ranks 1.. in the background
 	int ranks_rc = MC_OK;
 	std::string ranks_err;
@@ -115,6 +117,18 @@ std::vector<double> align_ids(Ctx &c, const std::vector<Pair> &pairs) {
 	return id;
 }
 
+// point ids in the order Trainer::split's first std::sort leaves them (Trainer.cpp:672-675): unstable
+// sort of (length, id) records by length, ids initially ascending
+std::vector<int> sort_ids_by_length(const std::vector<uint64_t> &len) {
+	struct LenId { uint64_t key; int id; };
+	std::vector<LenId> rec(len.size());
+	for (size_t i = 0; i < len.size(); i++) rec[i] = {len[i], (int)i};
+	std::sort(rec.begin(), rec.end(), [](const LenId &a, const LenId &b) { return a.key < b.key; });
+	std::vector<int> ids(len.size());
+	for (size_t i = 0; i < len.size(); i++) ids[i] = rec[i].id;
+	return ids;
+}
+
 // Trainer::split (Trainer.cpp:653-783)
 std::vector<Pair> trainer_split(Ctx &c) {
 	const Dataset &ds = c.ds;
@@ -127,15 +141,11 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	// The reference sorts Point* arrays with comparators that look the key up through the pointer.
 	// std::sort's permutation depends only on the comparison outcomes, so sorting (key, id) records
 	// with the same comparator on the key yields the identical order without the random accesses.
-	struct LenId { uint64_t key; int id; };
 	struct KeyId { uint16_t key; int id; };
-	// :672-675 unstable sort by length, then the median-length point
-	{
-		std::vector<LenId> rec((size_t)n);
-		for (int64_t i = 0; i < n; i++) rec[i] = {ds.len[i], (int)i};
-		std::sort(rec.begin(), rec.end(), [](const LenId &a, const LenId &b) { return a.key < b.key; });
-		for (int64_t i = 0; i < n; i++) points[i] = rec[i].id;
-	}
+	// :672-675 unstable sort by length, then the median-length point (sorted on a helper thread while
+	// the sequences were uploaded and counted: it needs nothing but the lengths)
+	if (c.by_length.valid()) points = c.by_length.get();
+	else points = sort_ids_by_length(ds.len);
 	const int begin_pt = points[points.size() / 2];
 	// :681-684 sort by distance to it
 	{
@@ -908,6 +918,7 @@ int run_pipeline(Options opt) {
 	ds.len.resize((size_t)ds.n);
 	for (int64_t i = 0; i < ds.n; i++) ds.len[i] = (uint64_t)(ds.fa.offsets[i + 1] - ds.fa.offsets[i]);
 	printf("Read %lld sequences  [%.2fs]\n", (long long)ds.n, tm.lap());
+	if (!opt.align && opt.similarity >= 0.6) c.by_length = std::async(std::launch::async, [&ds]() { return sort_ids_by_length(ds.len); });
 
 	// ---- k (Runner.cpp:265-292 find_k) ----------------------------------------------------------
 	c.k = opt.k;
