@@ -1,11 +1,17 @@
-"""Point sharding across GPUs: each rank holds a contiguous block of the
-rows, centers are replicated, and a sharded get_close needs one tiny exchange per scan:
+"""Point sharding across GPUs -- the collective-library path.
+
+The product path exchanges scan summaries through NVLink peer inboxes inside / behind the scan
+kernels (csrc/peer_exchange.cu; mc_scan_sharded_*, mc_accumulate_step_sharded).  This module is what
+`bench.py --gpus N` falls back to when peer memory cannot be opened between the processes, and what
+the CPU tests run over gloo: each rank holds a block of the rows, centers are replicated, and a
+sharded get_close needs one tiny exchange per scan:
 
     positives / evaluated : SUM
     arg-max of f0         : the reference keeps the FIRST maximum in iteration order
                             (Trainer.cpp:99), i.e. lexicographic (f0 descending, global row ascending)
 
-implemented as three all-reduces on a handful of scalars (NCCL on GPUs, gloo in the CPU tests).
+as three all-reduces on a handful of scalars, or one all-gather of the per-rank records folded on the
+host (NCCL on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
