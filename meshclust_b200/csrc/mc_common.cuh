@@ -110,7 +110,6 @@ struct McComm {
 	cudaEvent_t done = nullptr;                // recorded behind the last combine
 	uint8_t *marks_target = nullptr;           // sharded Phase A: the marks array of the rank that runs the tail
 	cudaStream_t xstream = nullptr;            // exchange stream of the burst path (fold + send + combine)
-	cudaEvent_t scans_done = nullptr;          // recorded on the scan stream behind a burst
 	unsigned int *d_ll_partials = nullptr;     // per exchange slot: MC_SCAN_PARTS CTA partials as {data, tag} words (burst path)
 	unsigned int slot_uses[MC_XSLOTS] = {};
 	cudaEvent_t burst_done[4] = {};            // per bank of MC_SCAN_BATCH slots: the burst's summaries are on the host

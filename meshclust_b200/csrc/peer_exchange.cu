@@ -110,7 +110,7 @@ static void comm_release(mc_ctx *ctx) {
 	cudaFree(cm.inbox);
 	cudaFree(cm.d_out);
 	if (cm.h_out) { cudaFreeHost(cm.h_out); cudaEventDestroy(cm.done); }
-	if (cm.xstream) { cudaStreamSynchronize(cm.xstream); cudaStreamDestroy(cm.xstream); cudaEventDestroy(cm.scans_done); }
+	if (cm.xstream) { cudaStreamSynchronize(cm.xstream); cudaStreamDestroy(cm.xstream); }
 	for (int b = 0; b < 4; b++) if (cm.burst_done[b]) cudaEventDestroy(cm.burst_done[b]);
 	cudaFree(cm.d_ll_partials);
 	cm = McComm();
@@ -402,7 +402,6 @@ static int burst_streams(mc_ctx *ctx) {
 	int prio_lo = 0, prio_hi = 0;
 	MC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	MC_CUDA(cudaStreamCreateWithPriority(&cm.xstream, cudaStreamNonBlocking, prio_hi));
-	MC_CUDA(cudaEventCreateWithFlags(&cm.scans_done, cudaEventDisableTiming));
 	if (!cm.h_out) {
 		MC_CUDA(cudaMallocHost(&cm.h_out, (size_t)MC_XSLOTS * sizeof(mc_scan_result) + 64));
 		MC_CUDA(cudaEventCreateWithFlags(&cm.done, cudaEventDisableTiming));
