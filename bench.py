@@ -222,8 +222,8 @@ def cpu_reference_rate(hist, lens, mins, maxs, w, centers, target_s: float, step
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)   # ~0.1 s of timed region: long enough for the clock sampler
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the C4-shape roofline probe")
     ap.add_argument("--scaling-only", action="store_true", help="development: skip the e2e and CPU-baseline legs too")
