@@ -1141,10 +1141,10 @@ extern "C" int mc_scan_host(mc_ctx *ctx, const void *hists, int tbytes, int k, c
 		MC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[chunk], 0));
 		if (chunk == 0) {
 			rc = mc_launch_point_stats_range(ctx, n, ncenters, d_lens + n, ctx->stream);
-			if (rc) return rc;
+			if (rc) break;
 		}
 		rc = mc_launch_point_stats_range(ctx, r0, r1 - r0, d_lens + r0, ctx->stream);
-		if (rc) return rc;
+		if (rc) break;
 		McScanReq req[MC_SCAN_BATCH];
 		for (int c = 0; c < ncenters; c++) {
 			req[c].lo = r0; req[c].hi = r1 - 1; req[c].center_row = n + c;
@@ -1158,9 +1158,17 @@ extern "C" int mc_scan_host(mc_ctx *ctx, const void *hists, int tbytes, int k, c
 		ctx->pdl_enabled = false;
 		rc = mc_launch_scan_batch(ctx, req, ncenters, 0, &ctx->slot_nparts[chunk * ncenters], nullptr);
 		ctx->pdl_enabled = true;
-		if (rc) return rc;
-		if (marks_out)
-			MC_CUDA(cudaMemcpy2DAsync(marks_out + r0, (size_t)n, d_marks_multi + r0, (size_t)n, (size_t)(r1 - r0), (size_t)ncenters, cudaMemcpyDeviceToHost, ctx->stream));
+		if (rc) break;
+		if (marks_out && cudaMemcpy2DAsync(marks_out + r0, (size_t)n, d_marks_multi + r0, (size_t)n, (size_t)(r1 - r0), (size_t)ncenters, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) {
+			mc_set_error("mc_scan_host: copying the marks back failed: %s", cudaGetErrorString(cudaGetLastError()));
+			rc = MC_ERR_CUDA;
+			break;
+		}
+	}
+	if (rc) {   // the caller's buffers must not be in flight when the call returns
+		cudaStreamSynchronize(ctx->copy_stream);
+		cudaStreamSynchronize(ctx->stream);
+		return rc;
 	}
 	MC_CUDA(cudaMemcpyAsync(h_part, ctx->d_scan_slots, (size_t)nchunks * ncenters * slot_bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
