@@ -1,20 +1,26 @@
 // K2a, the headline kernel: Trainer::get_close (Trainer.cpp:34-114) + bvec::remove_available
-// (bvec.cpp:290-317) for ONE center against every row of an inclusive row range.
+// (bvec.cpp:290-317) for ONE center against every row of an inclusive row range (several such scans
+// per launch when they are independent of each other, blockIdx.y = scan).
 //
-// HBM-bound streaming kernel, warp-specialised and persistent (one CTA per SM):
+// HBM-bound streaming kernel, warp-specialised; the CTAs of a scan are persistent over its tiles:
 //   * warp 0 = producer: one lane per ring slot feeds the shared-memory stages with 1-D TMA bulk
-//     copies (cp.async.bulk ... mbarrier::complete_tx): per stage one copy of TR contiguous
-//     histogram rows and one of their 32-byte McRowAux records.  The ring is as deep as shared
-//     memory allows (up to ~220 KB in flight per SM), so HBM latency never reaches the math.
-//   * warps 1..NCW = consumers: a warp owns 32 consecutive rows ("super-tile" = 32/TR stages),
-//     reduces them against the center held in registers (VABSDIFF4 / IDP.4A on 16-byte LDS),
-//     transposes the partials so lane l owns row l, and runs the FP64 feature + GLM epilogue on
-//     all 32 lanes; marks, alive flags, count and arg-max follow.
+//     copies (cp.async.bulk ... mbarrier::complete_tx): per stage one copy of RT contiguous
+//     histogram rows and one of their 32-byte McRowAux records.  One CTA per SM with ~216 KB in
+//     flight for rows of 1 KB and more; two (single scan) or three (several scans per launch) smaller
+//     CTAs per SM for rows up to 256 bytes, so that the next scan is resident while this one ends.
+//   * the other warps = consumers: a warp takes a tile of RT rows, reduces them against the center
+//     held in registers (VABSDIFF4 / IDP.4A on 16-byte LDS), transposes the partials so lane l owns
+//     row l, and runs the FP64 feature + GLM epilogue on all 32 lanes; marks, alive flags, count and
+//     arg-max follow.
+//   * programmatic dependent launch: everything up to the epilogue of a warp's first two tiles runs
+//     BEFORE griddepcontrol.wait -- only the alive flags (and the right to write) depend on the previous
+//     scan of the stream; histograms and the constants len / mag / sum p^2 are immutable while scans run.
 //   * every CTA leaves one partial (count, positives, arg-max); the <= 148-entry fold is done by the
-//     reader of the result (host), which keeps a threadfence + atomic ticket + last-CTA pass out
-//     of a kernel whose whole body is a few microseconds.
-// Dead rows are copied too ("dense" mode): the alive flag travels inside McRowAux, so there is no
-// dependent flag load before the row traffic starts.
+//     reader of the result (host, the fused tail kernel, or the exchange stream), which keeps a
+//     threadfence + atomic ticket + last-CTA pass out of a kernel whose whole body is a few microseconds.
+//   * multi-GPU variants (PUSH): this rank's blocks of tiles only; CTA partials go to the peers' inboxes
+//     from the kernel (direct) or are left as tag-polled copies for the exchange stream (burst).
+// Dead rows are copied too; the host compacts the row arrays as Phase A consumes them (mc_permute_rows).
 #include "pair_core.cuh"
 
 struct ScanPartial {
