@@ -112,6 +112,12 @@ int mc_pair_features(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m,
 int mc_pair_classify(mc_ctx *ctx, const int32_t *a, const int32_t *b, int64_t m, double *sum_out,
                      double *f0_out, uint8_t *flag_out, double *feats_out);
 
+/* Number of similar / not-similar decisions (mc_scan, mc_accumulate_step, mc_accumulate_run,
+ * mc_update_centers, mc_pair_classify with flag_out) this context has taken on a GLM sum within
+ * 1e-9 of the decision threshold (round(1/(1+exp(-sum))) == 1, Trainer.cpp:95,102) -- the only
+ * pairs whose decision a differently rounded exp() could change.  reset != 0 zeroes the count. */
+int mc_near_threshold_count(mc_ctx *ctx, int64_t *count_out, int reset);
+
 typedef struct mc_scan_result {
 	int64_t n_eval;   /* alive rows evaluated in [lo,hi] */
 	int64_t n_pos;    /* rows classified similar (marked and removed from the alive set) */
@@ -221,6 +227,37 @@ typedef struct mc_step_result {
  * hi < lo is an empty range (no evaluation; nearest_row = -1). */
 int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart,
                        mc_step_result *res, int64_t *marked_rows_out, int64_t cap);
+
+typedef struct mc_run_stats {
+	int64_t n_clusters;       /* centers pushed by accumulate() */
+	int64_t n_scans;          /* get_close calls over a non-empty range */
+	int64_t n_evals;          /* (center, point) pairs evaluated */
+	int64_t n_near_threshold; /* of those, pairs whose GLM sum lies within 1e-9 of the decision threshold */
+	int64_t n_steps;          /* iterations of accumulate()'s inner loop, empty ranges included */
+	double device_seconds;    /* time the loop spent on the GPU */
+} mc_run_stats;
+
+/* The whole of ClusterFactory::MS's first phase -- `while (last) accumulate(&last, points, ...)`
+ * (ClusterFactory.cpp:722-729 with accumulate, :637-714) -- in one call and one kernel launch: the
+ * bvec bookkeeping (bvec.cpp: pop :27-38, get_range :247-278 with index_of :123-149 and
+ * inner_index_of :52-120, erase :281-285, remove_available :290-317), Trainer::get_close
+ * (Trainer.cpp:34-114) and get_mean (ClusterFactory.cpp:382-425) run in a persistent device loop;
+ * nothing returns to the host between two scans.
+ * Rows must have been loaded in the bvec's iteration order: bin after bin, and inside a bin in the
+ * order bvec::insert_finalize's sort left (non-decreasing length; checked, MC_ERR_ARG otherwise).
+ * bin_bounds[nbins] are the bvec's bounds (bvec.cpp:10-24), bin_first_row[nbins + 1] the first row of
+ * every bin (bin_first_row[nbins] = number of rows).  similarity is --id (the length window of a
+ * center is [len * id, len / id], ClusterFactory.cpp:651-652).
+ * Outputs (capacity: n rows each, cluster_offsets_out n + 1): cluster c has center row
+ * center_rows_out[c] and the members member_rows_out[cluster_offsets_out[c] ..
+ * cluster_offsets_out[c + 1]) in the order accumulate() collected them (seed first).
+ * The run starts from a fresh bvec (all rows alive) and keeps its own alive set: the alive flags
+ * mc_scan / mc_accumulate_step use are neither read nor written.
+ * MC_ERR_UNSUPPORTED for histogram rows the staged scan kernel does not handle (k = 1, k >= 7) or a
+ * bvec with more bins than one SM's shared memory holds (~5000): use mc_accumulate_step then. */
+int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t *bin_bounds,
+                      const int64_t *bin_first_row, int64_t nbins, int64_t *center_rows_out,
+                      int64_t *cluster_offsets_out, int64_t *member_rows_out, mc_run_stats *stats);
 
 /* Copy histograms, point constants, alive flags and the model of `src` into `dst`, a context on
  * another GPU of the same process (device-to-device over NVLink): the one-time replication that

@@ -31,7 +31,7 @@ EXPORTS = [
     "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_copy_digits",
     "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
     "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
-    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_permute_rows", "mc_reserve_permute", "mc_comm_init", "mc_comm_connect", "mc_comm_connect_local",
+    "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_accumulate_run", "mc_near_threshold_count", "mc_permute_rows", "mc_reserve_permute", "mc_comm_init", "mc_comm_connect", "mc_comm_connect_local",
     "mc_scan_sharded_enqueue", "mc_scan_sharded_enqueue_many", "mc_scan_sharded_collect", "mc_scan_sharded_combine", "mc_scan_sharded_wait", "mc_scan_sharded_burst", "mc_clone_points", "mc_accumulate_step_sharded", "mc_update_centers", "mc_align_pairs",
     "mc_kmer_histograms_host", "mc_scan_host",
 ]
@@ -46,6 +46,11 @@ class ScanResult(C.Structure):
 
 class StepResult(C.Structure):
     _fields_ = [("scan", ScanResult), ("nearest_row", C.c_int64), ("n_members", C.c_int64)]
+
+
+class RunStats(C.Structure):
+    _fields_ = [("n_clusters", C.c_int64), ("n_scans", C.c_int64), ("n_evals", C.c_int64), ("n_near_threshold", C.c_int64),
+                ("n_steps", C.c_int64), ("device_seconds", C.c_double)]
 
 
 _lib.mc_version.restype = C.c_char_p
@@ -329,6 +334,26 @@ class Context:
         _check(_lib.mc_accumulate_step(self._h, C.c_int64(center_row), C.c_int64(lo), C.c_int64(hi), C.c_int(1 if restart else 0),
                                        C.byref(res), _p(rows), C.c_int64(rows.size)))
         return res, rows[: res.scan.n_pos].copy()
+
+    def accumulate_run(self, similarity: float, bin_bounds, bin_first_row):
+        """ClusterFactory::MS's first phase (all accumulate() calls) in one persistent kernel.
+        Returns (center_rows[nc], cluster_offsets[nc + 1], member_rows[n], RunStats)."""
+        bounds = np.ascontiguousarray(bin_bounds, np.uint64)
+        first = np.ascontiguousarray(bin_first_row, np.int64)
+        n = int(self.n)
+        centers = np.zeros(max(n, 1), np.int64)
+        offs = np.zeros(n + 1, np.int64)
+        members = np.zeros(max(n, 1), np.int64)
+        st = RunStats()
+        _check(_lib.mc_accumulate_run(self._h, C.c_double(similarity), _p(bounds), _p(first), C.c_int64(bounds.size),
+                                      _p(centers), _p(offs), _p(members), C.byref(st)))
+        nc = int(st.n_clusters)
+        return centers[:nc].copy(), offs[:nc + 1].copy(), members[:int(offs[nc])].copy(), st
+
+    def near_threshold_count(self, reset: bool = False) -> int:
+        out = C.c_int64(0)
+        _check(_lib.mc_near_threshold_count(self._h, C.byref(out), C.c_int(1 if reset else 0)))
+        return int(out.value)
 
     def permute_rows(self, old_of_new, n_alive: int):
         o = np.ascontiguousarray(old_of_new, np.int64)

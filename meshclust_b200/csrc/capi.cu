@@ -116,6 +116,9 @@ extern "C" int mc_ctx_create(mc_ctx **out, int device) {
 	MC_CUDA(cudaMemsetAsync(ctx->d_ticket, 0, 16 * sizeof(unsigned int), ctx->stream));
 	MC_CUDA(cudaMalloc(&ctx->d_flags, 16 * sizeof(unsigned int)));
 	MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 16 * sizeof(unsigned int), ctx->stream));
+	MC_CUDA(cudaMalloc(&ctx->d_near, 64));
+	MC_CUDA(cudaMemsetAsync(ctx->d_near, 0, 64, ctx->stream));
+	ctx->model.near = ctx->d_near;
 	lap("stream + small allocations");
 	int rc = mc_upload_lut();
 	if (rc) { delete ctx; return rc; }
@@ -162,6 +165,7 @@ extern "C" void mc_ctx_destroy(mc_ctx *ctx) {
 	for (int i = 0; i < 8; i++) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
 	cudaFree(ctx->d_ticket);
 	cudaFree(ctx->d_flags);
+	cudaFree(ctx->d_near);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -520,15 +524,8 @@ extern "C" int mc_pair_classify(mc_ctx *ctx, const int32_t *a, const int32_t *b,
 // row order wins, Trainer.cpp:99)
 static void fold_partials(const mc_scan_result *p, int np, mc_scan_result *out) {
 	mc_scan_result r;
-	r.n_eval = 0; r.n_pos = 0; r.best_row = -1; r.best_f0 = -1.0;
-	for (int i = 0; i < np; i++) {
-		r.n_eval += p[i].n_eval;
-		r.n_pos += p[i].n_pos;
-		if (p[i].best_row >= 0 && (p[i].best_f0 > r.best_f0 || (p[i].best_f0 == r.best_f0 && (r.best_row < 0 || p[i].best_row < r.best_row)))) {
-			r.best_f0 = p[i].best_f0;
-			r.best_row = p[i].best_row;
-		}
-	}
+	mc_scan_init(r);
+	for (int i = 0; i < np; i++) mc_scan_merge(r, p[i]);
 	*out = r;
 }
 
@@ -663,6 +660,20 @@ extern "C" int mc_scan_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_resul
 	return MC_OK;
 }
 
+extern "C" int mc_near_threshold_count(mc_ctx *ctx, int64_t *count_out, int reset) {
+	MC_REQUIRE(ctx && count_out, MC_ERR_ARG, "mc_near_threshold_count: bad arguments");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	unsigned long long dev = 0;
+	MC_CUDA(cudaMemcpyAsync(&dev, ctx->d_near, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	*count_out = (int64_t)dev + ctx->near_host;
+	if (reset) {
+		MC_CUDA(cudaMemsetAsync(ctx->d_near, 0, 8, ctx->stream));
+		ctx->near_host = 0;
+	}
+	return MC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // stage 3
 // ---------------------------------------------------------------------------------------------
@@ -787,6 +798,141 @@ extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, i
 	return MC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Phase A as one persistent kernel (phase_a.cu)
+// ---------------------------------------------------------------------------------------------
+int mc_pa_rows_per_tile(int tbytes, int nbins);
+size_t mc_pa_partial_bytes();
+size_t mc_pa_range_bytes();
+bool mc_pa_shape_supported(int tbytes, int nbins);
+int mc_launch_pa_prepare(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, double sim, void *range_tab_dev, unsigned int *err_dev);
+int mc_launch_phase_a(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, const void *range_tab_dev,
+                      uint32_t *alive_bits_dev, unsigned long long *g_sum_dev, void *partials_dev, void *near_dev,
+                      unsigned long long *bar_dev, int *members_dev, int *cl_center_dev, int *cl_off_dev, long long *stats_dev,
+                      unsigned long long *trace_dev, int trace_steps, int grid, int qmax);
+
+extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t *bin_bounds, const int64_t *bin_first_row,
+                                 int64_t nbins_bvec, int64_t *center_rows_out, int64_t *cluster_offsets_out,
+                                 int64_t *member_rows_out, mc_run_stats *stats) {
+	MC_NEED_HIST(ctx);
+	MC_NEED_MODEL(ctx);
+	MC_REQUIRE(bin_bounds && bin_first_row && nbins_bvec >= 1 && center_rows_out && cluster_offsets_out && member_rows_out,
+	           MC_ERR_ARG, "mc_accumulate_run: bad arguments");
+	MC_REQUIRE(similarity > 0 && similarity < 1, MC_ERR_ARG, "mc_accumulate_run: similarity must be between 0 and 1");
+	MC_REQUIRE(mc_pa_shape_supported(ctx->tbytes, ctx->nbins), MC_ERR_UNSUPPORTED,
+	           "mc_accumulate_run: histogram rows of %d bytes are not supported by the persistent kernel", ctx->tbytes * ctx->nbins);
+	MC_REQUIRE(nbins_bvec <= 16384, MC_ERR_UNSUPPORTED, "mc_accumulate_run: %lld bvec bins do not fit shared memory", (long long)nbins_bvec);
+	const int64_t n = ctx->n;
+	const int nb = (int)nbins_bvec;
+	MC_REQUIRE(bin_first_row[0] == 0 && bin_first_row[nb] == n, MC_ERR_ARG, "mc_accumulate_run: bin_first_row must run from 0 to the number of rows");
+	std::vector<int> row0((size_t)nb + 1);
+	for (int i = 0; i <= nb; i++) {
+		MC_REQUIRE(i == 0 || bin_first_row[i] >= bin_first_row[i - 1], MC_ERR_ARG, "mc_accumulate_run: bin_first_row is not sorted");
+		row0[(size_t)i] = (int)bin_first_row[i];
+	}
+	for (int i = 1; i < nb; i++) MC_REQUIRE(bin_bounds[i] >= bin_bounds[i - 1], MC_ERR_ARG, "mc_accumulate_run: bin_bounds is not sorted");
+	const int rt = mc_pa_rows_per_tile(ctx->tbytes, ctx->nbins);
+	const int64_t total_tiles = (n + rt - 1) / rt;
+	int grid = (int)std::min<int64_t>(ctx->num_sms, std::max<int64_t>(1, total_tiles));
+	if (getenv("MC_PA_GRID")) grid = std::max(1, std::min(grid, atoi(getenv("MC_PA_GRID"))));
+	const int qmax = (int)((total_tiles + grid - 1) / grid) + 2;
+	const int trace_steps = getenv("MC_PA_TRACE") ? atoi(getenv("MC_PA_TRACE")) : 0;
+	const size_t words = (size_t)((n + 31) / 32) + 64;
+	const size_t NB = (size_t)ctx->nbins;
+	int rc = mc_ensure_scratch(ctx, Carve::need({(size_t)nb * 8, (size_t)(nb + 1) * 4, (size_t)n * mc_pa_range_bytes(), words * 4, 3 * NB * 8,
+	                                             2 * (size_t)grid * mc_pa_partial_bytes(), 2 * (size_t)grid * mc_pa_partial_bytes(), 64,
+	                                             (size_t)n * 4, (size_t)n * 4, (size_t)(n + 1) * 4, 64, 64, (size_t)trace_steps * 64 + 64}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	unsigned long long *d_bounds = cv.take<unsigned long long>((size_t)nb);
+	int *d_row0 = cv.take<int>((size_t)nb + 1);
+	uint8_t *d_range = cv.take<uint8_t>((size_t)n * mc_pa_range_bytes());
+	uint32_t *d_bits = cv.take<uint32_t>(words);
+	unsigned long long *d_gsum = cv.take<unsigned long long>(3 * NB);
+	uint8_t *d_partials = cv.take<uint8_t>(2 * (size_t)grid * mc_pa_partial_bytes());
+	uint8_t *d_near = cv.take<uint8_t>(2 * (size_t)grid * mc_pa_partial_bytes());
+	unsigned long long *d_bar = cv.take<unsigned long long>(8);
+	int *d_members = cv.take<int>((size_t)n);
+	int *d_center = cv.take<int>((size_t)n);
+	int *d_off = cv.take<int>((size_t)n + 1);
+	long long *d_stats = cv.take<long long>(8);
+	unsigned int *d_err = cv.take<unsigned int>(16);
+	unsigned long long *d_trace = cv.take<unsigned long long>((size_t)trace_steps * 8 + 8);
+	MC_CUDA(cudaMemcpyAsync(d_bounds, bin_bounds, (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(d_row0, row0.data(), (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+	// a fresh bvec: every row alive, the bits past the last row clear
+	MC_CUDA(cudaMemsetAsync(d_bits, 0, words * 4, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_bits, 0xff, (size_t)(n / 32) * 4, ctx->stream));
+	const uint32_t tail_word = (n % 32) ? ((1u << (n % 32)) - 1u) : 0u;
+	if (n % 32) MC_CUDA(cudaMemcpyAsync(d_bits + n / 32, &tail_word, 4, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_gsum, 0, 3 * NB * 8, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_bar, 0, 64, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_stats, 0, 64, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_err, 0, 64, ctx->stream));
+	if (trace_steps) MC_CUDA(cudaMemsetAsync(d_trace, 0, (size_t)trace_steps * 64, ctx->stream));
+	rc = mc_launch_pa_prepare(ctx, d_bounds, d_row0, nb, similarity, d_range, d_err);
+	if (rc) return rc;
+	unsigned int h_err = 0;
+	MC_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	MC_REQUIRE(h_err == 0, MC_ERR_ARG, "mc_accumulate_run: the rows of a bvec bin are not in non-decreasing length order");
+	rc = mc_launch_phase_a(ctx, d_bounds, d_row0, nb, d_range, d_bits, d_gsum, d_partials, d_near, d_bar, d_members, d_center, d_off,
+	                       d_stats, trace_steps ? d_trace : nullptr, trace_steps, grid, qmax);
+	if (rc) return rc;
+	long long h_stats[8];
+	unsigned long long h_bar[2];
+	MC_CUDA(cudaMemcpyAsync(h_stats, d_stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(h_bar, d_bar, 16, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	MC_REQUIRE(h_bar[1] == 0, MC_ERR_CUDA, "mc_accumulate_run: a grid-wide barrier timed out (code %llu)", h_bar[1]);
+	const int64_t nc = h_stats[0];
+	MC_REQUIRE(nc >= 0 && nc <= n, MC_ERR_CUDA, "mc_accumulate_run: the kernel reported %lld clusters", (long long)nc);
+	std::vector<int> tmp((size_t)std::max<int64_t>(n + 1, 1));
+	if (nc) {
+		MC_CUDA(cudaMemcpyAsync(tmp.data(), d_center, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+		for (int64_t i = 0; i < nc; i++) center_rows_out[i] = tmp[(size_t)i];
+	}
+	MC_CUDA(cudaMemcpyAsync(tmp.data(), d_off, (size_t)(nc + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	for (int64_t i = 0; i <= nc; i++) cluster_offsets_out[i] = tmp[(size_t)i];
+	const int64_t total = cluster_offsets_out[nc];
+	MC_REQUIRE(total == n || nc == 0, MC_ERR_CUDA, "mc_accumulate_run: %lld of %lld rows were assigned", (long long)total, (long long)n);
+	if (total) {
+		MC_CUDA(cudaMemcpyAsync(tmp.data(), d_members, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+		for (int64_t i = 0; i < total; i++) member_rows_out[i] = tmp[(size_t)i];
+	}
+	ctx->near_host += h_stats[3];
+	if (stats) {
+		stats->n_clusters = nc;
+		stats->n_scans = h_stats[1];
+		stats->n_evals = h_stats[2];
+		stats->n_near_threshold = h_stats[3];
+		stats->n_steps = h_stats[4];
+		stats->device_seconds = (double)h_stats[5] * 1e-9;
+	}
+	if (trace_steps) {
+		std::vector<unsigned long long> tr((size_t)trace_steps * 8);
+		MC_CUDA(cudaMemcpy(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
+		// per phase: control, scan, barrier 1, fold, tail, barrier 2, rest (averages over the traced steps, in us)
+		double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+		long cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+		const long steps = (long)std::min<long long>(trace_steps, h_stats[4]);
+		for (long s = 0; s < steps; s++) {
+			const unsigned long long *t = tr.data() + (size_t)s * 8;
+			auto add = [&](int k, unsigned long long a, unsigned long long b) { if (a && b && b >= a) { acc[k] += (double)(b - a) * 1e-3; cnt[k]++; } };
+			add(0, t[0], t[1]); add(1, t[1], t[2]); add(2, t[2], t[3]); add(3, t[3], t[4]);
+			if (t[5]) { add(4, t[4], t[5]); add(5, t[5], t[6]); add(6, t[6], t[7]); }
+			else add(6, t[4], t[7]);
+		}
+		fprintf(stderr, "[mc_accumulate_run trace, %ld steps, us] control %.2f  scan %.2f  barrier1 %.2f  fold %.2f | tail %.2f (x%ld)  barrier2 %.2f  close %.2f\n",
+		        steps, acc[0] / std::max(1L, cnt[0]), acc[1] / std::max(1L, cnt[1]), acc[2] / std::max(1L, cnt[2]), acc[3] / std::max(1L, cnt[3]),
+		        acc[4] / std::max(1L, cnt[4]), cnt[4], acc[5] / std::max(1L, cnt[5]), acc[6] / std::max(1L, cnt[6]));
+	}
+	return MC_OK;
+}
+
 int mc_comm_scan_push(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked, int slot, int fence);
 int mc_comm_combine_dev(mc_ctx *ctx, int slot, const void **rec_dev_out, unsigned int **err_dev_out);
 
@@ -808,6 +954,7 @@ extern "C" int mc_clone_points(mc_ctx *dst, mc_ctx *src) {
 	}
 	MC_CUDA(cudaStreamSynchronize(dst->stream));
 	dst->model = src->model;
+	dst->model.near = dst->d_near;   // every GPU counts into its own word
 	dst->have_hist = true;
 	return MC_OK;
 }

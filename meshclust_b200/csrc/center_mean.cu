@@ -10,25 +10,6 @@
 
 #include "pair_core.cuh"
 
-// generic-address pair reduction of one row against a "center" row (global or shared memory)
-template <int TB>
-__device__ __forceinline__ PairAcc<TB> warp_pair_reduce(const uint8_t *p, const uint8_t *q, int rb, int lane) {
-	PairAcc<TB> acc;
-	if (rb >= 16) {
-		for (int c = lane; c < rb / 16; c += 32) {
-			const uint4 x = *(reinterpret_cast<const uint4 *>(p) + c);
-			const uint4 y = *(reinterpret_cast<const uint4 *>(q) + c);
-			acc.add(x.x, y.x); acc.add(x.y, y.y); acc.add(x.z, y.z); acc.add(x.w, y.w);
-		}
-	} else {
-		for (int c = lane; c < rb / 4; c += 32)
-			acc.add(*(reinterpret_cast<const uint32_t *>(p) + c), *(reinterpret_cast<const uint32_t *>(q) + c));
-	}
-#pragma unroll
-	for (int o = 16; o; o >>= 1) acc.shfl_add_from(acc, o);
-	return acc;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Phase A: running sum of member histograms
 // ---------------------------------------------------------------------------------------------
@@ -92,7 +73,7 @@ __global__ void nearest_kernel(const uint8_t *__restrict__ hist, const McRowAux 
 	const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
 	for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + wib; i < m; i += nwarps) {
 		const long long row = rows[i];
-		const PairAcc<TB> acc = warp_pair_reduce<TB>(hist + (size_t)row * rb, tq, rb, lane);
+		const PairAcc<TB> acc = mc_warp_pair_reduce<TB>(hist + (size_t)row * rb, tq, rb, lane);
 		const uint64_t mp = aux[row].mag;
 		const double d = mc_distance_d(acc.summin(mp, magc), mp, magc);
 		NearPartial c; c.pos = i; c.dist = d;
@@ -169,15 +150,6 @@ struct AccDev {
 
 constexpr int ACC_THREADS = 256;
 
-__device__ __forceinline__ void step_merge(mc_scan_result &a, const mc_scan_result &b) {
-	a.n_eval += b.n_eval;
-	a.n_pos += b.n_pos;
-	if (b.best_row >= 0 && (b.best_f0 > a.best_f0 || (b.best_f0 == a.best_f0 && (a.best_row < 0 || b.best_row < a.best_row)))) {
-		a.best_f0 = b.best_f0;
-		a.best_row = b.best_row;
-	}
-}
-
 // The result block lives in host-mapped pinned memory: [0,48) mc_step_result, [48,56) sequence word,
 // [56,60) error word of a sharded step.  The host does not synchronise with the stream; it polls the
 // sequence word, which is written last, behind a system-scope fence.
@@ -218,17 +190,9 @@ accumulate_tail_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restr
 			mc_scan_result p;
 			p.n_eval = __ldcg(&partials[i].n_eval); p.n_pos = __ldcg(&partials[i].n_pos);
 			p.best_row = __ldcg(&partials[i].best_row); p.best_f0 = __ldcg(&partials[i].best_f0);
-			step_merge(r, p);
+			mc_scan_merge(r, p);
 		}
-#pragma unroll
-		for (int o = 16; o; o >>= 1) {
-			mc_scan_result other;
-			other.n_eval = __shfl_xor_sync(MC_FULL_MASK, r.n_eval, o);
-			other.n_pos = __shfl_xor_sync(MC_FULL_MASK, r.n_pos, o);
-			other.best_row = __shfl_xor_sync(MC_FULL_MASK, r.best_row, o);
-			other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, r.best_f0, o);
-			step_merge(r, other);
-		}
+		mc_scan_warp_fold(r);
 		if (lane == 0) s_scan = r;
 	}
 	const long long m0 = restart ? 1 : acc->members_n;   // read before anyone may rewrite it (end of the kernel)
@@ -352,7 +316,7 @@ accumulate_tail_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restr
 	NearPartial best; best.pos = -1; best.dist = 0;
 	for (long long i = (long long)b * (ACC_THREADS / 32) + wib; i < m_all; i += (long long)G * (ACC_THREADS / 32)) {
 		const long long row = __ldcg(&members[i]);
-		const PairAcc<TB> pa = warp_pair_reduce<TB>(hist + (size_t)row * rb, tq, rb, lane);
+		const PairAcc<TB> pa = mc_warp_pair_reduce<TB>(hist + (size_t)row * rb, tq, rb, lane);
 		const uint64_t mp = aux[row].mag;
 		NearPartial cnd; cnd.pos = i; cnd.dist = mc_distance_d(pa.summin(mp, magc), mp, magc);
 		near_merge(best, cnd);
@@ -448,13 +412,14 @@ update_centers_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restri
 	unsigned int kept = 0;
 	for (long long i = wib; i < ncand; i += UPD_THREADS / 32) {
 		const long long row = cand_rows[cb + i];
-		const PairAcc<TB> acc = warp_pair_reduce<TB>(hist + (size_t)row * rb, hist + (size_t)crow * rb, rb, lane);
+		const PairAcc<TB> acc = mc_warp_pair_reduce<TB>(hist + (size_t)row * rb, hist + (size_t)crow * rb, rb, lane);
 		if (lane == 0) {
 			const uint64_t lp = aux[row].len, mp = aux[row].mag, sp = aux[row].sq;
 			double cc[5], f[4], sum;
 			mc_raw_features(acc.summin(mp, mq), acc.dot(), lp, mp, sp, lq, mq, sq, nbins, model.nfeat >= 4, cc);
 			mc_eval_model(model, cc, f, sum);
-			const bool keep = sum >= MC_SIGMOID_SUM_THRESHOLD;
+			const bool keep = MC_IS_SIMILAR(sum);
+			mc_count_near(model, sum);
 			fl[i] = keep ? 1 : 0;
 			kept += keep;
 		}
@@ -511,7 +476,7 @@ update_centers_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restri
 	for (long long i = wib; i < ncand; i += UPD_THREADS / 32) {
 		if (!fl[i]) continue;
 		const long long row = cand_rows[cb + i];
-		const PairAcc<TB> acc = warp_pair_reduce<TB>(hist + (size_t)row * rb, tq, rb, lane);
+		const PairAcc<TB> acc = mc_warp_pair_reduce<TB>(hist + (size_t)row * rb, tq, rb, lane);
 		const uint64_t mp = aux[row].mag;
 		NearPartial cnd; cnd.pos = i; cnd.dist = mc_distance_d(acc.summin(mp, magc), mp, magc);
 		near_merge(best, cnd);

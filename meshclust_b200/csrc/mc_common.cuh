@@ -43,6 +43,16 @@ void mc_set_error(const char *fmt, ...);
 		}                             \
 	} while (0)
 
+// round(1/(1+exp(-sum))) == 1.0 (Trainer.cpp:95,102) holds exactly when fl(1+exp(-sum)) <= 2,
+// i.e. exp(-sum) <= 1 + 2^-52 (ties-to-even), i.e. -sum < 1.5 * 2^-52 -- a STRICT bound: at
+// -sum = 1.5 * 2^-52 the exponential lies just above the midpoint and rounds up to 1 + 2^-51, the
+// sum to 2 + 2^-51 and the sigmoid below one half.  NaN is never similar.
+#define MC_SIGMOID_SUM_THRESHOLD (-0x1.8p-52)
+#define MC_IS_SIMILAR(sum) ((sum) > MC_SIGMOID_SUM_THRESHOLD)
+// pairs this close to the decision threshold are the ones a different rounding of exp() could flip
+// (north_star: "identical, except for pairs within that tolerance of the --id threshold, reported by count")
+#define MC_NEAR_THRESHOLD 1e-9
+
 // ---------------------------------------------------------------------------------------------
 // the trained classifier as the kernels see it (passed by value as a kernel argument)
 // lookup order [LD, INTERSECTION, MANHATTAN, PEARSON, KULCZYNSKI2]  (Feature.cpp:15-28)
@@ -55,11 +65,52 @@ struct McModel {
 	int fast_div;  // bit j set: (x - mins[j]) / (maxs[j] - mins[j]) may use rcp[j] (validated on the host)
 	int nfeat;     // 3 or 4
 	int valid;
+	unsigned long long *near;   // device counter of decisions with |sum| < MC_NEAR_THRESHOLD (this context's GPU)
 };
 
-// round(1/(1+exp(-sum))) == 1.0 (Trainer.cpp:95,102) holds exactly when fl(1+exp(-sum)) <= 2,
-// i.e. exp(-sum) <= 1 + 2^-52 (ties-to-even), i.e. -sum < 1.5 * 2^-52.  NaN is never similar.
-#define MC_SIGMOID_SUM_THRESHOLD (-0x1.8p-52)
+#ifdef __CUDACC__
+__device__ __forceinline__ void mc_count_near(const McModel &m, double sum) {
+	if (fabs(sum) < MC_NEAR_THRESHOLD) atomicAdd(m.near, 1ull);
+}
+#endif
+
+
+
+// ---------------------------------------------------------------------------------------------
+// THE scan summary and its ONE merge rule (Trainer.cpp:38-48,81,99): counts add up; the arg-max is
+// the largest f0, and among equal f0 the first row in iteration order (the reference iterates
+// serially with a strict >).  Every fold -- per lane, per warp, per CTA, per GPU, on the host --
+// goes through mc_scan_merge.
+// ---------------------------------------------------------------------------------------------
+typedef mc_scan_result ScanPartial;
+
+__host__ __device__ __forceinline__ void mc_scan_init(mc_scan_result &a) {
+	a.n_eval = 0; a.n_pos = 0; a.best_row = -1; a.best_f0 = -1.0;
+}
+
+__host__ __device__ __forceinline__ void mc_scan_merge(mc_scan_result &a, const mc_scan_result &b) {
+	a.n_eval += b.n_eval;
+	a.n_pos += b.n_pos;
+	if (b.best_row >= 0 && (b.best_f0 > a.best_f0 || (b.best_f0 == a.best_f0 && (a.best_row < 0 || b.best_row < a.best_row)))) {
+		a.best_f0 = b.best_f0;
+		a.best_row = b.best_row;
+	}
+}
+
+#ifdef __CUDACC__
+// butterfly over the 32 lanes of a warp: every lane ends with the warp's summary
+__device__ __forceinline__ void mc_scan_warp_fold(mc_scan_result &v) {
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		mc_scan_result other;
+		other.n_eval = __shfl_xor_sync(MC_FULL_MASK, v.n_eval, o);
+		other.n_pos = __shfl_xor_sync(MC_FULL_MASK, v.n_pos, o);
+		other.best_row = __shfl_xor_sync(MC_FULL_MASK, v.best_row, o);
+		other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, v.best_f0, o);
+		mc_scan_merge(v, other);
+	}
+}
+#endif
 
 // per-point constants next to the histogram: one 32-byte record per row, so a tile of rows needs
 // one bulk copy for the histograms and one for these
@@ -169,6 +220,8 @@ struct mc_ctx {
 	size_t pinned_bytes = 0;
 	unsigned int *d_ticket = nullptr;   // last-block-done counter + flags
 	unsigned int *d_flags = nullptr;    // [0] invalid-input flag, [1] max count, ...
+	unsigned long long *d_near = nullptr;   // near-threshold decisions counted by the kernels
+	int64_t near_host = 0;                  // ... and by runs that report their count through their own result (mc_accumulate_run)
 
 	// result slots of mc_scan_enqueue + per-launch block partials
 	void *d_scan_slots = nullptr;      // MC_SCAN_SLOTS x MC_SCAN_PARTS partial records

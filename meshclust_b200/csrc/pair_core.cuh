@@ -145,6 +145,25 @@ __device__ __forceinline__ PairAcc<TB> mc_row_partial(const uint8_t *row, int r,
 	return acc;
 }
 
+// generic-address pair reduction of one row against a "center" row (global or shared memory)
+template <int TB>
+__device__ __forceinline__ PairAcc<TB> mc_warp_pair_reduce(const uint8_t *p, const uint8_t *q, int rb, int lane) {
+	PairAcc<TB> acc;
+	if (rb >= 16) {
+		for (int c = lane; c < rb / 16; c += 32) {
+			const uint4 x = *(reinterpret_cast<const uint4 *>(p) + c);
+			const uint4 y = *(reinterpret_cast<const uint4 *>(q) + c);
+			acc.add(x.x, y.x); acc.add(x.y, y.y); acc.add(x.z, y.z); acc.add(x.w, y.w);
+		}
+	} else {
+		for (int c = lane; c < rb / 4; c += 32)
+			acc.add(*(reinterpret_cast<const uint32_t *>(p) + c), *(reinterpret_cast<const uint32_t *>(q) + c));
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) acc.shfl_add_from(acc, o);
+	return acc;
+}
+
 // dispatch a functor over the supported (tbytes, row bytes) pairs
 #define MC_DISPATCH_ROW(tbytes, nbins, FN)                                   \
 	do {                                                                     \

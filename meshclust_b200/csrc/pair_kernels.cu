@@ -90,23 +90,6 @@ int mc_launch_alive_reset(mc_ctx *ctx) {
 // ---------------------------------------------------------------------------------------------
 // K2a: scan = Trainer::get_close + bvec::remove_available
 // ---------------------------------------------------------------------------------------------
-struct ScanPartial {
-	long long n_eval;
-	long long n_pos;
-	long long best_row;
-	double best_f0;
-};
-
-__device__ __forceinline__ void scan_merge(ScanPartial &a, const ScanPartial &b) {
-	a.n_eval += b.n_eval;
-	a.n_pos += b.n_pos;
-	// first maximum in row order wins (Trainer.cpp:99 strict >, serial iteration order)
-	if (b.best_row >= 0 && (b.best_f0 > a.best_f0 || (b.best_f0 == a.best_f0 && (a.best_row < 0 || b.best_row < a.best_row)))) {
-		a.best_f0 = b.best_f0;
-		a.best_row = b.best_row;
-	}
-}
-
 constexpr int SCAN_THREADS = 256;
 
 template <int TB, int RB>
@@ -167,7 +150,8 @@ scan_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux,
 				double c[5], f[4], sum;
 				mc_raw_features(S, tot.dot(), lp, mp, sp, lq, mq, sq, NB, model.nfeat >= 4, c);
 				mc_eval_model(model, c, f, sum);
-				flag = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1u : 0u;
+				flag = MC_IS_SIMILAR(sum) ? 1u : 0u;
+				mc_count_near(model, sum);
 				mine.n_eval++;
 				mine.n_pos += flag;
 				if (f[0] > mine.best_f0) { mine.best_f0 = f[0]; mine.best_row = row_mine; }
@@ -178,20 +162,12 @@ scan_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux,
 	}
 
 	// warp -> block -> grid reduction, deterministic (merge rule is order independent)
-#pragma unroll
-	for (int o = 16; o; o >>= 1) {
-		ScanPartial other;
-		other.n_eval = __shfl_xor_sync(MC_FULL_MASK, mine.n_eval, o);
-		other.n_pos = __shfl_xor_sync(MC_FULL_MASK, mine.n_pos, o);
-		other.best_row = __shfl_xor_sync(MC_FULL_MASK, mine.best_row, o);
-		other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, mine.best_f0, o);
-		scan_merge(mine, other);
-	}
+	mc_scan_warp_fold(mine);
 	if (lane == 0) warp_part[wib] = mine;
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		ScanPartial b = warp_part[0];
-		for (int w = 1; w < SCAN_THREADS / 32; w++) scan_merge(b, warp_part[w]);
+		for (int w = 1; w < SCAN_THREADS / 32; w++) mc_scan_merge(b, warp_part[w]);
 		partials[blockIdx.x] = b;
 		__threadfence();
 		const unsigned t = atomicAdd(ticket, 1u);
@@ -209,22 +185,14 @@ scan_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux,
 			p.n_pos = __ldcg(&partials[i].n_pos);
 			p.best_row = __ldcg(&partials[i].best_row);
 			p.best_f0 = __ldcg(&partials[i].best_f0);
-			scan_merge(b, p);
+			mc_scan_merge(b, p);
 		}
-#pragma unroll
-		for (int o = 16; o; o >>= 1) {
-			ScanPartial other;
-			other.n_eval = __shfl_xor_sync(MC_FULL_MASK, b.n_eval, o);
-			other.n_pos = __shfl_xor_sync(MC_FULL_MASK, b.n_pos, o);
-			other.best_row = __shfl_xor_sync(MC_FULL_MASK, b.best_row, o);
-			other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, b.best_f0, o);
-			scan_merge(b, other);
-		}
+		mc_scan_warp_fold(b);
 		if (lane == 0) warp_part[wib] = b;
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			ScanPartial t = warp_part[0];
-			for (int w = 1; w < SCAN_THREADS / 32; w++) scan_merge(t, warp_part[w]);
+			for (int w = 1; w < SCAN_THREADS / 32; w++) mc_scan_merge(t, warp_part[w]);
 			*result = t;
 			*ticket = 0;   // re-arm for the next launch on this stream
 		}
@@ -374,7 +342,7 @@ __global__ void pair_list_kernel(const uint8_t *__restrict__ hist, const McRowAu
 				mc_eval_model(model, c, f, sum);
 				if (sum_out) sum_out[i] = sum;
 				if (f0_out) f0_out[i] = f[0];
-				if (flag_out) flag_out[i] = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1 : 0;
+				if (flag_out) { flag_out[i] = MC_IS_SIMILAR(sum) ? 1 : 0; mc_count_near(model, sum); }
 				if (feats_out) {
 #pragma unroll
 					for (int j = 0; j < 4; j++) feats_out[i * 4 + j] = f[j];

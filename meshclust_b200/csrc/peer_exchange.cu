@@ -27,15 +27,6 @@ struct CombineArgs {
 constexpr int COMBINE_THREADS = 256;
 constexpr unsigned long long COMBINE_TIMEOUT_NS = 4000000000ull;   // a peer that never sends is an error, not a hang
 
-__device__ __forceinline__ void xmerge(mc_scan_result &a, const mc_scan_result &b) {
-	a.n_eval += b.n_eval;
-	a.n_pos += b.n_pos;
-	if (b.best_row >= 0 && (b.best_f0 > a.best_f0 || (b.best_f0 == a.best_f0 && (a.best_row < 0 || b.best_row < a.best_row)))) {
-		a.best_f0 = b.best_f0;
-		a.best_row = b.best_row;
-	}
-}
-
 __device__ __forceinline__ uint4 ld_volatile16(const void *p) {
 	uint4 r;
 	asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
@@ -77,24 +68,16 @@ scan_combine_kernel(const uint8_t *__restrict__ inbox, int world, int nparts, Co
 		r.n_pos = (long long)((unsigned long long)q[1].x | ((unsigned long long)q[1].z << 32));
 		r.best_row = (long long)((unsigned long long)q[2].x | ((unsigned long long)q[2].z << 32));
 		r.best_f0 = __longlong_as_double((long long)((unsigned long long)q[3].x | ((unsigned long long)q[3].z << 32)));
-		xmerge(mine, r);
+		mc_scan_merge(mine, r);
 	}
 	if (failed) atomicExch(err, 1u);
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-#pragma unroll
-	for (int o = 16; o; o >>= 1) {
-		mc_scan_result other;
-		other.n_eval = __shfl_xor_sync(MC_FULL_MASK, mine.n_eval, o);
-		other.n_pos = __shfl_xor_sync(MC_FULL_MASK, mine.n_pos, o);
-		other.best_row = __shfl_xor_sync(MC_FULL_MASK, mine.best_row, o);
-		other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, mine.best_f0, o);
-		xmerge(mine, other);
-	}
+	mc_scan_warp_fold(mine);
 	if (lane == 0) s_part[wib] = mine;
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		mc_scan_result r = s_part[0];
-		for (int w = 1; w < (int)(blockDim.x >> 5); w++) xmerge(r, s_part[w]);
+		for (int w = 1; w < (int)(blockDim.x >> 5); w++) mc_scan_merge(r, s_part[w]);
 		out[slot] = r;
 	}
 }
@@ -367,18 +350,10 @@ __global__ void __launch_bounds__(32) fold_send_kernel(const unsigned int *__res
 		r.n_pos = (long long)((unsigned long long)q[1].x | ((unsigned long long)q[1].z << 32));
 		r.best_row = (long long)((unsigned long long)q[2].x | ((unsigned long long)q[2].z << 32));
 		r.best_f0 = __longlong_as_double((long long)((unsigned long long)q[3].x | ((unsigned long long)q[3].z << 32)));
-		xmerge(b, r);
+		mc_scan_merge(b, r);
 	}
 	if (__any_sync(MC_FULL_MASK, failed)) { if (lane == 0) atomicExch(err, 1u); return; }
-#pragma unroll
-	for (int o = 16; o; o >>= 1) {
-		mc_scan_result other;
-		other.n_eval = __shfl_xor_sync(MC_FULL_MASK, b.n_eval, o);
-		other.n_pos = __shfl_xor_sync(MC_FULL_MASK, b.n_pos, o);
-		other.best_row = __shfl_xor_sync(MC_FULL_MASK, b.best_row, o);
-		other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, b.best_f0, o);
-		xmerge(b, other);
-	}
+	mc_scan_warp_fold(b);
 	unsigned long long f[4] = {(unsigned long long)b.n_eval, (unsigned long long)b.n_pos, (unsigned long long)b.best_row,
 	                           (unsigned long long)__double_as_longlong(b.best_f0)};
 	const int w = lane & 7;

@@ -1,0 +1,874 @@
+// Phase A of the clustering -- ClusterFactory::accumulate (ClusterFactory.cpp:637-714) with its bvec
+// bookkeeping (bvec.cpp:27-38 pop, :52-120 inner_index_of, :123-149 index_of, :247-278 get_range,
+// :281-285 erase, :290-317 remove_available), Trainer::get_close (Trainer.cpp:34-114) and get_mean
+// (ClusterFactory.cpp:382-425) -- as ONE persistent cooperative kernel: the greedy loop
+//     range of the center's length window -> scan -> (marks: extend `current`, mean, nearest -> new
+//     center | no marks: close the cluster, arg-max becomes the next seed)
+// never returns to the host.  The host launches once and reads the clusters back.
+//
+// One CTA per SM; every CTA runs the same control flow on the same values (read from global memory
+// behind grid-wide barriers), so there is no controller CTA and no broadcast:
+//   control   two warps: the length window of the center as an inclusive row range.  The bvec lives on
+//             the device as (a) immutable per-row search records computed once (which bin the window
+//             starts / ends in and how many of the bin's entries are shorter / not longer than the
+//             bound), (b) an alive bitmap in global memory, (c) per-bin alive counts in shared memory,
+//             kept identical in every CTA.  The reference's binary search over the i-th ALIVE entry of
+//             a bin is replayed on ranks (popcounts of the bitmap), without touching the lengths.
+//   scan      the TMA-staged streaming scan of scan_tma.cu (one producer warp feeding per-consumer
+//             rings with cp.async.bulk, VABSDIFF4 / DP4A reductions, FP64 feature + GLM epilogue on all
+//             lanes); a CTA owns a contiguous run of tiles, so the rows it marks are ordered.  Marked rows
+//             leave the bitmap (one atomic per tile) and are added to per-CTA bin sums in shared memory.
+//   barrier 1 (after the CTA partials and the bin sums have been flushed)
+//   fold      every CTA folds all partials.  No positives: the cluster is closed, the arg-max (or the
+//             first alive row) becomes the next seed -- no second barrier.
+//   tail      positives: every CTA writes its marked rows into the cluster's member list at the offset
+//             its predecessors' counts give, derives the truncated mean from the global bin sums and
+//             evaluates distance_d for its own new members and its share of the older ones
+//   barrier 2, fold of the nearest-member partials -> the new center.
+// HBM traffic per step = the scan's algorithmic bytes; everything else is a few KB out of L2.
+#include "pair_core.cuh"
+#include "tma_utils.cuh"
+
+constexpr int PA_MAX_CONSUMERS = 15;   // 16 warps = 512 threads: 128 registers per thread
+constexpr int PA_WARPS = 1 + PA_MAX_CONSUMERS;
+constexpr int PA_THREADS = 32 * PA_WARPS;
+constexpr int PA_MAX_STAGES = 32;
+constexpr unsigned long long PA_TIMEOUT_NS = 20000000000ull;   // a barrier that does not complete is an error, not a hang
+
+struct PaPartial {   // one per CTA and step
+	mc_scan_result s;
+	long long n_near;   // evaluated pairs with |GLM sum| < 1e-9 (north_star: "reported by count")
+	long long pad;
+};
+
+struct PaNear {
+	long long pos;   // position in `current` (first minimum wins, ClusterFactory.cpp:412-418)
+	double dist;
+	long long row;
+	long long pad;
+};
+
+__device__ __forceinline__ void pa_near_merge(PaNear &a, const PaNear &b) {
+	if (b.pos >= 0 && (a.pos < 0 || b.dist < a.dist || (b.dist == a.dist && b.pos < a.pos))) a = b;
+}
+
+// Immutable search record of a row used as a center: bvec::get_range for its length window
+// [len * id, len / id] needs, per end, the bin index_of() picks and -- for the in-bin binary search --
+// how many entries of that bin (alive or not) are shorter than / not longer than the bound.
+struct __align__(32) PaRange {
+	int fb, bb;        // bins of the lower / upper bound (bvec::index_of)
+	int f_lt, f_le;    // entries of bin fb with length < / <= the lower bound
+	int b_lt, b_le;    // entries of bin bb with length < / <= the upper bound
+	int pad0, pad1;
+};
+
+struct PaArgs {
+	const uint8_t *hist;
+	const McRowAux *aux;
+	long long n;
+	const unsigned long long *bounds;   // nb bin bounds (bvec.cpp:10-24)
+	const int *row0;                    // nb + 1: first row of every bin
+	int nb;
+	int qmax;                           // capacity of the per-CTA tile tables
+	const PaRange *range_tab;           // n
+	uint32_t *alive_bits;               // bit r = row r is still in the bvec
+	unsigned long long *g_sum;          // 3 x bins: running bin sums of `current`, rotating per cluster
+	PaPartial *partials;                // 2 x grid
+	PaNear *near;                       // 2 x grid
+	unsigned long long *bar;            // [0] barrier counter, [1] abort code
+	int *members;                       // n: the clusters' member rows, cluster after cluster
+	int *cl_center;                     // n
+	int *cl_off;                        // n + 1
+	long long *stats;                   // [0] clusters [1] scans [2] evals [3] near-threshold pairs [4] steps [5] ns
+	unsigned long long *trace;          // optional: 8 timestamps per step of CTA 0
+	int trace_steps;
+	int ns, ncw, d;                     // ring geometry: stages, consumer warps, stages per consumer
+	McModel model;
+};
+
+// ---- bvec::index_of (bvec.cpp:123-149) on the sorted bounds ------------------------------------
+__device__ __forceinline__ void pa_index_of(const unsigned long long *b, int nb, unsigned long long point, int *pfront, int *pback) {
+	int low = nb - 1, high = 0;
+	int lo = 0, hi = nb;
+	while (lo < hi) { const int mid = (lo + hi) >> 1; if (b[mid] < point) lo = mid + 1; else hi = mid; }
+	const int i1 = lo;   // first bound >= point
+	if (i1 < nb) {
+		hi = nb;
+		while (lo < hi) { const int mid = (lo + hi) >> 1; if (b[mid] <= point) lo = mid + 1; else hi = mid; }
+		const int imax = lo < nb - 1 ? lo : nb - 1;   // number of bounds <= point, capped
+		const int l = i1 > 0 ? i1 - 1 : 0, h = imax > 0 ? imax - 1 : 0;
+		low = low < l ? low : l;
+		high = high > h ? high : h;
+	}
+	if (point >= b[nb - 1]) high = high > nb - 1 ? high : nb - 1;
+	*pfront = low;
+	*pback = high;
+}
+
+// One thread per row: the search records.  Also checks what the kernel relies on: rows of a bin are in
+// non-decreasing length order (bvec::insert_finalize sorts every bin, bvec.cpp:209-218).
+__global__ void pa_prepare_kernel(const McRowAux *__restrict__ aux, long long n, const unsigned long long *__restrict__ bounds,
+                                  const int *__restrict__ row0, int nb, double sim, PaRange *__restrict__ tab,
+                                  unsigned int *__restrict__ err) {
+	for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+		const unsigned long long len = aux[r].len;
+		// ClusterFactory.cpp:651-652: get_range(len * id, len / id), both converted to uint64
+		const unsigned long long begin_len = (unsigned long long)((double)len * sim);
+		const unsigned long long end_len = (unsigned long long)((double)len / sim);
+		PaRange g;
+		int dummy;
+		pa_index_of(bounds, nb, begin_len, &g.fb, &dummy);
+		pa_index_of(bounds, nb, end_len, &dummy, &g.bb);
+		auto count_below = [&](int bin, unsigned long long key, bool inclusive) {
+			int lo = row0[bin], hi = row0[bin + 1];
+			const int base = lo;
+			while (lo < hi) {
+				const int mid = (lo + hi) >> 1;
+				const unsigned long long v = aux[mid].len;
+				if (inclusive ? v <= key : v < key) lo = mid + 1; else hi = mid;
+			}
+			return lo - base;
+		};
+		g.f_lt = count_below(g.fb, begin_len, false);
+		g.f_le = count_below(g.fb, begin_len, true);
+		g.b_lt = count_below(g.bb, end_len, false);
+		g.b_le = count_below(g.bb, end_len, true);
+		g.pad0 = 0; g.pad1 = 0;
+		tab[r] = g;
+		// sortedness inside the bin of r
+		int lo = 0, hi = nb;
+		while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long)row0[mid + 1] <= r) lo = mid + 1; else hi = mid; }
+		if (r > row0[lo] && aux[r - 1].len > len) atomicExch(err, 1u);
+	}
+}
+
+// ---- alive bitmap helpers (warp-cooperative; every lane gets the result) ------------------------
+// alive rows among the first pa / pb rows of [r0, r1) and in all of it
+__device__ __forceinline__ void pa_rank3(const uint32_t *bits, long long r0, long long r1, long long pa, long long pb,
+                                         int lane, unsigned &ra, unsigned &rb, unsigned &tot) {
+	unsigned a = 0, b = 0, t = 0;
+	if (r1 > r0) {
+		const long long w0 = r0 >> 5, w1 = (r1 - 1) >> 5;
+		for (long long w = w0 + lane; w <= w1; w += 32) {
+			uint32_t v = __ldcg(bits + w);
+			if (w == w0) v &= 0xffffffffu << (r0 & 31);
+			if (w == w1 && (r1 & 31)) v &= 0xffffffffu >> (32 - (int)(r1 & 31));
+			auto below = [&](long long lim) {
+				const long long dlt = lim - (w << 5);
+				return dlt <= 0 ? 0u : (dlt >= 32 ? 0xffffffffu : ((1u << (int)dlt) - 1u));
+			};
+			a += __popc(v & below(r0 + pa));
+			b += __popc(v & below(r0 + pb));
+			t += __popc(v);
+		}
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		a += __shfl_xor_sync(MC_FULL_MASK, a, o);
+		b += __shfl_xor_sync(MC_FULL_MASK, b, o);
+		t += __shfl_xor_sync(MC_FULL_MASK, t, o);
+	}
+	ra = a; rb = b; tot = t;
+}
+
+// row of the pos-th (0-based) alive row of [r0, r1), or -1
+__device__ __forceinline__ long long pa_select(const uint32_t *bits, long long r0, long long r1, unsigned long long pos, int lane) {
+	if (r1 <= r0) return -1;
+	const long long w0 = r0 >> 5, w1 = (r1 - 1) >> 5;
+	unsigned long long seen = 0;
+	for (long long wb = w0; wb <= w1; wb += 32) {
+		const long long w = wb + lane;
+		uint32_t v = 0;
+		if (w <= w1) {
+			v = __ldcg(bits + w);
+			if (w == w0) v &= 0xffffffffu << (r0 & 31);
+			if (w == w1 && (r1 & 31)) v &= 0xffffffffu >> (32 - (int)(r1 & 31));
+		}
+		const unsigned pc = __popc(v);
+		unsigned incl = pc;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned u = __shfl_up_sync(MC_FULL_MASK, incl, o);
+			if (lane >= o) incl += u;
+		}
+		const unsigned tot = __shfl_sync(MC_FULL_MASK, incl, 31);
+		if (pos < seen + tot) {
+			const unsigned long long before = seen + incl - pc;
+			const bool mine = before <= pos && pos < seen + incl;
+			const unsigned ball = __ballot_sync(MC_FULL_MASK, mine);
+			const int src = __ffs(ball) - 1;
+			long long row = -1;
+			if (mine) row = (w << 5) + __fns(v, 0, (int)(pos - before) + 1);
+			return __shfl_sync(MC_FULL_MASK, row, src);
+		}
+		seen += tot;
+	}
+	return -1;
+}
+
+// bvec::inner_index_of's binary search (bvec.cpp:52-120) over the ALIVE entries of a bin, replayed on
+// ranks: alive entries [0, a_lt) are shorter than the bound, [a_lt, a_le) equal, [a_le, A) longer.
+__device__ __forceinline__ void pa_inner_search(unsigned long long A, unsigned long long a_lt, unsigned long long a_le,
+                                                unsigned long long &front, unsigned long long &back) {
+	front = 0; back = 0;
+	unsigned long long low = 0, high = A - 1;
+	while (low <= high) {
+		const unsigned long long mid = (low + high) / 2;
+		if (mid >= a_lt && mid < a_le) { front = back = mid; break; }   // d == length
+		else if (mid >= a_le) high = mid;                               // length < d
+		else low = mid + 1;
+		if (low == high) { front = low; back = high; break; }
+	}
+	// the walks over equal lengths (bvec.cpp:100-118)
+	if (front >= a_lt && front < a_le) front = a_lt;
+	if (back >= a_lt && back < a_le) back = a_le - 1;
+}
+
+// ---- grid-wide barrier -------------------------------------------------------------------------
+// Monotonic 64-bit counter: barrier e is passed when the counter reaches e * gridDim.x.  All CTAs are
+// co-resident (cooperative launch).  Returns false when the run has been aborted (time-out).
+__device__ __forceinline__ bool pa_grid_barrier(unsigned long long *bar, unsigned long long target) {
+	__shared__ int s_ok;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ull) : "memory");
+		unsigned long long t0 = 0;
+		int ok = 1;
+		for (unsigned spins = 0;; spins++) {
+			unsigned long long v;
+			asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+			if (v >= target) break;
+			if ((spins & 0x3ff) == 0x3ff) {
+				unsigned long long t1, ab;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+				asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(ab) : "l"(bar + 1) : "memory");
+				if (ab) { ok = 0; break; }
+				if (t0 == 0) t0 = t1;
+				else if (t1 - t0 > PA_TIMEOUT_NS) { atomicExch(bar + 1, 1ull); ok = 0; break; }
+			}
+		}
+		s_ok = ok;
+	}
+	__syncthreads();
+	return s_ok != 0;
+}
+
+// rows per tile: 32 (one row per lane in the epilogue) while the tile fits 32 KB
+template <int RB>
+struct PaTile {
+	static constexpr int RT = (RB * 32 <= 32 * 1024) ? 32 : (32 * 1024) / RB;
+	static constexpr int ROW_BYTES = RT * RB;
+	static constexpr int AUX_BYTES = RT * 32;
+	static constexpr int STAGE_BYTES = ((ROW_BYTES + AUX_BYTES + 127) / 128) * 128;
+};
+
+#define PA_TRACE(slot)                                                                      \
+	do {                                                                                    \
+		if (A.trace && blockIdx.x == 0 && threadIdx.x == 0 && step < A.trace_steps) {       \
+			unsigned long long _t;                                                          \
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                          \
+			A.trace[(size_t)step * 8 + (slot)] = _t;                                        \
+		}                                                                                   \
+	} while (0)
+
+template <int TB, int RB>
+__global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_constant__ PaArgs A) {
+	using C = RowCfg<RB>;
+	using T = PaTile<RB>;
+	constexpr int NB = RB / TB;
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ __align__(8) uint64_t full_bar[PA_MAX_STAGES];
+	__shared__ __align__(8) uint64_t empty_bar[PA_MAX_STAGES];
+	__shared__ PaPartial warp_part[PA_MAX_CONSUMERS];
+	__shared__ PaNear warp_near[PA_WARPS];
+	__shared__ PaPartial s_tot;
+	__shared__ long long s_base, s_lo, s_hi, s_front_row, s_back_row, s_new_center, s_seed;
+	__shared__ unsigned long long s_front_pos, s_back_pos, s_magc;
+	__shared__ unsigned long long s_red[PA_WARPS];
+	__shared__ int s_front_bin, s_back_bin, s_first_live, s_last_live, s_cta_npos;
+
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int G = gridDim.x, cta = blockIdx.x;
+	const int nb = A.nb;
+	const int NCW = A.ncw, D = A.d, NS = A.ns;
+
+	// ---- shared memory carve
+	uint8_t *sp = smem;
+	unsigned long long *s_bounds = reinterpret_cast<unsigned long long *>(sp); sp += (size_t)nb * 8;
+	uint32_t *s_row0 = reinterpret_cast<uint32_t *>(sp); sp += (size_t)(nb + 1) * 4;
+	uint32_t *s_alive = reinterpret_cast<uint32_t *>(sp); sp += (size_t)nb * 4;
+	uint32_t *s_sum = reinterpret_cast<uint32_t *>(sp); sp += (size_t)NB * 4;
+	uint32_t *s_marks = reinterpret_cast<uint32_t *>(sp); sp += (size_t)A.qmax * 4;
+	uint32_t *s_mpref = reinterpret_cast<uint32_t *>(sp); sp += (size_t)A.qmax * 4;
+	sp = reinterpret_cast<uint8_t *>(((uintptr_t)sp + 15) & ~(uintptr_t)15);
+	uint8_t *s_tq = sp; sp += RB;
+	sp = reinterpret_cast<uint8_t *>(((uintptr_t)sp + 127) & ~(uintptr_t)127);
+	uint8_t *ring = sp;
+
+	for (int i = threadIdx.x; i < nb; i += PA_THREADS) {
+		s_bounds[i] = A.bounds[i];
+		s_alive[i] = (uint32_t)(A.row0[i + 1] - A.row0[i]);
+	}
+	for (int i = threadIdx.x; i <= nb; i += PA_THREADS) s_row0[i] = (uint32_t)A.row0[i];
+	for (int i = threadIdx.x; i < NB; i += PA_THREADS) s_sum[i] = 0;
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < NS; s++) {
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		s_first_live = 0;
+		s_last_live = nb - 1;
+	}
+	__syncthreads();
+
+	auto bin_of = [&](long long row) {   // bin that holds `row`
+		int lo = 0, hi = nb;
+		while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long)s_row0[mid + 1] <= row) lo = mid + 1; else hi = mid; }
+		return lo;
+	};
+	// bvec::pop / erase (bvec.cpp:27-38,281-285) of a seed: every CTA clears the bit (idempotent) and
+	// updates its own bin counts
+	auto kill_row = [&](long long row) {
+		if (threadIdx.x == 0) {
+			// the returning form: the bit is cleared in L2 before this CTA reads the word again
+			const unsigned old = atomicAnd(A.alive_bits + (row >> 5), ~(1u << (row & 31)));
+			asm volatile("" ::"r"(old) : "memory");
+			s_alive[bin_of(row)]--;
+			__threadfence();
+		}
+	};
+	// first alive row in iteration order (bvec::pop), -1 when the bvec is empty; warp 0 only
+	auto pop_row = [&]() -> long long {
+		int fl = s_first_live;
+		while (fl < nb && s_alive[fl] == 0) fl++;
+		__syncwarp();
+		if (lane == 0) s_first_live = fl;
+		if (fl >= nb) return -1;
+		return pa_select(A.alive_bits, s_row0[fl], s_row0[fl + 1], 0, lane);
+	};
+
+	// ---- loop state, identical in every thread of every CTA
+	unsigned long long epoch = 0;     // grid barriers passed
+	long long step = 0;               // scans issued (parity of the partial buffers)
+	long long cluster = 0, cl_begin = 0, m0 = 1;
+	long long center;
+	bool first_step = true;
+	long long st_scans = 0, st_evals = 0, st_near = 0;
+	unsigned long long t_start = 0;
+	if (cta == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+
+	// running count of tiles consumed so far by (this consumer warp | the consumer this producer lane feeds)
+	long long ring_cnt = 0;
+
+	// first seed: bvec::pop (ClusterFactory.cpp:722)
+	if (wib == 0) {
+		const long long r = pop_row();
+		if (lane == 0) s_seed = r;
+	}
+	__syncthreads();
+	center = s_seed;
+	if (center >= 0) {
+		kill_row(center);
+		if (cta == 0 && threadIdx.x == 0) { A.members[0] = (int)center; A.cl_off[0] = 0; }
+	}
+	__syncthreads();
+
+	while (center >= 0) {
+		const int par = (int)(step & 1);
+		PA_TRACE(0);
+		// ================= control: bvec::get_range of the center's length window =================
+		if (wib < 2) {
+			const PaRange rec = A.range_tab[center];
+			if (wib == 0) {
+				int fb = rec.fb;
+				unsigned long long pos = 0;
+				if (s_alive[fb] == 0) {
+					int fl = s_first_live;
+					while (fl < nb && s_alive[fl] == 0) fl++;
+					if (fl < nb) fb = fl;   // position 0 of the first non-empty bin
+				} else {
+					unsigned a_lt, a_le, tot;
+					pa_rank3(A.alive_bits, s_row0[fb], s_row0[fb + 1], rec.f_lt, rec.f_le, lane, a_lt, a_le, tot);
+					unsigned long long f, b;
+					pa_inner_search(s_alive[fb], a_lt, a_le, f, b);
+					pos = f;
+				}
+				const long long row = pos < s_alive[fb] ? pa_select(A.alive_bits, s_row0[fb], s_row0[fb + 1], pos, lane) : -1;
+				if (lane == 0) { s_front_bin = fb; s_front_pos = pos; s_front_row = row; }
+			} else {
+				int bb = rec.bb;
+				unsigned long long pos = (unsigned long long)s_alive[nb - 1] - 1ull;   // wraps on an empty last bin, as in the reference
+				if (s_alive[bb] == 0) {
+					int ll = s_last_live;
+					while (ll >= 0 && s_alive[ll] == 0) ll--;
+					if (ll >= 0) { bb = ll; pos = 0; }   // position 0 of the LAST non-empty bin (bvec.cpp:68-77)
+				} else {
+					unsigned a_lt, a_le, tot;
+					pa_rank3(A.alive_bits, s_row0[bb], s_row0[bb + 1], rec.b_lt, rec.b_le, lane, a_lt, a_le, tot);
+					unsigned long long f, b;
+					pa_inner_search(s_alive[bb], a_lt, a_le, f, b);
+					pos = b;
+				}
+				const long long row = pos < s_alive[bb] ? pa_select(A.alive_bits, s_row0[bb], s_row0[bb + 1], pos, lane) : -1;
+				if (lane == 0) { s_back_bin = bb; s_back_pos = pos; s_back_row = row; }
+			}
+		}
+		__syncthreads();
+		if (wib == 0) {
+			// trip count of `for (it = front; it <= back; ++it)` = (back - front) + 1 with
+			// bvec_iterator::operator- (bvec_iterator.h:61-76); <= 0 means no iteration
+			int abin = s_back_bin, rbin = s_front_bin;
+			unsigned long long apos = s_back_pos, rpos = s_front_pos;
+			bool neg = false;
+			if (abin < rbin || (abin == rbin && apos < rpos)) {
+				neg = true;
+				const int tb = abin; abin = rbin; rbin = tb;
+				const unsigned long long tp = apos; apos = rpos; rpos = tp;
+			}
+			long long dlt;
+			if (abin == rbin) dlt = (long long)(apos - rpos);
+			else {
+				long long mid = 0;
+				for (int i = rbin + 1 + lane; i < abin; i += 32) mid += s_alive[i];
+#pragma unroll
+				for (int o = 16; o; o >>= 1) mid += __shfl_xor_sync(MC_FULL_MASK, mid, o);
+				dlt = (long long)apos + (long long)((unsigned long long)s_alive[rbin] - rpos) + mid;
+			}
+			if (neg) dlt = -dlt;
+			if (lane == 0) {
+				if (dlt + 1 > 0 && s_front_row >= 0 && s_back_row >= s_front_row) { s_lo = s_front_row; s_hi = s_back_row; }
+				else { s_lo = 0; s_hi = -1; }
+			}
+		}
+		__syncthreads();
+		const long long lo = s_lo, hi = s_hi;
+		PA_TRACE(1);
+
+		// ================= scan: Trainer::get_close over the alive rows of [lo, hi] =================
+		// tiles on an absolute grid (tile t = rows [t*RT, (t+1)*RT)); this CTA owns a contiguous run
+		const long long t0 = lo / T::RT, ntiles = hi >= lo ? hi / T::RT - t0 + 1 : 0;
+		const long long cbeg = t0 + ntiles * cta / G, cend = t0 + ntiles * (cta + 1) / G;
+		const int qc = (int)(cend - cbeg);   // <= qmax
+		PaPartial mine;
+		mc_scan_init(mine.s);
+		mine.n_near = 0; mine.pad = 0;
+		if (wib == 0) {
+			// ----- producer: lane l owns ring slot l = (consumer l / D, ring position l % D)
+			if (lane < NS) {
+				const int w = lane / D, dpos = lane % D;
+				const long long nw = qc > w ? (qc - w + NCW - 1) / NCW : 0;   // tiles of consumer w in this step
+				for (long long u = 0; u < nw; u++) {
+					const long long g = ring_cnt + u;
+					if ((int)(g % D) != dpos) continue;
+					const long long round = g / D;
+					if (round > 0) mbar_wait(&empty_bar[lane], (uint32_t)(round - 1) & 1);
+					const long long r0 = (cbeg + w + u * NCW) * T::RT;
+					long long nr = A.n - r0;
+					if (nr > T::RT) nr = T::RT;
+					uint8_t *dst = ring + (size_t)lane * T::STAGE_BYTES;
+					mbar_expect_tx(&full_bar[lane], (uint32_t)(nr * RB + nr * 32));
+					tma_bulk_g2s(dst, A.hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[lane]);
+					tma_bulk_g2s(dst + T::ROW_BYTES, A.aux + r0, (uint32_t)(nr * 32), &full_bar[lane]);
+				}
+				ring_cnt += nw;
+			}
+		} else if (wib - 1 < NCW) {
+			// ----- consumers
+			const int cw = wib - 1;
+			const int g = lane / C::LPP, r = lane % C::LPP;
+			CenterRegs<RB> cen;
+			cen.load(A.hist + (size_t)center * RB, r);
+			const McRowAux caux = A.aux[center];
+			const uint64_t lq = caux.len, mq = caux.mag, sq = caux.sq;
+			long long u = 0;
+			for (int jj = cw; jj < qc; jj += NCW, u++) {
+				const long long tile = cbeg + jj;
+				const long long row_mine = tile * T::RT + lane;
+				const long long word = (tile * T::RT) >> 5;
+				const int shift = (int)((tile * T::RT) & 31);
+				const uint32_t aw = __ldcg(A.alive_bits + word);
+				const bool have_row = lane < T::RT && row_mine >= lo && row_mine <= hi && ((aw >> (shift + lane)) & 1u) && row_mine != center;
+				const long long gcnt = ring_cnt + u;
+				const int slot = cw * D + (int)(gcnt % D);
+				mbar_wait(&full_bar[slot], (uint32_t)(gcnt / D) & 1);
+				const uint8_t *st = ring + (size_t)slot * T::STAGE_BYTES;
+				McRowAux my_aux;
+				my_aux.len = 0; my_aux.mag = 0; my_aux.sq = 0; my_aux.alive = 0; my_aux.pad = 0;
+				if (have_row) my_aux = *reinterpret_cast<const McRowAux *>(st + T::ROW_BYTES + (size_t)lane * 32);
+				PairAcc<TB> part[C::LPP];
+#pragma unroll
+				for (int it = 0; it < C::LPP; it++) {
+					const int p = g * C::LPP + it;
+					PairAcc<TB> acc;
+					if (T::RT == 32 || p < T::RT) {
+						const uint8_t *row = st + (size_t)p * RB;
+#pragma unroll
+						for (int c = 0; c < C::CH; c++) {
+							const uint4 v = *reinterpret_cast<const uint4 *>(row + (size_t)(c * C::LPP + r) * 16);
+							acc.add(v.x, cen.w[c][0]); acc.add(v.y, cen.w[c][1]);
+							acc.add(v.z, cen.w[c][2]); acc.add(v.w, cen.w[c][3]);
+						}
+					}
+					part[it] = acc;
+				}
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&empty_bar[slot]);   // the stage can be refilled during the epilogue
+				const PairAcc<TB> tot = mc_transpose_reduce<C::LPP>(part, r);
+				unsigned flag = 0;
+				if (have_row) {
+					double f0, sum;
+					mc_scan_epilogue<TB>(A.model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
+					flag = MC_IS_SIMILAR(sum) ? 1u : 0u;
+					mine.s.n_eval++;
+					mine.s.n_pos += flag;
+					if (fabs(sum) < MC_NEAR_THRESHOLD) mine.n_near++;
+					if (f0 > mine.s.best_f0) { mine.s.best_f0 = f0; mine.s.best_row = row_mine; }
+				}
+				const unsigned mask = __ballot_sync(MC_FULL_MASK, flag != 0);
+				if (lane == 0) s_marks[jj] = mask;
+				if (mask) {
+					// bvec::remove_available (bvec.cpp:290-317): the rows leave the bvec ...
+					if (lane == 0) atomicAnd(A.alive_bits + word, ~(mask << shift));
+					// ... and join `current`: their histograms go into this CTA's bin sums
+					for (unsigned mm = mask; mm; mm &= mm - 1) {
+						const long long mrow = tile * T::RT + (__ffs(mm) - 1);
+						const uint32_t *src = reinterpret_cast<const uint32_t *>(A.hist + (size_t)mrow * RB);
+						for (int wd = lane; wd < RB / 4; wd += 32) {
+							const uint32_t v = __ldg(src + wd);
+							if (TB == 1) {
+								atomicAdd(&s_sum[wd * 4 + 0], v & 0xffu); atomicAdd(&s_sum[wd * 4 + 1], (v >> 8) & 0xffu);
+								atomicAdd(&s_sum[wd * 4 + 2], (v >> 16) & 0xffu); atomicAdd(&s_sum[wd * 4 + 3], v >> 24);
+							} else {
+								atomicAdd(&s_sum[wd * 2 + 0], v & 0xffffu); atomicAdd(&s_sum[wd * 2 + 1], v >> 16);
+							}
+						}
+					}
+				}
+			}
+			ring_cnt += u;
+			mc_scan_warp_fold(mine.s);
+#pragma unroll
+			for (int o = 16; o; o >>= 1) mine.n_near += __shfl_xor_sync(MC_FULL_MASK, mine.n_near, o);
+			if (lane == 0) warp_part[cw] = mine;
+		}
+		__syncthreads();
+		PA_TRACE(2);
+		// ----- CTA partial, flush of the bin sums
+		if (wib == 0) {
+			PaPartial b;
+			mc_scan_init(b.s);
+			b.n_near = 0; b.pad = 0;
+			if (lane < NCW) b = warp_part[lane];
+			mc_scan_warp_fold(b.s);
+#pragma unroll
+			for (int o = 16; o; o >>= 1) b.n_near += __shfl_xor_sync(MC_FULL_MASK, b.n_near, o);
+			if (lane == 0) {
+				A.partials[(size_t)par * G + cta] = b;
+				s_cta_npos = (int)b.s.n_pos;
+			}
+		}
+		__syncthreads();
+		const int gbuf = (int)(cluster % 3);
+		{
+			// `current` starts as {seed} (ClusterFactory.cpp:641): CTA 0 adds the seed's histogram in the
+			// first step of a cluster
+			const bool seed_add = first_step && cta == 0;
+			if (s_cta_npos > 0 || seed_add) {
+				unsigned long long *gs = A.g_sum + (size_t)gbuf * NB;
+				for (int b = threadIdx.x; b < NB; b += PA_THREADS) {
+					unsigned long long v = s_sum[b];
+					if (seed_add) v += TB == 1 ? (unsigned long long)A.hist[(size_t)center * RB + b]
+					                           : (unsigned long long)reinterpret_cast<const uint16_t *>(A.hist + (size_t)center * RB)[b];
+					if (v) atomicAdd(gs + b, v);
+					s_sum[b] = 0;
+				}
+			}
+		}
+		if (!pa_grid_barrier(A.bar, ++epoch * (unsigned long long)G)) return;
+		PA_TRACE(3);
+
+		// ================= fold (every CTA, redundantly: <= 148 records out of L2) =================
+		if (wib == 0) {
+			PaPartial t;
+			mc_scan_init(t.s);
+			t.n_near = 0; t.pad = 0;
+			long long base = 0;
+			for (int i = lane; i < G; i += 32) {
+				const PaPartial *p = A.partials + (size_t)par * G + i;
+				mc_scan_result q;
+				q.n_eval = __ldcg(&p->s.n_eval); q.n_pos = __ldcg(&p->s.n_pos);
+				q.best_row = __ldcg(&p->s.best_row); q.best_f0 = __ldcg(&p->s.best_f0);
+				mc_scan_merge(t.s, q);
+				t.n_near += __ldcg(&p->n_near);
+				if (i < cta) base += q.n_pos;
+			}
+			mc_scan_warp_fold(t.s);
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				t.n_near += __shfl_xor_sync(MC_FULL_MASK, t.n_near, o);
+				base += __shfl_xor_sync(MC_FULL_MASK, base, o);
+			}
+			if (lane == 0) { s_tot = t; s_base = base; }
+		}
+		__syncthreads();
+		const mc_scan_result tot = s_tot.s;
+		if (hi >= lo) { st_scans++; st_evals += tot.n_eval; st_near += s_tot.n_near; }
+		step++;
+		first_step = false;
+		PA_TRACE(4);
+
+		if (tot.n_pos == 0) {
+			// ----- is_min: no close point left (ClusterFactory.cpp:693-711): the cluster is closed, the
+			// arg-max of f0 becomes the next seed, or the first point of the bvec when there is none
+			if (wib == 0) {
+				long long r = tot.best_row;
+				if (r < 0) r = pop_row();
+				if (lane == 0) s_seed = r;
+			}
+			if (cta == 0) {
+				if (threadIdx.x == 0) {
+					A.cl_center[cluster] = (int)center;
+					A.cl_off[cluster + 1] = (int)(cl_begin + m0);
+				}
+				// the sums buffer of the cluster after the next one (last read two clusters ago)
+				unsigned long long *gz = A.g_sum + (size_t)((cluster + 2) % 3) * NB;
+				for (int b = threadIdx.x; b < NB; b += PA_THREADS) gz[b] = 0;
+			}
+			__syncthreads();
+			const long long seed = s_seed;
+			cluster++;
+			cl_begin += m0;
+			m0 = 1;
+			first_step = true;
+			center = seed;
+			if (seed >= 0) {
+				kill_row(seed);
+				if (cta == 0 && threadIdx.x == 0) A.members[cl_begin] = (int)seed;
+			}
+			__syncthreads();
+			PA_TRACE(7);
+			continue;
+		}
+
+		// ================= tail: `current` += marked rows, get_mean, nearest member =================
+		const long long n_new = tot.n_pos, m_all = m0 + n_new;
+		if (wib == 0) {
+			// exclusive prefix of the marks per tile of this CTA's run
+			unsigned carry = 0;
+			for (int i0 = 0; i0 < qc; i0 += 32) {
+				const int i = i0 + lane;
+				const unsigned pc = i < qc ? __popc(s_marks[i]) : 0u;
+				unsigned incl = pc;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const unsigned v = __shfl_up_sync(MC_FULL_MASK, incl, o);
+					if (lane >= o) incl += v;
+				}
+				if (i < qc) s_mpref[i] = carry + incl - pc;
+				carry += __shfl_sync(MC_FULL_MASK, incl, 31);
+			}
+		}
+		{
+			// truncated mean: floor(sum / |current|) per bin and its magnitude (DivergencePoint.cpp:53-65,155-173)
+			const unsigned long long *gs = A.g_sum + (size_t)gbuf * NB;
+			unsigned long long local = 0;
+			for (int b = threadIdx.x; b < NB; b += PA_THREADS) {
+				const unsigned long long v = __ldcg(gs + b) / (unsigned long long)m_all;
+				if (TB == 1) s_tq[b] = (uint8_t)v; else reinterpret_cast<uint16_t *>(s_tq)[b] = (uint16_t)v;
+				local += v;
+			}
+#pragma unroll
+			for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(MC_FULL_MASK, local, o);
+			if (lane == 0) s_red[wib] = local;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			unsigned long long t = 0;
+			for (int w = 0; w < PA_WARPS; w++) t += s_red[w];
+			s_magc = t;
+		}
+		__syncthreads();
+		const unsigned long long magc = s_magc;
+		PaNear best;
+		best.pos = -1; best.dist = 0; best.row = -1; best.pad = 0;
+		auto consider = [&](long long row, long long pos) {
+			const PairAcc<TB> pa = mc_warp_pair_reduce<TB>(A.hist + (size_t)row * RB, s_tq, RB, lane);
+			const uint64_t mp = A.aux[row].mag;
+			PaNear cnd;
+			cnd.pos = pos; cnd.row = row; cnd.pad = 0;
+			cnd.dist = mc_distance_d(pa.summin(mp, magc), mp, magc);
+			pa_near_merge(best, cnd);   // NaN never replaces, like the reference's `<`
+		};
+		// this CTA's new members, in row order behind the ones of the CTAs before it
+		for (int i = wib; i < qc; i += PA_WARPS) {
+			const unsigned mask = s_marks[i];
+			if (!mask) continue;
+			long long pos = m0 + s_base + s_mpref[i];
+			for (unsigned mm = mask; mm; mm &= mm - 1, pos++) {
+				const long long row = (cbeg + i) * T::RT + (__ffs(mm) - 1);
+				if (lane == 0) A.members[cl_begin + pos] = (int)row;
+				consider(row, pos);
+			}
+		}
+		// its share of the members `current` already had
+		for (long long idx = (long long)cta * PA_WARPS + wib; idx < m0; idx += (long long)G * PA_WARPS)
+			consider(__ldcg(A.members + cl_begin + idx), idx);
+		if (lane == 0) warp_near[wib] = best;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			PaNear b = warp_near[0];
+			for (int w = 1; w < PA_WARPS; w++) pa_near_merge(b, warp_near[w]);
+			A.near[(size_t)par * G + cta] = b;
+		}
+		PA_TRACE(5);
+		if (!pa_grid_barrier(A.bar, ++epoch * (unsigned long long)G)) return;
+		PA_TRACE(6);
+		if (wib == 0) {
+			PaNear b;
+			b.pos = -1; b.dist = 0; b.row = -1; b.pad = 0;
+			for (int i = lane; i < G; i += 32) {
+				const PaNear *p = A.near + (size_t)par * G + i;
+				PaNear q;
+				q.pos = __ldcg(&p->pos); q.dist = __ldcg(&p->dist); q.row = __ldcg(&p->row); q.pad = 0;
+				pa_near_merge(b, q);
+			}
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				PaNear q;
+				q.pos = __shfl_xor_sync(MC_FULL_MASK, b.pos, o);
+				q.dist = __shfl_xor_sync(MC_FULL_MASK, b.dist, o);
+				q.row = __shfl_xor_sync(MC_FULL_MASK, b.row, o);
+				q.pad = 0;
+				pa_near_merge(b, q);
+			}
+			if (lane == 0) s_new_center = b.row;
+		}
+		// every CTA keeps its own bin counts: the new members leave their bins
+		for (long long i = threadIdx.x; i < n_new; i += PA_THREADS)
+			atomicSub(&s_alive[bin_of(__ldcg(A.members + cl_begin + m0 + i))], 1u);
+		__syncthreads();
+		center = s_new_center;   // get_mean always finds a member: `current` is never empty
+		m0 = m_all;
+		PA_TRACE(7);
+	}
+
+	if (cta == 0 && threadIdx.x == 0) {
+		unsigned long long t_end;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+		A.stats[0] = cluster;
+		A.stats[1] = st_scans;
+		A.stats[2] = st_evals;
+		A.stats[3] = st_near;
+		A.stats[4] = step;
+		A.stats[5] = (long long)(t_end - t_start);
+	}
+}
+
+// ---- launcher ----------------------------------------------------------------------------------
+struct PaLaunch {
+	PaArgs args;
+	int grid;
+	size_t smem;
+};
+
+template <int TB, int RB>
+static int pa_launch_t(mc_ctx *ctx, PaArgs &a, int grid) {
+	using T = PaTile<RB>;
+	constexpr int NB = RB / TB;
+	int dev_smem = 0;
+	MC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+	const size_t fixed = (size_t)a.nb * 8 + (size_t)(a.nb + 1) * 4 + (size_t)a.nb * 4 + (size_t)NB * 4 + (size_t)a.qmax * 8 + 16 + RB + 128 + 128;
+	const size_t static_smem = 4096;   // barriers, warp partials, control words (upper bound)
+	MC_REQUIRE(fixed + static_smem + 2 * (size_t)T::STAGE_BYTES <= (size_t)dev_smem, MC_ERR_UNSUPPORTED,
+	           "mc_accumulate_run: %d bvec bins / %lld rows need more shared memory than one CTA has", a.nb, (long long)a.n);
+	int ns = (int)(((size_t)dev_smem - static_smem - fixed) / T::STAGE_BYTES);
+	if (ns > PA_MAX_STAGES) ns = PA_MAX_STAGES;
+	a.ncw = ns < PA_MAX_CONSUMERS ? ns : PA_MAX_CONSUMERS;
+	a.d = ns / a.ncw;
+	a.ns = a.ncw * a.d;
+	const size_t smem = fixed + (size_t)a.ns * T::STAGE_BYTES;
+	const void *fn = (const void *)phase_a_kernel<TB, RB>;
+	MC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PA_THREADS, smem));
+	MC_REQUIRE(per_sm >= 1, MC_ERR_UNSUPPORTED, "mc_accumulate_run: the persistent kernel does not fit an SM (%zu bytes of shared memory)", smem);
+	void *params[] = {&a};
+	MC_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PA_THREADS), params, smem, ctx->stream));
+	ctx->launches++;
+	return MC_OK;
+}
+
+int mc_pa_rows_per_tile(int tbytes, int nbins) {
+	const int rb = tbytes * nbins;
+	return rb * 32 <= 32 * 1024 ? 32 : (32 * 1024) / rb;
+}
+
+size_t mc_pa_partial_bytes() { return sizeof(PaPartial) > sizeof(PaNear) ? sizeof(PaPartial) : sizeof(PaNear); }
+size_t mc_pa_range_bytes() { return sizeof(PaRange); }
+
+int mc_launch_pa_prepare(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, double sim,
+                         void *range_tab_dev, unsigned int *err_dev) {
+	int64_t blocks = (ctx->n + 255) / 256;
+	if (blocks > (int64_t)ctx->num_sms * 8) blocks = (int64_t)ctx->num_sms * 8;
+	pa_prepare_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(ctx->d_aux, ctx->n, bounds_dev, row0_dev, nb, sim, (PaRange *)range_tab_dev, err_dev);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
+// shapes of the staged scan: rows of 16 bytes .. 4 KB
+bool mc_pa_shape_supported(int tbytes, int nbins) {
+	const int rb = tbytes * nbins;
+	if (tbytes == 1) return rb == 16 || rb == 64 || rb == 256 || rb == 1024 || rb == 4096;
+	return rb == 32 || rb == 128 || rb == 512 || rb == 2048;
+}
+
+int mc_launch_phase_a(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, const void *range_tab_dev,
+                      uint32_t *alive_bits_dev, unsigned long long *g_sum_dev, void *partials_dev, void *near_dev,
+                      unsigned long long *bar_dev, int *members_dev, int *cl_center_dev, int *cl_off_dev, long long *stats_dev,
+                      unsigned long long *trace_dev, int trace_steps, int grid, int qmax) {
+	PaArgs a{};
+	a.hist = (const uint8_t *)ctx->d_hist;
+	a.aux = ctx->d_aux;
+	a.n = ctx->n;
+	a.bounds = bounds_dev;
+	a.row0 = row0_dev;
+	a.nb = nb;
+	a.qmax = qmax;
+	a.range_tab = (const PaRange *)range_tab_dev;
+	a.alive_bits = alive_bits_dev;
+	a.g_sum = g_sum_dev;
+	a.partials = (PaPartial *)partials_dev;
+	a.near = (PaNear *)near_dev;
+	a.bar = bar_dev;
+	a.members = members_dev;
+	a.cl_center = cl_center_dev;
+	a.cl_off = cl_off_dev;
+	a.stats = stats_dev;
+	a.trace = trace_dev;
+	a.trace_steps = trace_steps;
+	a.model = ctx->model;
+	const int rb = ctx->tbytes * ctx->nbins;
+	if (ctx->tbytes == 1) {
+		switch (rb) {
+		case 16: return pa_launch_t<1, 16>(ctx, a, grid);
+		case 64: return pa_launch_t<1, 64>(ctx, a, grid);
+		case 256: return pa_launch_t<1, 256>(ctx, a, grid);
+		case 1024: return pa_launch_t<1, 1024>(ctx, a, grid);
+		case 4096: return pa_launch_t<1, 4096>(ctx, a, grid);
+		default: break;
+		}
+	} else {
+		switch (rb) {
+		case 32: return pa_launch_t<2, 32>(ctx, a, grid);
+		case 128: return pa_launch_t<2, 128>(ctx, a, grid);
+		case 512: return pa_launch_t<2, 512>(ctx, a, grid);
+		case 2048: return pa_launch_t<2, 2048>(ctx, a, grid);
+		default: break;
+		}
+	}
+	mc_set_error("mc_accumulate_run: histogram rows of %d bytes are not supported by the persistent kernel", rb);
+	return MC_ERR_UNSUPPORTED;
+}

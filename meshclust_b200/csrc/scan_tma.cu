@@ -22,51 +22,7 @@
 //     from the kernel (direct) or are left as tag-polled copies for the exchange stream (burst).
 // Dead rows are copied too; the host compacts the row arrays as Phase A consumes them (mc_permute_rows).
 #include "pair_core.cuh"
-
-struct ScanPartial {
-	long long n_eval;
-	long long n_pos;
-	long long best_row;
-	double best_f0;
-};
-
-__device__ __forceinline__ void tscan_merge(ScanPartial &a, const ScanPartial &b) {
-	a.n_eval += b.n_eval;
-	a.n_pos += b.n_pos;
-	// first maximum in row order wins (Trainer.cpp:99 strict >, serial iteration order)
-	if (b.best_row >= 0 && (b.best_f0 > a.best_f0 || (b.best_f0 == a.best_f0 && (a.best_row < 0 || b.best_row < a.best_row)))) {
-		a.best_f0 = b.best_f0;
-		a.best_row = b.best_row;
-	}
-}
-
-// ---- mbarrier / TMA bulk-copy PTX --------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"WAIT_%=:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra DONE_%=;\n"
-		"bra WAIT_%=;\n"
-		"DONE_%=:\n"
-		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
+#include "tma_utils.cuh"
 
 // ---- geometry ----------------------------------------------------------------------------------
 constexpr int TSCAN_MAX_CONSUMERS = 24;   // small rows: one tile per warp hides the FP64 epilogue latency of short scans
@@ -272,7 +228,8 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			if (lane < T::RT && row >= lo && row <= hi) {
 				unsigned flag = 0;
 				if (__ldcg(&aux[row].alive)) {
-					flag = flag_in;
+					flag = flag_in & 1u;
+					if (flag_in & 2u) atomicAdd(model.near, 1ull);
 					mine.n_eval++;
 					mine.n_pos += flag;
 					if (f0 > mine.best_f0) { mine.best_f0 = f0; mine.best_row = row; }
@@ -332,7 +289,8 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 				if (have_row) {
 					double sum;
 					mc_scan_epilogue<TB>(model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
-					flag = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1u : 0u;
+					flag = MC_IS_SIMILAR(sum) ? 1u : 0u;
+					if (fabs(sum) < MC_NEAR_THRESHOLD) flag |= 2u;   // counted when the row turns out to be alive
 				}
 				if (u == 0) { pre_f0_0 = f0; pre_flag_0 = flag; } else { pre_f0_1 = f0; pre_flag_1 = flag; }
 				npre = (int)u + 1;
@@ -341,7 +299,8 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 				if (__ldcg(&aux[row_mine].alive)) {   // dead rows skip the epilogue
 					double f0, sum;
 					mc_scan_epilogue<TB>(model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
-					flag = (sum >= MC_SIGMOID_SUM_THRESHOLD) ? 1u : 0u;
+					flag = MC_IS_SIMILAR(sum) ? 1u : 0u;
+					mc_count_near(model, sum);
 					mine.n_eval++;
 					mine.n_pos += flag;
 					if (f0 > mine.best_f0) { mine.best_f0 = f0; mine.best_row = row_mine; }
@@ -351,15 +310,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 			}
 		}
 		if (!waited) dependency_wait();
-#pragma unroll
-		for (int o = 16; o; o >>= 1) {
-			ScanPartial other;
-			other.n_eval = __shfl_xor_sync(MC_FULL_MASK, mine.n_eval, o);
-			other.n_pos = __shfl_xor_sync(MC_FULL_MASK, mine.n_pos, o);
-			other.best_row = __shfl_xor_sync(MC_FULL_MASK, mine.best_row, o);
-			other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, mine.best_f0, o);
-			tscan_merge(mine, other);
-		}
+		mc_scan_warp_fold(mine);
 		if (lane == 0) warp_part[cw] = mine;
 		TRACE(5);
 	}
@@ -371,15 +322,7 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 		ScanPartial b;
 		b.n_eval = 0; b.n_pos = 0; b.best_row = -1; b.best_f0 = -1.0;
 		if (lane < T::NCW) b = warp_part[lane];
-#pragma unroll
-		for (int o = 16; o; o >>= 1) {
-			ScanPartial other;
-			other.n_eval = __shfl_xor_sync(MC_FULL_MASK, b.n_eval, o);
-			other.n_pos = __shfl_xor_sync(MC_FULL_MASK, b.n_pos, o);
-			other.best_row = __shfl_xor_sync(MC_FULL_MASK, b.best_row, o);
-			other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, b.best_f0, o);
-			tscan_merge(b, other);
-		}
+		mc_scan_warp_fold(b);
 		if (lane == 0) partials[blockIdx.x] = b;
 		if constexpr (PUSH == 2) {
 			// burst path: the exchange stream is not ordered behind this launch by an event (which would sit
@@ -433,16 +376,8 @@ __global__ void scan_fold_kernel(const ScanPartial *__restrict__ slots, const in
 	const ScanPartial *p = slots + (size_t)s * MC_SCAN_PARTS;
 	ScanPartial b;
 	b.n_eval = 0; b.n_pos = 0; b.best_row = -1; b.best_f0 = -1.0;
-	for (int i = lane; i < nparts[s]; i += 32) tscan_merge(b, p[i]);
-#pragma unroll
-	for (int o = 16; o; o >>= 1) {
-		ScanPartial other;
-		other.n_eval = __shfl_xor_sync(MC_FULL_MASK, b.n_eval, o);
-		other.n_pos = __shfl_xor_sync(MC_FULL_MASK, b.n_pos, o);
-		other.best_row = __shfl_xor_sync(MC_FULL_MASK, b.best_row, o);
-		other.best_f0 = __shfl_xor_sync(MC_FULL_MASK, b.best_f0, o);
-		tscan_merge(b, other);
-	}
+	for (int i = lane; i < nparts[s]; i += 32) mc_scan_merge(b, p[i]);
+	mc_scan_warp_fold(b);
 	if (lane == 0) out[s] = b;
 }
 

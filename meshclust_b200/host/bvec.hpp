@@ -244,6 +244,14 @@ public:
 	}
 
 	size_t nbins() const { return data_.size(); }
+	// the layout a device-resident copy needs (mc_accumulate_run): bin bounds and, after assign_rows(),
+	// the first row of every bin followed by the number of rows
+	const std::vector<uint64_t> &bounds() const { return bounds_; }
+	std::vector<int64_t> first_rows() const {
+		std::vector<int64_t> r(row0_);
+		r.push_back(row0_.empty() ? 0 : row0_.back() + (int64_t)data_.back().items.size());
+		return r;
+	}
 
 private:
 	struct Bin {

@@ -629,6 +629,32 @@ void mean_shift(Ctx &c, BVec &bv) {
 		fprintf(stderr, "meshclust: mc_ctx_create failed on an additional GPU: %s\n", c.ranks_err.c_str());
 		exit(2);
 	}
+	// ---------------- Phase A on the device (mc_accumulate_run) ---------------------------------
+	// The whole `while (last) accumulate(...)` loop (ClusterFactory.cpp:722-729, :637-714) with its bvec
+	// bookkeeping runs as one persistent kernel; the host only reads the clusters back.  --align (the
+	// decision is an alignment, not a scan), histogram shapes the staged scan kernel does not take and
+	// MC_PHASE_A_STEPS=1 (tests) go through the step-by-step loop below.
+	bool phase_a_done = false;
+	if (!c.model.align && !getenv("MC_PHASE_A_STEPS")) {
+		const std::vector<int64_t> first = bv.first_rows();
+		std::vector<int64_t> centers((size_t)ds.n), offs((size_t)ds.n + 1), members((size_t)ds.n);
+		mc_run_stats st;
+		const int rc = mc_accumulate_run(c.gpu, sim, bv.bounds().data(), first.data(), (int64_t)bv.nbins(), centers.data(), offs.data(), members.data(), &st);
+		if (rc == MC_OK) {
+			part.resize((size_t)st.n_clusters);
+#pragma omp parallel for schedule(dynamic, 64)
+			for (long ci = 0; ci < (long)st.n_clusters; ci++) {
+				part[(size_t)ci].center_row = centers[(size_t)ci];
+				part[(size_t)ci].rows.assign(members.begin() + offs[(size_t)ci], members.begin() + offs[(size_t)ci + 1]);
+			}
+			printf("Accumulation: %zu clusters, %lld scans, %lld evals, on the device in %.4fs (%.2f us per step)  [%.2fs]\n", part.size(),
+			       (long long)st.n_scans, (long long)st.n_evals, st.device_seconds, st.n_steps ? st.device_seconds * 1e6 / (double)st.n_steps : 0.0, tm.lap());
+			phase_a_done = true;
+		} else if (rc != MC_ERR_UNSUPPORTED) {
+			die_gpu("mc_accumulate_run");
+		}
+	}
+	if (!phase_a_done) {
 	if (world > 1 && !c.model.align) {
 		// rows are replicated once (device-to-device), scan work and alive flags are sharded
 		// block-interleaved (~256 KB of consecutive rows per block, blocks round-robin over the GPUs);
@@ -750,6 +776,7 @@ void mean_shift(Ctx &c, BVec &bv) {
 		last = next_seed;
 	}
 	printf("Accumulation: %zu clusters, %lld scans, %lld evals, %d row compactions (host %.3fs, gpu calls %.3fs)  [%.2fs]\n", part.size(), (long long)scans, (long long)evals, compactions, compact_host_s, compact_gpu_s, tm.lap());
+	}
 
 	// ---------------- Phase B: update + merge (ClusterFactory.cpp:733-753) -----------------------
 	int iters_run = 0;
@@ -843,6 +870,12 @@ void mean_shift(Ctx &c, BVec &bv) {
 		iters_run = iter + 1;
 	}
 	printf("Update: %zu clusters after %d of %d iterations (fixed point)  [%.2fs]\n", part.size(), iters_run, c.opt.iterations, tm.lap());
+	if (!c.model.align) {
+		// the only decisions a differently rounded exp() could turn: GLM sums within 1e-9 of the threshold
+		int64_t near = 0;
+		GPU(mc_near_threshold_count(c.gpu, &near, 0));
+		printf("Pairs within 1e-9 of the decision threshold: %lld\n", (long long)near);
+	}
 	write_clstr(c, part);
 }
 

@@ -74,7 +74,18 @@ CASES = {
     "J": ([("J.fa", dict(n=900, ntemp=9, lmin=300, lmax=360, mu=0.03, seed=23, crlf=True))], ["--id", "0.90", "--kmer", "3"]),
     "F": ([("F.fa", dict(n=1300, ntemp=20, lmin=260, lmax=420, mu=0.03, seed=17, iupac=True))],
           ["--id", "0.90", "--kmer", "4", "--sample", "2000", "--pivot", "10"]),
+    # 1024- and 4096-bin histograms (k = 5, k = 6: the shapes of BASELINE configs[3] and [4])
+    "P": ([("P.fa", dict(n=3000, ntemp=30, lmin=900, lmax=1100, mu=0.03, seed=51))], ["--id", "0.90", "--kmer", "5"]),
+    "Q": ([("Q.fa", dict(n=1500, ntemp=15, lmin=3000, lmax=3500, mu=0.03, seed=52))], ["--kmer", "6"]),
+    # BASELINE.json configs[1] in full (100k x 1.5 kb, 1000 clusters; the reference needs ~10 min at --threads 1)
+    "c2_full": ([("c2.fa", dict(config="c2"))], ["--id", "0.97", "--kmer", "4"]),
+    # BASELINE.json configs[2] (forced alignment) on its first 2000 sequences (~30 min of reference time)
+    "c3_2k": ([("c3.fa", dict(config="c3", n=2000))], ["--id", "0.70", "--align"]),
 }
+
+# cases whose CPU stand-in run (oracle arithmetic on a few host cores) would take many minutes: GPU tests only
+GPU_ONLY = {"c2_full", "c3_2k"}
+CPU_CASES = [c for c in CASES if c not in GPU_ONLY]
 
 
 def make_inputs(name: str, workdir: str):

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@ struct mc_ctx {
 	int nfeat = 0;
 	std::vector<int64_t> members;
 	int64_t launches = 0;
+	int64_t near = 0;   // decisions with |sum| < 1e-9
 };
 
 static thread_local char g_err[512] = "";
@@ -157,7 +159,13 @@ static void eval_one(mc_ctx *c, int64_t p, int64_t q, double *sum, double *f0, u
 	for (int j = 0; j < c->nfeat; j++) s = fma(c->w[j + 1], f[j], s);
 	if (sum) *sum = s;
 	if (f0) *f0 = f[0];
-	if (flag) *flag = round(1.0 / (1 + exp(-s))) == 1.0;
+	if (flag) {
+		*flag = round(1.0 / (1 + exp(-s))) == 1.0;
+		if (fabs(s) < 1e-9) {
+#pragma omp atomic
+			c->near++;
+		}
+	}
 	if (feats) memcpy(feats, f, sizeof(f));
 }
 int mc_pair_classify(mc_ctx *c, const int32_t *a, const int32_t *b, int64_t m, double *sum, double *f0, uint8_t *flag, double *feats) {
@@ -225,6 +233,125 @@ int mc_accumulate_step(mc_ctx *c, int64_t center, int64_t lo, int64_t hi, int re
 	res->n_members = (int64_t)c->members.size();
 	return MC_OK;
 }
+int mc_near_threshold_count(mc_ctx *c, int64_t *out, int reset) { *out = c->near; if (reset) c->near = 0; return MC_OK; }
+
+// A literal restatement of the reference's length-binned container (bvec.cpp) on (row, length)
+// entries -- vectors with erase, linear walks -- independent of host/bvec.hpp and of the device code.
+namespace {
+struct LitBvec {
+	typedef std::pair<int64_t, uint64_t> Item;   // row, length
+	std::vector<std::vector<Item>> data;
+	std::vector<uint64_t> bounds;
+	void index_of(uint64_t point, size_t *pfront, size_t *pback) const {   // bvec.cpp:123-149
+		size_t low = bounds.size() - 1, high = 0;
+		for (size_t i = 0; i < bounds.size(); i++) {
+			const size_t prev = i > 0 ? bounds[i - 1] : 0;
+			const size_t prev_index = i > 0 ? i - 1 : 0;
+			if (point >= prev && point <= bounds[i]) { low = std::min(low, prev_index); high = std::max(high, prev_index); }
+		}
+		if (point >= bounds.back()) high = std::max(high, bounds.size() - 1);
+		if (pfront) *pfront = low;
+		if (pback) *pback = high;
+	}
+	void inner_index_of(uint64_t length, size_t &idx, size_t *pfront, size_t *pback) const {   // bvec.cpp:52-120
+		if (data.at(idx).empty()) {
+			if (pfront) for (size_t i = 0; i < data.size(); i++) if (!data[i].empty()) { idx = i; *pfront = 0; break; }
+			if (pback) for (long i = (long)data.size() - 1; i >= 0; i--) if (!data[i].empty()) { idx = (size_t)i; *pback = 0; break; }
+			return;
+		}
+		const std::vector<Item> &bin = data[idx];
+		size_t front = 0, back = 0, low = 0, high = bin.size() - 1;
+		while (low <= high) {
+			const size_t mid = (low + high) / 2;
+			const uint64_t d = bin[mid].second;
+			if (d == length) { front = back = mid; break; }
+			else if (length < d) high = mid;
+			else low = mid + 1;
+			if (low == high) { front = low; back = high; break; }
+		}
+		if (pfront) { for (long i = (long)front; i >= 0 && bin[(size_t)i].second == length; i--) front = (size_t)i; *pfront = front; }
+		if (pback) { for (size_t i = back; i < bin.size() && bin[i].second == length; i++) back = i; *pback = back; }
+	}
+	long diff(size_t abin, size_t apos, size_t rbin, size_t rpos) const {   // bvec_iterator.h:61-76
+		if (abin < rbin || (abin == rbin && apos < rpos)) return -diff(rbin, rpos, abin, apos);
+		if (abin == rbin) return (long)(apos - rpos);
+		long sum = (long)apos;
+		sum += (long)(data.at(rbin).size() - rpos);
+		for (size_t i = rbin + 1; i < abin; i++) sum += (long)data[i].size();
+		return sum;
+	}
+	int64_t pop() {   // bvec.cpp:27-38
+		for (auto &bin : data) if (!bin.empty()) { const int64_t r = bin[0].first; bin.erase(bin.begin()); return r; }
+		return -1;
+	}
+};
+}  // namespace
+
+int mc_accumulate_run(mc_ctx *c, double sim, const uint64_t *bin_bounds, const int64_t *first_row, int64_t nb, int64_t *centers_out,
+                      int64_t *offs_out, int64_t *members_out, mc_run_stats *st) {
+	LitBvec bv;
+	bv.bounds.assign(bin_bounds, bin_bounds + nb);
+	bv.data.resize((size_t)nb);
+	for (int64_t b = 0; b < nb; b++)
+		for (int64_t r = first_row[b]; r < first_row[b + 1]; r++) bv.data[(size_t)b].push_back({r, c->len[(size_t)r]});
+	c->alive.assign((size_t)c->n, 1);
+	int64_t nc = 0, total = 0, scans = 0, evals = 0, steps = 0;
+	const int64_t near0 = c->near;
+	offs_out[0] = 0;
+	int64_t last = bv.pop();
+	if (last >= 0) c->alive[(size_t)last] = 0;
+	while (last >= 0) {   // ClusterFactory.cpp:722-729 around accumulate (:637-714)
+		std::vector<int64_t> current{last};
+		int64_t next_seed = -1;
+		for (bool is_min = false; !is_min;) {
+			const uint64_t len = c->len[(size_t)last];
+			size_t fbin = 0, fpos = 0, bbin = bv.data.size() - 1, bpos = bv.data[bbin].size() - 1;   // bvec.cpp:247-278
+			bv.index_of((uint64_t)(len * sim), &fbin, nullptr);
+			bv.index_of((uint64_t)(len / sim), nullptr, &bbin);
+			bv.inner_index_of((uint64_t)(len * sim), fbin, &fpos, nullptr);
+			bv.inner_index_of((uint64_t)(len / sim), bbin, nullptr, &bpos);
+			mc_scan_result res;
+			res.n_eval = 0; res.n_pos = 0; res.best_row = -1; res.best_f0 = -1;
+			std::vector<uint8_t> marks;
+			int64_t lo = 0, hi = -1;
+			if (bv.diff(bbin, bpos, fbin, fpos) + 1 > 0) {
+				lo = bv.data[fbin][fpos].first;
+				hi = bv.data[bbin][bpos].first;
+				marks.resize((size_t)(hi - lo + 1));
+				mc_scan(c, last, lo, hi, &res, marks.data());
+				scans++; evals += res.n_eval;
+			}
+			steps++;
+			is_min = res.n_pos == 0;
+			if (is_min) {
+				if (res.best_row < 0) next_seed = bv.pop();
+				else {
+					next_seed = res.best_row;
+					for (auto &bin : bv.data)
+						for (size_t i = 0; i < bin.size(); i++) if (bin[i].first == next_seed) { bin.erase(bin.begin() + (long)i); break; }
+				}
+				if (next_seed >= 0) c->alive[(size_t)next_seed] = 0;
+			} else {
+				for (size_t b = fbin; b <= bbin && b < bv.data.size(); b++) {   // remove_available, bvec.cpp:290-317
+					std::vector<LitBvec::Item> keep;
+					for (const auto &it : bv.data[b]) {
+						if (it.first >= lo && it.first <= hi && marks[(size_t)(it.first - lo)]) current.push_back(it.first);
+						else keep.push_back(it);
+					}
+					bv.data[b].swap(keep);
+				}
+				last = nearest_of(c, current, nullptr);
+			}
+		}
+		centers_out[nc] = last;
+		for (int64_t r : current) members_out[total++] = r;
+		offs_out[++nc] = total;
+		last = next_seed;
+	}
+	if (st) { st->n_clusters = nc; st->n_scans = scans; st->n_evals = evals; st->n_near_threshold = c->near - near0; st->n_steps = steps; st->device_seconds = 0; }
+	return MC_OK;
+}
+
 int mc_clone_points(mc_ctx *dst, mc_ctx *src) { *dst = *src; return MC_OK; }
 int mc_comm_init(mc_ctx *, int, int, uint8_t *) { return MC_OK; }
 int mc_comm_connect_local(mc_ctx *const *, int) { return MC_OK; }

@@ -434,6 +434,65 @@ def test_accumulate_step_vs_unfused_and_oracle(ctx, oracle, dtype, hi, k, n):
     assert r.scan.as_tuple() == (0, 0, -1, -1.0) and r.nearest_row == -1 and r.n_members == 1 and rows.size == 0
 
 
+@pytest.mark.parametrize("dtype,hi,k,n,sim,bin_size,spread", [
+    (np.uint8, 255, 4, 6000, 0.97, 1000, 40),     # every window covers all bins (the C2 situation)
+    (np.uint8, 255, 3, 5000, 0.90, 100, 400),     # many bins, windows that end inside bins, bins that run empty
+    (np.uint8, 255, 5, 3000, 0.80, 50, 900),      # very ragged lengths, 60 bins
+    (np.uint8, 200, 6, 1200, 0.90, 64, 300),      # 8-row tiles (4 KB rows)
+    (np.uint16, 3000, 4, 2500, 0.85, 70, 500),    # 16-bit bins
+    (np.uint8, 255, 2, 3000, 0.90, 200, 60),      # 16-byte rows, many equal lengths
+    (np.uint8, 255, 3, 37, 0.90, 8, 30),          # fewer rows than SMs
+])
+def test_accumulate_run_vs_step_loop(ctx, dtype, hi, k, n, sim, bin_size, spread):
+    """mc_accumulate_run (the whole accumulate() loop of ClusterFactory.cpp:637-729 with the bvec on the
+    device, one persistent kernel) against the same loop driven from the host: a literal restatement
+    of bvec.cpp (tests/_pybvec.py) + one mc_accumulate_step per scan.  Clusters, centers, member order,
+    scan and evaluation counts must be identical."""
+    import _pybvec
+    rng = np.random.default_rng(900 + k + n)
+    nb = 4 ** k
+    H0 = _rand_hists(rng, n, nb, dtype, hi, clusters=max(3, n // 150))
+    lens0 = (1000 + rng.integers(0, spread, n)).astype(np.uint64)
+    lens0[rng.integers(0, n, n // 10)] = 1000 + spread // 2      # runs of equal lengths
+    bounds, order, first = _pybvec.layout(lens0, bin_size)
+    H, lens = np.ascontiguousarray(H0[order]), np.ascontiguousarray(lens0[order])
+    mins, maxs, w = _model(3)
+    maxs[0] = float(spread)
+    maxs[2] = 4.0 * nb * (hi / 255.0)
+    ctx.load_histograms(H, lens, k)
+    ctx.set_model(mins, maxs, w, 3)
+    # bias: a scan marks roughly the rows of the center's own template
+    sums = ctx.pair_classify(np.arange(n, dtype=np.int32), np.zeros(n, np.int32))[0]
+    w = w.copy()
+    w[0] -= np.sort(sums)[int(n * (1 - 1.5 / max(3, n // 150)))]
+    ctx.set_model(mins, maxs, w, 3)
+    ctx.near_threshold_count(reset=True)
+    want = _pybvec.accumulate_by_steps(ctx, sim, bounds, first, lens)
+    near_steps = ctx.near_threshold_count(reset=True)
+    centers, offs, members, st = ctx.accumulate_run(sim, bounds, first)
+    assert np.array_equal(np.sort(members), np.arange(n)), "every row belongs to exactly one cluster"
+    assert np.array_equal(centers, want[0])
+    assert np.array_equal(offs, want[1])
+    assert np.array_equal(members, want[2])
+    assert (st.n_scans, st.n_evals, st.n_steps) == want[3]
+    assert st.n_near_threshold == near_steps == ctx.near_threshold_count()
+    assert st.n_clusters == centers.size >= 2
+    assert (np.diff(offs) > 1).sum() >= 2, "the test model never marks anything: no mean was exercised"
+
+
+def test_accumulate_run_rejects_unsorted_bins(ctx):
+    rng = np.random.default_rng(5)
+    n, k = 500, 3
+    H = _rand_hists(rng, n, 4 ** k)
+    lens = np.sort((1000 + rng.integers(0, 50, n)).astype(np.uint64))
+    lens[[10, 11]] = lens[[11, 10]] + np.array([5, 0], np.uint64)      # row 10 longer than row 11, same bin
+    ctx.load_histograms(H, lens, k)
+    ctx.set_model(*_model(3), 3)
+    with pytest.raises(Exception) as e:
+        ctx.accumulate_run(0.9, np.array([1000], np.uint64), np.array([0, n], np.int64))
+    assert "non-decreasing" in str(e.value)
+
+
 @pytest.mark.parametrize("world,k,n", [(2, 4, 5000), (3, 3, 4001), (4, 5, 3000)])
 def test_sharded_scan_equals_single(ctx, world, k, n):
     """`world` ranks (here: contexts on one GPU, wired like ranks of one process) each scan

@@ -18,16 +18,27 @@ MOCK_BIN = os.path.join(ROOT, "tests", "_build", "meshclust_hostlogic")
 
 @pytest.fixture(scope="session")
 def mock_cli():
+    """Always reflects the current sources: the rebuild is keyed on a hash of their contents and of the
+    flags (not on mtimes, which say nothing after a fresh clone)."""
+    import hashlib
     srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")]
     srcs += [os.path.join(ROOT, "tests", "mock", "mock_capi.cpp")]
-    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")] + [os.path.join(ROOT, "oracle", "mc_oracle.c")]
-    if (not os.path.exists(MOCK_BIN)) or any(os.path.getmtime(d) > os.path.getmtime(MOCK_BIN) for d in deps):
+    deps = srcs + [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".hpp")]
+    deps += [os.path.join(ROOT, "oracle", "mc_oracle.c"), os.path.join(ROOT, "oracle", "mc_oracle.h"), os.path.join(ROOT, "include", "meshclust_b200.h")]
+    cflags = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-std=c11", "-fopenmp"]
+    cxxflags = ["-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-Wno-sign-compare"]
+    h = hashlib.sha1(" ".join(cflags + cxxflags).encode())
+    for d in deps:
+        h.update(d.encode())
+        h.update(open(d, "rb").read())
+    stamp_file = MOCK_BIN + ".stamp"
+    if not (os.path.exists(MOCK_BIN) and os.path.exists(stamp_file) and open(stamp_file).read() == h.hexdigest()):
         os.makedirs(os.path.dirname(MOCK_BIN), exist_ok=True)
         obj = os.path.join(os.path.dirname(MOCK_BIN), "mc_oracle.o")
-        subprocess.check_call(["/usr/bin/gcc", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-std=c11", "-fopenmp", "-c",
-                               os.path.join(ROOT, "oracle", "mc_oracle.c"), "-o", obj])
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-Wno-sign-compare",
-                               "-I", os.path.join(ROOT, "include"), *srcs, obj, "-o", MOCK_BIN, "-lm"])
+        subprocess.check_call(["/usr/bin/gcc", *cflags, "-c", os.path.join(ROOT, "oracle", "mc_oracle.c"), "-o", obj])
+        subprocess.check_call(["/usr/bin/g++", *cxxflags, "-I", os.path.join(ROOT, "include"), *srcs, obj, "-o", MOCK_BIN, "-lm"])
+        with open(stamp_file, "w") as f:
+            f.write(h.hexdigest())
     return MOCK_BIN
 
 
@@ -40,9 +51,18 @@ def _run(binary, name, tmp_path, extra=(), env=None):
     return open(out, "rb").read(), r.stdout
 
 
-@pytest.mark.parametrize("name", list(H.CASES))
+@pytest.mark.parametrize("name", H.CPU_CASES)
 def test_clstr_identical_to_reference_cpu(mock_cli, tmp_path, name):
     got, _ = _run(mock_cli, name, tmp_path)
+    assert got == H.read_golden(name)
+
+
+@pytest.mark.parametrize("name", ["A", "B", "D", "F", "I", "N", "O", "P"])
+def test_clstr_identical_with_host_driven_phase_a_cpu(mock_cli, tmp_path, name):
+    # MC_PHASE_A_STEPS=1: accumulate() driven from the host (host/bvec.hpp + one mc_accumulate_step per
+    # scan) instead of mc_accumulate_run -- the path --align and unsupported histogram shapes take
+    got, log = _run(mock_cli, name, tmp_path, env={"MC_PHASE_A_STEPS": "1"})
+    assert "row compactions" in log
     assert got == H.read_golden(name)
 
 
@@ -50,7 +70,7 @@ def test_clstr_identical_to_reference_cpu(mock_cli, tmp_path, name):
 def test_clstr_identical_with_row_compaction_cpu(mock_cli, tmp_path, name):
     # rows that have joined a cluster are moved behind the alive ones as Phase A proceeds (here: from
     # 16 rows on, i.e. many times per run); the CLSTR file must not change
-    got, log = _run(mock_cli, name, tmp_path, env={"MC_COMPACT_MIN_ROWS": "16"})
+    got, log = _run(mock_cli, name, tmp_path, env={"MC_COMPACT_MIN_ROWS": "16", "MC_PHASE_A_STEPS": "1"})
     assert " 0 row compactions" not in log and "row compactions" in log
     assert got == H.read_golden(name)
 
@@ -78,13 +98,23 @@ def test_clstr_identical_to_reference_gpu(built_lib, tmp_path, name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["A", "B", "D", "F", "I", "K", "N", "O", "P", "Q", "c1_full"])
+def test_clstr_identical_with_host_driven_phase_a_gpu(built_lib, tmp_path, name):
+    from meshclust_b200 import build
+    cli = build.build_cli()
+    got, log = _run(cli, name, tmp_path, env={"MC_PHASE_A_STEPS": "1"})
+    assert "row compactions" in log
+    assert got == H.read_golden(name), log[-1500:]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,gpus", [("B", 2), ("c1_full", 3), ("F", 2)])
 def test_clstr_identical_with_sharded_phase_a(built_lib, tmp_path, name, gpus):
     # --gpus N shares the Phase-A scans between N contexts (on a 1-GPU box they share the device):
     # the CLSTR file must not change
     from meshclust_b200 import build
     cli = build.build_cli()
-    got, log = _run(cli, name, tmp_path, extra=("--gpus", str(gpus)))
+    got, log = _run(cli, name, tmp_path, extra=("--gpus", str(gpus)), env={"MC_PHASE_A_STEPS": "1"})
     assert "peer inboxes connected" in log
     assert got == H.read_golden(name), log[-1500:]
 
@@ -94,6 +124,6 @@ def test_clstr_identical_with_sharded_phase_a(built_lib, tmp_path, name, gpus):
 def test_clstr_identical_with_row_compaction_gpu(built_lib, tmp_path, name, gpus):
     from meshclust_b200 import build
     cli = build.build_cli()
-    got, log = _run(cli, name, tmp_path, extra=("--gpus", str(gpus)), env={"MC_COMPACT_MIN_ROWS": "16"})
+    got, log = _run(cli, name, tmp_path, extra=("--gpus", str(gpus)), env={"MC_COMPACT_MIN_ROWS": "16", "MC_PHASE_A_STEPS": "1"})
     assert " 0 row compactions" not in log and "row compactions" in log
     assert got == H.read_golden(name), log[-1500:]
