@@ -17,12 +17,13 @@
 //   scan      the TMA-staged streaming scan of scan_tma.cu (one producer warp feeding per-consumer
 //             rings with cp.async.bulk, VABSDIFF4 / DP4A reductions, FP64 feature + GLM epilogue on all
 //             lanes); a CTA owns a contiguous run of tiles, so the rows it marks are ordered.  Marked rows
-//             leave the bitmap (one atomic per tile) and are added to per-CTA bin sums in shared memory.
+//             are added to per-CTA bin sums in shared memory; the bitmap is READ-ONLY during control and
+//             scan (a fast CTA may be scanning while a slow one still derives the range of the same step).
 //   barrier 1 (after the CTA partials and the bin sums have been flushed)
 //   fold      every CTA folds all partials.  No positives: the cluster is closed, the arg-max (or the
 //             first alive row) becomes the next seed -- no second barrier.
-//   tail      positives: every CTA writes its marked rows into the cluster's member list at the offset
-//             its predecessors' counts give, derives the truncated mean from the global bin sums and
+//   tail      positives: every CTA clears the bits of its marked rows, writes them into the cluster's member
+//             list at the offset its predecessors' counts give, derives the truncated mean from the global bin sums and
 //             evaluates distance_d for its own new members and its share of the older ones
 //   barrier 2, fold of the nearest-member partials -> the new center.
 // HBM traffic per step = the scan's algorithmic bytes; everything else is a few KB out of L2.
@@ -367,7 +368,8 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		const long long r = pop_row();
 		if (lane == 0) s_seed = r;
 	}
-	__syncthreads();
+	// every CTA must have read the bitmap before any CTA clears the popped row's bit
+	if (!pa_grid_barrier(A.bar, ++epoch * (unsigned long long)G)) return;
 	center = s_seed;
 	if (center >= 0) {
 		kill_row(center);
@@ -529,9 +531,9 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				const unsigned mask = __ballot_sync(MC_FULL_MASK, flag != 0);
 				if (lane == 0) s_marks[jj] = mask;
 				if (mask) {
-					// bvec::remove_available (bvec.cpp:290-317): the rows leave the bvec ...
-					if (lane == 0) atomicAnd(A.alive_bits + word, ~(mask << shift));
-					// ... and join `current`: their histograms go into this CTA's bin sums
+					// bvec::remove_available (bvec.cpp:290-317): the rows leave the bvec -- their bits are
+					// cleared in the tail, behind barrier 1: a slower CTA may still be reading the bitmap for
+					// the range of THIS step -- and join `current`: their histograms go into this CTA's bin sums
 					for (unsigned mm = mask; mm; mm &= mm - 1) {
 						const long long mrow = tile * T::RT + (__ffs(mm) - 1);
 						const uint32_t *src = reinterpret_cast<const uint32_t *>(A.hist + (size_t)mrow * RB);
@@ -627,6 +629,9 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				if (r < 0) r = pop_row();
 				if (lane == 0) s_seed = r;
 			}
+			// a popped row is found in the bitmap: every CTA must have looked before any CTA clears its bit
+			// (uniform: all CTAs see the same summary)
+			if (tot.best_row < 0 && !pa_grid_barrier(A.bar, ++epoch * (unsigned long long)G)) return;
 			if (cta == 0) {
 				if (threadIdx.x == 0) {
 					A.cl_center[cluster] = (int)center;
@@ -705,6 +710,10 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		for (int i = wib; i < qc; i += PA_WARPS) {
 			const unsigned mask = s_marks[i];
 			if (!mask) continue;
+			if (lane == 0) {   // the rows leave the bvec (visible to every CTA behind barrier 2)
+				const long long trow = (cbeg + i) * T::RT;
+				atomicAnd(A.alive_bits + (trow >> 5), ~(mask << (int)(trow & 31)));
+			}
 			long long pos = m0 + s_base + s_mpref[i];
 			for (unsigned mm = mask; mm; mm &= mm - 1, pos++) {
 				const long long row = (cbeg + i) * T::RT + (__ffs(mm) - 1);
