@@ -723,6 +723,27 @@ def test_alignment_golden(ctx, golden):
     assert np.array_equal(mt, golden["al_matches"])
 
 
+def test_alignment_long_pairs_golden(ctx):
+    """BASELINE configs[4] lengths: 30 pairs of 9.5 - 10.5 kb (79+ strips of 128 rows, scratch lines
+    double-buffered across strips), unequal lengths, 'N' bytes, unrelated pairs, both argument orders,
+    and one 32.7 kb x 32.8 kb pair just under the limit of the packed (length, matches) word -- against
+    triples computed by the compiled reference (tests/golden/make_golden_long.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_align_long.npz"))
+    digits, offs = g["digits"], g["offs"]
+    n = offs.size - 1
+    assert (np.diff(offs) >= 9000).all() and g["pa"].size >= 20
+    ctx.load_sequences(digits, offs, np.zeros(0, np.int32), np.zeros(n + 1, np.int64))
+    sc, ln, mt = ctx.align_pairs(g["pa"], g["pb"])
+    assert np.array_equal(sc, g["score"])
+    assert np.array_equal(ln, g["alen"])
+    assert np.array_equal(mt, g["matches"])
+    # the same pairs one at a time and in reverse batch order: batching must not matter
+    order = np.arange(g["pa"].size)[::-1]
+    sc2, ln2, mt2 = ctx.align_pairs(g["pa"][order], g["pb"][order])
+    assert np.array_equal(sc2, g["score"][order]) and np.array_equal(ln2, g["alen"][order]) and np.array_equal(mt2, g["matches"][order])
+
+
 @pytest.mark.parametrize("cfg,n,npairs", [("c3", 400, 3000), ("c1", 300, 1200), ("c2", 120, 300)])
 def test_alignment_vs_oracle_configs(ctx, oracle, cfg, n, npairs):
     import _oracle

@@ -104,3 +104,13 @@ def test_scan_golden(oracle, golden, nfeat):
     near = np.abs(golden[f"sc_sum{nfeat}"]) < 1e-9
     assert np.array_equal(fl[~near], golden[f"sc_flag{nfeat}"][~near])
     assert 0 < fl.sum() < fl.size
+
+
+def test_alignment_long_pairs_golden(oracle):
+    """The C restatement of GlobAlignE against reference triples at BASELINE configs[4] lengths
+    (tests/golden/ref_align_long.npz; three 10 kb pairs here, the GPU test checks all of them)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_align_long.npz"))
+    sel = np.array([0, 2, 20])      # unequal lengths, an 'N' byte, an unrelated pair
+    sc, ln, mt = oracle.globalign_batch(g["digits"], g["offs"], g["pa"][sel], g["pb"][sel])
+    assert np.array_equal(sc, g["score"][sel]) and np.array_equal(ln, g["alen"][sel]) and np.array_equal(mt, g["matches"][sel])
