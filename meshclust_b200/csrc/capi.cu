@@ -397,6 +397,8 @@ extern "C" int mc_set_model(mc_ctx *ctx, const double *mins, const double *maxs,
 		ctx->model.maxs[i] = i < nlookup ? maxs[i] : 1.0;
 	}
 	for (int i = 0; i < 5; i++) ctx->model.w[i] = i <= nfeat ? weights[i] : 0.0;
+	ctx->model.filt[0] = std::fabs(ctx->model.w[3] / (ctx->model.maxs[3] - ctx->model.mins[3]));
+	ctx->model.filt[1] = nfeat >= 4 ? std::fabs(ctx->model.w[4] / (ctx->model.maxs[4] - ctx->model.mins[4])) : 0.0;
 	// division-free normalisation: allowed per feature only when q + (a - b*q)*RN(1/b) reproduces
 	// a / b bit for bit on a dense probe of the feature's value range (and on every special value)
 	ctx->model.fast_div = 0;
@@ -802,12 +804,15 @@ extern "C" int mc_accumulate_step(mc_ctx *ctx, int64_t center_row, int64_t lo, i
 // Phase A as one persistent kernel (phase_a.cu)
 // ---------------------------------------------------------------------------------------------
 int mc_pa_rows_per_tile(int tbytes, int nbins);
-size_t mc_pa_partial_bytes();
+size_t mc_pa_exchange_bytes(int grid);
+int mc_pa_max_grid();
+int mc_pa_trace_slots();
+size_t mc_pa_gsum_bytes(int nbins);
 size_t mc_pa_range_bytes();
 bool mc_pa_shape_supported(int tbytes, int nbins);
 int mc_launch_pa_prepare(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, double sim, void *range_tab_dev, unsigned int *err_dev);
 int mc_launch_phase_a(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, const void *range_tab_dev,
-                      uint32_t *alive_bits_dev, unsigned long long *g_sum_dev, void *partials_dev, void *near_dev,
+                      uint32_t *alive_bits_dev, unsigned long long *g_sum_dev, void *exch_dev,
                       unsigned long long *bar_dev, int *members_dev, int *cl_center_dev, int *cl_off_dev, long long *stats_dev,
                       unsigned long long *trace_dev, int trace_steps, int grid, int qmax);
 
@@ -833,31 +838,31 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 	for (int i = 1; i < nb; i++) MC_REQUIRE(bin_bounds[i] >= bin_bounds[i - 1], MC_ERR_ARG, "mc_accumulate_run: bin_bounds is not sorted");
 	const int rt = mc_pa_rows_per_tile(ctx->tbytes, ctx->nbins);
 	const int64_t total_tiles = (n + rt - 1) / rt;
-	int grid = (int)std::min<int64_t>(ctx->num_sms, std::max<int64_t>(1, total_tiles));
+	int grid = (int)std::min<int64_t>(std::min(ctx->num_sms, mc_pa_max_grid()), std::max<int64_t>(1, total_tiles));
 	if (getenv("MC_PA_GRID")) grid = std::max(1, std::min(grid, atoi(getenv("MC_PA_GRID"))));
 	const int qmax = (int)((total_tiles + grid - 1) / grid) + 2;
 	const int trace_steps = getenv("MC_PA_TRACE") ? atoi(getenv("MC_PA_TRACE")) : 0;
 	const size_t words = (size_t)((n + 31) / 32) + 64;
 	const size_t NB = (size_t)ctx->nbins;
-	int rc = mc_ensure_scratch(ctx, Carve::need({(size_t)nb * 8, (size_t)(nb + 1) * 4, (size_t)n * mc_pa_range_bytes(), words * 4, 3 * NB * 8,
-	                                             2 * (size_t)grid * mc_pa_partial_bytes(), 2 * (size_t)grid * mc_pa_partial_bytes(), 64,
-	                                             (size_t)n * 4, (size_t)n * 4, (size_t)(n + 1) * 4, 64, 64, (size_t)trace_steps * 64 + 64}));
+	int rc = mc_ensure_scratch(ctx, Carve::need({(size_t)nb * 8, (size_t)(nb + 1) * 4, (size_t)n * mc_pa_range_bytes(), words * 4, mc_pa_gsum_bytes((int)NB),
+	                                             mc_pa_exchange_bytes(grid), 64,
+	                                             (size_t)n * 4, (size_t)n * 4, (size_t)(n + 1) * 4, 64, 64, (size_t)trace_steps * mc_pa_trace_slots() * 8 + 64}));
 	if (rc) return rc;
 	Carve cv(ctx->d_scratch);
 	unsigned long long *d_bounds = cv.take<unsigned long long>((size_t)nb);
 	int *d_row0 = cv.take<int>((size_t)nb + 1);
 	uint8_t *d_range = cv.take<uint8_t>((size_t)n * mc_pa_range_bytes());
 	uint32_t *d_bits = cv.take<uint32_t>(words);
-	unsigned long long *d_gsum = cv.take<unsigned long long>(3 * NB);
-	uint8_t *d_partials = cv.take<uint8_t>(2 * (size_t)grid * mc_pa_partial_bytes());
-	uint8_t *d_near = cv.take<uint8_t>(2 * (size_t)grid * mc_pa_partial_bytes());
+	unsigned long long *d_gsum = cv.take<unsigned long long>(mc_pa_gsum_bytes((int)NB) / 8);
+	uint8_t *d_exch = cv.take<uint8_t>(mc_pa_exchange_bytes(grid));
 	unsigned long long *d_bar = cv.take<unsigned long long>(8);
 	int *d_members = cv.take<int>((size_t)n);
 	int *d_center = cv.take<int>((size_t)n);
 	int *d_off = cv.take<int>((size_t)n + 1);
 	long long *d_stats = cv.take<long long>(8);
 	unsigned int *d_err = cv.take<unsigned int>(16);
-	unsigned long long *d_trace = cv.take<unsigned long long>((size_t)trace_steps * 8 + 8);
+	const size_t TS = (size_t)mc_pa_trace_slots();
+	unsigned long long *d_trace = cv.take<unsigned long long>((size_t)trace_steps * TS + 8);
 	MC_CUDA(cudaMemcpyAsync(d_bounds, bin_bounds, (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(d_row0, row0.data(), (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
 	// a fresh bvec: every row alive, the bits past the last row clear
@@ -865,18 +870,20 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 	MC_CUDA(cudaMemsetAsync(d_bits, 0xff, (size_t)(n / 32) * 4, ctx->stream));
 	const uint32_t tail_word = (n % 32) ? ((1u << (n % 32)) - 1u) : 0u;
 	if (n % 32) MC_CUDA(cudaMemcpyAsync(d_bits + n / 32, &tail_word, 4, cudaMemcpyHostToDevice, ctx->stream));
-	MC_CUDA(cudaMemsetAsync(d_gsum, 0, 3 * NB * 8, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_gsum, 0, mc_pa_gsum_bytes((int)NB), ctx->stream));
 	MC_CUDA(cudaMemsetAsync(d_bar, 0, 64, ctx->stream));
 	MC_CUDA(cudaMemsetAsync(d_stats, 0, 64, ctx->stream));
 	MC_CUDA(cudaMemsetAsync(d_err, 0, 64, ctx->stream));
-	if (trace_steps) MC_CUDA(cudaMemsetAsync(d_trace, 0, (size_t)trace_steps * 64, ctx->stream));
+	// tagged records: tag 0 = never written
+	MC_CUDA(cudaMemsetAsync(d_exch, 0, mc_pa_exchange_bytes(grid), ctx->stream));
+	if (trace_steps) MC_CUDA(cudaMemsetAsync(d_trace, 0, (size_t)trace_steps * TS * 8, ctx->stream));
 	rc = mc_launch_pa_prepare(ctx, d_bounds, d_row0, nb, similarity, d_range, d_err);
 	if (rc) return rc;
 	unsigned int h_err = 0;
 	MC_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	MC_REQUIRE(h_err == 0, MC_ERR_ARG, "mc_accumulate_run: the rows of a bvec bin are not in non-decreasing length order");
-	rc = mc_launch_phase_a(ctx, d_bounds, d_row0, nb, d_range, d_bits, d_gsum, d_partials, d_near, d_bar, d_members, d_center, d_off,
+	rc = mc_launch_phase_a(ctx, d_bounds, d_row0, nb, d_range, d_bits, d_gsum, d_exch, d_bar, d_members, d_center, d_off,
 	                       d_stats, trace_steps ? d_trace : nullptr, trace_steps, grid, qmax);
 	if (rc) return rc;
 	long long h_stats[8];
@@ -913,22 +920,35 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 		stats->device_seconds = (double)h_stats[5] * 1e-9;
 	}
 	if (trace_steps) {
-		std::vector<unsigned long long> tr((size_t)trace_steps * 8);
+		std::vector<unsigned long long> tr((size_t)trace_steps * TS);
 		MC_CUDA(cudaMemcpy(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
-		// per phase: control, scan, barrier 1, fold, tail, barrier 2, rest (averages over the traced steps, in us)
-		double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-		long cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+		// CTA 0, averages over the traced steps in us: range of the window, scan, exchange of the summaries
+		// (incl. waiting for the slowest CTA), tail, exchange of the candidates, rest
+		double acc[32] = {0};
+		long cnt[32] = {0};
 		const long steps = (long)std::min<long long>(trace_steps, h_stats[4]);
 		for (long s = 0; s < steps; s++) {
-			const unsigned long long *t = tr.data() + (size_t)s * 8;
+			const unsigned long long *t = tr.data() + (size_t)s * TS;
 			auto add = [&](int k, unsigned long long a, unsigned long long b) { if (a && b && b >= a) { acc[k] += (double)(b - a) * 1e-3; cnt[k]++; } };
-			add(0, t[0], t[1]); add(1, t[1], t[2]); add(2, t[2], t[3]); add(3, t[3], t[4]);
-			if (t[5]) { add(4, t[4], t[5]); add(5, t[5], t[6]); add(6, t[6], t[7]); }
-			else add(6, t[4], t[7]);
+			add(0, t[0], t[1]); add(1, t[1], t[2]); add(2, t[2], t[3]);
+			if (t[5]) { add(3, t[3], t[5]); add(4, t[5], t[6]); add(5, t[6], t[7]); }
+			else add(6, t[3], t[7]);
+			acc[7] += (double)(long long)t[8] * 1e-3; cnt[7]++;
+			acc[8] += (double)(long long)t[9] * 1e-3; cnt[8]++;
+			add(10, t[0], t[10]); add(11, t[10], t[11]); add(12, t[4], t[12]); add(13, t[12], t[13]);
+			add(14, t[2], t[14]); add(15, t[14], t[4]); add(21, t[1], t[21]); add(22, t[21], t[14]);
+			add(23, t[1], t[22]); add(24, t[22], t[23]); add(25, t[23], t[24]); add(26, t[24], t[25]);
+			add(16, t[3], t[16]); add(17, t[16], t[17]); add(18, t[17], t[18]); add(19, t[18], t[19]); add(20, t[19], t[5]);
 		}
-		fprintf(stderr, "[mc_accumulate_run trace, %ld steps, us] control %.2f  scan %.2f  barrier1 %.2f  fold %.2f | tail %.2f (x%ld)  barrier2 %.2f  close %.2f\n",
-		        steps, acc[0] / std::max(1L, cnt[0]), acc[1] / std::max(1L, cnt[1]), acc[2] / std::max(1L, cnt[2]), acc[3] / std::max(1L, cnt[3]),
-		        acc[4] / std::max(1L, cnt[4]), cnt[4], acc[5] / std::max(1L, cnt[5]), acc[6] / std::max(1L, cnt[6]));
+		auto av = [&](int k) { return acc[k] / (double)std::max(1L, cnt[k]); };
+		fprintf(stderr, "[mc_accumulate_run trace, %ld steps, us] range %.2f  scan %.2f  exchange1 %.2f (last CTA starts its scan %.2f and ends it %.2f after CTA 0) | "
+		        "tail %.2f (x%ld)  exchange2 %.2f  rest %.2f | close %.2f (x%ld)\n",
+		        steps, av(0), av(1), av(2), av(7), av(8), av(3), cnt[3], av(4), av(5), av(6), cnt[6]);
+		fprintf(stderr, "[mc_accumulate_run trace, detail] range: search record loaded %.2f, position located +%.2f | exchange1: bin sums flushed %.2f, fold + fence +%.2f, "
+		        "record stored +%.2f, all records folded +%.2f (last consumer warp done %.2f after the range, sums flushed +%.2f) | tail: mean %.2f, distances +%.2f, block barrier +%.2f, fold + fence +%.2f, record stored +%.2f\n",
+		        av(10), av(11), av(14), av(15), av(12), av(13), av(21), av(22), av(16), av(17), av(18), av(19), av(20));
+		fprintf(stderr, "[mc_accumulate_run trace, consumer warp 0] center in registers %.2f after the range, first tile landed +%.2f, reduced + decided +%.2f, rest of its tiles +%.2f\n",
+		        av(23), av(24), av(25), av(26));
 	}
 	return MC_OK;
 }

@@ -62,6 +62,7 @@ struct McModel {
 	double maxs[5];
 	double w[5];   // w[0] bias, w[1..nfeat]
 	double rcp[5]; // correctly rounded 1 / (maxs - mins), for the division-free normalisation
+	double filt[2]; // |w[3] * rcp[3]| and |w[4] * rcp[4]|: how far an error of PEARSON / KULCZYNSKI2 moves the GLM sum (mc_scan_decide)
 	int fast_div;  // bit j set: (x - mins[j]) / (maxs[j] - mins[j]) may use rcp[j] (validated on the host)
 	int nfeat;     // 3 or 4
 	int valid;
@@ -359,6 +360,82 @@ __device__ __forceinline__ void mc_scan_epilogue(const McModel &m, uint64_t S64,
 	sum = fma(m.w[2], f1, sum);
 	sum = fma(m.w[3], 1.0 * v[3], sum);
 	if (m.nfeat >= 4) sum = fma(m.w[4], (1.0 * (v[0] * v[0])) * (v[4] * v[4]), sum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The decision of a scan without most of its FP64 work.  B200 issues FP64 at a fraction of the FP32
+// rate, and a scan of short rows (k <= 4) is bound by this epilogue, not by HBM.  What the caller
+// needs per row is f0 (bit-exact: it is the arg-max key), the DECISION sum > threshold, and whether the
+// sum lies within MC_NEAR_THRESHOLD of it.  f0 and the MANHATTAN term are cheap (one true division).
+// The expensive terms are PEARSON (integer -> double conversions, a square root and a division) and,
+// for 4-feature models, KULCZYNSKI2 (two more divisions).  They enter the sum linearly through
+// w3 * (1 - (c3 - min3) / range3) and w4 * (v0 * q4)^2, so an approximation of c3 / c4 with a known
+// error bound gives an interval for the sum; when the interval does not contain the threshold
+// (and stays 1e-9 away from it) the decision is the one the exact arithmetic would take, and the
+// exact terms are never computed.  Only rows whose sum is within ~1e-4 of the threshold run the full
+// epilogue (bit-identical to mc_scan_epilogue).
+//   c3 = dot / sqrt(prod) in FP32: three conversions, two products and MUFU.RSQ (2 ulp): relative
+//   error < 2^-21; |c3| <= 1 (Cauchy-Schwarz on the exact integer moments), so |c3 - c3f| < 2^-21.
+//   The bound used is 2^-18 (8x slack); c4 likewise (relative 2^-18 of |c4|).
+// flags: bit 0 = similar, bit 1 = within MC_NEAR_THRESHOLD of the threshold.
+// ---------------------------------------------------------------------------------------------
+template <int TB>
+__device__ __forceinline__ unsigned mc_scan_decide(const McModel &m, uint64_t S64, uint64_t D64, uint64_t lp,
+                                                   uint64_t mp64, uint64_t sp64, uint64_t lq, uint64_t mq64,
+                                                   uint64_t sq64, int N, double invN, double &f0) {
+	if constexpr (TB != 1) {
+		double sum;
+		mc_scan_epilogue<TB>(m, S64, D64, lp, mp64, sp64, lq, mq64, sq64, N, invN, f0, sum);
+		return (MC_IS_SIMILAR(sum) ? 1u : 0u) | (fabs(sum) < MC_NEAR_THRESHOLD ? 2u : 0u);
+	} else {
+		const uint32_t S = (uint32_t)S64, mp = (uint32_t)mp64, mq = (uint32_t)mq64;
+		auto norm = [&](int j, double c) {
+			const double num = c - m.mins[j], den = m.maxs[j] - m.mins[j];
+			return ((m.fast_div >> j) & 1) ? mc_div_const(num, den, m.rcp[j]) : num / den;
+		};
+		const double c0 = (double)(lp > lq ? lp - lq : lq - lp);
+		const double c1 = (double)(2u * S) / (double)(mp + mq);
+		const double c2 = (double)(int)(mp + mq - 2u * S);
+		const double v0 = 1 - norm(0, c0), v1 = norm(1, c1), v2 = 1 - norm(2, c2);
+		const double v00 = v0 * v0;
+		const double f1 = v00 * (v2 * v2);
+		f0 = v0 * v1;
+		const double P = fma(m.w[2], f1, fma(m.w[1], f0, m.w[0]));
+		// the exact integer moments of PEARSON (Feature.cpp:274-294)
+		const double dap = (double)mp * invN, daq = (double)mq * invN;
+		const int ap = (int)round(dap), aq = (int)round(daq);
+		const int np = (int)(uint32_t)sp64 - 2 * ap * (int)mp + N * ap * ap;
+		const int nq = (int)(uint32_t)sq64 - 2 * aq * (int)mq + N * aq * aq;
+		const int dot = (int)(uint32_t)D64 - aq * (int)mp - ap * (int)mq + N * ap * aq;
+		{
+			const float prodf = fmaxf((float)np * (float)nq, 0.5f);
+			const float c3f = (float)dot * rsqrtf(prodf);
+			const double q3 = ((double)c3f - m.mins[3]) * m.rcp[3];
+			double ra = m.w[3] * (1.0 - q3);
+			double tol = m.filt[0] * 0x1p-18;
+			if (m.nfeat >= 4) {
+				const float dapf = (float)dap, daqf = (float)daq;
+				const float c4f = ((float)N * (dapf + daqf) / (2.0f * dapf * daqf)) * (float)S;
+				const double q4 = ((double)c4f - m.mins[4]) * m.rcp[4];
+				const double e4 = m.filt[1] * fabs((double)c4f) * 0x1p-18;   // |w4| x the error of q4
+				ra = fma(m.w[4], v00 * (q4 * q4), ra);
+				tol += v00 * e4 * (2.0 * fabs(q4) + 1.0);
+			}
+			const double sa = P + ra;
+			tol += MC_NEAR_THRESHOLD + 1e-12 * (fabs(P) + fabs(ra));
+			if (fabs(sa) > tol) return sa > 0.0 ? 1u : 0u;   // false for NaN: falls through to the exact path
+		}
+		const double prod = (double)((long long)np * (long long)nq);
+		const double c3 = (double)dot / sqrt(prod > 0.5 ? prod : 0.5);
+		const double v3 = 1 - norm(3, c3);
+		double sum = fma(m.w[3], v3, P);
+		if (m.nfeat >= 4) {
+			const double coeff = N * (dap + daq) / (2 * dap * daq);
+			const double v4 = norm(4, coeff * (double)S);
+			sum = fma(m.w[4], v00 * (v4 * v4), sum);
+		}
+		return (MC_IS_SIMILAR(sum) ? 1u : 0u) | (fabs(sum) < MC_NEAR_THRESHOLD ? 2u : 0u);
+	}
 }
 
 // DivergencePoint::distance (DivergencePoint.cpp:68-81), with the fused 1 - f*f of the compiled

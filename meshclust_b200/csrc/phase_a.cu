@@ -73,15 +73,15 @@ struct PaArgs {
 	int qmax;                           // capacity of the per-CTA tile tables
 	const PaRange *range_tab;           // n
 	uint32_t *alive_bits;               // bit r = row r is still in the bvec
-	unsigned long long *g_sum;          // 3 x bins: running bin sums of `current`, rotating per cluster
-	PaPartial *partials;                // 2 x grid
-	PaNear *near;                       // 2 x grid
-	unsigned long long *bar;            // [0] barrier counter, [1] abort code
+	unsigned long long *g_sum;          // 3 x pa_gsum_words(bins): running bin sums of `current`, rotating per cluster
+	unsigned long long *recs;           // 2 x grid x PA_REC_WORDS: scan summaries of the CTAs as tagged words
+	unsigned long long *near_recs;      // 2 x grid x PA_REC_WORDS: nearest-member candidates of the CTAs
+	unsigned long long *bar;            // [1] abort code
 	int *members;                       // n: the clusters' member rows, cluster after cluster
 	int *cl_center;                     // n
 	int *cl_off;                        // n + 1
 	long long *stats;                   // [0] clusters [1] scans [2] evals [3] near-threshold pairs [4] steps [5] ns
-	unsigned long long *trace;          // optional: 8 timestamps per step of CTA 0
+	unsigned long long *trace;          // optional: PA_TRACE_SLOTS words per step of CTA 0
 	int trace_steps;
 	int ns, ncw, d;                     // ring geometry: stages, consumer warps, stages per consumer
 	McModel model;
@@ -145,7 +145,8 @@ __global__ void pa_prepare_kernel(const McRowAux *__restrict__ aux, long long n,
 
 // ---- alive bitmap helpers (warp-cooperative; every lane gets the result) ------------------------
 // alive rows among the first pa / pb rows of [r0, r1) and in all of it
-__device__ __forceinline__ void pa_rank3(const uint32_t *bits, long long r0, long long r1, long long pa, long long pb,
+// `skip`: a row that has left the bvec although its bit may still be set (the center of the running step)
+__device__ __forceinline__ void pa_rank3(const uint32_t *bits, long long r0, long long r1, long long pa, long long pb, long long skip,
                                          int lane, unsigned &ra, unsigned &rb, unsigned &tot) {
 	unsigned a = 0, b = 0, t = 0;
 	if (r1 > r0) {
@@ -154,6 +155,7 @@ __device__ __forceinline__ void pa_rank3(const uint32_t *bits, long long r0, lon
 			uint32_t v = __ldcg(bits + w);
 			if (w == w0) v &= 0xffffffffu << (r0 & 31);
 			if (w == w1 && (r1 & 31)) v &= 0xffffffffu >> (32 - (int)(r1 & 31));
+			if (w == (skip >> 5)) v &= ~(1u << (int)(skip & 31));
 			auto below = [&](long long lim) {
 				const long long dlt = lim - (w << 5);
 				return dlt <= 0 ? 0u : (dlt >= 32 ? 0xffffffffu : ((1u << (int)dlt) - 1u));
@@ -173,7 +175,7 @@ __device__ __forceinline__ void pa_rank3(const uint32_t *bits, long long r0, lon
 }
 
 // row of the pos-th (0-based) alive row of [r0, r1), or -1
-__device__ __forceinline__ long long pa_select(const uint32_t *bits, long long r0, long long r1, unsigned long long pos, int lane) {
+__device__ __forceinline__ long long pa_select(const uint32_t *bits, long long r0, long long r1, unsigned long long pos, long long skip, int lane) {
 	if (r1 <= r0) return -1;
 	const long long w0 = r0 >> 5, w1 = (r1 - 1) >> 5;
 	unsigned long long seen = 0;
@@ -184,6 +186,7 @@ __device__ __forceinline__ long long pa_select(const uint32_t *bits, long long r
 			v = __ldcg(bits + w);
 			if (w == w0) v &= 0xffffffffu << (r0 & 31);
 			if (w == w1 && (r1 & 31)) v &= 0xffffffffu >> (32 - (int)(r1 & 31));
+			if (w == (skip >> 5)) v &= ~(1u << (int)(skip & 31));
 		}
 		const unsigned pc = __popc(v);
 		unsigned incl = pc;
@@ -225,33 +228,212 @@ __device__ __forceinline__ void pa_inner_search(unsigned long long A, unsigned l
 	if (back >= a_lt && back < a_le) back = a_le - 1;
 }
 
-// ---- grid-wide barrier -------------------------------------------------------------------------
-// Monotonic 64-bit counter: barrier e is passed when the counter reaches e * gridDim.x.  All CTAs are
-// co-resident (cooperative launch).  Returns false when the run has been aborted (time-out).
-__device__ __forceinline__ bool pa_grid_barrier(unsigned long long *bar, unsigned long long target) {
-	__shared__ int s_ok;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ull) : "memory");
-		unsigned long long t0 = 0;
-		int ok = 1;
-		for (unsigned spins = 0;; spins++) {
-			unsigned long long v;
-			asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
-			if (v >= target) break;
-			if ((spins & 0x3ff) == 0x3ff) {
-				unsigned long long t1, ab;
-				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-				asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(ab) : "l"(bar + 1) : "memory");
-				if (ab) { ok = 0; break; }
-				if (t0 == 0) t0 = t1;
-				else if (t1 - t0 > PA_TIMEOUT_NS) { atomicExch(bar + 1, 1ull); ok = 0; break; }
-			}
-		}
-		s_ok = ok;
+// One end of bvec::get_range inside the bin that owns rows [r0, r1): of the bin's entries (alive or not)
+// the first p_lt are shorter than the bound and the first p_le not longer; the in-bin search of the
+// reference runs over the ALIVE entries and ends at a position (front or back flavour) whose row comes
+// back.  Bins of up to 32 * PA_KW words are searched out of registers: one load of the bitmap words,
+// then ranks, search and select without touching memory again.
+constexpr int PA_KW = 4;
+
+// 32-bit flavour of pa_inner_search (bins hold fewer than 2^31 entries)
+__device__ __forceinline__ void pa_inner_search32(unsigned A, unsigned a_lt, unsigned a_le, unsigned &front, unsigned &back) {
+	front = 0; back = 0;
+	unsigned low = 0, high = A - 1;
+	while (low <= high) {
+		const unsigned mid = (low + high) >> 1;   // A < 2^31: no overflow
+		if (mid >= a_lt && mid < a_le) { front = back = mid; break; }
+		else if (mid >= a_le) high = mid;
+		else low = mid + 1;
+		if (low == high) { front = low; back = high; break; }
 	}
-	__syncthreads();
-	return s_ok != 0;
+	if (front >= a_lt && front < a_le) front = a_lt;
+	if (back >= a_lt && back < a_le) back = a_le - 1;
+}
+
+__device__ __forceinline__ void pa_locate(const uint32_t *bits, long long r0l, long long r1l, int p_lt, int p_le, bool want_back,
+                                          long long skipl, int lane, unsigned long long &pos_out, long long &row_out) {
+	const int r0 = (int)r0l, r1 = (int)r1l, skip = (int)skipl;
+	const int w0 = r0 >> 5, w1 = (r1 - 1) >> 5;
+	const int nw = w1 - w0 + 1;
+	if (nw > 32 * PA_KW) {
+		unsigned a_lt, a_le, tot;
+		pa_rank3(bits, r0l, r1l, p_lt, p_le, skipl, lane, a_lt, a_le, tot);
+		unsigned long long f, b;
+		pa_inner_search(tot, a_lt, a_le, f, b);
+		pos_out = want_back ? b : f;
+		row_out = pos_out < tot ? pa_select(bits, r0l, r1l, pos_out, skipl, lane) : -1;
+		return;
+	}
+	uint32_t v[PA_KW];
+	unsigned a = 0, b = 0, t = 0;
+	const int lim_lt = r0 + p_lt, lim_le = r0 + p_le;
+#pragma unroll
+	for (int j = 0; j < PA_KW; j++) {
+		const int w = w0 + j * 32 + lane;
+		uint32_t x = 0;
+		if (w <= w1) {
+			x = __ldcg(bits + w);
+			if (w == w0) x &= 0xffffffffu << (r0 & 31);
+			if (w == w1 && (r1 & 31)) x &= 0xffffffffu >> (32 - (r1 & 31));
+			if (w == (skip >> 5)) x &= ~(1u << (skip & 31));
+		}
+		v[j] = x;
+		auto below = [&](int lim) {   // bits of word w that belong to rows < lim
+			const int dlt = lim - (w << 5);
+			return dlt <= 0 ? 0u : (dlt >= 32 ? 0xffffffffu : ((1u << dlt) - 1u));
+		};
+		a += __popc(x & below(lim_lt));
+		b += __popc(x & below(lim_le));
+		t += __popc(x);
+	}
+	a = __reduce_add_sync(MC_FULL_MASK, a);
+	b = __reduce_add_sync(MC_FULL_MASK, b);
+	t = __reduce_add_sync(MC_FULL_MASK, t);
+	if (t == 0) { pos_out = 0; row_out = -1; return; }
+	unsigned f, bk;
+	pa_inner_search32(t, a, b, f, bk);
+	const unsigned pos = want_back ? bk : f;
+	pos_out = pos;
+	int row = -1;
+	unsigned seen = 0;
+#pragma unroll
+	for (int j = 0; j < PA_KW; j++) {
+		if (j * 32 < nw) {
+			const unsigned pc = __popc(v[j]);
+			unsigned incl = pc;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const unsigned u = __shfl_up_sync(MC_FULL_MASK, incl, o);
+				if (lane >= o) incl += u;
+			}
+			const unsigned tot = __shfl_sync(MC_FULL_MASK, incl, 31);
+			if (row < 0 && pos >= seen && pos < seen + tot) {
+				const unsigned before = seen + incl - pc;
+				const bool mine = before <= pos && pos < before + pc;
+				const int src = __ffs(__ballot_sync(MC_FULL_MASK, mine)) - 1;
+				int r = -1;
+				if (mine) {
+					// the (pos - before)-th set bit of v[j]: drop the lower ones
+					uint32_t x = v[j];
+					for (unsigned k = pos - before; k; k--) x &= x - 1;
+					r = ((w0 + j * 32 + lane) << 5) + (__ffs(x) - 1);
+				}
+				row = __shfl_sync(MC_FULL_MASK, r, src);
+			}
+			seen += tot;
+		}
+	}
+	row_out = row;
+}
+
+// ---- grid-wide exchange: tagged records instead of a barrier -------------------------------------
+// What the CTAs owe each other at the two synchronisation points of a step is one small record each
+// (the scan summary of the CTA; its nearest-member candidate).  A record is PA_REC_WORDS 8-byte words
+// {u32 data, u32 tag}, tag = step + 1: an 8-byte store is single-copy atomic, so a reader that sees
+// the tag of this step in a word also has its data -- no counter, no atomic, one L2 round trip.  Every
+// CTA polls the records of ALL CTAs, so passing the poll is also the barrier: nobody is past it before
+// everybody has arrived.  Writers fence before they store (their bin-sum atomics, member lists and
+// bitmap updates are visible to whoever sees the record), readers fence after the poll.  Records are
+// double-buffered by step parity (a CTA is at most one exchange ahead of the slowest one).
+constexpr int PA_REC_WORDS = 8;   // 64 bytes
+constexpr int PA_RPL = 5;         // records a lane of the reading warp takes: grids of up to 160 CTAs
+
+__device__ __forceinline__ void pa_ll_store(unsigned long long *p, uint32_t data, uint32_t tag) {
+	const unsigned long long v = ((unsigned long long)tag << 32) | (unsigned long long)data;
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// one shot at the NW words of a record (pairs of words per load); true when every word carries `tag`
+template <int NW>
+__device__ __forceinline__ bool pa_rec_try(const unsigned long long *rec, uint32_t tag, uint32_t (&data)[NW]) {
+	static_assert(NW % 2 == 0, "records are read as pairs of words");
+	bool ok = true;
+#pragma unroll
+	for (int i = 0; i < NW; i += 2) {
+		unsigned long long a, b;
+		asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(rec + i) : "memory");
+		ok = ok && (uint32_t)(a >> 32) == tag && (uint32_t)(b >> 32) == tag;
+		data[i] = (uint32_t)a;
+		data[i + 1] = (uint32_t)b;
+	}
+	return ok;
+}
+
+// the record of a CTA that is late: spin on ONE word (every other CTA is spinning on the same line), then
+// read all of it; false = the run was aborted (a peer never wrote: time-out, not a hang)
+template <int NW>
+__device__ __forceinline__ bool pa_rec_wait(const unsigned long long *rec, uint32_t tag, uint32_t (&data)[NW], unsigned long long *abort_word) {
+	unsigned long long t0 = 0;
+	for (unsigned spins = 0;; spins++) {
+		unsigned long long a;
+		asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(rec) : "memory");
+		if ((uint32_t)(a >> 32) == tag && pa_rec_try<NW>(rec, tag, data)) return true;
+		if ((spins & 0xff) == 0xff) {
+			unsigned long long t1, ab;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(ab) : "l"(abort_word) : "memory");
+			if (ab) return false;
+			if (t0 == 0) t0 = t1;
+			else if (t1 - t0 > PA_TIMEOUT_NS) { atomicExch(abort_word, 1ull); return false; }
+		}
+	}
+}
+
+// Release without a fence.  What a CTA publishes before its record are read-modify-write operations on
+// global memory (bin-sum additions, bitmap bits, member rows as exchanges).  An atomic whose RESULT has come
+// back has been performed in L2, the point of coherence of the GPU; the record is stored after every such
+// result has been consumed (pa_retire: a real instruction that needs the value, then a block barrier), so a
+// CTA that sees the record reads the updated words (ld.cg / ld.relaxed.gpu go to L2).  A gpu-scope fence in
+// the same place costs 0.7 us per exchange on B200 (-DPA_RELEASE_BY_FENCE=1 builds that variant).
+#ifndef PA_RELEASE_BY_FENCE
+#define PA_RELEASE_BY_FENCE 0
+#endif
+__device__ __forceinline__ void pa_retire(unsigned long long v, int *sink) {
+#if !PA_RELEASE_BY_FENCE
+	unsigned z;
+	asm volatile("{ .reg .b64 t; and.b64 t, %1, 0; cvt.u32.u64 %0, t; }" : "=r"(z) : "l"(v));
+	if (z) *sink = 1;   // never true; the branch needs the result of the atomic
+#endif
+}
+__device__ __forceinline__ void pa_release_fence() {
+#if PA_RELEASE_BY_FENCE
+	__threadfence();
+#endif
+}
+
+// The running bin sums of `current` are the one thing every CTA adds to at the same time.  2 KB of
+// consecutive 64-bit counters live in FOUR L2 slices (the slice hash ignores most of the low address bits),
+// and ~100 CTAs x 4^k reductions queue up there for microseconds; one 32-byte sector (4 bins) per KB puts
+// every sector into a slice of its own.
+constexpr int PA_GSUM_STRIDE = 128;   // 64-bit words between the sectors of 4 bins
+__host__ __device__ __forceinline__ size_t pa_gsum_idx(int b) { return (size_t)(b >> 2) * PA_GSUM_STRIDE + (size_t)(b & 3); }
+__host__ __device__ __forceinline__ size_t pa_gsum_words(int nbins) { return (size_t)((nbins + 3) / 4) * PA_GSUM_STRIDE; }
+
+// the warp's scan summary with warp-wide reductions: counts are sums; the arg-max is the largest f0 and,
+// among equal f0, the smallest row (mc_scan_merge's rule): f0 as an order-preserving 64-bit key, high word
+// first.  Every lane returns the warp's summary.
+__device__ __forceinline__ void pa_scan_fold_redux(mc_scan_result &v) {
+	v.n_eval = __reduce_add_sync(MC_FULL_MASK, (unsigned)v.n_eval);
+	v.n_pos = __reduce_add_sync(MC_FULL_MASK, (unsigned)v.n_pos);
+	const bool has = v.best_row >= 0;
+	unsigned long long k = (unsigned long long)__double_as_longlong(v.best_f0);
+	if (k == 0x8000000000000000ull) k = 0;              // -0.0 == +0.0 for the comparison the reference makes
+	k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);   // total order of the doubles (no NaN: f0 > best never holds for one)
+	const unsigned hi = has ? (unsigned)(k >> 32) : 0u, lo = (unsigned)k;
+	const unsigned mhi = __reduce_max_sync(MC_FULL_MASK, hi);
+	const bool c1 = has && hi == mhi;
+	const unsigned mlo = __reduce_max_sync(MC_FULL_MASK, c1 ? lo : 0u);
+	const bool c2 = c1 && lo == mlo;
+	const unsigned mrow = __reduce_min_sync(MC_FULL_MASK, c2 ? (unsigned)v.best_row : 0xffffffffu);
+	if (__any_sync(MC_FULL_MASK, has)) {
+		unsigned long long kk = ((unsigned long long)mhi << 32) | mlo;
+		kk = (kk >> 63) ? (kk & 0x7fffffffffffffffull) : ~kk;
+		v.best_f0 = __longlong_as_double((long long)kk);
+		v.best_row = (long long)mrow;
+	} else {
+		v.best_f0 = -1.0;
+		v.best_row = -1;
+	}
 }
 
 // rows per tile: 32 (one row per lane in the epilogue) while the tile fits 32 KB
@@ -263,12 +445,34 @@ struct PaTile {
 	static constexpr int STAGE_BYTES = ((ROW_BYTES + AUX_BYTES + 127) / 128) * 128;
 };
 
+// trace slots of a step (CTA 0): 0 start, 1 range known, 2 scan done, 3 summaries of all CTAs in, 5 tail done,
+// 6 candidates of all CTAs in, 7 end; 8 / 9: how long after CTA 0 the LAST CTA started / finished its scan (ns)
+constexpr int PA_TRACE_SLOTS = 32;
 #define PA_TRACE(slot)                                                                      \
 	do {                                                                                    \
-		if (A.trace && blockIdx.x == 0 && threadIdx.x == 0 && step < A.trace_steps) {       \
+		if (A.trace && blockIdx.x == 0 && threadIdx.x == 0 && tstep < A.trace_steps) {      \
 			unsigned long long _t;                                                          \
 			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                          \
-			A.trace[(size_t)step * 8 + (slot)] = _t;                                        \
+			A.trace[(size_t)tstep * PA_TRACE_SLOTS + (slot)] = _t;                          \
+		}                                                                                   \
+	} while (0)
+
+// the same, but not before `dep` has been produced (a load result, say)
+// consumer warp 0 of CTA 0
+#define PA_TRACE_C(slot, dep)                                                               \
+	do {                                                                                    \
+		if (A.trace && blockIdx.x == 0 && threadIdx.x == 32 && tstep < A.trace_steps) {     \
+			unsigned long long _t;                                                          \
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t) : "r"((int)(dep)));        \
+			A.trace[(size_t)tstep * PA_TRACE_SLOTS + (slot)] = _t;                          \
+		}                                                                                   \
+	} while (0)
+#define PA_TRACE_DEP(slot, dep)                                                             \
+	do {                                                                                    \
+		if (A.trace && blockIdx.x == 0 && threadIdx.x == 0 && tstep < A.trace_steps) {      \
+			unsigned long long _t;                                                          \
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t) : "r"((int)(dep)));        \
+			A.trace[(size_t)tstep * PA_TRACE_SLOTS + (slot)] = _t;                          \
 		}                                                                                   \
 	} while (0)
 
@@ -284,9 +488,11 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 	__shared__ PaNear warp_near[PA_WARPS];
 	__shared__ PaPartial s_tot;
 	__shared__ long long s_base, s_lo, s_hi, s_front_row, s_back_row, s_new_center, s_seed;
-	__shared__ unsigned long long s_front_pos, s_back_pos, s_magc;
+	__shared__ unsigned long long s_front_pos, s_back_pos;
 	__shared__ unsigned long long s_red[PA_WARPS];
-	__shared__ int s_front_bin, s_back_bin, s_first_live, s_last_live, s_cta_npos;
+	__shared__ int s_front_bin, s_back_bin, s_first_live, s_last_live, s_any_marks, s_ok, s_cta_marks, s_sink;
+	__shared__ unsigned s_t_scan0;
+	__shared__ unsigned long long s_wend[PA_WARPS];
 
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const int G = gridDim.x, cta = blockIdx.x;
@@ -321,6 +527,9 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 		s_first_live = 0;
 		s_last_live = nb - 1;
+		s_any_marks = 0;
+		s_ok = 1;
+		s_sink = 0;
 	}
 	__syncthreads();
 
@@ -329,92 +538,84 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long)s_row0[mid + 1] <= row) lo = mid + 1; else hi = mid; }
 		return lo;
 	};
-	// bvec::pop / erase (bvec.cpp:27-38,281-285) of a seed: every CTA clears the bit (idempotent) and
-	// updates its own bin counts
-	auto kill_row = [&](long long row) {
-		if (threadIdx.x == 0) {
-			// the returning form: the bit is cleared in L2 before this CTA reads the word again
-			const unsigned old = atomicAnd(A.alive_bits + (row >> 5), ~(1u << (row & 31)));
-			asm volatile("" ::"r"(old) : "memory");
-			s_alive[bin_of(row)]--;
-			__threadfence();
-		}
-	};
-	// first alive row in iteration order (bvec::pop), -1 when the bvec is empty; warp 0 only
-	auto pop_row = [&]() -> long long {
+	// first alive row in iteration order (bvec::pop, bvec.cpp:27-38), -1 when the bvec is empty; warp 0 only.
+	// `skip`: the center of the running step (its bit may still be set, see below)
+	auto pop_row = [&](long long skip) -> long long {
 		int fl = s_first_live;
 		while (fl < nb && s_alive[fl] == 0) fl++;
 		__syncwarp();
 		if (lane == 0) s_first_live = fl;
 		if (fl >= nb) return -1;
-		return pa_select(A.alive_bits, s_row0[fl], s_row0[fl + 1], 0, lane);
+		return pa_select(A.alive_bits, s_row0[fl], s_row0[fl + 1], 0, skip, lane);
 	};
 
 	// ---- loop state, identical in every thread of every CTA
-	unsigned long long epoch = 0;     // grid barriers passed
-	long long step = 0;               // scans issued (parity of the partial buffers)
+	long long step = 0;               // scans issued (parity and tag of the records)
 	long long cluster = 0, cl_begin = 0, m0 = 1;
 	long long center;
 	bool first_step = true;
+	long long cl_seed = -1;   // `current` starts as {seed} (ClusterFactory.cpp:641): its histogram is added when the mean is taken
 	long long st_scans = 0, st_evals = 0, st_near = 0;
 	unsigned long long t_start = 0;
 	if (cta == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 
 	// running count of tiles consumed so far by (this consumer warp | the consumer this producer lane feeds)
-	long long ring_cnt = 0;
+	// (kept modulo 2 * D: slot = cnt % D, mbarrier parity = (cnt / D) & 1)
+	unsigned ring_cnt = 0;
+	unsigned slot_uses = 0;   // producer lane: copies issued into its slot so far (only "none yet" and the parity matter)
+	bool slot_used = false;
 
-	// first seed: bvec::pop (ClusterFactory.cpp:722)
+	// A seed leaves the bvec when it is chosen (bvec::pop / erase, bvec.cpp:27-38,281-285).  Its bit in the
+	// global bitmap is cleared LATER -- behind the exchange of the cluster's first scan, when no CTA can still
+	// be looking for the same seed -- and until then every reader of the bitmap masks the center's bit itself.
+	// The per-bin counts (private to the CTA) are updated at once.
 	if (wib == 0) {
-		const long long r = pop_row();
-		if (lane == 0) s_seed = r;
-	}
-	// every CTA must have read the bitmap before any CTA clears the popped row's bit
-	if (!pa_grid_barrier(A.bar, ++epoch * (unsigned long long)G)) return;
-	center = s_seed;
-	if (center >= 0) {
-		kill_row(center);
-		if (cta == 0 && threadIdx.x == 0) { A.members[0] = (int)center; A.cl_off[0] = 0; }
+		const long long r = pop_row(-1);   // first seed: bvec::pop (ClusterFactory.cpp:722)
+		if (lane == 0) {
+			s_seed = r;
+			if (r >= 0) s_alive[bin_of(r)]--;
+		}
 	}
 	__syncthreads();
+	center = s_seed;
+	if (center >= 0 && cta == 0 && threadIdx.x == 0) { A.members[0] = (int)center; A.cl_off[0] = 0; }
 
 	while (center >= 0) {
 		const int par = (int)(step & 1);
+		const uint32_t tag = (uint32_t)(step + 1);
+		if (first_step) cl_seed = center;
+		const long long tstep = step;
+		unsigned long long *my_rec = A.recs + ((size_t)par * G + cta) * PA_REC_WORDS;
+		unsigned long long *my_near = A.near_recs + ((size_t)par * G + cta) * PA_REC_WORDS;
 		PA_TRACE(0);
 		// ================= control: bvec::get_range of the center's length window =================
 		if (wib < 2) {
 			const PaRange rec = A.range_tab[center];
-			if (wib == 0) {
-				int fb = rec.fb;
-				unsigned long long pos = 0;
-				if (s_alive[fb] == 0) {
+			const bool back = wib == 1;
+			int bin = back ? rec.bb : rec.fb;
+			PA_TRACE_DEP(10, bin);
+			unsigned long long pos = 0;
+			long long row = -1;
+			if (s_alive[bin] == 0) {
+				if (!back) {
 					int fl = s_first_live;
 					while (fl < nb && s_alive[fl] == 0) fl++;
-					if (fl < nb) fb = fl;   // position 0 of the first non-empty bin
+					if (fl < nb) bin = fl;   // position 0 of the first non-empty bin
 				} else {
-					unsigned a_lt, a_le, tot;
-					pa_rank3(A.alive_bits, s_row0[fb], s_row0[fb + 1], rec.f_lt, rec.f_le, lane, a_lt, a_le, tot);
-					unsigned long long f, b;
-					pa_inner_search(s_alive[fb], a_lt, a_le, f, b);
-					pos = f;
-				}
-				const long long row = pos < s_alive[fb] ? pa_select(A.alive_bits, s_row0[fb], s_row0[fb + 1], pos, lane) : -1;
-				if (lane == 0) { s_front_bin = fb; s_front_pos = pos; s_front_row = row; }
-			} else {
-				int bb = rec.bb;
-				unsigned long long pos = (unsigned long long)s_alive[nb - 1] - 1ull;   // wraps on an empty last bin, as in the reference
-				if (s_alive[bb] == 0) {
+					pos = (unsigned long long)s_alive[nb - 1] - 1ull;   // wraps on an empty last bin, as in the reference
 					int ll = s_last_live;
 					while (ll >= 0 && s_alive[ll] == 0) ll--;
-					if (ll >= 0) { bb = ll; pos = 0; }   // position 0 of the LAST non-empty bin (bvec.cpp:68-77)
-				} else {
-					unsigned a_lt, a_le, tot;
-					pa_rank3(A.alive_bits, s_row0[bb], s_row0[bb + 1], rec.b_lt, rec.b_le, lane, a_lt, a_le, tot);
-					unsigned long long f, b;
-					pa_inner_search(s_alive[bb], a_lt, a_le, f, b);
-					pos = b;
+					if (ll >= 0) { bin = ll; pos = 0; }   // position 0 of the LAST non-empty bin (bvec.cpp:68-77)
 				}
-				const long long row = pos < s_alive[bb] ? pa_select(A.alive_bits, s_row0[bb], s_row0[bb + 1], pos, lane) : -1;
-				if (lane == 0) { s_back_bin = bb; s_back_pos = pos; s_back_row = row; }
+				if (pos < s_alive[bin]) row = pa_select(A.alive_bits, s_row0[bin], s_row0[bin + 1], pos, center, lane);
+			} else {
+				pa_locate(A.alive_bits, s_row0[bin], s_row0[bin + 1], back ? rec.b_lt : rec.f_lt, back ? rec.b_le : rec.f_le, back,
+				          center, lane, pos, row);
+			}
+			PA_TRACE_DEP(11, row);
+			if (lane == 0) {
+				if (back) { s_back_bin = bin; s_back_pos = pos; s_back_row = row; }
+				else { s_front_bin = bin; s_front_pos = pos; s_front_row = row; }
 			}
 		}
 		__syncthreads();
@@ -442,6 +643,9 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 			if (lane == 0) {
 				if (dlt + 1 > 0 && s_front_row >= 0 && s_back_row >= s_front_row) { s_lo = s_front_row; s_hi = s_back_row; }
 				else { s_lo = 0; s_hi = -1; }
+				unsigned long long t = 0;
+				if (A.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+				s_t_scan0 = (unsigned)t;
 			}
 		}
 		__syncthreads();
@@ -460,13 +664,14 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 			// ----- producer: lane l owns ring slot l = (consumer l / D, ring position l % D)
 			if (lane < NS) {
 				const int w = lane / D, dpos = lane % D;
-				const long long nw = qc > w ? (qc - w + NCW - 1) / NCW : 0;   // tiles of consumer w in this step
-				for (long long u = 0; u < nw; u++) {
-					const long long g = ring_cnt + u;
-					if ((int)(g % D) != dpos) continue;
-					const long long round = g / D;
-					if (round > 0) mbar_wait(&empty_bar[lane], (uint32_t)(round - 1) & 1);
-					const long long r0 = (cbeg + w + u * NCW) * T::RT;
+				const unsigned nw = qc > w ? (unsigned)(qc - w + NCW - 1) / (unsigned)NCW : 0u;   // tiles of consumer w in this step
+				// the first tile of this step that lands in this lane's slot, then every D-th
+				unsigned u = ((unsigned)dpos + (unsigned)D - ring_cnt % (unsigned)D) % (unsigned)D;
+				for (; u < nw; u += (unsigned)D) {
+					if (slot_used) mbar_wait(&empty_bar[lane], (slot_uses - 1u) & 1u);
+					slot_used = true;
+					slot_uses++;
+					const long long r0 = (cbeg + w + (long long)u * NCW) * T::RT;
 					long long nr = A.n - r0;
 					if (nr > T::RT) nr = T::RT;
 					uint8_t *dst = ring + (size_t)lane * T::STAGE_BYTES;
@@ -474,7 +679,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 					tma_bulk_g2s(dst, A.hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[lane]);
 					tma_bulk_g2s(dst + T::ROW_BYTES, A.aux + r0, (uint32_t)(nr * 32), &full_bar[lane]);
 				}
-				ring_cnt += nw;
+				ring_cnt = (ring_cnt + nw) % (2u * (unsigned)D);
 			}
 		} else if (wib - 1 < NCW) {
 			// ----- consumers
@@ -484,7 +689,9 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 			cen.load(A.hist + (size_t)center * RB, r);
 			const McRowAux caux = A.aux[center];
 			const uint64_t lq = caux.len, mq = caux.mag, sq = caux.sq;
-			long long u = 0;
+			PA_TRACE_C(22, cen.w[0][0] + (unsigned)lq);
+			unsigned u = 0;
+			unsigned rslot = ring_cnt % (unsigned)D, rpar = (ring_cnt / (unsigned)D) & 1u;
 			for (int jj = cw; jj < qc; jj += NCW, u++) {
 				const long long tile = cbeg + jj;
 				const long long row_mine = tile * T::RT + lane;
@@ -492,9 +699,10 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				const int shift = (int)((tile * T::RT) & 31);
 				const uint32_t aw = __ldcg(A.alive_bits + word);
 				const bool have_row = lane < T::RT && row_mine >= lo && row_mine <= hi && ((aw >> (shift + lane)) & 1u) && row_mine != center;
-				const long long gcnt = ring_cnt + u;
-				const int slot = cw * D + (int)(gcnt % D);
-				mbar_wait(&full_bar[slot], (uint32_t)(gcnt / D) & 1);
+				const int slot = cw * D + (int)rslot;
+				mbar_wait(&full_bar[slot], rpar);
+				if (++rslot == (unsigned)D) { rslot = 0; rpar ^= 1u; }
+				if (u == 0) PA_TRACE_C(23, 0);
 				const uint8_t *st = ring + (size_t)slot * T::STAGE_BYTES;
 				McRowAux my_aux;
 				my_aux.len = 0; my_aux.mag = 0; my_aux.sq = 0; my_aux.alive = 0; my_aux.pad = 0;
@@ -520,20 +728,22 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				const PairAcc<TB> tot = mc_transpose_reduce<C::LPP>(part, r);
 				unsigned flag = 0;
 				if (have_row) {
-					double f0, sum;
-					mc_scan_epilogue<TB>(A.model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
-					flag = MC_IS_SIMILAR(sum) ? 1u : 0u;
+					double f0;
+					const unsigned dec = mc_scan_decide<TB>(A.model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0);
+					flag = dec & 1u;
 					mine.s.n_eval++;
 					mine.s.n_pos += flag;
-					if (fabs(sum) < MC_NEAR_THRESHOLD) mine.n_near++;
+					mine.n_near += dec >> 1;
 					if (f0 > mine.s.best_f0) { mine.s.best_f0 = f0; mine.s.best_row = row_mine; }
 				}
 				const unsigned mask = __ballot_sync(MC_FULL_MASK, flag != 0);
+				if (u == 0) PA_TRACE_C(24, mask);
 				if (lane == 0) s_marks[jj] = mask;
 				if (mask) {
 					// bvec::remove_available (bvec.cpp:290-317): the rows leave the bvec -- their bits are
-					// cleared in the tail, behind barrier 1: a slower CTA may still be reading the bitmap for
+					// cleared in the tail, behind the exchange: a slower CTA may still be reading the bitmap for
 					// the range of THIS step -- and join `current`: their histograms go into this CTA's bin sums
+					if (lane == 0) s_any_marks = 1;
 					for (unsigned mm = mask; mm; mm &= mm - 1) {
 						const long long mrow = tile * T::RT + (__ffs(mm) - 1);
 						const uint32_t *src = reinterpret_cast<const uint32_t *>(A.hist + (size_t)mrow * RB);
@@ -549,97 +759,160 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 					}
 				}
 			}
-			ring_cnt += u;
-			mc_scan_warp_fold(mine.s);
-#pragma unroll
-			for (int o = 16; o; o >>= 1) mine.n_near += __shfl_xor_sync(MC_FULL_MASK, mine.n_near, o);
+			ring_cnt = (ring_cnt + u) % (2u * (unsigned)D);
+			PA_TRACE_C(25, u);
+			if (A.trace && cta == 0 && lane == 0) {
+				unsigned long long t;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+				s_wend[wib] = t;
+			}
+			pa_scan_fold_redux(mine.s);
+			mine.n_near = __reduce_add_sync(MC_FULL_MASK, (unsigned)mine.n_near);
 			if (lane == 0) warp_part[cw] = mine;
 		}
 		__syncthreads();
 		PA_TRACE(2);
-		// ----- CTA partial, flush of the bin sums
+		if (A.trace && cta == 0 && threadIdx.x == 0 && tstep < A.trace_steps) {
+			unsigned long long m = 0;
+			for (int w = 1; w <= NCW; w++) m = s_wend[w] > m ? s_wend[w] : m;
+			A.trace[(size_t)tstep * PA_TRACE_SLOTS + 21] = m;
+		}
+		// ----- the bin sums of this CTA's marked rows join the cluster's global sums
+		const int gbuf = (int)(cluster % 3);
+		{
+			if (s_any_marks) {   // uniform in the CTA
+				unsigned long long *gs = A.g_sum + (size_t)gbuf * pa_gsum_words(NB);
+				unsigned long long ret = 0;
+				for (int b = threadIdx.x; b < NB; b += PA_THREADS) {
+					const unsigned long long v = s_sum[b];
+					if (v) ret |= atomicAdd(gs + pa_gsum_idx(b), v);
+					s_sum[b] = 0;
+				}
+				pa_retire(ret, &s_sink);
+				__syncthreads();
+			}
+		}
+		PA_TRACE(14);
+		// ================= exchange 1: this CTA's summary out, everybody's summaries in =================
 		if (wib == 0) {
 			PaPartial b;
 			mc_scan_init(b.s);
 			b.n_near = 0; b.pad = 0;
 			if (lane < NCW) b = warp_part[lane];
-			mc_scan_warp_fold(b.s);
-#pragma unroll
-			for (int o = 16; o; o >>= 1) b.n_near += __shfl_xor_sync(MC_FULL_MASK, b.n_near, o);
-			if (lane == 0) {
-				A.partials[(size_t)par * G + cta] = b;
-				s_cta_npos = (int)b.s.n_pos;
-			}
-		}
-		__syncthreads();
-		const int gbuf = (int)(cluster % 3);
-		{
-			// `current` starts as {seed} (ClusterFactory.cpp:641): CTA 0 adds the seed's histogram in the
-			// first step of a cluster
-			const bool seed_add = first_step && cta == 0;
-			if (s_cta_npos > 0 || seed_add) {
-				unsigned long long *gs = A.g_sum + (size_t)gbuf * NB;
-				for (int b = threadIdx.x; b < NB; b += PA_THREADS) {
-					unsigned long long v = s_sum[b];
-					if (seed_add) v += TB == 1 ? (unsigned long long)A.hist[(size_t)center * RB + b]
-					                           : (unsigned long long)reinterpret_cast<const uint16_t *>(A.hist + (size_t)center * RB)[b];
-					if (v) atomicAdd(gs + b, v);
-					s_sum[b] = 0;
+			pa_scan_fold_redux(b.s);
+			b.n_near = __reduce_add_sync(MC_FULL_MASK, (unsigned)b.n_near);
+			unsigned long long tnow = 0;
+			if (A.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));
+			pa_release_fence();
+			PA_TRACE(4);
+			{
+				const unsigned long long f0b = (unsigned long long)__double_as_longlong(b.s.best_f0);
+				uint32_t wv = 0;
+				switch (lane) {
+				case 0: wv = (uint32_t)b.s.n_pos; break;
+				case 1: wv = (uint32_t)b.s.n_eval; break;
+				case 2: wv = (uint32_t)(int)b.s.best_row; break;
+				case 3: wv = (uint32_t)f0b; break;
+				case 4: wv = (uint32_t)(f0b >> 32); break;
+				case 5: wv = (uint32_t)b.n_near; break;
+				case 6: wv = s_t_scan0; break;
+				case 7: wv = (uint32_t)tnow; break;
+				default: break;
 				}
+				if (lane < PA_REC_WORDS) pa_ll_store(my_rec + lane, wv, tag);
 			}
-		}
-		if (!pa_grid_barrier(A.bar, ++epoch * (unsigned long long)G)) return;
-		PA_TRACE(3);
-
-		// ================= fold (every CTA, redundantly: <= 148 records out of L2) =================
-		if (wib == 0) {
+			PA_TRACE(12);
+			// every CTA reads the records of all CTAs (lane l: CTAs l, l + 32, ...): first one try at each of them
+			// with all loads in flight, then the late ones one by one
+			uint32_t d[PA_RPL][PA_REC_WORDS];
+			unsigned have = 0;
+#pragma unroll
+			for (int j = 0; j < PA_RPL; j++) {
+				const int i = lane + 32 * j;
+				if (i >= G) {
+					have |= 1u << j;
+					d[j][0] = 0; d[j][1] = 0; d[j][2] = 0xffffffffu; d[j][3] = 0; d[j][4] = 0xbff00000u; d[j][5] = 0;   // nothing, arg-max (-1, none)
+					d[j][6] = s_t_scan0; d[j][7] = (uint32_t)tnow;
+				} else if (pa_rec_try<PA_REC_WORDS>(A.recs + ((size_t)par * G + i) * PA_REC_WORDS, tag, d[j])) have |= 1u << j;
+			}
+			bool ok = true;
+#pragma unroll
+			for (int j = 0; j < PA_RPL; j++)
+				if (ok && !((have >> j) & 1u)) ok = pa_rec_wait<PA_REC_WORDS>(A.recs + ((size_t)par * G + lane + 32 * j) * PA_REC_WORDS, tag, d[j], A.bar + 1);
 			PaPartial t;
 			mc_scan_init(t.s);
 			t.n_near = 0; t.pad = 0;
-			long long base = 0;
-			for (int i = lane; i < G; i += 32) {
-				const PaPartial *p = A.partials + (size_t)par * G + i;
-				mc_scan_result q;
-				q.n_eval = __ldcg(&p->s.n_eval); q.n_pos = __ldcg(&p->s.n_pos);
-				q.best_row = __ldcg(&p->s.best_row); q.best_f0 = __ldcg(&p->s.best_f0);
-				mc_scan_merge(t.s, q);
-				t.n_near += __ldcg(&p->n_near);
-				if (i < cta) base += q.n_pos;
-			}
-			mc_scan_warp_fold(t.s);
+			unsigned base = 0, late0 = 0, late1 = 0;
 #pragma unroll
-			for (int o = 16; o; o >>= 1) {
-				t.n_near += __shfl_xor_sync(MC_FULL_MASK, t.n_near, o);
-				base += __shfl_xor_sync(MC_FULL_MASK, base, o);
+			for (int j = 0; j < PA_RPL; j++) {
+				mc_scan_result q;
+				q.n_pos = d[j][0]; q.n_eval = d[j][1]; q.best_row = (long long)(int)d[j][2];
+				q.best_f0 = __longlong_as_double((long long)(((unsigned long long)d[j][4] << 32) | d[j][3]));
+				mc_scan_merge(t.s, q);
+				t.n_near += d[j][5];
+				if (lane + 32 * j < cta) base += d[j][0];
+				const unsigned l0 = d[j][6] - s_t_scan0, l1 = d[j][7] - (unsigned)tnow;
+				if ((int)l0 > (int)late0) late0 = l0;
+				if ((int)l1 > (int)late1) late1 = l1;
 			}
-			if (lane == 0) { s_tot = t; s_base = base; }
+			ok = __all_sync(MC_FULL_MASK, ok);
+			pa_scan_fold_redux(t.s);
+			t.n_near = __reduce_add_sync(MC_FULL_MASK, (unsigned)t.n_near);
+			base = __reduce_add_sync(MC_FULL_MASK, base);
+			if (A.trace && cta == 0 && tstep < A.trace_steps) {
+				late0 = __reduce_max_sync(MC_FULL_MASK, late0);
+				late1 = __reduce_max_sync(MC_FULL_MASK, late1);
+				if (lane == 0) {
+					A.trace[(size_t)tstep * PA_TRACE_SLOTS + 8] = late0;
+					A.trace[(size_t)tstep * PA_TRACE_SLOTS + 9] = late1;
+				}
+			}
+			if (lane == 0) { s_tot = t; s_base = base; s_ok = ok ? 1 : 0; s_any_marks = 0; }
 		}
 		__syncthreads();
+		if (!s_ok) return;
+		PA_TRACE(3);
 		const mc_scan_result tot = s_tot.s;
 		if (hi >= lo) { st_scans++; st_evals += tot.n_eval; st_near += s_tot.n_near; }
+		// no CTA is looking for this cluster's seed any more: its bit goes (returning form: performed before
+		// the next block-wide barrier lets any thread of this CTA read the word again without the mask)
+		if (first_step && wib == PA_WARPS - 1 && lane == 0) {
+			const unsigned old = atomicAnd(A.alive_bits + (center >> 5), ~(1u << (center & 31)));
+			unsigned z;
+			asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(old));
+			if (z) s_sink = 1;   // never true: waits for the atomic
+		}
+		const bool was_first = first_step;
 		step++;
 		first_step = false;
-		PA_TRACE(4);
 
 		if (tot.n_pos == 0) {
 			// ----- is_min: no close point left (ClusterFactory.cpp:693-711): the cluster is closed, the
 			// arg-max of f0 becomes the next seed, or the first point of the bvec when there is none
 			if (wib == 0) {
 				long long r = tot.best_row;
-				if (r < 0) r = pop_row();
-				if (lane == 0) s_seed = r;
+				if (r < 0) r = pop_row(was_first ? center : -1);
+				if (lane == 0) {
+					s_seed = r;
+					if (r >= 0) s_alive[bin_of(r)]--;
+				}
 			}
-			// a popped row is found in the bitmap: every CTA must have looked before any CTA clears its bit
-			// (uniform: all CTAs see the same summary)
-			if (tot.best_row < 0 && !pa_grid_barrier(A.bar, ++epoch * (unsigned long long)G)) return;
 			if (cta == 0) {
-				if (threadIdx.x == 0) {
+				if (threadIdx.x == 32) {
 					A.cl_center[cluster] = (int)center;
 					A.cl_off[cluster + 1] = (int)(cl_begin + m0);
 				}
 				// the sums buffer of the cluster after the next one (last read two clusters ago)
-				unsigned long long *gz = A.g_sum + (size_t)((cluster + 2) % 3) * NB;
-				for (int b = threadIdx.x; b < NB; b += PA_THREADS) gz[b] = 0;
+				unsigned long long *gz = A.g_sum + (size_t)((cluster + 2) % 3) * pa_gsum_words(NB);
+				unsigned long long ret = 0;
+				for (int b = threadIdx.x; b < NB; b += PA_THREADS) {
+#if PA_RELEASE_BY_FENCE
+					gz[pa_gsum_idx(b)] = 0;
+#else
+					ret |= atomicExch(gz + pa_gsum_idx(b), 0ull);
+#endif
+				}
+				pa_retire(ret, &s_sink);   // performed before this CTA's next record (block barrier below)
 			}
 			__syncthreads();
 			const long long seed = s_seed;
@@ -648,11 +921,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 			m0 = 1;
 			first_step = true;
 			center = seed;
-			if (seed >= 0) {
-				kill_row(seed);
-				if (cta == 0 && threadIdx.x == 0) A.members[cl_begin] = (int)seed;
-			}
-			__syncthreads();
+			if (seed >= 0 && cta == 0 && threadIdx.x == 0) A.members[cl_begin] = (int)seed;
 			PA_TRACE(7);
 			continue;
 		}
@@ -674,13 +943,19 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				if (i < qc) s_mpref[i] = carry + incl - pc;
 				carry += __shfl_sync(MC_FULL_MASK, incl, 31);
 			}
+			if (lane == 0) s_cta_marks = (int)carry;
 		}
 		{
 			// truncated mean: floor(sum / |current|) per bin and its magnitude (DivergencePoint.cpp:53-65,155-173)
-			const unsigned long long *gs = A.g_sum + (size_t)gbuf * NB;
+			const unsigned long long *gs = A.g_sum + (size_t)gbuf * pa_gsum_words(NB);
 			unsigned long long local = 0;
+			const uint8_t *seed_hist = A.hist + (size_t)cl_seed * RB;
 			for (int b = threadIdx.x; b < NB; b += PA_THREADS) {
-				const unsigned long long v = __ldcg(gs + b) / (unsigned long long)m_all;
+				const unsigned long long sb = TB == 1 ? (unsigned long long)seed_hist[b] : (unsigned long long)reinterpret_cast<const uint16_t *>(seed_hist)[b];
+				const unsigned long long tot_b = __ldcg(gs + pa_gsum_idx(b)) + sb;
+				// 32-bit division whenever the operands allow (the 64-bit one is a ~100-instruction routine)
+				const unsigned long long v = ((tot_b | (unsigned long long)m_all) >> 32) ? tot_b / (unsigned long long)m_all
+				                                                                       : (unsigned long long)((uint32_t)tot_b / (uint32_t)m_all);
 				if (TB == 1) s_tq[b] = (uint8_t)v; else reinterpret_cast<uint16_t *>(s_tq)[b] = (uint16_t)v;
 				local += v;
 			}
@@ -689,13 +964,10 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 			if (lane == 0) s_red[wib] = local;
 		}
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			unsigned long long t = 0;
-			for (int w = 0; w < PA_WARPS; w++) t += s_red[w];
-			s_magc = t;
-		}
-		__syncthreads();
-		const unsigned long long magc = s_magc;
+		PA_TRACE(16);
+		unsigned long long magc = 0;
+#pragma unroll
+		for (int w = 0; w < PA_WARPS; w++) magc += s_red[w];
 		PaNear best;
 		best.pos = -1; best.dist = 0; best.row = -1; best.pad = 0;
 		auto consider = [&](long long row, long long pos) {
@@ -706,60 +978,106 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 			cnd.dist = mc_distance_d(pa.summin(mp, magc), mp, magc);
 			pa_near_merge(best, cnd);   // NaN never replaces, like the reference's `<`
 		};
-		// this CTA's new members, in row order behind the ones of the CTAs before it
-		for (int i = wib; i < qc; i += PA_WARPS) {
+		// this CTA's new members, in row order behind the ones of the CTAs before it; the k-th one goes to warp
+		// k mod PA_WARPS (rows of one length are neighbours: a tile can hold many of them)
+		unsigned long long ret = 0;
+		for (int i = threadIdx.x; i < qc; i += PA_THREADS) {
 			const unsigned mask = s_marks[i];
-			if (!mask) continue;
-			if (lane == 0) {   // the rows leave the bvec (visible to every CTA behind barrier 2)
+			if (mask) {   // the rows leave the bvec (visible to every CTA behind exchange 2)
 				const long long trow = (cbeg + i) * T::RT;
-				atomicAnd(A.alive_bits + (trow >> 5), ~(mask << (int)(trow & 31)));
+				ret |= atomicAnd(A.alive_bits + (trow >> 5), ~(mask << (int)(trow & 31)));
 			}
-			long long pos = m0 + s_base + s_mpref[i];
-			for (unsigned mm = mask; mm; mm &= mm - 1, pos++) {
-				const long long row = (cbeg + i) * T::RT + (__ffs(mm) - 1);
-				if (lane == 0) A.members[cl_begin + pos] = (int)row;
-				consider(row, pos);
+		}
+		for (int k = wib; k < s_cta_marks; k += PA_WARPS) {
+			int tl = 0, th = qc - 1;   // last tile whose prefix is <= k
+			while (tl < th) { const int mid = (tl + th + 1) >> 1; if ((int)s_mpref[mid] <= k) tl = mid; else th = mid - 1; }
+			const long long row = (cbeg + tl) * T::RT + __fns(s_marks[tl], 0, k - (int)s_mpref[tl] + 1);
+			const long long pos = m0 + s_base + k;
+			if (lane == 0) {
+#if PA_RELEASE_BY_FENCE
+				A.members[cl_begin + pos] = (int)row;
+#else
+				ret |= (unsigned)atomicExch(A.members + cl_begin + pos, (int)row);
+#endif
 			}
+			consider(row, pos);
 		}
 		// its share of the members `current` already had
 		for (long long idx = (long long)cta * PA_WARPS + wib; idx < m0; idx += (long long)G * PA_WARPS)
 			consider(__ldcg(A.members + cl_begin + idx), idx);
 		if (lane == 0) warp_near[wib] = best;
+		pa_retire(ret, &s_sink);
+		PA_TRACE_DEP(17, best.row);
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			PaNear b = warp_near[0];
-			for (int w = 1; w < PA_WARPS; w++) pa_near_merge(b, warp_near[w]);
-			A.near[(size_t)par * G + cta] = b;
-		}
-		PA_TRACE(5);
-		if (!pa_grid_barrier(A.bar, ++epoch * (unsigned long long)G)) return;
-		PA_TRACE(6);
+		PA_TRACE(18);
+		// ================= exchange 2: nearest-member candidates =================
 		if (wib == 0) {
 			PaNear b;
 			b.pos = -1; b.dist = 0; b.row = -1; b.pad = 0;
-			for (int i = lane; i < G; i += 32) {
-				const PaNear *p = A.near + (size_t)par * G + i;
-				PaNear q;
-				q.pos = __ldcg(&p->pos); q.dist = __ldcg(&p->dist); q.row = __ldcg(&p->row); q.pad = 0;
-				pa_near_merge(b, q);
-			}
+			if (lane < PA_WARPS) b = warp_near[lane];
+			auto fold_near = [&](PaNear &x) {
 #pragma unroll
-			for (int o = 16; o; o >>= 1) {
-				PaNear q;
-				q.pos = __shfl_xor_sync(MC_FULL_MASK, b.pos, o);
-				q.dist = __shfl_xor_sync(MC_FULL_MASK, b.dist, o);
-				q.row = __shfl_xor_sync(MC_FULL_MASK, b.row, o);
-				q.pad = 0;
-				pa_near_merge(b, q);
+				for (int o = 16; o; o >>= 1) {
+					PaNear q;
+					q.pos = __shfl_xor_sync(MC_FULL_MASK, x.pos, o);
+					q.dist = __shfl_xor_sync(MC_FULL_MASK, x.dist, o);
+					q.row = __shfl_xor_sync(MC_FULL_MASK, x.row, o);
+					q.pad = 0;
+					pa_near_merge(x, q);
+				}
+			};
+			fold_near(b);
+			pa_release_fence();   // member rows and cleared bits of the whole CTA precede the record
+			PA_TRACE(19);
+			{
+				const unsigned long long db = (unsigned long long)__double_as_longlong(b.dist);
+				uint32_t wv = 0;
+				switch (lane) {
+				case 0: wv = (uint32_t)(int)b.pos; break;
+				case 1: wv = (uint32_t)db; break;
+				case 2: wv = (uint32_t)(db >> 32); break;
+				case 3: wv = (uint32_t)(int)b.row; break;
+				default: break;
+				}
+				if (lane < 4) pa_ll_store(my_near + lane, wv, tag);
 			}
-			if (lane == 0) s_new_center = b.row;
+			PA_TRACE(5);
+			uint32_t d[PA_RPL][4];
+			unsigned have = 0;
+#pragma unroll
+			for (int j = 0; j < PA_RPL; j++) {
+				const int i = lane + 32 * j;
+				if (i >= G) { have |= 1u << j; d[j][0] = 0xffffffffu; d[j][1] = 0; d[j][2] = 0; d[j][3] = 0xffffffffu; }
+				else if (pa_rec_try<4>(A.near_recs + ((size_t)par * G + i) * PA_REC_WORDS, tag, d[j])) have |= 1u << j;
+			}
+			bool ok = true;
+#pragma unroll
+			for (int j = 0; j < PA_RPL; j++)
+				if (ok && !((have >> j) & 1u)) ok = pa_rec_wait<4>(A.near_recs + ((size_t)par * G + lane + 32 * j) * PA_REC_WORDS, tag, d[j], A.bar + 1);
+			PaNear t;
+			t.pos = -1; t.dist = 0; t.row = -1; t.pad = 0;
+#pragma unroll
+			for (int j = 0; j < PA_RPL; j++) {
+				PaNear q;
+				q.pos = (long long)(int)d[j][0];
+				q.dist = __longlong_as_double((long long)(((unsigned long long)d[j][2] << 32) | d[j][1]));
+				q.row = (long long)(int)d[j][3];
+				q.pad = 0;
+				pa_near_merge(t, q);
+			}
+			ok = __all_sync(MC_FULL_MASK, ok);
+			fold_near(t);
+			if (lane == 0) { s_new_center = t.row; s_ok = ok ? 1 : 0; }
 		}
+		__syncthreads();
+		if (!s_ok) return;
+		PA_TRACE(6);
 		// every CTA keeps its own bin counts: the new members leave their bins
 		for (long long i = threadIdx.x; i < n_new; i += PA_THREADS)
 			atomicSub(&s_alive[bin_of(__ldcg(A.members + cl_begin + m0 + i))], 1u);
-		__syncthreads();
 		center = s_new_center;   // get_mean always finds a member: `current` is never empty
 		m0 = m_all;
+		__syncthreads();
 		PA_TRACE(7);
 	}
 
@@ -814,7 +1132,10 @@ int mc_pa_rows_per_tile(int tbytes, int nbins) {
 	return rb * 32 <= 32 * 1024 ? 32 : (32 * 1024) / rb;
 }
 
-size_t mc_pa_partial_bytes() { return sizeof(PaPartial) > sizeof(PaNear) ? sizeof(PaPartial) : sizeof(PaNear); }
+size_t mc_pa_exchange_bytes(int grid) { return (size_t)4 * grid * PA_REC_WORDS * 8; }
+int mc_pa_max_grid() { return 32 * PA_RPL; }
+int mc_pa_trace_slots() { return PA_TRACE_SLOTS; }
+size_t mc_pa_gsum_bytes(int nbins) { return 3 * pa_gsum_words(nbins) * 8; }
 size_t mc_pa_range_bytes() { return sizeof(PaRange); }
 
 int mc_launch_pa_prepare(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, double sim,
@@ -835,7 +1156,7 @@ bool mc_pa_shape_supported(int tbytes, int nbins) {
 }
 
 int mc_launch_phase_a(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, const void *range_tab_dev,
-                      uint32_t *alive_bits_dev, unsigned long long *g_sum_dev, void *partials_dev, void *near_dev,
+                      uint32_t *alive_bits_dev, unsigned long long *g_sum_dev, void *exch_dev,
                       unsigned long long *bar_dev, int *members_dev, int *cl_center_dev, int *cl_off_dev, long long *stats_dev,
                       unsigned long long *trace_dev, int trace_steps, int grid, int qmax) {
 	PaArgs a{};
@@ -849,8 +1170,11 @@ int mc_launch_phase_a(mc_ctx *ctx, const unsigned long long *bounds_dev, const i
 	a.range_tab = (const PaRange *)range_tab_dev;
 	a.alive_bits = alive_bits_dev;
 	a.g_sum = g_sum_dev;
-	a.partials = (PaPartial *)partials_dev;
-	a.near = (PaNear *)near_dev;
+	{
+		unsigned long long *x = (unsigned long long *)exch_dev;
+		a.recs = x; x += 2 * (size_t)grid * PA_REC_WORDS;
+		a.near_recs = x;
+	}
 	a.bar = bar_dev;
 	a.members = members_dev;
 	a.cl_center = cl_center_dev;

@@ -287,20 +287,17 @@ scan_tma_kernel(const uint8_t *__restrict__ hist, McRowAux *__restrict__ aux, ui
 				double f0 = 0.0;
 				unsigned flag = 0;
 				if (have_row) {
-					double sum;
-					mc_scan_epilogue<TB>(model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
-					flag = MC_IS_SIMILAR(sum) ? 1u : 0u;
-					if (fabs(sum) < MC_NEAR_THRESHOLD) flag |= 2u;   // counted when the row turns out to be alive
+					flag = mc_scan_decide<TB>(model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0);   // bit 1: near the threshold, counted when the row turns out to be alive
 				}
 				if (u == 0) { pre_f0_0 = f0; pre_flag_0 = flag; } else { pre_f0_1 = f0; pre_flag_1 = flag; }
 				npre = (int)u + 1;
 			} else if (have_row) {
 				unsigned flag = 0;
 				if (__ldcg(&aux[row_mine].alive)) {   // dead rows skip the epilogue
-					double f0, sum;
-					mc_scan_epilogue<TB>(model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0, sum);
-					flag = MC_IS_SIMILAR(sum) ? 1u : 0u;
-					mc_count_near(model, sum);
+					double f0;
+					const unsigned dec = mc_scan_decide<TB>(model, tot.summin(my_aux.mag, mq), tot.dot(), my_aux.len, my_aux.mag, my_aux.sq, lq, mq, sq, NB, 1.0 / NB, f0);
+					flag = dec & 1u;
+					if (dec & 2u) atomicAdd(model.near, 1ull);
 					mine.n_eval++;
 					mine.n_pos += flag;
 					if (f0 > mine.best_f0) { mine.best_f0 = f0; mine.best_row = row_mine; }
