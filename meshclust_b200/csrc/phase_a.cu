@@ -313,10 +313,16 @@ __device__ __forceinline__ void pa_locate(const uint32_t *bits, long long r0l, l
 				const int src = __ffs(__ballot_sync(MC_FULL_MASK, mine)) - 1;
 				int r = -1;
 				if (mine) {
-					// the (pos - before)-th set bit of v[j]: drop the lower ones
+					// the (pos - before)-th set bit of v[j], by halving
 					uint32_t x = v[j];
-					for (unsigned k = pos - before; k; k--) x &= x - 1;
-					r = ((w0 + j * 32 + lane) << 5) + (__ffs(x) - 1);
+					unsigned k = pos - before;
+					int bit = 0;
+					unsigned c = __popc(x & 0xffffu); if (k >= c) { k -= c; x >>= 16; bit += 16; }
+					c = __popc(x & 0xffu); if (k >= c) { k -= c; x >>= 8; bit += 8; }
+					c = __popc(x & 0xfu); if (k >= c) { k -= c; x >>= 4; bit += 4; }
+					c = __popc(x & 0x3u); if (k >= c) { k -= c; x >>= 2; bit += 2; }
+					if (k >= (x & 1u)) bit += 1;
+					r = ((w0 + j * 32 + lane) << 5) + bit;
 				}
 				row = __shfl_sync(MC_FULL_MASK, r, src);
 			}
@@ -655,7 +661,10 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		// ================= scan: Trainer::get_close over the alive rows of [lo, hi] =================
 		// tiles on an absolute grid (tile t = rows [t*RT, (t+1)*RT)); this CTA owns a contiguous run
 		const long long t0 = lo / T::RT, ntiles = hi >= lo ? hi / T::RT - t0 + 1 : 0;
-		const long long cbeg = t0 + ntiles * cta / G, cend = t0 + ntiles * (cta + 1) / G;
+		// (32-bit divisions while the products fit: the 64-bit one is a long routine on the critical path)
+		const bool small = ntiles < (1ll << 24);
+		const long long cbeg = t0 + (small ? (long long)((unsigned)ntiles * (unsigned)cta / (unsigned)G) : ntiles * cta / G);
+		const long long cend = t0 + (small ? (long long)((unsigned)ntiles * (unsigned)(cta + 1) / (unsigned)G) : ntiles * (cta + 1) / G);
 		const int qc = (int)(cend - cbeg);   // <= qmax
 		PaPartial mine;
 		mc_scan_init(mine.s);
