@@ -4,19 +4,23 @@ C2 workload (100 k synthetic 1.5 kb 16S-like sequences, --id 0.97 --kmer 4), one
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is one Trainer::get_close-shaped pass (1 center x all n points: every live feature + the
-GLM decision + argmax/mark reduction) for each of S centers.  The S passes of a step remove nothing,
-so they are independent and mc_scan_enqueue_many sends them as one launch of the scan kernel
-(blockIdx.y = center); `dependent_chain` in the JSON line is the same work as S chained launches.
-  value  : evals/s with the histograms resident in HBM.  The batch is stored R times (R*29 MB >
-           2x the 126 MB L2) and consecutive launches rotate through the replicas, so every launch
+A "step" is 1000 Trainer::get_close-shaped scans (1 center x all n points each: every live feature +
+the GLM decision + argmax / mark reduction) issued the way accumulate() issues them: a DEPENDENT
+chain, one launch per scan, each behind the one before it (programmatic dependent launch).
+  value  : evals/s of that chain with the histograms resident in HBM.  The batch is stored R times
+           (R*29 MB > 2x the 126 MB L2) and consecutive scans rotate through the replicas, so every scan
            streams its rows from HBM ("inputs larger than L2").
-  e2e    : the same S-center pass through the host-buffer C-ABI call mc_scan_host(): pinned host
+  independent_scans: the same scans as independent work (S of them share one launch) -- a micro-benchmark
+           of the kernel; Phase A never issues that shape.
+  phase_a_in_product: Phase A of bin/meshclust on the full C2 input (one persistent kernel: range, scan,
+           exchange, mean, next center on the device), evals/s and fraction of the HBM roofline.
+  e2e    : S scans through the host-buffer C-ABI call mc_scan_host() on every rank: pinned host
            histograms -> HBM (in chunks, overlapped with the scans of the previous chunk), S scans,
            marks + summaries back to the host, all inside the timed region.
-  --gpus N (torchrun, one process per GPU): every rank holds all N*n points and evaluates its n of
-           every scan; the summaries cross GPUs through NVLink peer inboxes (CUDA IPC) on a second
-           stream; value = evals of all ranks / max-over-ranks time.  DESIGN.md section 5.
+  --gpus N (torchrun, one process per GPU): weak scaling: every rank holds all N*n points and evaluates
+           its n of every scan; the summaries cross GPUs through NVLink peer inboxes (CUDA IPC) on a second
+           stream; value = evals of all ranks / max-over-ranks time.  extra.c4_shape_scan is the 1 M-point
+           shape strong-scaled.  DESIGN.md section 5.
   roofline: the scan kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json);
            algorithmic bytes per eval = 4^k + 33.
   cpu_baseline: the compiled unmodified reference (oracle/_ref/libmcref.so, Feature::compute +
@@ -44,7 +48,8 @@ METRIC = "feature_evals_per_sec"
 UNIT = "evals/s"
 WORKLOAD = "c2"
 K = 4
-S_CENTERS = 10            # scans per step
+S_CENTERS = 10            # scans per enqueue call (and per launch of the independent-scan micro-benchmark)
+CALLS_PER_STEP = 100      # enqueue calls per step: a step is 1000 scans
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -109,7 +114,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -222,10 +227,10 @@ def cpu_reference_rate(hist, lens, mins, maxs, w, centers, target_s: float, step
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)   # ~0.1 s of timed region: long enough for the clock sampler
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)     # a step is 1000 scans (~5.5 ms): 20 steps = 0.11 s of timed region
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-extra", action="store_true", help="skip the C4-shape roofline probe")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4-shape probe and the CLI leg")
     ap.add_argument("--scaling-only", action="store_true", help="development: skip the e2e and CPU-baseline legs too")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -248,7 +253,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from meshclust_b200 import api, sharding
+    from meshclust_b200 import api
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: meshclust_b200 has no CPU fallback")
@@ -305,25 +310,19 @@ def main():
     centers_global = np.random.default_rng(1234).integers(0, N, 64)   # the same centers on every rank
     centers_local = centers_global if world == 1 else rng.integers(0, n, 64)
 
-    _args_cache = {}
+    # arguments of the enqueue calls, built once outside the timed region: call c scans S centers, scan s of it
+    # against replica (c*S + s) % R; the sequence repeats after 64*R calls
+    NCALLARGS = 64 * R
+    call_args = []
+    for c in range(NCALLARGS):
+        reps = [(c * S + s) % R for s in range(S)]
+        cr = np.array([r * N + centers_global[(c * S + s) % 64] for s, r in enumerate(reps)], np.int64)
+        lo = np.array([r * N for r in reps], np.int64)
+        call_args.append((cr, lo, np.ascontiguousarray(lo + N - 1)))
 
-    def step_args(step):
-        # built once per step index, outside the timed region (see the precompute loop below)
-        a = _args_cache.get(step)
-        if a is None:
-            reps = [(step * S + s) % R for s in range(S)]
-            cr = np.array([r * N + centers_global[(step * S + s) % 64] for s, r in enumerate(reps)], np.int64)
-            lo = np.array([r * N for r in reps], np.int64)
-            hi = lo + N - 1
-            a = _args_cache[step] = (cr, lo, hi, np.ascontiguousarray(lo + rank * n), np.ascontiguousarray(lo + (rank + 1) * n - 1))
-        return a
-
-    for _s in range(args.warmup + args.steps + 1):
-        step_args(_s)
-
-    # N > 1: the scans of a step run back to back on the scan stream; a second stream folds each scan's
-    # CTA partials, stores the record into all ranks' inboxes over NVLink peer memory (CUDA IPC between
-    # the processes) and combines the world records per scan on the device, one step behind the scans.
+    # N > 1: the scans run back to back on the scan stream; a second stream folds each scan's CTA partials,
+    # stores the record into all ranks' inboxes over NVLink peer memory (CUDA IPC between the processes) and
+    # combines the world records per scan on the device, behind the scans.
     # Fallback when peer memory cannot be opened: device fold + NCCL all-gather.
     if world > 1:
         try:
@@ -338,155 +337,145 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         exchange = "peer_inbox" if float(ok.item()) > 0 else "nccl_allgather"
         if exchange == "nccl_allgather":
+            from meshclust_b200 import sharding
             ctx.set_stream(torch.cuda.current_stream().cuda_stream)
             records = torch.zeros((S, 4), dtype=torch.int64, device="cuda")
     last_results = [None]
+    inflight = []   # calls whose summaries have not been collected yet (at most 2 + the one being enqueued)
+    call_no = [0]
 
-    inflight = []   # steps whose summaries have not been collected yet (at most 2 + the one being enqueued)
-
-    def run_step(step):
+    def one_call(mode):
+        """S scans: mode = MC_SCAN_CHAIN (one launch per scan, each behind the previous one: what Phase A issues)
+        or MC_SCAN_KEEP (independent scans, one launch carries all S)."""
+        c = call_no[0]
+        call_no[0] += 1
+        cr, lo, hi = call_args[c % NCALLARGS]
         if world == 1:
-            cr, lo, hi, _, _ = step_args(step)
-            ctx.scan_enqueue_many(cr, lo, hi, False, 0)
-            return
-        if exchange == "nccl_allgather":
-            cr, lo, hi, sl, sh = step_args(step)
-            ctx.scan_enqueue_many(cr, sl, sh, False, 0)
+            ctx.scan_enqueue_many(cr, lo, hi, mode, 0)
+        elif exchange == "nccl_allgather":
+            ctx.scan_enqueue_many(cr, lo + rank * n, lo + (rank + 1) * n - 1, mode, 0)
             ctx.scan_fold_dev(0, S, records.data_ptr())
             last_results[0] = sharding.combine_scan_records(records, 0)
-            return
-        # software pipeline, one C-ABI call per step: enqueue this step's scans (+ fold / send / combine on
-        # the exchange stream) and collect the summaries of the step before the previous one, so the ~50 us
-        # from the end of a burst to its summaries on the host never stall the next enqueue
-        cr, lo, hi, sl, sh = step_args(step)
-        inflight.append(step)
-        if len(inflight) > 2:
-            old = inflight.pop(0)
-            last_results[0] = ctx.scan_sharded_burst(cr, lo, hi, False, (step % 3) * 16, (old % 3) * 16, S)
         else:
-            ctx.scan_sharded_burst(cr, lo, hi, False, (step % 3) * 16, 0, 0)
+            # software pipeline, one C-ABI call per S scans: enqueue them (+ fold / send / combine on the exchange
+            # stream) and collect the summaries of the call before the previous one
+            inflight.append(c)
+            if len(inflight) > 2:
+                old = inflight.pop(0)
+                last_results[0] = ctx.scan_sharded_burst(cr, lo, hi, mode, (c % 3) * 16, (old % 3) * 16, S)
+            else:
+                ctx.scan_sharded_burst(cr, lo, hi, mode, (c % 3) * 16, 0, 0)
 
     def drain():
         if world > 1 and exchange == "peer_inbox":
             e = np.zeros(0, np.int64)
             while inflight:
                 old = inflight.pop(0)
-                last_results[0] = ctx.scan_sharded_burst(e, e, e, False, 0, (old % 3) * 16, S)
+                last_results[0] = ctx.scan_sharded_burst(e, e, e, 0, 0, (old % 3) * 16, S)
 
-    for i in range(args.warmup):
-        run_step(i)
-    drain()
-    ctx.sync()
-    launches0 = ctx.launches
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record(stream)
-    for i in range(args.steps):
-        run_step(args.warmup + i)
-    drain()
-    ev1.record(stream)
-    ctx.sync()
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop()
-    dev_ms = ev0.elapsed_time(ev1)
-    gpu_launches = ctx.launches - launches0
-    if world == 1:
-        results = ctx.scan_collect(0, S)
-        assert all(r[0] == n for r in results), "scan did not evaluate every point"
-    else:
-        results = last_results[0]
-        if os.environ.get("MC_BURST_NO_EXCHANGE"):
-            log("[bench] MC_BURST_NO_EXCHANGE: diagnosis run, summaries are not exchanged")
-            results = [(N, 0, -1, -1.0)] * S
-        assert all(r[0] == N for r in results), f"sharded scan did not evaluate every point: {results[:2]}"
-        if exchange == "peer_inbox" and not os.environ.get("MC_BURST_NO_EXCHANGE"):
-            # self-check of the exchange: this rank also holds all rows, so one un-sharded scan over the
-            # whole replica must give exactly the exchanged summary
-            cr, lo, hi, _, _ = step_args(args.warmup + args.steps - 1)
-            ctx.scan_enqueue(int(cr[0]), int(lo[0]), int(hi[0]), False, 100)
-            whole = ctx.scan_collect(100, 1)[0]
-            assert whole == results[0], f"sharded summary {results[0]} != single-GPU summary {whole}"
 
-    # device time when there is no exchange; wall (barrier+sync bracketed) when there is one
-    total_ms = dev_ms if world == 1 else t_wall * 1e3
-    if world > 1:
-        tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
+    def timed(ncalls_warm, ncalls, mode, sampler=None):
+        """device time (CUDA events on the library's stream) and wall time of `ncalls` enqueue calls, max over ranks"""
+        for _ in range(ncalls_warm):
+            one_call(mode)
+        drain()
+        ctx.sync()
+        l0 = ctx.launches
+        if sampler:
+            sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(ncalls):
+            one_call(mode)
+        drain()
+        ev1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - tw) * 1e3
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        dev_ms = ev0.elapsed_time(ev1)
+        # device time when there is no exchange; wall (barrier + sync bracketed) when there is one
+        total_ms = dev_ms if world == 1 else wall_ms
+        if world > 1:
+            tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            total_ms = float(tt.item())
+        return total_ms, dev_ms, ctx.launches - l0, clocks
+
+    def check_results():
+        if world == 1:
+            res = ctx.scan_collect(0, S)
+            assert all(r[0] == n for r in res), "scan did not evaluate every point"
+        else:
+            res = last_results[0]
+            assert all(r[0] == N for r in res), f"sharded scan did not evaluate every point: {res[:2]}"
+        return res
+
+    # ================= headline: the dependent chain =================
+    total_ms, dev_ms, gpu_launches, clocks = timed(args.warmup * CALLS_PER_STEP, args.steps * CALLS_PER_STEP, api.MC_SCAN_CHAIN,
+                                                   ClockSampler(local_rank))
+    results = check_results()
+    if world > 1 and exchange == "peer_inbox":
+        # self-check of the exchange: this rank also holds all rows, so one un-sharded scan over the
+        # whole replica must give exactly the exchanged summary
+        cr, lo, hi = call_args[(call_no[0] - 1) % NCALLARGS]
+        ctx.scan_enqueue(int(cr[0]), int(lo[0]), int(hi[0]), False, 100)
+        whole = ctx.scan_collect(100, 1)[0]
+        assert whole == results[0], f"sharded summary {results[0]} != single-GPU summary {whole}"
     ms_per_step = total_ms / args.steps
-    evals_per_step = S * n * world
+    scans_per_step = CALLS_PER_STEP * S
+    evals_per_step = scans_per_step * n * world
     value = evals_per_step / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (scan): per-launch time from the CUDA events.  The S scans of a
-    # step are independent (nothing is removed), so one launch carries all of them (blockIdx.y = scan):
-    # bytes per launch = S x n x (4^k + 33)
+    # ---- roofline of the dominant kernel (scan): one scan per launch in the chain.  launch_us = device time of
+    # the timed region (CUDA events on the stream the kernel is launched on) / launches; bytes = n x (4^k + 33)
     peak, peak_src = measured_peak()
-    scans_per_launch = S if exchange != "nccl_allgather" else 1
-    bytes_per_launch = scans_per_launch * n * (nbins + 33)
-    launch_us = dev_ms * 1e3 / (args.steps * S / scans_per_launch)
-    achieved = bytes_per_launch / (launch_us * 1e-6) / 1e9
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel and shape from the committed
-    # `ncu --set full` capture (profiles/scan_traffic.json, per scan), not measured in this run
+    bytes_per_scan = n * (nbins + 33)
+    launch_us = dev_ms * 1e3 / (args.steps * scans_per_step)
+    achieved = bytes_per_scan / (launch_us * 1e-6) / 1e9
     traffic = None
     try:
-        traffic = scans_per_launch * json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))[f"c2_{nbins}"]["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))[f"c2_{nbins}"]["dram_bytes_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "kernel": f"scan_tma_kernel<1,{nbins}>", "launch_us": round(launch_us, 3),
-                "scans_per_launch": scans_per_launch, "us_per_scan": round(launch_us / scans_per_launch, 3),
-                "algorithmic_bytes_per_launch": bytes_per_launch,
-                "note": "launch_us = CUDA-event time of the timed region / kernel launches in it; the scans of a step share a launch"}
+                "kernel": f"scan_tma_kernel<1,{nbins}>", "launch_us": round(launch_us, 3), "scans_per_launch": 1,
+                "algorithmic_bytes_per_launch": bytes_per_scan,
+                "note": "dependent chain: one launch per scan, chained by programmatic dependent launch; launch_us = CUDA-event time of "
+                        "the timed region / launches in it; traffic = dram bytes of one launch from the committed ncu capture (profiles/)"}
 
-    # the same scans as a dependent chain (what accumulate() issues: each scan may remove rows the next
-    # one must not see): one launch per scan, chained by programmatic dependent launch
-    chain = None
-    if world == 1:
-        os.environ["MC_SCAN_NO_BATCH"] = "1"   # mc_scan_enqueue_many: one launch per scan (read by the library per call)
-        for rep in range(2):
-            cr, lo, hi, _, _ = step_args(rep)
-            ctx.scan_enqueue_many(cr, lo, hi, False, 200)
-        ctx.sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        reps_chain = 30
-        for rep in range(reps_chain):
-            cr, lo, hi, _, _ = step_args(args.warmup + rep % max(args.steps, 1))
-            ctx.scan_enqueue_many(cr, lo, hi, False, 200)
-        e1.record(stream)
-        ctx.sync()
-        del os.environ["MC_SCAN_NO_BATCH"]
-        us = e0.elapsed_time(e1) * 1e3 / (reps_chain * S)
-        chain = {"us_per_scan": round(us, 3), "evals_per_s": n / (us * 1e-6), "achieved_GBs": round(n * (nbins + 33) / (us * 1e-6) / 1e9, 1),
-                 "frac_of_peak": round(n * (nbins + 33) / (us * 1e-6) / 1e9 / peak, 4),
-                 "note": "one launch per scan, programmatic dependent launch"}
+    # ================= the same scans as independent work: S of them share a launch =================
+    ind_calls = 200
+    ind_ms, ind_dev_ms, ind_launches, _ = timed(20, ind_calls, api.MC_SCAN_KEEP)
+    check_results()
+    ind_us_scan = ind_dev_ms * 1e3 / (ind_calls * S)
+    independent = {"value": ind_calls * S * n * world / (ind_ms * 1e-3), "unit": UNIT, "us_per_scan_on_device": round(ind_us_scan, 3),
+                   "scans_per_launch": S, "launches": int(ind_launches),
+                   "achieved_GBs": round(bytes_per_scan / (ind_us_scan * 1e-6) / 1e9, 1),
+                   "frac_of_peak": round(bytes_per_scan / (ind_us_scan * 1e-6) / 1e9 / peak, 4),
+                   "note": "micro-benchmark: scans that remove nothing are independent and share a launch (blockIdx.y = scan); "
+                           "Phase A never issues this shape"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8", "data": "synthetic",
            "config": {"workload": f"{WORKLOAD}: 100k synthetic 1.5 kb 16S-like sequences, --id 0.97 --kmer 4",
-                      "points_per_gpu": n, "bins": nbins, "centers_per_step": S, "evals_per_step": evals_per_step,
-                      "l2": f"inputs larger than L2: {R} replicas of the batch ({R * n * row_bytes / 1e6:.0f} MB), launches rotate through them",
+                      "step": f"{scans_per_step} dependent get_close scans (1 center x all points each), one launch per scan",
+                      "points_per_gpu": n, "bins": nbins, "scans_per_step": scans_per_step, "evals_per_step": evals_per_step,
+                      "l2": f"inputs larger than L2: {R} replicas of the batch ({R * n * row_bytes / 1e6:.0f} MB), consecutive scans rotate through them",
                       "model": "4 features, bounds from 3000 sampled pairs, least-squares GLM", "parallelism": f"points sharded x{world}", "exchange": exchange},
-           "clocks": clocks, "gpu_launches": int(gpu_launches), "roofline": roofline}
-    if chain is not None:
-        out["dependent_chain"] = chain
+           "clocks": clocks, "gpu_launches": int(gpu_launches), "roofline": roofline, "independent_scans": independent}
 
-    if rank == 0 and args.scaling_only:
-        emit(out)
-    elif rank == 0:
-        # ---- e2e through the host-buffer C-ABI call: pinned host histograms in, marks + summaries out
+    # ================= e2e: the host-buffer C-ABI call on every rank's own points =================
+    if not args.scaling_only:
         hp = torch.empty((n, nbins), dtype=torch.uint8, pin_memory=True)
         hp.numpy()[:] = hist
         lp = torch.empty(n, dtype=torch.int64, pin_memory=True)
@@ -498,47 +487,80 @@ def main():
         hnp, lnp, mnp = hp.numpy(), lp.numpy().view(np.uint64), marks.numpy()
         for _ in range(3):
             ctx2.scan_host(hnp, lnp, K, cr, mnp)
-        reps = max(5, min(args.steps, 30))
+        reps = 30
+        summ = torch.zeros((S, 4), dtype=torch.float64)
+        summ_dev = torch.zeros((S, 4), dtype=torch.float64, device="cuda")
+        gath_dev = torch.zeros((world * S, 4), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(reps):
             res = ctx2.scan_host(hnp, lnp, K, cr, mnp)
+            if world > 1:
+                # the job's summaries: counts add up, arg-max over the ranks (what Trainer::get_close reduces)
+                for i, r in enumerate(res):
+                    summ[i, 0], summ[i, 1], summ[i, 2], summ[i, 3] = r[0], r[1], r[3], (r[2] + rank * n if r[2] >= 0 else -1)
+                summ_dev.copy_(summ)
+                dist.all_gather_into_tensor(gath_dev, summ_dev)
+                gath = gath_dev.cpu()   # every rank has the job's S summaries: evals / positives add up, arg-max over the ranks
         e2e_s = (time.perf_counter() - t0) / reps
+        if world > 1:
+            tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.item())
         # bytes mc_scan_host moves per call: histograms + lengths + copies of the S center rows up; S mark
         # arrays + the CTA partial records of S scans x 4 chunks (160 x 32 B each) down
-        out["e2e"] = {"value": S * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * nbins + n * 8 + S * (nbins + 8)),
-                      "d2h_bytes_per_step": int(S * n + 4 * S * 160 * 32), "ms_per_step": e2e_s * 1e3,
-                      "call": "mc_scan_host (pinned host histograms -> chunked upload overlapped with S scans per chunk -> marks + summaries on the host)"}
-        # parity spot-check of what was just timed (oracle as the checker only)
-        import _oracle
-        s_o, f0_o, fl_o = _oracle.oracle().scan(hist[:4000], lens[:4000], hist[cr[0]], int(lens[cr[0]]), mins, maxs, w, 4)
-        near = np.abs(s_o) < 1e-9
-        assert np.array_equal(mnp[0, :4000][~near], fl_o[~near]), "bench: scan marks differ from the oracle"
+        out["e2e"] = {"value": world * S * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * (n * nbins + n * 8 + S * (nbins + 8))),
+                      "d2h_bytes_per_step": int(world * (S * n + 4 * S * 160 * 32)), "ms_per_step": e2e_s * 1e3,
+                      "step": f"{S} get_close scans of every rank's {n} points from pinned host memory",
+                      "call": "mc_scan_host on every rank (pinned host histograms -> chunked upload overlapped with S scans per chunk -> marks + summaries on the host); "
+                              "max over ranks of the time per call"}
+        if rank == 0:
+            # parity spot-check of what was just timed (oracle as the checker only)
+            import _oracle
+            s_o, f0_o, fl_o = _oracle.oracle().scan(hist[:4000], lens[:4000], hist[cr[0]], int(lens[cr[0]]), mins, maxs, w, 4)
+            near = np.abs(s_o) < 1e-9
+            assert np.array_equal(mnp[0, :4000][~near], fl_o[~near]), "bench: scan marks differ from the oracle"
         ctx2.close()
 
+    if rank == 0 and not args.scaling_only:
         # ---- CPU baseline beside it: compiled reference on a bounded sample, all host threads
         v, cores, kind, sample, _ = cpu_reference_rate(hist, lens, mins, maxs, w, centers_local[:8], target_s=12.0)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-
-        # ---- extra: the same kernel on the C4 shape (1 M points x 1024 bins, 1 GB > L2), HBM-bound regime
-        if not args.no_extra and world == 1:
-            try:
-                out["extra"] = {"c4_shape_scan": c4_shape_probe(api, local_rank, torch, peak)}
-            except Exception as e:   # never lose the headline line to the probe
-                out["extra"] = {"c4_shape_scan_error": str(e)[:200]}
         out["stage1_histograms_ms_host_to_host"] = t_hist * 1e3
+
+    # ---- extra: the HBM-bound regime, the C4 shape (1 M points x 1024 bins, 1 GB > L2), STRONG-scaled: the same
+    # 1 M rows at every N, every rank scans its share of each scan
+    if not args.no_extra and not args.scaling_only:
+        try:
+            c4 = c4_shape_probe(api, local_rank, torch, dist, peak, rank, world, exchange)
+        except Exception as e:   # never lose the headline line to the probe
+            c4 = {"error": str(e)[:200]}
+        if rank == 0:
+            out["extra"] = {"c4_shape_scan": c4}
+
+    if rank == 0:
         # ---- second half of the metric: sequences clustered per second, FASTA in -> CLSTR out, through
         # the drop-in CLI (bin/meshclust) on the full C2 input; the reference CLI beside it on a bounded
-        # sample (its training sorts are O(150 n log n 4^k) on the CPU)
-        if not args.no_extra:
-            # at N > 1 the same input goes through `bin/meshclust --gpus N` (one process driving N GPUs: Phase A
-            # sharded, the rest on GPU 0); this rank's own CUDA context stays alive next to it
+        # sample (its training sorts are O(150 n log n 4^k) on the CPU).  At N > 1 the same input goes through
+        # `bin/meshclust --gpus N` (one process driving N GPUs); this rank's own CUDA context stays alive next to it
+        if not args.no_extra and not args.scaling_only:
             try:
                 out["seqs_clustered"] = cli_leg(letters, offs, tmpl, cfg, world)
+                pa = out["seqs_clustered"].pop("phase_a", None)
+                if pa:
+                    # Phase A as the product runs it (one persistent kernel: range, scan, exchange, mean, next center)
+                    pa["achieved_GBs"] = round(pa["evals"] * (nbins + 33) / pa["device_s"] / 1e9, 1)
+                    pa["frac_of_peak"] = round(pa["achieved_GBs"] / peak, 4)
+                    pa["note"] = ("bin/meshclust, accumulate() on the device: evals = alive points actually evaluated (dead rows are streamed "
+                                  "too but not counted); algorithmic bytes = evals x (4^k + 33)")
+                    out["phase_a_in_product"] = pa
             except Exception as e:
                 out["seqs_clustered"] = {"error": str(e)[:200]}
         emit(out)
     ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -567,10 +589,15 @@ def cli_leg(letters, offs, tmpl, cfg, gpus=1):
         m = re.search(r"gpu context ([0-9.]+)s on a helper thread, waited ([0-9.]+)s", r.stdout)
         ctx_s = float(m.group(2)) if m else 0.0
         ncl = open(os.path.join(d, "o.clstr")).read().count(">Cluster")
+        pa = re.search(r"Accumulation: (\d+) clusters, (\d+) scans, (\d+) evals, on the device in ([0-9.]+)s \(([0-9.]+) us per step\)", r.stdout)
+        near = re.search(r"Pairs within 1e-9 of the decision threshold: (\d+)", r.stdout)
         res = {"workload": f"c2 full (100k x 1.5 kb), bin/meshclust --id 0.97 --kmer 4 --gpus {gpus}", "wall_s": round(wall, 3),
                "cuda_context_wait_s": round(ctx_s, 3), "value": cfg.n / wall, "value_excluding_cuda_context_wait": cfg.n / max(wall - ctx_s, 1e-9),
                "stages": [ln.strip() for ln in r.stdout.splitlines() if "[" in ln and "s]" in ln][:16],
-               "unit": "seqs/s", "clusters": ncl}
+               "unit": "seqs/s", "clusters": ncl, "pairs_within_1e-9_of_threshold": int(near.group(1)) if near else None}
+        if pa:
+            res["phase_a"] = {"clusters": int(pa.group(1)), "scans": int(pa.group(2)), "evals": int(pa.group(3)), "device_s": float(pa.group(4)),
+                              "us_per_step": float(pa.group(5)), "evals_per_s": int(pa.group(3)) / max(float(pa.group(4)), 1e-9)}
         if os.path.exists(_oracle.REF_BIN) and gpus == 1:
             ns = 4000
             fs = os.path.join(d, "c2_sample.fa")
@@ -584,33 +611,85 @@ def cli_leg(letters, offs, tmpl, cfg, gpus=1):
     return res
 
 
-def c4_shape_probe(api, device, torch, peak):
+def c4_shape_probe(api, device, torch, dist, peak, rank, world, exchange):
+    """BASELINE configs[3] shape: 1 M points x 1024 bins (1.06 GB per scan, > L2), the same rows at every N:
+    every rank holds them all and scans its share of each scan (block-interleaved), summaries through the
+    peer inboxes.  Both as a dependent chain (one launch per scan) and as independent scans."""
     n, k = 1_000_000, 5
     nb = 4 ** k
+    if world > 1 and exchange != "peer_inbox":
+        return {"skipped": "no peer memory"}
     rng = np.random.default_rng(1)
     base = rng.integers(1, 6, (1000, nb), dtype=np.uint8)
     hist = base[rng.integers(0, 1000, n)]
     lens = np.full(n, 1000, np.uint64)
     ctx = api.Context(device)
     ctx.load_histograms(hist, lens, k)
+    del hist
     ctx.set_model(np.array([0, 0.5, 0, -1, 100.0]), np.array([100, 1, 4000, 1, 4000.0]), np.array([-1.0, 2, 1, 0.5, 0.5]), 4)
+    if world > 1:
+        handle = ctx.comm_init(rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        ctx.comm_connect(handles)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", device))
+    S4 = 8
     cr = np.array([11, 500_000, 999_999, 123_456, 654_321, 42, 777_777, 31_337], np.int64)
-    lo = np.zeros(8, np.int64)
-    hi = np.full(8, n - 1, np.int64)
-    ctx.scan_enqueue_many(cr, lo, hi, False, 0)
-    ctx.sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    ctx.scan_enqueue_many(cr, lo, hi, False, 0)
-    e1.record(stream)
-    ctx.sync()
-    us = e0.elapsed_time(e1) * 1e3 / 8
-    by = n * (nb + 33)
-    ach = by / (us * 1e-6) / 1e9
+    lo = np.zeros(S4, np.int64)
+    hi = np.full(S4, n - 1, np.int64)
+    inflight, last, cno = [], [None], [0]
+    e = np.zeros(0, np.int64)
+
+    def call(mode):
+        c = cno[0]
+        cno[0] += 1
+        if world == 1:
+            ctx.scan_enqueue_many(cr, lo, hi, mode, 0)
+            return
+        inflight.append(c)
+        if len(inflight) > 2:
+            old = inflight.pop(0)
+            last[0] = ctx.scan_sharded_burst(cr, lo, hi, mode, (c % 3) * 16, (old % 3) * 16, S4)
+        else:
+            ctx.scan_sharded_burst(cr, lo, hi, mode, (c % 3) * 16, 0, 0)
+
+    def drain():
+        while inflight:
+            old = inflight.pop(0)
+            last[0] = ctx.scan_sharded_burst(e, e, e, 0, 0, (old % 3) * 16, S4)
+
+    def run(mode, warm, calls):
+        for _ in range(warm):
+            call(mode)
+        drain()
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw = time.perf_counter()
+        e0.record(stream)
+        for _ in range(calls):
+            call(mode)
+        drain()
+        e1.record(stream)
+        ctx.sync()
+        ms = e0.elapsed_time(e1) if world == 1 else (time.perf_counter() - tw) * 1e3
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+            assert all(r[0] == n for r in last[0]), "c4 probe: sharded scan did not evaluate every point"
+        us = ms * 1e3 / (calls * S4)
+        by = n * (nb + 33)
+        ach = by / (us * 1e-6) / 1e9
+        return {"us_per_scan": round(us, 2), "evals_per_s": n / (us * 1e-6), "achieved_GBs": round(ach, 1),
+                "frac_of_n_gpu_peak": round(ach / (peak * world), 4)}
+
+    res = {"points": n, "bins": nb, "scaling": "strong: 1 M rows in total at every N",
+           "dependent_chain": run(api.MC_SCAN_CHAIN, 2, 8), "independent_scans": run(api.MC_SCAN_KEEP, 2, 8),
+           "note": "1.06 GB of rows per scan (> L2): every scan streams from HBM; timing = CUDA events (N = 1) / wall, max over ranks (N > 1)"}
     ctx.close()
-    return {"points": n, "bins": nb, "launch_us": round(us, 2), "evals_per_s": n / (us * 1e-6), "achieved_GBs": round(ach, 1),
-            "frac_of_peak": round(ach / peak, 4), "note": "1.06 GB of rows per launch (> L2): every launch streams from HBM"}
+    return res
 
 
 def reference_arm(args):

@@ -146,7 +146,14 @@ int mc_scan(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, mc_scan_res
 int mc_scan_enqueue(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int remove_marked,
                     int slot);
 int mc_scan_collect(mc_ctx *ctx, int slot0, int nslots, mc_scan_result *res);
-/* count scans enqueued back to back: scan i uses center_rows[i], [lo[i],hi[i]] and slot slot0+i */
+/* count scans enqueued back to back: scan i uses center_rows[i], [lo[i],hi[i]] and slot slot0+i.
+ * remove_marked: MC_SCAN_KEEP (0) the scans are independent (several of them may share a launch);
+ * MC_SCAN_REMOVE (1) every scan removes what it marks before the next one looks (accumulate()'s chain);
+ * MC_SCAN_CHAIN (2) the scans run as such a dependent chain (one launch per scan, each behind the one
+ * before it) but remove nothing -- the timing of MC_SCAN_REMOVE on an alive set that does not shrink. */
+#define MC_SCAN_KEEP 0
+#define MC_SCAN_REMOVE 1
+#define MC_SCAN_CHAIN 2
 int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, const int64_t *lo,
                          const int64_t *hi, int count, int remove_marked, int slot0);
 

@@ -37,6 +37,9 @@ EXPORTS = [
 ]
 
 
+MC_SCAN_KEEP, MC_SCAN_REMOVE, MC_SCAN_CHAIN = 0, 1, 2
+
+
 class ScanResult(C.Structure):
     _fields_ = [("n_eval", C.c_int64), ("n_pos", C.c_int64), ("best_row", C.c_int64), ("best_f0", C.c_double)]
 
@@ -240,8 +243,9 @@ class Context:
         cr = np.ascontiguousarray(center_rows, np.int64)
         lo = np.ascontiguousarray(lo, np.int64)
         hi = np.ascontiguousarray(hi, np.int64)
+        # remove_marked: False / True, or MC_SCAN_CHAIN (2): a dependent chain that removes nothing
         _check(_lib.mc_scan_enqueue_many(self._h, _p(cr), _p(lo), _p(hi), C.c_int(cr.size),
-                                         C.c_int(1 if remove_marked else 0), C.c_int(slot0)))
+                                         C.c_int(int(remove_marked)), C.c_int(slot0)))
 
     def scan_fold_dev(self, slot0: int, nslots: int, out_dev_ptr: int):
         """fold nslots scans into mc_scan_result records at a DEVICE address (e.g. tensor.data_ptr())"""
@@ -293,7 +297,7 @@ class Context:
         """arrays must already be contiguous int64 (this is the per-step call of a streaming caller)"""
         res = (ScanResult * max(prev_count, 1))()
         _check(_lib.mc_scan_sharded_burst(self._h, _p(cr), _p(lo), _p(hi), C.c_int(cr.size),
-                                          C.c_int(1 if remove_marked else 0), C.c_int(slot0), C.c_int(prev_slot0),
+                                          C.c_int(int(remove_marked)), C.c_int(slot0), C.c_int(prev_slot0),
                                           C.c_int(prev_count), C.byref(res)))
         return [res[i].as_tuple() for i in range(prev_count)]
 

@@ -640,7 +640,7 @@ extern "C" int mc_scan_enqueue_many(mc_ctx *ctx, const int64_t *center_rows, con
 		}
 	}
 	for (int i = 0; i < count; i++) {
-		const int rc = mc_scan_enqueue(ctx, center_rows[i], lo[i], hi[i], remove_marked, slot0 + i);
+		const int rc = mc_scan_enqueue(ctx, center_rows[i], lo[i], hi[i], remove_marked & MC_SCAN_REMOVE, slot0 + i);
 		if (rc) return rc;
 	}
 	return MC_OK;

@@ -453,7 +453,7 @@ extern "C" int mc_scan_sharded_burst(mc_ctx *ctx, const int64_t *center_rows, co
 				bargs.tag[slot] = cm.slot_uses[slot];
 				cm.slot_pending[slot] = 3;
 			}
-			rc = mc_launch_scan_batch(ctx, req, m, remove_marked, &ctx->slot_nparts[slot0 + i0], &push);
+			rc = mc_launch_scan_batch(ctx, req, m, remove_marked & MC_SCAN_REMOVE, &ctx->slot_nparts[slot0 + i0], &push);
 			if (rc) return rc;
 		}
 		if (dbg) tq2 = now();

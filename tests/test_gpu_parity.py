@@ -229,6 +229,11 @@ def test_scan_batch_launch_equals_single_scans(ctx, k, n, monkeypatch):
     assert got == want
     one = [ctx.scan_enqueue(int(cr[i]), int(lo[i]), int(hi[i]), False, 300 + i) for i in range(5)]
     assert ctx.scan_collect(300, 5) == want[:5]
+    monkeypatch.delenv("MC_SCAN_NO_BATCH")
+    # the same scans as a dependent chain that removes nothing (MC_SCAN_CHAIN)
+    from meshclust_b200 import api
+    ctx.scan_enqueue_many(cr, lo, hi, api.MC_SCAN_CHAIN, 400)
+    assert ctx.scan_collect(400, m) == want
 
 
 @pytest.mark.parametrize("dtype,k,n,nc", [(np.uint8, 4, 20000, 10), (np.uint8, 5, 9000, 3), (np.uint16, 3, 6000, 16), (np.uint8, 4, 3000, 4), (np.uint8, 2, 5000, 20)])
