@@ -25,7 +25,8 @@ size_t mc_acc_dev_bytes();
 int mc_launch_accumulate_tail(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart, const void *partials_dev, int nparts, void *acc_dev, void *out_host_dev, int32_t *list_host_dev, unsigned long long seq, const unsigned int *err_dev);
 int mc_launch_permute_rows(mc_ctx *ctx, const int32_t *old_of_new_dev, int64_t count, int64_t n_alive, void *hist_out, void *aux_out);
 int mc_launch_update_centers(mc_ctx *ctx, const int64_t *center_rows_dev, int64_t ncenters, const int64_t *cand_rows_dev, const int64_t *cand_begin_dev, const int64_t *cand_end_dev, const int64_t *flag_off_dev, uint8_t *flags_dev, long long *next_rows_dev);
-int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len, int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b, int64_t scratch_stride, int64_t nwarps);
+int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len, int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b, int64_t scratch_stride, int64_t nwarps, int rows_per_lane);
+int mc_nw_pick_rows(const int64_t *lb, int64_t m);
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
@@ -267,6 +268,7 @@ extern "C" int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int6
 	MC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->have_seq = true;
+	ctx->h_seq_off.assign(offsets, offsets + n + 1);
 	MC_REQUIRE(flags[0] == 0, MC_ERR_INPUT, "Invalid nucleotide in input (the reference throws InvalidInputException)");
 	return MC_OK;
 }
@@ -1164,12 +1166,18 @@ extern "C" int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, i
 	if (rc) return rc;
 	rc = check_rows32(ctx, b, m);
 	if (rc) return rc;
-	// longest seq1 among the pairs decides the scratch line
-	std::vector<int64_t> off((size_t)ctx->n + 1);
-	MC_CUDA(cudaMemcpyAsync(off.data(), ctx->d_seq_off, (size_t)(ctx->n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	// longest seq1 among the pairs decides the scratch line, the lengths of seq2 the strip height (the offsets are
+	// kept on the host since mc_load_sequences)
+	const std::vector<int64_t> &off = ctx->h_seq_off;
+	MC_REQUIRE((int64_t)off.size() == ctx->n + 1, MC_ERR_STATE, "mc_align_pairs: sequence offsets missing");
 	int64_t max_la = 0;
-	for (int64_t i = 0; i < m; i++) max_la = std::max(max_la, off[a[i] + 1] - off[a[i]]);
+	std::vector<int64_t> lbs((size_t)m);
+	for (int64_t i = 0; i < m; i++) {
+		max_la = std::max(max_la, off[a[i] + 1] - off[a[i]]);
+		lbs[(size_t)i] = off[b[i] + 1] - off[b[i]];
+	}
+	static const int force_rows = getenv("MC_NW_ROWS") ? atoi(getenv("MC_NW_ROWS")) : 0;
+	const int rows_per_lane = force_rows ? force_rows : mc_nw_pick_rows(lbs.data(), m);
 	const int64_t stride = align_up((size_t)max_la + 2, 32);
 	int64_t nwarps = std::min<int64_t>(m, (int64_t)ctx->num_sms * 32);
 	// keep the scratch under ~4 GB
@@ -1185,7 +1193,7 @@ extern "C" int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, i
 	MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(unsigned int), ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(d_a, a, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(d_b, b, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
-	rc = mc_launch_nw(ctx, d_a, d_b, m, max_la, d_s, d_l, d_i, d_sa, d_sb, stride, nwarps);
+	rc = mc_launch_nw(ctx, d_a, d_b, m, max_la, d_s, d_l, d_i, d_sa, d_sb, stride, nwarps, rows_per_lane);
 	if (rc) return rc;
 	unsigned int flags[4];
 	MC_CUDA(cudaMemcpyAsync(score, d_s, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -183,6 +183,7 @@ struct mc_ctx {
 	int64_t total_bases = 0;
 	uint8_t *d_seq = nullptr;      // letters, then digits in place
 	int64_t *d_seq_off = nullptr;  // n+1
+	std::vector<int64_t> h_seq_off; // the same on the host
 	int32_t *d_segs = nullptr;     // 2*nseg
 	int64_t *d_seg_off = nullptr;  // n+1
 	int64_t nseg = 0;

@@ -8,8 +8,10 @@
 // inside the lane).  Only the lane's LAST row travels to the lane below (__shfl_up, 6 words per
 // step for 32*R cells); lane 31's last row is parked in a global scratch line for lane 0 of the
 // next strip, which reads it back in coalesced 32-column chunks fetched one chunk ahead.
-// Each DP state carries (score, len, id); len and id travel packed as (len << 16) | id so a path
-// copy is one move and "+1 column [+1 match]" one add.  Requires la + lb <= 65535.
+// Each DP state carries (score, diag, id): every transition adds one column to the alignment, so its
+// length is i + j - (diagonal moves) and only the diagonal moves need counting; diag and id travel packed
+// as (diag << 16) | id: a gap move copies the word, a diagonal move adds (1 << 16) + match.  Both
+// counts are at most min(la, lb): requires min(la, lb) <= 65535.
 //
 // Tie-breaking is the reference's: U and L prefer "open from M" on ties (:178-193,:258-273),
 // M prefers M, then L, then U (:201-241), the final pick prefers M, L, U (:278-291), and the
@@ -18,14 +20,17 @@
 
 struct NwCell {
 	int m, u, l;          // scores
-	uint32_t pm, pu, pl;  // packed (len << 16) | id
+	uint32_t pm, pu, pl;  // packed (diagonal moves << 16) | id
 };
 
 constexpr int NW_OPEN_EXT = 3;   // gapOpen + gapContinue
 constexpr int NW_EXT = 1;        // gapContinue
 constexpr int NW_OPEN = 2;
 constexpr uint32_t NW_LEN1 = 0x10000u;
-constexpr int NW_R = 4;          // rows per lane
+// rows per lane: a template parameter.  One wavefront step costs ~125 instructions of bookkeeping (14 shuffles,
+// chunk hand-over, boundary store) next to ~26 per cell, so 4 rows per lane spend half of the issue slots
+// outside the recurrence; 16 rows per lane (strips of 512 rows, ~160 registers) leave 8 per cell.  Short
+// sequences keep the narrow strips (rows past the end of seq2 are wasted work): the launcher picks per batch.
 
 __device__ __forceinline__ NwCell nw_shfl_up(const NwCell &c) {
 	NwCell r;
@@ -49,13 +54,13 @@ __device__ __forceinline__ NwCell nw_shfl_from(const NwCell &c, int src) {
 	return r;
 }
 
-__global__ void __launch_bounds__(128)
+template <int R>
+__global__ void __launch_bounds__(128, R >= 16 ? 3 : 1)
 nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
           const int32_t *__restrict__ pa, const int32_t *__restrict__ pb, long long npairs,
           int4 *__restrict__ scratch_a, int2 *__restrict__ scratch_b, long long scratch_stride,
           int32_t *__restrict__ score_out, int32_t *__restrict__ len_out, int32_t *__restrict__ id_out,
           unsigned int *__restrict__ flags) {
-	constexpr int R = NW_R;
 	const int lane = threadIdx.x & 31;
 	const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -72,7 +77,7 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 		const int shorter = min(la, lb), diff = abs(la - lb);
 		const int ninf = (diff >= 1 ? -NW_OPEN - diff * NW_EXT : 0) - shorter - 1;
 
-		if (la + lb > 65535) {   // packed len/id would overflow; reported to the host
+		if (shorter > 65535) {   // the packed counters would overflow; reported to the host
 			if (lane == 0) { atomicOr(&flags[2], 1u); score_out[pr] = 0; len_out[pr] = 0; id_out[pr] = 0; }
 			continue;
 		}
@@ -112,13 +117,13 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 				// column 0 of row j: M = L = ninf with len j; U[0] as the row below synthesises it
 				// (GlobAlignE.cpp:164-170,250-256)
 				left[r].m = ninf; left[r].l = ninf; left[r].u = -NW_OPEN - j * NW_EXT;
-				left[r].pm = left[r].pl = left[r].pu = (uint32_t)j << 16;
+				left[r].pm = left[r].pl = left[r].pu = 0;   // j vertical moves, no diagonal
 			}
 			// column 0 of row j0-1
 			diag0.m = (j0 == 1) ? 0 : ninf;
 			diag0.l = ninf;
 			diag0.u = -NW_OPEN - (j0 - 1) * NW_EXT;
-			diag0.pm = diag0.pl = diag0.pu = (uint32_t)(j0 - 1) << 16;
+			diag0.pm = diag0.pl = diag0.pu = 0;
 			NwCell mine;   // last row's newest cell, published to the lane below
 			mine.m = 0; mine.u = 0; mine.l = 0; mine.pm = 0; mine.pu = 0; mine.pl = 0;
 			uint32_t achunk = 0, achar = 0;
@@ -165,7 +170,7 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 				} else if (lane == 0) {
 					// init row (GlobAlignE.cpp:137-160)
 					up.m = ninf; up.u = ninf; up.l = -NW_OPEN - i * NW_EXT;
-					up.pm = up.pu = up.pl = (uint32_t)i << 16;
+					up.pm = up.pu = up.pl = 0;
 				}
 				if (i >= 1 && i <= la) {
 					NwCell dg = diag0;   // diagonal of the row being filled
@@ -173,23 +178,21 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 #pragma unroll
 					for (int r = 0; r < R; r++) {
 						// vertical gap: from (row-1, i)
-						const int ub = up.m - NW_OPEN_EXT, uc = up.u - NW_EXT;
-						const bool ubeg = ub >= uc;
+						// (DPX: VIMNMX with the predicate "first operand won" / three-input maximum)
 						NwCell cur;
-						cur.u = ubeg ? ub : uc;
-						cur.pu = (ubeg ? up.pm : up.pu) + NW_LEN1;
+						bool ubeg;
+						cur.u = __vibmax_s32(up.m - NW_OPEN_EXT, up.u - NW_EXT, &ubeg);   // ties open from M
+						cur.pu = ubeg ? up.pm : up.pu;
 						// diagonal: from (row-1, i-1), tie order M, L, U
-						const bool eq = achar == (uint32_t)bj[r];
-						int best = dg.m; uint32_t pbst = dg.pm;
-						if (dg.l > best) { best = dg.l; pbst = dg.pl; }
-						if (dg.u > best) { best = dg.u; pbst = dg.pu; }
-						cur.m = best + (eq ? 1 : -1);
-						cur.pm = pbst + NW_LEN1 + (eq ? 1u : 0u);
+						const int best = __vimax3_s32(dg.m, dg.l, dg.u);
+						const uint32_t pbst = dg.m == best ? dg.pm : (dg.l == best ? dg.pl : dg.pu);
+						cur.m = best - 1;
+						cur.pm = pbst + NW_LEN1;
+						if (achar == (uint32_t)bj[r]) { cur.m += 2; cur.pm += 1u; }   // two predicated adds
 						// horizontal gap on the current row: from (row, i-1)
-						const int hb = left[r].m - NW_OPEN_EXT, hc = left[r].l - NW_EXT;
-						const bool hbeg = hb >= hc;
-						cur.l = hbeg ? hb : hc;
-						cur.pl = (hbeg ? left[r].pm : left[r].pl) + NW_LEN1;
+						bool hbeg;
+						cur.l = __vibmax_s32(left[r].m - NW_OPEN_EXT, left[r].l - NW_EXT, &hbeg);
+						cur.pl = hbeg ? left[r].pm : left[r].pl;
 						// roll: (row, i-1) is the diagonal of the row below; this cell the left of (row, i+1)
 						dg = left[r];
 						left[r] = cur;
@@ -221,21 +224,46 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 		res_p = __shfl_sync(MC_FULL_MASK, res_p, owner);
 		if (lane == 0) {
 			score_out[pr] = res_sc;
-			len_out[pr] = (int32_t)(res_p >> 16);
+			len_out[pr] = la + lb - (int32_t)(res_p >> 16);
 			id_out[pr] = (int32_t)(res_p & 0xffffu);
 		}
 	}
 }
 
-// scratch: two lines of scratch_stride >= max_len + 1 columns per resident warp
+// scratch: two lines of scratch_stride >= max_len + 1 columns per resident warp.
+// rows_per_lane: 4, 8 or 16 (strips of 128 / 256 / 512 rows of seq2)
 int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len,
                  int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b,
-                 int64_t scratch_stride, int64_t nwarps) {
+                 int64_t scratch_stride, int64_t nwarps, int rows_per_lane) {
 	const int threads = 128;
 	const int64_t blocks = (nwarps * 32 + threads - 1) / threads;
 	(void)max_len;
-	nw_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, pa_dev, pb_dev, m, (int4 *)scratch_a, (int2 *)scratch_b, scratch_stride, score_dev, len_dev, id_dev, ctx->d_flags);
+#define NW_LAUNCH(RR) nw_kernel<RR><<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, pa_dev, pb_dev, m, (int4 *)scratch_a, (int2 *)scratch_b, scratch_stride, score_dev, len_dev, id_dev, ctx->d_flags)
+	switch (rows_per_lane) {
+	case 16: NW_LAUNCH(16); break;
+	case 8: NW_LAUNCH(8); break;
+	default: NW_LAUNCH(4); break;
+	}
+#undef NW_LAUNCH
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
+}
+
+// the strip height that wastes the fewest issue slots on a batch: cost per real cell ~ (rows a strip pads the
+// pair to) x (recurrence + per-step bookkeeping / rows per lane)
+int mc_nw_pick_rows(const int64_t *lb, int64_t m) {
+	int best = 4;
+	double best_cost = 0;
+	for (int r : {4, 8, 16}) {
+		double padded = 0, real = 0;
+		const int64_t strip = 32 * r;
+		for (int64_t i = 0; i < m; i++) {
+			padded += (double)((lb[i] + strip - 1) / strip * strip);
+			real += (double)lb[i];
+		}
+		const double cost = (real > 0 ? padded / real : 1.0) * (26.0 + 125.0 / r);
+		if (r == 4 || cost < best_cost) { best = r; best_cost = cost; }
+	}
+	return best;
 }
