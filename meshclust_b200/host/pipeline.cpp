@@ -202,7 +202,18 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	// search is a chain of ~log2(n/4) dependent rounds.  So every batch aligns, per pivot, all the
 	// positions the next SPEC rounds can reach (2^SPEC - 1 of them), and the rounds are then replayed
 	// from the answers exactly as the reference takes them; the unused answers are discarded.
-	constexpr int SPEC = 4;
+	// How far to look ahead: a round of short pairs is launch latency, so 4 levels (15 positions per pivot);
+	// long pairs fill the GPU with far fewer of them (one warp per pair, ~1800 resident warps), and every
+	// position beyond that is a second wave of work most of which is thrown away: 3 levels then (7 per pivot).
+	int SPEC = 4;
+	{
+		double mean_len = 0;
+		for (size_t i = 0; i < np; i++) mean_len += (double)(ds.fa.offsets[(size_t)pivots[i] + 1] - ds.fa.offsets[(size_t)pivots[i]]);
+		mean_len /= (double)std::max<size_t>(np, 1);
+		if (mean_len * mean_len > 1e7)
+			while (SPEC > 1 && np * ((size_t)(1 << SPEC) - 1) > 1800) SPEC--;
+		if (getenv("MC_SPLIT_SPEC")) SPEC = std::max(1, std::min(6, atoi(getenv("MC_SPLIT_SPEC"))));
+	}
 	std::vector<size_t> offset(np, (size_t)n / 4), pos(np, 2 * ((size_t)n / 4));
 	std::vector<char> active(np, 1);
 	for (size_t i = 0; i < np; i++) active[i] = offset[i] > 0;
