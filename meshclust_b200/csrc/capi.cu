@@ -12,6 +12,7 @@
 // kernel launchers (defined in the other translation units)
 int mc_upload_lut();
 int mc_launch_encode(mc_ctx *ctx);
+int mc_launch_validate(mc_ctx *ctx);
 int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes);
 int mc_launch_point_stats(mc_ctx *ctx, const uint64_t *lens_dev);
 int mc_launch_point_stats_range(mc_ctx *ctx, int64_t row0, int64_t n, const uint64_t *lens_dev, cudaStream_t stream);
@@ -262,7 +263,10 @@ extern "C" int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int6
 	MC_CUDA(cudaMemcpyAsync(ctx->d_seg_off, seg_offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
 	if (nseg) MC_CUDA(cudaMemcpyAsync(ctx->d_segs, segs, (size_t)nseg * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
 	MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(unsigned int), ctx->stream));
-	int rc = mc_launch_encode(ctx);
+	// the letters stay letters: K1 counts them in one pass; the digit strings the aligner reads are made by
+	// the in-place encode pass when they are first asked for (ensure_digits).  Invalid letters are reported now.
+	ctx->digits_ready = false;
+	int rc = mc_launch_validate(ctx);
 	if (rc) return rc;
 	unsigned int flags[4];
 	MC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
@@ -273,8 +277,23 @@ extern "C" int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int6
 	return MC_OK;
 }
 
+// ChromosomeOneDigit::encodeNucleotides (ChromosomeOneDigit.cpp:95-144) over the whole buffer, in place, once
+static int ensure_digits(mc_ctx *ctx) {
+	if (ctx->digits_ready) return MC_OK;
+	MC_CUDA(cudaSetDevice(ctx->device));
+	const int rc = mc_launch_encode(ctx);
+	if (rc) return rc;
+	ctx->digits_ready = true;
+	return MC_OK;
+}
+
 extern "C" int mc_copy_digits(mc_ctx *ctx, uint8_t *out) {
 	MC_REQUIRE(ctx && out, MC_ERR_ARG, "bad arguments");
+	MC_REQUIRE(ctx->have_seq, MC_ERR_STATE, "mc_copy_digits: load sequences first");
+	{
+		const int rc = ensure_digits(ctx);
+		if (rc) return rc;
+	}
 	MC_REQUIRE(ctx->have_seq, MC_ERR_STATE, "no sequences loaded");
 	MC_CUDA(cudaSetDevice(ctx->device));
 	MC_CUDA(cudaMemcpyAsync(out, ctx->d_seq, (size_t)ctx->total_bases, cudaMemcpyDeviceToHost, ctx->stream));
@@ -326,10 +345,22 @@ extern "C" int mc_build_histograms(mc_ctx *ctx, int k, int tbytes, int *tbytes_o
 		int rc = alloc_hist(ctx, ctx->n, k, use);
 		if (rc) return rc;
 		MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(unsigned int), ctx->stream));
+		static const bool dbg = getenv("MC_DEBUG_TIMING") != nullptr;
+		cudaEvent_t e0 = nullptr, e1 = nullptr;
+		if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
 		rc = mc_launch_kmer_hist(ctx, k, use);
 		if (rc) return rc;
+		if (dbg) cudaEventRecord(e1, ctx->stream);
 		MC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
 		MC_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (dbg) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, e0, e1);
+			const double by = (double)ctx->total_bases + (double)ctx->n * ctx->nbins * use;
+			fprintf(stderr, "[mc_build_histograms] kmer_count_kernel k=%d, %d-byte bins: %.1f us on the device, %.0f GB/s of %.1f MB (letters read + histograms written)\n",
+			        k, use, ms * 1e3, by / (ms * 1e-3) / 1e9, by / 1e6);
+			cudaEventDestroy(e0); cudaEventDestroy(e1);
+		}
 		// Runner.cpp:75-89: the width is the smallest that holds the largest bin
 		const int needed = flags[1] <= 0xffu ? 1 : (flags[1] <= 0xffffu ? 2 : 4);
 		if (needed > 2) {
@@ -483,6 +514,8 @@ static int pair_list_common(mc_ctx *ctx, const int32_t *a, const int32_t *b, int
 	int rc = check_rows32(ctx, a, m);
 	if (rc) return rc;
 	rc = check_rows32(ctx, b, m);
+	if (rc) return rc;
+	rc = ensure_digits(ctx);
 	if (rc) return rc;
 	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)m * 4, (size_t)m * 4, (size_t)m * 40, (size_t)m * 8, (size_t)m * 8, (size_t)m * 8, (size_t)m, (size_t)m * 32}));
 	if (rc) return rc;
@@ -1165,6 +1198,8 @@ extern "C" int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, i
 	int rc = check_rows32(ctx, a, m);
 	if (rc) return rc;
 	rc = check_rows32(ctx, b, m);
+	if (rc) return rc;
+	rc = ensure_digits(ctx);
 	if (rc) return rc;
 	// longest seq1 among the pairs decides the scratch line, the lengths of seq2 the strip height (the offsets are
 	// kept on the host since mc_load_sequences)

@@ -3,10 +3,9 @@
 // fill_table / KmerHashTable::wholesaleIncrement (ClusterFactory.h:40-55,
 // KmerHashTable.cpp:133-223) with the pseudo-count of ClusterFactory.cpp:995.
 //
-// One warp per sequence.  Bases are read with aligned 16-byte loads (the sequence start is
-// aligned down, leading bytes masked), each lane rolls the base-4 index over its 16 k-mer starts
-// and increments a per-warp shared-memory table with ATOMS; the table is then written once,
+// One warp per sequence, one pass over the LETTERS (kmer_count_kernel below); the table is written once,
 // narrowed to the output width, together with mag = sum, sum of squares and the running maximum.
+// The in-place encode to digit strings (what the aligner reads) runs lazily, mc_ensure_digits.
 #include "mc_common.cuh"
 
 // code LUT: 0..3 digit, 4 = 'N', 0xff = invalid   (ChromosomeOneDigit.cpp:59-85)
@@ -119,19 +118,66 @@ int mc_launch_encode(mc_ctx *ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// histogram: WPB warps per block, each with a private 4^k-entry uint32 table in shared memory
+// K1, one pass: letters -> 2-bit codes in registers -> k-mer counts.  One warp per sequence.
+// A lane takes 16 letters (one aligned 16-byte load) and packs them into one 32-bit word, first base
+// in the two most significant bits; with the word of the next 16 letters (the lane above, or lane 0 of
+// the next round for lane 31) the k-mer that starts at letter j is the top 2k bits of the 64-bit
+// window shifted left by 2j: a funnel shift and a shift per k-mer, then one shared-memory reduction
+// into the warp's table.  Plain ACGT / acgt words are coded with three logic operations per four
+// letters and checked with one byte permute against the letters the codes stand for; any other word
+// (IUPAC codes, N inside a merged segment -> C, digit strings of an already encoded buffer) goes
+// through the 256-entry table.  The digit strings the aligner wants are NOT written here: the in-place
+// encode pass runs when the first alignment (or mc_copy_digits) asks for them.
+// Bytes: L letters read + 4^k * sizeof(T) written per sequence.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t k1_codes4(uint32_t w, const uint8_t *lut, bool &fast) {
+	// A 0x41 C 0x43 G 0x47 T 0x54: bits 2..1 are 00 01 11 10 -> code = x ^ (x >> 1)
+	uint32_t x = (w >> 1) & 0x03030303u;
+	x ^= (x >> 1) & 0x01010101u;
+	// the letters these codes stand for, picked from "ACGT" by one byte permute (selector = code per nibble)
+	const uint32_t s = x | (x >> 4);
+	const uint32_t sel = (s & 0xffu) | ((s >> 8) & 0xff00u);
+	fast = __byte_perm(0x54474341u, 0u, sel) == (w & 0xdfdfdfdfu);
+	if (!fast) {
+		x = (uint32_t)(lut[w & 0xffu] & 3u) | ((uint32_t)(lut[(w >> 8) & 0xffu] & 3u) << 8) |
+		    ((uint32_t)(lut[(w >> 16) & 0xffu] & 3u) << 16) | ((uint32_t)(lut[w >> 24] & 3u) << 24);
+	}
+	return x;
+}
+
+// four codes (one per byte, first letter in byte 0) -> 8 bits, first letter in the top two
+__device__ __forceinline__ uint32_t k1_pack4(uint32_t x) {
+	const uint32_t r = __byte_perm(x, 0u, 0x0123u);   // first letter into the most significant byte
+	const uint32_t y = r | (r >> 6);
+	return (y & 0xfu) | ((y >> 12) & 0xf0u);
+}
+
+__device__ __forceinline__ uint32_t k1_pack16(const uint4 v, const uint8_t *lut) {
+	bool f0, f1, f2, f3;
+	const uint32_t a = k1_pack4(k1_codes4(v.x, lut, f0)), b = k1_pack4(k1_codes4(v.y, lut, f1));
+	const uint32_t c = k1_pack4(k1_codes4(v.z, lut, f2)), d = k1_pack4(k1_codes4(v.w, lut, f3));
+	return (a << 24) | (b << 16) | (c << 8) | d;
+}
+
 template <int TB>
-__global__ void kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
-                                 const int32_t *__restrict__ segs, const int64_t *__restrict__ seg_off,
-                                 long long n, int k, uint8_t *__restrict__ hist,
-                                 McRowAux *__restrict__ aux_out, unsigned int *__restrict__ flags) {
+__global__ void __launch_bounds__(256)
+kmer_count_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
+                  const int32_t *__restrict__ segs, const int64_t *__restrict__ seg_off,
+                  long long n, int k, uint8_t *__restrict__ hist,
+                  McRowAux *__restrict__ aux_out, unsigned int *__restrict__ flags) {
 	extern __shared__ uint32_t tables[];
+	__shared__ uint8_t lut[256];
+	// N swallowed by a merged segment counts as C (ChromosomeOneDigit.cpp:59-85); digits stay what they are
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+		const uint8_t c = c_code_lut[i];
+		lut[i] = i < 4 ? (uint8_t)i : (c == 4 ? 1 : c);
+	}
+	__syncthreads();
 	const int nbins = 1 << (2 * k);
-	const uint32_t mask = (uint32_t)nbins - 1u;
 	const int lane = threadIdx.x & 31;
 	const int wib = threadIdx.x >> 5;
 	uint32_t *tab = tables + (size_t)wib * nbins;
+	const int top = 32 - 2 * k;   // the k-mer is the top 2k bits of the shifted window
 	const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
 	const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
 	unsigned int local_max = 0;
@@ -144,23 +190,32 @@ __global__ void kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t 
 			// k-mer starts [ss, last] inside this segment (absolute byte positions)
 			const long long ss = b0 + segs[2 * gi];
 			const long long last = b0 + (long long)segs[2 * gi + 1] - k + 1;
+			if (last < ss) continue;
 			const long long a0 = ss & ~15LL;
-			for (long long base = a0 + lane * 16; base <= last; base += 32 * 16) {
-				// 32-byte window: own 16 bytes + the following 16 (k-1 <= 15 look-ahead)
-				const uint4 v0 = *reinterpret_cast<const uint4 *>(seq + base);
-				uint4 v1 = make_uint4(0, 0, 0, 0);
-				if (base + 16 < b1) v1 = *reinterpret_cast<const uint4 *>(seq + base + 16);
-				const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-				uint32_t idx = 0;
+			const long long nchunks = ((last - a0) >> 4) + 1;   // chunks with a k-mer start
+			// word of chunk c (letters a0 + 16c ...); chunks past the buffer's 64-byte tail are never needed
+			auto chunk_word = [&](long long c) -> uint32_t {
+				const long long base = a0 + 16 * c;
+				if (base >= b1) return 0u;
+				return k1_pack16(*reinterpret_cast<const uint4 *>(seq + base), lut);
+			};
+			uint32_t pn = chunk_word(lane);
+			for (long long c0 = 0; c0 < nchunks; c0 += 32) {
+				const uint32_t pc = pn;
+				pn = chunk_word(c0 + 32 + lane);   // next round's word, also lane 31's neighbour
+				uint32_t nb = __shfl_down_sync(MC_FULL_MASK, pc, 1);
+				const uint32_t n0 = __shfl_sync(MC_FULL_MASK, pn, 0);
+				if (lane == 31) nb = n0;
+				const long long c = c0 + lane;
+				if (c < nchunks) {
+					const long long base = a0 + 16 * c;
+					if (base >= ss && base + 15 <= last) {
 #pragma unroll
-				for (int u = 0; u < 31; u++) {
-					uint32_t d = (w[u >> 2] >> ((u & 3) * 8)) & 0xffu;
-					d = (d == (uint32_t)'N') ? 1u : d;   // N swallowed by a merged segment counts as C
-					idx = ((idx << 2) | (d & 3u)) & mask;
-					const int t = u - (k - 1);           // start (within the window) of the k-mer ending at u
-					if (t >= 0 && t < 16) {
-						const long long pos = base + t;
-						if (pos >= ss && pos <= last) atomicAdd(&tab[idx], 1u);
+						for (int j = 0; j < 16; j++) atomicAdd(&tab[__funnelshift_l(nb, pc, 2 * j) >> top], 1u);
+					} else {
+#pragma unroll
+						for (int j = 0; j < 16; j++)
+							if (base + j >= ss && base + j <= last) atomicAdd(&tab[__funnelshift_l(nb, pc, 2 * j) >> top], 1u);
 					}
 				}
 			}
@@ -172,7 +227,8 @@ __global__ void kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t 
 			uint8_t *row = hist + (size_t)s * nbins;
 			if (nbins >= 128) {
 				for (int i = lane * 4; i < nbins; i += 128) {
-					const uint32_t c0 = tab[i] + 1, c1 = tab[i + 1] + 1, c2 = tab[i + 2] + 1, c3 = tab[i + 3] + 1;
+					const uint4 t = *reinterpret_cast<const uint4 *>(tab + i);
+					const uint32_t c0 = t.x + 1, c1 = t.y + 1, c2 = t.z + 1, c3 = t.w + 1;
 					local_max = max(max(local_max, c0), max(c1, max(c2, c3)));
 					m += c0 + c1 + c2 + c3;
 					q += (unsigned long long)c0 * c0 + (unsigned long long)c1 * c1 + (unsigned long long)c2 * c2 + (unsigned long long)c3 * c3;
@@ -216,6 +272,46 @@ __global__ void kmer_hist_kernel(const uint8_t *__restrict__ seq, const int64_t 
 	if (lane == 0 && local_max) atomicMax(&flags[1], local_max);
 }
 
+// ---------------------------------------------------------------------------------------------
+// validation at load time: every letter must be one the reference encodes (ChromosomeOneDigit.cpp:59-85);
+// flags[0] is set otherwise (the reference throws InvalidInputException).  Read-only.
+// ---------------------------------------------------------------------------------------------
+__global__ void validate_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
+                                const int64_t *__restrict__ seg_off, long long n, unsigned int *__restrict__ flags) {
+	__shared__ uint8_t lut[256];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = c_code_lut[i];
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+	bool bad = false;
+	for (long long s = warp; s < n; s += nwarps) {
+		if (seg_off[s + 1] == seg_off[s]) continue;   // no segment: encodeNucleotides touches nothing (and checks nothing)
+		const long long b0 = seq_off[s], b1 = seq_off[s + 1];
+		for (long long base = (b0 & ~15LL) + lane * 16; base < b1; base += 32 * 16) {
+			const uint4 x = *reinterpret_cast<const uint4 *>(seq + base);
+			const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+			for (int j = 0; j < 16; j++) {
+				const uint32_t ch = (w[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+				if (base + j >= b0 && base + j < b1 && lut[ch] == 0xffu) bad = true;
+			}
+		}
+	}
+	if (__any_sync(MC_FULL_MASK, bad) && lane == 0) atomicOr(&flags[0], 1u);
+}
+
+int mc_launch_validate(mc_ctx *ctx) {
+	const int threads = 256;
+	int64_t blocks = (ctx->n * 32 + threads - 1) / threads;
+	if (blocks > (int64_t)ctx->num_sms * 16) blocks = (int64_t)ctx->num_sms * 16;
+	if (blocks < 1) blocks = 1;
+	validate_kernel<<<(int)blocks, threads, 0, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_seg_off, ctx->n, ctx->d_flags);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
 int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes) {
 	const int nbins = 1 << (2 * k);
 	const size_t per_warp = (size_t)nbins * 4;
@@ -229,11 +325,11 @@ int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes) {
 	if (blocks > cap) blocks = cap;
 	if (blocks < 1) blocks = 1;
 	if (tbytes == 1) {
-		if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kmer_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kmer_hist_kernel<1><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_flags);
+		if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kmer_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		kmer_count_kernel<1><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_flags);
 	} else {
-		if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kmer_hist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kmer_hist_kernel<2><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_flags);
+		if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kmer_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		kmer_count_kernel<2><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_flags);
 	}
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());

@@ -181,7 +181,8 @@ struct mc_ctx {
 	// sequences
 	int64_t n = 0;            // rows
 	int64_t total_bases = 0;
-	uint8_t *d_seq = nullptr;      // letters, then digits in place
+	uint8_t *d_seq = nullptr;      // letters; digits in place once an aligner asked for them
+	bool digits_ready = false;
 	int64_t *d_seq_off = nullptr;  // n+1
 	std::vector<int64_t> h_seq_off; // the same on the host
 	int32_t *d_segs = nullptr;     // 2*nseg

@@ -3,6 +3,7 @@
 // calls of Trainer::split's sort comparators.  HBM-bound byte work: one pass over the histogram
 // rows with 16-byte streaming loads, SIMD-in-word integer reductions, FP64 epilogue on all lanes.
 #include "pair_core.cuh"
+#include "tma_utils.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // per-point constants
@@ -275,7 +276,160 @@ dist_keys_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ 
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2b as a tile: C centers x all rows with every row read ONCE.  The centers of a group (all C of them
+// when C * row bytes fit shared memory: 150 KB for 150 centers at k = 5) are staged in shared memory with
+// 1-D bulk copies (cp.async.bulk, one per center); a warp keeps one row in registers (lane l owns bytes
+// [l * RB/32, (l+1) * RB/32)), runs it against 32 centers at a time -- lane-private partial sums of
+// |p - q| per center -- and a transposing reduction (31 shuffles for 32 centers) leaves the total of center c
+// in lane c, which computes the key.  DRAM traffic = n * 4^k (+ keys), not C times that.
+// Sum min(p, q) = (mag_p + mag_q - sum |p - q|) / 2 exactly.
+// ---------------------------------------------------------------------------------------------
+struct AbsAcc {
+	uint32_t a;
+	__device__ __forceinline__ void shfl_add_from(const AbsAcc &send, int mask) { a += __shfl_xor_sync(MC_FULL_MASK, send.a, mask); }
+};
+
+template <int TB>
+__device__ __forceinline__ uint32_t absdiff_acc(uint32_t p, uint32_t q, uint32_t acc) {
+	if constexpr (TB == 1) {
+		asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc) : "r"(p), "r"(q));
+		return acc;
+	} else {
+		// two 16-bit bins per word: |a - b| = max - min
+		const uint32_t mx = __vmaxu2(p, q), mn = __vminu2(p, q), d = mx - mn;   // no borrow across the halves: max >= min in each
+		return acc + (d & 0xffffu) + (d >> 16);
+	}
+}
+
+constexpr int TILE_THREADS = 256;
+
+template <int TB, int RB>
+__global__ void __launch_bounds__(TILE_THREADS)
+dist_keys_tile_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ aux, long long n,
+                      const int32_t *__restrict__ center_rows, int C, int group, uint16_t *__restrict__ keys) {
+	constexpr int W = RB / 128;   // 32-bit words of a row per lane
+	static_assert(W >= 1, "the tile kernel wants rows of 128 bytes and more");
+	extern __shared__ __align__(128) uint8_t tsm[];
+	__shared__ __align__(8) uint64_t bar;
+	uint8_t *cen = tsm;                                                      // group x RB
+	unsigned long long *cmag = reinterpret_cast<unsigned long long *>(tsm + (size_t)group * RB);   // group
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const long long nwarps = (long long)gridDim.x * (TILE_THREADS / 32);
+	const long long warp = (long long)blockIdx.x * (TILE_THREADS / 32) + wib;
+	if (threadIdx.x == 0) {
+		mbar_init(&bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncthreads();
+	uint32_t phase = 0;
+	for (int g0 = 0; g0 < C; g0 += group) {
+		const int gn = min(group, C - g0);
+		const int gpad = (gn + 31) & ~31;   // whole blocks of 32 centers: the padding repeats the group's first center
+		if (threadIdx.x == 0) {
+			mbar_expect_tx(&bar, (uint32_t)gpad * RB);
+			for (int c = 0; c < gpad; c++) {
+				const long long crow = center_rows[g0 + (c < gn ? c : 0)];
+				tma_bulk_g2s(cen + (size_t)c * RB, hist + (size_t)crow * RB, RB, &bar);
+			}
+		}
+		for (int c = threadIdx.x; c < gpad; c += TILE_THREADS) cmag[c] = aux[center_rows[g0 + (c < gn ? c : 0)]].mag;
+		mbar_wait(&bar, phase);
+		phase ^= 1;
+		__syncthreads();
+		for (long long row = warp; row < n; row += nwarps) {
+			uint32_t rw[W];
+			const uint32_t *src = reinterpret_cast<const uint32_t *>(hist + (size_t)row * RB) + lane * W;
+			if constexpr (W >= 4) {
+#pragma unroll
+				for (int w = 0; w < W; w += 4) {
+					const uint4 v = mc_ld_stream16(src + w);
+					rw[w] = v.x; rw[w + 1] = v.y; rw[w + 2] = v.z; rw[w + 3] = v.w;
+				}
+			} else {
+#pragma unroll
+				for (int w = 0; w < W; w++) rw[w] = __ldg(src + w);
+			}
+			const unsigned long long mp = aux[row].mag;
+			for (int sub = 0; sub < gpad; sub += 32) {
+				AbsAcc acc[32];
+#pragma unroll
+				for (int c = 0; c < 32; c++) {
+					const uint32_t *q = reinterpret_cast<const uint32_t *>(cen + (size_t)(sub + c) * RB) + lane * W;
+					uint32_t a = 0;
+					if constexpr (W >= 4) {
+#pragma unroll
+						for (int w = 0; w < W; w += 4) {
+							const uint4 v = *reinterpret_cast<const uint4 *>(q + w);
+							a = absdiff_acc<TB>(rw[w], v.x, a); a = absdiff_acc<TB>(rw[w + 1], v.y, a);
+							a = absdiff_acc<TB>(rw[w + 2], v.z, a); a = absdiff_acc<TB>(rw[w + 3], v.w, a);
+						}
+					} else {
+#pragma unroll
+						for (int w = 0; w < W; w++) a = absdiff_acc<TB>(rw[w], q[w], a);
+					}
+					acc[c].a = a;
+				}
+				const AbsAcc tot = mc_transpose_reduce<32>(acc, lane);   // lane c: center sub + c
+				const int c = sub + lane;
+				if (c < gn) {
+					const unsigned long long mq = cmag[c];
+					const unsigned long long S = (mp + mq - (unsigned long long)tot.a) >> 1;
+					keys[(size_t)(g0 + c) * n + row] = (uint16_t)mc_distance_key(S, mp + mq);
+				}
+			}
+		}
+		__syncthreads();   // every warp is done with this group's centers before the next group lands
+	}
+}
+
+template <int TB, int RB>
+static int launch_keys_tile(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint16_t *keys_dev) {
+	int dev_smem = 0;
+	MC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+	// centers per group: whole blocks of 32, as many as shared memory holds (row + 8 bytes each)
+	int group = (int)(((size_t)dev_smem - 2048) / ((size_t)RB + 8)) & ~31;
+	const int cpad = (C + 31) & ~31;
+	if (group > cpad) group = cpad;
+	MC_REQUIRE(group >= 32, MC_ERR_UNSUPPORTED, "rows of %d bytes: 32 centers do not fit shared memory", RB);
+	const size_t smem = (size_t)group * ((size_t)RB + 8);
+	MC_CUDA(cudaFuncSetAttribute(dist_keys_tile_kernel<TB, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 1;
+	MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dist_keys_tile_kernel<TB, RB>, TILE_THREADS, smem));
+	if (per_sm < 1) per_sm = 1;
+	int64_t blocks = (int64_t)ctx->num_sms * per_sm;
+	const int64_t need = (ctx->n + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32);
+	if (blocks > need) blocks = need;
+	if (blocks < 1) blocks = 1;
+	dist_keys_tile_kernel<TB, RB><<<(unsigned)blocks, TILE_THREADS, smem, ctx->stream>>>((const uint8_t *)ctx->d_hist, ctx->d_aux, ctx->n, center_rows_dev, C, group, keys_dev);
+	ctx->launches++;
+	MC_CUDA(cudaGetLastError());
+	return MC_OK;
+}
+
 int mc_launch_dist_keys(mc_ctx *ctx, const int32_t *center_rows_dev, int C, uint16_t *keys_dev) {
+	// several centers against rows of 128 bytes and more: the tile kernel (every row read once)
+	static const bool no_tile = getenv("MC_KEYS_NO_TILE") != nullptr;
+	const int rbytes = ctx->tbytes * ctx->nbins;
+	if (!no_tile && C >= 4 && rbytes >= 128 && rbytes <= 4096) {
+		if (ctx->tbytes == 1) {
+			switch (rbytes) {
+			case 256: return launch_keys_tile<1, 256>(ctx, center_rows_dev, C, keys_dev);
+			case 1024: return launch_keys_tile<1, 1024>(ctx, center_rows_dev, C, keys_dev);
+			case 4096: return launch_keys_tile<1, 4096>(ctx, center_rows_dev, C, keys_dev);
+			default: break;
+			}
+		} else {
+			switch (rbytes) {
+			case 128: return launch_keys_tile<2, 128>(ctx, center_rows_dev, C, keys_dev);
+			case 512: return launch_keys_tile<2, 512>(ctx, center_rows_dev, C, keys_dev);
+			case 2048: return launch_keys_tile<2, 2048>(ctx, center_rows_dev, C, keys_dev);
+			default: break;
+			}
+		}
+	}
+
 	int64_t blocks = (ctx->n + SCAN_THREADS - 1) / SCAN_THREADS;
 	const int64_t cap = (int64_t)ctx->num_sms * 4;
 	if (blocks > cap) blocks = cap;
