@@ -110,7 +110,9 @@ extern "C" int mc_ctx_create(mc_ctx **out, int device) {
 	ctx->device = device;
 	cudaDeviceProp prop;
 	MC_CUDA(cudaGetDeviceProperties(&prop, device));
-	ctx->num_sms = prop.multiProcessorCount;
+	// the per-scan record buffers (result slots, inboxes, tag-polled copies) hold MC_SCAN_PARTS entries per scan and
+	// every kernel sizes its grid from num_sms: a part with more SMs uses MC_SCAN_PARTS of them for these kernels
+	ctx->num_sms = std::min<int>(prop.multiProcessorCount, MC_SCAN_PARTS);
 	lap("cudaGetDeviceProperties");
 	MC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	ctx->own_stream = ctx->stream;
@@ -1024,6 +1026,7 @@ extern "C" int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_
 		MC_REQUIRE(c->comm.world == world && c->comm.rank == r && c->comm.connected, MC_ERR_STATE, "rank %d: mc_comm_init + mc_comm_connect_local first", r);
 		MC_REQUIRE(c->n == root->n && c->nbins == root->nbins && c->tbytes == root->tbytes, MC_ERR_STATE, "rank %d holds different points", r);
 		MC_REQUIRE(!c->comm.slot_pending[0], MC_ERR_STATE, "rank %d: exchange slot 0 is busy", r);
+		MC_REQUIRE(!c->comm.broken, MC_ERR_STATE, "rank %d: an earlier sharded step failed after some ranks had launched; the exchange is out of step (create the contexts again)", r);
 	}
 	MC_REQUIRE(center_row >= 0 && center_row < root->n, MC_ERR_ARG, "center row out of range");
 	MC_REQUIRE(hi < lo || (lo >= 0 && hi < root->n), MC_ERR_ARG, "scan range [%lld,%lld] out of range", (long long)lo, (long long)hi);
@@ -1045,7 +1048,12 @@ extern "C" int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_
 		c->comm.marks_target = r == 0 ? nullptr : root->d_marks;
 		rc = mc_comm_scan_push(c, center_row, lo, hi, 1, 0, 1);
 		c->comm.marks_target = nullptr;
-		if (rc) return rc;
+		if (rc) {
+			// ranks launched so far have advanced their epoch and pushed records, the others have not: later steps
+			// would wait 4 s for records that never come.  Fail fast from now on instead.
+			for (int q = 0; q < world; q++) ctxs[q]->comm.broken = true;
+			return rc;
+		}
 	}
 	double tb = 0, tc = 0;
 	if (dbg) {   // phase times (serialising): launches, all scans finished, tail finished
@@ -1323,9 +1331,27 @@ extern "C" int mc_scan_host(mc_ctx *ctx, const void *hists, int tbytes, int k, c
 	uint64_t *d_lens = cv.take<uint64_t>((size_t)(n + ncenters));
 	uint8_t *d_marks_multi = cv.take<uint8_t>((size_t)ncenters * (size_t)n + 64);
 	uint8_t *d_hist = (uint8_t *)ctx->d_hist;
+	// From here on copies out of / into the caller's buffers are in flight: EVERY failure leaves through fail(),
+	// which waits for both streams (the caller may free its buffers as soon as the call returns) and drops the
+	// half-uploaded histograms.
+	ctx->have_hist = false;
+	auto fail = [&](int code) {
+		cudaStreamSynchronize(ctx->copy_stream);
+		cudaStreamSynchronize(ctx->stream);
+		ctx->have_hist = false;
+		return code;
+	};
+#define SH_CUDA(call)                                                                                  \
+	do {                                                                                               \
+		const cudaError_t _e = (call);                                                                 \
+		if (_e != cudaSuccess) {                                                                       \
+			mc_set_error("mc_scan_host: %s failed: %s", #call, cudaGetErrorString(_e));               \
+			return fail(MC_ERR_CUDA);                                                                  \
+		}                                                                                              \
+	} while (0)
 	// the stream of the context may still be busy with earlier work on these buffers
-	MC_CUDA(cudaEventRecord(ctx->chunk_ev[NCHUNK], ctx->stream));
-	MC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[NCHUNK], 0));
+	SH_CUDA(cudaEventRecord(ctx->chunk_ev[NCHUNK], ctx->stream));
+	SH_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[NCHUNK], 0));
 	// centers first (tiny): gathered on the host into pinned memory
 	uint8_t *h_cent = (uint8_t *)ctx->h_pinned;
 	uint64_t *h_clen = (uint64_t *)(h_cent + (size_t)ncenters * rb);
@@ -1334,21 +1360,21 @@ extern "C" int mc_scan_host(mc_ctx *ctx, const void *hists, int tbytes, int k, c
 		memcpy(h_cent + (size_t)c * rb, (const uint8_t *)hists + (size_t)center_rows[c] * rb, rb);
 		h_clen[c] = lens[center_rows[c]];
 	}
-	MC_CUDA(cudaMemcpyAsync(d_hist + (size_t)n * rb, h_cent, (size_t)ncenters * rb, cudaMemcpyHostToDevice, ctx->copy_stream));
-	MC_CUDA(cudaMemcpyAsync(d_lens + n, h_clen, (size_t)ncenters * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+	SH_CUDA(cudaMemcpyAsync(d_hist + (size_t)n * rb, h_cent, (size_t)ncenters * rb, cudaMemcpyHostToDevice, ctx->copy_stream));
+	SH_CUDA(cudaMemcpyAsync(d_lens + n, h_clen, (size_t)ncenters * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
 	const int64_t per = ((n + NCHUNK - 1) / NCHUNK + 1023) / 1024 * 1024;   // chunk boundaries on 1024 rows
 	int nchunks = 0;
 	for (int64_t r0 = 0; r0 < n; r0 += per, nchunks++) {
 		const int64_t r1 = std::min(n, r0 + per);
-		MC_CUDA(cudaMemcpyAsync(d_hist + (size_t)r0 * rb, (const uint8_t *)hists + (size_t)r0 * rb, (size_t)(r1 - r0) * rb, cudaMemcpyHostToDevice, ctx->copy_stream));
-		MC_CUDA(cudaMemcpyAsync(d_lens + r0, lens + r0, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-		MC_CUDA(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->copy_stream));
+		SH_CUDA(cudaMemcpyAsync(d_hist + (size_t)r0 * rb, (const uint8_t *)hists + (size_t)r0 * rb, (size_t)(r1 - r0) * rb, cudaMemcpyHostToDevice, ctx->copy_stream));
+		SH_CUDA(cudaMemcpyAsync(d_lens + r0, lens + r0, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+		SH_CUDA(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->copy_stream));
 	}
 	const size_t slot_bytes = (size_t)MC_SCAN_PARTS * sizeof(mc_scan_result);
 	int chunk = 0;
 	for (int64_t r0 = 0; r0 < n; r0 += per, chunk++) {
 		const int64_t r1 = std::min(n, r0 + per);
-		MC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[chunk], 0));
+		SH_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[chunk], 0));
 		if (chunk == 0) {
 			rc = mc_launch_point_stats_range(ctx, n, ncenters, d_lens + n, ctx->stream);
 			if (rc) break;
@@ -1375,13 +1401,10 @@ extern "C" int mc_scan_host(mc_ctx *ctx, const void *hists, int tbytes, int k, c
 			break;
 		}
 	}
-	if (rc) {   // the caller's buffers must not be in flight when the call returns
-		cudaStreamSynchronize(ctx->copy_stream);
-		cudaStreamSynchronize(ctx->stream);
-		return rc;
-	}
-	MC_CUDA(cudaMemcpyAsync(h_part, ctx->d_scan_slots, (size_t)nchunks * ncenters * slot_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (rc) return fail(rc);
+	SH_CUDA(cudaMemcpyAsync(h_part, ctx->d_scan_slots, (size_t)nchunks * ncenters * slot_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	SH_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef SH_CUDA
 	ctx->have_hist = true;
 	// fold: per center, the CTA partials of all its chunks
 	std::vector<mc_scan_result> tmp((size_t)nchunks * MC_SCAN_PARTS);

@@ -130,6 +130,16 @@ int mc_launch_encode(mc_ctx *ctx) {
 // encode pass runs when the first alignment (or mc_copy_digits) asks for them.
 // Bytes: L letters read + 4^k * sizeof(T) written per sequence.
 // ---------------------------------------------------------------------------------------------
+// codes of four letters by arithmetic; fast = all four are A, C, G or T in either case
+__device__ __forceinline__ uint32_t k1_codes4_check(uint32_t w, bool &fast) {
+	uint32_t x = (w >> 1) & 0x03030303u;
+	x ^= (x >> 1) & 0x01010101u;
+	const uint32_t s = x | (x >> 4);
+	const uint32_t sel = (s & 0xffu) | ((s >> 8) & 0xff00u);
+	fast = __byte_perm(0x54474341u, 0u, sel) == (w & 0xdfdfdfdfu);
+	return x;
+}
+
 __device__ __forceinline__ uint32_t k1_codes4(uint32_t w, const uint8_t *lut, bool &fast) {
 	// A 0x41 C 0x43 G 0x47 T 0x54: bits 2..1 are 00 01 11 10 -> code = x ^ (x >> 1)
 	uint32_t x = (w >> 1) & 0x03030303u;
@@ -177,6 +187,7 @@ kmer_count_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ s
 	const int lane = threadIdx.x & 31;
 	const int wib = threadIdx.x >> 5;
 	uint32_t *tab = tables + (size_t)wib * nbins;
+	const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
 	const int top = 32 - 2 * k;   // the k-mer is the top 2k bits of the shifted window
 	const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
 	const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -186,37 +197,42 @@ kmer_count_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ s
 		__syncwarp();
 		const long long b0 = seq_off[s], b1 = seq_off[s + 1];
 		const long long g0 = seg_off[s], g1 = seg_off[s + 1];
+		const uint8_t *sbase = seq + (b0 & ~15LL);         // 16-byte aligned; positions below are relative to it
+		const int off0 = (int)(b0 & 15LL);
+		const int len = (int)(b1 - b0);
 		for (long long gi = g0; gi < g1; gi++) {
-			// k-mer starts [ss, last] inside this segment (absolute byte positions)
-			const long long ss = b0 + segs[2 * gi];
-			const long long last = b0 + (long long)segs[2 * gi + 1] - k + 1;
+			// k-mer starts [ss, last] inside this segment
+			const int ss = off0 + segs[2 * gi];
+			const int last = off0 + segs[2 * gi + 1] - k + 1;
 			if (last < ss) continue;
-			const long long a0 = ss & ~15LL;
-			const long long nchunks = ((last - a0) >> 4) + 1;   // chunks with a k-mer start
-			// word of chunk c (letters a0 + 16c ...); chunks past the buffer's 64-byte tail are never needed
-			auto chunk_word = [&](long long c) -> uint32_t {
-				const long long base = a0 + 16 * c;
-				if (base >= b1) return 0u;
-				return k1_pack16(*reinterpret_cast<const uint4 *>(seq + base), lut);
+			const int c_first = ss >> 4, c_last = last >> 4;   // chunks (16 letters) with a k-mer start
+			const int end = off0 + len;                        // letters of this sequence end here
+			auto chunk_word = [&](int c) -> uint32_t {
+				if (16 * c >= end) return 0u;                  // (the buffer has a 64-byte tail: a chunk that starts inside is whole)
+				return k1_pack16(*reinterpret_cast<const uint4 *>(sbase + 16 * c), lut);
 			};
-			uint32_t pn = chunk_word(lane);
-			for (long long c0 = 0; c0 < nchunks; c0 += 32) {
+			uint32_t pn = chunk_word(c_first + lane);
+			for (int c0 = c_first; c0 <= c_last; c0 += 32) {
 				const uint32_t pc = pn;
 				pn = chunk_word(c0 + 32 + lane);   // next round's word, also lane 31's neighbour
 				uint32_t nb = __shfl_down_sync(MC_FULL_MASK, pc, 1);
 				const uint32_t n0 = __shfl_sync(MC_FULL_MASK, pn, 0);
 				if (lane == 31) nb = n0;
-				const long long c = c0 + lane;
-				if (c < nchunks) {
-					const long long base = a0 + 16 * c;
-					if (base >= ss && base + 15 <= last) {
+				const int c = c0 + lane;
+				// which of the 16 starts of this chunk count: bit j <=> ss <= 16c + j <= last
+				uint32_t vm = 0;
+				if (c <= c_last) {
+					const int lo = ss - 16 * c, hi = last - 16 * c;
+					vm = 0xffffu;
+					if (lo > 0) vm &= 0xffffu << lo;
+					if (hi < 15) vm &= 0xffffu >> (15 - hi);
+				}
+				// one predicated shared-memory reduction per start (inline PTX: a 32-bit shared address computed once;
+				// the compiler's form re-derives the shared window and opens a reconvergence region per k-mer)
 #pragma unroll
-						for (int j = 0; j < 16; j++) atomicAdd(&tab[__funnelshift_l(nb, pc, 2 * j) >> top], 1u);
-					} else {
-#pragma unroll
-						for (int j = 0; j < 16; j++)
-							if (base + j >= ss && base + j <= last) atomicAdd(&tab[__funnelshift_l(nb, pc, 2 * j) >> top], 1u);
-					}
+				for (int j = 0; j < 16; j++) {
+					const uint32_t addr = tab_s + ((__funnelshift_l(nb, pc, 2 * j) >> top) << 2);
+					asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n @p red.shared.add.u32 [%0], 1;\n}\n" ::"r"(addr), "r"(vm & (1u << j)) : "memory");
 				}
 			}
 		}
@@ -292,9 +308,16 @@ __global__ void validate_kernel(const uint8_t *__restrict__ seq, const int64_t *
 			const uint4 x = *reinterpret_cast<const uint4 *>(seq + base);
 			const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-			for (int j = 0; j < 16; j++) {
-				const uint32_t ch = (w[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-				if (base + j >= b0 && base + j < b1 && lut[ch] == 0xffu) bad = true;
+			for (int q = 0; q < 4; q++) {
+				// words of plain ACGT / acgt inside the sequence pass on the permute check of K1; the table sees the rest
+				bool fast;
+				k1_codes4_check(w[q], fast);
+				if (fast && base + 4 * q >= b0 && base + 4 * q + 3 < b1) continue;
+#pragma unroll
+				for (int j = 4 * q; j < 4 * q + 4; j++) {
+					const uint32_t ch = (w[q] >> ((j & 3) * 8)) & 0xffu;
+					if (base + j >= b0 && base + j < b1 && lut[ch] == 0xffu) bad = true;
+				}
 			}
 		}
 	}

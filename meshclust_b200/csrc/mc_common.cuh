@@ -155,6 +155,7 @@ struct McComm {
 	uint8_t *peer_inbox[MC_MAX_PEERS] = {};
 	bool ipc_opened[MC_MAX_PEERS] = {};
 	bool connected = false;
+	bool broken = false;      // a sharded step failed after some ranks had launched: epochs are out of step, every later exchange would time out
 	unsigned int slot_epoch[MC_XSLOTS] = {};
 	unsigned char slot_pending[MC_XSLOTS] = {};   // 0 free, 1 scan enqueued, 2 combine enqueued, 3 burst scan enqueued (one folded record per rank)
 	void *d_out = nullptr;                     // MC_XSLOTS combined records + error word

@@ -279,8 +279,9 @@ dist_keys_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // K2b as a tile: C centers x all rows with every row read ONCE.  The centers of a group (all C of them
 // when C * row bytes fit shared memory: 150 KB for 150 centers at k = 5) are staged in shared memory with
-// 1-D bulk copies (cp.async.bulk, one per center); a warp keeps one row in registers (lane l owns bytes
-// [l * RB/32, (l+1) * RB/32)), runs it against 32 centers at a time -- lane-private partial sums of
+// 1-D bulk copies (cp.async.bulk, one per center); a warp keeps one row in registers (lane l owns the 16-byte
+// chunks l, l + 32, ... of it: a warp-wide 16-byte load of a center from shared memory is then 512
+// consecutive bytes, free of bank conflicts), runs it against 32 centers at a time -- lane-private partial sums of
 // |p - q| per center -- and a transposing reduction (31 shuffles for 32 centers) leaves the total of center c
 // in lane c, which computes the key.  DRAM traffic = n * 4^k (+ keys), not C times that.
 // Sum min(p, q) = (mag_p + mag_q - sum |p - q|) / 2 exactly.
@@ -302,7 +303,7 @@ __device__ __forceinline__ uint32_t absdiff_acc(uint32_t p, uint32_t q, uint32_t
 	}
 }
 
-constexpr int TILE_THREADS = 256;
+constexpr int TILE_THREADS = 512;
 
 template <int TB, int RB>
 __global__ void __launch_bounds__(TILE_THREADS)
@@ -340,11 +341,12 @@ dist_keys_tile_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restri
 		__syncthreads();
 		for (long long row = warp; row < n; row += nwarps) {
 			uint32_t rw[W];
-			const uint32_t *src = reinterpret_cast<const uint32_t *>(hist + (size_t)row * RB) + lane * W;
+			// W >= 4: chunk j of this lane = bytes (j * 32 + lane) * 16 of the row; narrower rows: W consecutive words
+			const uint32_t *src = reinterpret_cast<const uint32_t *>(hist + (size_t)row * RB) + (W >= 4 ? lane * 4 : lane * W);
 			if constexpr (W >= 4) {
 #pragma unroll
 				for (int w = 0; w < W; w += 4) {
-					const uint4 v = mc_ld_stream16(src + w);
+					const uint4 v = mc_ld_stream16(src + w * 32);
 					rw[w] = v.x; rw[w + 1] = v.y; rw[w + 2] = v.z; rw[w + 3] = v.w;
 				}
 			} else {
@@ -356,12 +358,12 @@ dist_keys_tile_kernel(const uint8_t *__restrict__ hist, const McRowAux *__restri
 				AbsAcc acc[32];
 #pragma unroll
 				for (int c = 0; c < 32; c++) {
-					const uint32_t *q = reinterpret_cast<const uint32_t *>(cen + (size_t)(sub + c) * RB) + lane * W;
+					const uint32_t *q = reinterpret_cast<const uint32_t *>(cen + (size_t)(sub + c) * RB) + (W >= 4 ? lane * 4 : lane * W);
 					uint32_t a = 0;
 					if constexpr (W >= 4) {
 #pragma unroll
 						for (int w = 0; w < W; w += 4) {
-							const uint4 v = *reinterpret_cast<const uint4 *>(q + w);
+							const uint4 v = *reinterpret_cast<const uint4 *>(q + w * 32);
 							a = absdiff_acc<TB>(rw[w], v.x, a); a = absdiff_acc<TB>(rw[w + 1], v.y, a);
 							a = absdiff_acc<TB>(rw[w + 2], v.z, a); a = absdiff_acc<TB>(rw[w + 3], v.w, a);
 						}

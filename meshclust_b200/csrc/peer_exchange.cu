@@ -150,6 +150,8 @@ extern "C" int mc_comm_connect_local(mc_ctx *const *ctxs, int world) {
 	MC_REQUIRE(ctxs && world >= 1 && world <= MC_MAX_PEERS, MC_ERR_ARG, "bad arguments");
 	for (int r = 0; r < world; r++) {
 		MC_REQUIRE(ctxs[r] && ctxs[r]->comm.world == world && ctxs[r]->comm.rank == r, MC_ERR_STATE, "context %d: mc_comm_init(rank %d, world %d) first", r, r, world);
+		// every rank leaves num_sms records per scan and expects as many from each peer
+		MC_REQUIRE(ctxs[r]->num_sms == ctxs[0]->num_sms, MC_ERR_UNSUPPORTED, "GPUs %d and %d have different SM counts (%d, %d)", ctxs[0]->device, ctxs[r]->device, ctxs[0]->num_sms, ctxs[r]->num_sms);
 	}
 	for (int r = 0; r < world; r++) {
 		MC_CUDA(cudaSetDevice(ctxs[r]->device));

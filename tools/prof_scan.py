@@ -11,6 +11,7 @@ from meshclust_b200 import api  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--shape", default="c2")
 ap.add_argument("--launches", type=int, default=6)
+ap.add_argument("--chain", action="store_true", help="one launch per scan, each behind the one before it (MC_SCAN_CHAIN)")
 a = ap.parse_args()
 n, k, reps = {"c1": (10_000, 3, 64), "c2": (100_000, 4, 10), "c4": (1_000_000, 5, 1), "c5": (200_000, 6, 1)}[a.shape]
 nb = 4 ** k
@@ -25,6 +26,6 @@ L = a.launches
 cr = np.array([(i % reps) * n + (i * 7919) % n for i in range(L)], np.int64)
 lo = np.array([(i % reps) * n for i in range(L)], np.int64)
 hi = lo + n - 1
-ctx.scan_enqueue_many(cr, lo, hi, False, 0)
+ctx.scan_enqueue_many(cr, lo, hi, api.MC_SCAN_CHAIN if a.chain else False, 0)
 ctx.sync()
 print(ctx.scan_collect(0, L)[:2])
