@@ -644,9 +644,10 @@ void mean_shift(Ctx &c, BVec &bv) {
 	// The whole `while (last) accumulate(...)` loop (ClusterFactory.cpp:722-729, :637-714) with its bvec
 	// bookkeeping runs as one persistent kernel; the host only reads the clusters back.  --align (the
 	// decision is an alignment, not a scan), histogram shapes the staged scan kernel does not take and
-	// MC_PHASE_A_STEPS=1 (tests) go through the step-by-step loop below.
+	// MC_PHASE_A_STEPS=1 (tests) go through the step-by-step loop below, and so do runs whose scans are sharded
+	// over several GPUs (inputs of gigabytes, see run_pipeline).
 	bool phase_a_done = false;
-	if (!c.model.align && !getenv("MC_PHASE_A_STEPS")) {
+	if (!c.model.align && !getenv("MC_PHASE_A_STEPS") && world == 1) {
 		const std::vector<int64_t> first = bv.first_rows();
 		std::vector<int64_t> centers((size_t)ds.n), offs((size_t)ds.n + 1), members((size_t)ds.n);
 		mc_run_stats st;
@@ -904,6 +905,25 @@ int run_pipeline(Options opt) {
 	int ctx_rc = MC_OK;
 	std::string ctx_err;
 	double ctx_s = 0;
+	// --gpus N shards the Phase-A scans (host-driven steps, summaries over NVLink): that pays when one scan is
+	// long -- hundreds of microseconds, i.e. gigabytes of histograms.  Below that the single persistent kernel on
+	// one GPU is faster than any exchange per step, and every additional CUDA context costs start-up time: small
+	// inputs stay on one GPU.  The input size is known before the first CUDA call (file sizes), the histogram
+	// size is not: the rule is on the bytes of FASTA (MC_SHARD_MIN_BYTES, default 3 GB; tests force sharding
+	// with MC_PHASE_A_STEPS).
+	if (opt.gpus > 1 && !getenv("MC_PHASE_A_STEPS")) {
+		unsigned long long total_bytes = 0;
+		for (const std::string &f : opt.files) {
+			struct stat stt;
+			if (stat(f.c_str(), &stt) == 0) total_bytes += (unsigned long long)stt.st_size;
+		}
+		const unsigned long long min_bytes = getenv("MC_SHARD_MIN_BYTES") ? strtoull(getenv("MC_SHARD_MIN_BYTES"), nullptr, 10) : 3000000000ull;
+		if (total_bytes < min_bytes) {
+			printf("  [--gpus %d: %.2f GB of input, Phase A stays on one GPU (persistent kernel)]\n", opt.gpus, (double)total_bytes * 1e-9);
+			opt.gpus = 1;
+			c.opt.gpus = 1;
+		}
+	}
 	// CUDA start-up time grows with the number of GPUs the driver has to initialise: expose only the
 	// ones this run uses (unless the user has chosen a set already)
 	if (!getenv("CUDA_VISIBLE_DEVICES")) {
