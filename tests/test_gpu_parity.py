@@ -201,6 +201,83 @@ def test_scan_vs_oracle(ctx, oracle, k, n, nfeat):
     print(f"near-threshold pairs (|sum| < {NEAR}): {total_near}")
 
 
+@pytest.mark.parametrize("nfeat", [3, 4])
+@pytest.mark.parametrize("k", [3, 4, 5])
+def test_scan_decisions_at_the_threshold(ctx, oracle, k, nfeat):
+    """The scan decides most rows from an interval of the GLM sum (FP32 PEARSON / KULCZYNSKI2 with an error
+    bound, mc_scan_decide) and runs the exact FP64 terms only when the interval touches the threshold.  Models
+    whose bias puts the threshold ON a row's sum, and 1e-12 .. 1e-3 beside it, exercise both sides of that
+    filter: every decision outside |sum| < 1e-9 must be the oracle's, and the near-threshold counter must
+    count exactly the rows inside."""
+    rng = np.random.default_rng(7000 + 10 * k + nfeat)
+    nb, n = 4 ** k, 3000
+    H = _rand_hists(rng, n, nb, clusters=5)
+    lens = (H.astype(np.int64).sum(1) - nb + k - 1 + rng.integers(0, 3, n)).astype(np.uint64)
+    mins, maxs, w = _model(nfeat)
+    maxs[2] = 4.0 * nb
+    maxs[4] = 2.0 * nb
+    mins[4] = 0.5 * nb
+    ctx.load_histograms(H, lens, k)
+    center = 17
+    base, _, _ = oracle.scan(H, lens, H[center], int(lens[center]), mins, maxs, w, nfeat)
+    targets = rng.choice(n, 6, replace=False)
+    flips = 0
+    for t, eps in zip(targets, (0.0, 1e-12, -1e-10, 3e-8, -1e-6, 2e-4)):
+        w2 = w.copy()
+        w2[0] = w[0] - base[t] + eps      # row t now sums to ~eps; its same-cluster neighbours lie close by
+        ws, wf0, wfl = oracle.scan(H, lens, H[center], int(lens[center]), mins, maxs, w2, nfeat)
+        near = np.abs(ws) < NEAR
+        ctx.set_model(mins, maxs, w2, nfeat)
+        ctx.alive_reset()
+        ctx.near_threshold_count(reset=True)
+        res, marks = ctx.scan(center, 0, n - 1)
+        got_near = ctx.near_threshold_count(reset=True)
+        live = np.ones(n, bool)
+        ok = live & ~near
+        assert np.array_equal(marks[ok], wfl[ok]), f"decision differs from the oracle away from the threshold (eps {eps})"
+        assert got_near == int((near & live).sum())
+        assert res.n_pos == int(marks[live].sum())
+        flips += int((np.abs(ws[live]) < 1e-3).sum())
+    assert flips >= 6    # the models did put rows next to the threshold
+
+
+@pytest.mark.parametrize("dtype,k,C", [(np.uint8, 4, 150), (np.uint8, 5, 37), (np.uint8, 6, 150), (np.uint16, 3, 33), (np.uint16, 4, 150), (np.uint16, 5, 5), (np.uint8, 3, 150)])
+def test_distance_keys_tile_equals_pair_lists(ctx, dtype, k, C):
+    """K2b as a tile (C centers staged in shared memory, every row read once; rows of 128 bytes and more) against
+    the one-warp-per-pair kernel on ALL C x n pairs, for center counts that are not multiples of 32 and for more
+    centers than shared memory holds at once (k = 6: 4 KB rows)."""
+    rng = np.random.default_rng(8100 + k)
+    nb, n = 4 ** k, 1111
+    H = _rand_hists(rng, n, nb, dtype, 255 if dtype == np.uint8 else 2000, clusters=7)
+    ctx.load_histograms(H, np.full(n, 900, np.uint64), k)
+    centers = rng.integers(0, n, C).astype(np.int32)
+    centers[0], centers[-1] = 0, n - 1
+    keys = ctx.distance_keys(centers)
+    a = np.repeat(centers, n).astype(np.int32)
+    b = np.tile(np.arange(n, dtype=np.int32), C)
+    _, dist = ctx.pair_features(b, a)
+    assert np.array_equal(keys.astype(np.uint64).reshape(-1), dist)
+
+
+def test_histograms_from_letters_and_from_digits(ctx, oracle):
+    """K1 counts LETTERS in one pass; the digit strings the aligner reads are made lazily, in place.  A buffer
+    that has been encoded already (mc_copy_digits forces it) must give the same histograms."""
+    l, o, _ = synth.generate_config("c2", 300)
+    l = l.copy()
+    l[5:40] = ord("N")          # a run of N: two segments
+    l[200] = ord("n")
+    l[900:905] = np.frombuffer(b"RYKMS", np.uint8)
+    l[1500:1600] |= 0x20        # lower case
+    rc, want, _ = oracle.hist_batch(l, o, 4, 1)
+    assert rc == 0
+    ctx.load_sequences(l, o)
+    ctx.build_histograms(4, 1)
+    assert np.array_equal(ctx.copy_histograms(), want)
+    ctx.copy_digits()           # in-place encode
+    ctx.build_histograms(4, 1)
+    assert np.array_equal(ctx.copy_histograms(), want)
+
+
 @pytest.mark.parametrize("k,n", [(2, 3000), (4, 5000), (5, 2100), (6, 600)])
 def test_scan_batch_launch_equals_single_scans(ctx, k, n, monkeypatch):
     """independent scans (nothing removed) share one launch (blockIdx.y = scan): same summaries as one
