@@ -242,6 +242,7 @@ typedef struct mc_run_stats {
 	int64_t n_near_threshold; /* of those, pairs whose GLM sum lies within 1e-9 of the decision threshold */
 	int64_t n_steps;          /* iterations of accumulate()'s inner loop, empty ranges included */
 	double device_seconds;    /* time the loop spent on the GPU */
+	int64_t n_compactions;    /* times the rows still in the bvec were copied together (the scans stream those only) */
 } mc_run_stats;
 
 /* The whole of ClusterFactory::MS's first phase -- `while (last) accumulate(&last, points, ...)`

@@ -53,7 +53,7 @@ class StepResult(C.Structure):
 
 class RunStats(C.Structure):
     _fields_ = [("n_clusters", C.c_int64), ("n_scans", C.c_int64), ("n_evals", C.c_int64), ("n_near_threshold", C.c_int64),
-                ("n_steps", C.c_int64), ("device_seconds", C.c_double)]
+                ("n_steps", C.c_int64), ("device_seconds", C.c_double), ("n_compactions", C.c_int64)]
 
 
 _lib.mc_version.restype = C.c_char_p

@@ -517,8 +517,6 @@ static int pair_list_common(mc_ctx *ctx, const int32_t *a, const int32_t *b, int
 	if (rc) return rc;
 	rc = check_rows32(ctx, b, m);
 	if (rc) return rc;
-	rc = ensure_digits(ctx);
-	if (rc) return rc;
 	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)m * 4, (size_t)m * 4, (size_t)m * 40, (size_t)m * 8, (size_t)m * 8, (size_t)m * 8, (size_t)m, (size_t)m * 32}));
 	if (rc) return rc;
 	Carve cv(ctx->d_scratch);
@@ -851,7 +849,8 @@ int mc_launch_pa_prepare(mc_ctx *ctx, const unsigned long long *bounds_dev, cons
 int mc_launch_phase_a(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, const void *range_tab_dev,
                       uint32_t *alive_bits_dev, unsigned long long *g_sum_dev, void *exch_dev,
                       unsigned long long *bar_dev, int *members_dev, int *cl_center_dev, int *cl_off_dev, long long *stats_dev,
-                      unsigned long long *trace_dev, int trace_steps, int grid, int qmax);
+                      unsigned long long *trace_dev, int trace_steps, int grid, int qmax, int *mcur_dev, double sim,
+                      void *const *staging, const long long *staging_cap, long long compact_min, int compact_shift);
 
 extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t *bin_bounds, const int64_t *bin_first_row,
                                  int64_t nbins_bvec, int64_t *center_rows_out, int64_t *cluster_offsets_out,
@@ -881,10 +880,37 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 	const int trace_steps = getenv("MC_PA_TRACE") ? atoi(getenv("MC_PA_TRACE")) : 0;
 	const size_t words = (size_t)((n + 31) / 32) + 64;
 	const size_t NB = (size_t)ctx->nbins;
-	int rc = mc_ensure_scratch(ctx, Carve::need({(size_t)nb * 8, (size_t)(nb + 1) * 4, (size_t)n * mc_pa_range_bytes(), words * 4, mc_pa_gsum_bytes((int)NB),
-	                                             mc_pa_exchange_bytes(grid), 64,
-	                                             (size_t)n * 4, (size_t)n * 4, (size_t)(n + 1) * 4, 64, 64, (size_t)trace_steps * mc_pa_trace_slots() * 8 + 64}));
-	if (rc) return rc;
+	// staging for the row compactions: alive rows in order, ping-pong between two buffers (histograms, constants,
+	// original row numbers, search records, bitmap).  A compaction happens once a fraction 2^-shift of the current
+	// rows has left the bvec (default 1/8: the scans stream at most 8/7 of the rows they evaluate; the copies add up
+	// to 7 n rows over a run, a few scans' worth), so the buffers hold 7/8 n and 49/64 n rows.  Without the memory
+	// for it (or with MC_PA_NO_COMPACT) the run streams the original rows to the end.
+	const size_t RBy = (size_t)ctx->tbytes * ctx->nbins;
+	int compact_shift = getenv("MC_PA_COMPACT_SHIFT") ? atoi(getenv("MC_PA_COMPACT_SHIFT")) : 3;
+	compact_shift = std::max(1, std::min(compact_shift, 6));
+	const long long n1 = n - (n >> compact_shift);
+	const long long cap[2] = {n1 + 64, n1 - (n1 >> compact_shift) + 64};
+	std::vector<size_t> need_base = {(size_t)nb * 8, (size_t)(nb + 1) * 4, (size_t)n * mc_pa_range_bytes(), words * 4, mc_pa_gsum_bytes((int)NB),
+	                                 mc_pa_exchange_bytes(grid), 64,
+	                                 (size_t)n * 4, (size_t)n * 4, (size_t)(n + 1) * 4, 64, 64, (size_t)trace_steps * mc_pa_trace_slots() * 8 + 64, (size_t)n * 4};
+	std::vector<size_t> need_st = need_base;
+	for (int b = 0; b < 2; b++) {
+		need_st.push_back((size_t)cap[b] * RBy + 256);
+		need_st.push_back((size_t)cap[b] * sizeof(McRowAux) + 64);
+		need_st.push_back((size_t)cap[b] * 4);
+		need_st.push_back((size_t)cap[b] * mc_pa_range_bytes());
+		need_st.push_back((size_t)(cap[b] / 32 + 2) * 4);
+	}
+	auto total_of = [](const std::vector<size_t> &v) { size_t t = 0; for (size_t x : v) t = align_up(t, 256) + x; return t + 256; };
+	// (MC_PA_COMPACT_MIN: tests compact inputs of a few thousand rows)
+	const long long compact_min = getenv("MC_PA_COMPACT_MIN") ? std::max(64LL, atoll(getenv("MC_PA_COMPACT_MIN"))) : 4096;
+	bool compact = n >= 2 * compact_min && !getenv("MC_PA_NO_COMPACT");
+	int rc = MC_OK;
+	if (compact && mc_ensure_scratch(ctx, total_of(need_st)) != MC_OK) { compact = false; cudaGetLastError(); }
+	if (!compact) {
+		rc = mc_ensure_scratch(ctx, total_of(need_base));
+		if (rc) return rc;
+	}
 	Carve cv(ctx->d_scratch);
 	unsigned long long *d_bounds = cv.take<unsigned long long>((size_t)nb);
 	int *d_row0 = cv.take<int>((size_t)nb + 1);
@@ -900,6 +926,16 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 	unsigned int *d_err = cv.take<unsigned int>(16);
 	const size_t TS = (size_t)mc_pa_trace_slots();
 	unsigned long long *d_trace = cv.take<unsigned long long>((size_t)trace_steps * TS + 8);
+	int *d_mcur = cv.take<int>((size_t)n);
+	void *staging[10] = {};
+	if (compact)
+		for (int b = 0; b < 2; b++) {
+			staging[b * 5 + 0] = cv.take<uint8_t>((size_t)cap[b] * RBy + 256);
+			staging[b * 5 + 1] = cv.take<uint8_t>((size_t)cap[b] * sizeof(McRowAux) + 64);
+			staging[b * 5 + 2] = cv.take<int>((size_t)cap[b]);
+			staging[b * 5 + 3] = cv.take<uint8_t>((size_t)cap[b] * mc_pa_range_bytes());
+			staging[b * 5 + 4] = cv.take<uint32_t>((size_t)(cap[b] / 32 + 2));
+		}
 	MC_CUDA(cudaMemcpyAsync(d_bounds, bin_bounds, (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(d_row0, row0.data(), (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
 	// a fresh bvec: every row alive, the bits past the last row clear
@@ -921,7 +957,7 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	MC_REQUIRE(h_err == 0, MC_ERR_ARG, "mc_accumulate_run: the rows of a bvec bin are not in non-decreasing length order");
 	rc = mc_launch_phase_a(ctx, d_bounds, d_row0, nb, d_range, d_bits, d_gsum, d_exch, d_bar, d_members, d_center, d_off,
-	                       d_stats, trace_steps ? d_trace : nullptr, trace_steps, grid, qmax);
+	                       d_stats, trace_steps ? d_trace : nullptr, trace_steps, grid, qmax, d_mcur, similarity, compact ? staging : nullptr, cap, compact_min, compact_shift);
 	if (rc) return rc;
 	long long h_stats[8];
 	unsigned long long h_bar[2];
@@ -955,6 +991,7 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 		stats->n_near_threshold = h_stats[3];
 		stats->n_steps = h_stats[4];
 		stats->device_seconds = (double)h_stats[5] * 1e-9;
+		stats->n_compactions = h_stats[6];
 	}
 	if (trace_steps) {
 		std::vector<unsigned long long> tr((size_t)trace_steps * TS);

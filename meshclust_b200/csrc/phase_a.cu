@@ -77,7 +77,18 @@ struct PaArgs {
 	unsigned long long *recs;           // 2 x grid x PA_REC_WORDS: scan summaries of the CTAs as tagged words
 	unsigned long long *near_recs;      // 2 x grid x PA_REC_WORDS: nearest-member candidates of the CTAs
 	unsigned long long *bar;            // [1] abort code
-	int *members;                       // n: the clusters' member rows, cluster after cluster
+	int *members;                       // n: the clusters' member rows (ORIGINAL row numbers), cluster after cluster
+	int *mcur;                          // n: the same members as rows of the current numbering (see compaction)
+	// row compaction: staging copies of the alive rows, ping-pong (capacities see mc_accumulate_run); null = off
+	uint8_t *st_hist[2];
+	McRowAux *st_aux[2];
+	int *st_orig[2];
+	PaRange *st_range[2];
+	uint32_t *st_bits[2];
+	long long st_cap[2];
+	long long compact_min;              // no compaction below this many current rows
+	int compact_shift;                  // compaction once at most n_cur - (n_cur >> shift) of the current rows are alive
+	double sim;
 	int *cl_center;                     // n
 	int *cl_off;                        // n + 1
 	long long *stats;                   // [0] clusters [1] scans [2] evals [3] near-threshold pairs [4] steps [5] ns
@@ -106,40 +117,48 @@ __device__ __forceinline__ void pa_index_of(const unsigned long long *b, int nb,
 	*pback = high;
 }
 
+// The search record of row r (see PaRange) for bins that start at row0[] (the rows of a bin in non-decreasing
+// length order, bvec::insert_finalize, bvec.cpp:209-218)
+template <class Row0>
+__device__ __forceinline__ PaRange pa_make_range(const McRowAux *__restrict__ aux, long long r, const unsigned long long *bounds,
+                                                 const Row0 *row0, int nb, double sim) {
+	const unsigned long long len = __ldcg(&aux[r].len);
+	// ClusterFactory.cpp:651-652: get_range(len * id, len / id), both converted to uint64
+	const unsigned long long begin_len = (unsigned long long)((double)len * sim);
+	const unsigned long long end_len = (unsigned long long)((double)len / sim);
+	PaRange g;
+	int dummy;
+	pa_index_of(bounds, nb, begin_len, &g.fb, &dummy);
+	pa_index_of(bounds, nb, end_len, &dummy, &g.bb);
+	auto count_below = [&](int bin, unsigned long long key, bool inclusive) {
+		int lo = (int)row0[bin], hi = (int)row0[bin + 1];
+		const int base = lo;
+		while (lo < hi) {
+			const int mid = (lo + hi) >> 1;
+			const unsigned long long v = __ldcg(&aux[mid].len);
+			if (inclusive ? v <= key : v < key) lo = mid + 1; else hi = mid;
+		}
+		return lo - base;
+	};
+	g.f_lt = count_below(g.fb, begin_len, false);
+	g.f_le = count_below(g.fb, begin_len, true);
+	g.b_lt = count_below(g.bb, end_len, false);
+	g.b_le = count_below(g.bb, end_len, true);
+	g.pad0 = 0; g.pad1 = 0;
+	return g;
+}
+
 // One thread per row: the search records.  Also checks what the kernel relies on: rows of a bin are in
-// non-decreasing length order (bvec::insert_finalize sorts every bin, bvec.cpp:209-218).
+// non-decreasing length order.
 __global__ void pa_prepare_kernel(const McRowAux *__restrict__ aux, long long n, const unsigned long long *__restrict__ bounds,
                                   const int *__restrict__ row0, int nb, double sim, PaRange *__restrict__ tab,
                                   unsigned int *__restrict__ err) {
 	for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
-		const unsigned long long len = aux[r].len;
-		// ClusterFactory.cpp:651-652: get_range(len * id, len / id), both converted to uint64
-		const unsigned long long begin_len = (unsigned long long)((double)len * sim);
-		const unsigned long long end_len = (unsigned long long)((double)len / sim);
-		PaRange g;
-		int dummy;
-		pa_index_of(bounds, nb, begin_len, &g.fb, &dummy);
-		pa_index_of(bounds, nb, end_len, &dummy, &g.bb);
-		auto count_below = [&](int bin, unsigned long long key, bool inclusive) {
-			int lo = row0[bin], hi = row0[bin + 1];
-			const int base = lo;
-			while (lo < hi) {
-				const int mid = (lo + hi) >> 1;
-				const unsigned long long v = aux[mid].len;
-				if (inclusive ? v <= key : v < key) lo = mid + 1; else hi = mid;
-			}
-			return lo - base;
-		};
-		g.f_lt = count_below(g.fb, begin_len, false);
-		g.f_le = count_below(g.fb, begin_len, true);
-		g.b_lt = count_below(g.bb, end_len, false);
-		g.b_le = count_below(g.bb, end_len, true);
-		g.pad0 = 0; g.pad1 = 0;
-		tab[r] = g;
+		tab[r] = pa_make_range(aux, r, bounds, row0, nb, sim);
 		// sortedness inside the bin of r
 		int lo = 0, hi = nb;
 		while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long)row0[mid + 1] <= r) lo = mid + 1; else hi = mid; }
-		if (r > row0[lo] && aux[r - 1].len > len) atomicExch(err, 1u);
+		if (r > row0[lo] && aux[r - 1].len > aux[r].len) atomicExch(err, 1u);
 	}
 }
 
@@ -407,6 +426,34 @@ __device__ __forceinline__ void pa_release_fence() {
 #endif
 }
 
+// grid-wide barrier on a monotonic counter (compactions only: a few per run): barrier e is passed when the
+// counter reaches e * gridDim.x.  false = the run was aborted (time-out).
+__device__ __forceinline__ bool pa_grid_barrier(unsigned long long *bar, unsigned long long target, int *s_flag) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ull) : "memory");
+		unsigned long long t0 = 0;
+		int ok = 1;
+		for (unsigned spins = 0;; spins++) {
+			unsigned long long v;
+			asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+			if (v >= target) break;
+			if ((spins & 0x3ff) == 0x3ff) {
+				unsigned long long t1, ab;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+				asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(ab) : "l"(bar + 1) : "memory");
+				if (ab) { ok = 0; break; }
+				if (t0 == 0) t0 = t1;
+				else if (t1 - t0 > PA_TIMEOUT_NS) { atomicExch(bar + 1, 1ull); ok = 0; break; }
+			}
+		}
+		*s_flag = ok;
+	}
+	__syncthreads();
+	return *s_flag != 0;
+}
+
+
 // The running bin sums of `current` are the one thing every CTA adds to at the same time.  2 KB of
 // consecutive 64-bit counters live in FOUR L2 slices (the slice hash ignores most of the low address bits),
 // and ~100 CTAs x 4^k reductions queue up there for microseconds; one 32-byte sector (4 bins) per KB puts
@@ -482,6 +529,15 @@ constexpr int PA_TRACE_SLOTS = 32;
 		}                                                                                   \
 	} while (0)
 
+// an index that would leave its array ends the run with a code (the host reports it) instead of a fault
+#define PA_CHECK(cond, code)                                                     \
+	do {                                                                         \
+		if (!(cond)) {                                                           \
+			atomicExch(A.bar + 1, (unsigned long long)(code));                   \
+			return;                                                              \
+		}                                                                        \
+	} while (0)
+
 template <int TB, int RB>
 __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_constant__ PaArgs A) {
 	using C = RowCfg<RB>;
@@ -510,6 +566,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 	unsigned long long *s_bounds = reinterpret_cast<unsigned long long *>(sp); sp += (size_t)nb * 8;
 	uint32_t *s_row0 = reinterpret_cast<uint32_t *>(sp); sp += (size_t)(nb + 1) * 4;
 	uint32_t *s_alive = reinterpret_cast<uint32_t *>(sp); sp += (size_t)nb * 4;
+	uint32_t *s_row0n = reinterpret_cast<uint32_t *>(sp); sp += (size_t)(nb + 1) * 4;   // bin starts after a compaction
 	uint32_t *s_sum = reinterpret_cast<uint32_t *>(sp); sp += (size_t)NB * 4;
 	uint32_t *s_marks = reinterpret_cast<uint32_t *>(sp); sp += (size_t)A.qmax * 4;
 	uint32_t *s_mpref = reinterpret_cast<uint32_t *>(sp); sp += (size_t)A.qmax * 4;
@@ -539,6 +596,20 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 	}
 	__syncthreads();
 
+	// ---- the rows the scans stream.  They start as the caller's arrays; once at most half of them are alive
+	// the alive ones are copied, in order, into a staging buffer (compact(), at a cluster boundary) and the scans
+	// read that: two numberings from then on -- ORIGINAL rows (members, centers' histograms, the output) and
+	// CURRENT rows (tiles, bitmap, bins, search records); cur_orig maps the second to the first.
+	const uint8_t *cur_hist = A.hist;
+	const McRowAux *cur_aux = A.aux;
+	uint32_t *cur_bits = A.alive_bits;
+	const PaRange *cur_range = A.range_tab;
+	const int *cur_orig = nullptr;     // null: the numberings coincide
+	long long n_cur = A.n, alive_cnt = A.n;
+	int n_compact = 0;
+	unsigned long long cbar = 0;       // grid barriers passed (compactions only)
+	auto to_orig = [&](long long r) -> long long { return cur_orig ? (long long)__ldcg(cur_orig + r) : r; };
+
 	auto bin_of = [&](long long row) {   // bin that holds `row`
 		int lo = 0, hi = nb;
 		while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long)s_row0[mid + 1] <= row) lo = mid + 1; else hi = mid; }
@@ -552,13 +623,13 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		__syncwarp();
 		if (lane == 0) s_first_live = fl;
 		if (fl >= nb) return -1;
-		return pa_select(A.alive_bits, s_row0[fl], s_row0[fl + 1], 0, skip, lane);
+		return pa_select(cur_bits, s_row0[fl], s_row0[fl + 1], 0, skip, lane);
 	};
 
 	// ---- loop state, identical in every thread of every CTA
 	long long step = 0;               // scans issued (parity and tag of the records)
 	long long cluster = 0, cl_begin = 0, m0 = 1;
-	long long center;
+	long long center, center_cur;     // the center as an original row (histogram, members) and as a current row (bitmap, search record)
 	bool first_step = true;
 	long long cl_seed = -1;   // `current` starts as {seed} (ClusterFactory.cpp:641): its histogram is added when the mean is taken
 	long long st_scans = 0, st_evals = 0, st_near = 0;
@@ -583,8 +654,9 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		}
 	}
 	__syncthreads();
-	center = s_seed;
-	if (center >= 0 && cta == 0 && threadIdx.x == 0) { A.members[0] = (int)center; A.cl_off[0] = 0; }
+	center = center_cur = s_seed;
+	if (center >= 0) alive_cnt--;
+	if (center >= 0 && cta == 0 && threadIdx.x == 0) { A.members[0] = (int)center; A.mcur[0] = (int)center; A.cl_off[0] = 0; }
 
 	while (center >= 0) {
 		const int par = (int)(step & 1);
@@ -595,8 +667,9 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		unsigned long long *my_near = A.near_recs + ((size_t)par * G + cta) * PA_REC_WORDS;
 		PA_TRACE(0);
 		// ================= control: bvec::get_range of the center's length window =================
+		PA_CHECK(center_cur >= 0 && center_cur < n_cur && center < A.n, 101);   // (every thread: the whole CTA leaves)
 		if (wib < 2) {
-			const PaRange rec = A.range_tab[center];
+			const PaRange rec = cur_range[center_cur];
 			const bool back = wib == 1;
 			int bin = back ? rec.bb : rec.fb;
 			PA_TRACE_DEP(10, bin);
@@ -613,10 +686,10 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 					while (ll >= 0 && s_alive[ll] == 0) ll--;
 					if (ll >= 0) { bin = ll; pos = 0; }   // position 0 of the LAST non-empty bin (bvec.cpp:68-77)
 				}
-				if (pos < s_alive[bin]) row = pa_select(A.alive_bits, s_row0[bin], s_row0[bin + 1], pos, center, lane);
+				if (pos < s_alive[bin]) row = pa_select(cur_bits, s_row0[bin], s_row0[bin + 1], pos, center_cur, lane);
 			} else {
-				pa_locate(A.alive_bits, s_row0[bin], s_row0[bin + 1], back ? rec.b_lt : rec.f_lt, back ? rec.b_le : rec.f_le, back,
-				          center, lane, pos, row);
+				pa_locate(cur_bits, s_row0[bin], s_row0[bin + 1], back ? rec.b_lt : rec.f_lt, back ? rec.b_le : rec.f_le, back,
+				          center_cur, lane, pos, row);
 			}
 			PA_TRACE_DEP(11, row);
 			if (lane == 0) {
@@ -677,16 +750,16 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				// the first tile of this step that lands in this lane's slot, then every D-th
 				unsigned u = ((unsigned)dpos + (unsigned)D - ring_cnt % (unsigned)D) % (unsigned)D;
 				for (; u < nw; u += (unsigned)D) {
-					if (slot_used) mbar_wait(&empty_bar[lane], (slot_uses - 1u) & 1u);
+					if (slot_used) mbar_wait_or_trap(&empty_bar[lane], (slot_uses - 1u) & 1u);
 					slot_used = true;
 					slot_uses++;
 					const long long r0 = (cbeg + w + (long long)u * NCW) * T::RT;
-					long long nr = A.n - r0;
+					long long nr = n_cur - r0;
 					if (nr > T::RT) nr = T::RT;
 					uint8_t *dst = ring + (size_t)lane * T::STAGE_BYTES;
 					mbar_expect_tx(&full_bar[lane], (uint32_t)(nr * RB + nr * 32));
-					tma_bulk_g2s(dst, A.hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[lane]);
-					tma_bulk_g2s(dst + T::ROW_BYTES, A.aux + r0, (uint32_t)(nr * 32), &full_bar[lane]);
+					tma_bulk_g2s(dst, cur_hist + (size_t)r0 * RB, (uint32_t)(nr * RB), &full_bar[lane]);
+					tma_bulk_g2s(dst + T::ROW_BYTES, cur_aux + r0, (uint32_t)(nr * 32), &full_bar[lane]);
 				}
 				ring_cnt = (ring_cnt + nw) % (2u * (unsigned)D);
 			}
@@ -706,10 +779,10 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				const long long row_mine = tile * T::RT + lane;
 				const long long word = (tile * T::RT) >> 5;
 				const int shift = (int)((tile * T::RT) & 31);
-				const uint32_t aw = __ldcg(A.alive_bits + word);
-				const bool have_row = lane < T::RT && row_mine >= lo && row_mine <= hi && ((aw >> (shift + lane)) & 1u) && row_mine != center;
+				const uint32_t aw = __ldcg(cur_bits + word);
+				const bool have_row = lane < T::RT && row_mine >= lo && row_mine <= hi && ((aw >> (shift + lane)) & 1u) && row_mine != center_cur;
 				const int slot = cw * D + (int)rslot;
-				mbar_wait(&full_bar[slot], rpar);
+				mbar_wait_or_trap(&full_bar[slot], rpar);
 				if (++rslot == (unsigned)D) { rslot = 0; rpar ^= 1u; }
 				if (u == 0) PA_TRACE_C(23, 0);
 				const uint8_t *st = ring + (size_t)slot * T::STAGE_BYTES;
@@ -755,7 +828,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 					if (lane == 0) s_any_marks = 1;
 					for (unsigned mm = mask; mm; mm &= mm - 1) {
 						const long long mrow = tile * T::RT + (__ffs(mm) - 1);
-						const uint32_t *src = reinterpret_cast<const uint32_t *>(A.hist + (size_t)mrow * RB);
+						const uint32_t *src = reinterpret_cast<const uint32_t *>(cur_hist + (size_t)mrow * RB);
 						for (int wd = lane; wd < RB / 4; wd += 32) {
 							const uint32_t v = __ldg(src + wd);
 							if (TB == 1) {
@@ -886,7 +959,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		// no CTA is looking for this cluster's seed any more: its bit goes (returning form: performed before
 		// the next block-wide barrier lets any thread of this CTA read the word again without the mask)
 		if (first_step && wib == PA_WARPS - 1 && lane == 0) {
-			const unsigned old = atomicAnd(A.alive_bits + (center >> 5), ~(1u << (center & 31)));
+			const unsigned old = atomicAnd(cur_bits + (center_cur >> 5), ~(1u << (center_cur & 31)));
 			unsigned z;
 			asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(old));
 			if (z) s_sink = 1;   // never true: waits for the atomic
@@ -900,7 +973,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 			// arg-max of f0 becomes the next seed, or the first point of the bvec when there is none
 			if (wib == 0) {
 				long long r = tot.best_row;
-				if (r < 0) r = pop_row(was_first ? center : -1);
+				if (r < 0) r = pop_row(was_first ? center_cur : -1);
 				if (lane == 0) {
 					s_seed = r;
 					if (r >= 0) s_alive[bin_of(r)]--;
@@ -924,13 +997,151 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				pa_retire(ret, &s_sink);   // performed before this CTA's next record (block barrier below)
 			}
 			__syncthreads();
-			const long long seed = s_seed;
+			const long long seed = s_seed;   // a current row
 			cluster++;
 			cl_begin += m0;
 			m0 = 1;
 			first_step = true;
-			center = seed;
-			if (seed >= 0 && cta == 0 && threadIdx.x == 0) A.members[cl_begin] = (int)seed;
+			center_cur = seed;
+			PA_CHECK(seed < n_cur, 107);
+			center = seed >= 0 ? to_orig(seed) : -1;
+			PA_CHECK(center < A.n, 108);
+			if (seed >= 0) alive_cnt--;
+			// ---------- row compaction (ClusterFactory.cpp has nothing like it: the bvec forgets removed points, the row
+			// arrays here do not).  At a cluster boundary, once at most 1 - 2^-shift of the current rows are still set in
+			// the bitmap, the set ones are copied in order into the next staging buffer and renumbered.  The seed's bit is
+			// still set (its clearing is pending), so it travels like any other row: nothing of the protocol changes.
+			if (seed >= 0 && A.st_hist[0] && n_cur >= A.compact_min && alive_cnt + 1 <= n_cur - (n_cur >> A.compact_shift) &&
+			    alive_cnt + 1 <= A.st_cap[n_compact & 1]) {
+				const int sb = n_compact & 1;
+				uint8_t *nh = A.st_hist[sb];
+				McRowAux *na = A.st_aux[sb];
+				int *no = A.st_orig[sb];
+				PaRange *nr = A.st_range[sb];
+				uint32_t *nbits = A.st_bits[sb];
+				const int seed_bin = bin_of(seed);
+				// new bin starts: the alive rows of every bin, plus the seed in its own
+				if (wib == 0) {
+					unsigned carry = 0;
+					for (int i0 = 0; i0 <= nb; i0 += 32) {
+						const int i = i0 + lane;
+						const unsigned v = i < nb ? s_alive[i] + (i == seed_bin ? 1u : 0u) : 0u;
+						unsigned incl = v;
+#pragma unroll
+						for (int o = 1; o < 32; o <<= 1) {
+							const unsigned u = __shfl_up_sync(MC_FULL_MASK, incl, o);
+							if (lane >= o) incl += u;
+						}
+						if (i <= nb) s_row0n[i] = carry + incl - v;
+						carry += __shfl_sync(MC_FULL_MASK, incl, 31);
+					}
+				}
+				__syncthreads();
+				const long long n_new_rows = s_row0n[nb];
+				// this CTA's share of the OLD rows: whole bitmap words
+				const long long W = (n_cur + 31) >> 5;
+				const long long W0 = W * cta / G, W1 = W * (cta + 1) / G;
+				const int nwords = (int)(W1 - W0);   // <= qmax (a tile is at most 32 rows)
+				if (wib == 0) {
+					// rows set before this share: whole bins from the new starts, the rest of the first bin by popcount
+					unsigned long long rank0 = 0;
+					if (nwords > 0) {
+						const long long r0 = W0 << 5;
+						const int b0 = bin_of(r0 < n_cur ? r0 : n_cur - 1);
+						unsigned ra, rb, tot = 0;
+						if (r0 > (long long)s_row0[b0]) pa_rank3(cur_bits, s_row0[b0], r0, 0, 0, -1, lane, ra, rb, tot);
+						rank0 = (unsigned long long)s_row0n[b0] + tot;
+					}
+					unsigned carry = 0;
+					for (int i0 = 0; i0 < nwords; i0 += 32) {
+						const int i = i0 + lane;
+						uint32_t v = 0;
+						if (i < nwords) {
+							v = __ldcg(cur_bits + W0 + i);
+							const long long rbase = (W0 + i) << 5;
+							if (rbase + 32 > n_cur) v &= (n_cur > rbase) ? (0xffffffffu >> (32 - (int)(n_cur - rbase))) : 0u;
+							s_marks[i] = v;
+						}
+						const unsigned pc = __popc(v);
+						unsigned incl = pc;
+#pragma unroll
+						for (int o = 1; o < 32; o <<= 1) {
+							const unsigned u = __shfl_up_sync(MC_FULL_MASK, incl, o);
+							if (lane >= o) incl += u;
+						}
+						if (i < nwords) s_mpref[i] = carry + incl - pc;
+						carry += __shfl_sync(MC_FULL_MASK, incl, 31);
+					}
+					if (lane == 0) s_base = (long long)rank0;
+				}
+				__syncthreads();
+				const long long rank0 = s_base;
+				// copy: one warp per bitmap word; the 16-byte units of the word's set rows as one flat index space, eight
+				// loads per lane in flight (lane r knows where the r-th set row is)
+				for (int i = wib; i < nwords; i += PA_WARPS) {
+					const uint32_t mm = s_marks[i];
+					const int cnt = __popc(mm);
+					if (cnt == 0) continue;
+					const long long dst0 = rank0 + s_mpref[i], src0 = (W0 + i) << 5;
+					PA_CHECK(src0 + (31 - __clz(mm)) < n_cur && dst0 + cnt <= A.st_cap[sb] && dst0 + cnt <= n_new_rows, 102);
+					const int pos = lane < cnt ? (int)__fns(mm, 0, lane + 1) : 0;
+					constexpr int U = RB / 16;   // a power of two
+					const int total = cnt * U;
+					for (int base = 0; base < total; base += 32 * 8) {
+						uint4 v[8];
+#pragma unroll
+						for (int j = 0; j < 8; j++) {
+							const int idx = base + j * 32 + lane;
+							const int r = idx / U < cnt ? idx / U : cnt - 1;
+							const int srow = __shfl_sync(MC_FULL_MASK, pos, r);
+							if (idx < total) v[j] = __ldcg(reinterpret_cast<const uint4 *>(cur_hist + (size_t)(src0 + srow) * RB) + (idx % U));
+						}
+#pragma unroll
+						for (int j = 0; j < 8; j++) {
+							const int idx = base + j * 32 + lane;
+							if (idx < total) reinterpret_cast<uint4 *>(nh + (size_t)(dst0 + idx / U) * RB)[idx % U] = v[j];
+						}
+					}
+					if (lane < cnt) {
+						const uint4 *pa = reinterpret_cast<const uint4 *>(cur_aux + src0 + pos);
+						const uint4 a0 = __ldcg(pa), a1 = __ldcg(pa + 1);
+						uint4 *qa = reinterpret_cast<uint4 *>(na + dst0 + lane);
+						qa[0] = a0; qa[1] = a1;
+						no[dst0 + lane] = (int)to_orig(src0 + pos);
+					}
+				}
+				// the new bitmap: every row set
+				{
+					const long long Wn = (n_new_rows + 31) >> 5;
+					for (long long w = Wn * cta / G + threadIdx.x; w < Wn * (cta + 1) / G; w += PA_THREADS) {
+						const long long left = n_new_rows - (w << 5);
+						nbits[w] = left >= 32 ? 0xffffffffu : (0xffffffffu >> (32 - (int)left));
+					}
+				}
+				// where the seed went: the rows set before it in its bin
+				if (wib == 1) {
+					unsigned ra, rb, tot = 0;
+					if (seed > (long long)s_row0[seed_bin]) pa_rank3(cur_bits, s_row0[seed_bin], seed, 0, 0, -1, lane, ra, rb, tot);
+					if (lane == 0) s_new_center = (long long)s_row0n[seed_bin] + tot;
+				}
+				asm volatile("fence.proxy.async;" ::: "memory");   // (writer side: generic stores -> bulk copies of other SMs)
+				__threadfence();
+				if (!pa_grid_barrier(A.bar, ++cbar * (unsigned long long)G, &s_ok)) return;
+				// the search records of the new rows, over all threads of the grid
+				for (long long j = (long long)cta * PA_THREADS + threadIdx.x; j < n_new_rows; j += (long long)G * PA_THREADS)
+					nr[j] = pa_make_range(na, j, s_bounds, s_row0n, nb, A.sim);
+				__threadfence();
+				if (!pa_grid_barrier(A.bar, ++cbar * (unsigned long long)G, &s_ok)) return;
+				asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies of the next scan read what generic stores wrote
+				for (int i = threadIdx.x; i <= nb; i += PA_THREADS) s_row0[i] = s_row0n[i];
+				cur_hist = nh; cur_aux = na; cur_orig = no; cur_range = nr; cur_bits = nbits;
+				n_cur = n_new_rows;
+				center_cur = s_new_center;
+				PA_CHECK(center_cur >= 0 && center_cur < n_cur, 103);
+				n_compact++;
+				__syncthreads();
+			}
+			if (seed >= 0 && cta == 0 && threadIdx.x == 0) { A.members[cl_begin] = (int)center; A.mcur[cl_begin] = (int)center_cur; }
 			PA_TRACE(7);
 			continue;
 		}
@@ -979,11 +1190,12 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		for (int w = 0; w < PA_WARPS; w++) magc += s_red[w];
 		PaNear best;
 		best.pos = -1; best.dist = 0; best.row = -1; best.pad = 0;
-		auto consider = [&](long long row, long long pos) {
-			const PairAcc<TB> pa = mc_warp_pair_reduce<TB>(A.hist + (size_t)row * RB, s_tq, RB, lane);
-			const uint64_t mp = A.aux[row].mag;
+		// a candidate: its histogram row (either numbering's array holds the same bytes), its position in `current`,
+		// and its row in both numberings (the winner becomes the center)
+		auto consider = [&](const uint8_t *hrow, uint64_t mp, long long row_orig, long long row_cur, long long pos) {
+			const PairAcc<TB> pa = mc_warp_pair_reduce<TB>(hrow, s_tq, RB, lane);
 			PaNear cnd;
-			cnd.pos = pos; cnd.row = row; cnd.pad = 0;
+			cnd.pos = pos; cnd.row = row_orig; cnd.pad = row_cur;
 			cnd.dist = mc_distance_d(pa.summin(mp, magc), mp, magc);
 			pa_near_merge(best, cnd);   // NaN never replaces, like the reference's `<`
 		};
@@ -994,26 +1206,34 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 			const unsigned mask = s_marks[i];
 			if (mask) {   // the rows leave the bvec (visible to every CTA behind exchange 2)
 				const long long trow = (cbeg + i) * T::RT;
-				ret |= atomicAnd(A.alive_bits + (trow >> 5), ~(mask << (int)(trow & 31)));
+				ret |= atomicAnd(cur_bits + (trow >> 5), ~(mask << (int)(trow & 31)));
 			}
 		}
 		for (int k = wib; k < s_cta_marks; k += PA_WARPS) {
 			int tl = 0, th = qc - 1;   // last tile whose prefix is <= k
 			while (tl < th) { const int mid = (tl + th + 1) >> 1; if ((int)s_mpref[mid] <= k) tl = mid; else th = mid - 1; }
-			const long long row = (cbeg + tl) * T::RT + __fns(s_marks[tl], 0, k - (int)s_mpref[tl] + 1);
+			const long long row = (cbeg + tl) * T::RT + __fns(s_marks[tl], 0, k - (int)s_mpref[tl] + 1);   // a current row
 			const long long pos = m0 + s_base + k;
+			PA_CHECK(row >= 0 && row < n_cur, 104);
+			const long long row_orig = to_orig(row);
+			PA_CHECK(row_orig >= 0 && row_orig < A.n, 105);
 			if (lane == 0) {
 #if PA_RELEASE_BY_FENCE
-				A.members[cl_begin + pos] = (int)row;
+				A.members[cl_begin + pos] = (int)row_orig;
+				A.mcur[cl_begin + pos] = (int)row;
 #else
-				ret |= (unsigned)atomicExch(A.members + cl_begin + pos, (int)row);
+				ret |= (unsigned)atomicExch(A.members + cl_begin + pos, (int)row_orig);
+				ret |= (unsigned)atomicExch(A.mcur + cl_begin + pos, (int)row);
 #endif
 			}
-			consider(row, pos);
+			consider(cur_hist + (size_t)row * RB, cur_aux[row].mag, row_orig, row, pos);
 		}
 		// its share of the members `current` already had
-		for (long long idx = (long long)cta * PA_WARPS + wib; idx < m0; idx += (long long)G * PA_WARPS)
-			consider(__ldcg(A.members + cl_begin + idx), idx);
+		for (long long idx = (long long)cta * PA_WARPS + wib; idx < m0; idx += (long long)G * PA_WARPS) {
+			const long long ro = __ldcg(A.members + cl_begin + idx), rc = __ldcg(A.mcur + cl_begin + idx);
+			PA_CHECK(ro >= 0 && ro < A.n && rc >= 0 && rc < n_cur, 106);
+			consider(A.hist + (size_t)ro * RB, A.aux[ro].mag, ro, rc, idx);
+		}
 		if (lane == 0) warp_near[wib] = best;
 		pa_retire(ret, &s_sink);
 		PA_TRACE_DEP(17, best.row);
@@ -1031,7 +1251,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 					q.pos = __shfl_xor_sync(MC_FULL_MASK, x.pos, o);
 					q.dist = __shfl_xor_sync(MC_FULL_MASK, x.dist, o);
 					q.row = __shfl_xor_sync(MC_FULL_MASK, x.row, o);
-					q.pad = 0;
+					q.pad = __shfl_xor_sync(MC_FULL_MASK, x.pad, o);
 					pa_near_merge(x, q);
 				}
 			};
@@ -1046,23 +1266,24 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				case 1: wv = (uint32_t)db; break;
 				case 2: wv = (uint32_t)(db >> 32); break;
 				case 3: wv = (uint32_t)(int)b.row; break;
+				case 4: wv = (uint32_t)(int)b.pad; break;   // the same row in the current numbering
 				default: break;
 				}
-				if (lane < 4) pa_ll_store(my_near + lane, wv, tag);
+				if (lane < 6) pa_ll_store(my_near + lane, wv, tag);
 			}
 			PA_TRACE(5);
-			uint32_t d[PA_RPL][4];
+			uint32_t d[PA_RPL][6];
 			unsigned have = 0;
 #pragma unroll
 			for (int j = 0; j < PA_RPL; j++) {
 				const int i = lane + 32 * j;
-				if (i >= G) { have |= 1u << j; d[j][0] = 0xffffffffu; d[j][1] = 0; d[j][2] = 0; d[j][3] = 0xffffffffu; }
-				else if (pa_rec_try<4>(A.near_recs + ((size_t)par * G + i) * PA_REC_WORDS, tag, d[j])) have |= 1u << j;
+				if (i >= G) { have |= 1u << j; d[j][0] = 0xffffffffu; d[j][1] = 0; d[j][2] = 0; d[j][3] = 0xffffffffu; d[j][4] = 0xffffffffu; d[j][5] = 0; }
+				else if (pa_rec_try<6>(A.near_recs + ((size_t)par * G + i) * PA_REC_WORDS, tag, d[j])) have |= 1u << j;
 			}
 			bool ok = true;
 #pragma unroll
 			for (int j = 0; j < PA_RPL; j++)
-				if (ok && !((have >> j) & 1u)) ok = pa_rec_wait<4>(A.near_recs + ((size_t)par * G + lane + 32 * j) * PA_REC_WORDS, tag, d[j], A.bar + 1);
+				if (ok && !((have >> j) & 1u)) ok = pa_rec_wait<6>(A.near_recs + ((size_t)par * G + lane + 32 * j) * PA_REC_WORDS, tag, d[j], A.bar + 1);
 			PaNear t;
 			t.pos = -1; t.dist = 0; t.row = -1; t.pad = 0;
 #pragma unroll
@@ -1071,20 +1292,22 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 				q.pos = (long long)(int)d[j][0];
 				q.dist = __longlong_as_double((long long)(((unsigned long long)d[j][2] << 32) | d[j][1]));
 				q.row = (long long)(int)d[j][3];
-				q.pad = 0;
+				q.pad = (long long)(int)d[j][4];
 				pa_near_merge(t, q);
 			}
 			ok = __all_sync(MC_FULL_MASK, ok);
 			fold_near(t);
-			if (lane == 0) { s_new_center = t.row; s_ok = ok ? 1 : 0; }
+			if (lane == 0) { s_new_center = t.row; s_seed = t.pad; s_ok = ok ? 1 : 0; }
 		}
 		__syncthreads();
 		if (!s_ok) return;
 		PA_TRACE(6);
 		// every CTA keeps its own bin counts: the new members leave their bins
 		for (long long i = threadIdx.x; i < n_new; i += PA_THREADS)
-			atomicSub(&s_alive[bin_of(__ldcg(A.members + cl_begin + m0 + i))], 1u);
+			atomicSub(&s_alive[bin_of(__ldcg(A.mcur + cl_begin + m0 + i))], 1u);
 		center = s_new_center;   // get_mean always finds a member: `current` is never empty
+		center_cur = s_seed;
+		alive_cnt -= n_new;
 		m0 = m_all;
 		__syncthreads();
 		PA_TRACE(7);
@@ -1099,6 +1322,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) phase_a_kernel(const __grid_con
 		A.stats[3] = st_near;
 		A.stats[4] = step;
 		A.stats[5] = (long long)(t_end - t_start);
+		A.stats[6] = n_compact;
 	}
 }
 
@@ -1115,7 +1339,7 @@ static int pa_launch_t(mc_ctx *ctx, PaArgs &a, int grid) {
 	constexpr int NB = RB / TB;
 	int dev_smem = 0;
 	MC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-	const size_t fixed = (size_t)a.nb * 8 + (size_t)(a.nb + 1) * 4 + (size_t)a.nb * 4 + (size_t)NB * 4 + (size_t)a.qmax * 8 + 16 + RB + 128 + 128;
+	const size_t fixed = (size_t)a.nb * 8 + 2 * (size_t)(a.nb + 1) * 4 + (size_t)a.nb * 4 + (size_t)NB * 4 + (size_t)a.qmax * 8 + 16 + RB + 128 + 128;
 	const size_t static_smem = 4096;   // barriers, warp partials, control words (upper bound)
 	MC_REQUIRE(fixed + static_smem + 2 * (size_t)T::STAGE_BYTES <= (size_t)dev_smem, MC_ERR_UNSUPPORTED,
 	           "mc_accumulate_run: %d bvec bins / %lld rows need more shared memory than one CTA has", a.nb, (long long)a.n);
@@ -1167,7 +1391,9 @@ bool mc_pa_shape_supported(int tbytes, int nbins) {
 int mc_launch_phase_a(mc_ctx *ctx, const unsigned long long *bounds_dev, const int *row0_dev, int nb, const void *range_tab_dev,
                       uint32_t *alive_bits_dev, unsigned long long *g_sum_dev, void *exch_dev,
                       unsigned long long *bar_dev, int *members_dev, int *cl_center_dev, int *cl_off_dev, long long *stats_dev,
-                      unsigned long long *trace_dev, int trace_steps, int grid, int qmax) {
+                      unsigned long long *trace_dev, int trace_steps, int grid, int qmax, int *mcur_dev, double sim,
+                      void *const *staging /* [2][5]: hist, aux, orig, range, bits; null = no compaction */, const long long *staging_cap,
+                      long long compact_min, int compact_shift) {
 	PaArgs a{};
 	a.hist = (const uint8_t *)ctx->d_hist;
 	a.aux = ctx->d_aux;
@@ -1186,6 +1412,18 @@ int mc_launch_phase_a(mc_ctx *ctx, const unsigned long long *bounds_dev, const i
 	}
 	a.bar = bar_dev;
 	a.members = members_dev;
+	a.mcur = mcur_dev;
+	a.sim = sim;
+	a.compact_min = compact_min;
+	a.compact_shift = compact_shift;
+	for (int b = 0; b < 2; b++) {
+		a.st_hist[b] = staging ? (uint8_t *)staging[b * 5 + 0] : nullptr;
+		a.st_aux[b] = staging ? (McRowAux *)staging[b * 5 + 1] : nullptr;
+		a.st_orig[b] = staging ? (int *)staging[b * 5 + 2] : nullptr;
+		a.st_range[b] = staging ? (PaRange *)staging[b * 5 + 3] : nullptr;
+		a.st_bits[b] = staging ? (uint32_t *)staging[b * 5 + 4] : nullptr;
+		a.st_cap[b] = staging ? staging_cap[b] : 0;
+	}
 	a.cl_center = cl_center_dev;
 	a.cl_off = cl_off_dev;
 	a.stats = stats_dev;

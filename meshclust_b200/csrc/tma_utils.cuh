@@ -24,6 +24,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 		"DONE_%=:\n"
 		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// the same for persistent kernels: a copy that never lands (a bug, not a slow one: ~10 s of polling) ends the
+// kernel with a trap -- an error the host sees -- instead of a hang
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t *bar, uint32_t parity) {
+	for (unsigned spins = 0;; spins++) {
+		uint32_t ok;
+		asm volatile(
+			"{\n"
+			".reg .pred p;\n"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+			"selp.u32 %0, 1, 0, p;\n"
+			"}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		if (ok) return;
+		if (spins > (1u << 26)) __trap();
+	}
+}
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");

@@ -659,8 +659,9 @@ void mean_shift(Ctx &c, BVec &bv) {
 				part[(size_t)ci].center_row = centers[(size_t)ci];
 				part[(size_t)ci].rows.assign(members.begin() + offs[(size_t)ci], members.begin() + offs[(size_t)ci + 1]);
 			}
-			printf("Accumulation: %zu clusters, %lld scans, %lld evals, on the device in %.4fs (%.2f us per step)  [%.2fs]\n", part.size(),
-			       (long long)st.n_scans, (long long)st.n_evals, st.device_seconds, st.n_steps ? st.device_seconds * 1e6 / (double)st.n_steps : 0.0, tm.lap());
+			printf("Accumulation: %zu clusters, %lld scans, %lld evals, on the device in %.4fs (%.2f us per step), %lld row compactions  [%.2fs]\n", part.size(),
+			       (long long)st.n_scans, (long long)st.n_evals, st.device_seconds, st.n_steps ? st.device_seconds * 1e6 / (double)st.n_steps : 0.0,
+			       (long long)st.n_compactions, tm.lap());
 			phase_a_done = true;
 		} else if (rc != MC_ERR_UNSUPPORTED) {
 			die_gpu("mc_accumulate_run");

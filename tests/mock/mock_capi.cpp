@@ -348,7 +348,7 @@ int mc_accumulate_run(mc_ctx *c, double sim, const uint64_t *bin_bounds, const i
 		offs_out[++nc] = total;
 		last = next_seed;
 	}
-	if (st) { st->n_clusters = nc; st->n_scans = scans; st->n_evals = evals; st->n_near_threshold = c->near - near0; st->n_steps = steps; st->device_seconds = 0; }
+	if (st) { st->n_clusters = nc; st->n_scans = scans; st->n_evals = evals; st->n_near_threshold = c->near - near0; st->n_steps = steps; st->device_seconds = 0; st->n_compactions = 0; }
 	return MC_OK;
 }
 

@@ -560,6 +560,19 @@ def test_accumulate_run_vs_step_loop(ctx, dtype, hi, k, n, sim, bin_size, spread
     assert st.n_near_threshold == near_steps == ctx.near_threshold_count()
     assert st.n_clusters == centers.size >= 2
     assert (np.diff(offs) > 1).sum() >= 2, "the test model never marks anything: no mean was exercised"
+    # the same run with row compactions (the alive rows copied together whenever an eighth / half of them are gone;
+    # inputs of this size do not compact by themselves): two row numberings inside the kernel, the same clusters outside
+    import os
+    for shift in ("3", "1"):
+        os.environ["MC_PA_COMPACT_MIN"] = "64"
+        os.environ["MC_PA_COMPACT_SHIFT"] = shift
+        try:
+            c2, o2, m2, st2 = ctx.accumulate_run(sim, bounds, first)
+        finally:
+            del os.environ["MC_PA_COMPACT_MIN"], os.environ["MC_PA_COMPACT_SHIFT"]
+        assert np.array_equal(c2, centers) and np.array_equal(o2, offs) and np.array_equal(m2, members)
+        assert (st2.n_scans, st2.n_evals, st2.n_steps, st2.n_near_threshold) == (st.n_scans, st.n_evals, st.n_steps, st.n_near_threshold)
+        assert st2.n_compactions >= (1 if n >= 500 else 0) and st.n_compactions == 0
 
 
 def test_accumulate_run_rejects_unsorted_bins(ctx):
