@@ -140,61 +140,71 @@ __device__ __forceinline__ uint32_t k1_codes4_check(uint32_t w, bool &fast) {
 	return x;
 }
 
-__device__ __forceinline__ uint32_t k1_codes4(uint32_t w, const uint8_t *lut, bool &fast) {
-	// A 0x41 C 0x43 G 0x47 T 0x54: bits 2..1 are 00 01 11 10 -> code = x ^ (x >> 1)
+// the 2-bit codes of four letters (one per byte, first letter in byte 0) by arithmetic, valid for A, C, G, T in either
+// case: A 0x41 C 0x43 G 0x47 T 0x54, bits 2..1 are 00 01 11 10 -> code = x ^ (x >> 1).  `diff` collects, over the
+// words of a chunk, the bits in which a word differs from the letters its codes stand for (picked from "ACGT" by one
+// byte permute, selector = code per nibble): zero <=> every letter was plain.
+__device__ __forceinline__ uint32_t k1_codes4_acc(uint32_t w, uint32_t &diff) {
 	uint32_t x = (w >> 1) & 0x03030303u;
 	x ^= (x >> 1) & 0x01010101u;
-	// the letters these codes stand for, picked from "ACGT" by one byte permute (selector = code per nibble)
 	const uint32_t s = x | (x >> 4);
-	const uint32_t sel = (s & 0xffu) | ((s >> 8) & 0xff00u);
-	fast = __byte_perm(0x54474341u, 0u, sel) == (w & 0xdfdfdfdfu);
-	if (!fast) {
-		x = (uint32_t)(lut[w & 0xffu] & 3u) | ((uint32_t)(lut[(w >> 8) & 0xffu] & 3u) << 8) |
-		    ((uint32_t)(lut[(w >> 16) & 0xffu] & 3u) << 16) | ((uint32_t)(lut[w >> 24] & 3u) << 24);
-	}
+	const uint32_t sel = (s & 0x00ffu) | ((s >> 8) & 0xff00u);
+	diff |= __byte_perm(0x54474341u, 0u, sel) ^ (w & 0xdfdfdfdfu);
 	return x;
 }
 
-// four codes (one per byte, first letter in byte 0) -> 8 bits, first letter in the top two
-__device__ __forceinline__ uint32_t k1_pack4(uint32_t x) {
-	const uint32_t r = __byte_perm(x, 0u, 0x0123u);   // first letter into the most significant byte
-	const uint32_t y = r | (r >> 6);
-	return (y & 0xfu) | ((y >> 12) & 0xf0u);
+// the same through the 256-entry table (IUPAC codes, N inside a merged segment -> C, digit strings of an encoded buffer)
+__device__ __forceinline__ uint32_t k1_codes4_lut(uint32_t w, const uint8_t *lut) {
+	return (uint32_t)(lut[w & 0xffu] & 3u) | ((uint32_t)(lut[(w >> 8) & 0xffu] & 3u) << 8) |
+	       ((uint32_t)(lut[(w >> 16) & 0xffu] & 3u) << 16) | ((uint32_t)(lut[w >> 24] & 3u) << 24);
 }
 
+// sixteen letters -> one 32-bit word of 2-bit codes, first letter in the two most significant bits.  Four codes
+// (bits 1..0 of the bytes of x) are gathered into the top byte of x * 0x40100401: the multiplier places code i at
+// bit 30 - 2 i, and every partial product is a 2-bit field of its own (no carries); three byte permutes collect the
+// four top bytes.
 __device__ __forceinline__ uint32_t k1_pack16(const uint4 v, const uint8_t *lut) {
-	bool f0, f1, f2, f3;
-	const uint32_t a = k1_pack4(k1_codes4(v.x, lut, f0)), b = k1_pack4(k1_codes4(v.y, lut, f1));
-	const uint32_t c = k1_pack4(k1_codes4(v.z, lut, f2)), d = k1_pack4(k1_codes4(v.w, lut, f3));
-	return (a << 24) | (b << 16) | (c << 8) | d;
+	uint32_t diff = 0;
+	uint32_t a = k1_codes4_acc(v.x, diff), b = k1_codes4_acc(v.y, diff), c = k1_codes4_acc(v.z, diff), d = k1_codes4_acc(v.w, diff);
+	if (diff) {   // rare: some letter of the chunk is not a plain A, C, G or T
+		a = k1_codes4_lut(v.x, lut); b = k1_codes4_lut(v.y, lut); c = k1_codes4_lut(v.z, lut); d = k1_codes4_lut(v.w, lut);
+	}
+	constexpr uint32_t M = 0x40100401u;
+	const uint32_t lo = __byte_perm(d * M, c * M, 0x0073u);   // {top byte of d, top byte of c}
+	const uint32_t hi = __byte_perm(b * M, a * M, 0x0073u);
+	return __byte_perm(lo, hi, 0x5410u);
 }
 
-template <int TB>
+// K = k as a compile-time constant: every shift of the inner loop is an immediate
+template <int TB, int K>
 __global__ void __launch_bounds__(256)
 kmer_count_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
                   const int32_t *__restrict__ segs, const int64_t *__restrict__ seg_off,
-                  long long n, int k, uint8_t *__restrict__ hist,
+                  long long n, uint8_t *__restrict__ hist,
                   McRowAux *__restrict__ aux_out, unsigned int *__restrict__ flags) {
-	extern __shared__ uint32_t tables[];
+	extern __shared__ uint32_t tables_raw[];
 	__shared__ uint8_t lut[256];
 	// N swallowed by a merged segment counts as C (ChromosomeOneDigit.cpp:59-85); digits stay what they are
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) {
 		const uint8_t c = c_code_lut[i];
 		lut[i] = i < 4 ? (uint8_t)i : (c == 4 ? 1 : c);
 	}
-	__syncthreads();
-	const int nbins = 1 << (2 * k);
+	constexpr int nbins = 1 << (2 * K);
+	constexpr uint32_t TABLE_BYTES = (uint32_t)nbins * 4u;
+	constexpr uint32_t IDX_MASK = (uint32_t)(nbins - 1) << 2;
 	const int lane = threadIdx.x & 31;
 	const int wib = threadIdx.x >> 5;
-	uint32_t *tab = tables + (size_t)wib * nbins;
-	const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
-	const int top = 32 - 2 * k;   // the k-mer is the top 2k bits of the shifted window
+	// the warp's table starts at a multiple of its size in the shared window: address = table | (k-mer << 2), one LOP3
+	const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(tables_raw);
+	const uint32_t base_s = (raw_s + TABLE_BYTES - 1u) & ~(TABLE_BYTES - 1u);
+	uint32_t *tab = tables_raw + (base_s - raw_s) / 4u + (size_t)wib * nbins;
+	const uint32_t tab_s = base_s + (uint32_t)wib * TABLE_BYTES;
+	for (int i = lane; i < nbins; i += 32) tab[i] = 0;   // (every row write-out leaves the table zeroed again)
+	__syncthreads();
 	const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
 	const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
 	unsigned int local_max = 0;
 	for (long long s = warp; s < n; s += nwarps) {
-		for (int i = lane; i < nbins; i += 32) tab[i] = 0;
-		__syncwarp();
 		const long long b0 = seq_off[s], b1 = seq_off[s + 1];
 		const long long g0 = seg_off[s], g1 = seg_off[s + 1];
 		const uint8_t *sbase = seq + (b0 & ~15LL);         // 16-byte aligned; positions below are relative to it
@@ -203,7 +213,7 @@ kmer_count_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ s
 		for (long long gi = g0; gi < g1; gi++) {
 			// k-mer starts [ss, last] inside this segment
 			const int ss = off0 + segs[2 * gi];
-			const int last = off0 + segs[2 * gi + 1] - k + 1;
+			const int last = off0 + segs[2 * gi + 1] - K + 1;
 			if (last < ss) continue;
 			const int c_first = ss >> 4, c_last = last >> 4;   // chunks (16 letters) with a k-mer start
 			const int end = off0 + len;                        // letters of this sequence end here
@@ -211,6 +221,10 @@ kmer_count_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ s
 				if (16 * c >= end) return 0u;                  // (the buffer has a 64-byte tail: a chunk that starts inside is whole)
 				return k1_pack16(*reinterpret_cast<const uint4 *>(sbase + 16 * c), lut);
 			};
+			// Every chunk of [c_first, c_last] counts ALL sixteen of its starts, without a predicate; the starts of
+			// the first chunk that lie before the segment and those of the last chunk behind `last` are taken back
+			// afterwards (one lane per start): the same words give the same k-mers, +1 - 1 cancels exactly.
+			uint32_t hp = 0, hn = 0, tp = 0, tn = 0;
 			uint32_t pn = chunk_word(c_first + lane);
 			for (int c0 = c_first; c0 <= c_last; c0 += 32) {
 				const uint32_t pc = pn;
@@ -218,32 +232,40 @@ kmer_count_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ s
 				uint32_t nb = __shfl_down_sync(MC_FULL_MASK, pc, 1);
 				const uint32_t n0 = __shfl_sync(MC_FULL_MASK, pn, 0);
 				if (lane == 31) nb = n0;
-				const int c = c0 + lane;
-				// which of the 16 starts of this chunk count: bit j <=> ss <= 16c + j <= last
-				uint32_t vm = 0;
-				if (c <= c_last) {
-					const int lo = ss - 16 * c, hi = last - 16 * c;
-					vm = 0xffffu;
-					if (lo > 0) vm &= 0xffffu << lo;
-					if (hi < 15) vm &= 0xffffu >> (15 - hi);
-				}
-				// one predicated shared-memory reduction per start (inline PTX: a 32-bit shared address computed once;
-				// the compiler's form re-derives the shared window and opens a reconvergence region per k-mer)
+				if (c0 == c_first) { hp = __shfl_sync(MC_FULL_MASK, pc, 0); hn = __shfl_sync(MC_FULL_MASK, nb, 0); }
+				if (c_last - c0 < 32) { tp = __shfl_sync(MC_FULL_MASK, pc, c_last - c0); tn = __shfl_sync(MC_FULL_MASK, nb, c_last - c0); }
+				if (c0 + lane <= c_last) {
 #pragma unroll
-				for (int j = 0; j < 16; j++) {
-					const uint32_t addr = tab_s + ((__funnelshift_l(nb, pc, 2 * j) >> top) << 2);
-					asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n @p red.shared.add.u32 [%0], 1;\n}\n" ::"r"(addr), "r"(vm & (1u << j)) : "memory");
+					for (int j = 0; j < 16; j++) {
+						// (k-mer << 2) = bits of the 64-bit window pc:nb shifted right by 62 - 2j - 2K
+						const int sh = 62 - 2 * j - 2 * K;
+						const uint32_t t = sh >= 32 ? (pc >> (sh - 32)) : __funnelshift_r(nb, pc, sh);
+						const uint32_t addr = (t & IDX_MASK) | tab_s;
+						asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+					}
+				}
+			}
+			{
+				const int h = ss - 16 * c_first, tl = last - 16 * c_last;   // starts j < h of the first, j > tl of the last chunk
+				const int j = lane & 15;
+				const bool head = lane < 16;
+				const uint32_t p = head ? hp : tp, q = head ? hn : tn;
+				const uint32_t kmer = __funnelshift_l(q, p, 2 * j) >> (32 - 2 * K);
+				if (head ? j < h : j > tl) {
+					const uint32_t addr = (kmer << 2) | tab_s;
+					asm volatile("red.shared.add.u32 [%0], 0xffffffff;" ::"r"(addr) : "memory");
 				}
 			}
 		}
 		__syncwarp();
-		// write the row: count + 1 (pseudo-count), narrowed to TB bytes
+		// write the row: count + 1 (pseudo-count), narrowed to TB bytes; the table is left zeroed
 		unsigned long long m = 0, q = 0;
 		if (TB == 1) {
 			uint8_t *row = hist + (size_t)s * nbins;
 			if (nbins >= 128) {
 				for (int i = lane * 4; i < nbins; i += 128) {
 					const uint4 t = *reinterpret_cast<const uint4 *>(tab + i);
+					*reinterpret_cast<uint4 *>(tab + i) = make_uint4(0u, 0u, 0u, 0u);
 					const uint32_t c0 = t.x + 1, c1 = t.y + 1, c2 = t.z + 1, c3 = t.w + 1;
 					local_max = max(max(local_max, c0), max(c1, max(c2, c3)));
 					m += c0 + c1 + c2 + c3;
@@ -253,6 +275,7 @@ kmer_count_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ s
 			} else {
 				for (int i = lane; i < nbins; i += 32) {
 					const uint32_t c = tab[i] + 1;
+					tab[i] = 0;
 					local_max = max(local_max, c);
 					m += c; q += (unsigned long long)c * c;
 					row[i] = (uint8_t)c;
@@ -262,6 +285,7 @@ kmer_count_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ s
 			uint16_t *row = reinterpret_cast<uint16_t *>(hist) + (size_t)s * nbins;
 			for (int i = lane; i < nbins; i += 32) {
 				const uint32_t c = tab[i] + 1;
+				tab[i] = 0;
 				local_max = max(local_max, c);
 				m += c; q += (unsigned long long)c * c;
 				row[i] = (uint16_t)c;
@@ -335,26 +359,32 @@ int mc_launch_validate(mc_ctx *ctx) {
 	return MC_OK;
 }
 
-int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes) {
-	const int nbins = 1 << (2 * k);
-	const size_t per_warp = (size_t)nbins * 4;
+template <int TB, int K>
+static int k1_launch(mc_ctx *ctx) {
+	constexpr int nbins = 1 << (2 * K);
+	constexpr size_t per_warp = (size_t)nbins * 4;
 	int wpb = 8;
-	while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
-	MC_REQUIRE(per_warp * wpb <= 200 * 1024, MC_ERR_UNSUPPORTED, "k=%d needs a %zu-byte table per sequence; k <= 7 is supported", k, per_warp);
-	const size_t smem = per_warp * wpb;
+	while (wpb > 1 && per_warp * (wpb + 1) > 200 * 1024) wpb >>= 1;
+	const size_t smem = per_warp * (wpb + 1);   // + one table of slack: the tables start at a multiple of their size
 	const int threads = wpb * 32;
 	int64_t blocks = (ctx->n + wpb - 1) / wpb;
 	const int64_t cap = (int64_t)ctx->num_sms * 16;
 	if (blocks > cap) blocks = cap;
 	if (blocks < 1) blocks = 1;
-	if (tbytes == 1) {
-		if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kmer_count_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kmer_count_kernel<1><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_flags);
-	} else {
-		if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kmer_count_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kmer_count_kernel<2><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, k, (uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_flags);
-	}
+	if (smem > 48 * 1024) MC_CUDA(cudaFuncSetAttribute(kmer_count_kernel<TB, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	kmer_count_kernel<TB, K><<<(int)blocks, threads, smem, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, ctx->d_segs, ctx->d_seg_off, ctx->n, (uint8_t *)ctx->d_hist, ctx->d_aux, ctx->d_flags);
 	ctx->launches++;
 	MC_CUDA(cudaGetLastError());
 	return MC_OK;
+}
+
+int mc_launch_kmer_hist(mc_ctx *ctx, int k, int tbytes) {
+	MC_REQUIRE(k >= 1 && k <= 7 && (tbytes == 1 || tbytes == 2), MC_ERR_UNSUPPORTED, "k=%d with %d-byte bins is not supported (k 1..7, 1 or 2 bytes)", k, tbytes);
+#define K1_CASE(KK) case KK: return tbytes == 1 ? k1_launch<1, KK>(ctx) : k1_launch<2, KK>(ctx);
+	switch (k) {
+		K1_CASE(1) K1_CASE(2) K1_CASE(3) K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7)
+	default: break;
+	}
+#undef K1_CASE
+	return MC_ERR_UNSUPPORTED;
 }

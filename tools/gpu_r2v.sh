@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "hist or kmer or encode or segment or golden" 2>&1 | tail -4
+MC_DEBUG_TIMING=1 python tools/prof_k1.py c2 2>&1 | tail -4
+MC_DEBUG_TIMING=1 python tools/prof_k1.py c4 2>&1 | tail -3
+for cfg in c2 c4 c5; do python tools/gen_config.py $cfg /tmp/$cfg.fa > /dev/null; done
+timeout 600 bin/meshclust /tmp/c2.fa --id 0.97 --kmer 4 --output /tmp/c2.clstr > gpurun_out/r2v_c2.log 2>&1; echo "c2 rc=$? $(md5sum < /tmp/c2.clstr) want 83cffd7e"
+timeout 600 bin/meshclust /tmp/c4.fa --id 0.90 --kmer 5 --output /tmp/c4.clstr > gpurun_out/r2v_c4.log 2>&1; echo "c4 rc=$? $(md5sum < /tmp/c4.clstr) want f0917a7a"
+timeout 600 bin/meshclust /tmp/c5.fa --kmer 6 --output /tmp/c5.clstr > gpurun_out/r2v_c5.log 2>&1; echo "c5 rc=$? $(md5sum < /tmp/c5.clstr) want 36aebc3b"
