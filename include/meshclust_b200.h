@@ -63,6 +63,24 @@ int mc_host_segments(const uint8_t *letters, int64_t len, int32_t *segs, int max
  * Replaces ChromosomeOneDigit::encodeNucleotides for every record of ChromListMaker's list. */
 int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int64_t *offsets, int64_t n,
                       const int32_t *segs, const int64_t *seg_offsets);
+/* FASTA ingest on the device.  Replaces, for files with LF line ends, the copy of every sequence
+ * line into the record's string (ChromListMaker.cpp:92-120, Chromosome::appendToSequence, Chromosome.cpp:73-82)
+ * and the scan for N of Chromosome::removeN (Chromosome.cpp:162-184).
+ * raw[raw_bytes]: the files' bytes as read (host).  Record i (in the caller's ROW order) owns the bytes
+ * [span_begin[i], span_end[i]) of raw -- its sequence lines, header line excluded -- which hold
+ * offsets[i+1] - offsets[i] letters and otherwise only '\n'.  The letters land at offsets[i] of the device letter
+ * buffer, exactly what mc_load_sequences would have uploaded.  rec_flags_out[i]: bit 0 = the record holds an N / n
+ * (derive its segments with mc_host_segments), bit 1 = it holds a letter other than A C G T N in either case
+ * (validate).  Must be followed by mc_load_segments.  MC_ERR_INPUT when spans and letter counts disagree. */
+int mc_ingest_fasta(mc_ctx *ctx, const uint8_t *raw, int64_t raw_bytes, const int64_t *span_begin, const int64_t *span_end,
+                    const int64_t *offsets, int64_t n, uint8_t *rec_flags_out);
+/* The segment lists of the records ingested by mc_ingest_fasta (same layout as in mc_load_sequences).  validate != 0
+ * checks every letter against the reference's code table (ChromosomeOneDigit.cpp:59-85; MC_ERR_INPUT = the
+ * reference's InvalidInputException); callers pass 0 when no record has flag bit 1. */
+int mc_load_segments(mc_ctx *ctx, const int32_t *segs, const int64_t *seg_offsets, int validate);
+/* D2H copy of the letters as they stand on the device (before any alignment: the letters; afterwards the digit
+ * strings) -- tests */
+int mc_copy_letters(mc_ctx *ctx, uint8_t *out);
 /* D2H copy of the encoded digit strings (same layout as the letters) -- tests / debugging */
 int mc_copy_digits(mc_ctx *ctx, uint8_t *out);
 

@@ -28,7 +28,7 @@ MC_ERR_CUDA, MC_ERR_ARG, MC_ERR_STATE, MC_ERR_INPUT, MC_ERR_UNSUPPORTED = -1, -2
 # every symbol include/meshclust_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "mc_version", "mc_last_error", "mc_device_count", "mc_ctx_create", "mc_ctx_destroy", "mc_stream",
-    "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_copy_digits",
+    "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_ingest_fasta", "mc_load_segments", "mc_copy_letters", "mc_copy_digits",
     "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
     "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
     "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_accumulate_run", "mc_near_threshold_count", "mc_permute_rows", "mc_reserve_permute", "mc_comm_init", "mc_comm_connect", "mc_comm_connect_local",
@@ -162,6 +162,29 @@ class Context:
         self.n = offsets.size - 1
         self.total_bases = int(offsets[-1])
         _check(_lib.mc_load_sequences(self._h, _p(letters), _p(offsets), C.c_int64(self.n), _p(segs), _p(seg_offsets)))
+
+    def ingest_fasta(self, raw: np.ndarray, span_begin: np.ndarray, span_end: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        """mc_ingest_fasta: raw file bytes + the byte span of every record's sequence lines -> letters on the device;
+        returns the per-record flags (bit 0: has N, bit 1: has a letter other than ACGTN)."""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        span_begin = np.ascontiguousarray(span_begin, np.int64)
+        span_end = np.ascontiguousarray(span_end, np.int64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        self.n = offsets.size - 1
+        self.total_bases = int(offsets[-1])
+        flags = np.zeros(self.n, np.uint8)
+        _check(_lib.mc_ingest_fasta(self._h, _p(raw), C.c_int64(raw.size), _p(span_begin), _p(span_end), _p(offsets), C.c_int64(self.n), _p(flags)))
+        return flags
+
+    def load_segments(self, segs: np.ndarray, seg_offsets: np.ndarray, validate: bool = True):
+        segs = np.ascontiguousarray(segs, np.int32)
+        seg_offsets = np.ascontiguousarray(seg_offsets, np.int64)
+        _check(_lib.mc_load_segments(self._h, _p(segs), _p(seg_offsets), C.c_int(1 if validate else 0)))
+
+    def copy_letters(self) -> np.ndarray:
+        out = np.zeros(self.total_bases, np.uint8)
+        _check(_lib.mc_copy_letters(self._h, _p(out)))
+        return out
 
     def copy_digits(self) -> np.ndarray:
         out = np.zeros(self.total_bases, np.uint8)

@@ -23,7 +23,7 @@ LIB = os.path.join(PKG, f"libmeshclust_b200{'_' + _VARIANT if _VARIANT else ''}.
 BIN = os.path.join(ROOT, "bin", "meshclust")
 OBJ = os.path.join(PKG, "_build" + ("_" + _VARIANT if _VARIANT else ""))
 
-CU_SOURCES = ["capi.cu", "kmer_hist.cu", "pair_kernels.cu", "scan_tma.cu", "center_mean.cu", "phase_a.cu", "nw_identity.cu", "peer_exchange.cu"]
+CU_SOURCES = ["capi.cu", "fasta_ingest.cu", "kmer_hist.cu", "pair_kernels.cu", "scan_tma.cu", "center_mean.cu", "phase_a.cu", "nw_identity.cu", "peer_exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -279,6 +279,83 @@ extern "C" int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int6
 	return MC_OK;
 }
 
+// FASTA ingest on the device: raw file bytes + per-record spans -> letters in row order + per-record flags
+int mc_launch_ingest(mc_ctx *ctx, const uint8_t *raw_dev, const int64_t *span_begin_dev, const int64_t *span_end_dev, uint8_t *rec_flags_dev,
+                     unsigned int *err_dev);
+
+extern "C" int mc_ingest_fasta(mc_ctx *ctx, const uint8_t *raw, int64_t raw_bytes, const int64_t *span_begin, const int64_t *span_end,
+                               const int64_t *offsets, int64_t n, uint8_t *rec_flags_out) {
+	MC_REQUIRE(ctx && raw && span_begin && span_end && offsets && rec_flags_out && n > 0 && raw_bytes >= 0, MC_ERR_ARG, "mc_ingest_fasta: bad arguments");
+	MC_REQUIRE(n < (1LL << 31), MC_ERR_UNSUPPORTED, "more than 2^31 sequences");
+	for (int64_t i = 0; i < n; i++)
+		MC_REQUIRE(span_begin[i] >= 0 && span_begin[i] <= span_end[i] && span_end[i] <= raw_bytes && offsets[i + 1] >= offsets[i] &&
+		           offsets[i + 1] - offsets[i] <= span_end[i] - span_begin[i], MC_ERR_ARG, "mc_ingest_fasta: span / offsets of record %lld", (long long)i);
+	MC_CUDA(cudaSetDevice(ctx->device));
+	free_seq(ctx);
+	const int64_t total = offsets[n];
+	MC_REQUIRE(offsets[0] == 0 && total >= 0, MC_ERR_ARG, "mc_ingest_fasta: bad offsets");
+	ctx->n = n; ctx->total_bases = total; ctx->nseg = 0;
+	MC_CUDA(cudaMalloc(&ctx->d_seq, (size_t)total + 64));
+	MC_CUDA(cudaMalloc(&ctx->d_seq_off, (size_t)(n + 1) * sizeof(int64_t)));
+	MC_CUDA(cudaMemsetAsync(ctx->d_seq + total, 0, 64, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(ctx->d_seq_off, offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+	// the raw bytes, the spans and the flags live in the scratch buffer for the length of this call
+	int rc = mc_ensure_scratch(ctx, Carve::need({(size_t)raw_bytes + 64, (size_t)n * 8, (size_t)n * 8, (size_t)n, 64}));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	uint8_t *d_raw = cv.take<uint8_t>((size_t)raw_bytes + 64);
+	int64_t *d_sb = cv.take<int64_t>((size_t)n), *d_se = cv.take<int64_t>((size_t)n);
+	uint8_t *d_fl = cv.take<uint8_t>((size_t)n);
+	unsigned int *d_err = cv.take<unsigned int>(16);
+	MC_CUDA(cudaMemcpyAsync(d_raw, raw, (size_t)raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_raw + raw_bytes, '\n', 64, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(d_sb, span_begin, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(d_se, span_end, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_err, 0, 64, ctx->stream));
+	rc = mc_launch_ingest(ctx, d_raw, d_sb, d_se, d_fl, d_err);
+	if (rc) return rc;
+	unsigned int h_err = 0;
+	MC_CUDA(cudaMemcpyAsync(rec_flags_out, d_fl, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->digits_ready = false;
+	ctx->h_seq_off.assign(offsets, offsets + n + 1);
+	MC_REQUIRE(h_err == 0, MC_ERR_INPUT, "mc_ingest_fasta: a record's span does not hold the number of letters its offsets announce");
+	return MC_OK;
+}
+
+extern "C" int mc_load_segments(mc_ctx *ctx, const int32_t *segs, const int64_t *seg_offsets, int validate) {
+	MC_REQUIRE(ctx && seg_offsets, MC_ERR_ARG, "mc_load_segments: bad arguments");
+	MC_REQUIRE(ctx->d_seq && ctx->d_seq_off && !ctx->have_seq, MC_ERR_STATE, "mc_load_segments: call mc_ingest_fasta first");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	const int64_t n = ctx->n, nseg = seg_offsets[n];
+	MC_REQUIRE(nseg >= 0 && (nseg == 0 || segs), MC_ERR_ARG, "mc_load_segments: bad offsets");
+	ctx->nseg = nseg;
+	MC_CUDA(cudaMalloc(&ctx->d_seg_off, (size_t)(n + 1) * sizeof(int64_t)));
+	MC_CUDA(cudaMalloc(&ctx->d_segs, (size_t)std::max<int64_t>(nseg, 1) * 2 * sizeof(int32_t)));
+	MC_CUDA(cudaMemcpyAsync(ctx->d_seg_off, seg_offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+	if (nseg) MC_CUDA(cudaMemcpyAsync(ctx->d_segs, segs, (size_t)nseg * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+	unsigned int flags[4] = {0, 0, 0, 0};
+	MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(unsigned int), ctx->stream));
+	if (validate) {
+		const int rc = mc_launch_validate(ctx);
+		if (rc) return rc;
+		MC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->have_seq = true;
+	MC_REQUIRE(flags[0] == 0, MC_ERR_INPUT, "Invalid nucleotide in input (the reference throws InvalidInputException)");
+	return MC_OK;
+}
+
+extern "C" int mc_copy_letters(mc_ctx *ctx, uint8_t *out) {
+	MC_REQUIRE(ctx && out && ctx->d_seq, MC_ERR_ARG, "mc_copy_letters: bad arguments");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	MC_CUDA(cudaMemcpyAsync(out, ctx->d_seq, (size_t)ctx->total_bases, cudaMemcpyDeviceToHost, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MC_OK;
+}
+
 // ChromosomeOneDigit::encodeNucleotides (ChromosomeOneDigit.cpp:95-144) over the whole buffer, in place, once
 static int ensure_digits(mc_ctx *ctx) {
 	if (ctx->digits_ready) return MC_OK;

@@ -8,6 +8,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,7 @@ public:
 	uint8_t *data() { return p_; }
 	const uint8_t *data() const { return p_; }
 	size_t size() const { return n_; }
+	void release() { free(p_); p_ = nullptr; n_ = cap_ = 0; }
 	void resize(size_t n) {
 		if (n > cap_) {
 			void *q = realloc(p_, n);
@@ -209,6 +211,148 @@ inline bool read_fasta(const std::string &path, FastaBatch &out, std::string &ms
 	out.letters.resize(w);
 	if (!open) { msg = "no FASTA record in " + path; return false; }
 	return close_record();
+}
+
+// ---- index only: what the device-side ingest (mc_ingest_fasta) needs --------------------------------------------
+// The files' bytes stay as they are (one buffer, file after file); per record the header, the byte span of its
+// sequence lines and the number of letters in it.  One parallel pass over the bytes, no copy of the letters.
+struct FastaIndex {
+	RawBytes raw;                        // all files, concatenated
+	std::vector<std::string> headers;
+	std::vector<int64_t> span_begin, span_end;   // sequence lines of record i: raw[span_begin[i], span_end[i])
+	std::vector<int64_t> letters;        // letters in that span (bytes that are not '\n')
+	std::vector<size_t> file_first;      // first record of every file, then the record count
+	size_t size() const { return headers.size(); }
+	void clear() {
+		raw.release();
+		std::vector<std::string>().swap(headers);
+		std::vector<int64_t>().swap(span_begin);
+		std::vector<int64_t>().swap(span_end);
+		std::vector<int64_t>().swap(letters);
+		file_first.clear();
+	}
+};
+
+// One file that already sits at raw[base, base + n).  Same eligibility as parse_fasta_parallel: LF line ends, the
+// file starts with a header, every header is followed by a line that is not a header; false = use read_fasta.
+inline bool index_fasta_region(const char *all, size_t base, size_t n, FastaIndex &out, int pieces) {
+	const char *bd = all + base;
+	if (n == 0 || bd[0] != '>') return false;
+	if (pieces < 1) pieces = 1;
+	if ((size_t)pieces > n / 4096 + 1) pieces = (int)(n / 4096 + 1);
+	struct Piece {
+		std::vector<size_t> hpos, hend, letters;   // per header that starts in the piece: '>' position, end of its line, letters after it (inside the piece)
+		size_t lead = 0;                           // letters before the piece's first header: they belong to the record before
+		bool bad = false, cr = false;
+	};
+	std::vector<Piece> pc((size_t)pieces);
+#pragma omp parallel for schedule(static)
+	for (int t = 0; t < pieces; t++) {
+		size_t a = n * (size_t)t / (size_t)pieces, b = n * (size_t)(t + 1) / (size_t)pieces;
+		Piece &p = pc[(size_t)t];
+		if (b > a && memchr(bd + a, '\r', b - a)) p.cr = true;
+		// a line belongs to the piece that holds its first byte
+		if (t > 0) {
+			const char *nl = (const char *)memchr(bd + a - 1, '\n', n - (a - 1));
+			a = nl ? (size_t)(nl - bd) + 1 : n;
+		}
+		if (t + 1 < pieces) {
+			const char *nl = b > 0 ? (const char *)memchr(bd + b - 1, '\n', n - (b - 1)) : nullptr;
+			b = nl ? (size_t)(nl - bd) + 1 : n;
+		}
+		for (size_t i = a; i < b;) {
+			const char *nl = (const char *)memchr(bd + i, '\n', n - i);
+			const size_t j = nl ? (size_t)(nl - bd) : n;
+			if (bd[i] == '>') {
+				p.hpos.push_back(i);
+				p.hend.push_back(j);
+				p.letters.push_back(0);
+				// a header needs a following line that is not a header (an empty one counts: safe_getline)
+				if (j >= n || (j + 1 < n && bd[j + 1] == '>')) p.bad = true;
+			} else if (p.letters.empty()) p.lead += j - i;
+			else p.letters.back() += j - i;
+			i = j + 1;
+		}
+	}
+	size_t nh = 0;
+	for (const Piece &p : pc) {
+		if (p.bad || p.cr) return false;
+		nh += p.hpos.size();
+	}
+	const size_t rec0 = out.headers.size();
+	out.headers.resize(rec0 + nh);
+	out.span_begin.resize(rec0 + nh);
+	out.span_end.resize(rec0 + nh);
+	out.letters.resize(rec0 + nh);
+	std::vector<size_t> first((size_t)pieces + 1, 0);
+	for (int t = 0; t < pieces; t++) first[(size_t)t + 1] = first[(size_t)t] + pc[(size_t)t].hpos.size();
+#pragma omp parallel for schedule(static)
+	for (int t = 0; t < pieces; t++) {
+		const Piece &p = pc[(size_t)t];
+		for (size_t h = 0; h < p.hpos.size(); h++) {
+			const size_t rec = rec0 + first[(size_t)t] + h;
+			out.headers[rec].assign(bd + p.hpos[h], p.hend[h] - p.hpos[h]);
+			out.span_begin[rec] = (int64_t)(base + std::min(p.hend[h] + 1, n));
+			out.letters[rec] = (int64_t)p.letters[h];
+			if (rec > rec0) out.span_end[rec - 1] = (int64_t)(base + p.hpos[h]);
+		}
+	}
+	out.span_end[rec0 + nh - 1] = (int64_t)(base + n);
+	// letters in front of a piece's first header belong to the last record opened before the piece
+	size_t last_rec = rec0;
+	for (int t = 0; t < pieces; t++) {
+		const Piece &p = pc[(size_t)t];
+		if (t > 0) out.letters[last_rec] += (int64_t)p.lead;   // (piece 0 starts with a header: lead = 0)
+		if (!p.hpos.empty()) last_rec = rec0 + first[(size_t)t + 1] - 1;
+	}
+	return true;
+}
+
+// all files into one buffer + their index; false (nothing usable in `out`) when a file needs the serial parser
+inline bool index_fasta_files(const std::vector<std::string> &files, FastaIndex &out) {
+	std::vector<size_t> sizes;
+	size_t total = 0;
+	for (const std::string &path : files) {
+		FILE *f = fopen(path.c_str(), "rb");
+		if (!f) return false;
+		fseek(f, 0, SEEK_END);
+		const long sz = ftell(f);
+		fclose(f);
+		if (sz <= 0) return false;
+		sizes.push_back((size_t)sz);
+		total += (size_t)sz;
+	}
+	out.raw.resize(total);
+	int threads = 1;
+#ifdef _OPENMP
+	threads = omp_get_max_threads();
+#endif
+	size_t base = 0;
+	for (size_t fi = 0; fi < files.size(); fi++) {
+		FILE *f = fopen(files[fi].c_str(), "rb");
+		if (!f) return false;
+		const int fd = fileno(f);
+		const size_t sz = sizes[fi];
+		bool short_read = false;
+		const int parts = sz >= ((size_t)8 << 20) ? 16 : 1;   // page-cache copies are memcpy-bound: the host threads share them
+#pragma omp parallel for schedule(dynamic) reduction(|| : short_read)
+		for (int t = 0; t < parts; t++) {
+			size_t a = sz * (size_t)t / (size_t)parts;
+			const size_t b = sz * (size_t)(t + 1) / (size_t)parts;
+			while (a < b) {
+				const ssize_t got = pread(fd, out.raw.data() + base + a, b - a, (off_t)a);
+				if (got <= 0) { short_read = true; break; }
+				a += (size_t)got;
+			}
+		}
+		fclose(f);
+		if (short_read) return false;
+		out.file_first.push_back(out.size());
+		if (!index_fasta_region((const char *)out.raw.data(), base, sz, out, threads)) return false;
+		base += sz;
+	}
+	out.file_first.push_back(out.size());
+	return true;
 }
 
 }  // namespace mch

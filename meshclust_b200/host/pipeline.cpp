@@ -969,15 +969,31 @@ int run_pipeline(Options opt) {
 			ctx_thread.join();
 			exit(1);
 		}
-		std::string msg;
-		file_first.push_back(c.ds.fa.size());
-		if (!read_fasta(f, c.ds.fa, msg)) {
-			fprintf(stderr, "meshclust: %s\n", msg.c_str());
-			ctx_thread.join();
-			abort();   // the reference dies with an uncaught exception on malformed input
-		}
 	}
-	file_first.push_back(c.ds.fa.size());
+	// Well-formed files with LF line ends are only INDEXED here (headers, where every record's sequence lines are,
+	// how many letters they hold): the bytes go to the GPU as they are and mc_ingest_fasta squeezes the line feeds
+	// out there.  Anything else (CR line ends, malformed records) takes the host parser, which owns the error
+	// semantics.  MC_HOST_PARSE=1 forces the host parser.
+	FastaIndex fidx;
+	const bool indexed = !getenv("MC_HOST_PARSE") && index_fasta_files(opt.files, fidx);
+	if (indexed) {
+		file_first = fidx.file_first;
+		c.ds.fa.headers.swap(fidx.headers);
+		c.ds.fa.offsets.assign(fidx.letters.size() + 1, 0);
+		for (size_t i = 0; i < fidx.letters.size(); i++) c.ds.fa.offsets[i + 1] = c.ds.fa.offsets[i] + fidx.letters[i];
+	} else {
+		fidx.clear();
+		for (const std::string &f : opt.files) {
+			std::string msg;
+			file_first.push_back(c.ds.fa.size());
+			if (!read_fasta(f, c.ds.fa, msg)) {
+				fprintf(stderr, "meshclust: %s\n", msg.c_str());
+				ctx_thread.join();
+				abort();   // the reference dies with an uncaught exception on malformed input
+			}
+		}
+		file_first.push_back(c.ds.fa.size());
+	}
 	Dataset &ds = c.ds;
 	ds.n = (int64_t)ds.fa.size();
 	ds.len.resize((size_t)ds.n);
@@ -1020,12 +1036,80 @@ int run_pipeline(Options opt) {
 
 	// ---- upload in row order, encode, histograms (K1) -------------------------------------------
 	{
+		std::vector<int64_t> offs((size_t)ds.n + 1, 0), seg_off((size_t)ds.n + 1, 0);
+		for (int64_t r = 0; r < ds.n; r++) offs[r + 1] = offs[r] + (int64_t)ds.len[ds.id_of_row[r]];
+		auto join_ctx = [&]() {
+			ctx_thread.join();
+			if (ctx_rc != MC_OK) {
+				fprintf(stderr, "meshclust: mc_ctx_create failed: %s\n", ctx_err.c_str());
+				exit(2);
+			}
+			printf("  [gpu context %.2fs on a helper thread, waited %.2fs]\n", ctx_s, tm.lap());
+		};
+		auto no_sequence = [&](int64_t bad_row) {
+			fprintf(stderr, "meshclust: record \"%s\" has no usable sequence (the reference throws std::out_of_range)\n", ds.fa.headers[ds.id_of_row[bad_row]].c_str());
+			if (ctx_thread.joinable()) ctx_thread.join();
+			abort();
+		};
+		if (indexed) {
+			// ---- device-side ingest: spans in row order, letters squeezed and permuted on the GPU
+			std::vector<int64_t> sb((size_t)ds.n), se((size_t)ds.n);
+			for (int64_t r = 0; r < ds.n; r++) { sb[r] = fidx.span_begin[ds.id_of_row[r]]; se[r] = fidx.span_end[ds.id_of_row[r]]; }
+			printf("  [row order %.2fs]\n", tm.lap());
+			join_ctx();
+			std::vector<uint8_t> rflags((size_t)ds.n);
+			if (mc_ingest_fasta(c.gpu, fidx.raw.data(), (int64_t)fidx.raw.size(), sb.data(), se.data(), offs.data(), ds.n, rflags.data()) != MC_OK) die_gpu("mc_ingest_fasta");
+			// segments (Chromosome.cpp:162-258): a record without N is one run -- kept from 20 letters on, cut at 1 Mbp --
+			// and needs no look at its letters; the others are rebuilt from their lines and go through mc_host_segments
+			std::vector<int32_t> segs;
+			bool validate = false;
+			std::vector<uint8_t> tmp;
+			std::vector<int32_t> sbuf;
+			for (int64_t r = 0; r < ds.n; r++) {
+				const int64_t len = offs[r + 1] - offs[r];
+				if (rflags[r] & 2) validate = true;
+				int ns;
+				if (!(rflags[r] & 1)) {
+					if (len <= 1) no_sequence(r);   // (mc_host_segments: an empty or one-letter record never closes a run)
+					ns = 0;
+					if (len >= 20) {
+						if (len > 1000000) {
+							const int64_t frag = len / 1000000;
+							for (int64_t h = 0; h < frag; h++) {
+								const int64_t fs = h * 1000000, fe = (h == frag - 1) ? len - 1 : fs + 1000000 - 1;
+								segs.push_back((int32_t)fs); segs.push_back((int32_t)fe);
+								ns++;
+							}
+						} else {
+							segs.push_back(0); segs.push_back((int32_t)(len - 1));
+							ns = 1;
+						}
+					}
+				} else {
+					tmp.resize((size_t)len);
+					size_t w = 0;
+					for (int64_t p = sb[r]; p < se[r]; p++) {
+						const uint8_t ch = fidx.raw.data()[p];
+						if (ch != '\n') tmp[w++] = ch;
+					}
+					ns = mc_host_segments(tmp.data(), len, nullptr, 0);
+					if (ns < 0) no_sequence(r);
+					sbuf.resize((size_t)ns * 2);
+					mc_host_segments(tmp.data(), len, sbuf.data(), ns);
+					segs.insert(segs.end(), sbuf.begin(), sbuf.end());
+				}
+				seg_off[r + 1] = seg_off[r] + ns;
+			}
+			if (mc_load_segments(c.gpu, segs.data(), seg_off.data(), validate ? 1 : 0) != MC_OK) {
+				fprintf(stderr, "meshclust: %s\n", mc_last_error());
+				abort();   // InvalidInputException in the reference
+			}
+			fidx.clear();
+		} else {
 		// letters in row order + the non-N segment list of every row; rows are independent, so the
 		// host threads share them (segments: first pass counts, second pass fills)
 		RawBytes letters;
 		letters.resize(ds.fa.letters.size());
-		std::vector<int64_t> offs((size_t)ds.n + 1, 0), seg_off((size_t)ds.n + 1, 0);
-		for (int64_t r = 0; r < ds.n; r++) offs[r + 1] = offs[r] + (int64_t)ds.len[ds.id_of_row[r]];
 		constexpr int INLINE_SEGS = 4;
 		std::vector<int32_t> seg_inline((size_t)ds.n * 2 * INLINE_SEGS);
 		std::vector<int32_t> nseg((size_t)ds.n);
@@ -1042,11 +1126,7 @@ int run_pipeline(Options opt) {
 				if (bad_row < 0 || r < bad_row) bad_row = r;
 			}
 		}
-		if (bad_row >= 0) {
-			fprintf(stderr, "meshclust: record \"%s\" has no usable sequence (the reference throws std::out_of_range)\n", ds.fa.headers[ds.id_of_row[bad_row]].c_str());
-			ctx_thread.join();
-			abort();
-		}
+		if (bad_row >= 0) no_sequence(bad_row);
 		sub("letters to row order + segments");
 		for (int64_t r = 0; r < ds.n; r++) seg_off[r + 1] = seg_off[r] + nseg[r];
 		std::vector<int32_t> segs((size_t)seg_off[ds.n] * 2);
@@ -1060,15 +1140,11 @@ int run_pipeline(Options opt) {
 			}
 		}
 		printf("  [row order + segments %.2fs]\n", tm.lap());
-		ctx_thread.join();
-		if (ctx_rc != MC_OK) {
-			fprintf(stderr, "meshclust: mc_ctx_create failed: %s\n", ctx_err.c_str());
-			exit(2);
-		}
-		printf("  [gpu context %.2fs on a helper thread, waited %.2fs]\n", ctx_s, tm.lap());
+		join_ctx();
 		if (mc_load_sequences(c.gpu, letters.data(), offs.data(), ds.n, segs.data(), seg_off.data()) != MC_OK) {
 			fprintf(stderr, "meshclust: %s\n", mc_last_error());
 			abort();   // InvalidInputException in the reference
+		}
 		}
 	}
 	printf("  [upload + encode %.2fs]\n", tm.lap());

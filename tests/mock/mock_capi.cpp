@@ -17,6 +17,7 @@
 struct mc_ctx {
 	int64_t n = 0;
 	std::vector<uint8_t> digits;
+	std::vector<uint8_t> letters;   // mc_ingest_fasta -> mc_load_segments
 	std::vector<int64_t> offs, seg_off;
 	std::vector<int32_t> segs;
 	int k = 0, nbins = 0, tbytes = 1;
@@ -74,6 +75,37 @@ int mc_load_sequences(mc_ctx *c, const uint8_t *letters, const int64_t *offsets,
 	}
 	return MC_OK;
 }
+int mc_ingest_fasta(mc_ctx *c, const uint8_t *raw, int64_t raw_bytes, const int64_t *span_begin, const int64_t *span_end, const int64_t *offsets,
+                    int64_t n, uint8_t *rec_flags_out) {
+	(void)raw_bytes;
+	c->n = n;
+	c->offs.assign(offsets, offsets + n + 1);
+	c->letters.assign((size_t)offsets[n], 0);
+	for (int64_t i = 0; i < n; i++) {
+		int64_t w = offsets[i];
+		uint8_t fl = 0;
+		for (int64_t p = span_begin[i]; p < span_end[i]; p++) {
+			const uint8_t ch = raw[p];
+			if (ch == '\n') continue;
+			if (w >= offsets[i + 1]) return fail(MC_ERR_INPUT, "mc_ingest_fasta: a record's span does not hold the number of letters its offsets announce");
+			c->letters[(size_t)w++] = ch;
+			const uint8_t u = ch & 0xdf;
+			if (u == 'N') fl |= 1;
+			else if (u != 'A' && u != 'C' && u != 'G' && u != 'T') fl |= 2;
+		}
+		if (w != offsets[i + 1]) return fail(MC_ERR_INPUT, "mc_ingest_fasta: a record's span does not hold the number of letters its offsets announce");
+		rec_flags_out[i] = fl;
+	}
+	return MC_OK;
+}
+int mc_load_segments(mc_ctx *c, const int32_t *segs, const int64_t *seg_offsets, int validate) {
+	(void)validate;   // the CPU encode below always validates: a stricter check than asked for can only fail where the real one would be asked
+	std::vector<uint8_t> letters;
+	letters.swap(c->letters);
+	const std::vector<int64_t> offs = c->offs;
+	return mc_load_sequences(c, letters.data(), offs.data(), c->n, segs, seg_offsets);
+}
+int mc_copy_letters(mc_ctx *c, uint8_t *out) { memcpy(out, c->letters.data(), c->letters.size()); return MC_OK; }
 int mc_copy_digits(mc_ctx *c, uint8_t *out) { memcpy(out, c->digits.data(), c->digits.size()); return MC_OK; }
 
 int mc_build_histograms(mc_ctx *c, int k, int tbytes, int *tbytes_out, uint64_t *max_count_out) {

@@ -51,6 +51,91 @@ def test_encode_and_hist_golden(ctx, golden):
         assert np.array_equal(ctx.copy_histograms(), want)
 
 
+def _fasta_text(rng, n, golden_like=True):
+    """A FASTA file as bytes + what a parser makes of it: letters per record; ragged line widths, empty lines,
+    N runs, IUPAC codes, lower case, records shorter than 20 letters, no newline at the very end."""
+    recs, out = [], bytearray()
+    spans = []
+    for i in range(n):
+        out += f">rec{i} some description {i * 7}\n".encode()
+        kind = rng.integers(0, 6)
+        L = int(rng.integers(2, 30)) if kind == 5 else int(rng.integers(20, 900))
+        seq = rng.choice(np.frombuffer(b"ACGT", np.uint8), L)
+        if kind == 1:
+            seq = seq | 0x20                                  # lower case
+        if kind == 2 and L > 60:                               # N runs, short and long, also at the ends
+            for _ in range(int(rng.integers(1, 4))):
+                a = int(rng.integers(0, L - 1))
+                seq[a:a + int(rng.integers(1, 40))] = ord("N") if rng.random() < 0.7 else ord("n")
+        if kind == 3:                                          # IUPAC codes
+            pos = rng.integers(0, L, 5)
+            seq[pos] = rng.choice(np.frombuffer(b"RYMKSWHBVDX", np.uint8), 5)
+        begin = len(out)
+        width = int(rng.integers(1, 100))
+        for a in range(0, L, width):
+            out += seq[a:a + width].tobytes() + b"\n"
+            if rng.random() < 0.05:
+                out += b"\n"                                   # an empty line inside the record
+        spans.append((begin, len(out)))
+        recs.append(seq.copy())
+    while out and out[-1:] == b"\n":
+        out = out[:-1]
+    spans[-1] = (spans[-1][0], len(out))
+    return np.frombuffer(bytes(out), np.uint8), spans, recs
+
+
+@pytest.mark.parametrize("n,k", [(700, 3), (64, 4), (1, 2)])
+def test_ingest_fasta_vs_host_parser(ctx, oracle, n, k):
+    """mc_ingest_fasta (raw file bytes + per-record spans -> letters, in a permuted row order, + N / non-ACGT flags
+    on the device; SURVEY 8(f1), ChromListMaker.cpp:92-120, Chromosome.cpp:162-184) against the letters a parser
+    extracts on the host, and the histograms built from them against the host-letter path and the oracle."""
+    from meshclust_b200.api import McError, segments_for_batch
+    rng = np.random.default_rng(4100 + n)
+    raw, spans, recs = _fasta_text(rng, n)
+    order = rng.permutation(n)                                 # row r holds record order[r]
+    lens = np.array([recs[i].size for i in order], np.int64)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    sb = np.array([spans[i][0] for i in order], np.int64)
+    se = np.array([spans[i][1] for i in order], np.int64)
+    letters = np.concatenate([recs[i] for i in order]).astype(np.uint8)
+    flags = ctx.ingest_fasta(raw, sb, se, offs)
+    assert np.array_equal(ctx.copy_letters(), letters)
+    up = letters & 0xDF
+    has_n = np.add.reduceat((up == ord("N")).astype(np.int64), offs[:-1]) > 0
+    other = np.add.reduceat((~np.isin(up, np.frombuffer(b"ACGTN", np.uint8))).astype(np.int64), offs[:-1]) > 0
+    assert np.array_equal((flags & 1) != 0, has_n) and np.array_equal((flags & 2) != 0, other)
+    segs, seg_off = segments_for_batch(letters, offs)
+    ctx.load_segments(segs, seg_off, validate=bool(other.any()))
+    used, mx = ctx.build_histograms(k, 0)
+    got = ctx.copy_histograms()
+    rc, want, wmx = oracle.hist_batch(letters, offs, k, used)
+    assert rc == 0 and mx == wmx and np.array_equal(got, want)
+    ln = ctx.copy_point_stats()[0]
+    assert np.array_equal(ln, lens.astype(np.uint64))
+    # the digit strings the aligner reads come out of the same buffer
+    ctx2_digits = ctx.copy_digits()
+    ctx.load_sequences(letters, offs, segs, seg_off)
+    assert np.array_equal(ctx.copy_digits(), ctx2_digits)
+    # spans and letter counts that disagree are an input error, not a silent truncation
+    long_rows = np.nonzero(lens >= 20)[0]
+    if long_rows.size:
+        r0 = int(long_rows[0])
+        lens2 = lens.copy()
+        lens2[r0] -= 1
+        with pytest.raises(McError):
+            ctx.ingest_fasta(raw, sb, se, np.concatenate([[0], np.cumsum(lens2)]).astype(np.int64))
+        # an invalid letter is reported by mc_load_segments when validation is asked for (records with a segment only)
+        raw2 = raw.copy()
+        p0 = int(sb[r0])
+        while raw2[p0] == 10:
+            p0 += 1
+        raw2[p0] = ord("!")
+        fl2 = ctx.ingest_fasta(raw2, sb, se, offs)
+        assert fl2[r0] & 2
+        with pytest.raises(McError):
+            ctx.load_segments(segs, seg_off, validate=True)
+
+
 @pytest.mark.parametrize("cfg,n,k", [("c1", 3000, 3), ("c2", 2000, 4), ("c4", 2000, 5), ("c5", 300, 6), ("c3", 1500, 4)])
 def test_hist_vs_oracle_configs(ctx, oracle, cfg, n, k):
     letters, offs, _ = synth.generate_config(cfg, n)

@@ -1,5 +1,7 @@
 // Self-check of host/fasta.hpp: the parallel parser must produce exactly what the serial parser
-// does on well-formed files, and must hand every irregular file back to the serial parser.
+// does on well-formed files, and must hand every irregular file back to the serial parser.  The indexer
+// (what the device-side ingest is fed with) must describe the same records: squeezing the line feeds out
+// of every span gives the serial parser's letters, and the announced letter counts are exact.
 #include <cstdio>
 #include <random>
 #include <string>
@@ -48,6 +50,56 @@ int main(int argc, char **argv) {
 			if (!oa2 || !ob2 || !same(a, b)) { printf("append mismatch in round %d\n", round); return 1; }
 		}
 	}
+	// the indexer: two files per round (the second one a copy with other record names), against the serial parser
+	int indexed = 0;
+	for (int round = 0; round < 60; round++) {
+		std::string txt[2];
+		const int kind = round % 6;
+		for (int fi = 0; fi < 2; fi++) {
+			const int nrec = 1 + rng() % (round < 6 ? 3 : 300);
+			for (int r = 0; r < nrec; r++) {
+				txt[fi] += ">f" + std::to_string(fi) + "r" + std::to_string(r) + (kind == 3 ? "\r\n" : "\n");
+				if (kind == 4 && fi == 1 && r == nrec / 2) continue;
+				const int len = rng() % 300, width = 1 + rng() % 90;
+				for (int i = 0; i < len; i++) {
+					txt[fi] += "ACGTNacgtRY>"[rng() % (i % width == 0 ? 11 : 12)];   // a '>' inside a line is a letter
+					if (i % width == width - 1) txt[fi] += kind == 3 ? "\r\n" : "\n";
+				}
+				if (rng() % 5 == 0) txt[fi] += "\n";
+				txt[fi] += kind == 3 ? "\r\n" : "\n";
+			}
+			if (kind == 5) while (!txt[fi].empty() && txt[fi].back() == '\n') txt[fi].pop_back();
+		}
+		std::vector<std::string> paths;
+		for (int fi = 0; fi < 2; fi++) {
+			paths.push_back(dir + "/fasta_selfcheck_" + std::to_string(fi) + ".fa");
+			FILE *f = fopen(paths.back().c_str(), "wb");
+			fwrite(txt[fi].data(), 1, txt[fi].size(), f);
+			fclose(f);
+		}
+		mch::FastaBatch a;
+		std::string msg;
+		bool oa = true;
+		std::vector<size_t> first;
+		for (int fi = 0; fi < 2 && oa; fi++) { first.push_back(a.size()); oa = mch::read_fasta(paths[fi], a, msg, (size_t)1 << 60); }
+		first.push_back(a.size());
+		mch::FastaIndex ix;
+		const bool oi = mch::index_fasta_files(paths, ix);
+		if (oi && !oa) { printf("the indexer accepted what the parser rejects (round %d, kind %d)\n", round, kind); return 1; }
+		if (!oi) {
+			if (kind != 3 && kind != 4) { printf("the indexer refused a regular input (round %d, kind %d)\n", round, kind); return 1; }
+			continue;
+		}
+		indexed++;
+		if (ix.headers != a.headers || ix.file_first != first || ix.raw.size() != txt[0].size() + txt[1].size()) { printf("index: headers / files differ in round %d\n", round); return 1; }
+		for (size_t r = 0; r < ix.size(); r++) {
+			std::string sq;
+			for (int64_t p = ix.span_begin[r]; p < ix.span_end[r]; p++) if (ix.raw.data()[p] != '\n') sq += (char)ix.raw.data()[p];
+			const std::string want((const char *)a.letters.data() + a.offsets[r], (size_t)(a.offsets[r + 1] - a.offsets[r]));
+			if (sq != want || (int64_t)sq.size() != ix.letters[r]) { printf("index: record %zu differs in round %d (kind %d)\n", r, round, kind); return 1; }
+		}
+	}
+	if (indexed < 30) { printf("indexer used only %d times\n", indexed); return 1; }
 	if (fast < 20) { printf("parallel path taken only %d times\n", fast); return 1; }
 	printf("ok (%d files took the parallel path)\n", fast);
 	return 0;

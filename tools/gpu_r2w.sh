@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "ingest or hist or encode" 2>&1 | tail -15
+timeout 1500 python -m pytest tests/test_host_logic.py -x -q -m gpu 2>&1 | tail -5
+for cfg in c2 c4 c5; do python tools/gen_config.py $cfg /tmp/$cfg.fa > /dev/null; done
+timeout 600 bin/meshclust /tmp/c2.fa --id 0.97 --kmer 4 --output /tmp/c2.clstr > gpurun_out/r2w_c2.log 2>&1; echo "c2 rc=$? $(md5sum < /tmp/c2.clstr) want 83cffd7e"
+timeout 600 bin/meshclust /tmp/c4.fa --id 0.90 --kmer 5 --output /tmp/c4.clstr > gpurun_out/r2w_c4.log 2>&1; echo "c4 rc=$? $(md5sum < /tmp/c4.clstr) want f0917a7a"
+MC_HOST_PARSE=1 timeout 600 bin/meshclust /tmp/c4.fa --id 0.90 --kmer 5 --output /tmp/c4.clstr > gpurun_out/r2w_c4_host.log 2>&1; echo "c4 host parse rc=$? $(md5sum < /tmp/c4.clstr)"
+timeout 600 bin/meshclust /tmp/c5.fa --kmer 6 --output /tmp/c5.clstr > gpurun_out/r2w_c5.log 2>&1; echo "c5 rc=$? $(md5sum < /tmp/c5.clstr) want 36aebc3b"
+grep -E "\[|Total|Read" gpurun_out/r2w_c4.log | grep -v "^bounds"; echo ---; grep -E "\[|Total|Read" gpurun_out/r2w_c4_host.log | head -8; echo ---; grep -E "\[|Total|Read" gpurun_out/r2w_c5.log | head -8
