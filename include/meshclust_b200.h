@@ -74,6 +74,10 @@ int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int64_t *offset
  * (validate).  Must be followed by mc_load_segments.  MC_ERR_INPUT when spans and letter counts disagree. */
 int mc_ingest_fasta(mc_ctx *ctx, const uint8_t *raw, int64_t raw_bytes, const int64_t *span_begin, const int64_t *span_end,
                     const int64_t *offsets, int64_t n, uint8_t *rec_flags_out);
+/* Optional: send the raw bytes ahead (blocking; meant for a helper thread) while the caller still derives the row
+ * order and the spans.  An mc_ingest_fasta with the same raw / raw_bytes and at most n_records records that follows
+ * without another call on ctx in between does not upload them again. */
+int mc_stage_fasta_bytes(mc_ctx *ctx, const uint8_t *raw, int64_t raw_bytes, int64_t n_records);
 /* The segment lists of the records ingested by mc_ingest_fasta (same layout as in mc_load_sequences).  validate != 0
  * checks every letter against the reference's code table (ChromosomeOneDigit.cpp:59-85; MC_ERR_INPUT = the
  * reference's InvalidInputException); callers pass 0 when no record has flag bit 1. */
@@ -289,6 +293,9 @@ int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t *bin_bounds
  * another GPU of the same process (device-to-device over NVLink): the one-time replication that
  * stands in for the per-scan center broadcast of SURVEY 8(e). */
 int mc_clone_points(mc_ctx *dst, mc_ctx *src);
+/* The same for the sequences (letters / digit strings, offsets, segments): K4 is split by pairs over the GPUs
+ * (Trainer.cpp:253-333, :703-721), and each of them needs both strings of its pairs. */
+int mc_clone_sequences(mc_ctx *dst, mc_ctx *src);
 
 /* mc_accumulate_step across `world` contexts of one process wired with mc_comm_connect_local:
  * rank r evaluates its tiles of the range and owns their alive flags, the marks of

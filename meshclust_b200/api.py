@@ -28,11 +28,11 @@ MC_ERR_CUDA, MC_ERR_ARG, MC_ERR_STATE, MC_ERR_INPUT, MC_ERR_UNSUPPORTED = -1, -2
 # every symbol include/meshclust_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "mc_version", "mc_last_error", "mc_device_count", "mc_ctx_create", "mc_ctx_destroy", "mc_stream",
-    "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_ingest_fasta", "mc_load_segments", "mc_copy_letters", "mc_copy_digits",
+    "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_ingest_fasta", "mc_stage_fasta_bytes", "mc_load_segments", "mc_copy_letters", "mc_copy_digits",
     "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
     "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
     "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_accumulate_run", "mc_near_threshold_count", "mc_permute_rows", "mc_reserve_permute", "mc_comm_init", "mc_comm_connect", "mc_comm_connect_local",
-    "mc_scan_sharded_enqueue", "mc_scan_sharded_enqueue_many", "mc_scan_sharded_collect", "mc_scan_sharded_combine", "mc_scan_sharded_wait", "mc_scan_sharded_burst", "mc_clone_points", "mc_accumulate_step_sharded", "mc_update_centers", "mc_align_pairs",
+    "mc_scan_sharded_enqueue", "mc_scan_sharded_enqueue_many", "mc_scan_sharded_collect", "mc_scan_sharded_combine", "mc_scan_sharded_wait", "mc_scan_sharded_burst", "mc_clone_points", "mc_clone_sequences", "mc_accumulate_step_sharded", "mc_update_centers", "mc_align_pairs",
     "mc_kmer_histograms_host", "mc_scan_host",
 ]
 
@@ -162,6 +162,10 @@ class Context:
         self.n = offsets.size - 1
         self.total_bases = int(offsets[-1])
         _check(_lib.mc_load_sequences(self._h, _p(letters), _p(offsets), C.c_int64(self.n), _p(segs), _p(seg_offsets)))
+
+    def stage_fasta_bytes(self, raw: np.ndarray, n_records: int):
+        assert raw.dtype == np.uint8 and raw.flags.c_contiguous
+        _check(_lib.mc_stage_fasta_bytes(self._h, _p(raw), C.c_int64(raw.size), C.c_int64(n_records)))
 
     def ingest_fasta(self, raw: np.ndarray, span_begin: np.ndarray, span_end: np.ndarray, offsets: np.ndarray) -> np.ndarray:
         """mc_ingest_fasta: raw file bytes + the byte span of every record's sequence lines -> letters on the device;

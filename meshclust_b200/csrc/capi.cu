@@ -283,6 +283,29 @@ extern "C" int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int6
 int mc_launch_ingest(mc_ctx *ctx, const uint8_t *raw_dev, const int64_t *span_begin_dev, const int64_t *span_end_dev, uint8_t *rec_flags_dev,
                      unsigned int *err_dev);
 
+// The raw bytes can go up before the spans are known (the host derives the row order meanwhile): they are parked at
+// the start of the scratch buffer, and the mc_ingest_fasta that follows with the same host buffer finds them there.
+static size_t ingest_scratch_bytes(int64_t raw_bytes, int64_t n) {
+	return Carve::need({(size_t)raw_bytes + 64, (size_t)n * 8, (size_t)n * 8, (size_t)n, 64});
+}
+
+extern "C" int mc_stage_fasta_bytes(mc_ctx *ctx, const uint8_t *raw, int64_t raw_bytes, int64_t n_records) {
+	MC_REQUIRE(ctx && raw && raw_bytes >= 0 && n_records > 0, MC_ERR_ARG, "mc_stage_fasta_bytes: bad arguments");
+	MC_CUDA(cudaSetDevice(ctx->device));
+	ctx->staged_raw = nullptr;
+	int rc = mc_ensure_scratch(ctx, ingest_scratch_bytes(raw_bytes, n_records));
+	if (rc) return rc;
+	Carve cv(ctx->d_scratch);
+	uint8_t *d_raw = cv.take<uint8_t>((size_t)raw_bytes + 64);
+	MC_CUDA(cudaMemcpyAsync(d_raw, raw, (size_t)raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	MC_CUDA(cudaMemsetAsync(d_raw + raw_bytes, '\n', 64, ctx->stream));
+	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->staged_raw = raw;
+	ctx->staged_raw_bytes = raw_bytes;
+	ctx->staged_scratch = ctx->d_scratch;
+	return MC_OK;
+}
+
 extern "C" int mc_ingest_fasta(mc_ctx *ctx, const uint8_t *raw, int64_t raw_bytes, const int64_t *span_begin, const int64_t *span_end,
                                const int64_t *offsets, int64_t n, uint8_t *rec_flags_out) {
 	MC_REQUIRE(ctx && raw && span_begin && span_end && offsets && rec_flags_out && n > 0 && raw_bytes >= 0, MC_ERR_ARG, "mc_ingest_fasta: bad arguments");
@@ -300,15 +323,21 @@ extern "C" int mc_ingest_fasta(mc_ctx *ctx, const uint8_t *raw, int64_t raw_byte
 	MC_CUDA(cudaMemsetAsync(ctx->d_seq + total, 0, 64, ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(ctx->d_seq_off, offsets, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
 	// the raw bytes, the spans and the flags live in the scratch buffer for the length of this call
-	int rc = mc_ensure_scratch(ctx, Carve::need({(size_t)raw_bytes + 64, (size_t)n * 8, (size_t)n * 8, (size_t)n, 64}));
+	const size_t need = ingest_scratch_bytes(raw_bytes, n);
+	// (bytes staged by mc_stage_fasta_bytes are still there if the scratch buffer has not been replaced since)
+	const bool staged = ctx->staged_raw == raw && ctx->staged_raw_bytes == raw_bytes && ctx->staged_scratch == ctx->d_scratch && need <= ctx->scratch_bytes;
+	ctx->staged_raw = nullptr;
+	int rc = mc_ensure_scratch(ctx, need);
 	if (rc) return rc;
 	Carve cv(ctx->d_scratch);
 	uint8_t *d_raw = cv.take<uint8_t>((size_t)raw_bytes + 64);
 	int64_t *d_sb = cv.take<int64_t>((size_t)n), *d_se = cv.take<int64_t>((size_t)n);
 	uint8_t *d_fl = cv.take<uint8_t>((size_t)n);
 	unsigned int *d_err = cv.take<unsigned int>(16);
-	MC_CUDA(cudaMemcpyAsync(d_raw, raw, (size_t)raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
-	MC_CUDA(cudaMemsetAsync(d_raw + raw_bytes, '\n', 64, ctx->stream));
+	if (!staged) {
+		MC_CUDA(cudaMemcpyAsync(d_raw, raw, (size_t)raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		MC_CUDA(cudaMemsetAsync(d_raw + raw_bytes, '\n', 64, ctx->stream));
+	}
 	MC_CUDA(cudaMemcpyAsync(d_sb, span_begin, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(d_se, span_end, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
 	MC_CUDA(cudaMemsetAsync(d_err, 0, 64, ctx->stream));
@@ -1127,6 +1156,39 @@ extern "C" int mc_clone_points(mc_ctx *dst, mc_ctx *src) {
 	dst->model = src->model;
 	dst->model.near = dst->d_near;   // every GPU counts into its own word
 	dst->have_hist = true;
+	return MC_OK;
+}
+
+// The sequences of `src` (letters or digit strings, offsets, segments) copied to `dst`, device to device: every GPU
+// that aligns pairs (K4 is split by pairs) needs the strings of both partners of a pair.
+extern "C" int mc_clone_sequences(mc_ctx *dst, mc_ctx *src) {
+	MC_REQUIRE(dst && src && dst != src, MC_ERR_ARG, "mc_clone_sequences: bad arguments");
+	MC_REQUIRE(src->have_seq, MC_ERR_STATE, "mc_clone_sequences: the source has no sequences");
+	MC_CUDA(cudaSetDevice(src->device));
+	MC_CUDA(cudaStreamSynchronize(src->stream));
+	MC_CUDA(cudaSetDevice(dst->device));
+	free_seq(dst);
+	const int64_t n = src->n, total = src->total_bases, nseg = src->nseg;
+	MC_REQUIRE(!dst->have_hist || dst->n == n, MC_ERR_STATE, "mc_clone_sequences: the destination holds histograms of %lld other rows", (long long)dst->n);
+	dst->n = n; dst->total_bases = total; dst->nseg = nseg;
+	MC_CUDA(cudaMalloc(&dst->d_seq, (size_t)total + 64));
+	MC_CUDA(cudaMalloc(&dst->d_seq_off, (size_t)(n + 1) * sizeof(int64_t)));
+	MC_CUDA(cudaMalloc(&dst->d_seg_off, (size_t)(n + 1) * sizeof(int64_t)));
+	MC_CUDA(cudaMalloc(&dst->d_segs, (size_t)std::max<int64_t>(nseg, 1) * 2 * sizeof(int32_t)));
+	auto copy = [&](void *d, const void *s_, size_t bytes) -> cudaError_t {
+		if (bytes == 0) return cudaSuccess;
+		return dst->device == src->device ? cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, dst->stream)
+		                                  : cudaMemcpyPeerAsync(d, dst->device, s_, src->device, bytes, dst->stream);
+	};
+	MC_CUDA(copy(dst->d_seq, src->d_seq, (size_t)total + 64));
+	MC_CUDA(copy(dst->d_seq_off, src->d_seq_off, (size_t)(n + 1) * sizeof(int64_t)));
+	MC_CUDA(copy(dst->d_seg_off, src->d_seg_off, (size_t)(n + 1) * sizeof(int64_t)));
+	MC_CUDA(copy(dst->d_segs, src->d_segs, (size_t)nseg * 2 * sizeof(int32_t)));
+	MC_CUDA(cudaStreamSynchronize(dst->stream));
+	dst->h_seq_off = src->h_seq_off;
+	dst->digits_ready = src->digits_ready;
+	dst->rows_permuted = false;
+	dst->have_seq = true;
 	return MC_OK;
 }
 

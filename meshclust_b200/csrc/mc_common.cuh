@@ -190,6 +190,9 @@ struct mc_ctx {
 	int64_t *d_seg_off = nullptr;  // n+1
 	int64_t nseg = 0;
 	bool have_seq = false;
+	const uint8_t *staged_raw = nullptr;   // mc_stage_fasta_bytes: host buffer whose bytes sit at the start of the scratch buffer
+	int64_t staged_raw_bytes = 0;
+	void *staged_scratch = nullptr;
 
 	// histograms
 	int k = 0;

@@ -78,6 +78,9 @@ struct Ctx {
 	std::thread ranks_thread;         // creates the contexts of ranks 1.. in the background
 	int ranks_rc = MC_OK;
 	std::string ranks_err;
+	bool shard_phase_a = false;       // the Phase-A scans are shared by all ranks (inputs of gigabytes)
+	bool seq_cloned = false;          // ranks 1.. hold copies of the sequences (alignments are split by pairs)
+	long align_split_calls = 0;       // alignment batches that were split over the GPUs
 	Options opt;
 	Dataset ds;
 	Model model;
@@ -103,15 +106,85 @@ struct ScoredLess {
 	bool operator()(const std::pair<Pair, double> &a, const std::pair<Pair, double> &b) const { return base(a.first, b.first); }
 };
 
+// the contexts of ranks 1.. (created in the background since start-up) and their copies of the sequences
+void join_ranks(Ctx &c) {
+	if (c.ranks_thread.joinable()) c.ranks_thread.join();
+	if (c.ranks_rc != MC_OK) {
+		fprintf(stderr, "meshclust: mc_ctx_create failed on an additional GPU: %s\n", c.ranks_err.c_str());
+		exit(2);
+	}
+}
+
+void ensure_rank_sequences(Ctx &c) {
+	if (c.seq_cloned) return;
+	Timer t;
+	join_ranks(c);
+	std::vector<std::thread> th;
+	std::vector<int> rcs(c.ranks.size(), MC_OK);
+	for (size_t r = 1; r < c.ranks.size(); r++) th.emplace_back([&, r]() { rcs[r] = mc_clone_sequences(c.ranks[r], c.gpu); });
+	for (auto &x : th) x.join();
+	for (size_t r = 1; r < c.ranks.size(); r++)
+		if (rcs[r] != MC_OK) die_gpu("mc_clone_sequences");
+	c.seq_cloned = true;
+	printf("  [sequences copied to %zu more GPUs %.2fs]\n", c.ranks.size() - 1, t.lap());
+}
+
+// mc_align_pairs over row pairs, on all GPUs of the run when the batch is worth it.
+// K4 is embarrassingly parallel over pairs.  Cells, not pairs, are the unit of work: the batch is cut
+// into contiguous runs of equal cell counts, one per GPU, each driven by its own host thread; the other GPUs get
+// their copy of the sequences the first time this happens.
+void align_rows(Ctx &c, const std::vector<int32_t> &a, const std::vector<int32_t> &b, std::vector<int32_t> &sc, std::vector<int32_t> &ln,
+                std::vector<int32_t> &mt) {
+	const size_t m = a.size();
+	sc.resize(m); ln.resize(m); mt.resize(m);
+	if (m == 0) return;
+	const int world = (int)c.ranks.size();
+	double cells = 0;
+	std::vector<double> cell_prefix;
+	if (world > 1 && m >= (size_t)(4 * world)) {
+		cell_prefix.resize(m + 1, 0.0);
+		for (size_t i = 0; i < m; i++)
+			cell_prefix[i + 1] = cell_prefix[i] + (double)c.ds.len[(size_t)c.ds.id_of_row[(size_t)a[i]]] * (double)c.ds.len[(size_t)c.ds.id_of_row[(size_t)b[i]]];
+		cells = cell_prefix[m];
+	}
+	static const double split_min_cells = getenv("MC_ALIGN_SPLIT_MIN_CELLS") ? atof(getenv("MC_ALIGN_SPLIT_MIN_CELLS")) : 4e9;
+	if (world > 1 && cells >= split_min_cells) {
+		ensure_rank_sequences(c);
+		std::vector<size_t> cut((size_t)world + 1, m);
+		cut[0] = 0;
+		for (int r = 1; r < world; r++)
+			cut[(size_t)r] = (size_t)(std::lower_bound(cell_prefix.begin(), cell_prefix.end(), cells * r / world) - cell_prefix.begin());
+		for (int r = 1; r <= world; r++) cut[(size_t)r] = std::min(m, std::max(cut[(size_t)r], cut[(size_t)r - 1]));
+		std::vector<int> rcs((size_t)world, MC_OK);
+		std::vector<std::string> errs((size_t)world);
+		std::vector<std::thread> th;
+		for (int r = 0; r < world; r++) {
+			const size_t lo = cut[(size_t)r], hi = cut[(size_t)r + 1];
+			if (hi <= lo) continue;
+			th.emplace_back([&, r, lo, hi]() {
+				rcs[(size_t)r] = mc_align_pairs(c.ranks[(size_t)r], a.data() + lo, b.data() + lo, (int64_t)(hi - lo), sc.data() + lo, ln.data() + lo, mt.data() + lo);
+				if (rcs[(size_t)r] != MC_OK) errs[(size_t)r] = mc_last_error();
+			});
+		}
+		for (auto &t : th) t.join();
+		for (int r = 0; r < world; r++)
+			if (rcs[(size_t)r] != MC_OK) {
+				fprintf(stderr, "meshclust: mc_align_pairs failed on GPU %d: %s\n", r, errs[(size_t)r].c_str());
+				exit(2);
+			}
+		c.align_split_calls++;
+	} else GPU(mc_align_pairs(c.gpu, a.data(), b.data(), (int64_t)m, sc.data(), ln.data(), mt.data()));
+}
+
 // GlobAlignE identity of (a, b) id pairs: matches / length as double (GlobAlignE.cpp:301-305)
 std::vector<double> align_ids(Ctx &c, const std::vector<Pair> &pairs) {
 	const size_t m = pairs.size();
-	std::vector<int32_t> a(m), b(m), sc(m), ln(m), mt(m);
+	std::vector<int32_t> a(m), b(m), sc, ln, mt;
 	for (size_t i = 0; i < m; i++) {
 		a[i] = (int32_t)c.ds.row_of_id[pairs[i].first];
 		b[i] = (int32_t)c.ds.row_of_id[pairs[i].second];
 	}
-	if (m) GPU(mc_align_pairs(c.gpu, a.data(), b.data(), (int64_t)m, sc.data(), ln.data(), mt.data()));
+	align_rows(c, a, b, sc, ln, mt);
 	std::vector<double> id(m);
 	for (size_t i = 0; i < m; i++) id[i] = (double)mt[i] / ln[i];
 	return id;
@@ -210,8 +283,11 @@ std::vector<Pair> trainer_split(Ctx &c) {
 		double mean_len = 0;
 		for (size_t i = 0; i < np; i++) mean_len += (double)(ds.fa.offsets[(size_t)pivots[i] + 1] - ds.fa.offsets[(size_t)pivots[i]]);
 		mean_len /= (double)std::max<size_t>(np, 1);
-		if (mean_len * mean_len > 1e7)
-			while (SPEC > 1 && np * ((size_t)(1 << SPEC) - 1) > 1800) SPEC--;
+		if (mean_len * mean_len > 1e7) {
+			// every GPU of the run takes its share of a round: with more of them, look further ahead (fewer rounds)
+			SPEC = c.ranks.size() > 1 ? 6 : 4;
+			while (SPEC > 1 && np * ((size_t)(1 << SPEC) - 1) > 1800 * c.ranks.size()) SPEC--;
+		}
 		if (getenv("MC_SPLIT_SPEC")) SPEC = std::max(1, std::min(6, atoi(getenv("MC_SPLIT_SPEC"))));
 	}
 	std::vector<size_t> offset(np, (size_t)n / 4), pos(np, 2 * ((size_t)n / 4));
@@ -561,8 +637,8 @@ void align_scan(Ctx &c, BVec &bv, AlignCache &cache, int64_t center_row, int64_t
 		else { need.push_back(i); a.push_back((int32_t)rows[i]); b.push_back((int32_t)center_row); }
 	}
 	if (!need.empty()) {
-		std::vector<int32_t> sc(need.size()), ln(need.size()), mt(need.size());
-		GPU(mc_align_pairs(c.gpu, a.data(), b.data(), (int64_t)need.size(), sc.data(), ln.data(), mt.data()));
+		std::vector<int32_t> sc, ln, mt;
+		align_rows(c, a, b, sc, ln, mt);
 		for (size_t t = 0; t < need.size(); t++) {
 			const double v = (double)mt[t] / ln[t];
 			ident[need[t]] = v;
@@ -634,12 +710,10 @@ void mean_shift(Ctx &c, BVec &bv) {
 	AlignCache cache;
 	std::vector<uint8_t> alive;   // host mirror, only needed by the --align scans
 	if (c.model.align) alive.assign((size_t)ds.n, 1);
-	const int world = (int)c.ranks.size();
-	if (c.ranks_thread.joinable()) c.ranks_thread.join();
-	if (c.ranks_rc != MC_OK) {
-		fprintf(stderr, "meshclust: mc_ctx_create failed on an additional GPU: %s\n", c.ranks_err.c_str());
-		exit(2);
-	}
+	// several GPUs share the Phase-A scans only when one scan is long (see run_pipeline); otherwise the additional
+	// GPUs have served the alignments of the training stage and rank 0 runs the persistent kernel alone
+	const int world = c.shard_phase_a ? (int)c.ranks.size() : 1;
+	if (world > 1) join_ranks(c);
 	// ---------------- Phase A on the device (mc_accumulate_run) ---------------------------------
 	// The whole `while (last) accumulate(...)` loop (ClusterFactory.cpp:722-729, :637-714) with its bvec
 	// bookkeeping runs as one persistent kernel; the host only reads the clusters back.  --align (the
@@ -912,17 +986,38 @@ int run_pipeline(Options opt) {
 	// inputs stay on one GPU.  The input size is known before the first CUDA call (file sizes), the histogram
 	// size is not: the rule is on the bytes of FASTA (MC_SHARD_MIN_BYTES, default 3 GB; tests force sharding
 	// with MC_PHASE_A_STEPS).
-	if (opt.gpus > 1 && !getenv("MC_PHASE_A_STEPS")) {
+	if (opt.gpus > 1) {
 		unsigned long long total_bytes = 0;
 		for (const std::string &f : opt.files) {
 			struct stat stt;
 			if (stat(f.c_str(), &stt) == 0) total_bytes += (unsigned long long)stt.st_size;
 		}
 		const unsigned long long min_bytes = getenv("MC_SHARD_MIN_BYTES") ? strtoull(getenv("MC_SHARD_MIN_BYTES"), nullptr, 10) : 3000000000ull;
-		if (total_bytes < min_bytes) {
-			printf("  [--gpus %d: %.2f GB of input, Phase A stays on one GPU (persistent kernel)]\n", opt.gpus, (double)total_bytes * 1e-9);
+		c.shard_phase_a = getenv("MC_PHASE_A_STEPS") != nullptr || total_bytes >= min_bytes;
+		// The alignments of the training stage (K4) are split by pairs over the GPUs; that pays when a pair is
+		// millions of cells, i.e. for sequences of several thousand letters.  The record length is estimated from
+		// the head of the first file (bytes per '>' line) -- all that is known before the first CUDA call.
+		double est_len = 0;
+		if (!opt.files.empty()) {
+			FILE *f = fopen(opt.files[0].c_str(), "rb");
+			if (f) {
+				std::vector<char> head((size_t)1 << 20);
+				const size_t got = fread(head.data(), 1, head.size(), f);
+				fclose(f);
+				size_t recs = 0;
+				for (size_t i = 0; i < got; i++) recs += head[i] == '>' && (i == 0 || head[i - 1] == '\n');
+				est_len = recs ? (double)got / (double)recs : (double)got;
+			}
+		}
+		const double min_len = getenv("MC_ALIGN_SHARD_MIN_LEN") ? atof(getenv("MC_ALIGN_SHARD_MIN_LEN")) : 3000.0;
+		const bool share_alignments = est_len >= min_len || opt.align;
+		if (!c.shard_phase_a && !share_alignments) {
+			printf("  [--gpus %d: %.2f GB of input, records of ~%.0f letters: one GPU (persistent Phase-A kernel, alignment batches too small to split)]\n",
+			       opt.gpus, (double)total_bytes * 1e-9, est_len);
 			opt.gpus = 1;
 			c.opt.gpus = 1;
+		} else if (!c.shard_phase_a) {
+			printf("  [--gpus %d: alignments are split over the GPUs, Phase A stays on one (%.2f GB of input)]\n", opt.gpus, (double)total_bytes * 1e-9);
 		}
 	}
 	// CUDA start-up time grows with the number of GPUs the driver has to initialise: expose only the
@@ -934,6 +1029,8 @@ int run_pipeline(Options opt) {
 		opt.device = 0;
 	}
 	c.ranks.assign((size_t)std::max(1, opt.gpus), nullptr);
+	std::promise<void> ctx_up;
+	std::shared_future<void> ctx_ready = ctx_up.get_future().share();
 	std::thread ctx_thread([&]() {
 		Timer t;
 		const int ndev = std::max(1, mc_device_count());
@@ -942,11 +1039,14 @@ int run_pipeline(Options opt) {
 		if (ctx_rc != MC_OK) ctx_err = mc_last_error();
 		c.gpu = c.ranks[0];
 		ctx_s = t.lap();
+		ctx_up.set_value();
 	});
-	// the other ranks are needed only when Phase A starts: their contexts come up in parallel, in the
-	// background, and are joined there
+	// the other ranks are needed only when the first large alignment batch or a sharded Phase A starts: their
+	// contexts come up in the background and are joined there -- AFTER rank 0's, which everything waits for
+	// (contexts created at the same time share the driver's start-up lock: rank 0 took 5.8 s instead of 1.6 s)
 	if (c.ranks.size() > 1)
-		c.ranks_thread = std::thread([&c, opt]() {
+		c.ranks_thread = std::thread([&c, opt, ctx_ready]() {
+			ctx_ready.wait();
 			const int ndev = std::max(1, mc_device_count());
 			std::vector<std::thread> more;
 			std::vector<int> rcs(c.ranks.size(), MC_OK);
@@ -976,6 +1076,18 @@ int run_pipeline(Options opt) {
 	// semantics.  MC_HOST_PARSE=1 forces the host parser.
 	FastaIndex fidx;
 	const bool indexed = !getenv("MC_HOST_PARSE") && index_fasta_files(opt.files, fidx);
+	// the raw bytes go up on a helper thread as soon as the context exists, while this thread derives the row order
+	std::thread stage_thread;
+	int stage_rc = MC_OK;
+	double stage_s = 0;
+	if (indexed)
+		stage_thread = std::thread([&]() {
+			ctx_ready.wait();
+			if (ctx_rc != MC_OK) return;
+			Timer t;
+			stage_rc = mc_stage_fasta_bytes(c.gpu, fidx.raw.data(), (int64_t)fidx.raw.size(), (int64_t)fidx.size());
+			stage_s = t.lap();
+		});
 	if (indexed) {
 		file_first = fidx.file_first;
 		c.ds.fa.headers.swap(fidx.headers);
@@ -1057,6 +1169,8 @@ int run_pipeline(Options opt) {
 			for (int64_t r = 0; r < ds.n; r++) { sb[r] = fidx.span_begin[ds.id_of_row[r]]; se[r] = fidx.span_end[ds.id_of_row[r]]; }
 			printf("  [row order %.2fs]\n", tm.lap());
 			join_ctx();
+			stage_thread.join();
+			if (stage_rc == MC_OK) printf("  [file bytes sent ahead in %.2fs on a helper thread, waited %.2fs]\n", stage_s, tm.lap());
 			std::vector<uint8_t> rflags((size_t)ds.n);
 			if (mc_ingest_fasta(c.gpu, fidx.raw.data(), (int64_t)fidx.raw.size(), sb.data(), se.data(), offs.data(), ds.n, rflags.data()) != MC_OK) die_gpu("mc_ingest_fasta");
 			// segments (Chromosome.cpp:162-258): a record without N is one run -- kept from 20 letters on, cut at 1 Mbp --
@@ -1166,7 +1280,7 @@ int run_pipeline(Options opt) {
 	}
 	mean_shift(c, bv);
 	printf("Total %.2fs\n", total.lap());
-	if (getenv("MC_CLEAN_EXIT")) { for (mc_ctx *g : c.ranks) mc_ctx_destroy(g); return 0; }
+	if (getenv("MC_CLEAN_EXIT")) { join_ranks(c); for (mc_ctx *g : c.ranks) mc_ctx_destroy(g); return 0; }
 	// the output file is closed: skip the teardown of the CUDA context and of GBs of host vectors
 	fflush(stdout);
 	fflush(stderr);

@@ -75,6 +75,7 @@ int mc_load_sequences(mc_ctx *c, const uint8_t *letters, const int64_t *offsets,
 	}
 	return MC_OK;
 }
+int mc_stage_fasta_bytes(mc_ctx *, const uint8_t *, int64_t, int64_t) { return MC_OK; }
 int mc_ingest_fasta(mc_ctx *c, const uint8_t *raw, int64_t raw_bytes, const int64_t *span_begin, const int64_t *span_end, const int64_t *offsets,
                     int64_t n, uint8_t *rec_flags_out) {
 	(void)raw_bytes;
@@ -385,6 +386,7 @@ int mc_accumulate_run(mc_ctx *c, double sim, const uint64_t *bin_bounds, const i
 }
 
 int mc_clone_points(mc_ctx *dst, mc_ctx *src) { *dst = *src; return MC_OK; }
+int mc_clone_sequences(mc_ctx *dst, mc_ctx *src) { *dst = *src; return MC_OK; }
 int mc_comm_init(mc_ctx *, int, int, uint8_t *) { return MC_OK; }
 int mc_comm_connect_local(mc_ctx *const *, int) { return MC_OK; }
 int mc_accumulate_step_sharded(mc_ctx *const *ctxs, int world, int64_t center, int64_t lo, int64_t hi, int restart, mc_step_result *res, int64_t *rows_out, int64_t cap) {

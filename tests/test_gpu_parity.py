@@ -98,6 +98,8 @@ def test_ingest_fasta_vs_host_parser(ctx, oracle, n, k):
     sb = np.array([spans[i][0] for i in order], np.int64)
     se = np.array([spans[i][1] for i in order], np.int64)
     letters = np.concatenate([recs[i] for i in order]).astype(np.uint8)
+    if n > 1:
+        ctx.stage_fasta_bytes(raw, n)       # the bytes go ahead; the ingest below must find them (same buffer)
     flags = ctx.ingest_fasta(raw, sb, se, offs)
     assert np.array_equal(ctx.copy_letters(), letters)
     up = letters & 0xDF

@@ -120,6 +120,18 @@ def test_clstr_identical_with_sharded_phase_a(built_lib, tmp_path, name, gpus):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,gpus", [("A", 2), ("c1_full", 3), ("Q", 2), ("G", 2)])
+def test_clstr_identical_with_split_alignments(built_lib, tmp_path, name, gpus):
+    # --gpus N splits the alignment batches of the training stage by pairs over N contexts (on a
+    # 1-GPU box they share the device), each with its own copy of the sequences; Phase A stays on one GPU
+    from meshclust_b200 import build
+    cli = build.build_cli()
+    got, log = _run(cli, name, tmp_path, extra=("--gpus", str(gpus)), env={"MC_ALIGN_SPLIT_MIN_CELLS": "1", "MC_ALIGN_SHARD_MIN_LEN": "1"})
+    assert "sequences copied to %d more GPUs" % (gpus - 1) in log and "peer inboxes connected" not in log
+    assert got == H.read_golden(name), log[-1500:]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,gpus", [("A", 1), ("B", 1), ("c1_full", 1), ("E", 2), ("F", 3)])
 def test_clstr_identical_with_row_compaction_gpu(built_lib, tmp_path, name, gpus):
     from meshclust_b200 import build
