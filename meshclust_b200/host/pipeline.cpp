@@ -28,6 +28,7 @@
 
 #include "bvec.hpp"
 #include "fasta.hpp"
+#include "lazy_sort.hpp"
 #include "matrix.hpp"
 #include "meshclust_b200.h"
 
@@ -252,23 +253,35 @@ std::vector<Pair> trainer_split(Ctx &c) {
 
 	// :694-701 per pivot: copy + unstable sort by distance to the pivot.  Independent per pivot, so
 	// the host threads can share them without changing any permutation.
-	std::vector<std::vector<int>> sorted(np);
+	// Only ~40 positions of every sorted array are ever looked at (the search below, twenty picks at the end): the
+	// sorts run lazily (host/lazy_sort.hpp: libstdc++'s introsort restricted to the ranges that hold a position asked
+	// for -- the same permutation among equal keys, a fraction of the work).  MC_SPLIT_FULL_SORT=1: plain std::sort.
+	struct ByKey { bool operator()(const KeyId &a, const KeyId &b) const { return a.key < b.key; } };
+	std::vector<LazySort<KeyId, ByKey>> sorted(np);
 	std::vector<int32_t> row_of_point((size_t)n);
 	for (int64_t i = 0; i < n; i++) row_of_point[i] = (int32_t)ds.row_of_id[points[i]];
+	const bool full_sort = getenv("MC_SPLIT_FULL_SORT") != nullptr;
 #pragma omp parallel for schedule(dynamic)
 	for (long i = 0; i < (long)np; i++) {
 		const uint16_t *kk = keys.data() + (size_t)i * n;
 		std::vector<KeyId> rec((size_t)n);
 		for (int64_t j = 0; j < n; j++) rec[j] = {kk[row_of_point[j]], points[j]};
-		std::sort(rec.begin(), rec.end(), [](const KeyId &a, const KeyId &b) { return a.key < b.key; });
-		std::vector<int> pts((size_t)n);
-		for (int64_t j = 0; j < n; j++) pts[j] = rec[j].id;
-		sorted[i].swap(pts);
+		if (full_sort) std::sort(rec.begin(), rec.end(), ByKey());
+		sorted[(size_t)i] = LazySort<KeyId, ByKey>(std::move(rec), ByKey(), full_sort ? 0 : -1);
+		if (full_sort) sorted[(size_t)i].mark_sorted();
 	}
 	keys.clear();
 	keys.shrink_to_fit();
-	const double t_sorts = st.lap();
+	double t_sorts = st.lap();
 	int rounds = 0;
+	// positions of sorted[i] resolved by the host threads, pivot by pivot, before the serial code reads them
+	auto resolve = [&](const std::vector<std::vector<size_t>> &ask) {
+		Timer tr;
+#pragma omp parallel for schedule(dynamic)
+		for (long i = 0; i < (long)np; i++)
+			for (size_t p : ask[(size_t)i]) sorted[(size_t)i].at(p);
+		t_sorts += tr.lap();
+	};
 
 	// :703-721 binary search with alignment, all pivots in lock step (each search is independent).
 	// One round of the reference is one alignment per pivot: 150 pairs cannot fill a GPU, and a
@@ -297,21 +310,33 @@ std::vector<Pair> trainer_split(Ctx &c) {
 		std::vector<Pair> q;
 		std::vector<char> reach;             // per node: will the search ever align it?
 		std::vector<size_t> first(np + 1, 0);
+		// breadth-first over the decision tree of every active pivot: node 0 = current position; children of
+		// node t are 2t+1 (answer below the cutoff: pos - off) and 2t+2 (above: pos + off), off halving per level
+		const size_t tree = (size_t)(1 << SPEC) - 1;
+		std::vector<size_t> npos(np * tree, 0), noff(np * tree, 0);
+		std::vector<std::vector<size_t>> ask(np);
+		for (size_t i = 0; i < np; i++) {
+			if (!active[i]) continue;
+			size_t *ps = npos.data() + i * tree, *of = noff.data() + i * tree;
+			ps[0] = pos[i]; of[0] = offset[i];
+			for (size_t t = 0; t < tree; t++) {
+				const bool reachable = of[t] > 0;   // offset 0 ends the search before this alignment
+				if (reachable) ask[i].push_back(ps[t]);
+				if (2 * t + 2 < tree) {
+					ps[2 * t + 1] = reachable ? ps[t] - of[t] : 0; of[2 * t + 1] = reachable ? of[t] / 2 : 0;
+					ps[2 * t + 2] = reachable ? ps[t] + of[t] : 0; of[2 * t + 2] = reachable ? of[t] / 2 : 0;
+				}
+			}
+		}
+		resolve(ask);
 		for (size_t i = 0; i < np; i++) {
 			first[i] = q.size();
 			if (!active[i]) continue;
-			// breadth-first over the decision tree: node 0 = current position; children of node t are
-			// 2t+1 (answer below the cutoff: pos - off) and 2t+2 (above: pos + off), off halving per level
-			std::vector<size_t> npos((size_t)(1 << SPEC) - 1), noff((size_t)(1 << SPEC) - 1);
-			npos[0] = pos[i]; noff[0] = offset[i];
-			for (size_t t = 0; t < npos.size(); t++) {
-				const bool reachable = noff[t] > 0;   // offset 0 ends the search before this alignment
-				q.push_back({pivots[i], reachable ? sorted[i][npos[t]] : pivots[i]});
+			const size_t *ps = npos.data() + i * tree, *of = noff.data() + i * tree;
+			for (size_t t = 0; t < tree; t++) {
+				const bool reachable = of[t] > 0;
+				q.push_back({pivots[i], reachable ? sorted[i].at(ps[t]).id : pivots[i]});
 				reach.push_back(reachable ? 1 : 0);
-				if (2 * t + 2 < npos.size()) {
-					npos[2 * t + 1] = reachable ? npos[t] - noff[t] : 0; noff[2 * t + 1] = reachable ? noff[t] / 2 : 0;
-					npos[2 * t + 2] = reachable ? npos[t] + noff[t] : 0; noff[2 * t + 2] = reachable ? noff[t] / 2 : 0;
-				}
 			}
 		}
 		first[np] = q.size();
@@ -344,8 +369,24 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	int aerr = 0;
 	HeaderPairLess less{&ds.fa.headers};
 	std::set<Pair, HeaderPairLess> pairs(less);
+	{
+		// the picks' positions, resolved by all threads first (the same arithmetic as the loop below)
+		std::vector<std::vector<size_t>> ask(np);
+		for (size_t i = 0; i < np; i++) {
+			const size_t pivot = pos[i], sz = sorted[i].size();
+			const double before_inc = (double)pivot / to_add_each, after_inc = ((double)(sz - pivot)) / to_add_each;
+			double before_start = 0, after_start = (double)pivot;
+			for (size_t t = 0; t < to_add_each; t++) { ask[i].push_back((size_t)(int)std::round(before_start)); before_start += before_inc; }
+			for (size_t t = 0; t < to_add_each && std::round(after_start) < sz; t++) { ask[i].push_back((size_t)(int)std::round(after_start)); after_start += after_inc; }
+		}
+		resolve(ask);
+	}
 	for (size_t i = 0; i < np; i++) {
-		const std::vector<int> &pts = sorted[i];
+		struct Pts {
+			LazySort<KeyId, ByKey> &s;
+			size_t size() const { return s.size(); }
+			int operator[](size_t k) const { return s.at(k).id; }
+		} pts{sorted[i]};
 		const int p = pivots[i];
 		const size_t pivot = pos[i];
 		const double before_inc = (double)pivot / to_add_each;
@@ -1080,14 +1121,16 @@ int run_pipeline(Options opt) {
 	std::thread stage_thread;
 	int stage_rc = MC_OK;
 	double stage_s = 0;
-	if (indexed)
-		stage_thread = std::thread([&]() {
+	if (indexed) {
+		const int64_t nrec = (int64_t)fidx.size();   // (the headers move out of the index below)
+		stage_thread = std::thread([&, nrec]() {
 			ctx_ready.wait();
 			if (ctx_rc != MC_OK) return;
 			Timer t;
-			stage_rc = mc_stage_fasta_bytes(c.gpu, fidx.raw.data(), (int64_t)fidx.raw.size(), (int64_t)fidx.size());
+			stage_rc = mc_stage_fasta_bytes(c.gpu, fidx.raw.data(), (int64_t)fidx.raw.size(), nrec);
 			stage_s = t.lap();
 		});
+	}
 	if (indexed) {
 		file_first = fidx.file_first;
 		c.ds.fa.headers.swap(fidx.headers);
@@ -1171,6 +1214,7 @@ int run_pipeline(Options opt) {
 			join_ctx();
 			stage_thread.join();
 			if (stage_rc == MC_OK) printf("  [file bytes sent ahead in %.2fs on a helper thread, waited %.2fs]\n", stage_s, tm.lap());
+			else fprintf(stderr, "meshclust: sending the file bytes ahead failed (%s); they go up with the ingest\n", mc_last_error());
 			std::vector<uint8_t> rflags((size_t)ds.n);
 			if (mc_ingest_fasta(c.gpu, fidx.raw.data(), (int64_t)fidx.raw.size(), sb.data(), se.data(), offs.data(), ds.n, rflags.data()) != MC_OK) die_gpu("mc_ingest_fasta");
 			// segments (Chromosome.cpp:162-258): a record without N is one run -- kept from 20 letters on, cut at 1 Mbp --
