@@ -552,8 +552,10 @@ def main():
                     # Phase A as the product runs it (one persistent kernel: range, scan, exchange, mean, next center)
                     pa["achieved_GBs"] = round(pa["evals"] * (nbins + 33) / pa["device_s"] / 1e9, 1)
                     pa["frac_of_peak"] = round(pa["achieved_GBs"] / peak, 4)
-                    pa["note"] = ("bin/meshclust, accumulate() on the device: evals = alive points actually evaluated (dead rows are streamed "
-                                  "too but not counted); algorithmic bytes = evals x (4^k + 33)")
+                    pa["note"] = ("bin/meshclust, accumulate() on the device: evals = alive points actually evaluated; the kernel compacts "
+                                  "the rows whenever an eighth has left, so it streams at most 8/7 of them; algorithmic bytes = evals x "
+                                  "(4^k + 33).  C2's 25.6 MB matrix lives in L2: a step is two exchange latencies around a 3.6 us scan; "
+                                  "the HBM-sized inputs run at 0.73 (C4) and 0.61 (C5) of the peak, profiles/r02_cli_stages.md")
                     out["phase_a_in_product"] = pa
             except Exception as e:
                 out["seqs_clustered"] = {"error": str(e)[:200]}
