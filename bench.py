@@ -14,9 +14,10 @@ chain, one launch per scan, each behind the one before it (programmatic dependen
            of the kernel; Phase A never issues that shape.
   phase_a_in_product: Phase A of bin/meshclust on the full C2 input (one persistent kernel: range, scan,
            exchange, mean, next center on the device), evals/s and fraction of the HBM roofline.
-  e2e    : S scans through the host-buffer C-ABI call mc_scan_host() on every rank: pinned host
-           histograms -> HBM (in chunks, overlapped with the scans of the previous chunk), S scans,
-           marks + summaries back to the host, all inside the timed region.
+  e2e    : the same step through host buffers on every rank: one batch goes up from pinned host memory
+           (mc_load_histograms), the step's dependent scans run against it, summaries and marks come back to
+           the host, all inside the timed region (wall clock, max over ranks).  e2e.one_upload_per_10_scans is
+           the round-1 form (mc_scan_host: S scans per upload, chunked upload overlapped with the scans).
   --gpus N (torchrun, one process per GPU): weak scaling: every rank holds all N*n points and evaluates
            its n of every scan; the summaries cross GPUs through NVLink peer inboxes (CUDA IPC) on a second
            stream; value = evals of all ranks / max-over-ranks time.  extra.c4_shape_scan is the 1 M-point
@@ -510,11 +511,54 @@ def main():
             e2e_s = float(tt.item())
         # bytes mc_scan_host moves per call: histograms + lengths + copies of the S center rows up; S mark
         # arrays + the CTA partial records of S scans x 4 chunks (160 x 32 B each) down
-        out["e2e"] = {"value": world * S * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * (n * nbins + n * 8 + S * (nbins + 8))),
-                      "d2h_bytes_per_step": int(world * (S * n + 4 * S * 160 * 32)), "ms_per_step": e2e_s * 1e3,
-                      "step": f"{S} get_close scans of every rank's {n} points from pinned host memory",
-                      "call": "mc_scan_host on every rank (pinned host histograms -> chunked upload overlapped with S scans per chunk -> marks + summaries on the host); "
-                              "max over ranks of the time per call"}
+        e2e_small = {"value": world * S * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * (n * nbins + n * 8 + S * (nbins + 8))),
+                     "d2h_bytes_per_step": int(world * (S * n + 4 * S * 160 * 32)), "ms_per_step": e2e_s * 1e3,
+                     "step": f"{S} get_close scans of every rank's {n} points from pinned host memory (one upload per {S} scans)",
+                     "call": "mc_scan_host on every rank (pinned host histograms -> chunked upload overlapped with S scans per chunk -> marks + summaries on the host); "
+                             "max over ranks of the time per call"}
+        # ---- the bench's own step through host buffers: one batch goes up from pinned host memory (mc_load_histograms),
+        # the step's dependent scans run against it (the same enqueue calls as the headline), the summaries of the last
+        # call and the marks of a final mc_scan come back.  The product uploads a batch once per ~2000 scans (Phase A).
+        cr_calls = [np.ascontiguousarray(centers_local[(np.arange(S) + c * S) % centers_local.size], np.int64) for c in range(CALLS_PER_STEP)]
+        lo0, hi0 = np.zeros(S, np.int64), np.full(S, n - 1, np.int64)
+
+        def chain_step():
+            ctx2.load_histograms(hnp, lnp, K)
+            for c in range(CALLS_PER_STEP):
+                ctx2.scan_enqueue_many(cr_calls[c], lo0, hi0, api.MC_SCAN_CHAIN, 0)
+            res = ctx2.scan_collect(0, S)
+            last, mk = ctx2.scan(int(cr_calls[0][0]), 0, n - 1)
+            return res + [last.as_tuple()], mk
+
+        for _ in range(2):
+            chain_step()
+        reps2 = max(3, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps2):
+            res, mk = chain_step()
+            if world > 1:
+                for i, r in enumerate(res[:S]):
+                    summ[i, 0], summ[i, 1], summ[i, 2], summ[i, 3] = r[0], r[1], r[3], (r[2] + rank * n if r[2] >= 0 else -1)
+                summ_dev.copy_(summ)
+                dist.all_gather_into_tensor(gath_dev, summ_dev)
+                gath = gath_dev.cpu()
+        chain_s = (time.perf_counter() - t0) / reps2
+        if world > 1:
+            tt = torch.tensor([chain_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            chain_s = float(tt.item())
+        assert all(r[0] == n for r in res[:S]), "e2e chain: a scan did not evaluate every point"
+        nscans = CALLS_PER_STEP * S + 1
+        out["e2e"] = {"value": world * nscans * n / chain_s, "unit": UNIT,
+                      "h2d_bytes_per_step": int(world * (n * nbins + n * 8 + CALLS_PER_STEP * S * 24 + 24)),
+                      "d2h_bytes_per_step": int(world * (n + (S + 1) * 160 * 32)), "ms_per_step": chain_s * 1e3,
+                      "step": f"one batch of {n} points per rank uploaded from pinned host memory, then the step's {nscans} dependent get_close scans "
+                              f"against it, summaries + marks read back (scans after the first find the {n * nbins / 1e6:.1f} MB batch in L2, as the "
+                              "product's Phase A does on this input)",
+                      "call": "mc_load_histograms + mc_scan_enqueue_many (MC_SCAN_CHAIN) x %d + mc_scan_collect + mc_scan, wall clock, max over ranks" % CALLS_PER_STEP,
+                      "one_upload_per_10_scans": e2e_small}
         if rank == 0:
             # parity spot-check of what was just timed (oracle as the checker only)
             import _oracle
