@@ -75,6 +75,19 @@ def test_clstr_identical_with_row_compaction_cpu(mock_cli, tmp_path, name):
     assert got == H.read_golden(name)
 
 
+@pytest.mark.parametrize("name", ["D", "F", "I"])
+def test_clstr_identical_with_host_parser_cpu(mock_cli, tmp_path, name):
+    # MC_HOST_PARSE=1: the host parser + mc_load_sequences instead of the index + mc_ingest_fasta the well-formed
+    # inputs take by default (two files, IUPAC / lower case / N runs, 16-bit histograms): the same CLSTR file;
+    # MC_SPLIT_FULL_SORT=1: Trainer::split's pivot sorts as full std::sorts instead of the lazy ones
+    got, log = _run(mock_cli, name, tmp_path, env={"MC_HOST_PARSE": "1", "MC_SPLIT_FULL_SORT": "1"})
+    assert "row order + segments" in log
+    assert got == H.read_golden(name)
+    got2, log2 = _run(mock_cli, name, tmp_path)
+    assert "row order + segments" not in log2 and "row order" in log2
+    assert got2 == got
+
+
 def test_cli_errors(mock_cli, tmp_path):
     # Runner.cpp:150-263: bad values and missing files exit non-zero with the reference's messages
     r = subprocess.run([mock_cli], capture_output=True, text=True)
