@@ -14,9 +14,9 @@ chain, one launch per scan, each behind the one before it (programmatic dependen
            of the kernel; Phase A never issues that shape.
   phase_a_in_product: Phase A of bin/meshclust on the full C2 input (one persistent kernel: range, scan,
            exchange, mean, next center on the device), evals/s and fraction of the HBM roofline.
-  e2e    : the same step through host buffers on every rank: one batch goes up from pinned host memory
-           (mc_load_histograms), the step's dependent scans run against it, summaries and marks come back to
-           the host, all inside the timed region (wall clock, max over ranks).  e2e.one_upload_per_10_scans is
+  e2e    : the same step through host buffers on every rank: everything the step's scans read (the R replicas,
+           larger than L2) goes up from pinned host memory first (mc_load_histograms), the dependent scans run,
+           summaries and marks come back to the host, all inside the timed region (wall clock, max over ranks).  e2e.one_upload_per_10_scans is
            the round-1 form (mc_scan_host: S scans per upload, chunked upload overlapped with the scans).
   --gpus N (torchrun, one process per GPU): weak scaling: every rank holds all N*n points and evaluates
            its n of every scan; the summaries cross GPUs through NVLink peer inboxes (CUDA IPC) on a second
@@ -113,6 +113,20 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        # NVML in-process (a sample every 5 ms, the first one at once); the nvidia-smi loop of the recipe as fall-back
+        # (its start-up alone is ~0.1 s: a 0.14 s timed region saw 1 to 13 samples)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.nvml = (pynvml, h)
+            self.samples, self.stop_flag = [], False
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -121,11 +135,44 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _nvml_index(self):
+        # NVML numbers the physical GPUs; CUDA_VISIBLE_DEVICES (indices) maps the local rank onto them
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
+
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if getattr(self, "nvml", None):
+            pynvml, _ = self.nvml
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            reasons = sorted(k for k, b in bits.items() if any(rs & b for _, _, rs in self.samples))
+            sm = [x[0] for x in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(x[1] for x in self.samples)) if sm else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml, 5 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -516,18 +563,28 @@ def main():
                      "step": f"{S} get_close scans of every rank's {n} points from pinned host memory (one upload per {S} scans)",
                      "call": "mc_scan_host on every rank (pinned host histograms -> chunked upload overlapped with S scans per chunk -> marks + summaries on the host); "
                              "max over ranks of the time per call"}
-        # ---- the bench's own step through host buffers: one batch goes up from pinned host memory (mc_load_histograms),
-        # the step's dependent scans run against it (the same enqueue calls as the headline), the summaries of the last
-        # call and the marks of a final mc_scan come back.  The product uploads a batch once per ~2000 scans (Phase A).
-        cr_calls = [np.ascontiguousarray(centers_local[(np.arange(S) + c * S) % centers_local.size], np.int64) for c in range(CALLS_PER_STEP)]
-        lo0, hi0 = np.zeros(S, np.int64), np.full(S, n - 1, np.int64)
+        # ---- the bench's own step through host buffers.  Exactly the scans of the headline -- the same dependent chain,
+        # rotating through the same R replicas so that every scan streams its rows from HBM -- but everything they read
+        # goes up from pinned host memory inside the timed region first (mc_load_histograms: R x n rows + lengths), and
+        # the summaries of the last call + the marks of a final mc_scan come back.  At N > 1 every rank does this
+        # with its own n points and the job's summaries are all-gathered, as above.
+        bigp = torch.empty((R * n, nbins), dtype=torch.uint8, pin_memory=True)
+        bigp.numpy()[:] = np.tile(hist, (R, 1))
+        biglp = torch.empty(R * n, dtype=torch.int64, pin_memory=True)
+        biglp.numpy()[:] = np.tile(lens.astype(np.int64), R)
+        bnp, blnp = bigp.numpy(), biglp.numpy().view(np.uint64)
+        chain_args = []
+        for c in range(CALLS_PER_STEP):
+            reps_ = [(c * S + s_) % R for s_ in range(S)]
+            chain_args.append((np.array([r_ * n + centers_local[(c * S + s_) % 64] for s_, r_ in enumerate(reps_)], np.int64),
+                               np.array([r_ * n for r_ in reps_], np.int64), np.array([r_ * n + n - 1 for r_ in reps_], np.int64)))
 
         def chain_step():
-            ctx2.load_histograms(hnp, lnp, K)
-            for c in range(CALLS_PER_STEP):
-                ctx2.scan_enqueue_many(cr_calls[c], lo0, hi0, api.MC_SCAN_CHAIN, 0)
+            ctx2.load_histograms(bnp, blnp, K)
+            for cr_, lo_, hi_ in chain_args:
+                ctx2.scan_enqueue_many(cr_, lo_, hi_, api.MC_SCAN_CHAIN, 0)
             res = ctx2.scan_collect(0, S)
-            last, mk = ctx2.scan(int(cr_calls[0][0]), 0, n - 1)
+            last, mk = ctx2.scan(int(chain_args[0][0][0]), 0, n - 1)
             return res + [last.as_tuple()], mk
 
         for _ in range(2):
@@ -552,13 +609,14 @@ def main():
         assert all(r[0] == n for r in res[:S]), "e2e chain: a scan did not evaluate every point"
         nscans = CALLS_PER_STEP * S + 1
         out["e2e"] = {"value": world * nscans * n / chain_s, "unit": UNIT,
-                      "h2d_bytes_per_step": int(world * (n * nbins + n * 8 + CALLS_PER_STEP * S * 24 + 24)),
+                      "h2d_bytes_per_step": int(world * (R * n * nbins + R * n * 8 + CALLS_PER_STEP * S * 24 + 24)),
                       "d2h_bytes_per_step": int(world * (n + (S + 1) * 160 * 32)), "ms_per_step": chain_s * 1e3,
-                      "step": f"one batch of {n} points per rank uploaded from pinned host memory, then the step's {nscans} dependent get_close scans "
-                              f"against it, summaries + marks read back (scans after the first find the {n * nbins / 1e6:.1f} MB batch in L2, as the "
-                              "product's Phase A does on this input)",
+                      "step": f"the headline's step with its input uploaded inside the timed region: {R} x {n} rows per rank ({R * n * nbins / 1e6:.0f} MB, "
+                              f"larger than L2) from pinned host memory, then the {nscans} dependent get_close scans rotating through them, "
+                              "summaries + marks read back",
                       "call": "mc_load_histograms + mc_scan_enqueue_many (MC_SCAN_CHAIN) x %d + mc_scan_collect + mc_scan, wall clock, max over ranks" % CALLS_PER_STEP,
                       "one_upload_per_10_scans": e2e_small}
+        del bigp, biglp
         if rank == 0:
             # parity spot-check of what was just timed (oracle as the checker only)
             import _oracle
