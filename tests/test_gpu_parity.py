@@ -148,6 +148,30 @@ def test_hist_vs_oracle_configs(ctx, oracle, cfg, n, k):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("k,width", [(7, 1), (7, 2), (1, 2), (2, 2)])
+def test_hist_extreme_k(ctx, oracle, k, width):
+    # the largest supported k (64 KB of counters per sequence: two warps per CTA) and the smallest, both bin widths;
+    # ragged lengths incl. sequences shorter than a 16-letter chunk, lower case, IUPAC and N runs (segments)
+    rng = np.random.default_rng(70 + k)
+    seqs = []
+    for i in range(60):
+        L = int(rng.integers(21, 40)) if i % 7 == 0 else int(rng.integers(200, 3000))
+        sq = rng.choice(np.frombuffer(b"ACGT", np.uint8), L)
+        if i % 5 == 1:
+            sq = sq | 0x20
+        if i % 5 == 2 and L > 100:
+            sq[30:55] = ord("N")
+            sq[L // 2] = ord("R")
+        seqs.append(sq.astype(np.uint8))
+    offs = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([s.size for s in seqs], out=offs[1:])
+    letters = np.concatenate(seqs)
+    rc, want, mx = oracle.hist_batch(letters, offs, k, width)
+    assert rc == 0
+    got, gmx = ctx.kmer_histograms_host(letters, offs, k, width)
+    assert gmx == mx and np.array_equal(got, want)
+
+
 def test_hist_u16_homopolymer(ctx, oracle):
     # long homopolymer runs push one bin past 255 -> 16-bit histograms (Runner.cpp:75-89)
     rng = np.random.default_rng(0)
