@@ -9,7 +9,10 @@
 #include <algorithm>
 #include <cstdint>
 #include <limits>
+#include <functional>
 #include <vector>
+
+#include "lazy_sort.hpp"
 
 namespace mch {
 
@@ -31,7 +34,7 @@ public:
 
 	// bvec::bvec (bvec.cpp:10-24): bounds are every bin_size-th sorted length
 	BVec(std::vector<uint64_t> lengths, uint64_t bin_size = 1000) {
-		std::sort(lengths.begin(), lengths.end());
+		parallel_std_sort(lengths, std::less<uint64_t>());   // (plain values: any correct sort gives this array)
 		for (uint64_t i = 0; i < lengths.size(); i += bin_size) bounds_.push_back(lengths[i]);
 		data_.resize(bounds_.size());
 	}
@@ -93,8 +96,12 @@ public:
 	// bvec::insert_finalize (bvec.cpp:209-218): per-bin std::sort by length (unstable: the same
 	// libstdc++ introsort on the same sequence and comparator gives the same permutation)
 	void finalize() {
-		for (auto &bin : data_)
+		// (bins are independent: the host threads share them)
+#pragma omp parallel for schedule(dynamic, 8)
+		for (long b = 0; b < (long)data_.size(); b++) {
+			auto &bin = data_[(size_t)b];
 			std::sort(bin.items.begin(), bin.items.end(), [](const Entry &a, const Entry &b) { return a.len < b.len; });
+		}
 	}
 
 	// after finalize(): rename the entries to their position in iteration order; returns id per row

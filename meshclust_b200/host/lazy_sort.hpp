@@ -136,4 +136,62 @@ private:
 	std::vector<Node> nodes_;
 };
 
+// ---- the whole array, with the host threads: std::sort's result (ties included), not just a sorted array --------
+// The same decomposition: after a range has been partitioned its two parts are independent, so they go to different
+// threads (OpenMP tasks above a size threshold); leaves get their insertion sort where they fall.  Used for the two
+// full sorts of Trainer::split, whose whole permutation is the input order of what follows.
+namespace detail {
+template <class Rec, class Less>
+void introsort_tasks(std::vector<Rec> &v, size_t first, size_t last, int depth, const Less &less) {
+	while (last - first > 16) {
+		if (depth == 0) {
+			std::partial_sort(v.begin() + (ptrdiff_t)first, v.begin() + (ptrdiff_t)last, v.begin() + (ptrdiff_t)last, less);
+			return;
+		}
+		--depth;
+		// std::__unguarded_partition_pivot
+		const size_t mid = first + (last - first) / 2, a = first + 1, c = last - 1;
+		if (less(v[a], v[mid])) {
+			if (less(v[mid], v[c])) std::swap(v[first], v[mid]);
+			else if (less(v[a], v[c])) std::swap(v[first], v[c]);
+			else std::swap(v[first], v[a]);
+		} else if (less(v[a], v[c])) std::swap(v[first], v[a]);
+		else if (less(v[mid], v[c])) std::swap(v[first], v[c]);
+		else std::swap(v[first], v[mid]);
+		size_t lo = first + 1, hi = last;
+		for (;;) {
+			while (less(v[lo], v[first])) ++lo;
+			--hi;
+			while (less(v[first], v[hi])) --hi;
+			if (!(lo < hi)) break;
+			std::swap(v[lo], v[hi]);
+			++lo;
+		}
+		const size_t cut = lo;
+		if (last - cut > 32768 && cut - first > 32768) {
+#pragma omp task default(none) shared(v, less) firstprivate(cut, last, depth)
+			introsort_tasks(v, cut, last, depth, less);
+		} else introsort_tasks(v, cut, last, depth, less);
+		last = cut;
+	}
+	for (size_t i = first + 1; i < last; i++) {   // the leaf's share of __final_insertion_sort
+		Rec val = v[i];
+		size_t j = i;
+		while (j > first && less(val, v[j - 1])) { v[j] = v[j - 1]; j--; }
+		v[j] = val;
+	}
+}
+}  // namespace detail
+
+template <class Rec, class Less>
+void parallel_std_sort(std::vector<Rec> &v, Less less) {
+	if (v.size() < 2) return;
+	int lg = 0;
+	for (size_t s = v.size(); s > 1; s >>= 1) lg++;
+	if (v.size() < 100000) { detail::introsort_tasks(v, 0, v.size(), 2 * lg, less); return; }
+#pragma omp parallel
+#pragma omp single nowait
+	detail::introsort_tasks(v, 0, v.size(), 2 * lg, less);
+}
+
 }  // namespace mch

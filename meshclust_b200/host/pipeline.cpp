@@ -197,7 +197,8 @@ std::vector<int> sort_ids_by_length(const std::vector<uint64_t> &len) {
 	struct LenId { uint64_t key; int id; };
 	std::vector<LenId> rec(len.size());
 	for (size_t i = 0; i < len.size(); i++) rec[i] = {len[i], (int)i};
-	std::sort(rec.begin(), rec.end(), [](const LenId &a, const LenId &b) { return a.key < b.key; });
+	// (std::sort's permutation, with the host threads: host/lazy_sort.hpp)
+	parallel_std_sort(rec, [](const LenId &a, const LenId &b) { return a.key < b.key; });
 	std::vector<int> ids(len.size());
 	for (size_t i = 0; i < len.size(); i++) ids[i] = rec[i].id;
 	return ids;
@@ -228,7 +229,7 @@ std::vector<Pair> trainer_split(Ctx &c) {
 		GPU(mc_distance_keys(c.gpu, &r, 1, key1.data()));
 		std::vector<KeyId> rec((size_t)n);
 		for (int64_t i = 0; i < n; i++) rec[i] = {key1[ds.row_of_id[points[i]]], points[i]};
-		std::sort(rec.begin(), rec.end(), [](const KeyId &a, const KeyId &b) { return a.key < b.key; });
+		parallel_std_sort(rec, [](const KeyId &a, const KeyId &b) { return a.key < b.key; });
 		for (int64_t i = 0; i < n; i++) points[i] = rec[i].id;
 	}
 	// :685-690 pivots at even ranks
@@ -713,38 +714,66 @@ void write_clstr(const Ctx &c, const std::vector<Cluster> &part) {
 	printf("Printing output\n");
 	FILE *f = fopen(c.opt.output.c_str(), "w");
 	if (!f) { fprintf(stderr, "cannot open %s\n", c.opt.output.c_str()); exit(1); }
-	// one big buffer, decimal conversion by hand: a million fprintf calls are a visible slice of a run
-	std::string buf;
-	buf.reserve(1 << 22);
-	char num[32];
-	auto put_u = [&](unsigned long long v) {
-		int k = 0;
-		do { num[k++] = (char)('0' + v % 10); v /= 10; } while (v);
-		while (k) buf.push_back(num[--k]);
-	};
-	int counter = 0;
-	for (const Cluster &cl : part) {
-		if (cl.rows.empty()) continue;
-		buf += ">Cluster ";
-		put_u((unsigned long long)counter);
-		buf.push_back('\n');
-		unsigned long long pt = 0;
-		for (int64_t r : cl.rows) {
-			const int64_t id = c.ds.id_of_row[r];
-			put_u(pt);
-			buf.push_back('\t');
-			put_u((unsigned long long)c.ds.len[id]);
-			buf += "nt, ";
-			buf += c.ds.fa.headers[id];
-			buf += "... ";
-			if (r == cl.center_row) buf.push_back('*');
+	// decimal conversion by hand into big buffers (a million fprintf calls are a visible slice of a run), formatted by
+	// all host threads: the non-empty clusters are numbered first, then cut into runs of about equal member counts,
+	// one buffer per run, written in order.  Rounds of at most ~4 M members bound the memory.
+	std::vector<size_t> live;
+	for (size_t i = 0; i < part.size(); i++) if (!part[i].rows.empty()) live.push_back(i);
+	int threads = 1;
+#ifdef _OPENMP
+	threads = omp_get_max_threads();
+#endif
+	auto format = [&](size_t first, size_t last, std::string &buf) {   // clusters live[first, last)
+		char num[32];
+		auto put_u = [&](unsigned long long v) {
+			int k = 0;
+			do { num[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+			while (k) buf.push_back(num[--k]);
+		};
+		for (size_t ci = first; ci < last; ci++) {
+			const Cluster &cl = part[live[ci]];
+			buf += ">Cluster ";
+			put_u((unsigned long long)ci);
 			buf.push_back('\n');
-			pt++;
-			if (buf.size() > (1 << 22) - 4096) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
+			unsigned long long pt = 0;
+			for (int64_t r : cl.rows) {
+				const int64_t id = c.ds.id_of_row[r];
+				put_u(pt);
+				buf.push_back('\t');
+				put_u((unsigned long long)c.ds.len[id]);
+				buf += "nt, ";
+				buf += c.ds.fa.headers[id];
+				buf += "... ";
+				if (r == cl.center_row) buf.push_back('*');
+				buf.push_back('\n');
+				pt++;
+			}
 		}
-		counter++;
+	};
+	size_t done = 0;
+	while (done < live.size()) {
+		// this round: clusters [done, end) with at most ~4 M members in total
+		size_t end = done, members = 0;
+		while (end < live.size() && (end == done || members + part[live[end]].rows.size() <= ((size_t)4 << 20))) members += part[live[end++]].rows.size();
+		std::vector<size_t> cut((size_t)threads + 1, end);
+		cut[0] = done;
+		{
+			size_t acc = 0, t = 1;
+			for (size_t ci = done; ci < end && t < (size_t)threads; ci++) {
+				acc += part[live[ci]].rows.size();
+				while (t < (size_t)threads && acc >= members * t / (size_t)threads) cut[t++] = ci + 1;
+			}
+		}
+		std::vector<std::string> bufs((size_t)threads);
+#pragma omp parallel for schedule(static, 1)
+		for (int t = 0; t < threads; t++) {
+			if (cut[(size_t)t + 1] <= cut[(size_t)t]) continue;
+			bufs[(size_t)t].reserve((members / (size_t)threads + 1024) * 48);
+			format(cut[(size_t)t], cut[(size_t)t + 1], bufs[(size_t)t]);
+		}
+		for (const std::string &bf : bufs) if (!bf.empty()) fwrite(bf.data(), 1, bf.size(), f);
+		done = end;
 	}
-	fwrite(buf.data(), 1, buf.size(), f);
 	fclose(f);
 }
 

@@ -27,6 +27,6 @@ def test_lazy_sort_selfcheck(tmp_path):
     # Trainer::split's ~150 sorts of all points run lazily (host/lazy_sort.hpp): every position resolved must hold the
     # element libstdc++'s std::sort puts there -- ties included -- also through introsort's heapsort branch
     exe = os.path.join(str(tmp_path), "lazy_sort_selfcheck")
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "units", "lazy_sort_selfcheck.cpp"), "-o", exe])
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", os.path.join(ROOT, "tests", "units", "lazy_sort_selfcheck.cpp"), "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr

@@ -32,6 +32,14 @@ int main() {
 			std::__introsort_loop(want.begin(), want.end(), (long)depth, __gnu_cxx::__ops::__iter_comp_iter(ByKey()));
 			std::__final_insertion_sort(want.begin(), want.end(), __gnu_cxx::__ops::__iter_comp_iter(ByKey()));
 		}
+		if (depth < 0) {
+			// the task-parallel full sort: the same array as std::sort, element by element
+			std::vector<KeyId> par = v;
+			mch::parallel_std_sort(par, ByKey());
+			for (size_t p = 0; p < n; p++)
+				if (par[p].key != want[p].key || par[p].id != want[p].id) { printf("round %d (n=%zu kind=%d): parallel_std_sort differs at %zu\n", round, n, kind, p); return 1; }
+			checks += (long)n;
+		}
 		mch::LazySort<KeyId, ByKey> lazy(std::vector<KeyId>(v), ByKey(), depth);
 		// a few positions in the order a binary search would ask for them, then strided ones, then all
 		std::vector<size_t> ask;
@@ -71,7 +79,15 @@ int main() {
 		for (int t = 0; t < 10; t++) { const size_t p = pos + (size_t)((double)(n - pos) * t / 10); bad += lazy.at(p).id != w[p].id; }
 		const double t2 = now();
 		if (bad) { printf("1 M records: %ld positions differ\n", bad); return 1; }
-		printf("ok %ld checks; 1 M records: std::sort %.3f s, 40 positions lazily %.3f s\n", checks, t1 - t0, t2 - t1);
+		std::vector<KeyId> par(n);
+		for (size_t i = 0; i < n; i++) par[i] = {(uint16_t)((i * 2654435761u) % 10001), (int)i};
+		std::vector<KeyId> ref = par;
+		std::sort(ref.begin(), ref.end(), ByKey());
+		const double t3 = now();
+		mch::parallel_std_sort(par, ByKey());
+		const double t4 = now();
+		for (size_t i = 0; i < n; i++) if (par[i].id != ref[i].id) { printf("1 M records: parallel_std_sort differs at %zu\n", i); return 1; }
+		printf("ok %ld checks; 1 M records: std::sort %.3f s, 40 positions lazily %.3f s, parallel full sort %.3f s\n", checks, t1 - t0, t2 - t1, t4 - t3);
 	}
 	return 0;
 }
