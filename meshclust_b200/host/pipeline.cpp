@@ -1254,44 +1254,72 @@ int run_pipeline(Options opt) {
 			if (mc_ingest_fasta(c.gpu, fidx.raw.data(), (int64_t)fidx.raw.size(), sb.data(), se.data(), offs.data(), ds.n, rflags.data()) != MC_OK) die_gpu("mc_ingest_fasta");
 			// segments (Chromosome.cpp:162-258): a record without N is one run -- kept from 20 letters on, cut at 1 Mbp --
 			// and needs no look at its letters; the others are rebuilt from their lines and go through mc_host_segments
-			std::vector<int32_t> segs;
+			// (two passes over the rows, shared by the host threads: count, prefix sum, fill)
 			bool validate = false;
-			std::vector<uint8_t> tmp;
-			std::vector<int32_t> sbuf;
-			for (int64_t r = 0; r < ds.n; r++) {
-				const int64_t len = offs[r + 1] - offs[r];
-				if (rflags[r] & 2) validate = true;
-				int ns;
-				if (!(rflags[r] & 1)) {
-					if (len <= 1) no_sequence(r);   // (mc_host_segments: an empty or one-letter record never closes a run)
-					ns = 0;
-					if (len >= 20) {
-						if (len > 1000000) {
-							const int64_t frag = len / 1000000;
-							for (int64_t h = 0; h < frag; h++) {
-								const int64_t fs = h * 1000000, fe = (h == frag - 1) ? len - 1 : fs + 1000000 - 1;
-								segs.push_back((int32_t)fs); segs.push_back((int32_t)fe);
-								ns++;
-							}
-						} else {
-							segs.push_back(0); segs.push_back((int32_t)(len - 1));
-							ns = 1;
-						}
-					}
-				} else {
-					tmp.resize((size_t)len);
-					size_t w = 0;
-					for (int64_t p = sb[r]; p < se[r]; p++) {
-						const uint8_t ch = fidx.raw.data()[p];
-						if (ch != '\n') tmp[w++] = ch;
-					}
-					ns = mc_host_segments(tmp.data(), len, nullptr, 0);
-					if (ns < 0) no_sequence(r);
-					sbuf.resize((size_t)ns * 2);
-					mc_host_segments(tmp.data(), len, sbuf.data(), ns);
-					segs.insert(segs.end(), sbuf.begin(), sbuf.end());
+			int64_t bad_row = -1;
+			std::vector<int32_t> nseg((size_t)ds.n, 0);
+			auto whole_run = [](int64_t len, int32_t *out) -> int {   // segments of a record without N; out may be null (count only)
+				if (len < 20) return 0;
+				if (len <= 1000000) {
+					if (out) { out[0] = 0; out[1] = (int32_t)(len - 1); }
+					return 1;
 				}
-				seg_off[r + 1] = seg_off[r] + ns;
+				const int64_t frag = len / 1000000;
+				for (int64_t h = 0; h < frag; h++) {
+					const int64_t fs = h * 1000000, fe = (h == frag - 1) ? len - 1 : fs + 1000000 - 1;
+					if (out) { out[2 * h] = (int32_t)fs; out[2 * h + 1] = (int32_t)fe; }
+				}
+				return (int)frag;
+			};
+			auto letters_of = [&](int64_t r, std::vector<uint8_t> &tmp) {
+				const int64_t len = offs[r + 1] - offs[r];
+				tmp.resize((size_t)len);
+				size_t w = 0;
+				const uint8_t *rawp = fidx.raw.data();
+				for (int64_t p = sb[r]; p < se[r]; p++)
+					if (rawp[p] != '\n') tmp[w++] = rawp[p];
+			};
+#pragma omp parallel
+			{
+				std::vector<uint8_t> tmp;
+				bool val_local = false;
+				int64_t bad_local = -1;
+#pragma omp for schedule(dynamic, 4096)
+				for (int64_t r = 0; r < ds.n; r++) {
+					const int64_t len = offs[r + 1] - offs[r];
+					if (rflags[r] & 2) val_local = true;
+					int ns;
+					if (!(rflags[r] & 1)) ns = len <= 1 ? -1 : whole_run(len, nullptr);   // (mc_host_segments: an empty or one-letter record never closes a run)
+					else {
+						letters_of(r, tmp);
+						ns = mc_host_segments(tmp.data(), len, nullptr, 0);
+					}
+					if (ns < 0) { if (bad_local < 0 || r < bad_local) bad_local = r; ns = 0; }
+					nseg[(size_t)r] = ns;
+				}
+#pragma omp critical
+				{
+					if (val_local) validate = true;
+					if (bad_local >= 0 && (bad_row < 0 || bad_local < bad_row)) bad_row = bad_local;
+				}
+			}
+			if (bad_row >= 0) no_sequence(bad_row);
+			for (int64_t r = 0; r < ds.n; r++) seg_off[r + 1] = seg_off[r] + nseg[(size_t)r];
+			std::vector<int32_t> segs((size_t)seg_off[ds.n] * 2);
+#pragma omp parallel
+			{
+				std::vector<uint8_t> tmp;
+#pragma omp for schedule(dynamic, 4096)
+				for (int64_t r = 0; r < ds.n; r++) {
+					if (nseg[(size_t)r] == 0) continue;
+					int32_t *dst = segs.data() + 2 * seg_off[r];
+					const int64_t len = offs[r + 1] - offs[r];
+					if (!(rflags[r] & 1)) whole_run(len, dst);
+					else {
+						letters_of(r, tmp);
+						mc_host_segments(tmp.data(), len, dst, nseg[(size_t)r]);
+					}
+				}
 			}
 			if (mc_load_segments(c.gpu, segs.data(), seg_off.data(), validate ? 1 : 0) != MC_OK) {
 				fprintf(stderr, "meshclust: %s\n", mc_last_error());

@@ -88,6 +88,34 @@ def test_clstr_identical_with_host_parser_cpu(mock_cli, tmp_path, name):
     assert got2 == got
 
 
+def test_ingest_path_edge_records_cpu(mock_cli, tmp_path):
+    # records the two input paths (index + mc_ingest_fasta / host parser + mc_load_sequences) must treat alike: all N and
+    # one-letter records abort like the reference's segment->at(0) (Chromosome.cpp:193), records under 20 letters have
+    # no segment but stay, an invalid letter is the InvalidInputException exit, N runs give several segments
+    import random
+    rnd = random.Random(3)
+    base = ["".join(rnd.choice("ACGT") for _ in range(300)) for _ in range(40)]
+    cases = {
+        "allN": (base[:20] + ["N" * 50] + base[20:], False, "no usable sequence"),
+        "one": (base[:5] + ["A"] + base[5:], False, "no usable sequence"),
+        "short": (base[:5] + ["ACGTACGTAC"] + base[5:], True, ""),
+        "bad": (base[:7] + [base[7][:100] + "!" + base[7][100:]] + base[8:], False, "Invalid nucleotide"),
+        "Nrun": (base[:3] + [base[3][:100] + "N" * 30 + base[3][100:] + "nnnn"] + base[4:], True, ""),
+    }
+    for name, (recs, ok, msg) in cases.items():
+        fa = os.path.join(str(tmp_path), name + ".fa")
+        with open(fa, "w") as f:
+            for i, sq in enumerate(recs):
+                f.write(f">r{i} d\n" + "\n".join(sq[j:j + 60] for j in range(0, len(sq), 60)) + "\n")
+        outs = []
+        for env in ({}, {"MC_HOST_PARSE": "1"}):
+            out = os.path.join(str(tmp_path), name + ".clstr")
+            r = subprocess.run([mock_cli, fa, "--id", "0.9", "--kmer", "3", "--output", out], capture_output=True, text=True, env={**os.environ, **env})
+            assert (r.returncode == 0) == ok and msg in r.stderr, (name, env, r.returncode, r.stderr[-300:])
+            outs.append(open(out).read() if ok else r.stderr.strip().splitlines()[-1])
+        assert outs[0] == outs[1], name
+
+
 def test_cli_errors(mock_cli, tmp_path):
     # Runner.cpp:150-263: bad values and missing files exit non-zero with the reference's messages
     r = subprocess.run([mock_cli], capture_output=True, text=True)
