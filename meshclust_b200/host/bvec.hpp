@@ -79,9 +79,12 @@ public:
 		index_of(len, &front, &back);
 		// least-filled candidate bin, the middle one among equals (the reference collects the minima in
 		// a vector and takes mins[mins.size() / 2]); two passes instead of a vector per insert
-		size_t minimum = std::numeric_limits<size_t>::max(), nmin = 0;
+		// (the fill counts in one flat array: equal lengths make the candidate range tens of bins wide)
+		if (fill_.size() != data_.size()) { fill_.resize(data_.size()); for (size_t i = 0; i < data_.size(); i++) fill_[i] = (uint32_t)data_[i].items.size(); }
+		uint32_t minimum = std::numeric_limits<uint32_t>::max();
+		size_t nmin = 0;
 		for (size_t i = front; i <= back; i++) {
-			const size_t sz = data_[i].items.size();
+			const uint32_t sz = fill_[i];
 			if (sz < minimum) { minimum = sz; nmin = 1; }
 			else if (sz == minimum) nmin++;
 		}
@@ -89,8 +92,9 @@ public:
 		// vector (undefined); it cannot happen for bounds taken from the same lengths
 		size_t pick = data_.size(), seen = 0;
 		for (size_t i = front; i <= back; i++)
-			if (data_[i].items.size() == minimum && seen++ == nmin / 2) { pick = i; break; }
+			if (fill_[i] == minimum && seen++ == nmin / 2) { pick = i; break; }
 		data_.at(pick).items.push_back({id, len});
+		fill_[pick]++;
 	}
 
 	// bvec::insert_finalize (bvec.cpp:209-218): per-bin std::sort by length (unstable: the same
@@ -261,6 +265,7 @@ public:
 	}
 
 private:
+	std::vector<uint32_t> fill_;   // items per bin while the container is being filled (insert)
 	struct Bin {
 		std::vector<Entry> items;     // fixed after finalize(); items[j].v = row0 + j
 		std::vector<uint64_t> bits;   // alive bitmap over items

@@ -219,17 +219,26 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	struct KeyId { uint16_t key; int id; };
 	// :672-675 unstable sort by length, then the median-length point (sorted on a helper thread while
 	// the sequences were uploaded and counted: it needs nothing but the lengths)
+	const bool dbg_t = getenv("MC_DEBUG_TIMING") != nullptr;
+	Timer tsub;
+	auto sub = [&](const char *what) { if (dbg_t) fprintf(stderr, "  [split: %-32s %.3f s]\n", what, tsub.lap()); };
 	if (c.by_length.valid()) points = c.by_length.get();
 	else points = sort_ids_by_length(ds.len);
+	sub("ids by length (wait)");
 	const int begin_pt = points[points.size() / 2];
 	// :681-684 sort by distance to it
 	{
 		std::vector<uint16_t> key1((size_t)n);
 		int32_t r = (int32_t)ds.row_of_id[begin_pt];
 		GPU(mc_distance_keys(c.gpu, &r, 1, key1.data()));
+		sub("keys of the median point");
 		std::vector<KeyId> rec((size_t)n);
+#pragma omp parallel for schedule(static)
 		for (int64_t i = 0; i < n; i++) rec[i] = {key1[ds.row_of_id[points[i]]], points[i]};
+		sub("records");
 		parallel_std_sort(rec, [](const KeyId &a, const KeyId &b) { return a.key < b.key; });
+		sub("sort by distance");
+#pragma omp parallel for schedule(static)
 		for (int64_t i = 0; i < n; i++) points[i] = rec[i].id;
 	}
 	// :685-690 pivots at even ranks
@@ -247,9 +256,12 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	// sort comparators, 2 per comparison)
 	std::vector<int32_t> prow(np);
 	for (size_t i = 0; i < np; i++) prow[i] = (int32_t)ds.row_of_id[pivots[i]];
-	std::vector<uint16_t> keys(np * (size_t)n);
+	// (not a std::vector: value-initialising 300 MB of keys that the copy overwrites was 0.1 s of "first sorts" at C4)
+	RawBytes keys_raw;
+	keys_raw.resize(np * (size_t)n * sizeof(uint16_t));
+	uint16_t *keys = reinterpret_cast<uint16_t *>(keys_raw.data());
 	const double t_first = st.lap();
-	GPU(mc_distance_keys(c.gpu, prow.data(), (int)np, keys.data()));
+	GPU(mc_distance_keys(c.gpu, prow.data(), (int)np, keys));
 	const double t_keys = st.lap();
 
 	// :694-701 per pivot: copy + unstable sort by distance to the pivot.  Independent per pivot, so
@@ -264,15 +276,14 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	const bool full_sort = getenv("MC_SPLIT_FULL_SORT") != nullptr;
 #pragma omp parallel for schedule(dynamic)
 	for (long i = 0; i < (long)np; i++) {
-		const uint16_t *kk = keys.data() + (size_t)i * n;
+		const uint16_t *kk = keys + (size_t)i * n;
 		std::vector<KeyId> rec((size_t)n);
 		for (int64_t j = 0; j < n; j++) rec[j] = {kk[row_of_point[j]], points[j]};
 		if (full_sort) std::sort(rec.begin(), rec.end(), ByKey());
 		sorted[(size_t)i] = LazySort<KeyId, ByKey>(std::move(rec), ByKey(), full_sort ? 0 : -1);
 		if (full_sort) sorted[(size_t)i].mark_sorted();
 	}
-	keys.clear();
-	keys.shrink_to_fit();
+	keys_raw.release();
 	double t_sorts = st.lap();
 	int rounds = 0;
 	// positions of sorted[i] resolved by the host threads, pivot by pivot, before the serial code reads them
