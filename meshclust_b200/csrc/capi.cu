@@ -1012,11 +1012,16 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 	const long long compact_min = getenv("MC_PA_COMPACT_MIN") ? std::max(64LL, atoll(getenv("MC_PA_COMPACT_MIN"))) : 4096;
 	bool compact = n >= 2 * compact_min && !getenv("MC_PA_NO_COMPACT");
 	int rc = MC_OK;
+	const bool dbg = getenv("MC_DEBUG_TIMING") != nullptr;
+	auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+	double t_prev = now();
+	auto lap = [&](const char *what) { if (dbg) { const double t = now(); fprintf(stderr, "[mc_accumulate_run] %-28s %.3f s\n", what, t - t_prev); t_prev = t; } };
 	if (compact && mc_ensure_scratch(ctx, total_of(need_st)) != MC_OK) { compact = false; cudaGetLastError(); }
 	if (!compact) {
 		rc = mc_ensure_scratch(ctx, total_of(need_base));
 		if (rc) return rc;
 	}
+	lap("scratch");
 	Carve cv(ctx->d_scratch);
 	unsigned long long *d_bounds = cv.take<unsigned long long>((size_t)nb);
 	int *d_row0 = cv.take<int>((size_t)nb + 1);
@@ -1062,6 +1067,7 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 	MC_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
 	MC_REQUIRE(h_err == 0, MC_ERR_ARG, "mc_accumulate_run: the rows of a bvec bin are not in non-decreasing length order");
+	lap("uploads + search records");
 	rc = mc_launch_phase_a(ctx, d_bounds, d_row0, nb, d_range, d_bits, d_gsum, d_exch, d_bar, d_members, d_center, d_off,
 	                       d_stats, trace_steps ? d_trace : nullptr, trace_steps, grid, qmax, d_mcur, similarity, compact ? staging : nullptr, cap, compact_min, compact_shift);
 	if (rc) return rc;
@@ -1070,6 +1076,7 @@ extern "C" int mc_accumulate_run(mc_ctx *ctx, double similarity, const uint64_t 
 	MC_CUDA(cudaMemcpyAsync(h_stats, d_stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(h_bar, d_bar, 16, cudaMemcpyDeviceToHost, ctx->stream));
 	MC_CUDA(cudaStreamSynchronize(ctx->stream));
+	lap("kernel");
 	MC_REQUIRE(h_bar[1] == 0, MC_ERR_CUDA, "mc_accumulate_run: a grid-wide barrier timed out (code %llu)", h_bar[1]);
 	const int64_t nc = h_stats[0];
 	MC_REQUIRE(nc >= 0 && nc <= n, MC_ERR_CUDA, "mc_accumulate_run: the kernel reported %lld clusters", (long long)nc);
