@@ -74,6 +74,9 @@ int mc_load_sequences(mc_ctx *ctx, const uint8_t *letters, const int64_t *offset
  * (validate).  Must be followed by mc_load_segments.  MC_ERR_INPUT when spans and letter counts disagree. */
 int mc_ingest_fasta(mc_ctx *ctx, const uint8_t *raw, int64_t raw_bytes, const int64_t *span_begin, const int64_t *span_end,
                     const int64_t *offsets, int64_t n, uint8_t *rec_flags_out);
+/* Optional hint: make the context's scratch buffer at least `bytes` large now, so that later stages (ingest, distance
+ * keys, alignments, mc_accumulate_run with its staging copies) do not have to replace it in the middle of a run. */
+int mc_reserve_scratch(mc_ctx *ctx, int64_t bytes);
 /* Optional: send the raw bytes ahead (blocking; meant for a helper thread) while the caller still derives the row
  * order and the spans.  An mc_ingest_fasta with the same raw / raw_bytes and at most n_records records that follows
  * without another call on ctx in between does not upload them again. */

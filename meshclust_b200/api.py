@@ -28,7 +28,7 @@ MC_ERR_CUDA, MC_ERR_ARG, MC_ERR_STATE, MC_ERR_INPUT, MC_ERR_UNSUPPORTED = -1, -2
 # every symbol include/meshclust_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "mc_version", "mc_last_error", "mc_device_count", "mc_ctx_create", "mc_ctx_destroy", "mc_stream",
-    "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_ingest_fasta", "mc_stage_fasta_bytes", "mc_load_segments", "mc_copy_letters", "mc_copy_digits",
+    "mc_sync", "mc_launch_count", "mc_host_segments", "mc_load_sequences", "mc_ingest_fasta", "mc_stage_fasta_bytes", "mc_reserve_scratch", "mc_load_segments", "mc_copy_letters", "mc_copy_digits",
     "mc_build_histograms", "mc_load_histograms", "mc_copy_histograms", "mc_copy_point_stats",
     "mc_set_model", "mc_distance_keys", "mc_pair_features", "mc_pair_classify", "mc_alive_reset",
     "mc_alive_kill", "mc_scan", "mc_scan_enqueue", "mc_scan_collect", "mc_scan_enqueue_many", "mc_scan_fold_dev", "mc_set_stream", "mc_mean_nearest", "mc_accumulate_step", "mc_accumulate_run", "mc_near_threshold_count", "mc_permute_rows", "mc_reserve_permute", "mc_comm_init", "mc_comm_connect", "mc_comm_connect_local",

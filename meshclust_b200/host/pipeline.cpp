@@ -260,6 +260,14 @@ std::vector<Pair> trainer_split(Ctx &c) {
 	RawBytes keys_raw;
 	keys_raw.resize(np * (size_t)n * sizeof(uint16_t));
 	uint16_t *keys = reinterpret_cast<uint16_t *>(keys_raw.data());
+	{
+		// first touch by all threads: the device-to-host copy into never-touched pages faults them in one by one
+		// (0.13 s for the 300 MB of C4), and so did the value-initialisation
+		uint8_t *kb = keys_raw.data();
+		const size_t bytes = keys_raw.size();
+#pragma omp parallel for schedule(static)
+		for (long long off = 0; off < (long long)bytes; off += 4096) kb[off] = 0;
+	}
 	const double t_first = st.lap();
 	GPU(mc_distance_keys(c.gpu, prow.data(), (int)np, keys));
 	const double t_keys = st.lap();
@@ -1173,6 +1181,13 @@ int run_pipeline(Options opt) {
 			ctx_ready.wait();
 			if (ctx_rc != MC_OK) return;
 			Timer t;
+			// one scratch allocation for the whole run where its size can be foreseen: Phase A's working set with the
+			// staging copies of the row compactions is ~1.7 x the histograms (8-bit bins assumed), the ingest needs the
+			// file bytes
+			if (opt.k >= 1 && opt.k <= 6 && !opt.align) {
+				const double rows_bytes = (double)nrec * ((double)(1ll << (2 * opt.k)) + 128.0);
+				mc_reserve_scratch(c.gpu, (int64_t)std::max(1.75 * rows_bytes + 64e6, (double)fidx.raw.size() + 32.0 * (double)nrec + 1e6));
+			}
 			stage_rc = mc_stage_fasta_bytes(c.gpu, fidx.raw.data(), (int64_t)fidx.raw.size(), nrec);
 			stage_s = t.lap();
 		});

@@ -76,6 +76,7 @@ int mc_load_sequences(mc_ctx *c, const uint8_t *letters, const int64_t *offsets,
 	return MC_OK;
 }
 int mc_stage_fasta_bytes(mc_ctx *, const uint8_t *, int64_t, int64_t) { return MC_OK; }
+int mc_reserve_scratch(mc_ctx *, int64_t) { return MC_OK; }
 int mc_ingest_fasta(mc_ctx *c, const uint8_t *raw, int64_t raw_bytes, const int64_t *span_begin, const int64_t *span_end, const int64_t *offsets,
                     int64_t n, uint8_t *rec_flags_out) {
 	(void)raw_bytes;
