@@ -81,18 +81,32 @@ public:
 		// a vector and takes mins[mins.size() / 2]); two passes instead of a vector per insert
 		// (the fill counts in one flat array: equal lengths make the candidate range tens of bins wide)
 		if (fill_.size() != data_.size()) { fill_.resize(data_.size()); for (size_t i = 0; i < data_.size(); i++) fill_[i] = (uint32_t)data_[i].items.size(); }
+		// three passes without a branch on the data (minimum, how many, where the middle one is): the single pass with
+		// its `if (smaller) ... else if (equal)` mispredicts on every few bins
+		const uint32_t *fl = fill_.data();
 		uint32_t minimum = std::numeric_limits<uint32_t>::max();
-		size_t nmin = 0;
-		for (size_t i = front; i <= back; i++) {
-			const uint32_t sz = fill_[i];
-			if (sz < minimum) { minimum = sz; nmin = 1; }
-			else if (sz == minimum) nmin++;
-		}
+#pragma omp simd reduction(min : minimum)
+		for (size_t i = front; i <= back; i++) minimum = fl[i] < minimum ? fl[i] : minimum;
+		uint32_t nmin = 0;
+#pragma omp simd reduction(+ : nmin)
+		for (size_t i = front; i <= back; i++) nmin += fl[i] == minimum ? 1u : 0u;
 		// front > back leaves no candidate: the reference prints an error and then indexes an empty
 		// vector (undefined); it cannot happen for bounds taken from the same lengths
 		size_t pick = data_.size(), seen = 0;
-		for (size_t i = front; i <= back; i++)
-			if (fill_[i] == minimum && seen++ == nmin / 2) { pick = i; break; }
+		const size_t want = (size_t)nmin / 2;
+		size_t i = front;
+		for (; i + 16 <= back + 1; i += 16) {   // whole blocks of 16 bins that end before the wanted one
+			uint32_t c = 0;
+#pragma omp simd reduction(+ : c)
+			for (size_t j = 0; j < 16; j++) c += fl[i + j] == minimum ? 1u : 0u;
+			if (seen + c > want) break;
+			seen += c;
+		}
+		for (; i <= back; i++) {
+			const bool is_min = fl[i] == minimum;
+			if (is_min && seen == want) { pick = i; break; }
+			seen += is_min;
+		}
 		data_.at(pick).items.push_back({id, len});
 		fill_[pick]++;
 	}

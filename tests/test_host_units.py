@@ -8,10 +8,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_bvec_selfcheck(tmp_path):
     # binary-search index_of == the reference's literal loop (bvec.cpp:123-149); bitmap-backed bins ==
     # an erase-based model: pop order, sizes, and "a bvec range is a contiguous alive row range"
-    exe = os.path.join(str(tmp_path), "bvec_selfcheck")
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "units", "bvec_selfcheck.cpp"), "-o", exe])
-    r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+    # (also: insert + finalize against the literal rule of bvec.cpp:152-177, 209-218; built with and without OpenMP:
+    # the bin choice uses `omp simd` reductions, the sorts OpenMP tasks)
+    for flags in ([], ["-fopenmp"]):
+        exe = os.path.join(str(tmp_path), "bvec_selfcheck" + ("_omp" if flags else ""))
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", *flags, os.path.join(ROOT, "tests", "units", "bvec_selfcheck.cpp"), "-o", exe])
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
 
 
 def test_fasta_parallel_parser_selfcheck(tmp_path):

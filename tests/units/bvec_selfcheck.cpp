@@ -25,6 +25,27 @@ int main() {
 		for (int i = 0; i < n; i++) bv.insert(i, len[i]);
 		bv.finalize();
 		std::vector<int64_t> id_of_row = bv.assign_rows();
+		{
+			// bvec::insert (bvec.cpp:152-177) literally: the minima of the candidate bins collected in a vector, the
+			// middle one taken; then insert_finalize's per-bin std::sort -- the container must hold the same rows
+			std::vector<std::vector<mch::BVec::Entry>> bins(bv.nbins());
+			for (int i = 0; i < n; i++) {
+				size_t f, b;
+				bv.index_of_linear(len[i], &f, &b);
+				size_t minimum = (size_t)-1;
+				for (size_t j = f; j <= b; j++) minimum = std::min(minimum, bins[j].size());
+				std::vector<size_t> mins;
+				for (size_t j = f; j <= b; j++) if (bins[j].size() == minimum) mins.push_back(j);
+				bins[mins[mins.size() / 2]].push_back({(int64_t)i, len[i]});
+			}
+			std::vector<int64_t> want;
+			for (auto &bin : bins) {
+				std::sort(bin.begin(), bin.end(), [](const mch::BVec::Entry &a, const mch::BVec::Entry &b) { return a.len < b.len; });
+				for (auto &e : bin) want.push_back(e.v);
+			}
+			if (want != id_of_row) { printf("insert / finalize differ from the literal rule in round %d\n", round); return 1; }
+			checks++;
+		}
 		// model: rows alive in order, with their lengths
 		std::vector<char> alive(n, 1);
 		size_t live = n;
