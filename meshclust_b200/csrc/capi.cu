@@ -26,7 +26,7 @@ size_t mc_acc_dev_bytes();
 int mc_launch_accumulate_tail(mc_ctx *ctx, int64_t center_row, int64_t lo, int64_t hi, int restart, const void *partials_dev, int nparts, void *acc_dev, void *out_host_dev, int32_t *list_host_dev, unsigned long long seq, const unsigned int *err_dev);
 int mc_launch_permute_rows(mc_ctx *ctx, const int32_t *old_of_new_dev, int64_t count, int64_t n_alive, void *hist_out, void *aux_out);
 int mc_launch_update_centers(mc_ctx *ctx, const int64_t *center_rows_dev, int64_t ncenters, const int64_t *cand_rows_dev, const int64_t *cand_begin_dev, const int64_t *cand_end_dev, const int64_t *flag_off_dev, uint8_t *flags_dev, long long *next_rows_dev);
-int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len, int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b, int64_t scratch_stride, int64_t nwarps, int rows_per_lane);
+int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len, int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b, int64_t scratch_stride, int64_t nwarps, int rows_per_lane, int team_warps);
 int mc_nw_pick_rows(const int64_t *lb, int64_t m);
 
 // ---------------------------------------------------------------------------------------------
@@ -1418,21 +1418,35 @@ extern "C" int mc_align_pairs(mc_ctx *ctx, const int32_t *a, const int32_t *b, i
 	static const int force_rows = getenv("MC_NW_ROWS") ? atoi(getenv("MC_NW_ROWS")) : 0;
 	const int rows_per_lane = force_rows ? force_rows : mc_nw_pick_rows(lbs.data(), m);
 	const int64_t stride = align_up((size_t)max_la + 2, 32);
-	int64_t nwarps = std::min<int64_t>(m, (int64_t)ctx->num_sms * 32);
+	// A batch too small to fill the GPU with one warp per pair, of pairs long enough to be cut into many strips, is
+	// run by teams of four warps per pair (nw_identity.cu): the batch then takes a quarter of one pair's latency
+	// instead of all of it.  MC_NW_TEAMS=1 / 4 / 6 / 0 forces teams (of 4 / 6 warps) / forbids them (tests run every batch both ways).
+	int64_t sum_lb = 0;
+	for (int64_t i = 0; i < m; i++) sum_lb += lbs[(size_t)i];
+	const int force_teams = getenv("MC_NW_TEAMS") ? atoi(getenv("MC_NW_TEAMS")) : -1;   // (read per call: tests switch it)
+	// (16 rows per lane, 168 registers: three CTAs of four warps or two of six per SM)
+	const int64_t teams4 = (int64_t)ctx->num_sms * 3, teams6 = (int64_t)ctx->num_sms * 2;
+	bool teams = force_teams >= 1 || (force_teams != 0 && m <= teams4 && sum_lb >= m * 8 * 512);
+	if (max_la >= (1 << 24) || (force_rows && force_rows != 16)) teams = false;
+	const int team_warps = !teams ? 1 : (force_teams == 4 || force_teams == 6 ? force_teams : (m <= teams6 ? 6 : 4));
+	const int64_t resident_teams = team_warps == 6 ? teams6 : teams4;
+	const int rows_launch = teams ? 16 : rows_per_lane;
+	const int lines = teams ? team_warps + 1 : 2;
+	int64_t nwarps = teams ? std::min<int64_t>(m, resident_teams) : std::min<int64_t>(m, (int64_t)ctx->num_sms * 32);
 	// keep the scratch under ~4 GB
-	while (nwarps > ctx->num_sms && nwarps * 2 * stride * 24 > (4LL << 30)) nwarps /= 2;
+	while (nwarps > ctx->num_sms && nwarps * lines * stride * 24 > (4LL << 30)) nwarps /= 2;
 	lap("offsets D2H");
-	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)nwarps * 2 * stride * 16, (size_t)nwarps * 2 * stride * 8}));
+	rc = mc_ensure_scratch(ctx, Carve::need({(size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)m * 4, (size_t)nwarps * lines * stride * 16, (size_t)nwarps * lines * stride * 8}));
 	if (rc) return rc;
 	lap("scratch");
 	Carve cv(ctx->d_scratch);
 	int32_t *d_a = cv.take<int32_t>(m), *d_b = cv.take<int32_t>(m), *d_s = cv.take<int32_t>(m), *d_l = cv.take<int32_t>(m), *d_i = cv.take<int32_t>(m);
-	void *d_sa = cv.take<uint8_t>((size_t)nwarps * 2 * stride * 16);
-	void *d_sb = cv.take<uint8_t>((size_t)nwarps * 2 * stride * 8);
+	void *d_sa = cv.take<uint8_t>((size_t)nwarps * lines * stride * 16);
+	void *d_sb = cv.take<uint8_t>((size_t)nwarps * lines * stride * 8);
 	MC_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(unsigned int), ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(d_a, a, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
 	MC_CUDA(cudaMemcpyAsync(d_b, b, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
-	rc = mc_launch_nw(ctx, d_a, d_b, m, max_la, d_s, d_l, d_i, d_sa, d_sb, stride, nwarps, rows_per_lane);
+	rc = mc_launch_nw(ctx, d_a, d_b, m, max_la, d_s, d_l, d_i, d_sa, d_sb, stride, nwarps, rows_launch, team_warps);
 	if (rc) return rc;
 	unsigned int flags[4];
 	MC_CUDA(cudaMemcpyAsync(score, d_s, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));

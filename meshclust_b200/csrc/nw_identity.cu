@@ -54,19 +54,37 @@ __device__ __forceinline__ NwCell nw_shfl_from(const NwCell &c, int src) {
 	return r;
 }
 
-template <int R>
-__global__ void __launch_bounds__(128, R >= 16 ? 3 : 1)
+// W = warps that share a pair (a "team" = one CTA of 128 threads when W = 4).  One warp per pair (W = 1) fills the GPU
+// only with thousands of pairs; the alignment-driven binary search of Trainer::split offers a few hundred long pairs
+// per round, and a round then lasts as long as ONE warp needs for ONE pair (0.125 s for 10 kb x 10 kb).  With a team
+// the strips of a pair form a pipeline: strip s is taken by warp (running strip number) mod W and may read column
+// chunk c of the boundary row as soon as strip s - 1 has stored it -- the boundary lines already live in global
+// memory, one line per strip in flight (W + 1 lines per team, line = running strip number mod (W + 1): the line a
+// strip writes was last read W strips ago, by the same warp), and what was missing is only flow control: a word per
+// line in shared memory, {running strip number, columns stored}, published by the writer every 32 columns behind a
+// fence and polled by the reader before it fetches a chunk.  Running strip numbers continue across the pairs of a
+// team, so warps drift into the next pair without a barrier.  The arithmetic is untouched.
+template <int R, int W>
+__global__ void __launch_bounds__(W == 1 ? 128 : 32 * W, W == 6 ? 2 : (R >= 16 ? 3 : 1))
 nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
           const int32_t *__restrict__ pa, const int32_t *__restrict__ pb, long long npairs,
           int4 *__restrict__ scratch_a, int2 *__restrict__ scratch_b, long long scratch_stride,
           int32_t *__restrict__ score_out, int32_t *__restrict__ len_out, int32_t *__restrict__ id_out,
           unsigned int *__restrict__ flags) {
+	constexpr int LINES = W == 1 ? 2 : W + 1;
+	__shared__ unsigned long long s_prog[W == 1 ? 1 : LINES];   // per boundary line: (running strip number + 1) << 24 | columns stored
 	const int lane = threadIdx.x & 31;
-	const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-	// two scratch lines per warp (strip parity) so a strip never overwrites what it still reads
-	int4 *sa0 = scratch_a + warp * 2 * scratch_stride;   // per column: m, u, l, pm
-	int2 *sb0 = scratch_b + warp * 2 * scratch_stride;   //             pu, pl
+	const int wteam = W == 1 ? 0 : (int)(threadIdx.x >> 5);      // this warp's place in its team
+	const long long warp = W == 1 ? (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) : (long long)blockIdx.x;   // pair owner: warp or team
+	const long long nwarps = W == 1 ? (((long long)gridDim.x * blockDim.x) >> 5) : (long long)gridDim.x;
+	// boundary lines of this warp / team (W = 1: two, by strip parity, so a strip never overwrites what it still reads)
+	int4 *sa0 = scratch_a + warp * LINES * scratch_stride;   // per column: m, u, l, pm
+	int2 *sb0 = scratch_b + warp * LINES * scratch_stride;   //             pu, pl
+	unsigned long long gbase = 0;   // strips of the pairs this team has been through (identical in all its warps)
+	if (W > 1) {
+		if (threadIdx.x < LINES) s_prog[threadIdx.x] = 0;
+		__syncthreads();
+	}
 
 	for (long long pr = warp; pr < npairs; pr += nwarps) {
 		const long long ia = pa[pr], ib = pb[pr];
@@ -78,12 +96,12 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 		const int ninf = (diff >= 1 ? -NW_OPEN - diff * NW_EXT : 0) - shorter - 1;
 
 		if (shorter > 65535) {   // the packed counters would overflow; reported to the host
-			if (lane == 0) { atomicOr(&flags[2], 1u); score_out[pr] = 0; len_out[pr] = 0; id_out[pr] = 0; }
+			if (lane == 0 && wteam == 0) { atomicOr(&flags[2], 1u); score_out[pr] = 0; len_out[pr] = 0; id_out[pr] = 0; }
 			continue;
 		}
 		if (la == 0 || lb == 0) {
 			// no DP cell: the answer is the boundary itself (see the init row / column-0 reset)
-			if (lane == 0) {
+			if (lane == 0 && wteam == 0) {
 				int sc, ln;
 				if (la == 0 && lb == 0) { sc = 0; ln = 0; }
 				else if (lb == 0) { sc = -NW_OPEN - la * NW_EXT; ln = la; }   // L[la] of the init row
@@ -96,12 +114,27 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 		int res_sc = 0; uint32_t res_p = 0;
 		const int rows_per_strip = 32 * R;
 		const int nstrips = (lb + rows_per_strip - 1) / rows_per_strip;
+		bool mine_last = W == 1;   // this warp took the pair's last strip (it holds the result)
 		for (int strip = 0; strip < nstrips; strip++) {
+			const unsigned long long g = gbase + (unsigned long long)strip;   // running strip number of the team
+			if (W > 1 && (int)(g % W) != wteam) continue;
+			if (W > 1) mine_last = strip == nstrips - 1;
 			const int j0 = strip * rows_per_strip + lane * R + 1;   // first row of this lane (1-based)
-			const int4 *sa_in = sa0 + (strip & 1) * scratch_stride;
-			const int2 *sb_in = sb0 + (strip & 1) * scratch_stride;
-			int4 *sa_out = sa0 + ((strip + 1) & 1) * scratch_stride;
-			int2 *sb_out = sb0 + ((strip + 1) & 1) * scratch_stride;
+			const int line_in = W == 1 ? (strip & 1) : (int)(g % LINES), line_out = W == 1 ? ((strip + 1) & 1) : (int)((g + 1) % LINES);
+			const int4 *sa_in = sa0 + line_in * scratch_stride;
+			const int2 *sb_in = sb0 + line_in * scratch_stride;
+			int4 *sa_out = sa0 + line_out * scratch_stride;
+			int2 *sb_out = sb0 + line_out * scratch_stride;
+			// flow control of the team: columns 1..need of line_in have been stored by the strip before this one
+			auto wait_cols = [&](int need) {
+				if (W == 1) return;
+				volatile unsigned long long *p = &s_prog[line_in];
+				for (;;) {
+					const unsigned long long v = *p;
+					if ((v >> 24) == g && (long long)(v & 0xffffffull) >= (long long)need) break;   // (tag g = strip g - 1, stored as number + 1)
+				}
+				__threadfence();
+			};
 
 			int bj[R];
 			// per row: the cell just to the left (row j, column i-1).  The diagonal of row r+1 is that
@@ -132,6 +165,7 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 			bnext = bchunk;
 			if (strip > 0) {
 				// prefetch columns 1..32 (chunk 0); chunk c holds columns 32c+1 .. 32c+32
+				wait_cols(la < 32 ? la : 32);
 				const int col = 1 + lane;
 				if (col <= la) {
 					const int4 x = __ldcg(&sa_in[col]);
@@ -147,6 +181,7 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 					achunk = (t + lane < la) ? A[t + lane] : 0xff;
 					if (strip > 0) {
 						bchunk = bnext;
+						if (t + 33 <= la) wait_cols(la < t + 64 ? la : t + 64);
 						const int col = t + 32 + 1 + lane;   // next chunk, one chunk ahead
 						if (col <= la) {
 							const int4 x = __ldcg(&sa_in[col]);
@@ -213,16 +248,21 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 					if (lane == 31 && strip + 1 < nstrips) {
 						__stcg(&sa_out[i], make_int4(mine.m, mine.u, mine.l, (int)mine.pm));
 						__stcg(&sb_out[i], make_int2((int)mine.pu, (int)mine.pl));
+						if (W > 1 && ((i & 31) == 0 || i == la)) {
+							__threadfence();
+							*(volatile unsigned long long *)&s_prog[line_out] = ((g + 1) << 24) | (unsigned long long)i;
+						}
 					}
 				}
 			}
 			__syncwarp();
 		}
-		// the lane that owned row lb holds the result
+		gbase += (unsigned long long)nstrips;
+		// the lane that owned row lb holds the result (in the warp that took the last strip)
 		const int owner = ((lb - 1) % (32 * R)) / R;
 		res_sc = __shfl_sync(MC_FULL_MASK, res_sc, owner);
 		res_p = __shfl_sync(MC_FULL_MASK, res_p, owner);
-		if (lane == 0) {
+		if (lane == 0 && mine_last) {
 			score_out[pr] = res_sc;
 			len_out[pr] = la + lb - (int32_t)(res_p >> 16);
 			id_out[pr] = (int32_t)(res_p & 0xffffu);
@@ -230,19 +270,27 @@ nw_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ seq_off,
 	}
 }
 
-// scratch: two lines of scratch_stride >= max_len + 1 columns per resident warp.
-// rows_per_lane: 4, 8 or 16 (strips of 128 / 256 / 512 rows of seq2)
+// scratch: boundary lines of scratch_stride >= max_len + 1 columns: two per resident warp (team_warps = 1) or
+// team_warps + 1 per resident team.  nwarps = resident warps / teams.
+// rows_per_lane: 4, 8 or 16 (strips of 128 / 256 / 512 rows of seq2); team_warps: 1, or 4 / 6 (16 rows per lane only:
+// three CTAs of 128 threads or two of 192 per SM)
 int mc_launch_nw(mc_ctx *ctx, const int32_t *pa_dev, const int32_t *pb_dev, int64_t m, int64_t max_len,
                  int32_t *score_dev, int32_t *len_dev, int32_t *id_dev, void *scratch_a, void *scratch_b,
-                 int64_t scratch_stride, int64_t nwarps, int rows_per_lane) {
-	const int threads = 128;
-	const int64_t blocks = (nwarps * 32 + threads - 1) / threads;
+                 int64_t scratch_stride, int64_t nwarps, int rows_per_lane, int team_warps) {
+	const int threads = team_warps > 1 ? 32 * team_warps : 128;
+	const int64_t blocks = team_warps > 1 ? nwarps : (nwarps * 32 + threads - 1) / threads;
 	(void)max_len;
-#define NW_LAUNCH(RR) nw_kernel<RR><<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, pa_dev, pb_dev, m, (int4 *)scratch_a, (int2 *)scratch_b, scratch_stride, score_dev, len_dev, id_dev, ctx->d_flags)
-	switch (rows_per_lane) {
-	case 16: NW_LAUNCH(16); break;
-	case 8: NW_LAUNCH(8); break;
-	default: NW_LAUNCH(4); break;
+#define NW_LAUNCH(RR, WW) nw_kernel<RR, WW><<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_seq, ctx->d_seq_off, pa_dev, pb_dev, m, (int4 *)scratch_a, (int2 *)scratch_b, scratch_stride, score_dev, len_dev, id_dev, ctx->d_flags)
+	if (team_warps > 1) {
+		MC_REQUIRE((team_warps == 4 || team_warps == 6) && rows_per_lane == 16, MC_ERR_ARG, "mc_launch_nw: teams are four or six warps of 16 rows per lane");
+		if (team_warps == 6) NW_LAUNCH(16, 6);
+		else NW_LAUNCH(16, 4);
+	} else {
+		switch (rows_per_lane) {
+		case 16: NW_LAUNCH(16, 1); break;
+		case 8: NW_LAUNCH(8, 1); break;
+		default: NW_LAUNCH(4, 1); break;
+		}
 	}
 #undef NW_LAUNCH
 	ctx->launches++;

@@ -318,9 +318,12 @@ std::vector<Pair> trainer_split(Ctx &c) {
 		for (size_t i = 0; i < np; i++) mean_len += (double)(ds.fa.offsets[(size_t)pivots[i] + 1] - ds.fa.offsets[(size_t)pivots[i]]);
 		mean_len /= (double)std::max<size_t>(np, 1);
 		if (mean_len * mean_len > 1e7) {
-			// every GPU of the run takes its share of a round: with more of them, look further ahead (fewer rounds)
-			SPEC = c.ranks.size() > 1 ? 6 : 4;
-			while (SPEC > 1 && np * ((size_t)(1 << SPEC) - 1) > 1800 * c.ranks.size()) SPEC--;
+			// long pairs: a batch that leaves every GPU at most two teams per SM (296 pairs on a B200) is aligned by
+			// teams of six warps per pair, and a round then lasts a sixth of one pair's single-warp latency -- fewer,
+			// speculative positions per round buy nothing beyond that.  One GPU: no look-ahead (150 pairs per round);
+			// every GPU of the run takes its share of a round, so with more of them look further ahead (fewer rounds).
+			SPEC = 6;
+			while (SPEC > 1 && np * ((size_t)(1 << SPEC) - 1) > 296 * c.ranks.size()) SPEC--;
 		}
 		if (getenv("MC_SPLIT_SPEC")) SPEC = std::max(1, std::min(6, atoi(getenv("MC_SPLIT_SPEC"))));
 	}

@@ -940,10 +940,20 @@ def test_alignment_long_pairs_golden(ctx):
     n = offs.size - 1
     assert (np.diff(offs) >= 8900).all() and g["pa"].size >= 20
     ctx.load_sequences(digits, offs, np.zeros(0, np.int32), np.zeros(n + 1, np.int64))
-    sc, ln, mt = ctx.align_pairs(g["pa"], g["pb"])
-    assert np.array_equal(sc, g["score"])
-    assert np.array_equal(ln, g["alen"])
-    assert np.array_equal(mt, g["matches"])
+    # a batch this small and long runs as teams of six warps per pair by default (strips of one pair pipelined over the
+    # warps of a CTA, flow control through shared memory); teams of four and one warp per pair must give the same triples
+    for teams in (None, "0", "4", "6"):
+        if teams is None:
+            os.environ.pop("MC_NW_TEAMS", None)
+        else:
+            os.environ["MC_NW_TEAMS"] = teams
+        try:
+            sc, ln, mt = ctx.align_pairs(g["pa"], g["pb"])
+        finally:
+            os.environ.pop("MC_NW_TEAMS", None)
+        assert np.array_equal(sc, g["score"]), teams
+        assert np.array_equal(ln, g["alen"]), teams
+        assert np.array_equal(mt, g["matches"]), teams
     # the same pairs one at a time and in reverse batch order: batching must not matter
     order = np.arange(g["pa"].size)[::-1]
     sc2, ln2, mt2 = ctx.align_pairs(g["pa"][order], g["pb"][order])
@@ -1022,3 +1032,35 @@ def test_full_size_properties_c2(ctx, oracle):
         assert res.best_f0 >= f0[0]
     keys = ctx.distance_keys(np.array([3, 77]))
     assert keys[0, 3] == 0 and keys[1, 77] == 0 and keys[0, 77] == keys[1, 3]
+
+
+def test_alignment_teams_ragged(ctx, oracle):
+    # teams of warps per pair (strips of 512 rows pipelined over the warps of a CTA) on lengths around the strip and
+    # chunk boundaries: one strip (no pipeline), exactly full strips, fewer strips than warps, many strips, columns that
+    # end inside / at a 32-column chunk, an empty partner; more pairs than resident teams (teams move on to the next
+    # pair without a barrier)
+    import os
+    rng = np.random.default_rng(29)
+    lens = [0, 1, 31, 33, 511, 512, 513, 1024, 1500, 2047, 2049, 3100, 6200]
+    seqs = []
+    for L in lens:
+        s = rng.integers(0, 4, L, dtype=np.uint8)
+        if L > 600:
+            s[L // 3] = ord("N")
+        seqs.append(s)
+    offs = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum([s.size for s in seqs], out=offs[1:])
+    digits = np.concatenate(seqs)
+    n = len(seqs)
+    ctx.load_sequences(digits, offs, np.zeros(0, np.int32), np.zeros(n + 1, np.int64))
+    pa, pb = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    pa, pb = np.tile(pa.reshape(-1), 4).astype(np.int32), np.tile(pb.reshape(-1), 4).astype(np.int32)   # 676 pairs > 444 teams
+    want = oracle.globalign_batch(digits, offs, pa, pb)
+    for teams in ("6", "4", "0"):
+        os.environ["MC_NW_TEAMS"] = teams
+        try:
+            got = ctx.align_pairs(pa, pb)
+        finally:
+            os.environ.pop("MC_NW_TEAMS", None)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w), teams
