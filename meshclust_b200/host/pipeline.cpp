@@ -122,7 +122,16 @@ void ensure_rank_sequences(Ctx &c) {
 	join_ranks(c);
 	std::vector<std::thread> th;
 	std::vector<int> rcs(c.ranks.size(), MC_OK);
-	for (size_t r = 1; r < c.ranks.size(); r++) th.emplace_back([&, r]() { rcs[r] = mc_clone_sequences(c.ranks[r], c.gpu); });
+	// (with the sequences, a scratch buffer that holds the boundary lines of a full batch of alignments: growing it in
+	// the middle of the first large batch is a cudaFree + cudaMalloc of hundreds of MB on every GPU at once -- 0.2 s)
+	uint64_t lmax = 0;
+	for (uint64_t l : c.ds.len) lmax = std::max(lmax, l);
+	const int64_t nw_scratch = (int64_t)std::min(4.3e9, 4736.0 * 2.0 * ((double)lmax + 34.0) * 24.0 + 64e6);
+	for (size_t r = 1; r < c.ranks.size(); r++)
+		th.emplace_back([&, r]() {
+			rcs[r] = mc_clone_sequences(c.ranks[r], c.gpu);
+			if (rcs[r] == MC_OK) mc_reserve_scratch(c.ranks[r], nw_scratch);
+		});
 	for (auto &x : th) x.join();
 	for (size_t r = 1; r < c.ranks.size(); r++)
 		if (rcs[r] != MC_OK) die_gpu("mc_clone_sequences");
@@ -1107,7 +1116,10 @@ int run_pipeline(Options opt) {
 				est_len = recs ? (double)got / (double)recs : (double)got;
 			}
 		}
-		const double min_len = getenv("MC_ALIGN_SHARD_MIN_LEN") ? atof(getenv("MC_ALIGN_SHARD_MIN_LEN")) : 3000.0;
+		// (the training stage aligns ~6000 pairs whatever n is: 0.9 s on one B200 at 10 kb per record, growing with the
+		// square of the length.  A second CUDA context costs 0.3 - 3 s to create and slows the first GPU's allocations
+		// while it comes up: measured on C5 (10 kb), two GPUs saved 0.36 s of alignments and lost 0.5 s elsewhere.)
+		const double min_len = getenv("MC_ALIGN_SHARD_MIN_LEN") ? atof(getenv("MC_ALIGN_SHARD_MIN_LEN")) : 20000.0;
 		const bool share_alignments = est_len >= min_len || opt.align;
 		if (!c.shard_phase_a && !share_alignments) {
 			printf("  [--gpus %d: %.2f GB of input, records of ~%.0f letters: one GPU (persistent Phase-A kernel, alignment batches too small to split)]\n",
