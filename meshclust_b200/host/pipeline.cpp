@@ -1427,6 +1427,7 @@ int run_pipeline(Options opt) {
 		}
 	}
 	mean_shift(c, bv);
+	if (c.ranks.size() > 1) printf("  [alignment batches split over the %zu GPUs: %ld]\n", c.ranks.size(), c.align_split_calls);
 	printf("Total %.2fs\n", total.lap());
 	if (getenv("MC_CLEAN_EXIT")) { join_ranks(c); for (mc_ctx *g : c.ranks) mc_ctx_destroy(g); return 0; }
 	// the output file is closed: skip the teardown of the CUDA context and of GBs of host vectors
