@@ -88,6 +88,15 @@ def test_clstr_identical_with_host_parser_cpu(mock_cli, tmp_path, name):
     assert got2 == got
 
 
+@pytest.mark.parametrize("name,gpus", [("A", 2), ("N", 3)])
+def test_clstr_identical_with_split_alignments_cpu(mock_cli, tmp_path, name, gpus):
+    # the host side of `--gpus N` (batches of alignments cut by cells into one run per context, each driven by its own
+    # host thread, sequences cloned once) against the CPU mock of the C-ABI: the CLSTR file must not change
+    got, log = _run(mock_cli, name, tmp_path, extra=("--gpus", str(gpus)), env={"MC_ALIGN_SPLIT_MIN_CELLS": "1", "MC_ALIGN_SHARD_MIN_LEN": "1"})
+    assert "sequences copied to %d more GPUs" % (gpus - 1) in log and "alignment batches split over the %d GPUs" % gpus in log
+    assert got == H.read_golden(name), log[-1500:]
+
+
 def test_ingest_path_edge_records_cpu(mock_cli, tmp_path):
     # records the two input paths (index + mc_ingest_fasta / host parser + mc_load_sequences) must treat alike: all N and
     # one-letter records abort like the reference's segment->at(0) (Chromosome.cpp:193), records under 20 letters have
