@@ -121,7 +121,12 @@ class ClockSampler:
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
             self.nvml = (pynvml, h)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             self.samples, self.stop_flag = [], False
+            # the timed loop is a tight sequence of short ctypes calls: with the default 5 ms switch interval the
+            # sampler thread gets the interpreter a few times per 100 ms only
+            self.switch_interval = sys.getswitchinterval()
+            sys.setswitchinterval(0.0005)
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
             return
@@ -149,7 +154,7 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                mx = self.max_mhz
                 try:
                     rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
@@ -168,6 +173,7 @@ class ClockSampler:
             pynvml, _ = self.nvml
             self.stop_flag = True
             self.t.join(timeout=1)
+            sys.setswitchinterval(self.switch_interval)
             bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
             reasons = sorted(k for k, b in bits.items() if any(rs & b for _, _, rs in self.samples))
             sm = [x[0] for x in self.samples]
