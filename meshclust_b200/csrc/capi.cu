@@ -52,6 +52,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int mc_ensure_scratch(mc_ctx *ctx, size_t bytes) {
 	if (bytes <= ctx->scratch_bytes) return MC_OK;
+	ctx->staged_raw = nullptr;   // (bytes parked by mc_stage_fasta_bytes do not survive a new buffer)
 	if (ctx->d_scratch) { MC_CUDA(cudaStreamSynchronize(ctx->stream)); MC_CUDA(cudaFree(ctx->d_scratch)); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0; }
 	bytes = align_up(bytes + bytes / 4, 1 << 20);
 	MC_CUDA(cudaMalloc(&ctx->d_scratch, bytes));
@@ -65,6 +66,7 @@ extern "C" int mc_reserve_scratch(mc_ctx *ctx, int64_t bytes) {
 	MC_REQUIRE(ctx && bytes >= 0, MC_ERR_ARG, "mc_reserve_scratch: bad arguments");
 	MC_CUDA(cudaSetDevice(ctx->device));
 	if ((size_t)bytes <= ctx->scratch_bytes) return MC_OK;
+	ctx->staged_raw = nullptr;
 	if (ctx->d_scratch) { MC_CUDA(cudaStreamSynchronize(ctx->stream)); MC_CUDA(cudaFree(ctx->d_scratch)); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0; }
 	const size_t want = align_up((size_t)bytes, 1 << 20);
 	if (cudaMalloc(&ctx->d_scratch, want) != cudaSuccess) { cudaGetLastError(); ctx->d_scratch = nullptr; return MC_OK; }   // a hint: later calls allocate what they need
