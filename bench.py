@@ -125,8 +125,11 @@ class ClockSampler:
             self.samples, self.stop_flag = [], False
             # the timed loop is a tight sequence of short ctypes calls: with the default 5 ms switch interval the
             # sampler thread gets the interpreter a few times per 100 ms only
+            # (one process per GPU under torchrun: the loop there spends longer inside each call and the sampler was
+            # never starved -- 19-21 samples -- so the interval is left alone)
             self.switch_interval = sys.getswitchinterval()
-            sys.setswitchinterval(0.0005)
+            if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+                sys.setswitchinterval(0.0005)
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
             return
