@@ -97,6 +97,18 @@ def test_clstr_identical_with_split_alignments_cpu(mock_cli, tmp_path, name, gpu
     assert got == H.read_golden(name), log[-1500:]
 
 
+def test_gpus_flag_keeps_small_inputs_on_one_gpu_cpu(mock_cli, tmp_path):
+    # --gpus N without anything to share (megabytes of input, records of a few hundred letters): the run says so, uses
+    # one context and writes the same file
+    got, log = _run(mock_cli, "A", tmp_path, extra=("--gpus", "4"))
+    assert "--gpus 4:" in log and "one GPU" in log and "sequences copied" not in log and "peer inboxes connected" not in log
+    assert got == H.read_golden("A")
+    # --align shares the alignments whatever the record length
+    got, log = _run(mock_cli, "G", tmp_path, extra=("--gpus", "2"))
+    assert "alignments are split over the GPUs" in log
+    assert got == H.read_golden("G")
+
+
 def test_ingest_path_edge_records_cpu(mock_cli, tmp_path):
     # records the two input paths (index + mc_ingest_fasta / host parser + mc_load_sequences) must treat alike: all N and
     # one-letter records abort like the reference's segment->at(0) (Chromosome.cpp:193), records under 20 letters have
